@@ -1,0 +1,12 @@
+"""gzp_b200 — B200-native drop-in for gzp's per-block encode path.
+
+The product is ``libgzpb.so`` (hand-written sm_100a CUDA behind the C ABI of
+``include/gzpb.h``).  This package is the host-side mirror of the reference's
+public surface (``ZBuilder`` / ``ParCompressBuilder`` / ``ParCompress`` / the
+format types / ``ZWriter::finish``; /root/reference/src/lib.rs:181-265,
+src/par/compress.rs:33-233) so that tests read like the reference's own.
+"""
+from ._lib import BGZF, GZIP, MGZIP, RAWDEFLATE, SNAP, ZLIB, load  # noqa: F401
+from .api import (BUFSIZE, DICT_SIZE, Bgzf, Compression, Context, Gzip, GzpError, Mgzip,  # noqa: F401
+                  ParCompress, ParCompressBuilder, RawDeflate, Snap, ZBuilder, Zlib, crc32_combine,
+                  encode_capacity, footer, header)

@@ -1,0 +1,65 @@
+"""ctypes binding of libgzpb.so (include/gzpb.h).  Fails loudly when the CUDA
+library is missing — there is no CPU fallback in the product path."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libgzpb.so")
+
+GZIP, ZLIB, RAWDEFLATE, MGZIP, BGZF, SNAP = 0, 1, 2, 3, 4, 5
+
+
+class BlockIn(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("len", C.c_size_t), ("dict", C.c_void_p), ("dict_len", C.c_size_t),
+                ("is_last", C.c_int)]
+
+
+class BlockOut(C.Structure):
+    _fields_ = [("dst", C.c_void_p), ("cap", C.c_size_t), ("out_len", C.c_size_t), ("check_sum", C.c_uint32),
+                ("check_amount", C.c_uint32), ("status", C.c_int)]
+
+
+_SIGS = {
+    "gzpb_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t]),
+    "gzpb_destroy": (None, [C.c_void_p]),
+    "gzpb_encode_batch": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(BlockIn), C.POINTER(BlockOut)]),
+    "gzpb_encode_stream": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t,
+                                     C.POINTER(C.c_size_t)]),
+    "gzpb_encode_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gzpb_encode_capacity": (C.c_size_t, [C.c_int, C.c_size_t]),
+    "gzpb_header": (C.c_size_t, [C.c_int, C.c_int, C.c_void_p]),
+    "gzpb_footer": (C.c_size_t, [C.c_int, C.c_uint32, C.c_uint32, C.c_void_p]),
+    "gzpb_crc32_combine": (C.c_uint32, [C.c_uint32, C.c_uint32, C.c_uint64]),
+    "gzpb_adler32_combine": (C.c_uint32, [C.c_uint32, C.c_uint32, C.c_uint64]),
+    "gzpb_default_bufsize": (C.c_size_t, [C.c_int]),
+    "gzpb_needs_dict": (C.c_int, [C.c_int]),
+    "gzpb_level_supported": (C.c_int, [C.c_int, C.c_int]),
+    "gzpb_host_alloc": (C.c_void_p, [C.c_size_t]),
+    "gzpb_host_free": (None, [C.c_void_p]),
+    "gzpb_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
+    "gzpb_kernel_ms": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
+    "gzpb_launch_count": (C.c_uint64, [C.c_void_p]),
+    "gzpb_strerror": (C.c_char_p, [C.c_int]),
+    "gzpb_version": (C.c_char_p, []),
+}
+
+EXPORTS = tuple(_SIGS)
+_lib = None
+
+
+def load():
+    """Load libgzpb.so; raises ImportError (never falls back) when it is absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise ImportError(
+                f"{SO_PATH} is missing: build it with `python -m gzp_b200.build` (nvcc, sm_100a). "
+                "gzp_b200 has no CPU fallback.")
+        lib = C.CDLL(SO_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib

@@ -1,0 +1,409 @@
+"""Host-side mirror of gzp's writer API on top of the C ABI (include/gzpb.h).
+
+Names, argument meaning and error behaviour follow the reference:
+  ParCompressBuilder / ParCompress  /root/reference/src/par/compress.rs:33-233, 248-468
+  ZBuilder                          /root/reference/src/lib.rs:181-265
+  format types                      /root/reference/src/deflate.rs:61,169,279,357,506; src/snap.rs:35
+  GzpError                          /root/reference/src/lib.rs:114-163
+The chunker keeps the reference's exact semantics (strict '>' hold-back, flush()
+emitting whatever is buffered — even an empty block —, finish() always sending a
+final is_last block, the 32 KiB dictionary rule); the worker pool is replaced by
+device batches handed to gzpb_encode_batch.
+"""
+import ctypes as C
+
+from . import _lib
+from ._lib import BGZF, GZIP, MGZIP, RAWDEFLATE, SNAP, ZLIB, BlockIn, BlockOut
+
+BUFSIZE = 131072      # lib.rs:105
+DICT_SIZE = 32768     # lib.rs:108
+
+_ERRNAMES = {-1: "BufferSize", -2: "NumThreads", -3: "BlockSizeExceeded", -4: "LibDeflaterCompress",
+             -5: "LibDeflaterCompressionLvl", -6: "Io", -7: "ChannelSend", -8: "Cuda", -9: "Unknown", -10: "NoMem"}
+
+
+class GzpError(Exception):
+    """GzpError (lib.rs:114-163); `.variant` names the enum variant, `.code` the C status."""
+
+    def __init__(self, code, detail=None):
+        self.code = int(code)
+        self.variant = _ERRNAMES.get(self.code, "Unknown")
+        msg = detail or _lib.load().gzpb_strerror(self.code).decode()
+        super().__init__(f"{self.variant}: {msg}")
+
+
+class Compression:
+    """flate2::Compression re-export (lib.rs:81)."""
+
+    def __init__(self, level):
+        self._level = int(level)
+
+    def level(self):
+        return self._level
+
+    @classmethod
+    def new(cls, level):
+        return cls(level)
+
+    @classmethod
+    def none(cls):
+        return cls(0)
+
+    @classmethod
+    def fast(cls):
+        return cls(1)
+
+    @classmethod
+    def best(cls):
+        return cls(9)
+
+    @classmethod
+    def default(cls):
+        return cls(6)
+
+
+def _lvl(x):
+    return x.level() if isinstance(x, Compression) else int(x)
+
+
+class _Format:
+    ID = None
+    NAME = ""
+
+    @classmethod
+    def new(cls):
+        return cls()
+
+    @property
+    def DEFAULT_BUFSIZE(self):
+        return _lib.load().gzpb_default_bufsize(self.ID)
+
+    def needs_dict(self):
+        return bool(_lib.load().gzpb_needs_dict(self.ID))
+
+    def header(self, level):
+        return header(self.ID, _lvl(level))
+
+    def footer(self, check_sum, check_amount):
+        return footer(self.ID, check_sum, check_amount)
+
+
+class Gzip(_Format):
+    ID, NAME = GZIP, "Gzip"
+
+
+class Zlib(_Format):
+    ID, NAME = ZLIB, "Zlib"
+
+
+class RawDeflate(_Format):
+    ID, NAME = RAWDEFLATE, "RawDeflate"
+
+
+class Mgzip(_Format):
+    ID, NAME = MGZIP, "Mgzip"
+
+
+class Bgzf(_Format):
+    ID, NAME = BGZF, "Bgzf"
+
+
+class Snap(_Format):
+    ID, NAME = SNAP, "Snap"
+
+
+def header(fmt, level):
+    b = C.create_string_buffer(16)
+    n = _lib.load().gzpb_header(fmt, level, b)
+    return b.raw[:n]
+
+
+def footer(fmt, check_sum, check_amount):
+    b = C.create_string_buffer(16)
+    n = _lib.load().gzpb_footer(fmt, check_sum & 0xFFFFFFFF, check_amount & 0xFFFFFFFF, b)
+    return b.raw[:n]
+
+
+def crc32_combine(a, b, len_b):
+    return _lib.load().gzpb_crc32_combine(a, b, len_b)
+
+
+def encode_capacity(fmt, n):
+    return _lib.load().gzpb_encode_capacity(fmt, n)
+
+
+class Context:
+    """One device context = the per-worker `Compressor` of the reference
+    (FormatSpec::create_compressor, lib.rs:343-346), but for a whole GPU."""
+
+    def __init__(self, fmt, level, device=0, max_block_bytes=0, max_blocks_in_flight=256):
+        self._lib = _lib.load()
+        self.fmt = fmt.ID if isinstance(fmt, _Format) or (isinstance(fmt, type) and issubclass(fmt, _Format)) else int(fmt)
+        self.level = _lvl(level)
+        h = C.c_void_p()
+        rc = self._lib.gzpb_create(C.byref(h), device, self.fmt, self.level, max_block_bytes, max_blocks_in_flight)
+        if rc != 0:
+            raise GzpError(rc)
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.gzpb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def encode_blocks(self, blocks):
+        """FormatSpec::encode + Check::update for a list of (bytes, dict|None, is_last).
+        Returns a list of (encoded bytes, check_sum, check_amount); raises GzpError."""
+        n = len(blocks)
+        if n == 0:
+            return []
+        ins = (BlockIn * n)()
+        outs = (BlockOut * n)()
+        keep = []
+        for i, (data, d, last) in enumerate(blocks):
+            data = bytes(data)
+            src = C.create_string_buffer(data, len(data)) if data else C.create_string_buffer(1)
+            cap = self._lib.gzpb_encode_capacity(self.fmt, len(data)) + 64
+            dst = C.create_string_buffer(cap)
+            keep.append((src, dst))
+            ins[i].ptr = C.cast(src, C.c_void_p)
+            ins[i].len = len(data)
+            if d:
+                db = C.create_string_buffer(bytes(d), len(d))
+                keep.append(db)
+                ins[i].dict = C.cast(db, C.c_void_p)
+                ins[i].dict_len = len(d)
+            ins[i].is_last = int(bool(last))
+            outs[i].dst = C.cast(dst, C.c_void_p)
+            outs[i].cap = cap
+        rc = self._lib.gzpb_encode_batch(self._h, n, ins, outs)
+        if rc != 0:
+            raise GzpError(rc)
+        res = []
+        k = 0
+        for i in range(n):
+            if outs[i].status != 0:
+                raise GzpError(outs[i].status)
+            dst = keep[k][1]
+            k += 2 if blocks[i][1] else 1
+            res.append((dst.raw[:outs[i].out_len], outs[i].check_sum, outs[i].check_amount))
+        return res
+
+    def encode_stream(self, data, buffer_size=0):
+        """ParCompress over an in-memory input: header + write(data) + finish()."""
+        data = bytes(data)
+        n = len(data)
+        bs = buffer_size or self._lib.gzpb_default_bufsize(self.fmt)
+        nblocks = max(1, (n + bs - 1) // bs)
+        cap = 64 + sum(self._lib.gzpb_encode_capacity(self.fmt, min(bs, n - i * bs)) for i in range(nblocks)) if nblocks < 4096 \
+            else 64 + nblocks * self._lib.gzpb_encode_capacity(self.fmt, bs)
+        out = C.create_string_buffer(cap)
+        olen = C.c_size_t(0)
+        src = C.create_string_buffer(data, n) if n else C.create_string_buffer(1)
+        rc = self._lib.gzpb_encode_stream(self._h, src, n, buffer_size, out, cap, C.byref(olen))
+        if rc != 0:
+            raise GzpError(rc)
+        return out.raw[:olen.value]
+
+    def set_profiling(self, on):
+        self._lib.gzpb_set_profiling(self._h, int(on))
+
+    def kernel_ms(self, name):
+        ms = C.c_double(0)
+        cnt = C.c_uint64(0)
+        self._lib.gzpb_kernel_ms(self._h, name.encode(), C.byref(ms), C.byref(cnt))
+        return ms.value, cnt.value
+
+    def launch_count(self):
+        return self._lib.gzpb_launch_count(self._h)
+
+
+class ParCompressBuilder:
+    """ParCompressBuilder<F> (par/compress.rs:33-138).  `num_threads` is kept for
+    API parity (it sizes nothing on the GPU); `blocks_in_flight` is the device
+    analogue of the 2*num_threads channel bound."""
+
+    def __init__(self, fmt=Gzip):
+        self.format = fmt() if isinstance(fmt, type) else fmt
+        self._buffer_size = self.format.DEFAULT_BUFSIZE       # par/compress.rs:56
+        self._num_threads = 0
+        self._level = Compression.new(3)                      # par/compress.rs:58
+        self._pin = None
+        self._device = 0
+        self._blocks_in_flight = 256
+
+    @classmethod
+    def new(cls, fmt=Gzip):
+        return cls(fmt)
+
+    def buffer_size(self, n):
+        if n < DICT_SIZE:                                      # par/compress.rs:68-74
+            raise GzpError(-1, f"Invalid buffer size ({n}), must be >= {DICT_SIZE}")
+        self._buffer_size = int(n)
+        return self
+
+    def compression_level(self, level):
+        self._level = level if isinstance(level, Compression) else Compression.new(level)
+        return self
+
+    def num_threads(self, n):
+        if n == 0:                                             # par/compress.rs:84-90
+            raise GzpError(-2, "Invalid number of threads (0) selected.")
+        self._num_threads = int(n)
+        return self
+
+    def pin_threads(self, first_core):
+        self._pin = first_core
+        return self
+
+    def device(self, index):
+        self._device = int(index)
+        return self
+
+    def blocks_in_flight(self, n):
+        self._blocks_in_flight = int(n)
+        return self
+
+    def from_writer(self, writer):
+        return ParCompress(self.format, writer, self._level, self._buffer_size, self._device, self._blocks_in_flight)
+
+    from_borrowed_writer = from_writer
+
+
+class ParCompress:
+    """ParCompress<F, W> as a Python `write`/`flush`/`finish` object
+    (par/compress.rs:221-233, 332-362, 377-388, 413-468)."""
+
+    def __init__(self, fmt, writer, level, buffer_size, device=0, blocks_in_flight=256):
+        self.format = fmt
+        self.writer = writer
+        self.level = level
+        self.buffer_size = buffer_size
+        self._ctx = Context(fmt.ID, level, device, buffer_size, blocks_in_flight)
+        self._buf = bytearray()
+        self._dict = None
+        self._pending = []          # messages not yet handed to the device (FIFO = ticket order)
+        self._max_pending = blocks_in_flight
+        self._sum = 1 if fmt.ID == ZLIB else 0
+        self._amount = 0
+        self._finished = False
+        self._error = None
+        self._wrote_header = False
+
+    @classmethod
+    def builder(cls, fmt=Gzip):
+        return ParCompressBuilder(fmt)
+
+    # -- writer side (par/compress.rs:303-313) --
+    def _drain(self):
+        if not self._wrote_header:
+            self.writer.write(self.format.header(self.level))
+            self._wrote_header = True
+        if not self._pending:
+            return
+        msgs, self._pending = self._pending, []
+        try:
+            res = self._ctx.encode_blocks(msgs)
+        except GzpError as e:
+            self._error = e
+            raise
+        for (data, _d, _l), (enc, s, a) in zip(msgs, res):
+            if self.format.ID == GZIP:
+                self._sum = crc32_combine(self._sum, s, len(data))
+                self._amount = (self._amount + len(data)) & 0xFFFFFFFF
+            self.writer.write(enc)
+
+    def _send(self, block, dictionary, is_last):
+        self._pending.append((block, dictionary, is_last))
+        if len(self._pending) >= self._max_pending:
+            self._drain()
+
+    def write(self, data):
+        if self._finished:
+            raise GzpError(-7)
+        if self._error:
+            raise self._error
+        self._buf.extend(data)
+        while len(self._buf) > self.buffer_size:               # strict '>' (par/compress.rs:415)
+            b = bytes(self._buf[:self.buffer_size])
+            del self._buf[:self.buffer_size]
+            d, self._dict = self._dict, (b[-DICT_SIZE:] if self.format.needs_dict() else None)
+            self._send(b, d, False)
+        return len(data)
+
+    def _flush_last(self, is_last):
+        while True:
+            k = min(len(self._buf), self.buffer_size)
+            b = bytes(self._buf[:k])
+            del self._buf[:k]
+            last = is_last and len(self._buf) == 0
+            d, self._dict = self._dict, None
+            if len(b) >= DICT_SIZE and not last and self.format.needs_dict():
+                self._dict = b[-DICT_SIZE:]
+            self._send(b, d, last)
+            if len(self._buf) == 0:
+                break
+
+    def flush(self):
+        if self._finished:
+            raise GzpError(-7)
+        self._flush_last(False)
+        self._drain()
+
+    def finish(self):
+        if self._finished:
+            raise GzpError(-7)
+        self._flush_last(True)
+        self._drain()
+        self.writer.write(self.format.footer(self._sum, self._amount))
+        if hasattr(self.writer, "flush"):
+            self.writer.flush()
+        self._finished = True
+        self._ctx.close()
+        return self.writer
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):                                   # Drop -> finish (par/compress.rs:391-402)
+        if not self._finished and exc[0] is None:
+            self.finish()
+        return False
+
+
+class ZBuilder:
+    """ZBuilder<F, W> facade (lib.rs:181-265)."""
+
+    def __init__(self, fmt=Gzip):
+        self._b = ParCompressBuilder(fmt)
+
+    @classmethod
+    def new(cls, fmt=Gzip):
+        return cls(fmt)
+
+    def buffer_size(self, n):
+        self._b._buffer_size = int(n)       # ZBuilder defers validation to from_writer (lib.rs:210-213)
+        return self
+
+    def compression_level(self, level):
+        self._b.compression_level(level)
+        return self
+
+    def num_threads(self, n):
+        self._b._num_threads = int(n)
+        return self
+
+    def pin_threads(self, first_core):
+        self._b.pin_threads(first_core)
+        return self
+
+    def from_writer(self, writer):
+        if self._b._buffer_size < DICT_SIZE:
+            raise GzpError(-1, f"Invalid buffer size ({self._b._buffer_size}), must be >= {DICT_SIZE}")
+        return self._b.from_writer(writer)

@@ -1,0 +1,39 @@
+"""In-tree build of libgzpb.so (hand-written sm_100a CUDA + the C ABI of include/gzpb.h).
+
+nvcc cross-compiles here without a GPU; the resulting .so is git-ignored but
+travels to the GPU box with the repo snapshot.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+SO = os.path.join(HERE, "libgzpb.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+         "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-diag-suppress", "1886"]
+
+
+def sources():
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cpp")))
+
+
+def build(force=False, verbose=False):
+    srcs = sources()
+    deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    deps.append(os.path.join(HERE, "..", "include", "gzpb.h"))
+    if not force and os.path.exists(SO) and all(os.path.getmtime(d) <= os.path.getmtime(SO) for d in deps):
+        return SO
+    objs = []
+    for s in srcs:
+        o = os.path.join(CSRC, os.path.basename(s).rsplit(".", 1)[0] + ".o")
+        cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-x", "cu", "-c", s, "-o", o]
+        subprocess.check_call(cmd)
+        objs.append(o)
+    subprocess.check_call([NVCC, "-shared", "-o", SO] + objs + ["-lpthread"])
+    return SO
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,1074 @@
+// deflate_kernels.cu — sm_100a kernels for the DEFLATE-family per-block encode
+// path (Bgzf / Mgzip / Gzip / Zlib / RawDeflate), i.e. the GPU replacement of
+// `format.encode(chunk, ...)` + `check.update(chunk)` in gzp's worker loop
+// (/root/reference/src/par/compress.rs:279-294 -> src/bgzf.rs:204-237,
+// src/mgzip.rs:187-218).  One thread block per gzp block.
+//
+// Pipeline per batch of units (a unit = one gzp block, <= 65536 positions):
+//   k_chain  : hash-chain links (hash4 -> next4[], hash3 -> prev3[]) + CRC-32
+//   k_match  : TMA-staged input + chains in shared memory; per-position longest
+//              match for search depth D and D/2 (parse-independent)
+//   k_emit   : sequential lazy/greedy parse over the match table, block
+//              splitting, Huffman construction, parallel bit packing, container
+//              header/footer
+//   k_scan / k_gather : exclusive scan of block sizes + compaction into stream order
+// Results are bit-identical to oracle/deflate_oracle.c (tests/test_gpu_parity.py).
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "gzpb_common.cuh"
+#include "deflate_kernels.cuh"
+
+namespace gzpb {
+
+__constant__ uint32_t c_crc_tab[4][256];      // slicing-by-4, reflected 0xEDB88320
+__constant__ uint32_t c_xpow512[130];         // x^(8*512*j) mod P
+__constant__ uint16_t c_static_litlen_cw[288];
+__constant__ uint8_t c_static_litlen_len[288];
+__constant__ uint8_t c_min_lens[80];
+
+static uint32_t h_bitrev(uint32_t v, int n) { uint32_t r = 0; for (int i = 0; i < n; i++) r |= ((v >> i) & 1u) << (n - 1 - i); return r; }
+
+void upload_deflate_constants()
+{
+    static uint32_t tab[4][256];
+    for (uint32_t i = 0; i < 256; i++) {
+        uint32_t c = i;
+        for (int k = 0; k < 8; k++) c = (c >> 1) ^ (kCrcPoly & (0u - (c & 1)));
+        tab[0][i] = c;
+    }
+    for (uint32_t i = 0; i < 256; i++)
+        for (int s = 1; s < 4; s++) tab[s][i] = (tab[s - 1][i] >> 8) ^ tab[0][tab[s - 1][i] & 0xFF];
+    cudaMemcpyToSymbol(c_crc_tab, tab, sizeof tab);
+    uint32_t xp[130];
+    for (int j = 0; j < 130; j++) xp[j] = gf2_xpow8((uint64_t)512 * j, kCrcPoly);
+    cudaMemcpyToSymbol(c_xpow512, xp, sizeof xp);
+    uint16_t cw[288]; uint8_t ln[288];
+    for (int s = 0; s < 288; s++) {
+        uint32_t code; int len;
+        if (s < 144) { len = 8; code = 0x30 + s; }
+        else if (s < 256) { len = 9; code = 0x190 + (s - 144); }
+        else if (s < 280) { len = 7; code = s - 256; }
+        else { len = 8; code = 0xC0 + (s - 280); }
+        cw[s] = (uint16_t)h_bitrev(code, len); ln[s] = (uint8_t)len;
+    }
+    cudaMemcpyToSymbol(c_static_litlen_cw, cw, sizeof cw);
+    cudaMemcpyToSymbol(c_static_litlen_len, ln, sizeof ln);
+    static const uint8_t min_lens[80] = {9,9,9,9,9,9,8,8,7,7,6,6,6,6,6,6,5,5,5,5,5,5,5,5,5,5,5,5,5,5,5,5,
+                                         5,5,5,5,5,5,5,5,5,5,5,5,5,5,5,5,5,5,5,5,5,5,5,5,5,5,5,5,5,5,5,5,
+                                         4,4,4,4,4,4,4,4,4,4,4,4,4,4,4,4};
+    cudaMemcpyToSymbol(c_min_lens, min_lens, sizeof min_lens);
+}
+
+// =============================================================================
+// k_chain: hash chains + CRC-32.  1 CTA (256 threads) per unit, 1 CTA per SM.
+//   warp 0      : hash4 buckets -> next4[p] = distance to the previous position
+//                 with the same 16-bit hash (0 = none / outside the 32 KiB window)
+//   warp 1      : hash3 buckets -> prev3[p] likewise (15-bit hash of 3 bytes)
+//   warps 2..7  : CRC-32 of the unit (512-byte chunks, GF(2) recombination)
+// Shared memory: head4 u16[65536] + head3 u16[32768] = 192 KiB.
+// Restates the insertion side of libdeflate's hc_matchfinder: every position
+// p <= n-5 is inserted, position 0 under hash 0 (next_hashes starts at {0,0}).
+// =============================================================================
+constexpr int kChainThreads = 256;
+constexpr uint32_t kNone16 = 0xFFFFu;
+
+__device__ __forceinline__ uint32_t ldg32u(const uint32_t *__restrict__ words, uint32_t byte_pos)
+{
+    uint32_t w = byte_pos >> 2, s = (byte_pos & 3) * 8;
+    return __funnelshift_r(__ldg(words + w), __ldg(words + w + 1), s);
+}
+
+template <int HASH_BITS, bool H3>
+__device__ __forceinline__ void chain_warp(const uint32_t *__restrict__ inw, uint32_t n, uint32_t dict0,
+                                           uint16_t *head, uint16_t *__restrict__ gout)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t ninsert = n >= 5 ? n - 4 : 0;
+    const uint32_t lt = lanemask_lt();
+    constexpr int G = 8;  // tiles per register group
+    uint32_t v[G], vn[G];
+#pragma unroll
+    for (int k = 0; k < G; k++) { uint32_t p = 32 * k + lane; vn[k] = p < ninsert ? ldg32u(inw, p) : 0; }
+    for (uint32_t base0 = 0; base0 < n; base0 += 32 * G) {
+#pragma unroll
+        for (int k = 0; k < G; k++) v[k] = vn[k];
+#pragma unroll
+        for (int k = 0; k < G; k++) { uint32_t p = base0 + 32 * (G + k) + lane; vn[k] = p < ninsert ? ldg32u(inw, p) : 0; }
+#pragma unroll
+        for (int k = 0; k < G; k++) {
+            const uint32_t base = base0 + 32 * k;
+            if (base >= n) break;
+            const uint32_t p = base + lane;
+            const bool act = p < ninsert;
+            uint32_t seq = H3 ? (v[k] & 0xFFFFFFu) : v[k];
+            uint32_t h = lz_hash(seq, HASH_BITS);
+            if (p == 0 && !dict0) h = 0;
+            uint32_t key = act ? h : (0x10000u + lane);
+            uint32_t grp = __match_any_sync(0xFFFFFFFFu, key);
+            uint32_t lower = grp & lt;
+            uint32_t prev = kNone16;
+            if (act) {
+                if (lower) prev = base + 31 - __clz(lower);
+                else prev = head[h];
+                if ((grp >> lane) == 1u) head[h] = (uint16_t)p;  // highest lane of the group
+            }
+            __syncwarp();
+            uint32_t dist = (prev != kNone16) ? p - prev : 0;
+            if (dist >= (uint32_t)kWindow) dist = 0;
+            if (p < n) gout[p] = (uint16_t)dist;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kChainThreads, 1)
+k_chain(const uint8_t *__restrict__ in_base, const uint32_t *__restrict__ unit_len, uint16_t *__restrict__ next4,
+        uint16_t *__restrict__ prev3, uint32_t *__restrict__ crc_out)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint16_t *head4 = (uint16_t *)smem;
+    uint16_t *head3 = head4 + 65536;
+    uint32_t(*s_tab)[256] = (uint32_t(*)[256])(smem + (65536 + 32768) * 2);
+    __shared__ uint32_t s_crc;
+    const uint32_t u = blockIdx.x;
+    const uint32_t n = unit_len[u];
+    const uint8_t *in = in_base + (size_t)u * kInStride;
+    const uint32_t *inw = (const uint32_t *)in;
+    const uint32_t tid = threadIdx.x, warp = tid >> 5;
+
+    // pull the unit into L2 ahead of the dependent loads
+    for (uint32_t off = tid * 128; off < n; off += kChainThreads * 128)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(in + off));
+    {
+        uint4 ones = make_uint4(~0u, ~0u, ~0u, ~0u);
+        uint4 *h = (uint4 *)smem;
+        for (uint32_t i = tid; i < (65536 + 32768) * 2 / 16; i += kChainThreads) h[i] = ones;
+    }
+    for (uint32_t i = tid; i < 1024; i += kChainThreads) s_tab[i >> 8][i & 255] = c_crc_tab[i >> 8][i & 255];
+    if (tid == 0) s_crc = 0;
+    __syncthreads();
+
+    if (warp == 0) {
+        chain_warp<16, false>(inw, n, 0, head4, next4 + (size_t)u * kMaxUnitBytes);
+    } else if (warp == 1) {
+        chain_warp<15, true>(inw, n, 0, head3, prev3 + (size_t)u * kMaxUnitBytes);
+    } else {
+        // CRC-32: chunk j covers [n-512(j+1), n-512j) clipped at 0; combine with x^(8*512*j)
+        uint32_t acc = 0;
+        for (uint32_t j = tid - 64; j * 512 < n; j += kChainThreads - 64) {
+            uint32_t end = n - 512 * j, beg = end >= 512 ? end - 512 : 0;
+            uint32_t c = ~0u, pos = beg;
+            while (pos < end && (pos & 3)) { c = (c >> 8) ^ s_tab[0][(c ^ in[pos]) & 0xFF]; pos++; }
+            for (; pos + 4 <= end; pos += 4) {
+                c ^= __ldg(inw + (pos >> 2));
+                c = s_tab[3][c & 0xFF] ^ s_tab[2][(c >> 8) & 0xFF] ^ s_tab[1][(c >> 16) & 0xFF] ^ s_tab[0][c >> 24];
+            }
+            while (pos < end) { c = (c >> 8) ^ s_tab[0][(c ^ in[pos]) & 0xFF]; pos++; }
+            c = ~c;
+            acc ^= (j == 0) ? c : gf2_mulmod(c, c_xpow512[j], kCrcPoly);
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) acc ^= __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+        if ((tid & 31) == 0 && acc) atomicXor(&s_crc, acc);
+    }
+    __syncthreads();
+    if (tid == 0) crc_out[u] = s_crc;
+}
+
+// =============================================================================
+// k_match: per-position longest-match search.  1 CTA (1024 threads) per unit.
+// The unit's bytes and its next4[] chain links are staged into shared memory
+// with two TMA bulk copies (cp.async.bulk + mbarrier); each thread then owns
+// positions and walks its hash chain exactly like hc_matchfinder_longest_match,
+// recording the best match over the first D nodes (A) and the first D/2 nodes
+// (B).  Because every position is inserted, the chain of a position does not
+// depend on parsing decisions, so all positions are searched in parallel.
+// =============================================================================
+constexpr int kMatchThreads = 1024;
+
+__device__ __forceinline__ uint32_t lz_extend(const uint32_t *s_in, uint32_t p, uint32_t q, uint32_t len, uint32_t maxlen)
+{
+    const uint8_t *b = (const uint8_t *)s_in;
+    while (len + 4 <= maxlen) {
+        uint32_t x = ld32u(s_in, p + len) ^ ld32u(s_in, q + len);
+        if (x) return len + ((__ffs(x) - 1) >> 3);
+        len += 4;
+    }
+    while (len < maxlen && b[p + len] == b[q + len]) len++;
+    return len;
+}
+
+__global__ void __launch_bounds__(kMatchThreads, 1)
+k_match(const uint8_t *__restrict__ in_base, const uint32_t *__restrict__ unit_len, const uint16_t *__restrict__ next4g,
+        const uint16_t *__restrict__ prev3g, uint64_t *__restrict__ mtab, int depth, int nice, int lazy)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint32_t *s_in = (uint32_t *)smem;
+    uint16_t *s_next = (uint16_t *)(smem + kInStride);
+    __shared__ __align__(8) uint64_t bar;
+    const uint32_t u = blockIdx.x, tid = threadIdx.x;
+    const uint32_t n = unit_len[u];
+    const uint8_t *in = in_base + (size_t)u * kInStride;
+    uint64_t *M = mtab + (size_t)u * kMaxUnitBytes;
+
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (n >= 5) {
+        if (tid == 0) {
+            uint32_t bin = (n + 15u) & ~15u, bnx = (n * 2 + 15u) & ~15u;
+            mbar_expect_tx(&bar, bin + bnx);
+            tma_load_1d(s_in, in, bin, &bar);
+            tma_load_1d(s_next, next4g + (size_t)u * kMaxUnitBytes, bnx, &bar);
+        }
+        mbar_wait(&bar, 0);
+    }
+    const uint16_t *p3 = prev3g + (size_t)u * kMaxUnitBytes;
+    const uint32_t depthB = (uint32_t)depth >> 1;
+
+    for (uint32_t p = tid; p < n; p += kMatchThreads) {
+        const uint32_t maxlen = min((uint32_t)kMaxMatch, n - p);
+        if (maxlen < 5) { M[p] = 0; continue; }
+        const uint32_t nicep = min((uint32_t)nice, maxlen);
+        const uint32_t seq4 = ld32u(s_in, p);
+        uint32_t d3 = p3[p];
+        uint32_t off3 = 0;
+        if (d3 && d3 <= 8192u && ((ld32u(s_in, p - d3) ^ seq4) & 0xFFFFFFu) == 0) off3 = d3;
+
+        uint32_t best = 3, boff = 0, lenB = 0, offB = 0;
+        bool haveB = !lazy;
+        uint32_t q = p, visited = 0;
+        for (;;) {
+            uint32_t d = s_next[q];
+            if (d == 0) break;
+            q -= d;
+            if (p - q >= (uint32_t)kWindow) break;
+            visited++;
+            bool cand;
+            if (best == 3) cand = (ld32u(s_in, q) == seq4);
+            else {
+                const uint8_t *b = (const uint8_t *)s_in;
+                cand = (b[q + best] == b[p + best]) && (ld32u(s_in, q) == seq4);
+            }
+            if (cand) {
+                uint32_t len = lz_extend(s_in, p, q, 4, maxlen);
+                if (len > best) {
+                    best = len; boff = p - q;
+                    if (len >= nicep) break;
+                }
+            }
+            if (!haveB && visited == depthB) { haveB = true; lenB = best > 3 ? best : 0; offB = boff; }
+            if (visited == (uint32_t)depth) break;
+        }
+        uint32_t lenA = best > 3 ? best : 0;
+        if (!haveB) { lenB = lenA; offB = boff; }
+        if (!lazy) { lenB = 0; offB = 0; }
+        M[p] = pack_entry(lenA, boff, lenB, offB, d3 != 0, off3);
+    }
+}
+
+// =============================================================================
+// k_emit: parse + Huffman + bit packing + container.  1 CTA (128 threads) per
+// unit, many CTAs per SM.  Thread 0 runs the sequential parser (greedy / lazy,
+// min_len heuristics, block splitting) over match-table tiles streamed into a
+// 2-slot shared-memory ring by TMA bulk copies; at each DEFLATE block boundary
+// the whole CTA builds the Huffman codes (libdeflate's sort / in-place tree /
+// length limiting / canonical codewords restated), picks the cheapest of
+// dynamic / static / stored, and packs the tokens in parallel (prefix scan of
+// code lengths, OR-merge in a shared staging buffer, coalesced 32-bit stores).
+// =============================================================================
+constexpr int kEmitThreads = 128;
+constexpr int kTile = 512;                 // positions per streamed tile
+constexpr int kTokPerThread = 8;
+constexpr int kChunkTok = kEmitThreads * kTokPerThread;
+constexpr int kStageWords = (kChunkTok * 48) / 32 + 8;
+
+struct EmitShared {
+    alignas(16) uint64_t mt[2][kTile];
+    alignas(16) uint8_t inb[2][kTile];
+    alignas(8) uint64_t bar[2];
+    uint32_t fl[kNumLitlen];
+    uint32_t fo[kNumOffset];
+    uint32_t obs[10], new_obs[10];
+    uint32_t A[kNumLitlen];
+    uint8_t lens[kNumLitlen + kNumOffset];   // litlen then offset lens (contiguous like libdeflate)
+    uint16_t lcw[kNumLitlen];
+    uint16_t ocw[kNumOffset];
+    uint8_t plen[kNumPrecode];
+    uint16_t pcw[kNumPrecode];
+    uint32_t pfreq[kNumPrecode];
+    uint16_t items[kNumLitlen + kNumOffset];
+    uint32_t stage[kStageWords];
+    uint32_t scan[kEmitThreads / 32];
+    uint32_t used[8];
+    // control block written by thread 0
+    uint32_t blk_begin, blk_end, ntok, is_final, min_len;
+    uint32_t nused, nitems, nlit, noff, nexpl, btype;
+    uint32_t cost_dyn, cost_static;
+    uint32_t G;        // bit position in the payload
+    uint32_t carry;    // partial word at G>>5
+    int32_t status;
+};
+
+__device__ __forceinline__ uint32_t bsr32(uint32_t v) { return 31 - __clz(v); }
+
+__device__ __forceinline__ void len_slot(uint32_t len, uint32_t &slot, uint32_t &ebits, uint32_t &eval)
+{
+    uint32_t l = len - 3;
+    if (l < 8) { slot = l; ebits = 0; eval = 0; }
+    else if (l == 255) { slot = 28; ebits = 0; eval = 0; }
+    else {
+        uint32_t k = 31 - __clz(l);
+        slot = 4 * k - 4 + ((l >> (k - 2)) & 3);
+        ebits = k - 2; eval = l & ((1u << (k - 2)) - 1);
+    }
+}
+__device__ __forceinline__ void off_slot(uint32_t off, uint32_t &slot, uint32_t &ebits, uint32_t &eval)
+{
+    uint32_t d = off - 1;
+    if (d < 4) { slot = d; ebits = 0; eval = 0; }
+    else {
+        uint32_t k = 31 - __clz(d);
+        slot = 2 * k + ((d >> (k - 1)) & 1);
+        ebits = k - 1; eval = d & ((1u << (k - 1)) - 1);
+    }
+}
+__device__ __forceinline__ uint32_t len_slot_only(uint32_t len) { uint32_t s, a, b; len_slot(len, s, a, b); return s; }
+__device__ __forceinline__ uint32_t off_slot_only(uint32_t off) { uint32_t s, a, b; off_slot(off, s, a, b); return s; }
+
+__device__ __forceinline__ void stage_put(uint32_t *st, uint32_t bitpos, uint64_t bits, uint32_t nbits)
+{
+    if (nbits == 0) return;
+    uint32_t w = bitpos >> 5, s = bitpos & 31;
+    uint64_t lo = bits << s;
+    uint32_t w0 = (uint32_t)lo, w1 = (uint32_t)(lo >> 32);
+    uint32_t w2 = s ? (uint32_t)(bits >> (64 - s)) : 0;
+    if (w0) atomicOr(&st[w], w0);
+    if (w1) atomicOr(&st[w + 1], w1);
+    if (w2) atomicOr(&st[w + 2], w2);
+}
+
+__device__ __forceinline__ uint32_t choose_min_match_len(uint32_t num_used, uint32_t depth)
+{
+    if (num_used >= 80) return 3;
+    uint32_t m = c_min_lens[num_used];
+    if (depth < 16) {
+        uint32_t cap = depth < 5 ? 4 : depth < 10 ? 5 : 7;
+        m = min(m, cap);
+    }
+    return m;
+}
+
+// Cooperative restatement of libdeflate's deflate_make_huffman_code().
+// freqs/lens/cw live in shared memory; all kEmitThreads threads call it.
+template <typename CW>
+__device__ void make_huffman_code(EmitShared &S, const uint32_t *freqs, uint32_t num_syms, uint32_t max_len,
+                                  uint8_t *lens, CW *cw)
+{
+    const uint32_t tid = threadIdx.x;
+    if (tid == 0) S.nused = 0;
+    __syncthreads();
+    // rank sort by (freq, sym)
+    for (uint32_t s = tid; s < num_syms; s += kEmitThreads) {
+        uint32_t f = freqs[s];
+        lens[s] = 0; cw[s] = 0;
+        if (f) {
+            uint32_t key = s | (f << 10), rank = 0;
+            for (uint32_t t = 0; t < num_syms; t++) {
+                uint32_t ft = freqs[t];
+                rank += (ft && (t | (ft << 10)) < key);
+            }
+            S.A[rank] = key;
+            atomicAdd(&S.nused, 1u);
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t *A = S.A;
+        const uint32_t n = S.nused;
+        if (n < 2) {
+            uint32_t sym = n ? (A[0] & 1023u) : 0;
+            uint32_t nz = sym ? sym : 1;
+            cw[0] = 0; lens[0] = 1; cw[nz] = 1; lens[nz] = 1;
+        } else {
+            const uint32_t FM = ~1023u;
+            const uint32_t last = n - 1;
+            uint32_t i = 0, b = 0, e = 0;
+            do {
+                uint32_t nf;
+                if (i + 1 <= last && (b == e || (A[i + 1] & FM) <= (A[b] & FM))) {
+                    nf = (A[i] & FM) + (A[i + 1] & FM); i += 2;
+                } else if (b + 2 <= e && (i > last || (A[b + 1] & FM) < (A[i] & FM))) {
+                    nf = (A[b] & FM) + (A[b + 1] & FM);
+                    A[b] = (e << 10) | (A[b] & 1023u);
+                    A[b + 1] = (e << 10) | (A[b + 1] & 1023u);
+                    b += 2;
+                } else {
+                    nf = (A[i] & FM) + (A[b] & FM);
+                    A[b] = (e << 10) | (A[b] & 1023u);
+                    i++; b++;
+                }
+                A[e] = nf | (A[e] & 1023u);
+            } while (++e < last);
+
+            uint32_t len_counts[16];
+            for (uint32_t l = 0; l <= max_len; l++) len_counts[l] = 0;
+            len_counts[1] = 2;
+            int root = (int)n - 2;
+            A[root] &= 1023u;
+            for (int node = root - 1; node >= 0; node--) {
+                uint32_t parent = A[node] >> 10;
+                uint32_t dpt = (A[parent] >> 10) + 1;
+                A[node] = (A[node] & 1023u) | (dpt << 10);
+                if (dpt >= max_len) {
+                    dpt = max_len;
+                    do { dpt--; } while (len_counts[dpt] == 0);
+                }
+                len_counts[dpt]--;
+                len_counts[dpt + 1] += 2;
+            }
+            uint32_t k = 0;
+            for (uint32_t len = max_len; len >= 1; len--) {
+                uint32_t c = len_counts[len];
+                while (c--) lens[A[k++] & 1023u] = (uint8_t)len;
+            }
+            uint32_t next_cw[16];
+            next_cw[0] = 0; next_cw[1] = 0;
+            for (uint32_t len = 2; len <= max_len; len++) next_cw[len] = (next_cw[len - 1] + len_counts[len - 1]) << 1;
+            for (uint32_t s = 0; s < num_syms; s++) {
+                uint32_t l = lens[s];
+                if (l) cw[s] = (CW)(__brev(next_cw[l]++) >> (32 - l));
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// flush `nbits` staged bits starting at S.G to the payload; all threads call it.
+__device__ __forceinline__ void stage_commit(EmitShared &S, uint32_t *__restrict__ payload, uint32_t nbits)
+{
+    __syncthreads();
+    const uint32_t g = S.G, bw = g >> 5, nfull = ((g & 31) + nbits) >> 5;
+    for (uint32_t i = threadIdx.x; i < nfull; i += kEmitThreads) payload[bw + i] = S.stage[i];
+    __syncthreads();
+    if (threadIdx.x == 0) { S.carry = S.stage[nfull]; S.G = g + nbits; }
+    __syncthreads();
+}
+// zero the staging area and seed word 0 with the carry; all threads call it.
+__device__ __forceinline__ void stage_begin(EmitShared &S, uint32_t words)
+{
+    for (uint32_t i = threadIdx.x; i < words; i += kEmitThreads) S.stage[i] = 0;
+    __syncthreads();
+    if (threadIdx.x == 0) S.stage[0] = S.carry;
+    __syncthreads();
+}
+
+struct Parser {
+    const uint64_t *mt_g;
+    const uint8_t *in_g;
+    EmitShared *S;
+    uint32_t n, ntiles, issued, ready;
+    __device__ __forceinline__ void issue(uint32_t t)
+    {
+        uint32_t slot = t & 1, pos = t * kTile;
+        uint32_t cnt = min((uint32_t)kTile, n - pos);
+        uint32_t bm = (cnt * 8 + 15u) & ~15u, bi = (cnt + 15u) & ~15u;
+        mbar_expect_tx(&S->bar[slot], bm + bi);
+        tma_load_1d(S->mt[slot], mt_g + pos, bm, &S->bar[slot]);
+        tma_load_1d(S->inb[slot], in_g + pos, bi, &S->bar[slot]);
+    }
+    __device__ __forceinline__ void advance(uint32_t p)
+    {
+        // tile (issued-2) is dead once p has moved past it
+        while (issued < ntiles && (issued - 1) * kTile <= p) { issue(issued); issued++; }
+    }
+    __device__ __forceinline__ void need(uint32_t p)
+    {
+        uint32_t t = p / kTile;
+        while (ready <= t) { mbar_wait(&S->bar[ready & 1], (ready >> 1) & 1); ready++; }
+    }
+    __device__ __forceinline__ uint64_t M(uint32_t p) { need(p); return S->mt[(p / kTile) & 1][p % kTile]; }
+    __device__ __forceinline__ uint32_t B(uint32_t p) { need(p); return S->inb[(p / kTile) & 1][p % kTile]; }
+};
+
+// hc_matchfinder_longest_match() answered from the match table
+__device__ __forceinline__ void table_search(uint64_t e, uint32_t b, bool useB, uint32_t maxlen, uint32_t &len, uint32_t &off)
+{
+    len = b; off = 0;
+    if (maxlen < 5) return;
+    uint32_t lx = useB ? (uint32_t)(e >> 23) & 0xFF : (uint32_t)e & 0xFF;
+    uint32_t ox = useB ? (uint32_t)(e >> 31) & 0x7FFF : (uint32_t)(e >> 8) & 0x7FFF;
+    if (lx) lx += 3;
+    if (b < 4) {
+        if (!((e >> 46) & 1)) return;
+        uint32_t off3 = (uint32_t)(e >> 47) & 0x3FFF;
+        if (b < 3 && off3) { len = 3; off = off3; }
+        if (lx) { len = lx; off = ox; }
+    } else if (lx > b) { len = lx; off = ox; }
+}
+
+__global__ void __launch_bounds__(kEmitThreads)
+k_emit(const uint8_t *__restrict__ in_base, const uint32_t *__restrict__ unit_len, const uint32_t *__restrict__ unit_flags,
+       const uint64_t *__restrict__ mtab, const uint32_t *__restrict__ crc_in, uint32_t *__restrict__ tok_base,
+       uint8_t *__restrict__ out_base, uint32_t *__restrict__ out_len, int32_t *__restrict__ out_status,
+       int mode, int depth, int nice, int level, int format)
+{
+    __shared__ EmitShared S;
+    const uint32_t u = blockIdx.x, tid = threadIdx.x;
+    const uint32_t n = unit_len[u];
+    const uint32_t flags = unit_flags[u];
+    const uint8_t *in = in_base + (size_t)u * kInStride;
+    uint32_t *tok = tok_base + (size_t)u * kTokStride;
+    uint8_t *slot = out_base + (size_t)u * kOutStride;
+    uint32_t *payload = (uint32_t *)(slot + kOutPayloadOff);
+    const bool sync_flush = (flags & 2u) != 0;    // Gzip/Zlib non-last and RawDeflate: no BFINAL, sync marker
+    const bool final_block = !sync_flush;
+
+    Parser P;
+    P.mt_g = mtab + (size_t)u * kMaxUnitBytes; P.in_g = in; P.S = &S; P.n = n;
+    P.ntiles = (n + kTile - 1) / kTile; P.issued = 0; P.ready = 0;
+
+    if (tid == 0) {
+        mbar_init(&S.bar[0], 1); mbar_init(&S.bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        S.G = 0; S.carry = 0; S.status = 0;
+    }
+    __syncthreads();
+
+    const uint32_t passthrough = (level == 0) ? 0xFFFFFFFFu : (uint32_t)(55 - level * 4);
+    if (n <= passthrough && !(sync_flush && n == 0)) {
+        // deflate_compress_none(): stored blocks of <= 65535 bytes
+        uint32_t pos = 0;
+        do {
+            uint32_t len = min(n - pos, 65535u);
+            uint32_t bfinal = (n - pos <= 65535u) ? (final_block ? 1u : 0u) : 0u;
+            uint32_t tot_bits = 8 + 32 + 8 * len;
+            for (uint32_t cb = 0; cb < tot_bits;) {
+                uint32_t chunk = min(tot_bits - cb, (uint32_t)(kStageWords - 4) * 32);
+                stage_begin(S, kStageWords);
+                uint32_t g0 = S.G & 31;
+                for (uint32_t bit = cb + tid * 8; bit < cb + chunk; bit += kEmitThreads * 8) {
+                    uint32_t v;
+                    if (bit == 0) v = bfinal;
+                    else if (bit < 24) v = (len >> (bit - 8)) & 0xFF;
+                    else if (bit < 40) v = ((~len & 0xFFFF) >> (bit - 24)) & 0xFF;
+                    else v = in[pos + (bit - 40) / 8];
+                    stage_put(S.stage, g0 + (bit - cb), v, 8);
+                }
+                stage_commit(S, payload, chunk);
+                cb += chunk;
+            }
+            pos += len;
+        } while (pos != n);
+    } else if (n > 0) {
+        if (tid == 0) { P.issue(0); P.issued = 1; if (P.ntiles > 1) { P.issue(1); P.issued = 2; } }
+        uint32_t p = 0;              // parser position (thread 0 only is authoritative)
+        uint32_t next_recalc = 0, min_len = 3;
+        while (true) {
+            // ---------------- block start (all threads) ----------------
+            if (tid == 0) S.blk_begin = p;
+            __syncthreads();
+            const uint32_t bb = S.blk_begin;
+            if (bb >= n) break;
+            const uint32_t max_block_end = (n - bb < (uint32_t)(kSoftMaxBlockLength + kMinBlockLength)) ? n : bb + kSoftMaxBlockLength;
+            for (uint32_t i = tid; i < kNumLitlen; i += kEmitThreads) S.fl[i] = 0;
+            if (tid < kNumOffset) S.fo[tid] = 0;
+            if (tid < 10) { S.obs[tid] = 0; S.new_obs[tid] = 0; }
+            if (tid < 8) S.used[tid] = 0;
+            __syncthreads();
+            {   // calculate_min_match_len(): distinct byte values in the first <= 4096 bytes
+                uint32_t span = min(max_block_end - bb, 4096u);
+                if (max_block_end - bb >= 512) {
+                    for (uint32_t i = tid; i < span; i += kEmitThreads) { uint32_t c = in[bb + i]; atomicOr(&S.used[c >> 5], 1u << (c & 31)); }
+                }
+                __syncthreads();
+            }
+            // ---------------- sequential parse (thread 0) ----------------
+            if (tid == 0) {
+                if (max_block_end - bb < 512) min_len = 3;
+                else {
+                    uint32_t nu = 0;
+                    for (int i = 0; i < 8; i++) nu += __popc(S.used[i]);
+                    min_len = choose_min_match_len(nu, depth);
+                }
+                next_recalc = bb + min(n - bb, 10000u);
+                uint32_t ntok = 0, nmatch = 0, num_obs = 0, num_new_obs = 0;
+                bool end_block = false;
+#define LITERAL(byte_)                                                                 \
+    do {                                                                               \
+        uint32_t lit_ = (byte_);                                                       \
+        atomicAdd(&S.fl[lit_], 1u);                                                    \
+        atomicAdd(&S.new_obs[((lit_ >> 5) & 6) | (lit_ & 1)], 1u);                     \
+        num_new_obs++;                                                                 \
+        tok[ntok++] = lit_;                                                            \
+    } while (0)
+#define MATCH(len_, off_)                                                              \
+    do {                                                                               \
+        atomicAdd(&S.fl[kFirstLenSym + len_slot_only(len_)], 1u);                      \
+        atomicAdd(&S.fo[off_slot_only(off_)], 1u);                                     \
+        atomicAdd(&S.new_obs[8 + ((len_) >= 9)], 1u);                                  \
+        num_new_obs++;                                                                 \
+        tok[ntok++] = 0x80000000u | ((len_) << 16) | (off_);                           \
+        nmatch++;                                                                      \
+    } while (0)
+                do {
+                    P.advance(p);
+                    uint32_t cur_len, cur_off;
+                    if (mode == 0) {
+                        uint32_t maxlen = min((uint32_t)kMaxMatch, n - p);
+                        table_search(P.M(p), min_len - 1, false, maxlen, cur_len, cur_off);
+                        if (cur_len >= min_len && (cur_len > 3 || cur_off <= 4096)) { MATCH(cur_len, cur_off); p += cur_len; }
+                        else { LITERAL(P.B(p)); p++; }
+                    } else {
+                        if (p >= next_recalc) {
+                            // recalculate_min_match_len() from the literal frequencies so far
+                            uint32_t total = 0, nu = 0;
+                            for (int i = 0; i < 256; i++) total += S.fl[i];
+                            uint32_t cutoff = total >> 10;
+                            for (int i = 0; i < 256; i++) nu += (S.fl[i] > cutoff);
+                            min_len = choose_min_match_len(nu, depth);
+                            next_recalc += min(n - next_recalc, p - bb);
+                        }
+                        uint32_t maxlen = min((uint32_t)kMaxMatch, n - p);
+                        table_search(P.M(p), min_len - 1, false, maxlen, cur_len, cur_off);
+                        if (cur_len < min_len || (cur_len == 3 && cur_off > 8192)) { LITERAL(P.B(p)); p++; }
+                        else {
+                            uint32_t m = p;
+                            for (;;) {
+                                uint32_t nice_m = min((uint32_t)nice, min((uint32_t)kMaxMatch, n - m));
+                                if (cur_len >= nice_m) break;
+                                uint32_t nl, no;
+                                uint32_t maxlen1 = min((uint32_t)kMaxMatch, n - (m + 1));
+                                table_search(maxlen1 >= 5 ? P.M(m + 1) : 0ull, cur_len - 1, true, maxlen1, nl, no);
+                                if (nl >= cur_len && 4 * (int)(nl - cur_len) + ((int)bsr32(cur_off) - (int)bsr32(no)) > 2) {
+                                    LITERAL(P.B(m));
+                                    m++; cur_len = nl; cur_off = no;
+                                    P.advance(m);
+                                    continue;
+                                }
+                                break;
+                            }
+                            MATCH(cur_len, cur_off);
+                            p = m + cur_len;
+                        }
+                    }
+                    // should_end_block()
+                    if (num_new_obs >= (uint32_t)kObsPerCheck && p - bb >= (uint32_t)kMinBlockLength && n - p >= (uint32_t)kMinBlockLength) {
+                        uint32_t block_length = p - bb;
+                        if (num_obs > 0) {
+                            uint32_t total_delta = 0;
+                            for (int i = 0; i < 10; i++) {
+                                uint32_t expected = S.obs[i] * num_new_obs, actual = S.new_obs[i] * num_obs;
+                                total_delta += actual > expected ? actual - expected : expected - actual;
+                            }
+                            uint32_t num_items = num_obs + num_new_obs;
+                            uint32_t cutoff = num_new_obs * 200 / 512 * num_obs;
+                            if (block_length < 10000 && num_items < 8192)
+                                cutoff += (uint32_t)((uint64_t)cutoff * (8192 - num_items) / 8192);
+                            if (total_delta + (block_length / 4096) * num_obs >= cutoff) end_block = true;
+                        }
+                        if (!end_block) {
+                            for (int i = 0; i < 10; i++) { S.obs[i] += S.new_obs[i]; S.new_obs[i] = 0; }
+                            num_obs += num_new_obs; num_new_obs = 0;
+                        }
+                    }
+                } while (p < max_block_end && nmatch < (uint32_t)kSeqStoreLength && !end_block);
+#undef LITERAL
+#undef MATCH
+                S.blk_end = p; S.ntok = ntok; S.is_final = (final_block && p == n) ? 1u : 0u;
+                S.fl[kEndOfBlock] += 1;
+            }
+            __syncthreads();
+            __threadfence_block();
+            // ---------------- finish block (all threads) ----------------
+            const uint32_t be = S.blk_end, ntok = S.ntok, block_len = be - bb, is_final = S.is_final;
+            uint8_t *ll = S.lens, *ol = S.lens + kNumLitlen;
+            make_huffman_code<uint16_t>(S, S.fl, kNumLitlen, kMaxLitlenCw, ll, S.lcw);
+            make_huffman_code<uint16_t>(S, S.fo, kNumOffset, kMaxOffsetCw, ol, S.ocw);
+            if (tid == 0) {
+                // deflate_precompute_huffman_header(): RLE of the code lengths
+                uint32_t nlit = kNumLitlen, noff = kNumOffset;
+                while (nlit > 257 && ll[nlit - 1] == 0) nlit--;
+                while (noff > 1 && ol[noff - 1] == 0) noff--;
+                S.nlit = nlit; S.noff = noff;
+                for (int i = 0; i < kNumPrecode; i++) S.pfreq[i] = 0;
+                const uint32_t num_lens = nlit + noff;
+                uint32_t ni = 0, run_start = 0;
+#define LENS_AT(i_) ((i_) < nlit ? ll[(i_)] : ol[(i_) - nlit])
+                do {
+                    uint32_t len = LENS_AT(run_start);
+                    uint32_t run_end = run_start;
+                    do { run_end++; } while (run_end != num_lens && len == LENS_AT(run_end));
+                    if (len == 0) {
+                        while (run_end - run_start >= 11) {
+                            uint32_t eb = min(run_end - run_start - 11, 0x7Fu);
+                            S.pfreq[18]++; S.items[ni++] = (uint16_t)(18 | (eb << 5)); run_start += 11 + eb;
+                        }
+                        if (run_end - run_start >= 3) {
+                            uint32_t eb = min(run_end - run_start - 3, 7u);
+                            S.pfreq[17]++; S.items[ni++] = (uint16_t)(17 | (eb << 5)); run_start += 3 + eb;
+                        }
+                    } else if (run_end - run_start >= 4) {
+                        S.pfreq[len]++; S.items[ni++] = (uint16_t)len; run_start++;
+                        do {
+                            uint32_t eb = min(run_end - run_start - 3, 3u);
+                            S.pfreq[16]++; S.items[ni++] = (uint16_t)(16 | (eb << 5)); run_start += 3 + eb;
+                        } while (run_end - run_start >= 3);
+                    }
+                    while (run_start != run_end) { S.pfreq[len]++; S.items[ni++] = (uint16_t)len; run_start++; }
+                } while (run_start != num_lens);
+#undef LENS_AT
+                S.nitems = ni;
+            }
+            __syncthreads();
+            make_huffman_code<uint16_t>(S, S.pfreq, kNumPrecode, kMaxPreCw, S.plen, S.pcw);
+            if (tid == 0) {
+                const uint8_t perm[19] = {16,17,18,0,8,7,9,6,10,5,11,4,12,3,13,2,14,1,15};
+                uint32_t nexpl = kNumPrecode;
+                while (nexpl > 4 && S.plen[perm[nexpl - 1]] == 0) nexpl--;
+                S.nexpl = nexpl;
+                uint32_t dyn = 3 + 5 + 5 + 4 + 3 * nexpl, stat = 3;
+                for (int s = 0; s < kNumPrecode; s++) {
+                    uint32_t extra = s == 16 ? 2 : s == 17 ? 3 : s == 18 ? 7 : 0;
+                    dyn += S.pfreq[s] * (extra + S.plen[s]);
+                }
+                S.cost_dyn = dyn; S.cost_static = stat;
+            }
+            __syncthreads();
+            {   // symbol costs (parallel)
+                uint32_t dyn = 0, stat = 0;
+                for (uint32_t s = tid; s < kNumLitlen; s += kEmitThreads) {
+                    uint32_t f = S.fl[s];
+                    if (s < 256) { dyn += f * ll[s]; stat += f * (s < 144 ? 8 : 9); }
+                    else if (s == 256) { dyn += ll[s]; stat += 7; }   // one end-of-block symbol
+                    else if (s < 286) {
+                        uint32_t k = s - 257;
+                        uint32_t extra = (k < 8 || k == 28) ? 0 : (k - 4) / 4;
+                        dyn += f * (extra + ll[s]); stat += f * (extra + c_static_litlen_len[s]);
+                    }
+                }
+                if (tid < 30) {
+                    uint32_t extra = tid < 4 ? 0 : (tid - 2) / 2;
+                    dyn += S.fo[tid] * (extra + ol[tid]); stat += S.fo[tid] * (extra + 5);
+                }
+                for (int o = 16; o; o >>= 1) { dyn += __shfl_xor_sync(0xFFFFFFFFu, dyn, o); stat += __shfl_xor_sync(0xFFFFFFFFu, stat, o); }
+                if ((tid & 31) == 0) { atomicAdd(&S.cost_dyn, dyn); atomicAdd(&S.cost_static, stat); }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                uint32_t bitcount = S.G & 7;
+                uint32_t unc = 3 + ((0u - (bitcount + 3)) & 7) + 32 + 40 * ((block_len + 65534) / 65535 - 1) + 8 * block_len;
+                uint32_t best = min(S.cost_dyn, min(S.cost_static, unc));
+                S.btype = (best == unc) ? 0 : (best == S.cost_static) ? 1 : 2;
+            }
+            __syncthreads();
+            const uint32_t btype = S.btype;
+            if (btype == 0) {
+                uint32_t pos = bb;
+                do {
+                    uint32_t len = min(be - pos, 65535u);
+                    uint32_t bfinal = (be - pos <= 65535u) ? is_final : 0u;
+                    // 3 header bits, pad to a byte boundary
+                    stage_begin(S, 4);
+                    uint32_t g0 = S.G & 31;
+                    uint32_t hb = 3 + ((0u - ((S.G & 7) + 3)) & 7);
+                    if (tid == 0) stage_put(S.stage, g0, bfinal, 3);
+                    stage_commit(S, payload, hb);
+                    uint32_t tot_bits = 32 + 8 * len;
+                    for (uint32_t cb = 0; cb < tot_bits;) {
+                        uint32_t chunk = min(tot_bits - cb, (uint32_t)(kStageWords - 4) * 32);
+                        stage_begin(S, kStageWords);
+                        g0 = S.G & 31;
+                        for (uint32_t bit = cb + tid * 8; bit < cb + chunk; bit += kEmitThreads * 8) {
+                            uint32_t v;
+                            if (bit < 16) v = (len >> bit) & 0xFF;
+                            else if (bit < 32) v = ((~len & 0xFFFF) >> (bit - 16)) & 0xFF;
+                            else v = in[pos + (bit - 32) / 8];
+                            stage_put(S.stage, g0 + (bit - cb), v, 8);
+                        }
+                        stage_commit(S, payload, chunk);
+                        cb += chunk;
+                    }
+                    pos += len;
+                } while (pos != be);
+            } else {
+                // ---- block header (thread 0) ----
+                stage_begin(S, kStageWords);
+                uint32_t hbits = 0;
+                if (tid == 0) {
+                    uint32_t g0 = S.G & 31, bp = g0;
+                    stage_put(S.stage, bp, is_final | (btype << 1), 3); bp += 3;
+                    if (btype == 2) {
+                        const uint8_t perm[19] = {16,17,18,0,8,7,9,6,10,5,11,4,12,3,13,2,14,1,15};
+                        stage_put(S.stage, bp, S.nlit - 257, 5); bp += 5;
+                        stage_put(S.stage, bp, S.noff - 1, 5); bp += 5;
+                        stage_put(S.stage, bp, S.nexpl - 4, 4); bp += 4;
+                        for (uint32_t i = 0; i < S.nexpl; i++) { stage_put(S.stage, bp, S.plen[perm[i]], 3); bp += 3; }
+                        for (uint32_t i = 0; i < S.nitems; i++) {
+                            uint32_t it = S.items[i], sym = it & 0x1F;
+                            uint32_t pl = S.plen[sym];
+                            stage_put(S.stage, bp, S.pcw[sym], pl); bp += pl;
+                            uint32_t extra = sym == 16 ? 2 : sym == 17 ? 3 : sym == 18 ? 7 : 0;
+                            stage_put(S.stage, bp, it >> 5, extra); bp += extra;
+                        }
+                    }
+                    S.scan[0] = bp - g0;
+                }
+                __syncthreads();
+                hbits = S.scan[0];
+                stage_commit(S, payload, hbits);
+                // ---- tokens (parallel) ----
+                const bool dynamic = (btype == 2);
+                for (uint32_t t0 = 0; t0 < ntok + 1; t0 += kChunkTok) {   // +1: the end-of-block symbol rides as a token
+                    stage_begin(S, kStageWords);
+                    uint64_t code[kTokPerThread]; uint32_t cl[kTokPerThread];
+                    uint32_t sum = 0;
+#pragma unroll
+                    for (int k = 0; k < kTokPerThread; k++) {
+                        uint32_t ti = t0 + tid * kTokPerThread + k;
+                        uint64_t c = 0; uint32_t l = 0;
+                        if (ti < ntok) {
+                            uint32_t t = tok[ti];
+                            if (!(t & 0x80000000u)) {
+                                c = dynamic ? S.lcw[t] : c_static_litlen_cw[t];
+                                l = dynamic ? ll[t] : c_static_litlen_len[t];
+                            } else {
+                                uint32_t len = (t >> 16) & 0x1FF, off = t & 0xFFFF;
+                                uint32_t ls, le, lv, os, oe, ov;
+                                len_slot(len, ls, le, lv); off_slot(off, os, oe, ov);
+                                uint32_t lsym = kFirstLenSym + ls;
+                                uint32_t lc = dynamic ? S.lcw[lsym] : c_static_litlen_cw[lsym];
+                                uint32_t lcl = dynamic ? ll[lsym] : c_static_litlen_len[lsym];
+                                uint32_t oc = dynamic ? S.ocw[os] : (__brev(os) >> 27);
+                                uint32_t ocl = dynamic ? ol[os] : 5;
+                                c = lc; l = lcl;
+                                c |= (uint64_t)lv << l; l += le;
+                                c |= (uint64_t)oc << l; l += ocl;
+                                c |= (uint64_t)ov << l; l += oe;
+                            }
+                        } else if (ti == ntok) {
+                            c = dynamic ? S.lcw[kEndOfBlock] : c_static_litlen_cw[kEndOfBlock];
+                            l = dynamic ? ll[kEndOfBlock] : c_static_litlen_len[kEndOfBlock];
+                        }
+                        code[k] = c; cl[k] = l; sum += l;
+                    }
+                    // block-wide exclusive scan of `sum`
+                    uint32_t incl = sum;
+                    for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if ((tid & 31) >= (uint32_t)o) incl += v; }
+                    if ((tid & 31) == 31) S.scan[tid >> 5] = incl;
+                    __syncthreads();
+                    uint32_t woff = 0, total = 0;
+                    for (int w = 0; w < kEmitThreads / 32; w++) { uint32_t v = S.scan[w]; if (w < (int)(tid >> 5)) woff += v; total += v; }
+                    uint32_t bp = (S.G & 31) + woff + incl - sum;
+#pragma unroll
+                    for (int k = 0; k < kTokPerThread; k++) { stage_put(S.stage, bp, code[k], cl[k]); bp += cl[k]; }
+                    stage_commit(S, payload, total);
+                }
+            }
+            p = be;   // (only thread 0's copy matters)
+            if (be >= n) break;
+        }
+    }
+
+    // ---- stream tail: sync-flush marker, final partial byte, container ----
+    if (sync_flush) {
+        stage_begin(S, 8);
+        uint32_t hb = 3 + ((0u - ((S.G & 7) + 3)) & 7);
+        stage_commit(S, payload, hb);            // 3 zero bits + padding
+        stage_begin(S, 8);
+        if (tid == 0) stage_put(S.stage, S.G & 31, 0xFFFF0000ull, 32);
+        stage_commit(S, payload, 32);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t G = S.G;
+        payload[G >> 5] = S.carry;               // upper bits are zero
+        uint32_t nbytes = (G + 7) >> 3;
+        uint32_t total = nbytes;
+        uint32_t hdr_off = kOutPayloadOff;
+        int32_t st = 0;
+        if (format == 4 || format == 3) {        // Bgzf / Mgzip member per unit
+            const uint32_t hs = format == 4 ? 18 : 20;
+            uint8_t *h = slot + kOutPayloadOff - hs;
+            hdr_off = kOutPayloadOff - hs;
+            uint32_t xfl = level >= 9 ? 2 : level <= 1 ? 4 : 0;
+            h[0] = 31; h[1] = 139; h[2] = 8; h[3] = 4; h[4] = h[5] = h[6] = h[7] = 0; h[8] = (uint8_t)xfl; h[9] = 255;
+            if (format == 4) {
+                h[10] = 6; h[11] = 0; h[12] = 'B'; h[13] = 'C'; h[14] = 2; h[15] = 0;
+                uint32_t bs = (uint16_t)((uint16_t)nbytes + 26 - 1);
+                h[16] = (uint8_t)bs; h[17] = (uint8_t)(bs >> 8);
+                if (nbytes >= 65536) st = -3;     // GZPB_EBLOCKSIZE (bgzf.rs:218-223)
+            } else {
+                h[10] = 8; h[11] = 0; h[12] = 'I'; h[13] = 'G'; h[14] = 4; h[15] = 0;
+                uint32_t bs = nbytes + 28;
+                h[16] = (uint8_t)bs; h[17] = (uint8_t)(bs >> 8); h[18] = (uint8_t)(bs >> 16); h[19] = (uint8_t)(bs >> 24);
+            }
+            uint8_t *f = slot + kOutPayloadOff + nbytes;
+            uint32_t crc = crc_in[u];
+            f[0] = (uint8_t)crc; f[1] = (uint8_t)(crc >> 8); f[2] = (uint8_t)(crc >> 16); f[3] = (uint8_t)(crc >> 24);
+            f[4] = (uint8_t)n; f[5] = (uint8_t)(n >> 8); f[6] = (uint8_t)(n >> 16); f[7] = (uint8_t)(n >> 24);
+            total = hs + nbytes + 8;
+            if (format == 4 && (flags & 1u)) {   // is_last: append BGZF_EOF (deflate.rs:622-624)
+                const uint8_t eof[28] = {0x1f,0x8b,0x08,0x04,0,0,0,0,0,0xff,0x06,0,0x42,0x43,0x02,0,0x1b,0,0x03,0,0,0,0,0,0,0,0,0};
+                for (int i = 0; i < 28; i++) f[8 + i] = eof[i];
+                total += 28;
+            }
+            uint32_t avail = n + max(128u, (uint32_t)((double)n * 0.1)) + 8;
+            if (nbytes > avail) st = -4;          // GZPB_ECOMPRESS: libdeflate would have returned 0
+        } else {
+            uint32_t avail = n + max(128u, (uint32_t)((double)n * 0.1));
+            if (nbytes > avail) st = -4;
+        }
+        out_len[u * 2] = total;
+        out_len[u * 2 + 1] = hdr_off;
+        out_status[u] = st;
+    }
+}
+
+// =============================================================================
+// k_scan: exclusive scan of the per-unit output sizes (single CTA).
+// k_gather: compaction of the fixed-stride unit slots into stream order.
+// =============================================================================
+__global__ void __launch_bounds__(1024)
+k_scan(const uint32_t *__restrict__ out_len, uint64_t *__restrict__ offsets, uint32_t nunits,
+       const uint64_t *__restrict__ base_ptr, uint64_t cap, int32_t *__restrict__ overflow)
+{
+    __shared__ uint64_t part[1024];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t per = (nunits + 1023) / 1024;
+    const uint64_t base = base_ptr ? *base_ptr : 0;
+    uint64_t s = 0;
+    for (uint32_t i = tid * per; i < min(nunits, (tid + 1) * per); i++) s += out_len[2 * i];
+    part[tid] = s;
+    __syncthreads();
+    if (tid == 0) {
+        uint64_t acc = base;
+        for (int i = 0; i < 1024; i++) { uint64_t v = part[i]; part[i] = acc; acc += v; }
+        offsets[nunits] = acc;
+        *overflow = (acc > cap) ? 1 : 0;
+    }
+    __syncthreads();
+    uint64_t acc = part[tid];
+    for (uint32_t i = tid * per; i < min(nunits, (tid + 1) * per); i++) { offsets[i] = acc; acc += out_len[2 * i]; }
+}
+
+__global__ void __launch_bounds__(256)
+k_gather(const uint8_t *__restrict__ out_base, const uint32_t *__restrict__ out_len, const uint64_t *__restrict__ offsets,
+         uint8_t *__restrict__ dst, const int32_t *__restrict__ overflow)
+{
+    const uint32_t u = blockIdx.x;
+    if (*overflow) return;
+    const uint32_t len = out_len[2 * u], hoff = out_len[2 * u + 1];
+    const uint8_t *src = out_base + (size_t)u * kOutStride + hoff;
+    uint8_t *d = dst + offsets[u];
+    // head bytes until d is 4-byte aligned
+    uint32_t head = min(len, (uint32_t)((4 - ((uintptr_t)d & 3)) & 3));
+    if (threadIdx.x < head) d[threadIdx.x] = src[threadIdx.x];
+    const uint8_t *s2 = src + head; uint8_t *d2 = d + head;
+    uint32_t rem = len - head, nw = rem >> 2;
+    const uint32_t *sw = (const uint32_t *)((uintptr_t)s2 & ~(uintptr_t)3);
+    uint32_t sh = ((uintptr_t)s2 & 3) * 8;
+    uint32_t *dw = (uint32_t *)d2;
+    for (uint32_t i = threadIdx.x; i < nw; i += blockDim.x) dw[i] = __funnelshift_r(sw[i], sw[i + 1], sh);
+    uint32_t tail = rem & 3;
+    if (threadIdx.x < tail) d2[nw * 4 + threadIdx.x] = s2[nw * 4 + threadIdx.x];
+}
+
+// =============================================================================
+// k_crc32: standalone CRC-32 of n bytes per unit (Check::update for the Gzip
+// format).  HBM-bound: one pass over the input, 512-byte chunks per thread.
+// =============================================================================
+__global__ void __launch_bounds__(256)
+k_crc32(const uint8_t *__restrict__ in_base, const uint32_t *__restrict__ unit_len, uint32_t *__restrict__ crc_out)
+{
+    __shared__ uint32_t s_crc;
+    __shared__ uint32_t s_tab[4][256];
+    const uint32_t u = blockIdx.x, tid = threadIdx.x;
+    const uint32_t n = unit_len[u];
+    const uint8_t *in = in_base + (size_t)u * kInStride;
+    const uint32_t *inw = (const uint32_t *)in;
+    for (uint32_t i = tid; i < 1024; i += 256) s_tab[i >> 8][i & 255] = c_crc_tab[i >> 8][i & 255];
+    if (tid == 0) s_crc = 0;
+    __syncthreads();
+    uint32_t acc = 0;
+    for (uint32_t j = tid; j * 512 < n; j += 256) {
+        uint32_t end = n - 512 * j, beg = end >= 512 ? end - 512 : 0;
+        uint32_t c = ~0u, pos = beg;
+        while (pos < end && (pos & 3)) { c = (c >> 8) ^ s_tab[0][(c ^ in[pos]) & 0xFF]; pos++; }
+        for (; pos + 4 <= end; pos += 4) {
+            c ^= __ldg(inw + (pos >> 2));
+            c = s_tab[3][c & 0xFF] ^ s_tab[2][(c >> 8) & 0xFF] ^ s_tab[1][(c >> 16) & 0xFF] ^ s_tab[0][c >> 24];
+        }
+        while (pos < end) { c = (c >> 8) ^ s_tab[0][(c ^ in[pos]) & 0xFF]; pos++; }
+        c = ~c;
+        acc ^= (j == 0) ? c : gf2_mulmod(c, c_xpow512[j], kCrcPoly);
+    }
+    for (int o = 16; o; o >>= 1) acc ^= __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+    if ((tid & 31) == 0 && acc) atomicXor(&s_crc, acc);
+    __syncthreads();
+    if (tid == 0) crc_out[u] = s_crc;
+}
+
+// ---------------------------------------------------------------------------
+// host-side launchers
+// ---------------------------------------------------------------------------
+static bool debug_sync() { static int v = -1; if (v < 0) { const char *e = getenv("GZPB_DEBUG_SYNC"); v = (e && *e == '1') ? 1 : 0; } return v == 1; }
+#define DBG_SYNC(name)                                                                        \
+    do {                                                                                      \
+        if (debug_sync()) {                                                                   \
+            cudaError_t e_ = cudaStreamSynchronize(st);                                       \
+            fprintf(stderr, "[gzpb] %s: %s\n", name, cudaGetErrorString(e_));                 \
+            if (e_ != cudaSuccess) return e_;                                                 \
+        }                                                                                     \
+    } while (0)
+
+cudaError_t launch_deflate_pipeline(const DeflateBatch &b, cudaStream_t st)
+{
+    static bool attr_done = false;
+    const int chain_smem = (65536 + 32768) * 2 + 4096;
+    const int match_smem = kInStride + 65536 * 2;
+    if (!attr_done) {
+        cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, chain_smem);
+        cudaFuncSetAttribute(k_match, cudaFuncAttributeMaxDynamicSharedMemorySize, match_smem);
+        attr_done = true;
+    }
+    if (b.nunits == 0) return cudaSuccess;
+    LevelParams lp;
+    if (!level_params(b.level, &lp)) return cudaErrorInvalidValue;
+    if (lp.mode >= 0) {
+        if (b.timer) b.timer->start(KT_CHAIN, st);
+        k_chain<<<b.nunits, kChainThreads, chain_smem, st>>>(b.in, b.unit_len, b.next4, b.prev3, b.crc);
+        DBG_SYNC("k_chain");
+        if (b.timer) { b.timer->stop(st); b.timer->start(KT_MATCH, st); }
+        k_match<<<b.nunits, kMatchThreads, match_smem, st>>>(b.in, b.unit_len, b.next4, b.prev3, b.mtab, lp.depth, lp.nice, lp.mode >= 1);
+        DBG_SYNC("k_match");
+        if (b.timer) b.timer->stop(st);
+    } else {
+        if (b.timer) b.timer->start(KT_CRC, st);
+        k_crc32<<<b.nunits, 256, 0, st>>>(b.in, b.unit_len, b.crc);
+        if (b.timer) b.timer->stop(st);
+    }
+    if (b.timer) b.timer->start(KT_EMIT, st);
+    k_emit<<<b.nunits, kEmitThreads, 0, st>>>(b.in, b.unit_len, b.unit_flags, b.mtab, b.crc, b.tokens, b.out, b.out_len,
+                                             b.status, lp.mode, lp.depth, lp.nice, b.level, b.format);
+    DBG_SYNC("k_emit");
+    if (b.timer) b.timer->stop(st);
+    return cudaGetLastError();
+}
+
+// scan + gather are launched separately so that the caller can order them
+// after the previous batch's scan (stream offsets chain from batch to batch).
+cudaError_t launch_pack(const DeflateBatch &b, cudaStream_t st)
+{
+    if (b.nunits == 0) return cudaSuccess;
+    if (b.timer) b.timer->start(KT_GATHER, st);
+    k_scan<<<1, 1024, 0, st>>>(b.out_len, b.offsets, b.nunits, b.base_ptr, b.packed_cap, b.overflow);
+    k_gather<<<b.nunits, 256, 0, st>>>(b.out, b.out_len, b.offsets, b.packed, b.overflow);
+    DBG_SYNC("k_scan+k_gather");
+    if (b.timer) b.timer->stop(st);
+    return cudaGetLastError();
+}
+
+}  // namespace gzpb

@@ -1,0 +1,61 @@
+// deflate_kernels.cuh — host-visible launch interface of the DEFLATE pipeline.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <vector>
+
+namespace gzpb {
+
+enum KernelId { KT_CHAIN = 0, KT_MATCH, KT_EMIT, KT_GATHER, KT_CRC, KT_SNAP, KT_COUNT };
+
+// CUDA-event timing of individual kernels on their launching stream.
+struct KernelTimer {
+    struct Rec { int id; cudaEvent_t a, b; };
+    std::vector<Rec> pending;
+    std::vector<cudaEvent_t> pool;
+    double total_ms[KT_COUNT] = {0};
+    uint64_t launches[KT_COUNT] = {0};
+    cudaEvent_t get() { if (pool.empty()) { cudaEvent_t e; cudaEventCreate(&e); return e; } cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+    void start(int id, cudaStream_t st) { Rec r{id, get(), get()}; cudaEventRecord(r.a, st); pending.push_back(r); }
+    void stop(cudaStream_t st) { cudaEventRecord(pending.back().b, st); }
+    // call after the stream work has completed
+    void collect() {
+        for (auto &r : pending) {
+            float ms = 0; if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { total_ms[r.id] += ms; launches[r.id]++; }
+            pool.push_back(r.a); pool.push_back(r.b);
+        }
+        pending.clear();
+    }
+    void reset() { collect(); for (int i = 0; i < KT_COUNT; i++) { total_ms[i] = 0; launches[i] = 0; } }
+};
+
+// Device arrays of one batch (all fixed-stride per unit, see gzpb_common.cuh).
+struct DeflateBatch {
+    uint32_t nunits;
+    int level;
+    int format;               // gzpb_format
+    const uint8_t *in;        // nunits * kInStride
+    const uint32_t *unit_len; // nunits
+    const uint32_t *unit_flags;  // bit0 = is_last (BGZF EOF), bit1 = sync flush (no BFINAL)
+    uint16_t *next4;          // nunits * 65536
+    uint16_t *prev3;          // nunits * 65536
+    uint64_t *mtab;           // nunits * 65536
+    uint32_t *crc;            // nunits
+    uint32_t *tokens;         // nunits * kTokStride
+    uint8_t *out;             // nunits * kOutStride
+    uint32_t *out_len;        // nunits * 2  (total bytes, header offset in the slot)
+    int32_t *status;          // nunits
+    uint64_t *offsets;        // nunits + 1 (exclusive scan of sizes; [nunits] = total)
+    uint8_t *packed;          // compacted stream (device memory or mapped pinned host memory)
+    uint64_t packed_cap;      // bytes available at `packed`
+    const uint64_t *base_ptr; // device address holding this batch's first offset (NULL = 0)
+    int32_t *overflow;        // set to 1 by k_scan when the batch would exceed packed_cap
+    KernelTimer *timer;       // optional
+};
+
+void upload_deflate_constants();
+cudaError_t launch_deflate_pipeline(const DeflateBatch &b, cudaStream_t st);
+cudaError_t launch_pack(const DeflateBatch &b, cudaStream_t st);
+
+}  // namespace gzpb

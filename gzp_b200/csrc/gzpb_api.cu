@@ -1,0 +1,580 @@
+// gzpb_api.cu — C-ABI implementation (include/gzpb.h): device context, batch
+// staging (pinned memory, H2D/D2H overlap across lanes), per-format unit
+// preparation, and the host-side FormatSpec helpers (header / footer / combine).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../../include/gzpb.h"
+#include "deflate_kernels.cuh"
+#include "gzpb_common.cuh"
+
+using namespace gzpb;
+
+#define CK(x)                                                                              \
+    do {                                                                                   \
+        cudaError_t e_ = (x);                                                              \
+        if (e_ != cudaSuccess) {                                                           \
+            snprintf(g_last_cuda_error, sizeof g_last_cuda_error, "%s at %s:%d", cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return GZPB_ECUDA;                                                             \
+        }                                                                                  \
+    } while (0)
+
+static thread_local char g_last_cuda_error[256];
+
+namespace {
+
+constexpr int kLanes = 3;
+
+struct Lane {
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev_scan = nullptr, ev_done = nullptr;
+    // device
+    uint8_t *d_in = nullptr;
+    uint32_t *d_len = nullptr, *d_flags = nullptr, *d_crc = nullptr, *d_tokens = nullptr, *d_out_len = nullptr;
+    uint16_t *d_next4 = nullptr, *d_prev3 = nullptr;
+    uint64_t *d_mtab = nullptr, *d_offsets = nullptr;
+    uint8_t *d_out = nullptr, *d_packed = nullptr;
+    int32_t *d_status = nullptr, *d_overflow = nullptr;
+    // pinned host
+    uint8_t *h_in = nullptr, *h_packed = nullptr;
+    uint32_t *h_len = nullptr, *h_flags = nullptr, *h_crc = nullptr;
+    uint64_t *h_offsets = nullptr;
+    int32_t *h_status = nullptr, *h_overflow = nullptr;
+    size_t nunits = 0;
+    bool busy = false;
+};
+
+}  // namespace
+
+struct gzpb_ctx {
+    int device = 0, format = 0, level = 0;
+    size_t max_block_bytes = 0, max_units = 0;
+    Lane lanes[kLanes];
+    bool scratch_only = false;
+    KernelTimer timer;
+    bool profiling = false;
+    uint64_t launches = 0;
+};
+
+static bool is_deflate_format(int f) { return f == GZPB_GZIP || f == GZPB_ZLIB || f == GZPB_RAWDEFLATE || f == GZPB_MGZIP || f == GZPB_BGZF; }
+
+static size_t extra_amount(size_t n) { size_t e = (size_t)((double)n * 0.1); return e > 128 ? e : 128; }
+
+extern "C" size_t gzpb_encode_capacity(int format, size_t n)
+{
+    switch (format) {
+    case GZPB_BGZF: return 18 + n + extra_amount(n) + 8 + 28;
+    case GZPB_MGZIP: return 20 + n + extra_amount(n) + 8;
+    case GZPB_SNAP: return 10 + ((n + 65535) / 65536) * 8 + (32 + n + n / 6) + 64;
+    default: return n + extra_amount(n);
+    }
+}
+
+extern "C" size_t gzpb_default_bufsize(int format) { return format == GZPB_BGZF ? GZPB_BGZF_BLOCK_SIZE : GZPB_BUFSIZE; }
+extern "C" int gzpb_needs_dict(int format) { return format == GZPB_GZIP || format == GZPB_ZLIB || format == GZPB_RAWDEFLATE; }
+
+extern "C" int gzpb_level_supported(int format, int level)
+{
+    if (format == GZPB_SNAP) return 1;
+    LevelParams lp;
+    return level_params(level, &lp) ? 1 : 0;
+}
+
+static int xfl(int level) { return level >= 9 ? 2 : level <= 1 ? 4 : 0; }
+
+extern "C" size_t gzpb_header(int format, int level, void *buf)
+{
+    uint8_t *o = (uint8_t *)buf;
+    if (format == GZPB_GZIP) {
+        const uint8_t h[10] = {31, 139, 8, 0, 0, 0, 0, 0, (uint8_t)xfl(level), 255};
+        memcpy(o, h, 10);
+        return 10;
+    }
+    if (format == GZPB_ZLIB) {
+        uint32_t cv = level >= 9 ? 3u << 6 : level == 1 ? 0 : level >= 6 ? 1u << 6 : 2u << 6;
+        uint32_t head = (0x78u << 8) + cv;
+        head += 31 - (head % 31);
+        o[0] = (uint8_t)(head >> 8); o[1] = (uint8_t)head;
+        return 2;
+    }
+    return 0;
+}
+
+extern "C" size_t gzpb_footer(int format, uint32_t sum, uint32_t amount, void *buf)
+{
+    uint8_t *o = (uint8_t *)buf;
+    if (format == GZPB_GZIP) {
+        for (int i = 0; i < 4; i++) { o[i] = (uint8_t)(sum >> (8 * i)); o[4 + i] = (uint8_t)(amount >> (8 * i)); }
+        return 8;
+    }
+    if (format == GZPB_ZLIB) {
+        for (int i = 0; i < 4; i++) o[i] = (uint8_t)(sum >> (24 - 8 * i));
+        return 4;
+    }
+    return 0;
+}
+
+extern "C" uint32_t gzpb_crc32_combine(uint32_t a, uint32_t b, uint64_t len_b)
+{
+    if (len_b == 0) return a;
+    return gf2_mulmod(a, gf2_xpow8(len_b, kCrcPoly), kCrcPoly) ^ b;
+}
+
+extern "C" uint32_t gzpb_adler32_combine(uint32_t a1, uint32_t a2, uint64_t len2)
+{
+    const uint32_t BASE = 65521u;
+    uint32_t rem = (uint32_t)(len2 % BASE);
+    uint32_t sum1 = a1 & 0xFFFF;
+    uint32_t sum2 = (rem * sum1) % BASE;
+    sum1 += (a2 & 0xFFFF) + BASE - 1;
+    sum2 += (a1 >> 16) + (a2 >> 16) + BASE - rem;
+    if (sum1 >= BASE) sum1 -= BASE;
+    if (sum1 >= BASE) sum1 -= BASE;
+    if (sum2 >= (BASE << 1)) sum2 -= (BASE << 1);
+    if (sum2 >= BASE) sum2 -= BASE;
+    return sum1 | (sum2 << 16);
+}
+
+extern "C" const char *gzpb_strerror(int code)
+{
+    switch (code) {
+    case GZPB_OK: return "ok";
+    case GZPB_EBUFFERSIZE: return "Invalid buffer size, must be >= 32768";
+    case GZPB_ENUMTHREADS: return "Invalid number of threads selected";
+    case GZPB_EBLOCKSIZE: return "Compressed block size exceeds max allowed (65536), try increasing compression";
+    case GZPB_ECOMPRESS: return "compression error: insufficient space in the output buffer";
+    case GZPB_ELEVEL: return "compression level not supported by the B200 engine";
+    case GZPB_EIO: return "io error";
+    case GZPB_ECHANNEL: return "failed to send over channel (stream finished)";
+    case GZPB_ECUDA: return g_last_cuda_error[0] ? g_last_cuda_error : "CUDA error";
+    case GZPB_EINVAL: return "invalid argument";
+    case GZPB_ENOMEM: return "out of memory";
+    default: return "unknown";
+    }
+}
+
+extern "C" const char *gzpb_version(void) { return "gzp-b200 0.1 (sm_100a)"; }
+
+extern "C" void *gzpb_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) return nullptr;
+    return p;
+}
+extern "C" void gzpb_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+template <typename T>
+static cudaError_t dmalloc(T **p, size_t count) { return cudaMalloc((void **)p, count * sizeof(T)); }
+template <typename T>
+static cudaError_t hmalloc(T **p, size_t count) { return cudaHostAlloc((void **)p, count * sizeof(T), cudaHostAllocPortable | cudaHostAllocMapped); }
+
+static int lane_alloc(gzpb_ctx *c, Lane &L, bool with_io)
+{
+    const size_t U = c->max_units;
+    CK(cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&L.ev_scan, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&L.ev_done, cudaEventDisableTiming));
+    CK(dmalloc(&L.d_next4, U * kMaxUnitBytes));
+    CK(dmalloc(&L.d_prev3, U * kMaxUnitBytes));
+    CK(dmalloc(&L.d_mtab, U * kMaxUnitBytes));
+    CK(dmalloc(&L.d_crc, U));
+    CK(dmalloc(&L.d_tokens, U * kTokStride));
+    CK(dmalloc(&L.d_out, U * kOutStride + 256));
+    CK(dmalloc(&L.d_out_len, U * 2));
+    CK(dmalloc(&L.d_overflow, 1));
+    CK(cudaMemset(L.d_overflow, 0, sizeof(int32_t)));
+    if (with_io) {
+        CK(dmalloc(&L.d_in, U * kInStride + 256));
+        CK(dmalloc(&L.d_len, U));
+        CK(dmalloc(&L.d_flags, U));
+        CK(dmalloc(&L.d_offsets, U + 1));
+        CK(dmalloc(&L.d_status, U));
+        CK(hmalloc(&L.h_len, U));
+        CK(hmalloc(&L.h_flags, U));
+        CK(hmalloc(&L.h_crc, U));
+        CK(hmalloc(&L.h_offsets, U + 1));
+        CK(hmalloc(&L.h_status, U));
+        CK(hmalloc(&L.h_overflow, 1));
+        CK(hmalloc(&L.h_packed, U * kOutStride));
+    }
+    return GZPB_OK;
+}
+
+static void lane_free(Lane &L)
+{
+    cudaFree(L.d_in); cudaFree(L.d_len); cudaFree(L.d_flags); cudaFree(L.d_crc); cudaFree(L.d_tokens); cudaFree(L.d_out_len);
+    cudaFree(L.d_next4); cudaFree(L.d_prev3); cudaFree(L.d_mtab); cudaFree(L.d_offsets); cudaFree(L.d_out); cudaFree(L.d_packed);
+    cudaFree(L.d_status); cudaFree(L.d_overflow);
+    cudaFreeHost(L.h_in); cudaFreeHost(L.h_packed); cudaFreeHost(L.h_len); cudaFreeHost(L.h_flags); cudaFreeHost(L.h_crc);
+    cudaFreeHost(L.h_offsets); cudaFreeHost(L.h_status); cudaFreeHost(L.h_overflow);
+    if (L.ev_scan) cudaEventDestroy(L.ev_scan);
+    if (L.ev_done) cudaEventDestroy(L.ev_done);
+    if (L.st) cudaStreamDestroy(L.st);
+    L = Lane();
+}
+
+extern "C" int gzpb_create(gzpb_ctx **out, int device, int format, int level, size_t max_block_bytes,
+                           size_t max_blocks_in_flight)
+{
+    if (!out) return GZPB_EINVAL;
+    *out = nullptr;
+    if (format < GZPB_GZIP || format > GZPB_SNAP) return GZPB_EINVAL;
+    if (!gzpb_level_supported(format, level)) return GZPB_ELEVEL;
+    if (max_block_bytes == 0) max_block_bytes = gzpb_default_bufsize(format);
+    if (max_blocks_in_flight == 0) max_blocks_in_flight = 1024;
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) { snprintf(g_last_cuda_error, sizeof g_last_cuda_error, "no CUDA device %d", device); return GZPB_ECUDA; }
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        snprintf(g_last_cuda_error, sizeof g_last_cuda_error, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+        return GZPB_ECUDA;
+    }
+    if (format == GZPB_SNAP || format == GZPB_ZLIB) return GZPB_EINVAL;  // (not wired yet)
+    size_t dict = gzpb_needs_dict(format) ? GZPB_DICT_SIZE : 0;
+    if (max_block_bytes + dict > kMaxUnitBytes) return GZPB_EBUFFERSIZE;
+    gzpb_ctx *c = new gzpb_ctx();
+    c->device = device; c->format = format; c->level = level;
+    c->max_block_bytes = max_block_bytes; c->max_units = max_blocks_in_flight;
+    upload_deflate_constants();
+    for (int i = 0; i < kLanes; i++) {
+        int r = lane_alloc(c, c->lanes[i], true);
+        if (r != GZPB_OK) { gzpb_destroy(c); return r; }
+    }
+    CK(cudaDeviceSynchronize());
+    *out = c;
+    return GZPB_OK;
+}
+
+extern "C" void gzpb_destroy(gzpb_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < kLanes; i++) lane_free(c->lanes[i]);
+    c->timer.collect();
+    for (auto e : c->timer.pool) cudaEventDestroy(e);
+    delete c;
+}
+
+extern "C" int gzpb_set_profiling(gzpb_ctx *c, int on)
+{
+    if (!c) return GZPB_EINVAL;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    c->timer.reset();
+    c->profiling = on != 0;
+    return GZPB_OK;
+}
+
+extern "C" int gzpb_kernel_ms(gzpb_ctx *c, const char *name, double *total_ms, uint64_t *launches)
+{
+    static const char *names[KT_COUNT] = {"chain", "match", "emit", "gather", "crc", "snap"};
+    if (!c || !name) return GZPB_EINVAL;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    c->timer.collect();
+    for (int i = 0; i < KT_COUNT; i++)
+        if (!strcmp(name, names[i])) {
+            if (total_ms) *total_ms = c->timer.total_ms[i];
+            if (launches) *launches = c->timer.launches[i];
+            return GZPB_OK;
+        }
+    return GZPB_EINVAL;
+}
+
+extern "C" uint64_t gzpb_launch_count(gzpb_ctx *c) { return c ? c->launches : 0; }
+
+static uint32_t unit_flags_for(int format, int is_last)
+{
+    switch (format) {
+    case GZPB_BGZF: return is_last ? 1u : 0u;
+    case GZPB_MGZIP: return 0u;
+    case GZPB_RAWDEFLATE: return 2u;                      // always Z_SYNC_FLUSH (deflate.rs:319-320)
+    default: return is_last ? 0u : 2u;                    // Gzip / Zlib: Sync unless last (deflate.rs:96-100)
+    }
+}
+
+static void fill_batch(gzpb_ctx *c, Lane &L, DeflateBatch &b, size_t n)
+{
+    b.nunits = (uint32_t)n; b.level = c->level; b.format = c->format;
+    b.in = L.d_in; b.unit_len = L.d_len; b.unit_flags = L.d_flags;
+    b.next4 = L.d_next4; b.prev3 = L.d_prev3; b.mtab = L.d_mtab; b.crc = L.d_crc; b.tokens = L.d_tokens;
+    b.out = L.d_out; b.out_len = L.d_out_len; b.status = L.d_status; b.offsets = L.d_offsets;
+    b.packed = nullptr; b.packed_cap = 0; b.base_ptr = nullptr; b.overflow = L.d_overflow;
+    b.timer = c->profiling ? &c->timer : nullptr;
+}
+
+static bool is_pinned(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+extern "C" int gzpb_encode_device(gzpb_ctx *c, const void *d_in, const uint32_t *d_len, const uint32_t *d_flags,
+                                  size_t nunits, void *d_packed, uint64_t *d_offsets, int32_t *d_status,
+                                  void *cuda_stream)
+{
+    if (!c || !is_deflate_format(c->format)) return GZPB_EINVAL;
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    Lane &L = c->lanes[0];
+    CK(cudaMemsetAsync(d_offsets, 0, sizeof(uint64_t), st));
+    for (size_t done = 0; done < nunits; done += c->max_units) {
+        size_t n = std::min(c->max_units, nunits - done);
+        DeflateBatch b;
+        fill_batch(c, L, b, n);
+        b.in = (const uint8_t *)d_in + done * kInStride; b.unit_len = d_len + done; b.unit_flags = d_flags + done;
+        b.status = d_status + done; b.offsets = d_offsets + done; b.base_ptr = d_offsets + done;
+        b.packed = (uint8_t *)d_packed; b.packed_cap = ~0ull;
+        CK(launch_deflate_pipeline(b, st));
+        CK(launch_pack(b, st));
+        c->launches += 5;
+    }
+    return GZPB_OK;
+}
+
+// ---- host-buffer paths ---------------------------------------------------------
+namespace {
+struct UnitRef { const uint8_t *ptr; size_t len; const uint8_t *dict; size_t dict_len; int is_last; };
+}
+
+// Launch one batch on a lane: H2D + kernels (+ scan/gather when `packed` is given).
+static int lane_launch(gzpb_ctx *c, Lane &L, const UnitRef *units, size_t n, const uint8_t *contig_src, size_t contig_pitch,
+                       bool src_pinned)
+{
+    for (size_t i = 0; i < n; i++) {
+        L.h_len[i] = (uint32_t)(units[i].dict_len + units[i].len);
+        L.h_flags[i] = unit_flags_for(c->format, units[i].is_last);
+    }
+    if (contig_src && src_pinned && n > 0) {
+        // blocks are consecutive slices of one pinned buffer: one strided DMA
+        size_t full = n;
+        size_t last_len = units[n - 1].len;
+        if (last_len != contig_pitch) full = n - 1;
+        if (full) CK(cudaMemcpy2DAsync(L.d_in, kInStride, contig_src, contig_pitch, contig_pitch, full, cudaMemcpyHostToDevice, L.st));
+        if (full != n && last_len) CK(cudaMemcpyAsync(L.d_in + full * kInStride, units[n - 1].ptr, last_len, cudaMemcpyHostToDevice, L.st));
+    } else {
+        if (!L.h_in) CK(cudaHostAlloc((void **)&L.h_in, c->max_units * (size_t)kInStride, cudaHostAllocPortable));
+        size_t used = 0;
+        for (size_t i = 0; i < n; i++) {
+            uint8_t *dst = L.h_in + i * kInStride;
+            if (units[i].dict_len) memcpy(dst, units[i].dict, units[i].dict_len);
+            if (units[i].len) memcpy(dst + units[i].dict_len, units[i].ptr, units[i].len);
+            used = (i + 1) * (size_t)kInStride;
+        }
+        if (used) CK(cudaMemcpyAsync(L.d_in, L.h_in, used, cudaMemcpyHostToDevice, L.st));
+    }
+    CK(cudaMemcpyAsync(L.d_len, L.h_len, n * sizeof(uint32_t), cudaMemcpyHostToDevice, L.st));
+    CK(cudaMemcpyAsync(L.d_flags, L.h_flags, n * sizeof(uint32_t), cudaMemcpyHostToDevice, L.st));
+    DeflateBatch b;
+    fill_batch(c, L, b, n);
+    CK(launch_deflate_pipeline(b, L.st));
+    c->launches += 3;
+    L.nunits = n; L.busy = true;
+    return GZPB_OK;
+}
+
+// scan + gather into `packed` (device-visible), chained after `prev` lane's scan
+static int lane_pack(gzpb_ctx *c, Lane &L, uint8_t *packed, uint64_t cap, const uint64_t *base_ptr, Lane *prev)
+{
+    DeflateBatch b;
+    fill_batch(c, L, b, L.nunits);
+    b.packed = packed; b.packed_cap = cap; b.base_ptr = base_ptr;
+    if (prev) CK(cudaStreamWaitEvent(L.st, prev->ev_scan, 0));
+    CK(launch_pack(b, L.st));
+    CK(cudaEventRecord(L.ev_scan, L.st));
+    c->launches += 2;
+    CK(cudaMemcpyAsync(L.h_offsets, L.d_offsets, (L.nunits + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, L.st));
+    CK(cudaMemcpyAsync(L.h_status, L.d_status, L.nunits * sizeof(int32_t), cudaMemcpyDeviceToHost, L.st));
+    CK(cudaMemcpyAsync(L.h_crc, L.d_crc, L.nunits * sizeof(uint32_t), cudaMemcpyDeviceToHost, L.st));
+    CK(cudaMemcpyAsync(L.h_overflow, L.d_overflow, sizeof(int32_t), cudaMemcpyDeviceToHost, L.st));
+    CK(cudaEventRecord(L.ev_done, L.st));
+    return GZPB_OK;
+}
+
+static int lane_wait(gzpb_ctx *c, Lane &L)
+{
+    CK(cudaEventSynchronize(L.ev_done));
+    if (c->profiling) c->timer.collect();
+    L.busy = false;
+    return GZPB_OK;
+}
+
+extern "C" int gzpb_encode_batch(gzpb_ctx *c, size_t n, const gzpb_block_in *in, gzpb_block_out *out)
+{
+    if (!c || (n && (!in || !out))) return GZPB_EINVAL;
+    if (!is_deflate_format(c->format)) return GZPB_EINVAL;
+    CK(cudaSetDevice(c->device));
+    const bool dict_fmt = gzpb_needs_dict(c->format);
+    for (size_t i = 0; i < n; i++) {
+        size_t dl = (dict_fmt && in[i].dict) ? in[i].dict_len : 0;
+        if (in[i].len + dl > kMaxUnitBytes || in[i].len > c->max_block_bytes) return GZPB_EBUFFERSIZE;
+        if (out[i].cap < gzpb_encode_capacity(c->format, in[i].len)) return GZPB_EINVAL;
+    }
+    int rc = GZPB_OK;
+    std::vector<UnitRef> units;
+    size_t done = 0;
+    int li = 0;
+    struct Pending { size_t first, count; int lane; };
+    std::vector<Pending> pend;
+    auto retire = [&](const Pending &p) -> int {
+        Lane &L = c->lanes[p.lane];
+        int r = lane_wait(c, L);
+        if (r != GZPB_OK) return r;
+        if (*L.h_overflow) return GZPB_ECUDA;
+        for (size_t i = 0; i < p.count; i++) {
+            gzpb_block_out &o = out[p.first + i];
+            o.status = L.h_status[i];
+            size_t len = (size_t)(L.h_offsets[i + 1] - L.h_offsets[i]);
+            o.out_len = 0; o.check_sum = 0; o.check_amount = 0;
+            if (o.status == GZPB_OK) {
+                if (len > o.cap) { o.status = GZPB_ECOMPRESS; continue; }
+                memcpy(o.dst, L.h_packed + L.h_offsets[i], len);
+                o.out_len = len;
+                if (c->format == GZPB_GZIP) { o.check_sum = L.h_crc[i]; o.check_amount = (uint32_t)in[p.first + i].len; }
+            }
+        }
+        return GZPB_OK;
+    };
+    while (done < n) {
+        size_t cnt = std::min(c->max_units, n - done);
+        Lane &L = c->lanes[li];
+        if (L.busy) {
+            rc = retire(pend.front()); pend.erase(pend.begin());
+            if (rc != GZPB_OK) return rc;
+        }
+        units.resize(cnt);
+        for (size_t i = 0; i < cnt; i++) {
+            const gzpb_block_in &b = in[done + i];
+            size_t dl = (dict_fmt && b.dict) ? b.dict_len : 0;
+            units[i] = UnitRef{(const uint8_t *)b.ptr, b.len, (const uint8_t *)b.dict, dl, b.is_last};
+        }
+        rc = lane_launch(c, L, units.data(), cnt, nullptr, 0, false);
+        if (rc != GZPB_OK) return rc;
+        rc = lane_pack(c, L, L.h_packed, (uint64_t)c->max_units * kOutStride, nullptr, nullptr);
+        if (rc != GZPB_OK) return rc;
+        pend.push_back(Pending{done, cnt, li});
+        done += cnt;
+        li = (li + 1) % kLanes;
+    }
+    for (auto &p : pend) { rc = retire(p); if (rc != GZPB_OK) return rc; }
+    return GZPB_OK;
+}
+
+extern "C" int gzpb_encode_stream(gzpb_ctx *c, const void *in_v, size_t in_len, size_t buffer_size, void *out_v,
+                                  size_t out_cap, size_t *out_len)
+{
+    if (!c || !out_v || !out_len || (in_len && !in_v)) return GZPB_EINVAL;
+    if (!is_deflate_format(c->format)) return GZPB_EINVAL;
+    if (buffer_size == 0) buffer_size = c->max_block_bytes;
+    if (buffer_size < GZPB_DICT_SIZE) return GZPB_EBUFFERSIZE;   // par/compress.rs:68-74
+    if (buffer_size > c->max_block_bytes) return GZPB_EBUFFERSIZE;
+    CK(cudaSetDevice(c->device));
+    const uint8_t *in = (const uint8_t *)in_v;
+    uint8_t *out = (uint8_t *)out_v;
+    const bool dict_fmt = gzpb_needs_dict(c->format);
+    const bool in_pinned = in_len && is_pinned(in) && !dict_fmt;
+    const bool out_pinned = is_pinned(out);
+
+    // ParCompress::write + finish: full blocks while MORE than buffer_size bytes remain,
+    // then flush_last(true) — always at least one (possibly empty) is_last block.
+    size_t nblocks = 0;
+    { size_t rem = in_len; while (rem > buffer_size) { rem -= buffer_size; nblocks++; } nblocks++; }
+
+    if (out_cap < 64) return GZPB_ECOMPRESS;
+    size_t pos_out = gzpb_header(c->format, c->level, out);
+    uint8_t *dev_out = nullptr;
+    if (out_pinned) CK(cudaHostGetDevicePointer((void **)&dev_out, out, 0));
+
+    // device-side running offset lives in each lane's d_offsets[nunits]; batch 0 starts at the header size
+    uint64_t *d_base0 = nullptr;
+    CK(cudaMalloc((void **)&d_base0, sizeof(uint64_t)));
+    uint64_t base0 = out_pinned ? pos_out : 0;
+    CK(cudaMemcpy(d_base0, &base0, sizeof base0, cudaMemcpyHostToDevice));
+
+    struct Pending { size_t first, count; int lane; };
+    std::vector<Pending> pend;
+    std::vector<UnitRef> units;
+    uint32_t run_sum = (c->format == GZPB_ZLIB) ? 1u : 0u, run_amount = 0;
+    int rc = GZPB_OK;
+    Lane *prev = nullptr;
+    const uint64_t *prev_end = d_base0;
+
+    auto retire = [&](const Pending &p) -> int {
+        Lane &L = c->lanes[p.lane];
+        int r = lane_wait(c, L);
+        if (r != GZPB_OK) return r;
+        if (*L.h_overflow) return GZPB_ECOMPRESS;
+        for (size_t i = 0; i < p.count; i++) {
+            if (L.h_status[i] != GZPB_OK) return L.h_status[i];
+            if (c->format == GZPB_GZIP) {
+                size_t blen = L.h_len[i] - 0;
+                // (dictionary bytes are not part of the block's check)
+                size_t b0 = (p.first + i) * buffer_size;
+                size_t real = std::min(buffer_size, in_len - std::min(in_len, b0));
+                (void)blen;
+                run_sum = gzpb_crc32_combine(run_sum, L.h_crc[i], real);
+                run_amount += (uint32_t)real;
+            }
+        }
+        if (out_pinned) {
+            pos_out = (size_t)L.h_offsets[p.count];
+        } else {
+            size_t len = (size_t)L.h_offsets[p.count];
+            if (pos_out + len > out_cap) return GZPB_ECOMPRESS;
+            memcpy(out + pos_out, L.h_packed, len);
+            pos_out += len;
+        }
+        return GZPB_OK;
+    };
+
+    size_t done = 0;
+    int li = 0;
+    while (done < nblocks && rc == GZPB_OK) {
+        size_t cnt = std::min(c->max_units, nblocks - done);
+        Lane &L = c->lanes[li];
+        if (L.busy) {
+            rc = retire(pend.front()); pend.erase(pend.begin());
+            if (rc != GZPB_OK) break;
+        }
+        units.resize(cnt);
+        for (size_t i = 0; i < cnt; i++) {
+            size_t bi = done + i, b0 = bi * buffer_size;
+            size_t len = (bi + 1 == nblocks) ? in_len - b0 : buffer_size;
+            const uint8_t *d = (dict_fmt && bi > 0) ? in + b0 - GZPB_DICT_SIZE : nullptr;
+            units[i] = UnitRef{in + b0, len, d, d ? (size_t)GZPB_DICT_SIZE : 0, bi + 1 == nblocks};
+        }
+        rc = lane_launch(c, L, units.data(), cnt, in_pinned ? in + done * buffer_size : nullptr, buffer_size, in_pinned);
+        if (rc != GZPB_OK) break;
+        if (out_pinned) rc = lane_pack(c, L, dev_out, out_cap, prev_end, prev);
+        else rc = lane_pack(c, L, L.h_packed, (uint64_t)c->max_units * kOutStride, nullptr, nullptr);
+        if (rc != GZPB_OK) break;
+        prev = &L; prev_end = L.d_offsets + cnt;
+        pend.push_back(Pending{done, cnt, li});
+        done += cnt;
+        li = (li + 1) % kLanes;
+    }
+    for (auto &p : pend) {
+        int r = retire(p);
+        if (rc == GZPB_OK) rc = r;
+    }
+    cudaFree(d_base0);
+    if (rc != GZPB_OK) { for (int i = 0; i < kLanes; i++) c->lanes[i].busy = false; cudaDeviceSynchronize(); return rc; }
+    uint8_t foot[16];
+    size_t fl = gzpb_footer(c->format, run_sum, run_amount, foot);
+    if (pos_out + fl > out_cap) return GZPB_ECOMPRESS;
+    memcpy(out + pos_out, foot, fl);
+    pos_out += fl;
+    *out_len = pos_out;
+    return GZPB_OK;
+}

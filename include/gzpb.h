@@ -1,0 +1,142 @@
+/*
+ * gzpb.h — C ABI of the B200-native per-block encode path for gzp.
+ *
+ * This is the drop-in boundary: the entry points a Rust `FormatSpec` impl (or the
+ * worker loop of gzp's ParCompress) would bind over FFI instead of calling
+ * libdeflate / zlib-ng / snap on a CPU thread.  Plain C types only; no CUDA or
+ * torch types cross the boundary (streams and device pointers travel as void*).
+ * Every entry point cites the reference interface it replaces
+ * (paths relative to the reference repo sstadick/gzp v2.0.1).
+ *
+ * Threading: a gzpb_ctx is owned by ONE host thread at a time (Send, not Sync),
+ * like the per-worker `Compressor` of src/par/compress.rs:278.
+ * Errors: negative int codes, 1:1 with GzpError variants (src/lib.rs:114-163);
+ * nothing unwinds across the ABI; no partial output on error.
+ */
+#ifndef GZPB_H
+#define GZPB_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Format types (src/deflate.rs:61,169,279,357,506; src/snap.rs:35). */
+enum gzpb_format {
+    GZPB_GZIP = 0,
+    GZPB_ZLIB = 1,
+    GZPB_RAWDEFLATE = 2,
+    GZPB_MGZIP = 3,
+    GZPB_BGZF = 4,
+    GZPB_SNAP = 5
+};
+
+/* Error codes <-> GzpError (src/lib.rs:114-163). */
+enum gzpb_status {
+    GZPB_OK = 0,
+    GZPB_EBUFFERSIZE = -1,  /* BufferSize(got, min): buffer_size < 32 KiB (src/par/compress.rs:68-74) */
+    GZPB_ENUMTHREADS = -2,  /* NumThreads(0) (src/par/compress.rs:84-90) */
+    GZPB_EBLOCKSIZE = -3,   /* BlockSizeExceeded(n, 65536) (src/bgzf.rs:218-223) */
+    GZPB_ECOMPRESS = -4,    /* LibDeflaterCompress: output did not fit the capacity (src/bgzf.rs:214-216) */
+    GZPB_ELEVEL = -5,       /* LibDeflaterCompressionLvl: level not supported by this engine */
+    GZPB_EIO = -6,          /* Io */
+    GZPB_ECHANNEL = -7,     /* ChannelSend / ChannelReceive: stream already finished / torn down */
+    GZPB_ECUDA = -8,        /* CUDA runtime / launch failure (no reference analogue) */
+    GZPB_EINVAL = -9,       /* bad argument (Unknown) */
+    GZPB_ENOMEM = -10
+};
+
+/* Constants of the reference (src/lib.rs:105,108; src/bgzf.rs:20,22). */
+#define GZPB_BUFSIZE 131072u
+#define GZPB_DICT_SIZE 32768u
+#define GZPB_BGZF_BLOCK_SIZE 65280u
+#define GZPB_MAX_BGZF_BLOCK_SIZE 65536u
+/* device layout of one unit (one gzp block) for gzpb_encode_device */
+#define GZPB_IN_STRIDE 65600u
+#define GZPB_MAX_UNIT_BYTES 65536u
+
+typedef struct gzpb_ctx gzpb_ctx;
+
+/* One message of the compressor channel: `Message{buffer, dictionary, is_last}`
+ * (src/lib.rs:282-312). */
+typedef struct {
+    const void *ptr;
+    size_t len;
+    const void *dict; /* last 32 KiB of the previous block, or NULL (src/par/compress.rs:419-423) */
+    size_t dict_len;
+    int is_last;
+} gzpb_block_in;
+
+/* One completed oneshot: `(F::C, Vec<u8>)` (src/lib.rs:112). */
+typedef struct {
+    void *dst;        /* caller-owned, capacity >= gzpb_encode_capacity(format, len) */
+    size_t cap;
+    size_t out_len;
+    uint32_t check_sum;    /* Check::sum of this block (CRC-32 for Gzip, Adler-32 for Zlib, 0 otherwise) */
+    uint32_t check_amount; /* Check::amount */
+    int status;
+} gzpb_block_out;
+
+/* FormatSpec::create_compressor (src/lib.rs:343-346): one context per GPU.
+ * max_block_bytes = the ParCompress buffer_size; max_blocks_in_flight bounds the
+ * device batch (the analogue of the 2*num_threads channel bound,
+ * src/par/compress.rs:111-112).  Fails with GZPB_ECUDA when no sm_100 device /
+ * library is usable — there is no CPU fallback. */
+int gzpb_create(gzpb_ctx **ctx, int device, int format, int level, size_t max_block_bytes,
+                size_t max_blocks_in_flight);
+void gzpb_destroy(gzpb_ctx *ctx);
+
+/* FormatSpec::encode + Check::update for n blocks at once
+ * (src/par/compress.rs:281-289; src/deflate.rs:86-110,304-323,463-472,613-626;
+ * src/snap.rs:61-74).  Host pointers in, host pointers out; synchronous. */
+int gzpb_encode_batch(gzpb_ctx *ctx, size_t n, const gzpb_block_in *in, gzpb_block_out *out);
+
+/* ParCompress end to end for an in-memory input: header + write(in) + finish()
+ * + footer, i.e. chunking with the reference's strict '>' hold-back and final
+ * flush (src/par/compress.rs:413-463, 332-362), ordered output (:303-313).
+ * `in`/`out` may be pageable or pinned (gzpb_host_alloc) host memory. */
+int gzpb_encode_stream(gzpb_ctx *ctx, const void *in, size_t in_len, size_t buffer_size, void *out,
+                       size_t out_cap, size_t *out_len);
+
+/* Device-resident form of the same path, asynchronous on `cuda_stream`:
+ * d_in holds nunits slots of GZPB_IN_STRIDE bytes, d_len/d_flags one u32 per unit
+ * (flags bit0 = is_last, bit1 = sync flush); on completion d_packed holds the
+ * encoded blocks in order, d_offsets[i] their byte offsets (d_offsets[nunits] =
+ * total), d_status[i] the per-block status. */
+int gzpb_encode_device(gzpb_ctx *ctx, const void *d_in, const uint32_t *d_len, const uint32_t *d_flags,
+                       size_t nunits, void *d_packed, uint64_t *d_offsets, int32_t *d_status,
+                       void *cuda_stream);
+
+/* Capacity contract of the reference's output Vec (src/bgzf.rs:211-212,
+ * src/mgzip.rs:194-195, src/deflate.rs:50-53). */
+size_t gzpb_encode_capacity(int format, size_t len);
+/* FormatSpec::header / footer (src/deflate.rs:113-142, 221-251, 325-331, 474-480, 628-634). */
+size_t gzpb_header(int format, int level, void *buf16);
+size_t gzpb_footer(int format, uint32_t check_sum, uint32_t check_amount, void *buf16);
+/* Check::combine (src/check.rs:162, 121-128). */
+uint32_t gzpb_crc32_combine(uint32_t crc_a, uint32_t crc_b, uint64_t len_b);
+uint32_t gzpb_adler32_combine(uint32_t adler_a, uint32_t adler_b, uint64_t len_b);
+/* FormatSpec::DEFAULT_BUFSIZE / needs_dict (src/lib.rs:330, src/deflate.rs:79-82,583). */
+size_t gzpb_default_bufsize(int format);
+int gzpb_needs_dict(int format);
+int gzpb_level_supported(int format, int level);
+
+/* Pinned host memory for zero-copy staging (replaces the `Bytes` buffers the
+ * reference moves through its channels, src/par/compress.rs:416). */
+void *gzpb_host_alloc(size_t bytes);
+void gzpb_host_free(void *p);
+
+/* Per-kernel device time of the calls since the last reset, measured with CUDA
+ * events on the launching stream (for bench.py's roofline block).
+ * names: "chain","match","emit","gather","crc","snap" */
+int gzpb_set_profiling(gzpb_ctx *ctx, int on);
+int gzpb_kernel_ms(gzpb_ctx *ctx, const char *name, double *total_ms, uint64_t *launches);
+uint64_t gzpb_launch_count(gzpb_ctx *ctx);
+
+const char *gzpb_strerror(int code);
+const char *gzpb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
