@@ -104,14 +104,21 @@ __device__ __forceinline__ void chain_warp(const uint32_t *__restrict__ inw, uin
             uint32_t seq = H3 ? (v[k] & 0xFFFFFFu) : v[k];
             uint32_t h = lz_hash(seq, HASH_BITS);
             if (p == 0 && !dict0) h = 0;
-            uint32_t key = act ? h : (0x10000u + lane);
-            uint32_t grp = __match_any_sync(0xFFFFFFFFu, key);
-            uint32_t lower = grp & lt;
-            uint32_t prev = kNone16;
-            if (act) {
-                if (lower) prev = base + 31 - __clz(lower);
-                else prev = head[h];
-                if ((grp >> lane) == 1u) head[h] = (uint16_t)p;  // highest lane of the group
+            // Optimistic insert: every lane reads the bucket, then all store their
+            // position.  If each lane reads its own position back there were no equal
+            // hashes inside the tile (the common case) and `old` is the predecessor.
+            // Otherwise fall back to MATCH.ANY to order the duplicates.
+            uint32_t old = act ? (uint32_t)head[h] : kNone16;
+            if (act) head[h] = (uint16_t)p;
+            __syncwarp();
+            bool lost = act && head[h] != (uint16_t)p;
+            uint32_t prev = old;
+            if (__any_sync(0xFFFFFFFFu, lost)) {
+                uint32_t key = act ? h : (0x10000u + lane);
+                uint32_t grp = __match_any_sync(0xFFFFFFFFu, key);
+                uint32_t lower = grp & lt;
+                if (act && lower) prev = base + 31 - __clz(lower);
+                if (act && (grp >> lane) == 1u) head[h] = (uint16_t)p;  // highest lane of the group wins
             }
             __syncwarp();
             uint32_t dist = (prev != kNone16) ? p - prev : 0;
@@ -281,14 +288,16 @@ k_match(const uint8_t *__restrict__ in_base, const uint32_t *__restrict__ unit_l
 // =============================================================================
 constexpr int kEmitThreads = 128;
 constexpr int kTile = 512;                 // positions per streamed tile
+constexpr int kRing = 4;                   // tiles resident in the shared-memory ring
+constexpr int kChainCap = 500;             // lazy look-ahead steps evaluated per window lane
 constexpr int kTokPerThread = 8;
 constexpr int kChunkTok = kEmitThreads * kTokPerThread;
 constexpr int kStageWords = (kChunkTok * 48) / 32 + 8;
 
 struct EmitShared {
-    alignas(16) uint64_t mt[2][kTile];
-    alignas(16) uint8_t inb[2][kTile];
-    alignas(8) uint64_t bar[2];
+    alignas(16) uint64_t mt[kRing][kTile];
+    alignas(16) uint8_t inb[kRing][kTile];
+    alignas(8) uint64_t bar[kRing];
     uint32_t fl[kNumLitlen];
     uint32_t fo[kNumOffset];
     uint32_t obs[10], new_obs[10];
@@ -465,6 +474,9 @@ __device__ __forceinline__ void stage_begin(EmitShared &S, uint32_t words)
     __syncthreads();
 }
 
+// Match-table / input tiles streamed into a kRing-slot shared-memory ring by TMA
+// bulk copies.  All methods are warp-collective (called by every lane of warp 0
+// with uniform arguments); lane 0 issues the copies.
 struct Parser {
     const uint64_t *mt_g;
     const uint8_t *in_g;
@@ -472,25 +484,33 @@ struct Parser {
     uint32_t n, ntiles, issued, ready;
     __device__ __forceinline__ void issue(uint32_t t)
     {
-        uint32_t slot = t & 1, pos = t * kTile;
+        uint32_t slot = t % kRing, pos = t * kTile;
         uint32_t cnt = min((uint32_t)kTile, n - pos);
         uint32_t bm = (cnt * 8 + 15u) & ~15u, bi = (cnt + 15u) & ~15u;
         mbar_expect_tx(&S->bar[slot], bm + bi);
         tma_load_1d(S->mt[slot], mt_g + pos, bm, &S->bar[slot]);
         tma_load_1d(S->inb[slot], in_g + pos, bi, &S->bar[slot]);
     }
+    // tiles below p's tile are dead: refill their slots
     __device__ __forceinline__ void advance(uint32_t p)
     {
-        // tile (issued-2) is dead once p has moved past it
-        while (issued < ntiles && (issued - 1) * kTile <= p) { issue(issued); issued++; }
+        uint32_t want = min(ntiles, p / kTile + kRing);
+        if (issued < want) {
+            __syncwarp();
+            if ((threadIdx.x & 31) == 0) {
+                fence_proxy_async();
+                for (uint32_t t = issued; t < want; t++) issue(t);
+            }
+            issued = want;
+        }
     }
     __device__ __forceinline__ void need(uint32_t p)
     {
         uint32_t t = p / kTile;
-        while (ready <= t) { mbar_wait(&S->bar[ready & 1], (ready >> 1) & 1); ready++; }
+        while (ready <= t) { mbar_wait(&S->bar[ready % kRing], (ready / kRing) & 1); ready++; }
     }
-    __device__ __forceinline__ uint64_t M(uint32_t p) { need(p); return S->mt[(p / kTile) & 1][p % kTile]; }
-    __device__ __forceinline__ uint32_t B(uint32_t p) { need(p); return S->inb[(p / kTile) & 1][p % kTile]; }
+    __device__ __forceinline__ uint64_t M(uint32_t p) { return S->mt[(p / kTile) % kRing][p % kTile]; }
+    __device__ __forceinline__ uint32_t B(uint32_t p) { return S->inb[(p / kTile) % kRing][p % kTile]; }
 };
 
 // hc_matchfinder_longest_match() answered from the match table
@@ -531,7 +551,7 @@ k_emit(const uint8_t *__restrict__ in_base, const uint32_t *__restrict__ unit_le
     P.ntiles = (n + kTile - 1) / kTile; P.issued = 0; P.ready = 0;
 
     if (tid == 0) {
-        mbar_init(&S.bar[0], 1); mbar_init(&S.bar[1], 1);
+        for (int i = 0; i < kRing; i++) mbar_init(&S.bar[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         S.G = 0; S.carry = 0; S.status = 0;
     }
@@ -563,7 +583,6 @@ k_emit(const uint8_t *__restrict__ in_base, const uint32_t *__restrict__ unit_le
             pos += len;
         } while (pos != n);
     } else if (n > 0) {
-        if (tid == 0) { P.issue(0); P.issued = 1; if (P.ntiles > 1) { P.issue(1); P.issued = 2; } }
         uint32_t p = 0;              // parser position (thread 0 only is authoritative)
         uint32_t next_recalc = 0, min_len = 3;
         while (true) {
@@ -585,8 +604,14 @@ k_emit(const uint8_t *__restrict__ in_base, const uint32_t *__restrict__ unit_le
                 }
                 __syncthreads();
             }
-            // ---------------- sequential parse (thread 0) ----------------
-            if (tid == 0) {
+            // ---------------- windowed parse (warp 0) ----------------
+            // Each lane evaluates one main-loop iteration of the reference parser
+            // ("step") as if the parser were in its fresh state at P0+lane; the
+            // warp then follows the actual path through the window, commits the
+            // tokens of the steps on the path and stops exactly at the events that
+            // change parser state (min_len recalculation, block-split checks).
+            if (tid < 32) {
+                const uint32_t lane = tid;
                 if (max_block_end - bb < 512) min_len = 3;
                 else {
                     uint32_t nu = 0;
@@ -594,91 +619,127 @@ k_emit(const uint8_t *__restrict__ in_base, const uint32_t *__restrict__ unit_le
                     min_len = choose_min_match_len(nu, depth);
                 }
                 next_recalc = bb + min(n - bb, 10000u);
-                uint32_t ntok = 0, nmatch = 0, num_obs = 0, num_new_obs = 0;
+                uint32_t ntok = 0, num_obs = 0, num_new_obs = 0;
                 bool end_block = false;
-#define LITERAL(byte_)                                                                 \
-    do {                                                                               \
-        uint32_t lit_ = (byte_);                                                       \
-        atomicAdd(&S.fl[lit_], 1u);                                                    \
-        atomicAdd(&S.new_obs[((lit_ >> 5) & 6) | (lit_ & 1)], 1u);                     \
-        num_new_obs++;                                                                 \
-        tok[ntok++] = lit_;                                                            \
-    } while (0)
-#define MATCH(len_, off_)                                                              \
-    do {                                                                               \
-        atomicAdd(&S.fl[kFirstLenSym + len_slot_only(len_)], 1u);                      \
-        atomicAdd(&S.fo[off_slot_only(off_)], 1u);                                     \
-        atomicAdd(&S.new_obs[8 + ((len_) >= 9)], 1u);                                  \
-        num_new_obs++;                                                                 \
-        tok[ntok++] = 0x80000000u | ((len_) << 16) | (off_);                           \
-        nmatch++;                                                                      \
-    } while (0)
                 do {
                     P.advance(p);
-                    uint32_t cur_len, cur_off;
-                    if (mode == 0) {
-                        uint32_t maxlen = min((uint32_t)kMaxMatch, n - p);
-                        table_search(P.M(p), min_len - 1, false, maxlen, cur_len, cur_off);
-                        if (cur_len >= min_len && (cur_len > 3 || cur_off <= 4096)) { MATCH(cur_len, cur_off); p += cur_len; }
-                        else { LITERAL(P.B(p)); p++; }
-                    } else {
-                        if (p >= next_recalc) {
-                            // recalculate_min_match_len() from the literal frequencies so far
-                            uint32_t total = 0, nu = 0;
-                            for (int i = 0; i < 256; i++) total += S.fl[i];
-                            uint32_t cutoff = total >> 10;
-                            for (int i = 0; i < 256; i++) nu += (S.fl[i] > cutoff);
-                            min_len = choose_min_match_len(nu, depth);
-                            next_recalc += min(n - next_recalc, p - bb);
-                        }
-                        uint32_t maxlen = min((uint32_t)kMaxMatch, n - p);
-                        table_search(P.M(p), min_len - 1, false, maxlen, cur_len, cur_off);
-                        if (cur_len < min_len || (cur_len == 3 && cur_off > 8192)) { LITERAL(P.B(p)); p++; }
-                        else {
-                            uint32_t m = p;
+                    P.need(min(n - 1, p + 31 + kChainCap + 2));
+                    // ---- step evaluation at q = p + lane ----
+                    const uint32_t q = p + lane;
+                    uint32_t nlit = 0, mlen = 0, moff = 0;
+                    bool bad = false;
+                    if (q < max_block_end) {
+                        uint32_t cur_len, cur_off;
+                        uint32_t maxlen = min((uint32_t)kMaxMatch, n - q);
+                        table_search(P.M(q), min_len - 1, false, maxlen, cur_len, cur_off);
+                        if (mode == 0) {
+                            if (cur_len >= min_len && (cur_len > 3 || cur_off <= 4096)) { mlen = cur_len; moff = cur_off; }
+                            else nlit = 1;
+                        } else if (cur_len < min_len || (cur_len == 3 && cur_off > 8192)) {
+                            nlit = 1;
+                        } else {
+                            uint32_t m = q;
                             for (;;) {
                                 uint32_t nice_m = min((uint32_t)nice, min((uint32_t)kMaxMatch, n - m));
                                 if (cur_len >= nice_m) break;
+                                if (m - q >= (uint32_t)kChainCap) { bad = true; break; }
                                 uint32_t nl, no;
                                 uint32_t maxlen1 = min((uint32_t)kMaxMatch, n - (m + 1));
                                 table_search(maxlen1 >= 5 ? P.M(m + 1) : 0ull, cur_len - 1, true, maxlen1, nl, no);
                                 if (nl >= cur_len && 4 * (int)(nl - cur_len) + ((int)bsr32(cur_off) - (int)bsr32(no)) > 2) {
-                                    LITERAL(P.B(m));
                                     m++; cur_len = nl; cur_off = no;
-                                    P.advance(m);
                                     continue;
                                 }
                                 break;
                             }
-                            MATCH(cur_len, cur_off);
-                            p = m + cur_len;
+                            nlit = m - q; mlen = cur_len; moff = cur_off;
                         }
                     }
-                    // should_end_block()
-                    if (num_new_obs >= (uint32_t)kObsPerCheck && p - bb >= (uint32_t)kMinBlockLength && n - p >= (uint32_t)kMinBlockLength) {
+                    const uint32_t adv = nlit + mlen;            // >= 1 for valid lanes
+                    const uint32_t ntoks = nlit + (mlen ? 1u : 0u);
+                    // ---- follow the path through the window ----
+                    uint32_t pathmask = 0, c = 0;
+                    while (c < 32 && p + c < max_block_end) {
+                        pathmask |= 1u << c;
+                        c += __shfl_sync(0xFFFFFFFFu, adv, c);
+                    }
+                    const bool onpath = (pathmask >> lane) & 1u;
+                    // inclusive token count along the path
+                    uint32_t incl = onpath ? ntoks : 0;
+                    for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (uint32_t)o) incl += v; }
+                    // ---- events ----
+                    const uint32_t e_l = q + adv;
+                    uint32_t rmask = (mode != 0) ? __ballot_sync(0xFFFFFFFFu, onpath && q >= next_recalc) : 0u;
+                    uint32_t cmask = __ballot_sync(0xFFFFFFFFu, onpath && (num_new_obs + incl >= (uint32_t)kObsPerCheck) &&
+                                                                     (e_l - bb >= (uint32_t)kMinBlockLength) && (n - e_l >= (uint32_t)kMinBlockLength));
+                    int Lr = rmask ? __ffs(rmask) - 1 : 64, Lc = cmask ? __ffs(cmask) - 1 : 64;
+                    uint32_t commit_mask, next_p;
+                    int event = 0;   // 1 = recalc before lane Lr, 2 = block check after lane Lc
+                    if (Lr <= Lc && Lr < 64) { event = 1; commit_mask = pathmask & ((1u << Lr) - 1); next_p = p + Lr; }
+                    else if (Lc < 64) { event = 2; commit_mask = pathmask & (Lc == 31 ? 0xFFFFFFFFu : ((2u << Lc) - 1)); next_p = __shfl_sync(0xFFFFFFFFu, e_l, Lc); }
+                    else { commit_mask = pathmask; next_p = p + c; }
+                    // ---- commit ----
+                    const bool mine = (commit_mask >> lane) & 1u;
+                    if (mine) {
+                        if (bad) S.status = -9;
+                        uint32_t ti = ntok + incl - ntoks;
+                        for (uint32_t i = 0; i < nlit; i++) {
+                            uint32_t lit = P.B(q + i);
+                            atomicAdd(&S.fl[lit], 1u);
+                            atomicAdd(&S.new_obs[((lit >> 5) & 6) | (lit & 1)], 1u);
+                            tok[ti++] = lit;
+                        }
+                        if (mlen) {
+                            atomicAdd(&S.fl[kFirstLenSym + len_slot_only(mlen)], 1u);
+                            atomicAdd(&S.fo[off_slot_only(moff)], 1u);
+                            atomicAdd(&S.new_obs[8 + (mlen >= 9)], 1u);
+                            tok[ti] = 0x80000000u | (mlen << 16) | moff;
+                        }
+                    }
+                    {
+                        uint32_t last = commit_mask ? 31 - __clz(commit_mask) : 0;
+                        uint32_t added = commit_mask ? __shfl_sync(0xFFFFFFFFu, incl, last) : 0;
+                        ntok += added; num_new_obs += added;
+                    }
+                    p = next_p;
+                    __syncwarp();
+                    if (event == 1) {
+                        // recalculate_min_match_len() from the literal frequencies so far
+                        uint32_t total = 0;
+                        for (int i = 0; i < 8; i++) total += S.fl[lane * 8 + i];
+                        for (int o = 16; o; o >>= 1) total += __shfl_xor_sync(0xFFFFFFFFu, total, o);
+                        uint32_t cutoff = total >> 10, nu = 0;
+                        for (int i = 0; i < 8; i++) nu += (S.fl[lane * 8 + i] > cutoff);
+                        for (int o = 16; o; o >>= 1) nu += __shfl_xor_sync(0xFFFFFFFFu, nu, o);
+                        min_len = choose_min_match_len(nu, depth);
+                        next_recalc += min(n - next_recalc, p - bb);
+                    } else if (event == 2) {
+                        // should_end_block() -> do_end_block_check()
                         uint32_t block_length = p - bb;
                         if (num_obs > 0) {
-                            uint32_t total_delta = 0;
-                            for (int i = 0; i < 10; i++) {
-                                uint32_t expected = S.obs[i] * num_new_obs, actual = S.new_obs[i] * num_obs;
-                                total_delta += actual > expected ? actual - expected : expected - actual;
+                            uint32_t d = 0;
+                            if (lane < 10) {
+                                uint32_t expected = S.obs[lane] * num_new_obs, actual = S.new_obs[lane] * num_obs;
+                                d = actual > expected ? actual - expected : expected - actual;
                             }
+                            for (int o = 16; o; o >>= 1) d += __shfl_xor_sync(0xFFFFFFFFu, d, o);
                             uint32_t num_items = num_obs + num_new_obs;
                             uint32_t cutoff = num_new_obs * 200 / 512 * num_obs;
                             if (block_length < 10000 && num_items < 8192)
                                 cutoff += (uint32_t)((uint64_t)cutoff * (8192 - num_items) / 8192);
-                            if (total_delta + (block_length / 4096) * num_obs >= cutoff) end_block = true;
+                            if (d + (block_length / 4096) * num_obs >= cutoff) end_block = true;
                         }
                         if (!end_block) {
-                            for (int i = 0; i < 10; i++) { S.obs[i] += S.new_obs[i]; S.new_obs[i] = 0; }
+                            if (lane < 10) { S.obs[lane] += S.new_obs[lane]; S.new_obs[lane] = 0; }
                             num_obs += num_new_obs; num_new_obs = 0;
                         }
+                        __syncwarp();
                     }
-                } while (p < max_block_end && nmatch < (uint32_t)kSeqStoreLength && !end_block);
-#undef LITERAL
-#undef MATCH
-                S.blk_end = p; S.ntok = ntok; S.is_final = (final_block && p == n) ? 1u : 0u;
-                S.fl[kEndOfBlock] += 1;
+                } while (p < max_block_end && !end_block);
+                if (lane == 0) {
+                    S.blk_end = p; S.ntok = ntok; S.is_final = (final_block && p == n) ? 1u : 0u;
+                    S.fl[kEndOfBlock] += 1;
+                }
             }
             __syncthreads();
             __threadfence_block();
@@ -888,7 +949,7 @@ k_emit(const uint8_t *__restrict__ in_base, const uint32_t *__restrict__ unit_le
         uint32_t nbytes = (G + 7) >> 3;
         uint32_t total = nbytes;
         uint32_t hdr_off = kOutPayloadOff;
-        int32_t st = 0;
+        int32_t st = S.status;
         if (format == 4 || format == 3) {        // Bgzf / Mgzip member per unit
             const uint32_t hs = format == 4 ? 18 : 20;
             uint8_t *h = slot + kOutPayloadOff - hs;
