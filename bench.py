@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native per-block encode path.
+
+Metric (BASELINE.json): compressed GiB/s of INPUT bytes, ParCompress<Bgzf> level 6,
+65 280-byte blocks, on a synthetic English-text stream shaped like
+shakespeare.txt x N (period 5 465 394 B; the reference corpus itself does not
+travel to the GPU box, see gzp_b200/synth.py).
+
+A "step" = one pass of the hot path over one batch of `--blocks` consecutive
+blocks of that stream (a different window of the stream every step, each batch
+larger than L2).  Per JSON line:
+  value      device-resident throughput: inputs already in HBM (unit layout),
+             gzpb_encode_device on the launching stream, CUDA-event timed.
+  e2e        the same batches through the reference-facing C-ABI call
+             gzpb_encode_stream with pinned HOST buffers (H2D + kernels + D2H
+             inside the timed region).
+  roofline   dominant kernel (k_match), algorithmic bytes / CUDA-event time.
+  cpu_baseline  the oracle's ParCompress port on the host cores (bounded sample).
+
+`--impl reference` times the reference's CPU path (the oracle port of its
+thread topology + libdeflate-style level 6) on the host cores instead.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BLOCK = 65280
+LEVEL = 6
+METRIC = "bgzf_l6_compress_input_throughput"
+UNIT = "GiB/s"
+GIB = float(1 << 30)
+# k_match algorithmic HBM bytes per input byte: input 1 + next4 2 + prev3 2 read, match table 8 written
+MATCH_BYTES_PER_INPUT_BYTE = 13.0
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--blocks", type=int, default=4096, help="gzp blocks per step and GPU")
+    ap.add_argument("--cpu-sample-mb", type=float, default=0.0, help="override the CPU baseline sample size")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], 0, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = max(mx, float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_baseline(data, threads, sample_mb=0.0):
+    """Time the oracle's ParCompress port (kind 'port': the reference cannot be built here,
+    no Rust toolchain / libdeflate source) on a bounded sample of the same workload."""
+    import oracle
+    L = oracle.lib()
+    cal = data[: 8 * BLOCK * max(1, threads)]
+    out = C.create_string_buffer(len(data) // 2 + len(cal) + (1 << 20))
+    olen = C.c_size_t(0)
+    t = L.oracle_par_compress(oracle.BGZF, LEVEL, BLOCK, threads, cal, len(cal), out, len(out), C.byref(olen))
+    rate = len(cal) / max(t, 1e-6)
+    target = int(rate * 12.0) if not sample_mb else int(sample_mb * 1e6)
+    n = max(BLOCK * threads, min(len(data), target)) // BLOCK * BLOCK
+    sample = data[:n]
+    t = L.oracle_par_compress(oracle.BGZF, LEVEL, BLOCK, threads, sample, n, out, len(out), C.byref(olen))
+    if t <= 0:
+        raise RuntimeError("oracle_par_compress failed")
+    return {"value": n / t / GIB, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{n} B of the same text stream, {n // BLOCK} blocks, ratio {olen.value / n:.4f}, {t:.2f} s"}, n / t / GIB
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path (oracle port, all host threads)."""
+    if rank != 0:
+        return
+    from gzp_b200 import synth
+    import oracle
+    threads = host_threads()
+    L = oracle.lib()
+    # each step = a bounded sample sized for ~3 s of CPU work
+    probe = synth.text_stream(8 * BLOCK * threads)
+    out = C.create_string_buffer(64 << 20)
+    olen = C.c_size_t(0)
+    t = L.oracle_par_compress(oracle.BGZF, LEVEL, BLOCK, threads, probe, len(probe), out, len(out), C.byref(olen))
+    rate = len(probe) / max(t, 1e-6)
+    nblocks = max(threads, min(args.blocks, int(rate * 3.0) // BLOCK))
+    nbytes = nblocks * BLOCK
+    data = synth.text_stream(nbytes + 16 * BLOCK * (args.steps + args.warmup))
+    out = C.create_string_buffer(nbytes // 2 + (4 << 20))
+    times = []
+    for i in range(args.warmup + args.steps):
+        off = (i * 16 * BLOCK)
+        sample = data[off: off + nbytes]
+        t = L.oracle_par_compress(oracle.BGZF, LEVEL, BLOCK, threads, sample, nbytes, out, len(out), C.byref(olen))
+        if i >= args.warmup:
+            times.append(t)
+    total = sum(times)
+    val = nbytes * len(times) / total / GIB
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": f"ParCompress<Bgzf> level {LEVEL}, {BLOCK}-B blocks, synthetic text stream (period 5465394 B)",
+                       "sample_blocks_per_step": nblocks, "host_threads": threads},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": f"{nblocks} blocks ({nbytes} B) per step: oracle port of gzp's ParCompress topology + libdeflate-style L6 (reference not buildable here: no Rust toolchain)"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import gzp_b200
+    from gzp_b200 import _lib, synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    L = _lib.load()
+    nblk = args.blocks
+    step_bytes = nblk * BLOCK
+    nwin = 4                                             # distinct stream windows rotated over the steps
+    shift = 977 * BLOCK                                  # window start moves by this much per step
+    stream = synth.text_stream(step_bytes + nwin * shift + rank * 131 * BLOCK)
+    base_off = rank * 131 * BLOCK                        # every rank compresses a different part of the stream
+
+    ctx = gzp_b200.Context(gzp_b200.BGZF, LEVEL, device=local_rank, max_block_bytes=BLOCK, max_blocks_in_flight=min(nblk, 2048))
+
+    # ---------------- device-resident arm ----------------
+    host_all = torch.frombuffer(bytearray(stream), dtype=torch.uint8)
+    d_ins = []
+    for w in range(nwin):
+        flat = host_all[base_off + w * shift: base_off + w * shift + step_bytes].to(dev)
+        d_in = torch.zeros((nblk, 65600), dtype=torch.uint8, device=dev)
+        d_in[:, :BLOCK] = flat.view(nblk, BLOCK)
+        d_ins.append(d_in)
+    d_len = torch.full((nblk,), BLOCK, dtype=torch.int32, device=dev)
+    d_flags = torch.zeros((nblk,), dtype=torch.int32, device=dev)
+    d_packed = torch.empty((nblk * 73728,), dtype=torch.uint8, device=dev)
+    d_off = torch.zeros((nblk + 1,), dtype=torch.int64, device=dev)
+    d_status = torch.zeros((nblk,), dtype=torch.int32, device=dev)
+    st = torch.cuda.current_stream()
+
+    def dev_step(i):
+        rc = L.gzpb_encode_device(ctx._h, d_ins[i % nwin].data_ptr(), d_len.data_ptr(), d_flags.data_ptr(), nblk,
+                                  d_packed.data_ptr(), d_off.data_ptr(), d_status.data_ptr(), st.cuda_stream)
+        if rc != 0:
+            raise RuntimeError("gzpb_encode_device: " + L.gzpb_strerror(rc).decode())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        dev_step(i)
+    torch.cuda.synchronize()
+    assert int(d_status.abs().max().item()) == 0
+    out_bytes_dev = int(d_off[nblk].item())
+
+    ctx.set_profiling(True)
+    sampler = ClockSampler(local_rank)
+    launches0 = ctx.launch_count()
+    barrier()
+    sampler.start()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for i in range(args.steps):
+        dev_step(args.warmup + i)
+    e1.record(st)
+    barrier()
+    clocks = sampler.stop()
+    dev_ms = e0.elapsed_time(e1)
+    launches = ctx.launch_count() - launches0
+    kms = {k: ctx.kernel_ms(k) for k in ("chain", "match", "emit", "gather")}
+    ctx.set_profiling(False)
+    if world > 1:
+        t = torch.tensor([dev_ms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); dev_ms = float(t.item())
+
+    # ---------------- end-to-end arm (host buffers through the C ABI) ----------------
+    h_in = L.gzpb_host_alloc(step_bytes + nwin * shift)
+    out_cap = step_bytes // 2 + (8 << 20)
+    h_out = L.gzpb_host_alloc(out_cap)
+    if not h_in or not h_out:
+        raise RuntimeError("gzpb_host_alloc failed")
+    C.memmove(h_in, bytes(stream[base_off: base_off + step_bytes + nwin * shift]), step_bytes + nwin * shift)
+    olen = C.c_size_t(0)
+
+    def e2e_step(i):
+        rc = L.gzpb_encode_stream(ctx._h, h_in + (i % nwin) * shift, step_bytes, BLOCK, h_out, out_cap, C.byref(olen))
+        if rc != 0:
+            raise RuntimeError("gzpb_encode_stream: " + L.gzpb_strerror(rc).decode())
+
+    for i in range(args.warmup):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        e2e_step(args.warmup + i)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    out_bytes = olen.value
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); e2e_s = float(t.item())
+
+    # correctness spot check of what was timed: the e2e stream of the last step decodes to its input
+    if rank == 0:
+        import gzip
+        last = (args.warmup + args.steps - 1) % nwin
+        got = gzip.decompress(C.string_at(h_out, out_bytes))
+        want = stream[base_off + last * shift: base_off + last * shift + step_bytes]
+        assert got == want, "e2e output does not decode to the input"
+
+    total_in = step_bytes * args.steps * world
+    value = total_in / (dev_ms / 1e3) / GIB
+    e2e_val = total_in / e2e_s / GIB
+
+    if rank == 0:
+        match_ms, match_n = kms["match"]
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        per_launch_bytes = MATCH_BYTES_PER_INPUT_BYTE * BLOCK * min(nblk, 2048)
+        achieved = per_launch_bytes / (match_ms / max(match_n, 1) / 1e3) / 1e9 if match_n else 0.0
+        cpu, _ = cpu_baseline(stream, host_threads(), args.cpu_sample_mb)
+        share = {k: round(v[0] / max(sum(x[0] for x in kms.values()), 1e-9), 4) for k, v in kms.items()}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": f"ParCompress<Bgzf> level {LEVEL}, {BLOCK}-B blocks, synthetic text stream (period 5465394 B; BASELINE configs[1] shape)",
+                       "blocks_per_step_per_gpu": nblk, "bytes_per_step_per_gpu": step_bytes, "ratio": out_bytes_dev / step_bytes,
+                       "l2": "each step's input (%.0f MB) exceeds L2 and rotates over %d stream windows" % (step_bytes / 1e6, nwin),
+                       "parallelism": f"independent blocks sharded over {world} GPU(s), no data collective"},
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": step_bytes, "d2h_bytes_per_step": out_bytes,
+                    "ms_per_step": 1e3 * e2e_s / args.steps, "api": "gzpb_encode_stream (pinned host in/out)"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "k_match", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650 GB/s",
+                         "note": "k_match is instruction-issue bound (ncu: profiles/), not HBM bound; algorithmic bytes = 13 B per input byte",
+                         "kernel_ms_per_launch": {k: v[0] / max(v[1], 1) for k, v in kms.items()}, "kernel_time_share": share},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    L.gzpb_host_free(h_in); L.gzpb_host_free(h_out)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

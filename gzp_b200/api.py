@@ -285,7 +285,8 @@ class ParCompress:
         self.writer = writer
         self.level = level
         self.buffer_size = buffer_size
-        self._ctx = Context(fmt.ID, level, device, buffer_size, blocks_in_flight)
+        self._ctx = None
+        self._ctx_args = (fmt.ID, level, device, buffer_size, blocks_in_flight)
         self._buf = bytearray()
         self._dict = None
         self._pending = []          # messages not yet handed to the device (FIFO = ticket order)
@@ -308,6 +309,8 @@ class ParCompress:
         if not self._pending:
             return
         msgs, self._pending = self._pending, []
+        if self._ctx is None:
+            self._ctx = Context(*self._ctx_args)     # FormatSpec::create_compressor (par/compress.rs:278)
         try:
             res = self._ctx.encode_blocks(msgs)
         except GzpError as e:
@@ -365,7 +368,8 @@ class ParCompress:
         if hasattr(self.writer, "flush"):
             self.writer.flush()
         self._finished = True
-        self._ctx.close()
+        if self._ctx is not None:
+            self._ctx.close()
         return self.writer
 
     def __enter__(self):

@@ -26,6 +26,7 @@ __constant__ uint32_t c_xpow512[130];         // x^(8*512*j) mod P
 __constant__ uint16_t c_static_litlen_cw[288];
 __constant__ uint8_t c_static_litlen_len[288];
 __constant__ uint8_t c_min_lens[80];
+__device__ unsigned long long g_phase[32];   // SM-cycle accounting of kernel phases (debug/profiling aid)
 
 static uint32_t h_bitrev(uint32_t v, int n) { uint32_t r = 0; for (int i = 0; i < n; i++) r |= ((v >> i) & 1u) << (n - 1 - i); return r; }
 
@@ -107,18 +108,25 @@ __device__ __forceinline__ void chain_warp(const uint32_t *__restrict__ inw, uin
             // Optimistic insert: every lane reads the bucket, then all store their
             // position.  If each lane reads its own position back there were no equal
             // hashes inside the tile (the common case) and `old` is the predecessor.
-            // Otherwise fall back to MATCH.ANY to order the duplicates.
+            // Otherwise order each group of duplicates with ballots.
             uint32_t old = act ? (uint32_t)head[h] : kNone16;
             if (act) head[h] = (uint16_t)p;
             __syncwarp();
             bool lost = act && head[h] != (uint16_t)p;
             uint32_t prev = old;
-            if (__any_sync(0xFFFFFFFFu, lost)) {
-                uint32_t key = act ? h : (0x10000u + lane);
-                uint32_t grp = __match_any_sync(0xFFFFFFFFu, key);
-                uint32_t lower = grp & lt;
-                if (act && lower) prev = base + 31 - __clz(lower);
-                if (act && (grp >> lane) == 1u) head[h] = (uint16_t)p;  // highest lane of the group wins
+            uint32_t lostmask = __ballot_sync(0xFFFFFFFFu, lost);
+            while (lostmask) {
+                // one iteration per group of equal hashes: order its members by lane
+                const int j = __ffs(lostmask) - 1;
+                const uint32_t hj = __shfl_sync(0xFFFFFFFFu, h, j);
+                const bool member = act && h == hj;
+                const uint32_t grp = __ballot_sync(0xFFFFFFFFu, member);
+                if (member) {
+                    uint32_t lower = grp & lt;
+                    if (lower) prev = base + 31 - __clz(lower);
+                    if ((grp >> lane) == 1u) head[h] = (uint16_t)p;  // highest lane of the group wins
+                }
+                lostmask &= ~grp;
             }
             __syncwarp();
             uint32_t dist = (prev != kNone16) ? p - prev : 0;
@@ -143,6 +151,7 @@ k_chain(const uint8_t *__restrict__ in_base, const uint32_t *__restrict__ unit_l
     const uint32_t *inw = (const uint32_t *)in;
     const uint32_t tid = threadIdx.x, warp = tid >> 5;
 
+    const long long t_start = clock64();
     // pull the unit into L2 ahead of the dependent loads
     for (uint32_t off = tid * 128; off < n; off += kChainThreads * 128)
         asm volatile("prefetch.global.L2 [%0];" ::"l"(in + off));
@@ -156,7 +165,9 @@ k_chain(const uint8_t *__restrict__ in_base, const uint32_t *__restrict__ unit_l
     __syncthreads();
 
     if (warp == 0) {
+        long long t0 = clock64();
         chain_warp<16, false>(inw, n, 0, head4, next4 + (size_t)u * kMaxUnitBytes);
+        if (tid == 0) atomicAdd(&g_phase[16], (unsigned long long)(clock64() - t0));
     } else if (warp == 1) {
         chain_warp<15, true>(inw, n, 0, head3, prev3 + (size_t)u * kMaxUnitBytes);
     } else {
@@ -177,9 +188,10 @@ k_chain(const uint8_t *__restrict__ in_base, const uint32_t *__restrict__ unit_l
 #pragma unroll
         for (int o = 16; o; o >>= 1) acc ^= __shfl_xor_sync(0xFFFFFFFFu, acc, o);
         if ((tid & 31) == 0 && acc) atomicXor(&s_crc, acc);
+        if (tid == 64) atomicAdd(&g_phase[17], (unsigned long long)(clock64() - t_start));
     }
     __syncthreads();
-    if (tid == 0) crc_out[u] = s_crc;
+    if (tid == 0) { crc_out[u] = s_crc; atomicAdd(&g_phase[18], (unsigned long long)(clock64() - t_start)); }
 }
 
 // =============================================================================
@@ -286,10 +298,9 @@ k_match(const uint8_t *__restrict__ in_base, const uint32_t *__restrict__ unit_l
 // dynamic / static / stored, and packs the tokens in parallel (prefix scan of
 // code lengths, OR-merge in a shared staging buffer, coalesced 32-bit stores).
 // =============================================================================
-constexpr int kEmitThreads = 128;
-constexpr int kTile = 512;                 // positions per streamed tile
-constexpr int kRing = 4;                   // tiles resident in the shared-memory ring
-constexpr int kChainCap = 500;             // lazy look-ahead steps evaluated per window lane
+constexpr int kEmitThreads = 64;
+constexpr int kTile = 256;                 // positions per streamed tile
+constexpr int kRing = 2;                   // tiles resident in the shared-memory ring
 constexpr int kTokPerThread = 8;
 constexpr int kChunkTok = kEmitThreads * kTokPerThread;
 constexpr int kStageWords = (kChunkTok * 48) / 32 + 8;
@@ -557,6 +568,8 @@ k_emit(const uint8_t *__restrict__ in_base, const uint32_t *__restrict__ unit_le
     }
     __syncthreads();
 
+    long long t_prev = clock64();
+#define PHASE(idx_) do { if (tid == 0) { long long t_ = clock64(); atomicAdd(&g_phase[idx_], (unsigned long long)(t_ - t_prev)); t_prev = t_; } } while (0)
     const uint32_t passthrough = (level == 0) ? 0xFFFFFFFFu : (uint32_t)(55 - level * 4);
     if (n <= passthrough && !(sync_flush && n == 0)) {
         // deflate_compress_none(): stored blocks of <= 65535 bytes
@@ -604,6 +617,7 @@ k_emit(const uint8_t *__restrict__ in_base, const uint32_t *__restrict__ unit_le
                 }
                 __syncthreads();
             }
+            PHASE(0);
             // ---------------- windowed parse (warp 0) ----------------
             // Each lane evaluates one main-loop iteration of the reference parser
             // ("step") as if the parser were in its fresh state at P0+lane; the
@@ -619,88 +633,102 @@ k_emit(const uint8_t *__restrict__ in_base, const uint32_t *__restrict__ unit_le
                     min_len = choose_min_match_len(nu, depth);
                 }
                 next_recalc = bb + min(n - bb, 10000u);
-                uint32_t ntok = 0, num_obs = 0, num_new_obs = 0;
+                uint32_t ntok = 0, num_obs = 0, num_new_obs = 0, in_h = 0;
                 bool end_block = false;
                 do {
                     P.advance(p);
-                    P.need(min(n - 1, p + 31 + kChainCap + 2));
-                    // ---- step evaluation at q = p + lane ----
+                    P.need(min(n - 1, p + 33));
+                    // ---- per-lane transitions at q = p + lane ----
+                    // F(q): parser in its fresh state at q (top of the reference's main loop).
+                    // H(q): parser at `have_cur_match` at q, the current match being the
+                    //       depth/2 search result at q (the only way that state is reached).
+                    // A transition emits ONE token and names the next state:
+                    //   word = advance (bits 0-8) | next-is-H (bit 9) | token-is-match (bit 10)
                     const uint32_t q = p + lane;
-                    uint32_t nlit = 0, mlen = 0, moff = 0;
-                    bool bad = false;
+                    uint32_t wF = 1, wH = 1, lenF = 0, offF = 0, lenH = 0, offH = 0;
                     if (q < max_block_end) {
-                        uint32_t cur_len, cur_off;
-                        uint32_t maxlen = min((uint32_t)kMaxMatch, n - q);
-                        table_search(P.M(q), min_len - 1, false, maxlen, cur_len, cur_off);
+                        const uint64_t e0 = P.M(q);
+                        const uint32_t maxlen = min((uint32_t)kMaxMatch, n - q);
+                        const uint32_t maxlen1 = (q + 1 < n) ? min((uint32_t)kMaxMatch, n - (q + 1)) : 0u;
+                        const uint64_t e1 = maxlen1 >= 5 ? P.M(q + 1) : 0ull;
+                        const uint32_t nice_q = min((uint32_t)nice, maxlen);
+                        uint32_t cl, co;
+                        table_search(e0, min_len - 1, false, maxlen, cl, co);
                         if (mode == 0) {
-                            if (cur_len >= min_len && (cur_len > 3 || cur_off <= 4096)) { mlen = cur_len; moff = cur_off; }
-                            else nlit = 1;
-                        } else if (cur_len < min_len || (cur_len == 3 && cur_off > 8192)) {
-                            nlit = 1;
+                            if (cl >= min_len && (cl > 3 || co <= 4096)) { lenF = cl; offF = co; wF = cl | (1u << 10); }
                         } else {
-                            uint32_t m = q;
-                            for (;;) {
-                                uint32_t nice_m = min((uint32_t)nice, min((uint32_t)kMaxMatch, n - m));
-                                if (cur_len >= nice_m) break;
-                                if (m - q >= (uint32_t)kChainCap) { bad = true; break; }
-                                uint32_t nl, no;
-                                uint32_t maxlen1 = min((uint32_t)kMaxMatch, n - (m + 1));
-                                table_search(maxlen1 >= 5 ? P.M(m + 1) : 0ull, cur_len - 1, true, maxlen1, nl, no);
-                                if (nl >= cur_len && 4 * (int)(nl - cur_len) + ((int)bsr32(cur_off) - (int)bsr32(no)) > 2) {
-                                    m++; cur_len = nl; cur_off = no;
-                                    continue;
+                            // decide(): emit the current match, or a literal and move to H(q+1)
+                            if (!(cl < min_len || (cl == 3 && co > 8192))) {
+                                bool take = cl >= nice_q;
+                                if (!take) {
+                                    uint32_t nl, no;
+                                    table_search(e1, cl - 1, true, maxlen1, nl, no);
+                                    take = !(nl >= cl && 4 * (int)(nl - cl) + ((int)bsr32(co) - (int)bsr32(no)) > 2);
                                 }
-                                break;
+                                if (take) { lenF = cl; offF = co; wF = cl | (1u << 10); }
+                                else wF = 1u | (1u << 9);
                             }
-                            nlit = m - q; mlen = cur_len; moff = cur_off;
+                            // H(q): current match = depth/2 result at q (or the 3-byte match)
+                            uint32_t hl = (uint32_t)(e0 >> 23) & 0xFF, ho = (uint32_t)(e0 >> 31) & 0x7FFF;
+                            if (hl) hl += 3;
+                            else { ho = (uint32_t)(e0 >> 47) & 0x3FFF; hl = ho ? 3 : 0; }
+                            if (hl && maxlen >= 5) {
+                                bool take = hl >= nice_q;
+                                if (!take) {
+                                    uint32_t nl, no;
+                                    table_search(e1, hl - 1, true, maxlen1, nl, no);
+                                    take = !(nl >= hl && 4 * (int)(nl - hl) + ((int)bsr32(ho) - (int)bsr32(no)) > 2);
+                                }
+                                if (take) { lenH = hl; offH = ho; wH = hl | (1u << 10); }
+                                else wH = 1u | (1u << 9);
+                            }
                         }
                     }
-                    const uint32_t adv = nlit + mlen;            // >= 1 for valid lanes
-                    const uint32_t ntoks = nlit + (mlen ? 1u : 0u);
-                    // ---- follow the path through the window ----
-                    uint32_t pathmask = 0, c = 0;
+                    // ---- follow the path through the window (one token per hop) ----
+                    uint32_t visF = 0, visH = 0, c = 0, st_h = in_h;
                     while (c < 32 && p + c < max_block_end) {
-                        pathmask |= 1u << c;
-                        c += __shfl_sync(0xFFFFFFFFu, adv, c);
+                        if (st_h) visH |= 1u << c; else visF |= 1u << c;
+                        uint32_t w = __shfl_sync(0xFFFFFFFFu, st_h ? wH : wF, c);
+                        c += w & 0x1FF; st_h = (w >> 9) & 1;
                     }
-                    const bool onpath = (pathmask >> lane) & 1u;
-                    // inclusive token count along the path
-                    uint32_t incl = onpath ? ntoks : 0;
-                    for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (uint32_t)o) incl += v; }
+                    const uint32_t vis = visF | visH;
+                    const bool onpath = (vis >> lane) & 1u;
+                    const bool asH = (visH >> lane) & 1u;
+                    const uint32_t myw = asH ? wH : wF;
+                    const uint32_t incl = __popc(vis & (lane == 31 ? 0xFFFFFFFFu : ((2u << lane) - 1)));   // tokens up to and including mine
+                    const uint32_t e_l = q + (myw & 0x1FF);
+                    const bool ends_iter = !((myw >> 9) & 1);     // next state is F: a main-loop iteration ends here
                     // ---- events ----
-                    const uint32_t e_l = q + adv;
-                    uint32_t rmask = (mode != 0) ? __ballot_sync(0xFFFFFFFFu, onpath && q >= next_recalc) : 0u;
-                    uint32_t cmask = __ballot_sync(0xFFFFFFFFu, onpath && (num_new_obs + incl >= (uint32_t)kObsPerCheck) &&
+                    uint32_t rmask = (mode != 0) ? __ballot_sync(0xFFFFFFFFu, onpath && !asH && q >= next_recalc) : 0u;
+                    uint32_t cmask = __ballot_sync(0xFFFFFFFFu, onpath && ends_iter && (num_new_obs + incl >= (uint32_t)kObsPerCheck) &&
                                                                      (e_l - bb >= (uint32_t)kMinBlockLength) && (n - e_l >= (uint32_t)kMinBlockLength));
                     int Lr = rmask ? __ffs(rmask) - 1 : 64, Lc = cmask ? __ffs(cmask) - 1 : 64;
-                    uint32_t commit_mask, next_p;
+                    uint32_t commit_mask, next_p, next_h;
                     int event = 0;   // 1 = recalc before lane Lr, 2 = block check after lane Lc
-                    if (Lr <= Lc && Lr < 64) { event = 1; commit_mask = pathmask & ((1u << Lr) - 1); next_p = p + Lr; }
-                    else if (Lc < 64) { event = 2; commit_mask = pathmask & (Lc == 31 ? 0xFFFFFFFFu : ((2u << Lc) - 1)); next_p = __shfl_sync(0xFFFFFFFFu, e_l, Lc); }
-                    else { commit_mask = pathmask; next_p = p + c; }
+                    if (Lr <= Lc && Lr < 64) { event = 1; commit_mask = vis & ((1u << Lr) - 1); next_p = p + Lr; next_h = 0; }
+                    else if (Lc < 64) { event = 2; commit_mask = vis & (Lc == 31 ? 0xFFFFFFFFu : ((2u << Lc) - 1)); next_p = __shfl_sync(0xFFFFFFFFu, e_l, Lc); next_h = 0; }
+                    else { commit_mask = vis; next_p = p + c; next_h = st_h; }
                     // ---- commit ----
-                    const bool mine = (commit_mask >> lane) & 1u;
-                    if (mine) {
-                        if (bad) S.status = -9;
-                        uint32_t ti = ntok + incl - ntoks;
-                        for (uint32_t i = 0; i < nlit; i++) {
-                            uint32_t lit = P.B(q + i);
-                            atomicAdd(&S.fl[lit], 1u);
-                            atomicAdd(&S.new_obs[((lit >> 5) & 6) | (lit & 1)], 1u);
-                            tok[ti++] = lit;
-                        }
-                        if (mlen) {
+                    if ((commit_mask >> lane) & 1u) {
+                        const uint32_t ti = ntok + incl - 1;
+                        if ((myw >> 10) & 1) {
+                            const uint32_t mlen = asH ? lenH : lenF, moff = asH ? offH : offF;
                             atomicAdd(&S.fl[kFirstLenSym + len_slot_only(mlen)], 1u);
                             atomicAdd(&S.fo[off_slot_only(moff)], 1u);
                             atomicAdd(&S.new_obs[8 + (mlen >= 9)], 1u);
                             tok[ti] = 0x80000000u | (mlen << 16) | moff;
+                        } else {
+                            const uint32_t lit = P.B(q);
+                            atomicAdd(&S.fl[lit], 1u);
+                            atomicAdd(&S.new_obs[((lit >> 5) & 6) | (lit & 1)], 1u);
+                            tok[ti] = lit;
                         }
                     }
                     {
-                        uint32_t last = commit_mask ? 31 - __clz(commit_mask) : 0;
-                        uint32_t added = commit_mask ? __shfl_sync(0xFFFFFFFFu, incl, last) : 0;
+                        uint32_t added = __popc(commit_mask);
                         ntok += added; num_new_obs += added;
                     }
+                    in_h = next_h;
                     p = next_p;
                     __syncwarp();
                     if (event == 1) {
@@ -741,13 +769,16 @@ k_emit(const uint8_t *__restrict__ in_base, const uint32_t *__restrict__ unit_le
                     S.fl[kEndOfBlock] += 1;
                 }
             }
+            PHASE(1);
             __syncthreads();
-            __threadfence_block();
+            PHASE(2);
             // ---------------- finish block (all threads) ----------------
             const uint32_t be = S.blk_end, ntok = S.ntok, block_len = be - bb, is_final = S.is_final;
             uint8_t *ll = S.lens, *ol = S.lens + kNumLitlen;
             make_huffman_code<uint16_t>(S, S.fl, kNumLitlen, kMaxLitlenCw, ll, S.lcw);
+            PHASE(3);
             make_huffman_code<uint16_t>(S, S.fo, kNumOffset, kMaxOffsetCw, ol, S.ocw);
+            PHASE(4);
             if (tid == 0) {
                 // deflate_precompute_huffman_header(): RLE of the code lengths
                 uint32_t nlit = kNumLitlen, noff = kNumOffset;
@@ -784,7 +815,9 @@ k_emit(const uint8_t *__restrict__ in_base, const uint32_t *__restrict__ unit_le
                 S.nitems = ni;
             }
             __syncthreads();
+            PHASE(5);
             make_huffman_code<uint16_t>(S, S.pfreq, kNumPrecode, kMaxPreCw, S.plen, S.pcw);
+            PHASE(6);
             if (tid == 0) {
                 const uint8_t perm[19] = {16,17,18,0,8,7,9,6,10,5,11,4,12,3,13,2,14,1,15};
                 uint32_t nexpl = kNumPrecode;
@@ -826,6 +859,7 @@ k_emit(const uint8_t *__restrict__ in_base, const uint32_t *__restrict__ unit_le
             }
             __syncthreads();
             const uint32_t btype = S.btype;
+            PHASE(7);
             if (btype == 0) {
                 uint32_t pos = bb;
                 do {
@@ -880,6 +914,7 @@ k_emit(const uint8_t *__restrict__ in_base, const uint32_t *__restrict__ unit_le
                 __syncthreads();
                 hbits = S.scan[0];
                 stage_commit(S, payload, hbits);
+                PHASE(8);
                 // ---- tokens (parallel) ----
                 const bool dynamic = (btype == 2);
                 for (uint32_t t0 = 0; t0 < ntok + 1; t0 += kChunkTok) {   // +1: the end-of-block symbol rides as a token
@@ -928,11 +963,13 @@ k_emit(const uint8_t *__restrict__ in_base, const uint32_t *__restrict__ unit_le
                     stage_commit(S, payload, total);
                 }
             }
+            PHASE(9);
             p = be;   // (only thread 0's copy matters)
             if (be >= n) break;
         }
     }
 
+    PHASE(10);
     // ---- stream tail: sync-flush marker, final partial byte, container ----
     if (sync_flush) {
         stage_begin(S, 8);
@@ -1070,6 +1107,12 @@ k_crc32(const uint8_t *__restrict__ in_base, const uint32_t *__restrict__ unit_l
     if ((tid & 31) == 0 && acc) atomicXor(&s_crc, acc);
     __syncthreads();
     if (tid == 0) crc_out[u] = s_crc;
+}
+
+void read_phase_counters(unsigned long long *out, bool reset)
+{
+    cudaMemcpyFromSymbol(out, g_phase, sizeof(unsigned long long) * 32);
+    if (reset) { unsigned long long z[32] = {0}; cudaMemcpyToSymbol(g_phase, z, sizeof z); }
 }
 
 // ---------------------------------------------------------------------------

@@ -55,6 +55,7 @@ struct DeflateBatch {
 };
 
 void upload_deflate_constants();
+void read_phase_counters(unsigned long long *out, bool reset);
 cudaError_t launch_deflate_pipeline(const DeflateBatch &b, cudaStream_t st);
 cudaError_t launch_pack(const DeflateBatch &b, cudaStream_t st);
 

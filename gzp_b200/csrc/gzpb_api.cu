@@ -293,6 +293,16 @@ extern "C" int gzpb_kernel_ms(gzpb_ctx *c, const char *name, double *total_ms, u
 
 extern "C" uint64_t gzpb_launch_count(gzpb_ctx *c) { return c ? c->launches : 0; }
 
+/* debugging aid (not part of the reference-facing surface): SM-cycle totals per kernel phase */
+extern "C" int gzpb_debug_phase_cycles(gzpb_ctx *c, uint64_t *out32, int reset)
+{
+    if (!c || !out32) return GZPB_EINVAL;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    read_phase_counters((unsigned long long *)out32, reset != 0);
+    return GZPB_OK;
+}
+
 static uint32_t unit_flags_for(int format, int is_last)
 {
     switch (format) {

@@ -141,3 +141,22 @@ def fastq(nbytes, seed=0x5EED0005):
         if len(out) >= nbytes:
             break
     return bytes(out[:nbytes])
+
+
+def text_stream(nbytes, seed=0x5EED0001):
+    """`nbytes` of the TEXT_PERIOD-byte synthetic corpus repeated, exactly as the reference
+    bench concatenates shakespeare.txt xN (benches/bench.rs, README.md:166-167)."""
+    import os
+    cache = f"/tmp/gzpb_text_{TEXT_PERIOD}_{seed:x}.bin"
+    if os.path.exists(cache) and os.path.getsize(cache) == TEXT_PERIOD:
+        base = open(cache, "rb").read()
+    else:
+        base = text(TEXT_PERIOD, seed)
+        try:
+            with open(cache + ".tmp", "wb") as f:
+                f.write(base)
+            os.replace(cache + ".tmp", cache)
+        except OSError:
+            pass
+    reps = nbytes // TEXT_PERIOD + 1
+    return (base * reps)[:nbytes]

@@ -1,0 +1,160 @@
+"""CPU tests: pin the oracle (the parity judge of the GPU tests) against the golden
+vectors and known-answer material the reference holds for this path
+and against stock decoders — the reference's own test strategy
+(/root/reference/src/deflate.rs:679-1379: compress -> independent decoder -> equal)."""
+import gzip
+import json
+import os
+import random
+import zlib
+
+import pytest
+
+import oracle
+from oracle import BGZF, GZIP, MGZIP, RAWDEFLATE, SNAP, ZLIB
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_vectors.json")))
+BGZF_EOF = bytes.fromhex(GOLD["bgzf_eof_hex"])
+
+
+def test_bgzf_eof_marker_is_the_reference_constant():
+    # /root/reference/src/bgzf.rs:24-38
+    assert len(BGZF_EOF) == 28
+    z = oracle.compress_stream(BGZF, 6, 65280, [b""])
+    assert z.endswith(BGZF_EOF)
+    assert gzip.decompress(z) == b""
+
+
+def test_crc_known_answers():
+    assert oracle.crc32(b"123456789") == 0xCBF43926
+    assert oracle.crc32c(b"123456789") == 0xE3069283
+    assert oracle.lib().oracle_crc32c_masked(b"123456789", 9) == 0xC78AB0E5
+    rnd = random.Random(1)
+    for _ in range(50):
+        a = bytes(rnd.randrange(256) for _ in range(rnd.randrange(0, 5000)))
+        b = bytes(rnd.randrange(256) for _ in range(rnd.randrange(0, 5000)))
+        assert oracle.crc32(a) == zlib.crc32(a)
+        assert oracle.lib().oracle_crc32_combine(zlib.crc32(a), zlib.crc32(b), len(b)) == zlib.crc32(a + b)
+        assert oracle.lib().oracle_adler32(1, a, len(a)) == zlib.adler32(a)
+        assert oracle.lib().oracle_adler32_combine(zlib.adler32(a), zlib.adler32(b), len(b)) == zlib.adler32(a + b)
+
+
+def test_header_recipes():
+    # bgzf.rs:274-303, mgzip.rs:246-275, deflate.rs:113-133, 221-243
+    for level, xfl in ((1, 4), (3, 0), (6, 0), (9, 2)):
+        if oracle.lib().oracle_level_supported(level):
+            b = oracle.encode_block(BGZF, level, b"hello world, hello world, hello world")
+            assert b[:16] == bytes([31, 139, 8, 4, 0, 0, 0, 0, xfl, 255, 6, 0, 0x42, 0x43, 2, 0])
+            assert int.from_bytes(b[16:18], "little") == len(b) - 1
+            m = oracle.encode_block(MGZIP, level, b"hello world, hello world, hello world")
+            assert m[:16] == bytes([31, 139, 8, 4, 0, 0, 0, 0, xfl, 255, 8, 0, 0x49, 0x47, 4, 0])
+            assert int.from_bytes(m[16:20], "little") == len(m)
+        assert oracle.header(GZIP, level) == bytes([31, 139, 8, 0, 0, 0, 0, 0, xfl, 255])
+    # deflate.rs:221-243 as written: level>=6 -> FLEVEL 1, 2..5 -> FLEVEL 2 (mirrored verbatim)
+    assert oracle.header(ZLIB, 6) == b"\x78\x5e" and oracle.header(ZLIB, 9) == b"\x78\xda" and oracle.header(ZLIB, 3) == b"\x78\x9c"
+    assert oracle.footer(GZIP, 0x11223344, 5) == bytes.fromhex("4433221105000000")
+    assert oracle.footer(ZLIB, 0x11223344, 5) == bytes.fromhex("11223344")
+
+
+def test_reference_regression_vector_gzip():
+    # /root/reference/src/deflate.rs:949-992 (test_regression): 206 fixed bytes, buffer_size = DICT_SIZE
+    data = bytes(GOLD["regression_input"])
+    assert len(data) == 206
+    z = oracle.compress_stream(GZIP, 3, 32768, [data])
+    assert gzip.decompress(z) == data
+
+
+@pytest.mark.parametrize("fmt", [GZIP, ZLIB, RAWDEFLATE, MGZIP, BGZF])
+@pytest.mark.parametrize("level", [0, 2, 3, 6, 9])
+def test_streams_decode_with_stock_decoders(fmt, level, text_corpus):
+    # multi-block streams incl. dictionary carry, partial last block, odd write sizes
+    bs = 65280 if fmt == BGZF else 40000
+    data = text_corpus[: 3 * bs + 1234]
+    rnd = random.Random(level)
+    writes, pos = [], 0
+    while pos < len(data):
+        k = rnd.randrange(1, 10000)
+        writes.append(data[pos: pos + k]); pos += k
+    z = oracle.compress_stream(fmt, level, bs, writes)
+    if fmt in (GZIP, MGZIP, BGZF):
+        assert gzip.decompress(z) == data
+    elif fmt == ZLIB:
+        assert zlib.decompress(z) == data
+    else:
+        assert zlib.decompressobj(-15).decompress(z) == data
+
+
+def test_proptest_analogue_random_bytes():
+    # deflate.rs:1053-1379: random bytes 0..u8::MAX (exclusive), odd buffer / write sizes
+    rnd = random.Random(99)
+    for _ in range(12):
+        n = rnd.randrange(1, 120000)
+        data = bytes(rnd.randrange(255) for _ in range(n))
+        bs = rnd.randrange(32768, 65280)
+        level = rnd.choice([2, 3, 4, 5, 6, 7, 8, 9])
+        z = oracle.compress_stream(BGZF, level, bs, [data])
+        assert gzip.decompress(z) == data
+        z = oracle.compress_stream(GZIP, level, bs, [data])
+        assert gzip.decompress(z) == data
+
+
+def test_flush_emits_short_blocks_and_empty_block():
+    # par/compress.rs:332-362, 466-468: flush() on an empty buffer still emits an (empty) block
+    msgs = oracle.chunk_stream(BGZF, 65280, [b"abc", b"", b"def"], flushes={0, 1})
+    assert [(m[0], m[2]) for m in msgs] == [(b"abc", False), (b"", False), (b"def", True)]
+    # strict '>' hold-back: exactly buffer_size bytes stay buffered until finish
+    msgs = oracle.chunk_stream(BGZF, 65280, [b"x" * 65280])
+    assert len(msgs) == 1 and msgs[0][2] is True
+    msgs = oracle.chunk_stream(BGZF, 65280, [b"x" * 65281])
+    assert [len(m[0]) for m in msgs] == [65280, 1]
+    # dictionary rule (Gzip): last 32 KiB of the previous block
+    msgs = oracle.chunk_stream(GZIP, 40000, [bytes(range(256)) * 400])
+    assert msgs[0][1] is None and msgs[1][1] == msgs[0][0][-32768:]
+
+
+def test_snappy_frame_decodes_with_stock_snappy(text_corpus):
+    pa = pytest.importorskip("pyarrow")
+    codec = pa.Codec("snappy")
+    from gzp_b200 import synth
+    for data in (text_corpus[:131072], synth.low_entropy(200000), bytes(random.Random(3).randrange(256) for _ in range(70000)), b"a"):
+        z = oracle.encode_block(SNAP, 0, data)
+        assert z[:10] == bytes.fromhex("ff060000734e61507059")
+        pos, out = 10, b""
+        while pos < len(z):
+            t = z[pos]; ln = int.from_bytes(z[pos + 1: pos + 4], "little")
+            crc = int.from_bytes(z[pos + 4: pos + 8], "little"); body = z[pos + 8: pos + 4 + ln]; pos += 4 + ln
+            if t == 0:
+                v = sh = i = 0
+                while True:
+                    b = body[i]; v |= (b & 0x7F) << sh; sh += 7; i += 1
+                    if b < 0x80:
+                        break
+                dec = codec.decompress(body, decompressed_size=v).to_pybytes()
+            else:
+                assert t == 1
+                dec = body
+            assert oracle.lib().oracle_crc32c_masked(dec, len(dec)) == crc
+            out += dec
+        assert out == data
+    assert oracle.encode_block(SNAP, 0, b"") == b""
+
+
+def test_static_huffman_code_is_rfc1951_fixed_code():
+    import ctypes
+    f = (ctypes.c_uint32 * 288)(*([2] * 144 + [1] * 112 + [4] * 24 + [2] * 8))
+    lens = (ctypes.c_uint8 * 288)(); cw = (ctypes.c_uint32 * 288)()
+    oracle.lib().oracle_make_huffman_code(288, 15, f, lens, cw)
+    assert list(lens) == [8] * 144 + [9] * 112 + [7] * 24 + [8] * 8
+    rev = lambda v, n: int(bin(v)[2:].zfill(n)[::-1], 2)
+    assert cw[0] == rev(0x30, 8) and cw[144] == rev(0x190, 9) and cw[256] == 0 and cw[280] == rev(0xC0, 8)
+
+
+def test_par_oracle_topology_matches_sequential_stream(text_corpus):
+    import ctypes
+    data = text_corpus[: 65280 * 9 + 55]
+    for fmt, bs in ((BGZF, 65280), (GZIP, 40000)):
+        out = ctypes.create_string_buffer(len(data) + 4096)
+        olen = ctypes.c_size_t(0)
+        t = oracle.lib().oracle_par_compress(fmt, 6, bs, 4, data, len(data), out, len(out), ctypes.byref(olen))
+        assert t > 0
+        assert out.raw[: olen.value] == oracle.compress_stream(fmt, 6, bs, [data])
