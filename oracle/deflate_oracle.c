@@ -662,6 +662,17 @@ static int level_params(int level, unsigned *depth, unsigned *nice, int *mode)
 
 int oracle_level_supported(int level) { unsigned d, nn; int m; return level == 0 || level_params(level, &d, &nn, &m) == 0; }
 
+/* per-thread scratch (see oracle_deflate_ex); released by oracle_thread_cleanup() */
+static __thread int32_t *t_head3, *t_head4, *t_next;
+static __thread uint32_t *t_tokens;
+static __thread size_t t_cap;
+
+void oracle_thread_cleanup(void)
+{
+    free(t_head3); free(t_head4); free(t_next); free(t_tokens);
+    t_head3 = t_head4 = t_next = NULL; t_tokens = NULL; t_cap = 0;
+}
+
 /* General entry: in[0..dict_len) is a preset dictionary, in[dict_len..dict_len+n)
  * the data.  flush: 0 = finish (BFINAL on the last block), 1 = sync flush (no
  * BFINAL; append an empty stored block so the segment ends byte-aligned). */
@@ -680,11 +691,17 @@ size_t oracle_deflate_ex(const uint8_t *in, size_t dict_len, size_t n, int level
         compress_none(in + dict_len, n, &w, final_block);
     } else if (n > 0) {
         size_t tot = dict_len + n;
-        c.head3 = malloc(32768 * sizeof(int32_t)); c.head4 = malloc(65536 * sizeof(int32_t));
-        c.next = malloc((tot + 1) * sizeof(int32_t)); c.tokens = malloc((n + 1) * sizeof(uint32_t));
+        /* per-thread scratch, grown on demand and reused across calls (like a
+         * libdeflate_compressor that lives as long as its worker thread) */
+        if (!t_head3) { t_head3 = malloc(32768 * sizeof(int32_t)); t_head4 = malloc(65536 * sizeof(int32_t)); }
+        if (t_cap < tot + 1) {
+            free(t_next); free(t_tokens);
+            t_cap = tot + 1 + tot / 4;
+            t_next = malloc(t_cap * sizeof(int32_t)); t_tokens = malloc(t_cap * sizeof(uint32_t));
+        }
+        c.head3 = t_head3; c.head4 = t_head4; c.next = t_next; c.tokens = t_tokens;
         init_static(&c);
         compress_hc(&c, in, dict_len, tot, &w, final_block);
-        free(c.head3); free(c.head4); free(c.next); free(c.tokens);
     }
     if (flush == 1) {
         /* Z_SYNC_FLUSH marker: empty stored block, byte aligned: 00 00 ff ff */

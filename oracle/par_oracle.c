@@ -23,29 +23,29 @@ typedef struct {
 } ticket_t;
 
 typedef struct {
-    pthread_mutex_t mu; pthread_cond_t cv;
+    pthread_mutex_t mu; pthread_cond_t not_empty, not_full;
     ticket_t **ring; size_t cap, head, tail; int closed;
 } chan_t;
 
-static void chan_init(chan_t *c, size_t cap) { pthread_mutex_init(&c->mu, 0); pthread_cond_init(&c->cv, 0); c->ring = calloc(cap, sizeof(*c->ring)); c->cap = cap; c->head = c->tail = 0; c->closed = 0; }
+static void chan_init(chan_t *c, size_t cap) { pthread_mutex_init(&c->mu, 0); pthread_cond_init(&c->not_empty, 0); pthread_cond_init(&c->not_full, 0); c->ring = calloc(cap, sizeof(*c->ring)); c->cap = cap; c->head = c->tail = 0; c->closed = 0; }
 static void chan_send(chan_t *c, ticket_t *t)
 {
     pthread_mutex_lock(&c->mu);
-    while (c->tail - c->head == c->cap) pthread_cond_wait(&c->cv, &c->mu);
+    while (c->tail - c->head == c->cap) pthread_cond_wait(&c->not_full, &c->mu);
     c->ring[c->tail++ % c->cap] = t;
-    pthread_cond_broadcast(&c->cv);
+    pthread_cond_signal(&c->not_empty);
     pthread_mutex_unlock(&c->mu);
 }
 static ticket_t *chan_recv(chan_t *c)
 {
     ticket_t *t = 0;
     pthread_mutex_lock(&c->mu);
-    while (c->tail == c->head && !c->closed) pthread_cond_wait(&c->cv, &c->mu);
-    if (c->tail != c->head) { t = c->ring[c->head++ % c->cap]; pthread_cond_broadcast(&c->cv); }
+    while (c->tail == c->head && !c->closed) pthread_cond_wait(&c->not_empty, &c->mu);
+    if (c->tail != c->head) { t = c->ring[c->head++ % c->cap]; pthread_cond_signal(&c->not_full); }
     pthread_mutex_unlock(&c->mu);
     return t;
 }
-static void chan_close(chan_t *c) { pthread_mutex_lock(&c->mu); c->closed = 1; pthread_cond_broadcast(&c->cv); pthread_mutex_unlock(&c->mu); }
+static void chan_close(chan_t *c) { pthread_mutex_lock(&c->mu); c->closed = 1; pthread_cond_broadcast(&c->not_empty); pthread_mutex_unlock(&c->mu); }
 
 typedef struct {
     int format, level; chan_t work, order;
@@ -64,6 +64,7 @@ static void *worker(void *arg)
         else if (p->format == ORACLE_FMT_ZLIB) { t->sum = oracle_adler32(1, t->buf, t->len); t->amount = (uint32_t)t->len; }
         pthread_mutex_lock(&p->dmu); t->done = 1; pthread_cond_broadcast(&p->dcv); pthread_mutex_unlock(&p->dmu);
     }
+    oracle_thread_cleanup();
     return 0;
 }
 
