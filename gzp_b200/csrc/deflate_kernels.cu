@@ -22,7 +22,7 @@
 namespace gzpb {
 
 __constant__ uint32_t c_crc_tab[4][256];      // slicing-by-4, reflected 0xEDB88320
-__constant__ uint32_t c_xpow512[130];         // x^(8*512*j) mod P
+__constant__ uint32_t c_xpow512[1024];        // x^(8*512*j) mod P
 __constant__ uint16_t c_static_litlen_cw[288];
 __constant__ uint8_t c_static_litlen_len[288];
 __constant__ uint8_t c_min_lens[80];
@@ -41,8 +41,8 @@ void upload_deflate_constants()
     for (uint32_t i = 0; i < 256; i++)
         for (int s = 1; s < 4; s++) tab[s][i] = (tab[s - 1][i] >> 8) ^ tab[0][tab[s - 1][i] & 0xFF];
     cudaMemcpyToSymbol(c_crc_tab, tab, sizeof tab);
-    uint32_t xp[130];
-    for (int j = 0; j < 130; j++) xp[j] = gf2_xpow8((uint64_t)512 * j, kCrcPoly);
+    static uint32_t xp[1024];
+    for (int j = 0; j < 1024; j++) xp[j] = gf2_xpow8((uint64_t)512 * j, kCrcPoly);
     cudaMemcpyToSymbol(c_xpow512, xp, sizeof xp);
     uint16_t cw[288]; uint8_t ln[288];
     for (int s = 0; s < 288; s++) {
@@ -61,17 +61,50 @@ void upload_deflate_constants()
     cudaMemcpyToSymbol(c_min_lens, min_lens, sizeof min_lens);
 }
 
+// Sub-unit geometry.  A unit (one gzp block, with its optional 32 KiB dictionary in
+// front) longer than 65 536 positions is searched in segments of `seg` new
+// positions; each segment's chain/match kernels see a sub-unit = [32 KiB halo |
+// seg new positions | 262 bytes of look-ahead] <= 65 536 bytes.  Links beyond the
+// 32 KiB window are never followed, so the halo reproduces the full-history chains
+// exactly (bit-identical results, tests/test_gpu_parity.py).
+struct Geo {
+    const uint8_t *in;         // unit slots
+    const uint32_t *unit_len;  // dict + data bytes
+    const uint32_t *unit_dict; // dictionary bytes in front of the data
+    uint32_t in_stride, m_stride, tok_stride, out_stride;
+    uint32_t spu, seg;         // sub-units per unit, new positions per sub-unit
+};
+struct Sub { uint32_t u, h, len, nb, ne, quirk; bool valid; };
+
+__device__ __forceinline__ Sub sub_geometry(const Geo &g, uint32_t sub)
+{
+    Sub r;
+    r.u = sub / g.spu;
+    const uint32_t k = sub % g.spu;
+    const uint32_t n = g.unit_len[r.u], dict = g.unit_dict[r.u];
+    if (g.spu == 1) {
+        r.h = 0; r.len = n; r.nb = dict; r.ne = n; r.quirk = (dict == 0); r.valid = n > dict;
+        return r;
+    }
+    const uint32_t a = dict + k * g.seg;
+    r.valid = a < n;
+    const uint32_t b = min(a + g.seg, n);
+    r.h = a > (uint32_t)kWindow ? ((a - kWindow) & ~15u) : 0u;
+    const uint32_t t = min(n, b + 262u);
+    r.len = r.valid ? t - r.h : 0; r.nb = a - r.h; r.ne = b - r.h; r.quirk = (r.h == 0 && dict == 0);
+    return r;
+}
+
 // =============================================================================
-// k_chain: hash chains + CRC-32.  1 CTA (256 threads) per unit, 1 CTA per SM.
+// k_chain: hash chains.  1 CTA (256 threads) per unit, 1 CTA per SM.
 //   warp 0      : hash4 buckets -> next4[p] = distance to the previous position
 //                 with the same 16-bit hash (0 = none / outside the 32 KiB window)
 //   warp 1      : hash3 buckets -> prev3[p] likewise (15-bit hash of 3 bytes)
-//   warps 2..7  : CRC-32 of the unit (512-byte chunks, GF(2) recombination)
 // Shared memory: head4 u16[65536] + head3 u16[32768] = 192 KiB.
 // Restates the insertion side of libdeflate's hc_matchfinder: every position
 // p <= n-5 is inserted, position 0 under hash 0 (next_hashes starts at {0,0}).
 // =============================================================================
-constexpr int kChainThreads = 256;
+constexpr int kChainThreads = 64;
 constexpr uint32_t kNone16 = 0xFFFFu;
 
 __device__ __forceinline__ uint32_t ldg32u(const uint32_t *__restrict__ words, uint32_t byte_pos)
@@ -137,22 +170,20 @@ __device__ __forceinline__ void chain_warp(const uint32_t *__restrict__ inw, uin
 }
 
 __global__ void __launch_bounds__(kChainThreads, 1)
-k_chain(const uint8_t *__restrict__ in_base, const uint32_t *__restrict__ unit_len, uint16_t *__restrict__ next4,
-        uint16_t *__restrict__ prev3, uint32_t *__restrict__ crc_out)
+k_chain(const __grid_constant__ Geo g, uint16_t *__restrict__ next4, uint16_t *__restrict__ prev3)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     uint16_t *head4 = (uint16_t *)smem;
     uint16_t *head3 = head4 + 65536;
-    uint32_t(*s_tab)[256] = (uint32_t(*)[256])(smem + (65536 + 32768) * 2);
-    __shared__ uint32_t s_crc;
-    const uint32_t u = blockIdx.x;
-    const uint32_t n = unit_len[u];
-    const uint8_t *in = in_base + (size_t)u * kInStride;
+    const Sub sb = sub_geometry(g, blockIdx.x);
+    if (!sb.valid) return;
+    const uint32_t n = sb.len;
+    const uint8_t *in = g.in + (size_t)sb.u * g.in_stride + sb.h;
     const uint32_t *inw = (const uint32_t *)in;
     const uint32_t tid = threadIdx.x, warp = tid >> 5;
 
     const long long t_start = clock64();
-    // pull the unit into L2 ahead of the dependent loads
+    // pull the sub-unit into L2 ahead of the dependent loads
     for (uint32_t off = tid * 128; off < n; off += kChainThreads * 128)
         asm volatile("prefetch.global.L2 [%0];" ::"l"(in + off));
     {
@@ -160,38 +191,14 @@ k_chain(const uint8_t *__restrict__ in_base, const uint32_t *__restrict__ unit_l
         uint4 *h = (uint4 *)smem;
         for (uint32_t i = tid; i < (65536 + 32768) * 2 / 16; i += kChainThreads) h[i] = ones;
     }
-    for (uint32_t i = tid; i < 1024; i += kChainThreads) s_tab[i >> 8][i & 255] = c_crc_tab[i >> 8][i & 255];
-    if (tid == 0) s_crc = 0;
     __syncthreads();
 
     if (warp == 0) {
-        long long t0 = clock64();
-        chain_warp<16, false>(inw, n, 0, head4, next4 + (size_t)u * kMaxUnitBytes);
-        if (tid == 0) atomicAdd(&g_phase[16], (unsigned long long)(clock64() - t0));
+        chain_warp<16, false>(inw, n, !sb.quirk, head4, next4 + (size_t)blockIdx.x * kMaxUnitBytes);
+        if (tid == 0) atomicAdd(&g_phase[16], (unsigned long long)(clock64() - t_start));
     } else if (warp == 1) {
-        chain_warp<15, true>(inw, n, 0, head3, prev3 + (size_t)u * kMaxUnitBytes);
-    } else {
-        // CRC-32: chunk j covers [n-512(j+1), n-512j) clipped at 0; combine with x^(8*512*j)
-        uint32_t acc = 0;
-        for (uint32_t j = tid - 64; j * 512 < n; j += kChainThreads - 64) {
-            uint32_t end = n - 512 * j, beg = end >= 512 ? end - 512 : 0;
-            uint32_t c = ~0u, pos = beg;
-            while (pos < end && (pos & 3)) { c = (c >> 8) ^ s_tab[0][(c ^ in[pos]) & 0xFF]; pos++; }
-            for (; pos + 4 <= end; pos += 4) {
-                c ^= __ldg(inw + (pos >> 2));
-                c = s_tab[3][c & 0xFF] ^ s_tab[2][(c >> 8) & 0xFF] ^ s_tab[1][(c >> 16) & 0xFF] ^ s_tab[0][c >> 24];
-            }
-            while (pos < end) { c = (c >> 8) ^ s_tab[0][(c ^ in[pos]) & 0xFF]; pos++; }
-            c = ~c;
-            acc ^= (j == 0) ? c : gf2_mulmod(c, c_xpow512[j], kCrcPoly);
-        }
-#pragma unroll
-        for (int o = 16; o; o >>= 1) acc ^= __shfl_xor_sync(0xFFFFFFFFu, acc, o);
-        if ((tid & 31) == 0 && acc) atomicXor(&s_crc, acc);
-        if (tid == 64) atomicAdd(&g_phase[17], (unsigned long long)(clock64() - t_start));
+        chain_warp<15, true>(inw, n, !sb.quirk, head3, prev3 + (size_t)blockIdx.x * kMaxUnitBytes);
     }
-    __syncthreads();
-    if (tid == 0) { crc_out[u] = s_crc; atomicAdd(&g_phase[18], (unsigned long long)(clock64() - t_start)); }
 }
 
 // =============================================================================
@@ -218,17 +225,19 @@ __device__ __forceinline__ uint32_t lz_extend(const uint32_t *s_in, uint32_t p, 
 }
 
 __global__ void __launch_bounds__(kMatchThreads, 1)
-k_match(const uint8_t *__restrict__ in_base, const uint32_t *__restrict__ unit_len, const uint16_t *__restrict__ next4g,
-        const uint16_t *__restrict__ prev3g, uint64_t *__restrict__ mtab, int depth, int nice, int lazy)
+k_match(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, const uint16_t *__restrict__ prev3g,
+        uint64_t *__restrict__ mtab, int depth, int nice, int lazy)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     uint32_t *s_in = (uint32_t *)smem;
     uint16_t *s_next = (uint16_t *)(smem + kInStride);
     __shared__ __align__(8) uint64_t bar;
-    const uint32_t u = blockIdx.x, tid = threadIdx.x;
-    const uint32_t n = unit_len[u];
-    const uint8_t *in = in_base + (size_t)u * kInStride;
-    uint64_t *M = mtab + (size_t)u * kMaxUnitBytes;
+    const uint32_t tid = threadIdx.x;
+    const Sub sb = sub_geometry(g, blockIdx.x);
+    if (!sb.valid) return;
+    const uint32_t n = sb.len;
+    const uint8_t *in = g.in + (size_t)sb.u * g.in_stride + sb.h;
+    uint64_t *M = mtab + (size_t)sb.u * g.m_stride + sb.h;
 
     if (tid == 0) {
         mbar_init(&bar, 1);
@@ -240,14 +249,14 @@ k_match(const uint8_t *__restrict__ in_base, const uint32_t *__restrict__ unit_l
             uint32_t bin = (n + 15u) & ~15u, bnx = (n * 2 + 15u) & ~15u;
             mbar_expect_tx(&bar, bin + bnx);
             tma_load_1d(s_in, in, bin, &bar);
-            tma_load_1d(s_next, next4g + (size_t)u * kMaxUnitBytes, bnx, &bar);
+            tma_load_1d(s_next, next4g + (size_t)blockIdx.x * kMaxUnitBytes, bnx, &bar);
         }
         mbar_wait(&bar, 0);
     }
-    const uint16_t *p3 = prev3g + (size_t)u * kMaxUnitBytes;
+    const uint16_t *p3 = prev3g + (size_t)blockIdx.x * kMaxUnitBytes;
     const uint32_t depthB = (uint32_t)depth >> 1;
 
-    for (uint32_t p = tid; p < n; p += kMatchThreads) {
+    for (uint32_t p = sb.nb + tid; p < sb.ne; p += kMatchThreads) {
         const uint32_t maxlen = min((uint32_t)kMaxMatch, n - p);
         if (maxlen < 5) { M[p] = 0; continue; }
         const uint32_t nicep = min((uint32_t)nice, maxlen);
@@ -541,25 +550,27 @@ __device__ __forceinline__ void table_search(uint64_t e, uint32_t b, bool useB, 
 }
 
 __global__ void __launch_bounds__(kEmitThreads)
-k_emit(const uint8_t *__restrict__ in_base, const uint32_t *__restrict__ unit_len, const uint32_t *__restrict__ unit_flags,
+k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
        const uint64_t *__restrict__ mtab, const uint32_t *__restrict__ crc_in, uint32_t *__restrict__ tok_base,
        uint8_t *__restrict__ out_base, uint32_t *__restrict__ out_len, int32_t *__restrict__ out_status,
        int mode, int depth, int nice, int level, int format)
 {
     __shared__ EmitShared S;
     const uint32_t u = blockIdx.x, tid = threadIdx.x;
-    const uint32_t n = unit_len[u];
+    const uint32_t n = g.unit_len[u];          // dictionary + data
+    const uint32_t dict = g.unit_dict[u];      // preset dictionary in front of the data (never emitted)
+    const uint32_t dl = n - dict;              // bytes to encode
     const uint32_t flags = unit_flags[u];
-    const uint8_t *in = in_base + (size_t)u * kInStride;
-    uint32_t *tok = tok_base + (size_t)u * kTokStride;
-    uint8_t *slot = out_base + (size_t)u * kOutStride;
+    const uint8_t *in = g.in + (size_t)u * g.in_stride;
+    uint32_t *tok = tok_base + (size_t)u * g.tok_stride;
+    uint8_t *slot = out_base + (size_t)u * g.out_stride;
     uint32_t *payload = (uint32_t *)(slot + kOutPayloadOff);
     const bool sync_flush = (flags & 2u) != 0;    // Gzip/Zlib non-last and RawDeflate: no BFINAL, sync marker
     const bool final_block = !sync_flush;
 
     Parser P;
-    P.mt_g = mtab + (size_t)u * kMaxUnitBytes; P.in_g = in; P.S = &S; P.n = n;
-    P.ntiles = (n + kTile - 1) / kTile; P.issued = 0; P.ready = 0;
+    P.mt_g = mtab + (size_t)u * g.m_stride; P.in_g = in; P.S = &S; P.n = n;
+    P.ntiles = (n + kTile - 1) / kTile; P.issued = dict / kTile; P.ready = dict / kTile;
 
     if (tid == 0) {
         for (int i = 0; i < kRing; i++) mbar_init(&S.bar[i], 1);
@@ -571,9 +582,9 @@ k_emit(const uint8_t *__restrict__ in_base, const uint32_t *__restrict__ unit_le
     long long t_prev = clock64();
 #define PHASE(idx_) do { if (tid == 0) { long long t_ = clock64(); atomicAdd(&g_phase[idx_], (unsigned long long)(t_ - t_prev)); t_prev = t_; } } while (0)
     const uint32_t passthrough = (level == 0) ? 0xFFFFFFFFu : (uint32_t)(55 - level * 4);
-    if (n <= passthrough && !(sync_flush && n == 0)) {
+    if (dl <= passthrough && !(sync_flush && dl == 0)) {
         // deflate_compress_none(): stored blocks of <= 65535 bytes
-        uint32_t pos = 0;
+        uint32_t pos = dict;
         do {
             uint32_t len = min(n - pos, 65535u);
             uint32_t bfinal = (n - pos <= 65535u) ? (final_block ? 1u : 0u) : 0u;
@@ -595,8 +606,8 @@ k_emit(const uint8_t *__restrict__ in_base, const uint32_t *__restrict__ unit_le
             }
             pos += len;
         } while (pos != n);
-    } else if (n > 0) {
-        uint32_t p = 0;              // parser position (thread 0 only is authoritative)
+    } else if (dl > 0) {
+        uint32_t p = dict;           // parser position (warp 0 is authoritative)
         uint32_t next_recalc = 0, min_len = 3;
         while (true) {
             // ---------------- block start (all threads) ----------------
@@ -633,7 +644,7 @@ k_emit(const uint8_t *__restrict__ in_base, const uint32_t *__restrict__ unit_le
                     min_len = choose_min_match_len(nu, depth);
                 }
                 next_recalc = bb + min(n - bb, 10000u);
-                uint32_t ntok = 0, num_obs = 0, num_new_obs = 0, in_h = 0;
+                uint32_t ntok = 0, nmatch = 0, num_obs = 0, num_new_obs = 0, in_h = 0;
                 bool end_block = false;
                 do {
                     P.advance(p);
@@ -702,10 +713,15 @@ k_emit(const uint8_t *__restrict__ in_base, const uint32_t *__restrict__ unit_le
                     uint32_t rmask = (mode != 0) ? __ballot_sync(0xFFFFFFFFu, onpath && !asH && q >= next_recalc) : 0u;
                     uint32_t cmask = __ballot_sync(0xFFFFFFFFu, onpath && ends_iter && (num_new_obs + incl >= (uint32_t)kObsPerCheck) &&
                                                                      (e_l - bb >= (uint32_t)kMinBlockLength) && (n - e_l >= (uint32_t)kMinBlockLength));
-                    int Lr = rmask ? __ffs(rmask) - 1 : 64, Lc = cmask ? __ffs(cmask) - 1 : 64;
+                    // sequence store full (SEQ_STORE_LENGTH matches in this DEFLATE block): the block ends
+                    const uint32_t mmask = __ballot_sync(0xFFFFFFFFu, onpath && ((myw >> 10) & 1));
+                    const uint32_t mincl = __popc(mmask & (lane == 31 ? 0xFFFFFFFFu : ((2u << lane) - 1)));
+                    uint32_t smask = __ballot_sync(0xFFFFFFFFu, onpath && ends_iter && (nmatch + mincl >= (uint32_t)kSeqStoreLength));
+                    int Lr = rmask ? __ffs(rmask) - 1 : 64, Lc = cmask ? __ffs(cmask) - 1 : 64, Ls = smask ? __ffs(smask) - 1 : 64;
                     uint32_t commit_mask, next_p, next_h;
-                    int event = 0;   // 1 = recalc before lane Lr, 2 = block check after lane Lc
-                    if (Lr <= Lc && Lr < 64) { event = 1; commit_mask = vis & ((1u << Lr) - 1); next_p = p + Lr; next_h = 0; }
+                    int event = 0;   // 1 = recalc before lane Lr, 2 = block check after lane Lc, 3 = sequence store full after lane Ls
+                    if (Lr <= Lc && Lr <= Ls && Lr < 64) { event = 1; commit_mask = vis & ((1u << Lr) - 1); next_p = p + Lr; next_h = 0; }
+                    else if (Ls <= Lc && Ls < 64) { event = 3; commit_mask = vis & (Ls == 31 ? 0xFFFFFFFFu : ((2u << Ls) - 1)); next_p = __shfl_sync(0xFFFFFFFFu, e_l, Ls); next_h = 0; }
                     else if (Lc < 64) { event = 2; commit_mask = vis & (Lc == 31 ? 0xFFFFFFFFu : ((2u << Lc) - 1)); next_p = __shfl_sync(0xFFFFFFFFu, e_l, Lc); next_h = 0; }
                     else { commit_mask = vis; next_p = p + c; next_h = st_h; }
                     // ---- commit ----
@@ -727,6 +743,7 @@ k_emit(const uint8_t *__restrict__ in_base, const uint32_t *__restrict__ unit_le
                     {
                         uint32_t added = __popc(commit_mask);
                         ntok += added; num_new_obs += added;
+                        nmatch += __popc(commit_mask & mmask);
                     }
                     in_h = next_h;
                     p = next_p;
@@ -762,6 +779,8 @@ k_emit(const uint8_t *__restrict__ in_base, const uint32_t *__restrict__ unit_le
                             num_obs += num_new_obs; num_new_obs = 0;
                         }
                         __syncwarp();
+                    } else if (event == 3) {
+                        end_block = true;
                     }
                 } while (p < max_block_end && !end_block);
                 if (lane == 0) {
@@ -1006,17 +1025,17 @@ k_emit(const uint8_t *__restrict__ in_base, const uint32_t *__restrict__ unit_le
             uint8_t *f = slot + kOutPayloadOff + nbytes;
             uint32_t crc = crc_in[u];
             f[0] = (uint8_t)crc; f[1] = (uint8_t)(crc >> 8); f[2] = (uint8_t)(crc >> 16); f[3] = (uint8_t)(crc >> 24);
-            f[4] = (uint8_t)n; f[5] = (uint8_t)(n >> 8); f[6] = (uint8_t)(n >> 16); f[7] = (uint8_t)(n >> 24);
+            f[4] = (uint8_t)dl; f[5] = (uint8_t)(dl >> 8); f[6] = (uint8_t)(dl >> 16); f[7] = (uint8_t)(dl >> 24);
             total = hs + nbytes + 8;
             if (format == 4 && (flags & 1u)) {   // is_last: append BGZF_EOF (deflate.rs:622-624)
                 const uint8_t eof[28] = {0x1f,0x8b,0x08,0x04,0,0,0,0,0,0xff,0x06,0,0x42,0x43,0x02,0,0x1b,0,0x03,0,0,0,0,0,0,0,0,0};
                 for (int i = 0; i < 28; i++) f[8 + i] = eof[i];
                 total += 28;
             }
-            uint32_t avail = n + max(128u, (uint32_t)((double)n * 0.1)) + 8;
+            uint32_t avail = dl + max(128u, (uint32_t)((double)dl * 0.1)) + 8;
             if (nbytes > avail) st = -4;          // GZPB_ECOMPRESS: libdeflate would have returned 0
         } else {
-            uint32_t avail = n + max(128u, (uint32_t)((double)n * 0.1));
+            uint32_t avail = dl + max(128u, (uint32_t)((double)dl * 0.1));
             if (nbytes > avail) st = -4;
         }
         out_len[u * 2] = total;
@@ -1054,12 +1073,12 @@ k_scan(const uint32_t *__restrict__ out_len, uint64_t *__restrict__ offsets, uin
 
 __global__ void __launch_bounds__(256)
 k_gather(const uint8_t *__restrict__ out_base, const uint32_t *__restrict__ out_len, const uint64_t *__restrict__ offsets,
-         uint8_t *__restrict__ dst, const int32_t *__restrict__ overflow)
+         uint8_t *__restrict__ dst, const int32_t *__restrict__ overflow, uint32_t out_stride)
 {
     const uint32_t u = blockIdx.x;
     if (*overflow) return;
     const uint32_t len = out_len[2 * u], hoff = out_len[2 * u + 1];
-    const uint8_t *src = out_base + (size_t)u * kOutStride + hoff;
+    const uint8_t *src = out_base + (size_t)u * out_stride + hoff;
     uint8_t *d = dst + offsets[u];
     // head bytes until d is 4-byte aligned
     uint32_t head = min(len, (uint32_t)((4 - ((uintptr_t)d & 3)) & 3));
@@ -1075,38 +1094,61 @@ k_gather(const uint8_t *__restrict__ out_base, const uint32_t *__restrict__ out_
 }
 
 // =============================================================================
-// k_crc32: standalone CRC-32 of n bytes per unit (Check::update for the Gzip
-// format).  HBM-bound: one pass over the input, 512-byte chunks per thread.
+// k_check: per-unit checksum of the DATA part of a unit (Check::update):
+// kind 0 = CRC-32 (512-byte chunks recombined with x^(8*512*j) mod P),
+// kind 1 = Adler-32 (per-chunk partial sums recombined mod 65521).
+// HBM-bound: one pass over the input.
 // =============================================================================
 __global__ void __launch_bounds__(256)
-k_crc32(const uint8_t *__restrict__ in_base, const uint32_t *__restrict__ unit_len, uint32_t *__restrict__ crc_out)
+k_check(const __grid_constant__ Geo g, uint32_t *__restrict__ sum_out, int kind)
 {
     __shared__ uint32_t s_crc;
+    __shared__ unsigned long long s_a, s_b;
     __shared__ uint32_t s_tab[4][256];
     const uint32_t u = blockIdx.x, tid = threadIdx.x;
-    const uint32_t n = unit_len[u];
-    const uint8_t *in = in_base + (size_t)u * kInStride;
-    const uint32_t *inw = (const uint32_t *)in;
-    for (uint32_t i = tid; i < 1024; i += 256) s_tab[i >> 8][i & 255] = c_crc_tab[i >> 8][i & 255];
-    if (tid == 0) s_crc = 0;
-    __syncthreads();
-    uint32_t acc = 0;
-    for (uint32_t j = tid; j * 512 < n; j += 256) {
-        uint32_t end = n - 512 * j, beg = end >= 512 ? end - 512 : 0;
-        uint32_t c = ~0u, pos = beg;
-        while (pos < end && (pos & 3)) { c = (c >> 8) ^ s_tab[0][(c ^ in[pos]) & 0xFF]; pos++; }
-        for (; pos + 4 <= end; pos += 4) {
-            c ^= __ldg(inw + (pos >> 2));
-            c = s_tab[3][c & 0xFF] ^ s_tab[2][(c >> 8) & 0xFF] ^ s_tab[1][(c >> 16) & 0xFF] ^ s_tab[0][c >> 24];
+    const uint32_t dict = g.unit_dict[u];
+    const uint32_t n = g.unit_len[u] - dict;
+    const uint8_t *in = g.in + (size_t)u * g.in_stride + dict;
+    if (tid == 0) { s_crc = 0; s_a = 0; s_b = 0; }
+    if (kind == 0) {
+        const uint32_t mis = (uint32_t)((uintptr_t)in & 3);
+        for (uint32_t i = tid; i < 1024; i += 256) s_tab[i >> 8][i & 255] = c_crc_tab[i >> 8][i & 255];
+        __syncthreads();
+        uint32_t acc = 0;
+        for (uint32_t j = tid; j * 512 < n; j += 256) {
+            uint32_t end = n - 512 * j, beg = end >= 512 ? end - 512 : 0;
+            uint32_t c = ~0u, pos = beg;
+            while (pos < end && ((pos + mis) & 3)) { c = (c >> 8) ^ s_tab[0][(c ^ in[pos]) & 0xFF]; pos++; }
+            for (; pos + 4 <= end; pos += 4) {
+                c ^= __ldg((const uint32_t *)(in + pos));
+                c = s_tab[3][c & 0xFF] ^ s_tab[2][(c >> 8) & 0xFF] ^ s_tab[1][(c >> 16) & 0xFF] ^ s_tab[0][c >> 24];
+            }
+            while (pos < end) { c = (c >> 8) ^ s_tab[0][(c ^ in[pos]) & 0xFF]; pos++; }
+            c = ~c;
+            acc ^= (j == 0) ? c : gf2_mulmod(c, c_xpow512[j], kCrcPoly);
         }
-        while (pos < end) { c = (c >> 8) ^ s_tab[0][(c ^ in[pos]) & 0xFF]; pos++; }
-        c = ~c;
-        acc ^= (j == 0) ? c : gf2_mulmod(c, c_xpow512[j], kCrcPoly);
+        for (int o = 16; o; o >>= 1) acc ^= __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+        if ((tid & 31) == 0 && acc) atomicXor(&s_crc, acc);
+        __syncthreads();
+        if (tid == 0) sum_out[u] = s_crc;
+    } else {
+        __syncthreads();
+        unsigned long long sa = 0, sb2 = 0;
+        for (uint32_t j = tid; j * 512 < n; j += 256) {
+            uint32_t beg = 512 * j, end = min(n, beg + 512);
+            uint32_t a = 0, b = 0;
+            for (uint32_t pos = beg; pos < end; pos++) { a += in[pos]; b += a; }
+            sa += a;
+            sb2 += (b + (unsigned long long)a * (n - end)) % 65521ull;
+        }
+        for (int o = 16; o; o >>= 1) { sa += __shfl_xor_sync(0xFFFFFFFFu, sa, o); sb2 += __shfl_xor_sync(0xFFFFFFFFu, sb2, o); }
+        if ((tid & 31) == 0) { atomicAdd(&s_a, sa); atomicAdd(&s_b, sb2); }
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t a = (uint32_t)((1ull + s_a) % 65521ull), b = (uint32_t)(((unsigned long long)n + s_b) % 65521ull);
+            sum_out[u] = (b << 16) | a;
+        }
     }
-    for (int o = 16; o; o >>= 1) acc ^= __shfl_xor_sync(0xFFFFFFFFu, acc, o);
-    if ((tid & 31) == 0 && acc) atomicXor(&s_crc, acc);
-    __syncthreads();
-    if (tid == 0) crc_out[u] = s_crc;
 }
 
 void read_phase_counters(unsigned long long *out, bool reset)
@@ -1128,10 +1170,19 @@ static bool debug_sync() { static int v = -1; if (v < 0) { const char *e = geten
         }                                                                                     \
     } while (0)
 
+static Geo make_geo(const DeflateBatch &b)
+{
+    Geo g;
+    g.in = b.in; g.unit_len = b.unit_len; g.unit_dict = b.unit_dict;
+    g.in_stride = b.in_stride; g.m_stride = b.m_stride; g.tok_stride = b.tok_stride; g.out_stride = b.out_stride;
+    g.spu = b.spu; g.seg = b.seg;
+    return g;
+}
+
 cudaError_t launch_deflate_pipeline(const DeflateBatch &b, cudaStream_t st)
 {
     static bool attr_done = false;
-    const int chain_smem = (65536 + 32768) * 2 + 4096;
+    const int chain_smem = (65536 + 32768) * 2;
     const int match_smem = kInStride + 65536 * 2;
     if (!attr_done) {
         cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, chain_smem);
@@ -1141,21 +1192,23 @@ cudaError_t launch_deflate_pipeline(const DeflateBatch &b, cudaStream_t st)
     if (b.nunits == 0) return cudaSuccess;
     LevelParams lp;
     if (!level_params(b.level, &lp)) return cudaErrorInvalidValue;
+    const Geo g = make_geo(b);
+    if (b.check_kind >= 0) {
+        if (b.timer) b.timer->start(KT_CRC, st);
+        k_check<<<b.nunits, 256, 0, st>>>(g, b.crc, b.check_kind);
+        if (b.timer) b.timer->stop(st);
+    }
     if (lp.mode >= 0) {
         if (b.timer) b.timer->start(KT_CHAIN, st);
-        k_chain<<<b.nunits, kChainThreads, chain_smem, st>>>(b.in, b.unit_len, b.next4, b.prev3, b.crc);
+        k_chain<<<b.nunits * b.spu, kChainThreads, chain_smem, st>>>(g, b.next4, b.prev3);
         DBG_SYNC("k_chain");
         if (b.timer) { b.timer->stop(st); b.timer->start(KT_MATCH, st); }
-        k_match<<<b.nunits, kMatchThreads, match_smem, st>>>(b.in, b.unit_len, b.next4, b.prev3, b.mtab, lp.depth, lp.nice, lp.mode >= 1);
+        k_match<<<b.nunits * b.spu, kMatchThreads, match_smem, st>>>(g, b.next4, b.prev3, b.mtab, lp.depth, lp.nice, lp.mode >= 1);
         DBG_SYNC("k_match");
-        if (b.timer) b.timer->stop(st);
-    } else {
-        if (b.timer) b.timer->start(KT_CRC, st);
-        k_crc32<<<b.nunits, 256, 0, st>>>(b.in, b.unit_len, b.crc);
         if (b.timer) b.timer->stop(st);
     }
     if (b.timer) b.timer->start(KT_EMIT, st);
-    k_emit<<<b.nunits, kEmitThreads, 0, st>>>(b.in, b.unit_len, b.unit_flags, b.mtab, b.crc, b.tokens, b.out, b.out_len,
+    k_emit<<<b.nunits, kEmitThreads, 0, st>>>(g, b.unit_flags, b.mtab, b.crc, b.tokens, b.out, b.out_len,
                                              b.status, lp.mode, lp.depth, lp.nice, b.level, b.format);
     DBG_SYNC("k_emit");
     if (b.timer) b.timer->stop(st);
@@ -1169,7 +1222,7 @@ cudaError_t launch_pack(const DeflateBatch &b, cudaStream_t st)
     if (b.nunits == 0) return cudaSuccess;
     if (b.timer) b.timer->start(KT_GATHER, st);
     k_scan<<<1, 1024, 0, st>>>(b.out_len, b.offsets, b.nunits, b.base_ptr, b.packed_cap, b.overflow);
-    k_gather<<<b.nunits, 256, 0, st>>>(b.out, b.out_len, b.offsets, b.packed, b.overflow);
+    k_gather<<<b.nunits, 256, 0, st>>>(b.out, b.out_len, b.offsets, b.packed, b.overflow, b.out_stride);
     DBG_SYNC("k_scan+k_gather");
     if (b.timer) b.timer->stop(st);
     return cudaGetLastError();

@@ -36,11 +36,12 @@ struct DeflateBatch {
     int level;
     int format;               // gzpb_format
     const uint8_t *in;        // nunits * kInStride
-    const uint32_t *unit_len; // nunits
+    const uint32_t *unit_len; // nunits: dictionary + data bytes of the unit
+    const uint32_t *unit_dict; // nunits: dictionary bytes in front of the data
     const uint32_t *unit_flags;  // bit0 = is_last (BGZF EOF), bit1 = sync flush (no BFINAL)
-    uint16_t *next4;          // nunits * 65536
-    uint16_t *prev3;          // nunits * 65536
-    uint64_t *mtab;           // nunits * 65536
+    uint16_t *next4;          // nunits * spu * 65536
+    uint16_t *prev3;          // nunits * spu * 65536
+    uint64_t *mtab;           // nunits * m_stride
     uint32_t *crc;            // nunits
     uint32_t *tokens;         // nunits * kTokStride
     uint8_t *out;             // nunits * kOutStride
@@ -52,6 +53,9 @@ struct DeflateBatch {
     const uint64_t *base_ptr; // device address holding this batch's first offset (NULL = 0)
     int32_t *overflow;        // set to 1 by k_scan when the batch would exceed packed_cap
     KernelTimer *timer;       // optional
+    uint32_t in_stride, m_stride, tok_stride, out_stride;   // per-unit strides (bytes / entries / tokens / bytes)
+    uint32_t spu, seg;        // sub-units per unit and new positions per sub-unit (gzpb_common.cuh: Geo)
+    int check_kind;           // -1 none, 0 CRC-32, 1 Adler-32 (written to `crc`)
 };
 
 void upload_deflate_constants();

@@ -36,14 +36,14 @@ struct Lane {
     cudaEvent_t ev_scan = nullptr, ev_done = nullptr;
     // device
     uint8_t *d_in = nullptr;
-    uint32_t *d_len = nullptr, *d_flags = nullptr, *d_crc = nullptr, *d_tokens = nullptr, *d_out_len = nullptr;
+    uint32_t *d_len = nullptr, *d_dict = nullptr, *d_flags = nullptr, *d_crc = nullptr, *d_tokens = nullptr, *d_out_len = nullptr;
     uint16_t *d_next4 = nullptr, *d_prev3 = nullptr;
     uint64_t *d_mtab = nullptr, *d_offsets = nullptr;
     uint8_t *d_out = nullptr, *d_packed = nullptr;
     int32_t *d_status = nullptr, *d_overflow = nullptr;
     // pinned host
     uint8_t *h_in = nullptr, *h_packed = nullptr;
-    uint32_t *h_len = nullptr, *h_flags = nullptr, *h_crc = nullptr;
+    uint32_t *h_len = nullptr, *h_dict = nullptr, *h_flags = nullptr, *h_crc = nullptr;
     uint64_t *h_offsets = nullptr;
     int32_t *h_status = nullptr, *h_overflow = nullptr;
     size_t nunits = 0;
@@ -55,6 +55,9 @@ struct Lane {
 struct gzpb_ctx {
     int device = 0, format = 0, level = 0;
     size_t max_block_bytes = 0, max_units = 0;
+    uint32_t dict_cap = 0;                         // 32 KiB for the dictionary formats, else 0
+    uint32_t in_stride = 0, m_stride = 0, tok_stride = 0, out_stride = 0, spu = 1, seg = 0;
+    int check_kind = -1;
     Lane lanes[kLanes];
     bool scratch_only = false;
     KernelTimer timer;
@@ -180,38 +183,41 @@ static int lane_alloc(gzpb_ctx *c, Lane &L, bool with_io)
     CK(cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&L.ev_scan, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&L.ev_done, cudaEventDisableTiming));
-    CK(dmalloc(&L.d_next4, U * kMaxUnitBytes));
-    CK(dmalloc(&L.d_prev3, U * kMaxUnitBytes));
-    CK(dmalloc(&L.d_mtab, U * kMaxUnitBytes));
+    CK(dmalloc(&L.d_next4, U * c->spu * kMaxUnitBytes));
+    CK(dmalloc(&L.d_prev3, U * c->spu * kMaxUnitBytes));
+    CK(dmalloc(&L.d_mtab, U * c->m_stride));
     CK(dmalloc(&L.d_crc, U));
-    CK(dmalloc(&L.d_tokens, U * kTokStride));
-    CK(dmalloc(&L.d_out, U * kOutStride + 256));
+    CK(dmalloc(&L.d_tokens, U * c->tok_stride));
+    CK(dmalloc(&L.d_out, U * c->out_stride + 256));
     CK(dmalloc(&L.d_out_len, U * 2));
     CK(dmalloc(&L.d_overflow, 1));
     CK(cudaMemset(L.d_overflow, 0, sizeof(int32_t)));
+    CK(dmalloc(&L.d_dict, U));
+    CK(cudaMemset(L.d_dict, 0, U * sizeof(uint32_t)));
     if (with_io) {
-        CK(dmalloc(&L.d_in, U * kInStride + 256));
+        CK(dmalloc(&L.d_in, U * c->in_stride + 256));
         CK(dmalloc(&L.d_len, U));
         CK(dmalloc(&L.d_flags, U));
         CK(dmalloc(&L.d_offsets, U + 1));
         CK(dmalloc(&L.d_status, U));
         CK(hmalloc(&L.h_len, U));
+        CK(hmalloc(&L.h_dict, U));
         CK(hmalloc(&L.h_flags, U));
         CK(hmalloc(&L.h_crc, U));
         CK(hmalloc(&L.h_offsets, U + 1));
         CK(hmalloc(&L.h_status, U));
         CK(hmalloc(&L.h_overflow, 1));
-        CK(hmalloc(&L.h_packed, U * kOutStride));
+        CK(hmalloc(&L.h_packed, U * c->out_stride));
     }
     return GZPB_OK;
 }
 
 static void lane_free(Lane &L)
 {
-    cudaFree(L.d_in); cudaFree(L.d_len); cudaFree(L.d_flags); cudaFree(L.d_crc); cudaFree(L.d_tokens); cudaFree(L.d_out_len);
+    cudaFree(L.d_in); cudaFree(L.d_len); cudaFree(L.d_dict); cudaFree(L.d_flags); cudaFree(L.d_crc); cudaFree(L.d_tokens); cudaFree(L.d_out_len);
     cudaFree(L.d_next4); cudaFree(L.d_prev3); cudaFree(L.d_mtab); cudaFree(L.d_offsets); cudaFree(L.d_out); cudaFree(L.d_packed);
     cudaFree(L.d_status); cudaFree(L.d_overflow);
-    cudaFreeHost(L.h_in); cudaFreeHost(L.h_packed); cudaFreeHost(L.h_len); cudaFreeHost(L.h_flags); cudaFreeHost(L.h_crc);
+    cudaFreeHost(L.h_in); cudaFreeHost(L.h_packed); cudaFreeHost(L.h_len); cudaFreeHost(L.h_dict); cudaFreeHost(L.h_flags); cudaFreeHost(L.h_crc);
     cudaFreeHost(L.h_offsets); cudaFreeHost(L.h_status); cudaFreeHost(L.h_overflow);
     if (L.ev_scan) cudaEventDestroy(L.ev_scan);
     if (L.ev_done) cudaEventDestroy(L.ev_done);
@@ -238,12 +244,26 @@ extern "C" int gzpb_create(gzpb_ctx **out, int device, int format, int level, si
         snprintf(g_last_cuda_error, sizeof g_last_cuda_error, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
         return GZPB_ECUDA;
     }
-    if (format == GZPB_SNAP || format == GZPB_ZLIB) return GZPB_EINVAL;  // (not wired yet)
+    if (format == GZPB_SNAP) return GZPB_EINVAL;  // (Snap kernel: snappy_kernels.cu, not wired yet)
     size_t dict = gzpb_needs_dict(format) ? GZPB_DICT_SIZE : 0;
-    if (max_block_bytes + dict > kMaxUnitBytes) return GZPB_EBUFFERSIZE;
+    if (max_block_bytes > (1u << 22)) return GZPB_EBUFFERSIZE;
     gzpb_ctx *c = new gzpb_ctx();
     c->device = device; c->format = format; c->level = level;
     c->max_block_bytes = max_block_bytes; c->max_units = max_blocks_in_flight;
+    {
+        const size_t U = dict + max_block_bytes;
+        c->dict_cap = (uint32_t)dict;
+        if (U <= (size_t)kMaxUnitBytes) { c->spu = 1; c->seg = (uint32_t)U; c->in_stride = kInStride; }
+        else {
+            c->seg = 32256;
+            c->spu = (uint32_t)((max_block_bytes + c->seg - 1) / c->seg);
+            c->in_stride = (uint32_t)((U + 80 + 127) & ~(size_t)127);
+        }
+        c->m_stride = (uint32_t)(((U + 15) & ~(size_t)15) + 32);
+        c->tok_stride = (uint32_t)(U + 64);
+        c->out_stride = (uint32_t)((kOutPayloadOff + gzpb_encode_capacity(format, max_block_bytes) + 64 + 127) & ~(size_t)127);
+        c->check_kind = (format == GZPB_ZLIB) ? 1 : (format == GZPB_RAWDEFLATE ? -1 : 0);
+    }
     upload_deflate_constants();
     for (int i = 0; i < kLanes; i++) {
         int r = lane_alloc(c, c->lanes[i], true);
@@ -316,7 +336,9 @@ static uint32_t unit_flags_for(int format, int is_last)
 static void fill_batch(gzpb_ctx *c, Lane &L, DeflateBatch &b, size_t n)
 {
     b.nunits = (uint32_t)n; b.level = c->level; b.format = c->format;
-    b.in = L.d_in; b.unit_len = L.d_len; b.unit_flags = L.d_flags;
+    b.in = L.d_in; b.unit_len = L.d_len; b.unit_dict = L.d_dict; b.unit_flags = L.d_flags;
+    b.in_stride = c->in_stride; b.m_stride = c->m_stride; b.tok_stride = c->tok_stride; b.out_stride = c->out_stride;
+    b.spu = c->spu; b.seg = c->seg; b.check_kind = c->check_kind;
     b.next4 = L.d_next4; b.prev3 = L.d_prev3; b.mtab = L.d_mtab; b.crc = L.d_crc; b.tokens = L.d_tokens;
     b.out = L.d_out; b.out_len = L.d_out_len; b.status = L.d_status; b.offsets = L.d_offsets;
     b.packed = nullptr; b.packed_cap = 0; b.base_ptr = nullptr; b.overflow = L.d_overflow;
@@ -334,7 +356,7 @@ extern "C" int gzpb_encode_device(gzpb_ctx *c, const void *d_in, const uint32_t 
                                   size_t nunits, void *d_packed, uint64_t *d_offsets, int32_t *d_status,
                                   void *cuda_stream)
 {
-    if (!c || !is_deflate_format(c->format)) return GZPB_EINVAL;
+    if (!c || !is_deflate_format(c->format) || c->dict_cap) return GZPB_EINVAL;   // device path: formats without dictionary
     CK(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t)cuda_stream;
     Lane &L = c->lanes[0];
@@ -343,7 +365,7 @@ extern "C" int gzpb_encode_device(gzpb_ctx *c, const void *d_in, const uint32_t 
         size_t n = std::min(c->max_units, nunits - done);
         DeflateBatch b;
         fill_batch(c, L, b, n);
-        b.in = (const uint8_t *)d_in + done * kInStride; b.unit_len = d_len + done; b.unit_flags = d_flags + done;
+        b.in = (const uint8_t *)d_in + done * (size_t)c->in_stride; b.unit_len = d_len + done; b.unit_flags = d_flags + done;
         b.status = d_status + done; b.offsets = d_offsets + done; b.base_ptr = d_offsets + done;
         b.packed = (uint8_t *)d_packed; b.packed_cap = ~0ull;
         CK(launch_deflate_pipeline(b, st));
@@ -359,37 +381,48 @@ struct UnitRef { const uint8_t *ptr; size_t len; const uint8_t *dict; size_t dic
 }
 
 // Launch one batch on a lane: H2D + kernels (+ scan/gather when `packed` is given).
-static int lane_launch(gzpb_ctx *c, Lane &L, const UnitRef *units, size_t n, const uint8_t *contig_src, size_t contig_pitch,
-                       bool src_pinned)
+static int lane_launch(gzpb_ctx *c, Lane &L, const UnitRef *units, size_t n, bool contig, size_t pitch, bool src_pinned)
 {
+    const size_t IS = c->in_stride;
     for (size_t i = 0; i < n; i++) {
         L.h_len[i] = (uint32_t)(units[i].dict_len + units[i].len);
+        L.h_dict[i] = (uint32_t)units[i].dict_len;
         L.h_flags[i] = unit_flags_for(c->format, units[i].is_last);
     }
-    if (contig_src && src_pinned && n > 0) {
-        // blocks are consecutive slices of one pinned buffer: one strided DMA
-        size_t full = n;
-        size_t last_len = units[n - 1].len;
-        if (last_len != contig_pitch) full = n - 1;
-        if (full) CK(cudaMemcpy2DAsync(L.d_in, kInStride, contig_src, contig_pitch, contig_pitch, full, cudaMemcpyHostToDevice, L.st));
-        if (full != n && last_len) CK(cudaMemcpyAsync(L.d_in + full * kInStride, units[n - 1].ptr, last_len, cudaMemcpyHostToDevice, L.st));
+    if (contig && src_pinned && n > 0) {
+        // blocks are consecutive slices of ONE pinned buffer (dictionary = the 32 KiB right before the
+        // block, so dict||data is contiguous too): strided DMA for the uniform units, plain copies for
+        // the stream's first block (no dictionary) and a short last block.
+        size_t first = 0, last = n;
+        if (units[0].dict_len != units[n > 1 ? 1 : 0].dict_len || (n == 1)) first = 1;
+        if (n > 1 && units[n - 1].len != pitch) last = n - 1;
+        if (first > last) first = last;
+        for (size_t i = 0; i < first; i++)
+            if (L.h_len[i]) CK(cudaMemcpyAsync(L.d_in + i * IS, units[i].ptr - units[i].dict_len, L.h_len[i], cudaMemcpyHostToDevice, L.st));
+        if (last > first) {
+            const size_t w = units[first].dict_len + pitch;
+            CK(cudaMemcpy2DAsync(L.d_in + first * IS, IS, units[first].ptr - units[first].dict_len, pitch, w, last - first, cudaMemcpyHostToDevice, L.st));
+        }
+        for (size_t i = last; i < n; i++)
+            if (L.h_len[i]) CK(cudaMemcpyAsync(L.d_in + i * IS, units[i].ptr - units[i].dict_len, L.h_len[i], cudaMemcpyHostToDevice, L.st));
     } else {
-        if (!L.h_in) CK(cudaHostAlloc((void **)&L.h_in, c->max_units * (size_t)kInStride, cudaHostAllocPortable));
+        if (!L.h_in) CK(cudaHostAlloc((void **)&L.h_in, c->max_units * IS, cudaHostAllocPortable));
         size_t used = 0;
         for (size_t i = 0; i < n; i++) {
-            uint8_t *dst = L.h_in + i * kInStride;
+            uint8_t *dst = L.h_in + i * IS;
             if (units[i].dict_len) memcpy(dst, units[i].dict, units[i].dict_len);
             if (units[i].len) memcpy(dst + units[i].dict_len, units[i].ptr, units[i].len);
-            used = (i + 1) * (size_t)kInStride;
+            used = (i + 1) * IS;
         }
         if (used) CK(cudaMemcpyAsync(L.d_in, L.h_in, used, cudaMemcpyHostToDevice, L.st));
     }
     CK(cudaMemcpyAsync(L.d_len, L.h_len, n * sizeof(uint32_t), cudaMemcpyHostToDevice, L.st));
+    CK(cudaMemcpyAsync(L.d_dict, L.h_dict, n * sizeof(uint32_t), cudaMemcpyHostToDevice, L.st));
     CK(cudaMemcpyAsync(L.d_flags, L.h_flags, n * sizeof(uint32_t), cudaMemcpyHostToDevice, L.st));
     DeflateBatch b;
     fill_batch(c, L, b, n);
     CK(launch_deflate_pipeline(b, L.st));
-    c->launches += 3;
+    c->launches += 4;
     L.nunits = n; L.busy = true;
     return GZPB_OK;
 }
@@ -428,7 +461,7 @@ extern "C" int gzpb_encode_batch(gzpb_ctx *c, size_t n, const gzpb_block_in *in,
     const bool dict_fmt = gzpb_needs_dict(c->format);
     for (size_t i = 0; i < n; i++) {
         size_t dl = (dict_fmt && in[i].dict) ? in[i].dict_len : 0;
-        if (in[i].len + dl > kMaxUnitBytes || in[i].len > c->max_block_bytes) return GZPB_EBUFFERSIZE;
+        if (dl > c->dict_cap || in[i].len > c->max_block_bytes) return GZPB_EBUFFERSIZE;
         if (out[i].cap < gzpb_encode_capacity(c->format, in[i].len)) return GZPB_EINVAL;
     }
     int rc = GZPB_OK;
@@ -451,7 +484,7 @@ extern "C" int gzpb_encode_batch(gzpb_ctx *c, size_t n, const gzpb_block_in *in,
                 if (len > o.cap) { o.status = GZPB_ECOMPRESS; continue; }
                 memcpy(o.dst, L.h_packed + L.h_offsets[i], len);
                 o.out_len = len;
-                if (c->format == GZPB_GZIP) { o.check_sum = L.h_crc[i]; o.check_amount = (uint32_t)in[p.first + i].len; }
+                if (c->format == GZPB_GZIP || c->format == GZPB_ZLIB) { o.check_sum = L.h_crc[i]; o.check_amount = (uint32_t)in[p.first + i].len; }
             }
         }
         return GZPB_OK;
@@ -469,9 +502,9 @@ extern "C" int gzpb_encode_batch(gzpb_ctx *c, size_t n, const gzpb_block_in *in,
             size_t dl = (dict_fmt && b.dict) ? b.dict_len : 0;
             units[i] = UnitRef{(const uint8_t *)b.ptr, b.len, (const uint8_t *)b.dict, dl, b.is_last};
         }
-        rc = lane_launch(c, L, units.data(), cnt, nullptr, 0, false);
+        rc = lane_launch(c, L, units.data(), cnt, false, 0, false);
         if (rc != GZPB_OK) return rc;
-        rc = lane_pack(c, L, L.h_packed, (uint64_t)c->max_units * kOutStride, nullptr, nullptr);
+        rc = lane_pack(c, L, L.h_packed, (uint64_t)c->max_units * c->out_stride, nullptr, nullptr);
         if (rc != GZPB_OK) return rc;
         pend.push_back(Pending{done, cnt, li});
         done += cnt;
@@ -493,7 +526,7 @@ extern "C" int gzpb_encode_stream(gzpb_ctx *c, const void *in_v, size_t in_len, 
     const uint8_t *in = (const uint8_t *)in_v;
     uint8_t *out = (uint8_t *)out_v;
     const bool dict_fmt = gzpb_needs_dict(c->format);
-    const bool in_pinned = in_len && is_pinned(in) && !dict_fmt;
+    const bool in_pinned = in_len && is_pinned(in);
     const bool out_pinned = is_pinned(out);
 
     // ParCompress::write + finish: full blocks while MORE than buffer_size bytes remain,
@@ -527,13 +560,12 @@ extern "C" int gzpb_encode_stream(gzpb_ctx *c, const void *in_v, size_t in_len, 
         if (*L.h_overflow) return GZPB_ECOMPRESS;
         for (size_t i = 0; i < p.count; i++) {
             if (L.h_status[i] != GZPB_OK) return L.h_status[i];
-            if (c->format == GZPB_GZIP) {
-                size_t blen = L.h_len[i] - 0;
+            if (c->format == GZPB_GZIP || c->format == GZPB_ZLIB) {
                 // (dictionary bytes are not part of the block's check)
                 size_t b0 = (p.first + i) * buffer_size;
                 size_t real = std::min(buffer_size, in_len - std::min(in_len, b0));
-                (void)blen;
-                run_sum = gzpb_crc32_combine(run_sum, L.h_crc[i], real);
+                run_sum = c->format == GZPB_GZIP ? gzpb_crc32_combine(run_sum, L.h_crc[i], real)
+                                                 : gzpb_adler32_combine(run_sum, L.h_crc[i], real);
                 run_amount += (uint32_t)real;
             }
         }
@@ -564,10 +596,10 @@ extern "C" int gzpb_encode_stream(gzpb_ctx *c, const void *in_v, size_t in_len, 
             const uint8_t *d = (dict_fmt && bi > 0) ? in + b0 - GZPB_DICT_SIZE : nullptr;
             units[i] = UnitRef{in + b0, len, d, d ? (size_t)GZPB_DICT_SIZE : 0, bi + 1 == nblocks};
         }
-        rc = lane_launch(c, L, units.data(), cnt, in_pinned ? in + done * buffer_size : nullptr, buffer_size, in_pinned);
+        rc = lane_launch(c, L, units.data(), cnt, true, buffer_size, in_pinned);
         if (rc != GZPB_OK) break;
         if (out_pinned) rc = lane_pack(c, L, dev_out, out_cap, prev_end, prev);
-        else rc = lane_pack(c, L, L.h_packed, (uint64_t)c->max_units * kOutStride, nullptr, nullptr);
+        else rc = lane_pack(c, L, L.h_packed, (uint64_t)c->max_units * c->out_stride, nullptr, nullptr);
         if (rc != GZPB_OK) break;
         prev = &L; prev_end = L.d_offsets + cnt;
         pend.push_back(Pending{done, cnt, li});

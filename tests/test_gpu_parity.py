@@ -10,7 +10,7 @@ import pytest
 
 import oracle
 import gzp_b200
-from gzp_b200 import BGZF, MGZIP
+from gzp_b200 import BGZF, GZIP, MGZIP, RAWDEFLATE, ZLIB
 
 pytestmark = pytest.mark.gpu
 
@@ -63,4 +63,62 @@ def test_mgzip_small_blocks(text_corpus):
     for b, (enc, _, _) in zip(blocks, got):
         assert enc == oracle.encode_block(oracle.MGZIP, 6, b)
     assert gzip.decompress(b"".join(e for e, _, _ in got)) == b"".join(blocks)
+    ctx.close()
+
+
+def test_mgzip_default_block_size_long_units(text_corpus):
+    # 131 072-byte blocks (mgzip default, BASELINE configs[2]) -> segmented sub-units with a 32 KiB halo
+    ctx = gzp_b200.Context(MGZIP, 6, max_blocks_in_flight=8)
+    data = text_corpus[: 131072 * 5 + 4321]
+    got = ctx.encode_stream(data)
+    want = oracle.compress_stream(oracle.MGZIP, 6, 131072, [data])
+    assert got == want
+    assert gzip.decompress(got) == data
+    rnd = random.Random(3)
+    blocks = [bytes(131072), bytes(rnd.randrange(255) for _ in range(100000)), text_corpus[7:7 + 70000], b"q" * 65537]
+    res = ctx.encode_blocks([(b, None, False) for b in blocks])
+    for b, (enc, _, _) in zip(blocks, res):
+        assert enc == oracle.encode_block(oracle.MGZIP, 6, b)
+    ctx.close()
+
+
+@pytest.mark.parametrize("fmt,bs,level", [(GZIP, 131072, 6), (GZIP, 40000, 3), (GZIP, 262144, 7), (RAWDEFLATE, 131072, 6),
+                                          (ZLIB, 131072, 6), (ZLIB, 32768, 2)])
+def test_dictionary_formats_bit_exact_and_decodable(text_corpus, fmt, bs, level):
+    # Gzip / Zlib / RawDeflate: 32 KiB dictionary carry + sync-flush terminators + combined check
+    ctx = gzp_b200.Context(fmt, level, max_block_bytes=bs, max_blocks_in_flight=4)
+    data = text_corpus[: bs * 3 + 12345]
+    got = ctx.encode_stream(data, bs)
+    want = oracle.compress_stream(fmt, level, bs, [data])
+    assert got == want
+    if fmt == GZIP:
+        assert gzip.decompress(got) == data
+    elif fmt == ZLIB:
+        assert zlib.decompress(got) == data
+    else:
+        assert zlib.decompressobj(-15).decompress(got) == data
+    # per-block API with explicit dictionaries and checks
+    msgs = oracle.chunk_stream(fmt, bs, [data[: bs + 999]])
+    res = ctx.encode_blocks(msgs)
+    for (b, d, last), (enc, s, a) in zip(msgs, res):
+        assert enc == oracle.encode_block(fmt, level, b, d, last)
+        if fmt == GZIP:
+            assert (s, a) == (zlib.crc32(b), len(b))
+        if fmt == ZLIB:
+            assert (s, a) == (zlib.adler32(b), len(b))
+    # empty stream and tiny stream
+    for tiny in (b"", b"x", text_corpus[:300]):
+        assert ctx.encode_stream(tiny, bs) == oracle.compress_stream(fmt, level, bs, [tiny])
+    ctx.close()
+
+
+def test_reference_regression_vector_on_gpu():
+    # /root/reference/src/deflate.rs:949-992: 206 bytes, buffer_size = DICT_SIZE, Gzip level 3 (the default)
+    import json, os
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_vectors.json")))
+    data = bytes(g["regression_input"])
+    ctx = gzp_b200.Context(GZIP, 3, max_block_bytes=32768, max_blocks_in_flight=4)
+    got = ctx.encode_stream(data, 32768)
+    assert got == oracle.compress_stream(oracle.GZIP, 3, 32768, [data])
+    assert gzip.decompress(got) == data
     ctx.close()
