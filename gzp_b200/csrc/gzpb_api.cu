@@ -12,6 +12,7 @@
 
 #include "../../include/gzpb.h"
 #include "deflate_kernels.cuh"
+#include "snappy_kernels.cuh"
 #include "gzpb_common.cuh"
 
 using namespace gzpb;
@@ -58,6 +59,7 @@ struct gzpb_ctx {
     uint32_t dict_cap = 0;                         // 32 KiB for the dictionary formats, else 0
     uint32_t in_stride = 0, m_stride = 0, tok_stride = 0, out_stride = 0, spu = 1, seg = 0;
     int check_kind = -1;
+    uint32_t cpu = 1;                              // gather entries per unit (Snap: 64 KiB chunks per block)
     Lane lanes[kLanes];
     bool scratch_only = false;
     KernelTimer timer;
@@ -183,6 +185,27 @@ static int lane_alloc(gzpb_ctx *c, Lane &L, bool with_io)
     CK(cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&L.ev_scan, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&L.ev_done, cudaEventDisableTiming));
+    if (c->format == GZPB_SNAP) {
+        const size_t E = U * c->cpu;
+        CK(dmalloc(&L.d_out, E * c->out_stride + 256));
+        CK(dmalloc(&L.d_out_len, E * 2));
+        CK(dmalloc(&L.d_overflow, 1));
+        CK(cudaMemset(L.d_overflow, 0, sizeof(int32_t)));
+        CK(dmalloc(&L.d_in, U * c->in_stride + 256));
+        CK(dmalloc(&L.d_len, U));
+        CK(dmalloc(&L.d_offsets, E + 1));
+        CK(hmalloc(&L.h_len, U));
+        CK(hmalloc(&L.h_dict, U));
+        CK(hmalloc(&L.h_flags, U));
+        CK(hmalloc(&L.h_crc, U));
+        CK(hmalloc(&L.h_offsets, E + 1));
+        CK(hmalloc(&L.h_status, U));
+        CK(hmalloc(&L.h_overflow, 1));
+        CK(hmalloc(&L.h_packed, E * c->out_stride));
+        memset(L.h_status, 0, U * sizeof(int32_t));
+        memset(L.h_crc, 0, U * sizeof(uint32_t));
+        return GZPB_OK;
+    }
     CK(dmalloc(&L.d_next4, U * c->spu * kMaxUnitBytes));
     CK(dmalloc(&L.d_prev3, U * c->spu * kMaxUnitBytes));
     CK(dmalloc(&L.d_mtab, U * c->m_stride));
@@ -244,7 +267,6 @@ extern "C" int gzpb_create(gzpb_ctx **out, int device, int format, int level, si
         snprintf(g_last_cuda_error, sizeof g_last_cuda_error, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
         return GZPB_ECUDA;
     }
-    if (format == GZPB_SNAP) return GZPB_EINVAL;  // (Snap kernel: snappy_kernels.cu, not wired yet)
     size_t dict = gzpb_needs_dict(format) ? GZPB_DICT_SIZE : 0;
     if (max_block_bytes > (1u << 22)) return GZPB_EBUFFERSIZE;
     gzpb_ctx *c = new gzpb_ctx();
@@ -263,7 +285,15 @@ extern "C" int gzpb_create(gzpb_ctx **out, int device, int format, int level, si
         c->tok_stride = (uint32_t)(U + 64);
         c->out_stride = (uint32_t)((kOutPayloadOff + gzpb_encode_capacity(format, max_block_bytes) + 64 + 127) & ~(size_t)127);
         c->check_kind = (format == GZPB_ZLIB) ? 1 : (format == GZPB_RAWDEFLATE ? -1 : 0);
+        if (format == GZPB_SNAP) {
+            c->cpu = (uint32_t)((max_block_bytes + 65535) / 65536);
+            if (c->cpu == 0) c->cpu = 1;
+            c->in_stride = (uint32_t)((max_block_bytes + 80 + 127) & ~(size_t)127);
+            c->out_stride = 76544;   // 32 + max_compress_len(65536) rounded up: one slot per 64 KiB chunk
+            c->spu = 1;
+        }
     }
+    upload_snappy_constants();
     upload_deflate_constants();
     for (int i = 0; i < kLanes; i++) {
         int r = lane_alloc(c, c->lanes[i], true);
@@ -400,8 +430,10 @@ static int lane_launch(gzpb_ctx *c, Lane &L, const UnitRef *units, size_t n, boo
         for (size_t i = 0; i < first; i++)
             if (L.h_len[i]) CK(cudaMemcpyAsync(L.d_in + i * IS, units[i].ptr - units[i].dict_len, L.h_len[i], cudaMemcpyHostToDevice, L.st));
         if (last > first) {
-            const size_t w = units[first].dict_len + pitch;
-            CK(cudaMemcpy2DAsync(L.d_in + first * IS, IS, units[first].ptr - units[first].dict_len, pitch, w, last - first, cudaMemcpyHostToDevice, L.st));
+            // rows may not overlap in a 2-D copy: dictionary columns and data columns go separately
+            const size_t dl = units[first].dict_len;
+            if (dl) CK(cudaMemcpy2DAsync(L.d_in + first * IS, IS, units[first].ptr - dl, pitch, dl, last - first, cudaMemcpyHostToDevice, L.st));
+            CK(cudaMemcpy2DAsync(L.d_in + first * IS + dl, IS, units[first].ptr, pitch, pitch, last - first, cudaMemcpyHostToDevice, L.st));
         }
         for (size_t i = last; i < n; i++)
             if (L.h_len[i]) CK(cudaMemcpyAsync(L.d_in + i * IS, units[i].ptr - units[i].dict_len, L.h_len[i], cudaMemcpyHostToDevice, L.st));
@@ -417,6 +449,15 @@ static int lane_launch(gzpb_ctx *c, Lane &L, const UnitRef *units, size_t n, boo
         if (used) CK(cudaMemcpyAsync(L.d_in, L.h_in, used, cudaMemcpyHostToDevice, L.st));
     }
     CK(cudaMemcpyAsync(L.d_len, L.h_len, n * sizeof(uint32_t), cudaMemcpyHostToDevice, L.st));
+    if (c->format == GZPB_SNAP) {
+        SnapBatch sb;
+        sb.nunits = (uint32_t)n; sb.cpu = c->cpu; sb.in = L.d_in; sb.unit_len = L.d_len; sb.in_stride = c->in_stride;
+        sb.out = L.d_out; sb.out_stride = c->out_stride; sb.out_len = L.d_out_len; sb.timer = c->profiling ? &c->timer : nullptr;
+        CK(launch_snap(sb, L.st));
+        c->launches += 1;
+        L.nunits = n; L.busy = true;
+        return GZPB_OK;
+    }
     CK(cudaMemcpyAsync(L.d_dict, L.h_dict, n * sizeof(uint32_t), cudaMemcpyHostToDevice, L.st));
     CK(cudaMemcpyAsync(L.d_flags, L.h_flags, n * sizeof(uint32_t), cudaMemcpyHostToDevice, L.st));
     DeflateBatch b;
@@ -432,14 +473,18 @@ static int lane_pack(gzpb_ctx *c, Lane &L, uint8_t *packed, uint64_t cap, const 
 {
     DeflateBatch b;
     fill_batch(c, L, b, L.nunits);
+    const size_t entries = L.nunits * c->cpu;
+    b.nunits = (uint32_t)entries;
     b.packed = packed; b.packed_cap = cap; b.base_ptr = base_ptr;
     if (prev) CK(cudaStreamWaitEvent(L.st, prev->ev_scan, 0));
     CK(launch_pack(b, L.st));
     CK(cudaEventRecord(L.ev_scan, L.st));
     c->launches += 2;
-    CK(cudaMemcpyAsync(L.h_offsets, L.d_offsets, (L.nunits + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, L.st));
-    CK(cudaMemcpyAsync(L.h_status, L.d_status, L.nunits * sizeof(int32_t), cudaMemcpyDeviceToHost, L.st));
-    CK(cudaMemcpyAsync(L.h_crc, L.d_crc, L.nunits * sizeof(uint32_t), cudaMemcpyDeviceToHost, L.st));
+    CK(cudaMemcpyAsync(L.h_offsets, L.d_offsets, (entries + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, L.st));
+    if (c->format != GZPB_SNAP) {
+        CK(cudaMemcpyAsync(L.h_status, L.d_status, L.nunits * sizeof(int32_t), cudaMemcpyDeviceToHost, L.st));
+        CK(cudaMemcpyAsync(L.h_crc, L.d_crc, L.nunits * sizeof(uint32_t), cudaMemcpyDeviceToHost, L.st));
+    }
     CK(cudaMemcpyAsync(L.h_overflow, L.d_overflow, sizeof(int32_t), cudaMemcpyDeviceToHost, L.st));
     CK(cudaEventRecord(L.ev_done, L.st));
     return GZPB_OK;
@@ -456,7 +501,6 @@ static int lane_wait(gzpb_ctx *c, Lane &L)
 extern "C" int gzpb_encode_batch(gzpb_ctx *c, size_t n, const gzpb_block_in *in, gzpb_block_out *out)
 {
     if (!c || (n && (!in || !out))) return GZPB_EINVAL;
-    if (!is_deflate_format(c->format)) return GZPB_EINVAL;
     CK(cudaSetDevice(c->device));
     const bool dict_fmt = gzpb_needs_dict(c->format);
     for (size_t i = 0; i < n; i++) {
@@ -478,11 +522,12 @@ extern "C" int gzpb_encode_batch(gzpb_ctx *c, size_t n, const gzpb_block_in *in,
         for (size_t i = 0; i < p.count; i++) {
             gzpb_block_out &o = out[p.first + i];
             o.status = L.h_status[i];
-            size_t len = (size_t)(L.h_offsets[i + 1] - L.h_offsets[i]);
+            const size_t o0 = (size_t)L.h_offsets[i * c->cpu], o1 = (size_t)L.h_offsets[(i + 1) * c->cpu];
+            size_t len = o1 - o0;
             o.out_len = 0; o.check_sum = 0; o.check_amount = 0;
             if (o.status == GZPB_OK) {
                 if (len > o.cap) { o.status = GZPB_ECOMPRESS; continue; }
-                memcpy(o.dst, L.h_packed + L.h_offsets[i], len);
+                memcpy(o.dst, L.h_packed + o0, len);
                 o.out_len = len;
                 if (c->format == GZPB_GZIP || c->format == GZPB_ZLIB) { o.check_sum = L.h_crc[i]; o.check_amount = (uint32_t)in[p.first + i].len; }
             }
@@ -504,7 +549,7 @@ extern "C" int gzpb_encode_batch(gzpb_ctx *c, size_t n, const gzpb_block_in *in,
         }
         rc = lane_launch(c, L, units.data(), cnt, false, 0, false);
         if (rc != GZPB_OK) return rc;
-        rc = lane_pack(c, L, L.h_packed, (uint64_t)c->max_units * c->out_stride, nullptr, nullptr);
+        rc = lane_pack(c, L, L.h_packed, (uint64_t)c->max_units * c->cpu * c->out_stride, nullptr, nullptr);
         if (rc != GZPB_OK) return rc;
         pend.push_back(Pending{done, cnt, li});
         done += cnt;
@@ -518,7 +563,6 @@ extern "C" int gzpb_encode_stream(gzpb_ctx *c, const void *in_v, size_t in_len, 
                                   size_t out_cap, size_t *out_len)
 {
     if (!c || !out_v || !out_len || (in_len && !in_v)) return GZPB_EINVAL;
-    if (!is_deflate_format(c->format)) return GZPB_EINVAL;
     if (buffer_size == 0) buffer_size = c->max_block_bytes;
     if (buffer_size < GZPB_DICT_SIZE) return GZPB_EBUFFERSIZE;   // par/compress.rs:68-74
     if (buffer_size > c->max_block_bytes) return GZPB_EBUFFERSIZE;
@@ -570,9 +614,9 @@ extern "C" int gzpb_encode_stream(gzpb_ctx *c, const void *in_v, size_t in_len, 
             }
         }
         if (out_pinned) {
-            pos_out = (size_t)L.h_offsets[p.count];
+            pos_out = (size_t)L.h_offsets[p.count * c->cpu];
         } else {
-            size_t len = (size_t)L.h_offsets[p.count];
+            size_t len = (size_t)L.h_offsets[p.count * c->cpu];
             if (pos_out + len > out_cap) return GZPB_ECOMPRESS;
             memcpy(out + pos_out, L.h_packed, len);
             pos_out += len;
@@ -599,9 +643,9 @@ extern "C" int gzpb_encode_stream(gzpb_ctx *c, const void *in_v, size_t in_len, 
         rc = lane_launch(c, L, units.data(), cnt, true, buffer_size, in_pinned);
         if (rc != GZPB_OK) break;
         if (out_pinned) rc = lane_pack(c, L, dev_out, out_cap, prev_end, prev);
-        else rc = lane_pack(c, L, L.h_packed, (uint64_t)c->max_units * c->out_stride, nullptr, nullptr);
+        else rc = lane_pack(c, L, L.h_packed, (uint64_t)c->max_units * c->cpu * c->out_stride, nullptr, nullptr);
         if (rc != GZPB_OK) break;
-        prev = &L; prev_end = L.d_offsets + cnt;
+        prev = &L; prev_end = L.d_offsets + cnt * c->cpu;
         pend.push_back(Pending{done, cnt, li});
         done += cnt;
         li = (li + 1) % kLanes;

@@ -10,7 +10,7 @@ import pytest
 
 import oracle
 import gzp_b200
-from gzp_b200 import BGZF, GZIP, MGZIP, RAWDEFLATE, ZLIB
+from gzp_b200 import BGZF, GZIP, MGZIP, RAWDEFLATE, SNAP, ZLIB
 
 pytestmark = pytest.mark.gpu
 
@@ -121,4 +121,45 @@ def test_reference_regression_vector_on_gpu():
     got = ctx.encode_stream(data, 32768)
     assert got == oracle.compress_stream(oracle.GZIP, 3, 32768, [data])
     assert gzip.decompress(got) == data
+    ctx.close()
+
+
+def _snappy_deframe(z):
+    import pyarrow as pa
+    codec = pa.Codec("snappy")
+    out, pos = b"", 0
+    while pos < len(z):
+        if z[pos] == 0xFF:
+            assert z[pos:pos + 10] == bytes.fromhex("ff060000734e61507059"); pos += 10; continue
+        t = z[pos]; ln = int.from_bytes(z[pos + 1:pos + 4], "little"); crc = int.from_bytes(z[pos + 4:pos + 8], "little")
+        body = z[pos + 8:pos + 4 + ln]; pos += 4 + ln
+        if t == 0:
+            v = sh = i = 0
+            while True:
+                b = body[i]; v |= (b & 0x7F) << sh; sh += 7; i += 1
+                if b < 0x80:
+                    break
+            dec = codec.decompress(body, decompressed_size=v).to_pybytes()
+        else:
+            dec = body
+        assert oracle.lib().oracle_crc32c_masked(dec, len(dec)) == crc
+        out += dec
+    return out
+
+
+def test_snap_blocks_bit_exact_and_decodable(text_corpus):
+    from gzp_b200 import synth
+    rnd = random.Random(17)
+    ctx = gzp_b200.Context(SNAP, 0, max_blocks_in_flight=8)
+    blocks = [text_corpus[:131072], synth.low_entropy(131072), bytes(rnd.randrange(256) for _ in range(70000)), b"", b"a", b"ab" * 8,
+              b"x" * 17, text_corpus[100:100 + 65536], text_corpus[5:5 + 65537], bytes(100000), synth.fastq(90000),
+              bytes(rnd.choice(b"ab") for _ in range(3000)) * 20]
+    res = ctx.encode_blocks([(b, None, False) for b in blocks])
+    for i, (b, (enc, _, _)) in enumerate(zip(blocks, res)):
+        assert enc == oracle.encode_block(oracle.SNAP, 0, b), f"snap block {i} (len {len(b)}) differs from the oracle"
+        assert _snappy_deframe(enc) == b
+    data = synth.low_entropy(131072 * 9 + 777)
+    got = ctx.encode_stream(data)
+    assert got == oracle.compress_stream(oracle.SNAP, 0, 131072, [data])
+    assert _snappy_deframe(got) == data
     ctx.close()
