@@ -226,12 +226,14 @@ __device__ __forceinline__ uint32_t lz_extend(const uint32_t *s_in, uint32_t p, 
 
 __global__ void __launch_bounds__(kMatchThreads, 1)
 k_match(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, const uint16_t *__restrict__ prev3g,
-        uint64_t *__restrict__ mtab, int depth, int nice, int lazy)
+        uint64_t *__restrict__ mtab, uint8_t *__restrict__ clen_g, uint16_t *__restrict__ order_g, int depth, int nice, int lazy)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     uint32_t *s_in = (uint32_t *)smem;
     uint16_t *s_next = (uint16_t *)(smem + kInStride);
     __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t s_whist[32][128];
+    __shared__ uint32_t s_tot[128];
     const uint32_t tid = threadIdx.x;
     const Sub sb = sub_geometry(g, blockIdx.x);
     if (!sb.valid) return;
@@ -256,7 +258,54 @@ k_match(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, cons
     const uint16_t *p3 = prev3g + (size_t)blockIdx.x * kMaxUnitBytes;
     const uint32_t depthB = (uint32_t)depth >> 1;
 
+    // ---- phase 1: order the positions by chain length -------------------------
+    // Chains differ wildly in length (average ~10 nodes, cap D), so 32 consecutive
+    // positions walked in lock step keep only ~8/32 lanes busy.  A links-only
+    // pre-walk (no byte compares) gives every position's chain length; a counting
+    // sort (per-warp histograms in shared memory) then lets each warp of phase 2
+    // process 32 positions of EQUAL chain length.  Ordering only changes the
+    // schedule, never a result.
+    uint8_t *clen = clen_g + (size_t)blockIdx.x * kMaxUnitBytes;
+    uint16_t *order = order_g + (size_t)blockIdx.x * kMaxUnitBytes;
+    const uint32_t warp = tid >> 5;
+    for (uint32_t i = tid; i < 32 * 128; i += kMatchThreads) (&s_whist[0][0])[i] = 0;
+    __syncthreads();
     for (uint32_t p = sb.nb + tid; p < sb.ne; p += kMatchThreads) {
+        uint32_t len = 0;
+        if (n - p >= 5) {
+            uint32_t q = p;
+            while (len < (uint32_t)depth) {
+                uint32_t d = s_next[q];
+                if (d == 0) break;
+                q -= d;
+                if (p - q >= (uint32_t)kWindow) break;
+                len++;
+            }
+        }
+        clen[p] = (uint8_t)len;
+        atomicAdd(&s_whist[warp][len], 1u);
+    }
+    __syncthreads();
+    if (tid < 128) {
+        // column `tid` (one chain length): exclusive prefix over the 32 warps
+        uint32_t acc = 0;
+        for (int w = 0; w < 32; w++) { uint32_t v = s_whist[w][tid]; s_whist[w][tid] = acc; acc += v; }
+        s_tot[tid] = acc;
+    }
+    __syncthreads();
+    if (tid == 0) { uint32_t acc = 0; for (int l = 127; l >= 0; l--) { uint32_t v = s_tot[l]; s_tot[l] = acc; acc += v; } }   // longest first
+    __syncthreads();
+    for (uint32_t p = sb.nb + tid; p < sb.ne; p += kMatchThreads) {
+        uint32_t len = clen[p];
+        uint32_t slot = s_tot[len] + atomicAdd(&s_whist[warp][len], 1u);
+        order[slot] = (uint16_t)p;
+    }
+    __syncthreads();
+
+    // ---- phase 2: the searches, 32 positions of equal chain length per warp ----
+    const uint32_t npos = sb.ne - sb.nb;
+    for (uint32_t i = tid; i < npos; i += kMatchThreads) {
+        const uint32_t p = order[i];
         const uint32_t maxlen = min((uint32_t)kMaxMatch, n - p);
         if (maxlen < 5) { M[p] = 0; continue; }
         const uint32_t nicep = min((uint32_t)nice, maxlen);
@@ -1203,7 +1252,7 @@ cudaError_t launch_deflate_pipeline(const DeflateBatch &b, cudaStream_t st)
         k_chain<<<b.nunits * b.spu, kChainThreads, chain_smem, st>>>(g, b.next4, b.prev3);
         DBG_SYNC("k_chain");
         if (b.timer) { b.timer->stop(st); b.timer->start(KT_MATCH, st); }
-        k_match<<<b.nunits * b.spu, kMatchThreads, match_smem, st>>>(g, b.next4, b.prev3, b.mtab, lp.depth, lp.nice, lp.mode >= 1);
+        k_match<<<b.nunits * b.spu, kMatchThreads, match_smem, st>>>(g, b.next4, b.prev3, b.mtab, b.clen, b.order, lp.depth, lp.nice, lp.mode >= 1);
         DBG_SYNC("k_match");
         if (b.timer) b.timer->stop(st);
     }

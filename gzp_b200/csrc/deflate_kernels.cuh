@@ -42,6 +42,8 @@ struct DeflateBatch {
     uint16_t *next4;          // nunits * spu * 65536
     uint16_t *prev3;          // nunits * spu * 65536
     uint64_t *mtab;           // nunits * m_stride
+    uint8_t *clen;            // nunits * spu * 65536 (chain lengths, k_match scratch)
+    uint16_t *order;          // nunits * spu * 65536 (positions sorted by chain length)
     uint32_t *crc;            // nunits
     uint32_t *tokens;         // nunits * kTokStride
     uint8_t *out;             // nunits * kOutStride
