@@ -356,9 +356,9 @@ k_match(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, cons
 // dynamic / static / stored, and packs the tokens in parallel (prefix scan of
 // code lengths, OR-merge in a shared staging buffer, coalesced 32-bit stores).
 // =============================================================================
-constexpr int kEmitThreads = 64;
-constexpr int kTile = 256;                 // positions per streamed tile
-constexpr int kRing = 2;                   // tiles resident in the shared-memory ring
+constexpr int kEmitThreads = 32;
+constexpr int kTile = 128;                 // positions per streamed tile
+constexpr int kRing = 4;                   // tiles resident in the shared-memory ring
 constexpr int kTokPerThread = 8;
 constexpr int kChunkTok = kEmitThreads * kTokPerThread;
 constexpr int kStageWords = (kChunkTok * 48) / 32 + 8;
@@ -370,7 +370,6 @@ struct EmitShared {
     uint32_t fl[kNumLitlen];
     uint32_t fo[kNumOffset];
     uint32_t obs[10], new_obs[10];
-    uint32_t A[kNumLitlen];
     uint8_t lens[kNumLitlen + kNumOffset];   // litlen then offset lens (contiguous like libdeflate)
     uint16_t lcw[kNumLitlen];
     uint16_t ocw[kNumOffset];
@@ -378,7 +377,10 @@ struct EmitShared {
     uint16_t pcw[kNumPrecode];
     uint32_t pfreq[kNumPrecode];
     uint16_t items[kNumLitlen + kNumOffset];
-    uint32_t stage[kStageWords];
+    union {                                  // never live at the same time
+        uint32_t A[kNumLitlen];              // Huffman sort / tree array
+        uint32_t stage[kStageWords];         // bit-packing staging words
+    };
     uint32_t scan[kEmitThreads / 32];
     uint32_t used[8];
     // control block written by thread 0
@@ -565,6 +567,10 @@ struct Parser {
     {
         uint32_t want = min(ntiles, p / kTile + kRing);
         if (issued < want) {
+            // tiles a long match jumped over were issued but never consumed: observe their
+            // completion before their slots (and mbarrier phases) are reused
+            const uint32_t first = p / kTile;
+            while (ready < issued && ready < first) { mbar_wait(&S->bar[ready % kRing], (ready / kRing) & 1); ready++; }
             __syncwarp();
             if ((threadIdx.x & 31) == 0) {
                 fence_proxy_async();
@@ -759,35 +765,37 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
                     const uint32_t e_l = q + (myw & 0x1FF);
                     const bool ends_iter = !((myw >> 9) & 1);     // next state is F: a main-loop iteration ends here
                     // ---- events ----
-                    uint32_t rmask = (mode != 0) ? __ballot_sync(0xFFFFFFFFu, onpath && !asH && q >= next_recalc) : 0u;
-                    uint32_t cmask = __ballot_sync(0xFFFFFFFFu, onpath && ends_iter && (num_new_obs + incl >= (uint32_t)kObsPerCheck) &&
-                                                                     (e_l - bb >= (uint32_t)kMinBlockLength) && (n - e_l >= (uint32_t)kMinBlockLength));
-                    // sequence store full (SEQ_STORE_LENGTH matches in this DEFLATE block): the block ends
-                    const uint32_t mmask = __ballot_sync(0xFFFFFFFFu, onpath && ((myw >> 10) & 1));
-                    const uint32_t mincl = __popc(mmask & (lane == 31 ? 0xFFFFFFFFu : ((2u << lane) - 1)));
-                    uint32_t smask = __ballot_sync(0xFFFFFFFFu, onpath && ends_iter && (nmatch + mincl >= (uint32_t)kSeqStoreLength));
-                    int Lr = rmask ? __ffs(rmask) - 1 : 64, Lc = cmask ? __ffs(cmask) - 1 : 64, Ls = smask ? __ffs(smask) - 1 : 64;
-                    uint32_t commit_mask, next_p, next_h;
+                    // (cheap uniform pre-test: most windows cannot contain any event)
+                    uint32_t commit_mask = vis, next_p = p + c, next_h = st_h;
                     int event = 0;   // 1 = recalc before lane Lr, 2 = block check after lane Lc, 3 = sequence store full after lane Ls
-                    if (Lr <= Lc && Lr <= Ls && Lr < 64) { event = 1; commit_mask = vis & ((1u << Lr) - 1); next_p = p + Lr; next_h = 0; }
-                    else if (Ls <= Lc && Ls < 64) { event = 3; commit_mask = vis & (Ls == 31 ? 0xFFFFFFFFu : ((2u << Ls) - 1)); next_p = __shfl_sync(0xFFFFFFFFu, e_l, Ls); next_h = 0; }
-                    else if (Lc < 64) { event = 2; commit_mask = vis & (Lc == 31 ? 0xFFFFFFFFu : ((2u << Lc) - 1)); next_p = __shfl_sync(0xFFFFFFFFu, e_l, Lc); next_h = 0; }
-                    else { commit_mask = vis; next_p = p + c; next_h = st_h; }
+                    uint32_t mmask = __ballot_sync(0xFFFFFFFFu, onpath && ((myw >> 10) & 1));
+                    const bool may_check = (num_new_obs + 32 >= (uint32_t)kObsPerCheck) && (p + 32 + 258 - bb >= (uint32_t)kMinBlockLength) && (n - p > (uint32_t)kMinBlockLength);
+                    const bool may_recalc = (mode != 0) && (p + 32 > next_recalc);
+                    const bool may_seq = nmatch + 32 >= (uint32_t)kSeqStoreLength;
+                    if (may_check || may_recalc || may_seq) {
+                        uint32_t rmask = may_recalc ? __ballot_sync(0xFFFFFFFFu, onpath && !asH && q >= next_recalc) : 0u;
+                        uint32_t cmask = __ballot_sync(0xFFFFFFFFu, onpath && ends_iter && (num_new_obs + incl >= (uint32_t)kObsPerCheck) &&
+                                                                         (e_l - bb >= (uint32_t)kMinBlockLength) && (n - e_l >= (uint32_t)kMinBlockLength));
+                        // sequence store full (SEQ_STORE_LENGTH matches in this DEFLATE block): the block ends
+                        const uint32_t mincl = __popc(mmask & (lane == 31 ? 0xFFFFFFFFu : ((2u << lane) - 1)));
+                        uint32_t smask = __ballot_sync(0xFFFFFFFFu, onpath && ends_iter && (nmatch + mincl >= (uint32_t)kSeqStoreLength));
+                        int Lr = rmask ? __ffs(rmask) - 1 : 64, Lc = cmask ? __ffs(cmask) - 1 : 64, Ls = smask ? __ffs(smask) - 1 : 64;
+                        if (Lr <= Lc && Lr <= Ls && Lr < 64) { event = 1; commit_mask = vis & ((1u << Lr) - 1); next_p = p + Lr; next_h = 0; }
+                        else if (Ls <= Lc && Ls < 64) { event = 3; commit_mask = vis & (Ls == 31 ? 0xFFFFFFFFu : ((2u << Ls) - 1)); next_p = __shfl_sync(0xFFFFFFFFu, e_l, Ls); next_h = 0; }
+                        else if (Lc < 64) { event = 2; commit_mask = vis & (Lc == 31 ? 0xFFFFFFFFu : ((2u << Lc) - 1)); next_p = __shfl_sync(0xFFFFFFFFu, e_l, Lc); next_h = 0; }
+                    }
                     // ---- commit ----
                     if ((commit_mask >> lane) & 1u) {
                         const uint32_t ti = ntok + incl - 1;
-                        if ((myw >> 10) & 1) {
-                            const uint32_t mlen = asH ? lenH : lenF, moff = asH ? offH : offF;
-                            atomicAdd(&S.fl[kFirstLenSym + len_slot_only(mlen)], 1u);
-                            atomicAdd(&S.fo[off_slot_only(moff)], 1u);
-                            atomicAdd(&S.new_obs[8 + (mlen >= 9)], 1u);
-                            tok[ti] = 0x80000000u | (mlen << 16) | moff;
-                        } else {
-                            const uint32_t lit = P.B(q);
-                            atomicAdd(&S.fl[lit], 1u);
-                            atomicAdd(&S.new_obs[((lit >> 5) & 6) | (lit & 1)], 1u);
-                            tok[ti] = lit;
-                        }
+                        const bool isM = (myw >> 10) & 1;
+                        const uint32_t mlen = asH ? lenH : lenF, moff = asH ? offH : offF;
+                        const uint32_t lit = isM ? 0u : P.B(q);
+                        const uint32_t lsym = isM ? kFirstLenSym + len_slot_only(mlen) : lit;
+                        const uint32_t ocls = isM ? 8 + (mlen >= 9) : (((lit >> 5) & 6) | (lit & 1));
+                        atomicAdd(&S.fl[lsym], 1u);
+                        atomicAdd(&S.new_obs[ocls], 1u);
+                        if (isM) atomicAdd(&S.fo[off_slot_only(moff)], 1u);
+                        tok[ti] = isM ? (0x80000000u | (mlen << 16) | moff) : lit;
                     }
                     {
                         uint32_t added = __popc(commit_mask);
