@@ -120,7 +120,7 @@ __device__ __forceinline__ void chain_warp(const uint32_t *__restrict__ inw, uin
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t ninsert = n >= 5 ? n - 4 : 0;
     const uint32_t lt = lanemask_lt();
-    constexpr int G = 8;  // tiles per register group
+    constexpr int G = 16;  // tiles per register group (prefetched one group ahead)
     uint32_t v[G], vn[G];
 #pragma unroll
     for (int k = 0; k < G; k++) { uint32_t p = 32 * k + lane; vn[k] = p < ninsert ? ldg32u(inw, p) : 0; }
@@ -310,6 +310,7 @@ k_match(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, cons
         if (maxlen < 5) { M[p] = 0; continue; }
         const uint32_t nicep = min((uint32_t)nice, maxlen);
         const uint32_t seq4 = ld32u(s_in, p);
+        const uint32_t w1 = ld32u(s_in, p + 4), w2 = ld32u(s_in, p + 8);   // bytes 4..11 of this position, for the inline extension
         uint32_t d3 = p3[p];
         uint32_t off3 = 0;
         if (d3 && d3 <= 8192u && ((ld32u(s_in, p - d3) ^ seq4) & 0xFFFFFFu) == 0) off3 = d3;
@@ -330,7 +331,16 @@ k_match(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, cons
                 cand = (b[q + best] == b[p + best]) && (ld32u(s_in, q) == seq4);
             }
             if (cand) {
-                uint32_t len = lz_extend(s_in, p, q, 4, maxlen);
+                // most matches are short: first 8 bytes of the extension inline, the rest in lz_extend
+                uint32_t len;
+                uint32_t x = ld32u(s_in, q + 4) ^ w1;
+                if (x) len = 4 + ((__ffs(x) - 1) >> 3);
+                else {
+                    x = ld32u(s_in, q + 8) ^ w2;
+                    if (x) len = 8 + ((__ffs(x) - 1) >> 3);
+                    else len = (maxlen > 12) ? lz_extend(s_in, p, q, 12, maxlen) : 12;
+                }
+                len = min(len, maxlen);
                 if (len > best) {
                     best = len; boff = p - q;
                     if (len >= nicep) break;
