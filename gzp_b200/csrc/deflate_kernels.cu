@@ -226,7 +226,8 @@ __device__ __forceinline__ uint32_t lz_extend(const uint32_t *s_in, uint32_t p, 
 
 __global__ void __launch_bounds__(kMatchThreads, 1)
 k_match(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, const uint16_t *__restrict__ prev3g,
-        uint64_t *__restrict__ mtab, uint8_t *__restrict__ clen_g, uint16_t *__restrict__ order_g, int depth, int nice, int lazy)
+        uint64_t *__restrict__ mtab, uint32_t *__restrict__ mtab2, uint8_t *__restrict__ clen_g, uint16_t *__restrict__ order_g,
+        int depth, int nice, int lazy)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     uint32_t *s_in = (uint32_t *)smem;
@@ -240,6 +241,7 @@ k_match(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, cons
     const uint32_t n = sb.len;
     const uint8_t *in = g.in + (size_t)sb.u * g.in_stride + sb.h;
     uint64_t *M = mtab + (size_t)sb.u * g.m_stride + sb.h;
+    uint32_t *M2 = (lazy == 2) ? mtab2 + (size_t)sb.u * g.m_stride + sb.h : nullptr;   // lazy2: depth/4 column
 
     if (tid == 0) {
         mbar_init(&bar, 1);
@@ -256,7 +258,7 @@ k_match(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, cons
         mbar_wait(&bar, 0);
     }
     const uint16_t *p3 = prev3g + (size_t)blockIdx.x * kMaxUnitBytes;
-    const uint32_t depthB = (uint32_t)depth >> 1;
+    const uint32_t depthB = (uint32_t)depth >> 1, depthC = (uint32_t)depth >> 2;
 
     // ---- phase 1: order the positions by chain length -------------------------
     // Chains differ wildly in length (average ~10 nodes, cap D), so 32 consecutive
@@ -282,6 +284,7 @@ k_match(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, cons
                 len++;
             }
         }
+        len = min(len, 127u);
         clen[p] = (uint8_t)len;
         atomicAdd(&s_whist[warp][len], 1u);
     }
@@ -307,7 +310,7 @@ k_match(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, cons
     for (uint32_t i = tid; i < npos; i += kMatchThreads) {
         const uint32_t p = order[i];
         const uint32_t maxlen = min((uint32_t)kMaxMatch, n - p);
-        if (maxlen < 5) { M[p] = 0; continue; }
+        if (maxlen < 5) { M[p] = 0; if (M2) M2[p] = 0; continue; }
         const uint32_t nicep = min((uint32_t)nice, maxlen);
         const uint32_t seq4 = ld32u(s_in, p);
         const uint32_t w1 = ld32u(s_in, p + 4), w2 = ld32u(s_in, p + 8);   // bytes 4..11 of this position, for the inline extension
@@ -315,8 +318,8 @@ k_match(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, cons
         uint32_t off3 = 0;
         if (d3 && d3 <= 8192u && ((ld32u(s_in, p - d3) ^ seq4) & 0xFFFFFFu) == 0) off3 = d3;
 
-        uint32_t best = 3, boff = 0, lenB = 0, offB = 0;
-        bool haveB = !lazy;
+        uint32_t best = 3, boff = 0, lenB = 0, offB = 0, lenC = 0, offC = 0;
+        bool haveB = !lazy, haveC = (lazy != 2);
         uint32_t q = p, visited = 0;
         for (;;) {
             uint32_t d = s_next[q];
@@ -346,11 +349,13 @@ k_match(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, cons
                     if (len >= nicep) break;
                 }
             }
+            if (!haveC && visited == depthC) { haveC = true; lenC = best > 3 ? best : 0; offC = boff; }
             if (!haveB && visited == depthB) { haveB = true; lenB = best > 3 ? best : 0; offB = boff; }
             if (visited == (uint32_t)depth) break;
         }
         uint32_t lenA = best > 3 ? best : 0;
         if (!haveB) { lenB = lenA; offB = boff; }
+        if (M2) { if (!haveC) { lenC = lenA; offC = boff; } M2[p] = (lenC ? lenC - 3 : 0) | (offC << 8); }
         if (!lazy) { lenB = 0; offB = 0; }
         M[p] = pack_entry(lenA, boff, lenB, offB, d3 != 0, off3);
     }
@@ -616,7 +621,7 @@ __device__ __forceinline__ void table_search(uint64_t e, uint32_t b, bool useB, 
 
 __global__ void __launch_bounds__(kEmitThreads)
 k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
-       const uint64_t *__restrict__ mtab, const uint32_t *__restrict__ crc_in, uint32_t *__restrict__ tok_base,
+       const uint64_t *__restrict__ mtab, const uint32_t *__restrict__ mtab2, const uint32_t *__restrict__ crc_in, uint32_t *__restrict__ tok_base,
        uint8_t *__restrict__ out_base, uint32_t *__restrict__ out_len, int32_t *__restrict__ out_status,
        int mode, int depth, int nice, int level, int format)
 {
@@ -711,6 +716,107 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
                 next_recalc = bb + min(n - bb, 10000u);
                 uint32_t ntok = 0, nmatch = 0, num_obs = 0, num_new_obs = 0, in_h = 0;
                 bool end_block = false;
+                if (mode == 2) {
+                    // lazy2 (levels 8-9): the reference's loop restated one iteration at a time; every lane
+                    // runs the same (uniform) control flow, lane 0 commits.  These levels are bound by the
+                    // depth-300/600 chain walks of k_match, not by this loop.
+                    const uint32_t *M2 = mtab2 + (size_t)u * g.m_stride;
+                    auto emit_lit = [&](uint32_t pos) {
+                        if (lane == 0) {
+                            uint32_t lit = in[pos];
+                            atomicAdd(&S.fl[lit], 1u);
+                            atomicAdd(&S.new_obs[((lit >> 5) & 6) | (lit & 1)], 1u);
+                            tok[ntok] = lit;
+                        }
+                        ntok++; num_new_obs++;
+                    };
+                    do {
+                        P.advance(p);
+                        P.need(min(n - 1, p + 3));
+                        if (p >= next_recalc) {
+                            __syncwarp();
+                            uint32_t total = 0;
+                            for (int i = 0; i < 8; i++) total += S.fl[lane * 8 + i];
+                            for (int o = 16; o; o >>= 1) total += __shfl_xor_sync(0xFFFFFFFFu, total, o);
+                            uint32_t cutoff = total >> 10, nu = 0;
+                            for (int i = 0; i < 8; i++) nu += (S.fl[lane * 8 + i] > cutoff);
+                            for (int o = 16; o; o >>= 1) nu += __shfl_xor_sync(0xFFFFFFFFu, nu, o);
+                            min_len = choose_min_match_len(nu, depth);
+                            next_recalc += min(n - next_recalc, p - bb);
+                        }
+                        uint32_t cur_len, cur_off;
+                        table_search(P.M(p), min_len - 1, false, min((uint32_t)kMaxMatch, n - p), cur_len, cur_off);
+                        if (cur_len < min_len || (cur_len == 3 && cur_off > 8192)) { emit_lit(p); p++; }
+                        else {
+                            uint32_t m = p;
+                            for (;;) {
+                                const uint32_t nice_m = min((uint32_t)nice, min((uint32_t)kMaxMatch, n - m));
+                                if (cur_len >= nice_m) break;
+                                P.advance(m);
+                                P.need(min(n - 1, m + 3));
+                                uint32_t nl, no;
+                                const uint32_t maxlen1 = (m + 1 < n) ? min((uint32_t)kMaxMatch, n - (m + 1)) : 0u;
+                                table_search(maxlen1 >= 5 ? P.M(m + 1) : 0ull, cur_len - 1, true, maxlen1, nl, no);
+                                if (nl >= cur_len && 4 * (int)(nl - cur_len) + ((int)bsr32(cur_off) - (int)bsr32(no)) > 2) {
+                                    emit_lit(m); m++; cur_len = nl; cur_off = no;
+                                    continue;
+                                }
+                                const uint32_t maxlen2 = (m + 2 < n) ? min((uint32_t)kMaxMatch, n - (m + 2)) : 0u;
+                                nl = cur_len - 1; no = 0;
+                                if (maxlen2 >= 5) {
+                                    // longest_match(m+2, cur_len-1, depth>>2) answered from the depth/4 column
+                                    const uint64_t e2 = P.M(m + 2);
+                                    const uint32_t c2 = M2[m + 2];
+                                    uint32_t lx = c2 & 0xFF, ox = (c2 >> 8) & 0x7FFF, b = cur_len - 1;
+                                    if (lx) lx += 3;
+                                    if (b < 4) {
+                                        if ((e2 >> 46) & 1) {
+                                            uint32_t off3 = (uint32_t)(e2 >> 47) & 0x3FFF;
+                                            if (b < 3 && off3) { nl = 3; no = off3; }
+                                            if (lx) { nl = lx; no = ox; }
+                                        }
+                                    } else if (lx > b) { nl = lx; no = ox; }
+                                }
+                                if (nl >= cur_len && 4 * (int)(nl - cur_len) + ((int)bsr32(cur_off) - (int)bsr32(no)) > 6) {
+                                    emit_lit(m); emit_lit(m + 1); m += 2; cur_len = nl; cur_off = no;
+                                    continue;
+                                }
+                                break;
+                            }
+                            if (lane == 0) {
+                                atomicAdd(&S.fl[kFirstLenSym + len_slot_only(cur_len)], 1u);
+                                atomicAdd(&S.fo[off_slot_only(cur_off)], 1u);
+                                atomicAdd(&S.new_obs[8 + (cur_len >= 9)], 1u);
+                                tok[ntok] = 0x80000000u | (cur_len << 16) | cur_off;
+                            }
+                            ntok++; num_new_obs++; nmatch++;
+                            p = m + cur_len;
+                        }
+                        if (nmatch >= (uint32_t)kSeqStoreLength) end_block = true;
+                        else if (num_new_obs >= (uint32_t)kObsPerCheck && p - bb >= (uint32_t)kMinBlockLength && n - p >= (uint32_t)kMinBlockLength) {
+                            __syncwarp();
+                            uint32_t block_length = p - bb;
+                            if (num_obs > 0) {
+                                uint32_t d = 0;
+                                if (lane < 10) {
+                                    uint32_t expected = S.obs[lane] * num_new_obs, actual = S.new_obs[lane] * num_obs;
+                                    d = actual > expected ? actual - expected : expected - actual;
+                                }
+                                for (int o = 16; o; o >>= 1) d += __shfl_xor_sync(0xFFFFFFFFu, d, o);
+                                uint32_t num_items = num_obs + num_new_obs;
+                                uint32_t cutoff = num_new_obs * 200 / 512 * num_obs;
+                                if (block_length < 10000 && num_items < 8192)
+                                    cutoff += (uint32_t)((uint64_t)cutoff * (8192 - num_items) / 8192);
+                                if (d + (block_length / 4096) * num_obs >= cutoff) end_block = true;
+                            }
+                            if (!end_block) {
+                                if (lane < 10) { S.obs[lane] += S.new_obs[lane]; S.new_obs[lane] = 0; }
+                                num_obs += num_new_obs; num_new_obs = 0;
+                            }
+                            __syncwarp();
+                        }
+                    } while (p < max_block_end && !end_block);
+                } else
                 do {
                     P.advance(p);
                     P.need(min(n - 1, p + 33));
@@ -1270,12 +1376,12 @@ cudaError_t launch_deflate_pipeline(const DeflateBatch &b, cudaStream_t st)
         k_chain<<<b.nunits * b.spu, kChainThreads, chain_smem, st>>>(g, b.next4, b.prev3);
         DBG_SYNC("k_chain");
         if (b.timer) { b.timer->stop(st); b.timer->start(KT_MATCH, st); }
-        k_match<<<b.nunits * b.spu, kMatchThreads, match_smem, st>>>(g, b.next4, b.prev3, b.mtab, b.clen, b.order, lp.depth, lp.nice, lp.mode >= 1);
+        k_match<<<b.nunits * b.spu, kMatchThreads, match_smem, st>>>(g, b.next4, b.prev3, b.mtab, b.mtab2, b.clen, b.order, lp.depth, lp.nice, lp.mode);
         DBG_SYNC("k_match");
         if (b.timer) b.timer->stop(st);
     }
     if (b.timer) b.timer->start(KT_EMIT, st);
-    k_emit<<<b.nunits, kEmitThreads, 0, st>>>(g, b.unit_flags, b.mtab, b.crc, b.tokens, b.out, b.out_len,
+    k_emit<<<b.nunits, kEmitThreads, 0, st>>>(g, b.unit_flags, b.mtab, b.mtab2, b.crc, b.tokens, b.out, b.out_len,
                                              b.status, lp.mode, lp.depth, lp.nice, b.level, b.format);
     DBG_SYNC("k_emit");
     if (b.timer) b.timer->stop(st);

@@ -42,6 +42,7 @@ struct DeflateBatch {
     uint16_t *next4;          // nunits * spu * 65536
     uint16_t *prev3;          // nunits * spu * 65536
     uint64_t *mtab;           // nunits * m_stride
+    uint32_t *mtab2;          // nunits * m_stride, lazy2 levels only (depth/4 column), else NULL
     uint8_t *clen;            // nunits * spu * 65536 (chain lengths, k_match scratch)
     uint16_t *order;          // nunits * spu * 65536 (positions sorted by chain length)
     uint32_t *crc;            // nunits

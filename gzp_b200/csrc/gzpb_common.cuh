@@ -64,6 +64,8 @@ __host__ __device__ inline bool level_params(int level, LevelParams *lp)
     case 5: lp->mode = 1; lp->depth = 16; lp->nice = 30; return true;
     case 6: lp->mode = 1; lp->depth = 35; lp->nice = 65; return true;
     case 7: lp->mode = 1; lp->depth = 100; lp->nice = 130; return true;
+    case 8: lp->mode = 2; lp->depth = 300; lp->nice = 258; return true;
+    case 9: lp->mode = 2; lp->depth = 600; lp->nice = 258; return true;
     default: return false;
     }
 }

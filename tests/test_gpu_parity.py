@@ -163,3 +163,21 @@ def test_snap_blocks_bit_exact_and_decodable(text_corpus):
     assert got == oracle.compress_stream(oracle.SNAP, 0, 131072, [data])
     assert _snappy_deframe(got) == data
     ctx.close()
+
+
+@pytest.mark.parametrize("level", [8, 9])
+def test_lazy2_levels(text_corpus, level):
+    # levels 8-9: lazy2 parser, depth 300/600 (BASELINE configs[4] uses level 9 for Gzip)
+    ctx = gzp_b200.Context(BGZF, level, max_blocks_in_flight=8)
+    blocks = [text_corpus[i:i + 65280] for i in range(0, 3 * 65280, 65280)] + _edge_blocks()[:12]
+    got = ctx.encode_blocks([(b, None, False) for b in blocks])
+    for i, (b, (enc, _, _)) in enumerate(zip(blocks, got)):
+        assert enc == oracle.encode_block(oracle.BGZF, level, b), f"block {i} level {level}"
+    ctx.close()
+    ctx = gzp_b200.Context(GZIP, level, max_block_bytes=262144, max_blocks_in_flight=2)
+    from gzp_b200 import synth
+    data = synth.fastq(262144 * 2 + 999)
+    got = ctx.encode_stream(data, 262144)
+    assert got == oracle.compress_stream(oracle.GZIP, level, 262144, [data])
+    assert gzip.decompress(got) == data
+    ctx.close()
