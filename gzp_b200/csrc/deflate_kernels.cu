@@ -202,6 +202,165 @@ k_chain(const __grid_constant__ Geo g, uint16_t *__restrict__ next4, uint16_t *_
 }
 
 // =============================================================================
+// k_split + k_link: the same hash-chain links as k_chain, restructured for
+// concurrency.  k_chain keeps only two latency-bound warps busy per SM (its
+// 192 KiB of bucket tables allow one CTA per SM).  Here a fully parallel pass
+// (k_split) partitions the positions of a sub-unit by bucket range into
+// position-ordered lists (4 quarters of the hash4 space, 2 halves of the hash3
+// space), and each list is linked by its own single-warp job (k_link) that needs
+// only a 32 KiB table, so seven jobs share an SM.  Same optimistic-insert /
+// ballot-ordering logic per tile of 32 list entries; identical links.
+// =============================================================================
+constexpr int kSplitThreads = 1024;
+constexpr int kL4 = 8, kL3 = 4;          // lists: hash4 space in eighths, hash3 space in quarters
+constexpr int kSplitLists = kL4 + kL3;
+constexpr int kLinkBits = 13;            // buckets per link job (16 KiB table)
+constexpr int kLsStride = 16;            // list_start entries per sub-unit: [0..8] hash4 bounds, [9..13] hash3 bounds
+
+__global__ void __launch_bounds__(kSplitThreads)
+k_split(const __grid_constant__ Geo g, uint32_t *__restrict__ lists, uint32_t *__restrict__ list_start,
+        uint16_t *__restrict__ next4, uint16_t *__restrict__ prev3)
+{
+    __shared__ uint32_t s_w[32][kSplitLists];     // per-warp member counts, then running bases
+    __shared__ uint32_t s_start[kSplitLists];
+    const Sub sb = sub_geometry(g, blockIdx.x);
+    if (!sb.valid) return;
+    const uint32_t n = sb.len, ninsert = n >= 5 ? n - 4 : 0;
+    const uint32_t *inw = (const uint32_t *)(g.in + (size_t)sb.u * g.in_stride + sb.h);
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, lt = lanemask_lt();
+    const uint32_t ntiles = (ninsert + 31) / 32, tpw = (ntiles + 31) / 32;
+    const uint32_t t0 = warp * tpw, t1 = min(ntiles, t0 + tpw);
+    uint32_t *arr4 = lists + (size_t)blockIdx.x * 2 * kMaxUnitBytes;
+    uint32_t *arr3 = arr4 + kMaxUnitBytes;
+
+    if (lane < kSplitLists) s_w[warp][lane] = 0;
+    __syncwarp();
+    // pass 1: every warp counts the list members of its contiguous range of tiles
+    for (uint32_t t = t0; t < t1; t++) {
+        const uint32_t p = t * 32 + lane;
+        const bool act = p < ninsert;
+        const uint32_t v = act ? ldg32u(inw, p) : 0;
+        uint32_t h4 = lz_hash(v, 16), h3 = lz_hash(v & 0xFFFFFFu, 15);
+        if (p == 0 && sb.quirk) { h4 = 0; h3 = 0; }
+        const uint32_t q4 = h4 >> kLinkBits, q3 = h3 >> kLinkBits;
+        const uint32_t m4 = __match_any_sync(0xFFFFFFFFu, act ? q4 : 64u);
+        const uint32_t m3 = __match_any_sync(0xFFFFFFFFu, act ? q3 : 64u);
+        if (act && (m4 & lt) == 0) s_w[warp][q4] += __popc(m4);          // group leader
+        if (act && (m3 & lt) == 0) s_w[warp][kL4 + q3] += __popc(m3);
+        __syncwarp();
+    }
+    __syncthreads();
+    if (tid < kSplitLists) {
+        // exclusive prefix over the warps (position order) for list `tid`
+        uint32_t acc = 0;
+        for (int w = 0; w < 32; w++) { uint32_t c = s_w[w][tid]; s_w[w][tid] = acc; acc += c; }
+        s_start[tid] = acc;   // total
+    }
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t *ls = list_start + (size_t)blockIdx.x * kLsStride;
+        uint32_t a = 0;
+        for (int k = 0; k < kL4; k++) { uint32_t c = s_start[k]; s_start[k] = a; ls[k] = a; a += c; }
+        ls[kL4] = a;
+        a = 0;
+        for (int k = 0; k < kL3; k++) { uint32_t c = s_start[kL4 + k]; s_start[kL4 + k] = a; ls[kL4 + 1 + k] = a; a += c; }
+        ls[kL4 + 1 + kL3] = a;
+    }
+    __syncthreads();
+    // pass 2: scatter (hash, position) entries in position order
+    for (uint32_t t = t0; t < t1; t++) {
+        const uint32_t p = t * 32 + lane;
+        const bool act = p < ninsert;
+        const uint32_t v = act ? ldg32u(inw, p) : 0;
+        uint32_t h4 = lz_hash(v, 16), h3 = lz_hash(v & 0xFFFFFFu, 15);
+        if (p == 0 && sb.quirk) { h4 = 0; h3 = 0; }
+        const uint32_t q4 = h4 >> kLinkBits, q3 = h3 >> kLinkBits;
+        const uint32_t m4 = __match_any_sync(0xFFFFFFFFu, act ? q4 : 64u);
+        const uint32_t m3 = __match_any_sync(0xFFFFFFFFu, act ? q3 : 64u);
+        uint32_t b4 = 0, b3 = 0;
+        if (act) { b4 = s_w[warp][q4]; b3 = s_w[warp][kL4 + q3]; }
+        __syncwarp();
+        if (act) {
+            arr4[s_start[q4] + b4 + __popc(m4 & lt)] = h4 | (p << 16);
+            arr3[s_start[kL4 + q3] + b3 + __popc(m3 & lt)] = h3 | (p << 16);
+            if ((m4 & lt) == 0) s_w[warp][q4] = b4 + __popc(m4);
+            if ((m3 & lt) == 0) s_w[warp][kL4 + q3] = b3 + __popc(m3);
+        }
+        __syncwarp();
+    }
+    // positions that are never inserted carry no link
+    for (uint32_t p = ninsert + tid; p < n; p += kSplitThreads) {
+        next4[(size_t)blockIdx.x * kMaxUnitBytes + p] = 0;
+        prev3[(size_t)blockIdx.x * kMaxUnitBytes + p] = 0;
+    }
+}
+
+__global__ void __launch_bounds__(32)
+k_link(const __grid_constant__ Geo g, const uint32_t *__restrict__ lists, const uint32_t *__restrict__ list_start,
+       uint16_t *__restrict__ next4, uint16_t *__restrict__ prev3)
+{
+    __shared__ __align__(16) uint16_t head[1 << kLinkBits];
+    const uint32_t sub = blockIdx.x / kSplitLists, job = blockIdx.x % kSplitLists;
+    const Sub sb = sub_geometry(g, sub);
+    if (!sb.valid) return;
+    const uint32_t lane = threadIdx.x, lt = lanemask_lt();
+    const uint32_t *ls = list_start + (size_t)sub * kLsStride;
+    const bool is4 = job < kL4;
+    const uint32_t *arr = lists + (size_t)sub * 2 * kMaxUnitBytes + (is4 ? 0 : kMaxUnitBytes);
+    const uint32_t beg = is4 ? ls[job] : ls[kL4 + 1 + (job - kL4)];
+    const uint32_t end = is4 ? ls[job + 1] : ls[kL4 + 2 + (job - kL4)];
+    uint16_t *out = (is4 ? next4 : prev3) + (size_t)sub * kMaxUnitBytes;
+    {
+        uint4 ones = make_uint4(~0u, ~0u, ~0u, ~0u);
+        uint4 *h = (uint4 *)head;
+        for (uint32_t i = lane; i < (2u << kLinkBits) / 16; i += 32) h[i] = ones;
+    }
+    __syncwarp();
+    constexpr int G = 8;
+    uint32_t en[G];
+#pragma unroll
+    for (int k = 0; k < G; k++) { uint32_t i = beg + 32 * k + lane; en[k] = i < end ? __ldg(arr + i) : 0; }
+    for (uint32_t base0 = beg; base0 < end; base0 += 32 * G) {
+        uint32_t e[G];
+#pragma unroll
+        for (int k = 0; k < G; k++) e[k] = en[k];
+#pragma unroll
+        for (int k = 0; k < G; k++) { uint32_t i = base0 + 32 * (G + k) + lane; en[k] = i < end ? __ldg(arr + i) : 0; }
+#pragma unroll
+        for (int k = 0; k < G; k++) {
+            const uint32_t i = base0 + 32 * k + lane;
+            if (base0 + 32 * k >= end) break;
+            const bool act = i < end;
+            const uint32_t b = e[k] & ((1u << kLinkBits) - 1), p = e[k] >> 16;
+            uint32_t prev = act ? (uint32_t)head[b] : kNone16;
+            if (act) head[b] = (uint16_t)p;
+            __syncwarp();
+            bool lost = act && head[b] != (uint16_t)p;
+            uint32_t lostmask = __ballot_sync(0xFFFFFFFFu, lost);
+            while (lostmask) {
+                const int j = __ffs(lostmask) - 1;
+                const uint32_t bj = __shfl_sync(0xFFFFFFFFu, b, j);
+                const bool member = act && b == bj;
+                const uint32_t grp = __ballot_sync(0xFFFFFFFFu, member);
+                const uint32_t lower = grp & lt;
+                const uint32_t pl = __shfl_sync(0xFFFFFFFFu, p, lower ? 31 - __clz(lower) : lane);
+                if (member) {
+                    if (lower) prev = pl;
+                    if ((grp >> lane) == 1u) head[b] = (uint16_t)p;
+                }
+                lostmask &= ~grp;
+            }
+            __syncwarp();
+            if (act) {
+                uint32_t dist = (prev != kNone16) ? p - prev : 0;
+                if (dist >= (uint32_t)kWindow) dist = 0;
+                out[p] = (uint16_t)dist;
+            }
+        }
+    }
+}
+
+// =============================================================================
 // k_match: per-position longest-match search.  1 CTA (1024 threads) per unit.
 // The unit's bytes and its next4[] chain links are staged into shared memory
 // with two TMA bulk copies (cp.async.bulk + mbarrier); each thread then owns
@@ -1373,8 +1532,15 @@ cudaError_t launch_deflate_pipeline(const DeflateBatch &b, cudaStream_t st)
     }
     if (lp.mode >= 0) {
         if (b.timer) b.timer->start(KT_CHAIN, st);
-        k_chain<<<b.nunits * b.spu, kChainThreads, chain_smem, st>>>(g, b.next4, b.prev3);
-        DBG_SYNC("k_chain");
+        if (b.lists) {
+            k_split<<<b.nunits * b.spu, kSplitThreads, 0, st>>>(g, b.lists, b.list_start, b.next4, b.prev3);
+            DBG_SYNC("k_split");
+            k_link<<<b.nunits * b.spu * kSplitLists, 32, 0, st>>>(g, b.lists, b.list_start, b.next4, b.prev3);
+            DBG_SYNC("k_link");
+        } else {
+            k_chain<<<b.nunits * b.spu, kChainThreads, chain_smem, st>>>(g, b.next4, b.prev3);
+            DBG_SYNC("k_chain");
+        }
         if (b.timer) { b.timer->stop(st); b.timer->start(KT_MATCH, st); }
         k_match<<<b.nunits * b.spu, kMatchThreads, match_smem, st>>>(g, b.next4, b.prev3, b.mtab, b.mtab2, b.clen, b.order, lp.depth, lp.nice, lp.mode);
         DBG_SYNC("k_match");

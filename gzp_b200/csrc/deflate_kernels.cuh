@@ -41,6 +41,8 @@ struct DeflateBatch {
     const uint32_t *unit_flags;  // bit0 = is_last (BGZF EOF), bit1 = sync flush (no BFINAL)
     uint16_t *next4;          // nunits * spu * 65536
     uint16_t *prev3;          // nunits * spu * 65536
+    uint32_t *lists;          // nunits * spu * 2 * 65536 (k_split position lists), NULL = use k_chain
+    uint32_t *list_start;     // nunits * spu * 16
     uint64_t *mtab;           // nunits * m_stride
     uint32_t *mtab2;          // nunits * m_stride, lazy2 levels only (depth/4 column), else NULL
     uint8_t *clen;            // nunits * spu * 65536 (chain lengths, k_match scratch)

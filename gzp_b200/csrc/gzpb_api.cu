@@ -41,7 +41,7 @@ struct Lane {
     uint16_t *d_next4 = nullptr, *d_prev3 = nullptr, *d_order = nullptr;
     uint8_t *d_clen = nullptr;
     uint64_t *d_mtab = nullptr, *d_offsets = nullptr;
-    uint32_t *d_mtab2 = nullptr;
+    uint32_t *d_mtab2 = nullptr, *d_lists = nullptr, *d_list_start = nullptr;
     uint8_t *d_out = nullptr, *d_packed = nullptr;
     int32_t *d_status = nullptr, *d_overflow = nullptr;
     // pinned host
@@ -211,6 +211,10 @@ static int lane_alloc(gzpb_ctx *c, Lane &L, bool with_io)
     CK(dmalloc(&L.d_next4, U * c->spu * kMaxUnitBytes));
     CK(dmalloc(&L.d_prev3, U * c->spu * kMaxUnitBytes));
     CK(dmalloc(&L.d_order, U * c->spu * kMaxUnitBytes));
+    if (!getenv("GZPB_USE_KCHAIN")) {
+        CK(dmalloc(&L.d_lists, U * c->spu * 2 * kMaxUnitBytes));
+        CK(dmalloc(&L.d_list_start, U * c->spu * 16));
+    }
     CK(dmalloc(&L.d_clen, U * c->spu * kMaxUnitBytes));
     CK(dmalloc(&L.d_mtab, U * c->m_stride));
     if (c->level >= 8) CK(dmalloc(&L.d_mtab2, U * c->m_stride));
@@ -243,7 +247,7 @@ static int lane_alloc(gzpb_ctx *c, Lane &L, bool with_io)
 static void lane_free(Lane &L)
 {
     cudaFree(L.d_in); cudaFree(L.d_len); cudaFree(L.d_dict); cudaFree(L.d_flags); cudaFree(L.d_crc); cudaFree(L.d_tokens); cudaFree(L.d_out_len);
-    cudaFree(L.d_next4); cudaFree(L.d_prev3); cudaFree(L.d_order); cudaFree(L.d_clen); cudaFree(L.d_mtab2); cudaFree(L.d_mtab); cudaFree(L.d_offsets); cudaFree(L.d_out); cudaFree(L.d_packed);
+    cudaFree(L.d_next4); cudaFree(L.d_prev3); cudaFree(L.d_order); cudaFree(L.d_clen); cudaFree(L.d_mtab2); cudaFree(L.d_lists); cudaFree(L.d_list_start); cudaFree(L.d_mtab); cudaFree(L.d_offsets); cudaFree(L.d_out); cudaFree(L.d_packed);
     cudaFree(L.d_status); cudaFree(L.d_overflow);
     cudaFreeHost(L.h_in); cudaFreeHost(L.h_packed); cudaFreeHost(L.h_len); cudaFreeHost(L.h_dict); cudaFreeHost(L.h_flags); cudaFreeHost(L.h_crc);
     cudaFreeHost(L.h_offsets); cudaFreeHost(L.h_status); cudaFreeHost(L.h_overflow);
@@ -374,7 +378,7 @@ static void fill_batch(gzpb_ctx *c, Lane &L, DeflateBatch &b, size_t n)
     b.in = L.d_in; b.unit_len = L.d_len; b.unit_dict = L.d_dict; b.unit_flags = L.d_flags;
     b.in_stride = c->in_stride; b.m_stride = c->m_stride; b.tok_stride = c->tok_stride; b.out_stride = c->out_stride;
     b.spu = c->spu; b.seg = c->seg; b.check_kind = c->check_kind;
-    b.next4 = L.d_next4; b.prev3 = L.d_prev3; b.clen = L.d_clen; b.order = L.d_order; b.mtab = L.d_mtab; b.mtab2 = L.d_mtab2; b.crc = L.d_crc; b.tokens = L.d_tokens;
+    b.next4 = L.d_next4; b.prev3 = L.d_prev3; b.clen = L.d_clen; b.order = L.d_order; b.mtab = L.d_mtab; b.mtab2 = L.d_mtab2; b.lists = L.d_lists; b.list_start = L.d_list_start; b.crc = L.d_crc; b.tokens = L.d_tokens;
     b.out = L.d_out; b.out_len = L.d_out_len; b.status = L.d_status; b.offsets = L.d_offsets;
     b.packed = nullptr; b.packed_cap = 0; b.base_ptr = nullptr; b.overflow = L.d_overflow;
     b.timer = c->profiling ? &c->timer : nullptr;
