@@ -212,10 +212,10 @@ k_chain(const __grid_constant__ Geo g, uint16_t *__restrict__ next4, uint16_t *_
 // ballot-ordering logic per tile of 32 list entries; identical links.
 // =============================================================================
 constexpr int kSplitThreads = 1024;
-constexpr int kL4 = 8, kL3 = 4;          // lists: hash4 space in eighths, hash3 space in quarters
+constexpr int kL4 = 16, kL3 = 4;         // lists: hash4 space in 16ths, hash3 space in quarters
 constexpr int kSplitLists = kL4 + kL3;
-constexpr int kLinkBits = 13;            // buckets per link job (16 KiB table)
-constexpr int kLsStride = 16;            // list_start entries per sub-unit: [0..8] hash4 bounds, [9..13] hash3 bounds
+constexpr int kBits4 = 12, kBits3 = 13;  // buckets per link job: hash4 8 KiB table + 4 KiB counts, hash3 16 KiB table
+constexpr int kLsStride = 32;            // list_start entries per sub-unit: [0..kL4] hash4 bounds, [kL4+1..kL4+1+kL3] hash3 bounds
 
 __global__ void __launch_bounds__(kSplitThreads)
 k_split(const __grid_constant__ Geo g, uint32_t *__restrict__ lists, uint32_t *__restrict__ list_start,
@@ -242,7 +242,7 @@ k_split(const __grid_constant__ Geo g, uint32_t *__restrict__ lists, uint32_t *_
         const uint32_t v = act ? ldg32u(inw, p) : 0;
         uint32_t h4 = lz_hash(v, 16), h3 = lz_hash(v & 0xFFFFFFu, 15);
         if (p == 0 && sb.quirk) { h4 = 0; h3 = 0; }
-        const uint32_t q4 = h4 >> kLinkBits, q3 = h3 >> kLinkBits;
+        const uint32_t q4 = h4 >> kBits4, q3 = h3 >> kBits3;
         const uint32_t m4 = __match_any_sync(0xFFFFFFFFu, act ? q4 : 64u);
         const uint32_t m3 = __match_any_sync(0xFFFFFFFFu, act ? q3 : 64u);
         if (act && (m4 & lt) == 0) s_w[warp][q4] += __popc(m4);          // group leader
@@ -274,7 +274,7 @@ k_split(const __grid_constant__ Geo g, uint32_t *__restrict__ lists, uint32_t *_
         const uint32_t v = act ? ldg32u(inw, p) : 0;
         uint32_t h4 = lz_hash(v, 16), h3 = lz_hash(v & 0xFFFFFFu, 15);
         if (p == 0 && sb.quirk) { h4 = 0; h3 = 0; }
-        const uint32_t q4 = h4 >> kLinkBits, q3 = h3 >> kLinkBits;
+        const uint32_t q4 = h4 >> kBits4, q3 = h3 >> kBits3;
         const uint32_t m4 = __match_any_sync(0xFFFFFFFFu, act ? q4 : 64u);
         const uint32_t m3 = __match_any_sync(0xFFFFFFFFu, act ? q3 : 64u);
         uint32_t b4 = 0, b3 = 0;
@@ -297,9 +297,12 @@ k_split(const __grid_constant__ Geo g, uint32_t *__restrict__ lists, uint32_t *_
 
 __global__ void __launch_bounds__(32)
 k_link(const __grid_constant__ Geo g, const uint32_t *__restrict__ lists, const uint32_t *__restrict__ list_start,
-       uint16_t *__restrict__ next4, uint16_t *__restrict__ prev3)
+       uint16_t *__restrict__ next4, uint16_t *__restrict__ prev3, uint8_t *__restrict__ clen_g)
 {
-    __shared__ __align__(16) uint16_t head[1 << kLinkBits];
+    // hash4 job: u16 head[4096] + u8 cnt[4096] (occurrences so far per bucket = chain-length estimate);
+    // hash3 job: u16 head[8192]
+    __shared__ __align__(16) uint16_t head[1 << kBits3];
+    uint8_t *cnt = (uint8_t *)(head + (1 << kBits4));
     const uint32_t sub = blockIdx.x / kSplitLists, job = blockIdx.x % kSplitLists;
     const Sub sb = sub_geometry(g, sub);
     if (!sb.valid) return;
@@ -310,10 +313,12 @@ k_link(const __grid_constant__ Geo g, const uint32_t *__restrict__ lists, const 
     const uint32_t beg = is4 ? ls[job] : ls[kL4 + 1 + (job - kL4)];
     const uint32_t end = is4 ? ls[job + 1] : ls[kL4 + 2 + (job - kL4)];
     uint16_t *out = (is4 ? next4 : prev3) + (size_t)sub * kMaxUnitBytes;
+    uint8_t *clen = clen_g + (size_t)sub * kMaxUnitBytes;
     {
-        uint4 ones = make_uint4(~0u, ~0u, ~0u, ~0u);
-        uint4 *h = (uint4 *)head;
-        for (uint32_t i = lane; i < (2u << kLinkBits) / 16; i += 32) h[i] = ones;
+        uint4 ones = make_uint4(~0u, ~0u, ~0u, ~0u), zero = make_uint4(0, 0, 0, 0);
+        uint4 *h = (uint4 *)head, *c4 = (uint4 *)cnt;
+        for (uint32_t i = lane; i < (is4 ? (2u << kBits4) : (2u << kBits3)) / 16; i += 32) h[i] = ones;
+        if (is4) for (uint32_t i = lane; i < (1u << kBits4) / 16; i += 32) c4[i] = zero;
     }
     __syncwarp();
     constexpr int G = 8;
@@ -331,8 +336,9 @@ k_link(const __grid_constant__ Geo g, const uint32_t *__restrict__ lists, const 
             const uint32_t i = base0 + 32 * k + lane;
             if (base0 + 32 * k >= end) break;
             const bool act = i < end;
-            const uint32_t b = e[k] & ((1u << kLinkBits) - 1), p = e[k] >> 16;
+            const uint32_t b = e[k] & (is4 ? ((1u << kBits4) - 1) : ((1u << kBits3) - 1)), p = e[k] >> 16;
             uint32_t prev = act ? (uint32_t)head[b] : kNone16;
+            uint32_t occ = (act && is4) ? (uint32_t)cnt[b] : 0u, gsize = 1;
             if (act) head[b] = (uint16_t)p;
             __syncwarp();
             bool lost = act && head[b] != (uint16_t)p;
@@ -347,6 +353,8 @@ k_link(const __grid_constant__ Geo g, const uint32_t *__restrict__ lists, const 
                 if (member) {
                     if (lower) prev = pl;
                     if ((grp >> lane) == 1u) head[b] = (uint16_t)p;
+                    occ += __popc(lower);
+                    gsize = ((grp >> lane) == 1u) ? (uint32_t)__popc(grp) : 0u;   // only the last member updates the count
                 }
                 lostmask &= ~grp;
             }
@@ -355,7 +363,12 @@ k_link(const __grid_constant__ Geo g, const uint32_t *__restrict__ lists, const 
                 uint32_t dist = (prev != kNone16) ? p - prev : 0;
                 if (dist >= (uint32_t)kWindow) dist = 0;
                 out[p] = (uint16_t)dist;
+                if (is4) {
+                    clen[p] = (uint8_t)min(occ, 127u);
+                    if (gsize) cnt[b] = (uint8_t)min(occ + 1u, 255u);   // occ of the last member + 1 = occurrences so far
+                }
             }
+            __syncwarp();
         }
     }
 }
@@ -386,7 +399,7 @@ __device__ __forceinline__ uint32_t lz_extend(const uint32_t *s_in, uint32_t p, 
 __global__ void __launch_bounds__(kMatchThreads, 1)
 k_match(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, const uint16_t *__restrict__ prev3g,
         uint64_t *__restrict__ mtab, uint32_t *__restrict__ mtab2, uint8_t *__restrict__ clen_g, uint16_t *__restrict__ order_g,
-        int depth, int nice, int lazy)
+        int depth, int nice, int lazy, int have_est)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     uint32_t *s_in = (uint32_t *)smem;
@@ -434,13 +447,16 @@ k_match(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, cons
     for (uint32_t p = sb.nb + tid; p < sb.ne; p += kMatchThreads) {
         uint32_t len = 0;
         if (n - p >= 5) {
-            uint32_t q = p;
-            while (len < (uint32_t)depth) {
-                uint32_t d = s_next[q];
-                if (d == 0) break;
-                q -= d;
-                if (p - q >= (uint32_t)kWindow) break;
-                len++;
+            if (have_est) len = min((uint32_t)clen[p], (uint32_t)depth);   // occurrence index in the bucket (k_link)
+            else {
+                uint32_t q = p;
+                while (len < (uint32_t)depth) {
+                    uint32_t d = s_next[q];
+                    if (d == 0) break;
+                    q -= d;
+                    if (p - q >= (uint32_t)kWindow) break;
+                    len++;
+                }
             }
         }
         len = min(len, 127u);
@@ -1535,14 +1551,14 @@ cudaError_t launch_deflate_pipeline(const DeflateBatch &b, cudaStream_t st)
         if (b.lists) {
             k_split<<<b.nunits * b.spu, kSplitThreads, 0, st>>>(g, b.lists, b.list_start, b.next4, b.prev3);
             DBG_SYNC("k_split");
-            k_link<<<b.nunits * b.spu * kSplitLists, 32, 0, st>>>(g, b.lists, b.list_start, b.next4, b.prev3);
+            k_link<<<b.nunits * b.spu * kSplitLists, 32, 0, st>>>(g, b.lists, b.list_start, b.next4, b.prev3, b.clen);
             DBG_SYNC("k_link");
         } else {
             k_chain<<<b.nunits * b.spu, kChainThreads, chain_smem, st>>>(g, b.next4, b.prev3);
             DBG_SYNC("k_chain");
         }
         if (b.timer) { b.timer->stop(st); b.timer->start(KT_MATCH, st); }
-        k_match<<<b.nunits * b.spu, kMatchThreads, match_smem, st>>>(g, b.next4, b.prev3, b.mtab, b.mtab2, b.clen, b.order, lp.depth, lp.nice, lp.mode);
+        k_match<<<b.nunits * b.spu, kMatchThreads, match_smem, st>>>(g, b.next4, b.prev3, b.mtab, b.mtab2, b.clen, b.order, lp.depth, lp.nice, lp.mode, b.lists != nullptr);
         DBG_SYNC("k_match");
         if (b.timer) b.timer->stop(st);
     }

@@ -213,7 +213,7 @@ static int lane_alloc(gzpb_ctx *c, Lane &L, bool with_io)
     CK(dmalloc(&L.d_order, U * c->spu * kMaxUnitBytes));
     if (!getenv("GZPB_USE_KCHAIN")) {
         CK(dmalloc(&L.d_lists, U * c->spu * 2 * kMaxUnitBytes));
-        CK(dmalloc(&L.d_list_start, U * c->spu * 16));
+        CK(dmalloc(&L.d_list_start, U * c->spu * 32));
     }
     CK(dmalloc(&L.d_clen, U * c->spu * kMaxUnitBytes));
     CK(dmalloc(&L.d_mtab, U * c->m_stride));
