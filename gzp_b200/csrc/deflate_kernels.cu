@@ -1499,6 +1499,65 @@ k_check(const __grid_constant__ Geo g, uint32_t *__restrict__ sum_out, int kind)
     }
 }
 
+// =============================================================================
+// k_check_combine: Check::combine over a batch (src/check.rs:162, 121-128;
+// src/par/compress.rs:308).  (sum_a, len_a) o (sum_b, len_b) is associative:
+//   CRC-32 : (x^(8*len_b) * sum_a mod P) xor sum_b        (GF(2) polynomial arithmetic)
+//   Adler32: zlib's adler32_combine recurrence
+// so the batch folds with a block-wide tree reduction; the host folds ONE value per batch
+// into the stream's running check.
+// =============================================================================
+__device__ __forceinline__ uint32_t adler_combine_dev(uint32_t a1, uint32_t a2, uint64_t len2)
+{
+    const uint32_t BASE = 65521u;
+    uint32_t rem = (uint32_t)(len2 % BASE);
+    uint32_t sum1 = a1 & 0xFFFF;
+    uint32_t sum2 = (uint32_t)(((uint64_t)rem * sum1) % BASE);
+    sum1 += (a2 & 0xFFFF) + BASE - 1;
+    sum2 += (a1 >> 16) + (a2 >> 16) + BASE - rem;
+    if (sum1 >= BASE) sum1 -= BASE;
+    if (sum1 >= BASE) sum1 -= BASE;
+    if (sum2 >= (BASE << 1)) sum2 -= (BASE << 1);
+    if (sum2 >= BASE) sum2 -= BASE;
+    return sum1 | (sum2 << 16);
+}
+
+__global__ void __launch_bounds__(256)
+k_check_combine(const uint32_t *__restrict__ sums, const uint32_t *__restrict__ unit_len, const uint32_t *__restrict__ unit_dict,
+                uint32_t nunits, int kind, uint32_t *__restrict__ out /* [0] = sum, [1],[2] = length lo/hi */)
+{
+    __shared__ uint32_t s_sum[256];
+    __shared__ unsigned long long s_len[256];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t per = (nunits + 255) / 256;
+    uint32_t acc = (kind == 1) ? 1u : 0u;       // identity: crc32("") = 0, adler32("") = 1
+    unsigned long long alen = 0;
+    for (uint32_t i = tid * per; i < min(nunits, (tid + 1) * per); i++) {
+        const unsigned long long l = unit_len[i] - unit_dict[i];
+        if (l) acc = (kind == 1) ? adler_combine_dev(acc, sums[i], l) : (gf2_mulmod(acc, gf2_xpow8(l, kCrcPoly), kCrcPoly) ^ sums[i]);
+        alen += l;
+    }
+    s_sum[tid] = acc; s_len[tid] = alen;
+    __syncthreads();
+    for (uint32_t stride = 1; stride < 256; stride <<= 1) {
+        if ((tid & (2 * stride - 1)) == 0) {
+            const uint32_t b = s_sum[tid + stride];
+            const unsigned long long lb = s_len[tid + stride];
+            if (lb) s_sum[tid] = (kind == 1) ? adler_combine_dev(s_sum[tid], b, lb) : (gf2_mulmod(s_sum[tid], gf2_xpow8(lb, kCrcPoly), kCrcPoly) ^ b);
+            s_len[tid] += lb;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) { out[0] = s_sum[0]; out[1] = (uint32_t)s_len[0]; out[2] = (uint32_t)(s_len[0] >> 32); }
+}
+
+cudaError_t launch_check_combine(const uint32_t *sums, const uint32_t *unit_len, const uint32_t *unit_dict, uint32_t nunits, int kind,
+                                 uint32_t *out3, cudaStream_t st)
+{
+    k_check_combine<<<1, 256, 0, st>>>(sums, unit_len, unit_dict, nunits, kind, out3);
+    return cudaGetLastError();
+}
+
 void read_phase_counters(unsigned long long *out, bool reset)
 {
     cudaMemcpyFromSymbol(out, g_phase, sizeof(unsigned long long) * 32);

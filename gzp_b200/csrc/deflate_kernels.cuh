@@ -67,5 +67,7 @@ void upload_deflate_constants();
 void read_phase_counters(unsigned long long *out, bool reset);
 cudaError_t launch_deflate_pipeline(const DeflateBatch &b, cudaStream_t st);
 cudaError_t launch_pack(const DeflateBatch &b, cudaStream_t st);
+cudaError_t launch_check_combine(const uint32_t *sums, const uint32_t *unit_len, const uint32_t *unit_dict, uint32_t nunits, int kind,
+                                 uint32_t *out3, cudaStream_t st);
 
 }  // namespace gzpb

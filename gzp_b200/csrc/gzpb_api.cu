@@ -44,6 +44,7 @@ struct Lane {
     uint32_t *d_mtab2 = nullptr, *d_lists = nullptr, *d_list_start = nullptr;
     uint8_t *d_out = nullptr, *d_packed = nullptr;
     int32_t *d_status = nullptr, *d_overflow = nullptr;
+    uint32_t *d_comb = nullptr, *h_comb = nullptr;   // batch-combined check {sum, len lo, len hi}
     // pinned host
     uint8_t *h_in = nullptr, *h_packed = nullptr;
     uint32_t *h_len = nullptr, *h_dict = nullptr, *h_flags = nullptr, *h_crc = nullptr;
@@ -226,6 +227,8 @@ static int lane_alloc(gzpb_ctx *c, Lane &L, bool with_io)
     CK(cudaMemset(L.d_overflow, 0, sizeof(int32_t)));
     CK(dmalloc(&L.d_dict, U));
     CK(cudaMemset(L.d_dict, 0, U * sizeof(uint32_t)));
+    CK(dmalloc(&L.d_comb, 4));
+    CK(hmalloc(&L.h_comb, 4));
     if (with_io) {
         CK(dmalloc(&L.d_in, U * c->in_stride + 256));
         CK(dmalloc(&L.d_len, U));
@@ -248,7 +251,7 @@ static void lane_free(Lane &L)
 {
     cudaFree(L.d_in); cudaFree(L.d_len); cudaFree(L.d_dict); cudaFree(L.d_flags); cudaFree(L.d_crc); cudaFree(L.d_tokens); cudaFree(L.d_out_len);
     cudaFree(L.d_next4); cudaFree(L.d_prev3); cudaFree(L.d_order); cudaFree(L.d_clen); cudaFree(L.d_mtab2); cudaFree(L.d_lists); cudaFree(L.d_list_start); cudaFree(L.d_mtab); cudaFree(L.d_offsets); cudaFree(L.d_out); cudaFree(L.d_packed);
-    cudaFree(L.d_status); cudaFree(L.d_overflow);
+    cudaFree(L.d_status); cudaFree(L.d_overflow); cudaFree(L.d_comb); cudaFreeHost(L.h_comb);
     cudaFreeHost(L.h_in); cudaFreeHost(L.h_packed); cudaFreeHost(L.h_len); cudaFreeHost(L.h_dict); cudaFreeHost(L.h_flags); cudaFreeHost(L.h_crc);
     cudaFreeHost(L.h_offsets); cudaFreeHost(L.h_status); cudaFreeHost(L.h_overflow);
     if (L.ev_scan) cudaEventDestroy(L.ev_scan);
@@ -409,7 +412,7 @@ extern "C" int gzpb_encode_device(gzpb_ctx *c, const void *d_in, const uint32_t 
         b.packed = (uint8_t *)d_packed; b.packed_cap = ~0ull;
         CK(launch_deflate_pipeline(b, st));
         CK(launch_pack(b, st));
-        c->launches += 5;
+        c->launches += 7;   // k_check, k_split, k_link, k_match, k_emit, k_scan, k_gather
     }
     return GZPB_OK;
 }
@@ -472,7 +475,7 @@ static int lane_launch(gzpb_ctx *c, Lane &L, const UnitRef *units, size_t n, boo
     DeflateBatch b;
     fill_batch(c, L, b, n);
     CK(launch_deflate_pipeline(b, L.st));
-    c->launches += 4;
+    c->launches += 5;   // k_check, k_split, k_link, k_match, k_emit
     L.nunits = n; L.busy = true;
     return GZPB_OK;
 }
@@ -493,6 +496,12 @@ static int lane_pack(gzpb_ctx *c, Lane &L, uint8_t *packed, uint64_t cap, const 
     if (c->format != GZPB_SNAP) {
         CK(cudaMemcpyAsync(L.h_status, L.d_status, L.nunits * sizeof(int32_t), cudaMemcpyDeviceToHost, L.st));
         CK(cudaMemcpyAsync(L.h_crc, L.d_crc, L.nunits * sizeof(uint32_t), cudaMemcpyDeviceToHost, L.st));
+        if (c->format == GZPB_GZIP || c->format == GZPB_ZLIB) {
+            // Check::combine over the batch on the device: the host folds one value per batch
+            CK(launch_check_combine(L.d_crc, L.d_len, L.d_dict, (uint32_t)L.nunits, c->check_kind, L.d_comb, L.st));
+            CK(cudaMemcpyAsync(L.h_comb, L.d_comb, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, L.st));
+            c->launches += 1;
+        }
     }
     CK(cudaMemcpyAsync(L.h_overflow, L.d_overflow, sizeof(int32_t), cudaMemcpyDeviceToHost, L.st));
     CK(cudaEventRecord(L.ev_done, L.st));
@@ -611,16 +620,14 @@ extern "C" int gzpb_encode_stream(gzpb_ctx *c, const void *in_v, size_t in_len, 
         int r = lane_wait(c, L);
         if (r != GZPB_OK) return r;
         if (*L.h_overflow) return GZPB_ECOMPRESS;
-        for (size_t i = 0; i < p.count; i++) {
+        for (size_t i = 0; i < p.count; i++)
             if (L.h_status[i] != GZPB_OK) return L.h_status[i];
-            if (c->format == GZPB_GZIP || c->format == GZPB_ZLIB) {
-                // (dictionary bytes are not part of the block's check)
-                size_t b0 = (p.first + i) * buffer_size;
-                size_t real = std::min(buffer_size, in_len - std::min(in_len, b0));
-                run_sum = c->format == GZPB_GZIP ? gzpb_crc32_combine(run_sum, L.h_crc[i], real)
-                                                 : gzpb_adler32_combine(run_sum, L.h_crc[i], real);
-                run_amount += (uint32_t)real;
-            }
+        if (c->format == GZPB_GZIP || c->format == GZPB_ZLIB) {
+            // k_check_combine folded the batch; fold the batch into the running check (par/compress.rs:308)
+            const uint64_t blen = (uint64_t)L.h_comb[1] | ((uint64_t)L.h_comb[2] << 32);
+            if (blen) run_sum = c->format == GZPB_GZIP ? gzpb_crc32_combine(run_sum, L.h_comb[0], blen)
+                                                       : gzpb_adler32_combine(run_sum, L.h_comb[0], blen);
+            run_amount += (uint32_t)blen;
         }
         if (out_pinned) {
             pos_out = (size_t)L.h_offsets[p.count * c->cpu];

@@ -181,3 +181,21 @@ def test_lazy2_levels(text_corpus, level):
     assert got == oracle.compress_stream(oracle.GZIP, level, 262144, [data])
     assert gzip.decompress(got) == data
     ctx.close()
+
+
+def test_bgzf_block_size_exceeded_error():
+    # bgzf.rs:218-223: a compressed payload >= 65536 bytes is an error, not a silent fallback.
+    # ParCompressBuilder does not bound buffer_size for Bgzf, so 131072 random bytes hit it.
+    rnd = random.Random(5)
+    data = bytes(rnd.randrange(256) for _ in range(131072))
+    with pytest.raises(ValueError) as eo:
+        oracle.encode_block(oracle.BGZF, 6, data)
+    assert eo.value.args[0] == -3
+    ctx = gzp_b200.Context(BGZF, 6, max_block_bytes=131072, max_blocks_in_flight=2)
+    with pytest.raises(gzp_b200.GzpError) as e:
+        ctx.encode_blocks([(data, None, False)])
+    assert e.value.variant == "BlockSizeExceeded" and e.value.code == -3
+    # the context stays usable after a per-block error
+    ok = ctx.encode_blocks([(b"hello " * 1000, None, True)])[0][0]
+    assert ok == oracle.encode_block(oracle.BGZF, 6, b"hello " * 1000, None, True)
+    ctx.close()
