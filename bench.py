@@ -40,9 +40,9 @@ GIB = float(1 << 30)
 # k_match algorithmic HBM bytes per input byte: input 1 + next4 2 + prev3 2 read, match table 8 written
 MATCH_BYTES_PER_INPUT_BYTE = 13.0
 # DRAM traffic of k_match per input byte from the round-1 ncu --set full capture (profiles/r1_final_ncu_full_summary.txt:
-# dram__bytes_read+write = 4.674 GB over 2368 units of 65 280 B); above the algorithmic figure because the
+# dram__bytes_read+write = 4.815 GB over 2368 units of 65 280 B); above the algorithmic figure because the
 # chain-length sort scatters the 8-byte match-table stores (partial-sector writes) and adds 3 B/position of scratch
-MATCH_TRAFFIC_PER_INPUT_BYTE = 4.674e9 / (2368 * 65280)
+MATCH_TRAFFIC_PER_INPUT_BYTE = 4.815e9 / (2368 * 65280)
 
 
 def parse_args():
@@ -320,7 +320,7 @@ def main():
             "roofline": {"bound": "hbm", "kernel": "k_match", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": MATCH_TRAFFIC_PER_INPUT_BYTE * BLOCK * min(nblk, 2048) / 1e9, "traffic_unit": "GB per launch (ncu dram__bytes_read+write, profiles/r1_final_ncu_full_summary.txt)",
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650 GB/s",
-                         "note": "k_match is instruction-issue bound (ncu: 68 % issue-active, 6 % of DRAM peak; profiles/), not HBM bound; algorithmic bytes = 13 B per input byte",
+                         "note": "k_match is instruction-issue bound (ncu: 64 % issue-active, 7.5 % of DRAM peak; profiles/), not HBM bound; algorithmic bytes = 13 B per input byte",
                          "kernel_ms_per_launch": {k: v[0] / max(v[1], 1) for k, v in kms.items()}, "kernel_time_share": share},
             "cpu_baseline": cpu,
         }
