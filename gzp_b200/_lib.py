@@ -40,10 +40,16 @@ _SIGS = {
     "gzpb_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "gzpb_kernel_ms": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "gzpb_launch_count": (C.c_uint64, [C.c_void_p]),
+    "gzpb_writer_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "gzpb_writer_write": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "gzpb_writer_flush": (C.c_int, [C.c_void_p]),
+    "gzpb_writer_finish": (C.c_int, [C.c_void_p]),
+    "gzpb_writer_destroy": (None, [C.c_void_p]),
     "gzpb_strerror": (C.c_char_p, [C.c_int]),
     "gzpb_version": (C.c_char_p, []),
 }
 
+SINK_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t)
 EXPORTS = tuple(_SIGS)
 _lib = None
 

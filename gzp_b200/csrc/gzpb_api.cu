@@ -680,3 +680,164 @@ extern "C" int gzpb_encode_stream(gzpb_ctx *c, const void *in_v, size_t in_len, 
     *out_len = pos_out;
     return GZPB_OK;
 }
+
+
+// ---- incremental writer: ParCompress<F, W> as a C object ---------------------------------
+struct gzpb_writer {
+    gzpb_ctx *ctx = nullptr;
+    int format = 0, level = 0;
+    size_t buffer_size = 0, max_pending = 0;
+    gzpb_sink_fn sink = nullptr;
+    void *user = nullptr;
+    std::vector<uint8_t> buf;                                    // bytes not yet cut into blocks
+    struct Msg { std::vector<uint8_t> data, dict; bool is_last; };
+    std::vector<Msg> pending;                                    // FIFO of messages = ticket order
+    std::vector<uint8_t> dict;                                   // dictionary for the next block
+    bool have_dict = false, wrote_header = false, finished = false;
+    uint32_t sum = 0, amount = 0;
+    int error = GZPB_OK;
+};
+
+static int writer_emit(gzpb_writer *w, const void *p, size_t n)
+{
+    if (n == 0) return GZPB_OK;
+    if (w->sink(w->user, p, n) != 0) { w->error = GZPB_EIO; return GZPB_EIO; }
+    return GZPB_OK;
+}
+
+static int writer_drain(gzpb_writer *w)
+{
+    if (w->error) return w->error;
+    if (!w->wrote_header) {
+        uint8_t hb[16];
+        size_t hl = gzpb_header(w->format, w->level, hb);
+        w->wrote_header = true;
+        int r = writer_emit(w, hb, hl);
+        if (r) return r;
+    }
+    const size_t n = w->pending.size();
+    if (n == 0) return GZPB_OK;
+    std::vector<gzpb_block_in> in(n);
+    std::vector<gzpb_block_out> out(n);
+    std::vector<std::vector<uint8_t>> bufs(n);
+    for (size_t i = 0; i < n; i++) {
+        auto &m = w->pending[i];
+        in[i] = gzpb_block_in{m.data.data(), m.data.size(), m.dict.empty() ? nullptr : m.dict.data(), m.dict.size(), m.is_last ? 1 : 0};
+        bufs[i].resize(gzpb_encode_capacity(w->format, m.data.size()) + 64);
+        out[i] = gzpb_block_out{bufs[i].data(), bufs[i].size(), 0, 0, 0, 0};
+    }
+    int rc = gzpb_encode_batch(w->ctx, n, in.data(), out.data());
+    if (rc != GZPB_OK) { w->error = rc; return rc; }
+    for (size_t i = 0; i < n; i++) {
+        if (out[i].status != GZPB_OK) { w->error = out[i].status; return w->error; }   // a failed block fails the stream
+        const size_t len = w->pending[i].data.size();
+        if (w->format == GZPB_GZIP) w->sum = gzpb_crc32_combine(w->sum, out[i].check_sum, len);
+        else if (w->format == GZPB_ZLIB) w->sum = gzpb_adler32_combine(w->sum, out[i].check_sum, len);
+        if (w->format == GZPB_GZIP || w->format == GZPB_ZLIB) w->amount += (uint32_t)len;
+        int r = writer_emit(w, bufs[i].data(), out[i].out_len);
+        if (r) return r;
+    }
+    w->pending.clear();
+    return GZPB_OK;
+}
+
+static int writer_send(gzpb_writer *w, const uint8_t *p, size_t n, bool is_last)
+{
+    gzpb_writer::Msg m;
+    m.data.assign(p, p + n);
+    if (w->have_dict) m.dict = w->dict;
+    m.is_last = is_last;
+    w->have_dict = false;
+    w->pending.push_back(std::move(m));
+    if (w->pending.size() >= w->max_pending) return writer_drain(w);
+    return GZPB_OK;
+}
+
+extern "C" int gzpb_writer_create(gzpb_writer **out, int device, int format, int level, size_t buffer_size,
+                                  size_t blocks_in_flight, gzpb_sink_fn sink, void *user)
+{
+    if (!out || !sink) return GZPB_EINVAL;
+    *out = nullptr;
+    if (buffer_size == 0) buffer_size = gzpb_default_bufsize(format);
+    if (buffer_size < GZPB_DICT_SIZE) return GZPB_EBUFFERSIZE;   // par/compress.rs:68-74
+    if (blocks_in_flight == 0) blocks_in_flight = 256;
+    gzpb_writer *w = new gzpb_writer();
+    int rc = gzpb_create(&w->ctx, device, format, level, buffer_size, blocks_in_flight);
+    if (rc != GZPB_OK) { delete w; return rc; }
+    w->format = format; w->level = level; w->buffer_size = buffer_size; w->max_pending = blocks_in_flight;
+    w->sink = sink; w->user = user;
+    w->sum = (format == GZPB_ZLIB) ? 1u : 0u;
+    *out = w;
+    return GZPB_OK;
+}
+
+extern "C" int gzpb_writer_write(gzpb_writer *w, const void *data, size_t len)
+{
+    if (!w || (len && !data)) return GZPB_EINVAL;
+    if (w->finished) return GZPB_ECHANNEL;
+    if (w->error) return w->error;
+    const uint8_t *p = (const uint8_t *)data;
+    w->buf.insert(w->buf.end(), p, p + len);
+    size_t off = 0;
+    while (w->buf.size() - off > w->buffer_size) {                // strict '>' (par/compress.rs:415)
+        int rc = writer_send(w, w->buf.data() + off, w->buffer_size, false);
+        if (gzpb_needs_dict(w->format)) {
+            w->dict.assign(w->buf.data() + off + w->buffer_size - GZPB_DICT_SIZE, w->buf.data() + off + w->buffer_size);
+            w->have_dict = true;
+        }
+        off += w->buffer_size;
+        if (rc != GZPB_OK) { w->buf.erase(w->buf.begin(), w->buf.begin() + off); return rc; }
+    }
+    if (off) w->buf.erase(w->buf.begin(), w->buf.begin() + off);
+    return GZPB_OK;
+}
+
+static int writer_flush_last(gzpb_writer *w, bool is_last)
+{
+    size_t off = 0;
+    for (;;) {                                                     // par/compress.rs:332-362
+        const size_t k = std::min(w->buf.size() - off, w->buffer_size);
+        const bool last = is_last && (off + k == w->buf.size());
+        int rc = writer_send(w, w->buf.data() + off, k, last);
+        if (k >= GZPB_DICT_SIZE && !last && gzpb_needs_dict(w->format)) {
+            w->dict.assign(w->buf.data() + off + k - GZPB_DICT_SIZE, w->buf.data() + off + k);
+            w->have_dict = true;
+        }
+        off += k;
+        if (rc != GZPB_OK) { w->buf.erase(w->buf.begin(), w->buf.begin() + off); return rc; }
+        if (off == w->buf.size()) break;
+    }
+    w->buf.clear();
+    return GZPB_OK;
+}
+
+extern "C" int gzpb_writer_flush(gzpb_writer *w)
+{
+    if (!w) return GZPB_EINVAL;
+    if (w->finished) return GZPB_ECHANNEL;
+    int rc = writer_flush_last(w, false);
+    if (rc != GZPB_OK) return rc;
+    return writer_drain(w);
+}
+
+extern "C" int gzpb_writer_finish(gzpb_writer *w)
+{
+    if (!w) return GZPB_EINVAL;
+    if (w->finished) return GZPB_ECHANNEL;
+    int rc = writer_flush_last(w, true);
+    if (rc == GZPB_OK) rc = writer_drain(w);
+    if (rc == GZPB_OK) {
+        uint8_t fb[16];
+        size_t fl = gzpb_footer(w->format, w->sum, w->amount, fb);
+        rc = writer_emit(w, fb, fl);
+    }
+    w->finished = true;
+    return rc;
+}
+
+extern "C" void gzpb_writer_destroy(gzpb_writer *w)
+{
+    if (!w) return;
+    if (w->ctx) gzpb_destroy(w->ctx);
+    delete w;
+}

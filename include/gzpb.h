@@ -98,6 +98,21 @@ int gzpb_encode_batch(gzpb_ctx *ctx, size_t n, const gzpb_block_in *in, gzpb_blo
 int gzpb_encode_stream(gzpb_ctx *ctx, const void *in, size_t in_len, size_t buffer_size, void *out,
                        size_t out_cap, size_t *out_len);
 
+/* Incremental writer = `ParCompress<F, W>` as a C object (src/par/compress.rs:221-233): the caller
+ * `write`s bytes, the writer cuts blocks with the reference's semantics (strict '>' hold-back :415,
+ * 32 KiB dictionary carry :419-423, `flush` = flush_last(false) :466-468 incl. the empty block,
+ * `finish` = flush_last(true) + footer :377-388) and hands the encoded blocks to `sink` in stream
+ * order (the ordered writer loop :303-313).  `sink` plays `W: Write`: nonzero return = io error
+ * (GZPB_EIO is then returned by the next call, like the reference surfaces a BrokenPipe). */
+typedef int (*gzpb_sink_fn)(void *user, const void *data, size_t len);
+typedef struct gzpb_writer gzpb_writer;
+int gzpb_writer_create(gzpb_writer **w, int device, int format, int level, size_t buffer_size,
+                       size_t blocks_in_flight, gzpb_sink_fn sink, void *user);
+int gzpb_writer_write(gzpb_writer *w, const void *buf, size_t len);
+int gzpb_writer_flush(gzpb_writer *w);
+int gzpb_writer_finish(gzpb_writer *w);
+void gzpb_writer_destroy(gzpb_writer *w);
+
 /* Device-resident form of the same path, asynchronous on `cuda_stream`:
  * d_in holds nunits slots of GZPB_IN_STRIDE bytes, d_len/d_flags one u32 per unit
  * (flags bit0 = is_last, bit1 = sync flush); on completion d_packed holds the

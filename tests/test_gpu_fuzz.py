@@ -76,3 +76,35 @@ def test_parcompress_mirror_on_gpu_random_writes(text_corpus):
                 pc.flush()
         pc.finish()
         assert sink.getvalue() == oracle.compress_stream(fmt, 6, bs, writes, flushes)
+
+
+def test_c_writer_matches_oracle_random_writes(text_corpus):
+    """gzpb_writer_* (the C++ ParCompress) driven with random write sizes and flushes."""
+    import ctypes as C
+    from gzp_b200 import _lib
+    L = _lib.load()
+    rnd = random.Random(123)
+    for fmt, bs in ((BGZF, 65280), (GZIP, 40000), (MGZIP, 131072), (SNAP, 70000), (ZLIB, 32768)):
+        data = _gen(rnd, 500000, text_corpus)[:500000]
+        chunks = bytearray()
+
+        @_lib.SINK_FN
+        def sink(user, ptr, n):
+            chunks.extend(C.string_at(ptr, n))
+            return 0
+
+        h = C.c_void_p()
+        assert L.gzpb_writer_create(C.byref(h), 0, fmt, 6, bs, 3, C.cast(sink, C.c_void_p), None) == 0
+        writes, pos = [], 0
+        while pos < len(data):
+            k = rnd.randrange(1, 10000) if rnd.random() < 0.7 else rnd.randrange(1, 4 * bs)
+            writes.append(data[pos:pos + k]); pos += k
+        flushes = {2, 7}
+        for i, wdata in enumerate(writes):
+            assert L.gzpb_writer_write(h, wdata, len(wdata)) == 0
+            if i in flushes:
+                assert L.gzpb_writer_flush(h) == 0
+        assert L.gzpb_writer_finish(h) == 0
+        assert L.gzpb_writer_write(h, b"x", 1) == -7          # write after finish: ChannelSend
+        L.gzpb_writer_destroy(h)
+        assert bytes(chunks) == oracle.compress_stream(fmt, 6, bs, writes, flushes), f"fmt {fmt}"
