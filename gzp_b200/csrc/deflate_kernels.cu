@@ -143,6 +143,7 @@ __device__ __forceinline__ void chain_warp(const uint32_t *__restrict__ inw, uin
             // hashes inside the tile (the common case) and `old` is the predecessor.
             // Otherwise order each group of duplicates with ballots.
             uint32_t old = act ? (uint32_t)head[h] : kNone16;
+            __syncwarp();   // every lane has read its bucket before any lane overwrites one
             if (act) head[h] = (uint16_t)p;
             __syncwarp();
             bool lost = act && head[h] != (uint16_t)p;
@@ -172,7 +173,7 @@ __device__ __forceinline__ void chain_warp(const uint32_t *__restrict__ inw, uin
 __global__ void __launch_bounds__(kChainThreads, 1)
 k_chain(const __grid_constant__ Geo g, uint16_t *__restrict__ next4, uint16_t *__restrict__ prev3)
 {
-    extern __shared__ __align__(128) uint8_t smem[];
+    GZPB_DYN_SMEM(smem);
     uint16_t *head4 = (uint16_t *)smem;
     uint16_t *head3 = head4 + 65536;
     const Sub sb = sub_geometry(g, blockIdx.x);
@@ -185,7 +186,7 @@ k_chain(const __grid_constant__ Geo g, uint16_t *__restrict__ next4, uint16_t *_
     const long long t_start = clock64();
     // pull the sub-unit into L2 ahead of the dependent loads
     for (uint32_t off = tid * 128; off < n; off += kChainThreads * 128)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(in + off));
+        prefetch_l2(in + off);
     {
         uint4 ones = make_uint4(~0u, ~0u, ~0u, ~0u);
         uint4 *h = (uint4 *)smem;
@@ -339,6 +340,7 @@ k_link(const __grid_constant__ Geo g, const uint32_t *__restrict__ lists, const 
             const uint32_t b = e[k] & (is4 ? ((1u << kBits4) - 1) : ((1u << kBits3) - 1)), p = e[k] >> 16;
             uint32_t prev = act ? (uint32_t)head[b] : kNone16;
             uint32_t occ = (act && is4) ? (uint32_t)cnt[b] : 0u, gsize = 1;
+            __syncwarp();   // every lane has read its bucket before any lane overwrites one
             if (act) head[b] = (uint16_t)p;
             __syncwarp();
             bool lost = act && head[b] != (uint16_t)p;
@@ -401,7 +403,7 @@ k_match(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, cons
         uint64_t *__restrict__ mtab, uint32_t *__restrict__ mtab2, uint8_t *__restrict__ clen_g, uint16_t *__restrict__ order_g,
         int depth, int nice, int lazy, int have_est)
 {
-    extern __shared__ __align__(128) uint8_t smem[];
+    GZPB_DYN_SMEM(smem);
     uint32_t *s_in = (uint32_t *)smem;
     uint16_t *s_next = (uint16_t *)(smem + kInStride);
     __shared__ __align__(8) uint64_t bar;
@@ -417,7 +419,7 @@ k_match(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, cons
 
     if (tid == 0) {
         mbar_init(&bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_mbar_init();
     }
     __syncthreads();
     if (n >= 5) {
@@ -819,7 +821,7 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
 
     if (tid == 0) {
         for (int i = 0; i < kRing; i++) mbar_init(&S.bar[i], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_mbar_init();
         S.G = 0; S.carry = 0; S.status = 0;
     }
     __syncthreads();
@@ -1554,7 +1556,7 @@ k_check_combine(const uint32_t *__restrict__ sums, const uint32_t *__restrict__ 
 cudaError_t launch_check_combine(const uint32_t *sums, const uint32_t *unit_len, const uint32_t *unit_dict, uint32_t nunits, int kind,
                                  uint32_t *out3, cudaStream_t st)
 {
-    k_check_combine<<<1, 256, 0, st>>>(sums, unit_len, unit_dict, nunits, kind, out3);
+    GZPB_LAUNCH(k_check_combine, 1, 256, 0, st, sums, unit_len, unit_dict, nunits, kind, out3);
     return cudaGetLastError();
 }
 
@@ -1602,27 +1604,27 @@ cudaError_t launch_deflate_pipeline(const DeflateBatch &b, cudaStream_t st)
     const Geo g = make_geo(b);
     if (b.check_kind >= 0) {
         if (b.timer) b.timer->start(KT_CRC, st);
-        k_check<<<b.nunits, 256, 0, st>>>(g, b.crc, b.check_kind);
+        GZPB_LAUNCH(k_check, b.nunits, 256, 0, st, g, b.crc, b.check_kind);
         if (b.timer) b.timer->stop(st);
     }
     if (lp.mode >= 0) {
         if (b.timer) b.timer->start(KT_CHAIN, st);
         if (b.lists) {
-            k_split<<<b.nunits * b.spu, kSplitThreads, 0, st>>>(g, b.lists, b.list_start, b.next4, b.prev3);
+            GZPB_LAUNCH(k_split, b.nunits * b.spu, kSplitThreads, 0, st, g, b.lists, b.list_start, b.next4, b.prev3);
             DBG_SYNC("k_split");
-            k_link<<<b.nunits * b.spu * kSplitLists, 32, 0, st>>>(g, b.lists, b.list_start, b.next4, b.prev3, b.clen);
+            GZPB_LAUNCH(k_link, b.nunits * b.spu * kSplitLists, 32, 0, st, g, b.lists, b.list_start, b.next4, b.prev3, b.clen);
             DBG_SYNC("k_link");
         } else {
-            k_chain<<<b.nunits * b.spu, kChainThreads, chain_smem, st>>>(g, b.next4, b.prev3);
+            GZPB_LAUNCH(k_chain, b.nunits * b.spu, kChainThreads, chain_smem, st, g, b.next4, b.prev3);
             DBG_SYNC("k_chain");
         }
         if (b.timer) { b.timer->stop(st); b.timer->start(KT_MATCH, st); }
-        k_match<<<b.nunits * b.spu, kMatchThreads, match_smem, st>>>(g, b.next4, b.prev3, b.mtab, b.mtab2, b.clen, b.order, lp.depth, lp.nice, lp.mode, b.lists != nullptr);
+        GZPB_LAUNCH(k_match, b.nunits * b.spu, kMatchThreads, match_smem, st, g, b.next4, b.prev3, b.mtab, b.mtab2, b.clen, b.order, lp.depth, lp.nice, lp.mode, b.lists != nullptr);
         DBG_SYNC("k_match");
         if (b.timer) b.timer->stop(st);
     }
     if (b.timer) b.timer->start(KT_EMIT, st);
-    k_emit<<<b.nunits, kEmitThreads, 0, st>>>(g, b.unit_flags, b.mtab, b.mtab2, b.crc, b.tokens, b.out, b.out_len,
+    GZPB_LAUNCH(k_emit, b.nunits, kEmitThreads, 0, st, g, b.unit_flags, b.mtab, b.mtab2, b.crc, b.tokens, b.out, b.out_len,
                                              b.status, lp.mode, lp.depth, lp.nice, b.level, b.format);
     DBG_SYNC("k_emit");
     if (b.timer) b.timer->stop(st);
@@ -1635,8 +1637,8 @@ cudaError_t launch_pack(const DeflateBatch &b, cudaStream_t st)
 {
     if (b.nunits == 0) return cudaSuccess;
     if (b.timer) b.timer->start(KT_GATHER, st);
-    k_scan<<<1, 1024, 0, st>>>(b.out_len, b.offsets, b.nunits, b.base_ptr, b.packed_cap, b.overflow);
-    k_gather<<<b.nunits, 256, 0, st>>>(b.out, b.out_len, b.offsets, b.packed, b.overflow, b.out_stride);
+    GZPB_LAUNCH(k_scan, 1, 1024, 0, st, b.out_len, b.offsets, b.nunits, b.base_ptr, b.packed_cap, b.overflow);
+    GZPB_LAUNCH(k_gather, b.nunits, 256, 0, st, b.out, b.out_len, b.offsets, b.packed, b.overflow, b.out_stride);
     DBG_SYNC("k_scan+k_gather");
     if (b.timer) b.timer->stop(st);
     return cudaGetLastError();

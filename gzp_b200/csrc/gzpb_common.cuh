@@ -80,11 +80,25 @@ __device__ __forceinline__ uint32_t ld32u(const uint32_t *words, uint32_t byte_p
     return __funnelshift_r(lo, hi, s);
 }
 
+// Kernel launch and dynamic shared memory go through two macros so that the same
+// sources also build against tests/emu (a CPU SIMT emulator used only by the tests).
+#ifndef GZPB_EMU
+#define GZPB_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define GZPB_DYN_SMEM(name) extern __shared__ __align__(128) uint8_t name[]
+#else
+#define GZPB_LAUNCH(kernel, grid, block, smem, stream, ...) gzpb_emu::launch(dim3(grid), dim3(block), (smem), [&]() { kernel(__VA_ARGS__); })
+#define GZPB_DYN_SMEM(name) uint8_t *name = gzpb_emu::dyn_smem()
+#endif
+
 __device__ __forceinline__ uint32_t lanemask_lt()
 {
+#ifndef GZPB_EMU
     uint32_t m;
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
     return m;
+#else
+    return (1u << (threadIdx.x & 31)) - 1u;
+#endif
 }
 
 // ---- CRC-32 (reflected 0xEDB88320) GF(2) helpers ---------------------------
@@ -116,6 +130,7 @@ __host__ __device__ inline uint32_t gf2_xpow8(uint64_t nbytes, uint32_t poly)
     return r;
 }
 
+#ifndef GZPB_EMU
 // ---- TMA 1-D bulk copy (cp.async.bulk) + mbarrier ---------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -162,5 +177,35 @@ __device__ __forceinline__ void fence_proxy_async()
 {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
+__device__ __forceinline__ void fence_mbar_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void *p)
+{
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+#else
+// ---- tests/emu: the mbarrier is a small state machine, the bulk copy a memcpy ----------
+struct EmuMbar { int32_t tx; uint16_t pending; uint16_t count_phase; };   // overlays the 64-bit barrier word
+static_assert(sizeof(EmuMbar) == 8, "EmuMbar must overlay a uint64_t");
+inline void emu_mbar_check(EmuMbar *b)
+{
+    if (b->pending == 0 && b->tx == 0) { b->count_phase ^= 0x8000u; b->pending = b->count_phase & 0x7FFFu; gzpb_emu::note_progress(); }
+}
+inline void mbar_init(uint64_t *bar, uint32_t count) { EmuMbar *b = (EmuMbar *)bar; b->tx = 0; b->pending = (uint16_t)count; b->count_phase = (uint16_t)count; }
+inline void mbar_expect_tx(uint64_t *bar, uint32_t bytes) { EmuMbar *b = (EmuMbar *)bar; b->tx += (int32_t)bytes; b->pending--; emu_mbar_check(b); }
+inline bool mbar_try_wait(uint64_t *bar, uint32_t phase) { EmuMbar *b = (EmuMbar *)bar; return (uint32_t)(b->count_phase >> 15) != (phase & 1u); }
+inline void mbar_wait(uint64_t *bar, uint32_t phase) { while (!mbar_try_wait(bar, phase)) gzpb_emu::wait_yield(); }
+inline void tma_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar)
+{
+    if (((uintptr_t)smem_dst & 15) || ((uintptr_t)gsrc & 15) || (bytes & 15)) gzpb_emu::trap("cp.async.bulk: dst/src/size must be 16-byte aligned");
+    memcpy(smem_dst, gsrc, bytes);
+    EmuMbar *b = (EmuMbar *)bar; b->tx -= (int32_t)bytes; emu_mbar_check(b);
+}
+inline void fence_proxy_async() {}
+inline void fence_mbar_init() {}
+inline void prefetch_l2(const void *) {}
+#endif
 
 }  // namespace gzpb

@@ -222,7 +222,7 @@ cudaError_t launch_snap(const SnapBatch &b, cudaStream_t st)
 {
     if (b.nunits == 0) return cudaSuccess;
     if (b.timer) b.timer->start(KT_SNAP, st);
-    k_snap<<<b.nunits * b.cpu, 32, 0, st>>>(b.in, b.unit_len, b.in_stride, b.cpu, b.out, b.out_stride, b.out_len);
+    GZPB_LAUNCH(k_snap, b.nunits * b.cpu, 32, 0, st, b.in, b.unit_len, b.in_stride, b.cpu, b.out, b.out_stride, b.out_len);
     if (b.timer) b.timer->stop(st);
     return cudaGetLastError();
 }

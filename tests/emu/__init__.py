@@ -1,0 +1,91 @@
+"""tests/emu — CPU SIMT emulator build of the kernels.  TEST INFRASTRUCTURE ONLY.
+
+The .cu sources of gzp_b200/csrc are compiled with g++ against tests/emu/shim
+(every CUDA thread a fiber, see shim/cuda_runtime.h) into tests/emu/_build/
+libgzpb_emu.so, which exports the same C ABI as the product library.  It lets
+the CPU test suite run the *kernel logic* bit-for-bit against the oracle in a
+container without a GPU.  Nothing under gzp_b200/ can load this library: the
+product path fails loudly when libgzpb.so / an sm_100 device is missing.
+"""
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(os.path.dirname(_HERE))
+_CSRC = os.path.join(_ROOT, "gzp_b200", "csrc")
+_BUILD = os.path.join(_HERE, "_build")
+SO = os.path.join(_BUILD, "libgzpb_emu.so")
+CXX = os.environ.get("CXX", "g++")
+FLAGS = ["-std=c++17", "-O2", "-g", "-fPIC", "-fno-strict-aliasing", "-Wno-unused", "-I", os.path.join(_HERE, "shim"),
+         "-I", _CSRC, "-DGZPB_EMU=1"]
+
+
+def build(force=False):
+    os.makedirs(_BUILD, exist_ok=True)
+    srcs = sorted(os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith(".cu"))
+    deps = srcs + [os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith(".cuh")]
+    deps += [os.path.join(_HERE, "shim", "cuda_runtime.h"), os.path.join(_HERE, "emu_runtime.cpp"),
+             os.path.join(_ROOT, "include", "gzpb.h")]
+    if not force and os.path.exists(SO) and all(os.path.getmtime(d) <= os.path.getmtime(SO) for d in deps):
+        return SO
+    objs = []
+    procs = []
+    for s in srcs + [os.path.join(_HERE, "emu_runtime.cpp")]:
+        o = os.path.join(_BUILD, os.path.basename(s).rsplit(".", 1)[0] + ".o")
+        procs.append(subprocess.Popen([CXX] + FLAGS + ["-x", "c++", "-c", s, "-o", o]))
+        objs.append(o)
+    for p in procs:
+        if p.wait() != 0:
+            raise RuntimeError("emulator build failed")
+    subprocess.check_call([CXX, "-shared", "-o", SO] + objs + ["-lpthread"])
+    return SO
+
+
+_lib = None
+
+
+def lib():
+    """ctypes handle of the emulated library with the product's prototypes."""
+    global _lib
+    if _lib is None:
+        from gzp_b200 import _lib as product
+        L = C.CDLL(build())
+        for name, (res, args) in product._SIGS.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+class EmuContext:
+    """The slice of gzp_b200.Context the emulator tests need, bound to the emulated library."""
+
+    def __init__(self, fmt, level, max_block_bytes=0, max_blocks_in_flight=8):
+        self.L = lib()
+        self.fmt, self.level = int(fmt), int(level)
+        h = C.c_void_p()
+        rc = self.L.gzpb_create(C.byref(h), 0, self.fmt, self.level, max_block_bytes, max_blocks_in_flight)
+        if rc != 0:
+            raise RuntimeError("gzpb_create (emu): %d %s" % (rc, self.L.gzpb_strerror(rc).decode()))
+        self.h = h
+
+    def close(self):
+        if self.h:
+            self.L.gzpb_destroy(self.h)
+            self.h = None
+
+    def encode_stream(self, data, buffer_size=0):
+        data = bytes(data)
+        n = len(data)
+        bs = buffer_size or self.L.gzpb_default_bufsize(self.fmt)
+        nblocks = max(1, (n + bs - 1) // bs)
+        cap = 64 + nblocks * self.L.gzpb_encode_capacity(self.fmt, bs)
+        out = C.create_string_buffer(cap)
+        olen = C.c_size_t(0)
+        src = C.create_string_buffer(data, n) if n else C.create_string_buffer(1)
+        rc = self.L.gzpb_encode_stream(self.h, src, n, buffer_size, out, cap, C.byref(olen))
+        if rc != 0:
+            raise RuntimeError("gzpb_encode_stream (emu): %d %s" % (rc, self.L.gzpb_strerror(rc).decode()))
+        return out.raw[:olen.value]
