@@ -19,6 +19,11 @@ class BlockOut(C.Structure):
                 ("check_amount", C.c_uint32), ("status", C.c_int)]
 
 
+class BlockDesc(C.Structure):
+    _fields_ = [("in_off", C.c_uint64), ("out_off", C.c_uint64), ("in_len", C.c_uint32), ("out_len", C.c_uint32),
+                ("crc", C.c_uint32), ("pad", C.c_uint32)]
+
+
 _SIGS = {
     "gzpb_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t]),
     "gzpb_destroy": (None, [C.c_void_p]),
@@ -45,6 +50,19 @@ _SIGS = {
     "gzpb_writer_flush": (C.c_int, [C.c_void_p]),
     "gzpb_writer_finish": (C.c_int, [C.c_void_p]),
     "gzpb_writer_destroy": (None, [C.c_void_p]),
+    "gzpb_block_header_size": (C.c_size_t, [C.c_int]),
+    "gzpb_block_size": (C.c_long, [C.c_int, C.c_void_p, C.c_size_t]),
+    "gzpb_scan_blocks": (C.c_int, [C.c_int, C.c_void_p, C.c_size_t, C.POINTER(BlockDesc), C.c_size_t, C.POINTER(C.c_size_t),
+                                   C.POINTER(C.c_size_t), C.POINTER(C.c_uint64)]),
+    "gzpb_decoder_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_size_t]),
+    "gzpb_decoder_destroy": (None, [C.c_void_p]),
+    "gzpb_decode_stream": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t),
+                                     C.POINTER(C.c_size_t)]),
+    "gzpb_decode_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gzpb_decoder_last_check": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]),
+    "gzpb_decoder_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
+    "gzpb_decoder_kernel_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
+    "gzpb_decoder_launch_count": (C.c_uint64, [C.c_void_p]),
     "gzpb_strerror": (C.c_char_p, [C.c_int]),
     "gzpb_version": (C.c_char_p, []),
 }

@@ -5,6 +5,7 @@ Names, argument meaning and error behaviour follow the reference:
   ZBuilder                          /root/reference/src/lib.rs:181-265
   format types                      /root/reference/src/deflate.rs:61,169,279,357,506; src/snap.rs:35
   GzpError                          /root/reference/src/lib.rs:114-163
+  ParDecompressBuilder / ParDecompress  /root/reference/src/par/decompress.rs:16-111, 113-352
 The chunker keeps the reference's exact semantics (strict '>' hold-back, flush()
 emitting whatever is buffered — even an empty block —, finish() always sending a
 final is_last block, the 32 KiB dictionary rule); the worker pool is replaced by
@@ -19,7 +20,8 @@ BUFSIZE = 131072      # lib.rs:105
 DICT_SIZE = 32768     # lib.rs:108
 
 _ERRNAMES = {-1: "BufferSize", -2: "NumThreads", -3: "BlockSizeExceeded", -4: "LibDeflaterCompress",
-             -5: "LibDeflaterCompressionLvl", -6: "Io", -7: "ChannelSend", -8: "Cuda", -9: "Unknown", -10: "NoMem"}
+             -5: "LibDeflaterCompressionLvl", -6: "Io", -7: "ChannelSend", -8: "Cuda", -9: "Unknown", -10: "NoMem",
+             -11: "InvalidHeader", -12: "InvalidCheck", -13: "LibDelfaterDecompress", -14: "InvalidBlockSize"}
 
 
 class GzpError(Exception):
@@ -411,3 +413,180 @@ class ZBuilder:
         if self._b._buffer_size < DICT_SIZE:
             raise GzpError(-1, f"Invalid buffer size ({self._b._buffer_size}), must be >= {DICT_SIZE}")
         return self._b.from_writer(writer)
+
+
+class Decoder:
+    """One device decoder = the per-worker `Decompressor` of the reference
+    (BlockFormatSpec::create_decompressor, deflate.rs:372-381, 521-530), for a whole GPU."""
+
+    def __init__(self, fmt, device=0, max_blocks_in_flight=2048):
+        self._lib = _lib.load()
+        self.fmt = fmt.ID if isinstance(fmt, _Format) or (isinstance(fmt, type) and issubclass(fmt, _Format)) else int(fmt)
+        h = C.c_void_p()
+        rc = self._lib.gzpb_decoder_create(C.byref(h), device, self.fmt, max_blocks_in_flight)
+        if rc != 0:
+            raise GzpError(rc)
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.gzpb_decoder_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def header_size(self):
+        return self._lib.gzpb_block_header_size(self.fmt)
+
+    def decode(self, data, partial=False):
+        """Decode the whole members in `data`.  Returns (decoded bytes, consumed input bytes).
+        partial=True leaves an incomplete trailing member unconsumed; otherwise it is an Io error."""
+        data = bytes(data)
+        total = C.c_uint64(0)
+        self._lib.gzpb_scan_blocks(self.fmt, data, len(data), None, 0, None, None, C.byref(total))
+        out = C.create_string_buffer(max(1, total.value))
+        olen = C.c_size_t(0)
+        used = C.c_size_t(0)
+        rc = self._lib.gzpb_decode_stream(self._h, data, len(data), out, total.value, C.byref(olen),
+                                          C.byref(used) if partial else None)
+        if rc != 0:
+            raise self._error(rc)
+        return out.raw[:olen.value], (used.value if partial else len(data))
+
+    def _error(self, rc):
+        if rc == -12:
+            f, e = C.c_uint32(0), C.c_uint32(0)
+            self._lib.gzpb_decoder_last_check(self._h, C.byref(f), C.byref(e), None)
+            err = GzpError(rc, f"Invalid checksum, found {f.value}, expected {e.value}")      # lib.rs:139-140
+            err.found, err.expected = f.value, e.value
+            return err
+        return GzpError(rc)
+
+    def launch_count(self):
+        return self._lib.gzpb_decoder_launch_count(self._h)
+
+
+class ParDecompressBuilder:
+    """ParDecompressBuilder<F: BlockFormatSpec> (par/decompress.rs:16-111).  `num_threads` is kept for API
+    parity; the device batch (`blocks_in_flight`) replaces the 2*num_threads channel bound (:73)."""
+
+    def __init__(self, fmt=Bgzf):
+        self.format = fmt() if isinstance(fmt, type) else fmt
+        if self.format.ID not in (BGZF, MGZIP):
+            raise GzpError(-9, "ParDecompress needs a BlockFormatSpec format (Mgzip or Bgzf)")
+        self._buffer_size = BUFSIZE                              # par/decompress.rs:34
+        self._num_threads = 1
+        self._pin = None
+        self._device = 0
+        self._blocks_in_flight = 2048
+
+    @classmethod
+    def new(cls, fmt=Bgzf):
+        return cls(fmt)
+
+    def buffer_size(self, n):
+        if n < DICT_SIZE:                                         # par/decompress.rs:41-47
+            raise GzpError(-1, f"Invalid buffer size ({n}), must be >= {DICT_SIZE}")
+        self._buffer_size = int(n)
+        return self
+
+    def num_threads(self, n):
+        if n == 0:                                                # par/decompress.rs:50-56
+            raise GzpError(-2, "Invalid number of threads (0) selected.")
+        self._num_threads = int(n)
+        return self
+
+    def maybe_num_threads(self, n):                               # par/decompress.rs:90-93
+        self._num_threads = int(n)
+        return self
+
+    def pin_threads(self, first_core):
+        self._pin = first_core
+        return self
+
+    def device(self, index):
+        self._device = int(index)
+        return self
+
+    def blocks_in_flight(self, n):
+        self._blocks_in_flight = int(n)
+        return self
+
+    def from_reader(self, reader):
+        return ParDecompress(self.format, reader, self._buffer_size, self._device, self._blocks_in_flight)
+
+    def maybe_par_from_reader(self, reader):
+        # the reference falls back to a single-threaded MultiGzDecoder for 0 threads (:96-102);
+        # this engine has no CPU decoder, so the GPU path serves both cases
+        return self.from_reader(reader)
+
+
+class ParDecompress:
+    """ParDecompress<F> as a Python `read` object (par/decompress.rs:113-352): the reader loop
+    (:190-207) pulls whole members from `reader`, the GPU decodes them in batches, `read`
+    hands the decoded bytes out in stream order."""
+
+    _CHUNK = 8 << 20
+
+    def __init__(self, fmt, reader, buffer_size=BUFSIZE, device=0, blocks_in_flight=2048):
+        self.format = fmt
+        self.reader = reader
+        self.buffer_size = buffer_size
+        self._dec = Decoder(fmt.ID, device, blocks_in_flight)
+        self._in = bytearray()
+        self._out = bytearray()
+        self._eof = False
+        self._error = None
+
+    @classmethod
+    def builder(cls, fmt=Bgzf):
+        return ParDecompressBuilder(fmt)
+
+    def _fill(self):
+        chunk = self.reader.read(self._CHUNK)
+        if chunk:
+            self._in.extend(chunk)
+        else:
+            self._eof = True
+        try:
+            if self._eof:
+                # a short trailing header is EOF (:193, 205-206); a truncated member is an Io error (:197)
+                hs = self._dec.header_size()
+                if len(self._in) >= hs:
+                    out, used = self._dec.decode(self._in, partial=False)
+                    self._out.extend(out)
+                self._in.clear()
+            else:
+                out, used = self._dec.decode(self._in, partial=True)
+                self._out.extend(out)
+                del self._in[:used]
+        except GzpError as e:
+            self._error = e
+            raise
+
+    def read(self, n=-1):
+        if self._error:
+            raise self._error
+        while (n < 0 or len(self._out) < n) and not self._eof:
+            self._fill()
+        k = len(self._out) if n < 0 else min(n, len(self._out))
+        b = bytes(self._out[:k])
+        del self._out[:k]
+        return b
+
+    def finish(self):
+        """Close things in such a way as to get errors (:222-236)."""
+        self._dec.close()
+        if self._error:
+            raise self._error
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self._dec.close()
+        return False

@@ -7,7 +7,7 @@
 
 namespace gzpb {
 
-enum KernelId { KT_CHAIN = 0, KT_MATCH, KT_EMIT, KT_GATHER, KT_CRC, KT_SNAP, KT_COUNT };
+enum KernelId { KT_CHAIN = 0, KT_MATCH, KT_EMIT, KT_GATHER, KT_CRC, KT_SNAP, KT_INFLATE, KT_COUNT };
 
 // CUDA-event timing of individual kernels on their launching stream.
 struct KernelTimer {

@@ -163,6 +163,10 @@ extern "C" const char *gzpb_strerror(int code)
     case GZPB_ECUDA: return g_last_cuda_error[0] ? g_last_cuda_error : "CUDA error";
     case GZPB_EINVAL: return "invalid argument";
     case GZPB_ENOMEM: return "out of memory";
+    case GZPB_EHEADER: return "Invalid block header";
+    case GZPB_ECHECK: return "Invalid checksum";
+    case GZPB_EDECOMPRESS: return "decompression error: corrupt DEFLATE data";
+    case GZPB_EBLOCK: return "Invalid block size";
     default: return "unknown";
     }
 }
@@ -339,7 +343,7 @@ extern "C" int gzpb_set_profiling(gzpb_ctx *c, int on)
 
 extern "C" int gzpb_kernel_ms(gzpb_ctx *c, const char *name, double *total_ms, uint64_t *launches)
 {
-    static const char *names[KT_COUNT] = {"chain", "match", "emit", "gather", "crc", "snap"};
+    static const char *names[KT_COUNT] = {"chain", "match", "emit", "gather", "crc", "snap", "inflate"};
     if (!c || !name) return GZPB_EINVAL;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();

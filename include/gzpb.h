@@ -43,7 +43,11 @@ enum gzpb_status {
     GZPB_ECHANNEL = -7,     /* ChannelSend / ChannelReceive: stream already finished / torn down */
     GZPB_ECUDA = -8,        /* CUDA runtime / launch failure (no reference analogue) */
     GZPB_EINVAL = -9,       /* bad argument (Unknown) */
-    GZPB_ENOMEM = -10
+    GZPB_ENOMEM = -10,
+    GZPB_EHEADER = -11,     /* InvalidHeader: "Extra field flag not set" / "Bad SID" (src/deflate.rs:407-417, 555-565) */
+    GZPB_ECHECK = -12,      /* InvalidCheck{found, expected} (src/par/decompress.rs:176-181) */
+    GZPB_EDECOMPRESS = -13, /* LibDelfaterDecompress / DecompressError: corrupt DEFLATE data (src/deflate.rs:393, 541) */
+    GZPB_EBLOCK = -14       /* InvalidBlockSize: a member shorter than its own header + footer */
 };
 
 /* Constants of the reference (src/lib.rs:105,108; src/bgzf.rs:20,22). */
@@ -147,6 +151,53 @@ void gzpb_host_free(void *p);
 int gzpb_set_profiling(gzpb_ctx *ctx, int on);
 int gzpb_kernel_ms(gzpb_ctx *ctx, const char *name, double *total_ms, uint64_t *launches);
 uint64_t gzpb_launch_count(gzpb_ctx *ctx);
+
+/* ---- decoder: the ParDecompress path -------------------------------
+ * `trait BlockFormatSpec` (src/lib.rs:411-448) is implemented by Mgzip and Bgzf
+ * (src/deflate.rs:359-423, 508-571); ParDecompress::run (src/par/decompress.rs:132-220) reads
+ * one member at a time (check_header, get_block_size), and a worker inflates it into ISIZE
+ * bytes and verifies the CRC-32 of the footer. */
+typedef struct gzpb_decoder gzpb_decoder;
+
+/* One member to decode (also the device layout consumed by gzpb_decode_device): raw DEFLATE
+ * payload at comp + in_off, `out_len` (ISIZE) bytes to produce at out + out_off, footer CRC-32. */
+typedef struct {
+    uint64_t in_off;
+    uint64_t out_off;
+    uint32_t in_len;
+    uint32_t out_len;
+    uint32_t crc;
+    uint32_t pad;
+} gzpb_block_desc;
+
+/* BlockFormatSpec::HEADER_SIZE (src/deflate.rs:370, 519). */
+size_t gzpb_block_header_size(int format);
+/* BlockFormatSpec::check_header + get_block_size (src/deflate.rs:407-422, 555-570): total size of
+ * the member starting at `hdr`, or a negative status code: GZPB_EHEADER, or GZPB_EIO when fewer than
+ * HEADER_SIZE bytes are available. */
+long gzpb_block_size(int format, const void *hdr, size_t avail);
+/* The reader loop of ParDecompress::run (src/par/decompress.rs:190-207) over an in-memory input:
+ * one descriptor per member (get_footer_values, src/lib.rs:440-447).  `descs` may be NULL to count.
+ * A short trailing header is EOF; a truncated member returns GZPB_EIO with `consumed` at its start. */
+int gzpb_scan_blocks(int format, const void *in, size_t in_len, gzpb_block_desc *descs, size_t max_descs,
+                     size_t *nblocks, size_t *consumed, uint64_t *total_out);
+/* BlockFormatSpec::create_decompressor (src/deflate.rs:372-381, 521-530): one decoder per GPU. */
+int gzpb_decoder_create(gzpb_decoder **d, int device, int format, size_t max_blocks_in_flight);
+void gzpb_decoder_destroy(gzpb_decoder *d);
+/* ParDecompress end to end for an in-memory input of concatenated members: decoded bytes in stream
+ * order.  With `consumed` non-NULL an incomplete trailing member is left unconsumed (incremental
+ * readers call again with more bytes); with NULL it is GZPB_EIO like the reference's read_exact. */
+int gzpb_decode_stream(gzpb_decoder *d, const void *in, size_t in_len, void *out, size_t out_cap, size_t *out_len,
+                       size_t *consumed);
+/* Device-resident form, asynchronous on `cuda_stream`: d_status[i] = 0 ok, 1 bad data,
+ * 2 output overrun, 3 input overrun, 4 CRC mismatch; d_crc_found[i] = CRC-32 of the decoded block. */
+int gzpb_decode_device(gzpb_decoder *d, const void *d_comp, const gzpb_block_desc *d_desc, size_t nblocks, void *d_out,
+                       int32_t *d_status, uint32_t *d_crc_found, void *cuda_stream);
+/* InvalidCheck{found, expected} of the last GZPB_ECHECK (and the index of the failing block). */
+int gzpb_decoder_last_check(gzpb_decoder *d, uint32_t *found, uint32_t *expected, uint64_t *block_index);
+int gzpb_decoder_set_profiling(gzpb_decoder *d, int on);
+int gzpb_decoder_kernel_ms(gzpb_decoder *d, double *total_ms, uint64_t *launches);
+uint64_t gzpb_decoder_launch_count(gzpb_decoder *d);
 
 const char *gzpb_strerror(int code);
 const char *gzpb_version(void);

@@ -72,6 +72,13 @@ def lib():
         L.oracle_par_compress.argtypes = [c.c_int, c.c_int, c.c_size_t, c.c_int, c.c_char_p, c.c_size_t, c.c_char_p, c.c_size_t, c.POINTER(c.c_size_t)]
         L.oracle_make_huffman_code.restype = None
         L.oracle_make_huffman_code.argtypes = [c.c_uint, c.c_uint, c.POINTER(c.c_uint32), c.POINTER(c.c_uint8), c.POINTER(c.c_uint32)]
+        L.oracle_inflate.restype = c.c_long
+        L.oracle_inflate.argtypes = [c.c_char_p, c.c_size_t, c.c_char_p, c.c_size_t]
+        L.oracle_block_size.restype = c.c_long
+        L.oracle_block_size.argtypes = [c.c_int, c.c_char_p, c.c_size_t]
+        L.oracle_decode_stream.restype = c.c_int
+        L.oracle_decode_stream.argtypes = [c.c_int, c.c_char_p, c.c_size_t, c.c_char_p, c.c_size_t, c.POINTER(c.c_size_t),
+                                           c.POINTER(c.c_uint32), c.POINTER(c.c_uint32)]
         L.oracle_level_supported.restype = c.c_int
         L.oracle_level_supported.argtypes = [c.c_int]
         _lib = L
@@ -171,3 +178,24 @@ def compress_stream(fmt, level, buffer_size, writes, flushes=()):
             amount = (amount + len(blk)) & 0xFFFFFFFF
     out += footer(fmt, total, amount)
     return bytes(out)
+
+
+def inflate(raw, out_cap):
+    """Raw DEFLATE -> bytes (decode_block restated); raises ValueError(code) on corrupt input."""
+    out = ctypes.create_string_buffer(max(out_cap, 1))
+    r = lib().oracle_inflate(bytes(raw), len(raw), out, out_cap)
+    if r < 0:
+        raise ValueError(int(r))
+    return out.raw[:r]
+
+
+def decode_stream(fmt, data, out_cap=None):
+    """ParDecompress over concatenated Bgzf / Mgzip members: (status, bytes, found_crc, expected_crc)."""
+    data = bytes(data)
+    if out_cap is None:
+        out_cap = 64 + 1032 * len(data)
+    out = ctypes.create_string_buffer(max(out_cap, 1))
+    olen = ctypes.c_size_t(0)
+    found, expected = ctypes.c_uint32(0), ctypes.c_uint32(0)
+    rc = lib().oracle_decode_stream(fmt, data, len(data), out, out_cap, ctypes.byref(olen), ctypes.byref(found), ctypes.byref(expected))
+    return rc, out.raw[:olen.value], found.value, expected.value

@@ -69,6 +69,12 @@ size_t oracle_footer(int format, uint32_t sum, uint32_t amount, uint8_t *out);
 double oracle_par_compress(int format, int level, size_t buffer_size, int num_threads, const uint8_t *in,
                            size_t n, uint8_t *out, size_t out_cap, size_t *out_len);
 
+/* inflate_oracle.c — the block DECODE path (ParDecompress worker + reader loop). */
+long oracle_inflate(const uint8_t *in, size_t n, uint8_t *out, size_t out_cap);
+long oracle_block_size(int format, const uint8_t *hdr, size_t avail);
+int oracle_decode_stream(int format, const uint8_t *in, size_t n, uint8_t *out, size_t out_cap, size_t *out_len,
+                         uint32_t *found, uint32_t *expected);
+
 #ifdef __cplusplus
 }
 #endif

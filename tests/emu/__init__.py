@@ -89,3 +89,34 @@ class EmuContext:
         if rc != 0:
             raise RuntimeError("gzpb_encode_stream (emu): %d %s" % (rc, self.L.gzpb_strerror(rc).decode()))
         return out.raw[:olen.value]
+
+
+class EmuDecoder:
+    """gzpb_decoder bound to the emulated library."""
+
+    def __init__(self, fmt, max_blocks_in_flight=64):
+        self.L = lib()
+        self.fmt = int(fmt)
+        h = C.c_void_p()
+        rc = self.L.gzpb_decoder_create(C.byref(h), 0, self.fmt, max_blocks_in_flight)
+        if rc != 0:
+            raise RuntimeError("gzpb_decoder_create (emu): %d" % rc)
+        self.h = h
+
+    def close(self):
+        if self.h:
+            self.L.gzpb_decoder_destroy(self.h)
+            self.h = None
+
+    def decode_stream(self, data, out_cap=None):
+        """Returns (status, bytes, found_crc, expected_crc)."""
+        data = bytes(data)
+        total = C.c_uint64(0)
+        self.L.gzpb_scan_blocks(self.fmt, data, len(data), None, 0, None, None, C.byref(total))
+        cap = out_cap if out_cap is not None else total.value + 64
+        out = C.create_string_buffer(max(cap, 1))
+        olen = C.c_size_t(0)
+        rc = self.L.gzpb_decode_stream(self.h, data, len(data), out, cap, C.byref(olen), None)
+        f, e = C.c_uint32(0), C.c_uint32(0)
+        self.L.gzpb_decoder_last_check(self.h, C.byref(f), C.byref(e), None)
+        return rc, out.raw[:olen.value], f.value, e.value

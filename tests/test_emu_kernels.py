@@ -63,3 +63,128 @@ def test_emu_snap():
     rnd = random.Random(7)
     for d in (TEXT, bytes(70000), bytes(rnd.getrandbits(8) for _ in range(50000)), b"", b"abc"):
         _run(oracle.SNAP, 0, 131072, d)
+
+
+# ---- decode path (k_inflate) -------------------------------------------------------------
+import io
+import struct
+
+
+def _bgzf_member(data, level=6, strategy=zlib.Z_DEFAULT_STRATEGY):
+    """A BGZF member whose payload comes from stock zlib (not from this repo's encoder)."""
+    co = zlib.compressobj(level, zlib.DEFLATED, -15, 9, strategy)
+    raw = co.compress(data) + co.flush()
+    hdr = bytes([31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 66, 67, 2, 0]) + struct.pack("<H", len(raw) + 26 - 1)
+    return hdr + raw + struct.pack("<II", zlib.crc32(data), len(data))
+
+
+@pytest.fixture()
+def emu_backend(monkeypatch):
+    """Route the Python mirror (gzp_b200.api) to the emulated library for the duration of a test."""
+    from gzp_b200 import _lib as product
+    monkeypatch.setattr(product, "_lib", emu.lib())
+    yield
+
+
+def test_emu_inflate_roundtrip_own_streams():
+    dec = emu.EmuDecoder(oracle.BGZF)
+    try:
+        for lvl in (0, 2, 6, 9):
+            s = oracle.compress_stream(oracle.BGZF, lvl, 65280, [TEXT])
+            rc, out, _, _ = dec.decode_stream(s)
+            assert rc == 0 and out == TEXT
+            assert oracle.decode_stream(oracle.BGZF, s)[:2] == (0, TEXT)
+    finally:
+        dec.close()
+    dm = emu.EmuDecoder(oracle.MGZIP)
+    try:
+        s = oracle.compress_stream(oracle.MGZIP, 6, 131072, [TEXT])
+        rc, out, _, _ = dm.decode_stream(s)
+        assert rc == 0 and out == TEXT
+    finally:
+        dm.close()
+
+
+def test_emu_inflate_stock_zlib_members():
+    rnd = random.Random(3)
+    blobs = [TEXT[:60000], b"", b"a", bytes(60000), bytes(rnd.getrandbits(8) for _ in range(30000)), TEXT[1000:1200],
+             b"ab" * 20000, bytes(rnd.choice(b"ACGT") for _ in range(50000))]
+    dec = emu.EmuDecoder(oracle.BGZF)
+    try:
+        for lvl, strat in ((1, zlib.Z_DEFAULT_STRATEGY), (6, zlib.Z_DEFAULT_STRATEGY), (9, zlib.Z_DEFAULT_STRATEGY),
+                           (6, zlib.Z_FIXED), (6, zlib.Z_HUFFMAN_ONLY), (0, zlib.Z_DEFAULT_STRATEGY), (6, zlib.Z_RLE)):
+            s = b"".join(_bgzf_member(b, lvl, strat) for b in blobs)
+            rc, out, _, _ = dec.decode_stream(s)
+            assert rc == 0 and out == b"".join(blobs), (lvl, strat)
+    finally:
+        dec.close()
+
+
+def test_emu_inflate_error_paths_match_the_oracle():
+    good = oracle.compress_stream(oracle.BGZF, 6, 65280, [TEXT[:150000]])
+    dec = emu.EmuDecoder(oracle.BGZF)
+    try:
+        cases = {}
+        b = bytearray(good); b[-28 - 8] ^= 0xFF; cases["crc"] = bytes(b)             # CRC of the last data block
+        b = bytearray(good); b[3] = 0; cases["flag"] = bytes(b)                       # FEXTRA flag cleared
+        b = bytearray(good); b[12] = ord("X"); cases["sid"] = bytes(b)                # bad SID
+        cases["truncated"] = good[:len(good) - 40]
+        b = bytearray(good); b[40] ^= 0x55; b[41] ^= 0xAA; b[60] ^= 0x0F; cases["payload"] = bytes(b)
+        cases["short_tail"] = good + b"\x1f\x8b\x08"                                  # < HEADER_SIZE trailing bytes = EOF
+        for name, s in cases.items():
+            rc_o, out_o, f_o, e_o = oracle.decode_stream(oracle.BGZF, s)
+            rc, out, f, e = dec.decode_stream(s)
+            if name == "payload":
+                # corrupt DEFLATE data: either a decode error or a checksum mismatch, never success
+                assert rc in (-12, -13) and rc_o in (-12, -13), name
+                continue
+            assert rc == rc_o, (name, rc, rc_o)
+            if rc == 0:
+                assert out == out_o == TEXT[:150000]
+            if rc == -12:
+                assert (f, e) == (f_o, e_o)
+    finally:
+        dec.close()
+
+
+def test_emu_pardecompress_mirror(emu_backend):
+    import gzp_b200
+
+    class Dribble(io.RawIOBase):
+        """A reader that returns odd-sized pieces, so members straddle read() calls."""
+
+        def __init__(self, data):
+            self.d, self.p, self.k = data, 0, 0
+
+        def read(self, n=-1):
+            self.k += 1
+            step = min(n if n > 0 else 1 << 30, 7919 * (1 + self.k % 5))
+            b = self.d[self.p:self.p + step]
+            self.p += len(b)
+            return b
+
+    sink = io.BytesIO()
+    w = gzp_b200.ParCompressBuilder(gzp_b200.Bgzf).compression_level(6).from_writer(sink)
+    w.write(TEXT[:100000]); w.flush(); w.write(TEXT[100000:]); w.finish()
+    comp = sink.getvalue()
+    assert gzip.decompress(comp) == TEXT
+    r = gzp_b200.ParDecompressBuilder(gzp_b200.Bgzf).from_reader(Dribble(comp))
+    r._CHUNK = 50000
+    got = bytearray()
+    while True:
+        b = r.read(33333)
+        if not b:
+            break
+        got.extend(b)
+    r.finish()
+    assert bytes(got) == TEXT
+    # InvalidCheck carries found / expected (lib.rs:139-140)
+    bad = bytearray(comp); bad[-28 - 8] ^= 1
+    r = gzp_b200.ParDecompress.builder(gzp_b200.Bgzf).from_reader(io.BytesIO(bytes(bad)))
+    with pytest.raises(gzp_b200.GzpError) as ei:
+        r.read()
+    assert ei.value.variant == "InvalidCheck" and ei.value.found != ei.value.expected
+    with pytest.raises(gzp_b200.GzpError):
+        gzp_b200.ParDecompressBuilder(gzp_b200.Bgzf).num_threads(0)
+    with pytest.raises(gzp_b200.GzpError):
+        gzp_b200.ParDecompressBuilder(gzp_b200.Bgzf).buffer_size(100)
