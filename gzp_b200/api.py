@@ -415,6 +415,25 @@ class ZBuilder:
         return self._b.from_writer(writer)
 
 
+def bgzf_index(stream):
+    """.gzi index of a BGZF stream (htslib `bgzip -i` layout); host-only, needs no GPU."""
+    stream = bytes(stream)
+    L = _lib.load()
+    n = C.c_size_t(0)
+    rc = L.gzpb_bgzf_index(stream, len(stream), None, 0, C.byref(n))
+    if rc != 0:
+        raise GzpError(rc)
+    out = C.create_string_buffer(n.value)
+    rc = L.gzpb_bgzf_index(stream, len(stream), out, n.value, C.byref(n))
+    if rc != 0:
+        raise GzpError(rc)
+    return out.raw[:n.value]
+
+
+def bgzf_virtual_offset(block_offset, within_block):
+    return _lib.load().gzpb_bgzf_virtual_offset(block_offset, within_block)
+
+
 class Decoder:
     """One device decoder = the per-worker `Decompressor` of the reference
     (BlockFormatSpec::create_decompressor, deflate.rs:372-381, 521-530), for a whole GPU."""

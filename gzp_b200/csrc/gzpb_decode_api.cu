@@ -314,3 +314,42 @@ extern "C" int gzpb_decode_stream(gzpb_decoder *d, const void *in_v, size_t in_l
     if (consumed) *consumed = used;
     return scan_rc;
 }
+
+// ---- BGZF block index (.gzi) and virtual offsets (a TODO of the reference,
+// /root/reference/README.md:161).  Layout as written by htslib's `bgzip -i`: u64 LE entry count, then per
+// entry {u64 LE compressed offset, u64 LE uncompressed offset} of every data block after the first.
+extern "C" int gzpb_bgzf_index(const void *bgzf_v, size_t len, void *out_v, size_t out_cap, size_t *out_len)
+{
+    const uint8_t *in = (const uint8_t *)bgzf_v;
+    uint8_t *out = (uint8_t *)out_v;
+    if (!out_len || (len && !in)) return GZPB_EINVAL;
+    size_t pos = 0;
+    uint64_t upos = 0, n = 0;
+    bool first = true;
+    auto put64 = [&](size_t at, uint64_t v) { for (int i = 0; i < 8; i++) out[at + i] = (uint8_t)(v >> (8 * i)); };
+    while (len - pos >= 18) {
+        const long size = gzpb_block_size(GZPB_BGZF, in + pos, len - pos);
+        if (size < 0) return (int)size;
+        if ((size_t)size < 26) return GZPB_EBLOCK;
+        if ((size_t)size > len - pos) return GZPB_EIO;
+        const uint8_t *f = in + pos + size - 4;
+        const uint32_t isize = (uint32_t)f[0] | ((uint32_t)f[1] << 8) | ((uint32_t)f[2] << 16) | ((uint32_t)f[3] << 24);
+        if (isize) {                                   // the EOF marker and empty flush blocks carry no data
+            if (!first) {
+                const size_t at = 8 + 16 * (size_t)n;
+                if (out) { if (at + 16 > out_cap) return GZPB_ECOMPRESS; put64(at, pos); put64(at + 8, upos); }
+                n++;
+            }
+            first = false;
+        }
+        upos += isize; pos += (size_t)size;
+    }
+    if (out) { if (out_cap < 8) return GZPB_ECOMPRESS; put64(0, n); }
+    *out_len = 8 + 16 * (size_t)n;
+    return GZPB_OK;
+}
+
+extern "C" uint64_t gzpb_bgzf_virtual_offset(uint64_t block_offset, uint32_t within_block)
+{
+    return (block_offset << 16) | (within_block & 0xFFFFu);
+}

@@ -10,8 +10,9 @@
 // a warp decodes up to 32 tokens at a time (64-bit bit buffer refilled with 32-bit
 // loads, 10-bit / 8-bit direct lookup tables in shared memory, canonical bit-by-bit
 // fallback for longer codes) and the whole warp then writes them out: a prefix scan
-// of the token lengths places every token, literals are stored in parallel, matches
-// are copied 32 bytes per step in token order.  The warp finally computes the
+// of the token lengths places every token, literals are stored in parallel, matches that only read
+// bytes from before the batch are copied four at a time (loads before stores), the
+// few that read the batch's own output follow in token order.  The warp finally computes the
 // CRC-32 of its output (per-lane slices recombined in GF(2)) = `Check::update`, and
 // compares it with the member's footer.  Decoded bytes land directly at their final
 // stream offset (the host computed the offsets from the ISIZE fields), so there is
@@ -61,6 +62,8 @@ struct InfWarp {
     uint8_t lens[kNumLitlen + kNumOffset + 4];
     uint8_t plens[kNumPrecode + 1];
     uint32_t tok[kBatch];              // literal byte, or 0x80000000 | len << 16 | dist
+    uint32_t pos[kBatch];              // output position of every token of the batch
+    uint8_t idx[kBatch];               // lanes holding batch-independent matches, compacted
 };
 
 // unaligned little-endian 32-bit global load (two aligned loads; may touch up to 7 bytes past p)
@@ -290,15 +293,50 @@ k_inflate(const uint8_t *__restrict__ comp, const InflateDesc *__restrict__ desc
             for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (uint32_t)o) incl += v; }
             const uint32_t mypos = opos + incl - mylen;
             const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+            // Matches whose source lies entirely before this batch depend on nothing written in this
+            // round: they are copied first, four at a time with all loads issued before the stores, so
+            // their L2 round trips overlap.  The rest (sources inside the batch) follow in token order.
+            const bool indep = is_match && (mypos - mydist + min(mylen, mydist) <= opos);
+            const uint32_t ind = __ballot_sync(0xFFFFFFFFu, indep);
+            uint32_t dep = __ballot_sync(0xFFFFFFFFu, is_match && !indep);
+            S.pos[lane] = mypos;
+            if (indep) S.idx[__popc(ind & lanemask_lt())] = (uint8_t)lane;
             if (lane < ntok && !is_match) dst[mypos] = (uint8_t)t;
-            uint32_t matches = __ballot_sync(0xFFFFFFFFu, is_match);
             __syncwarp();
-            while (matches) {
-                const int j = __ffs(matches) - 1;
-                matches &= matches - 1;
-                const uint32_t pj = __shfl_sync(0xFFFFFFFFu, mypos, j);
-                const uint32_t lj = __shfl_sync(0xFFFFFFFFu, mylen, j);
-                const uint32_t dj = __shfl_sync(0xFFFFFFFFu, mydist, j);
+            const uint32_t nind = __popc(ind);
+            for (uint32_t k = 0; k < nind; k += 4) {
+                uint32_t ml[4], mp[4], ms[4];
+                uint8_t v[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    ml[u] = 0; mp[u] = 0; ms[u] = 0;
+                    if (k + u < nind) {
+                        const uint32_t j = S.idx[k + u], tj = S.tok[j];
+                        const uint32_t lj = (tj >> 16) & 0x1FFu, dj = tj & 0xFFFFu;
+                        ml[u] = lj; mp[u] = S.pos[j];
+                        ms[u] = mp[u] - dj + (dj >= lj ? lane : lane % dj);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) v[u] = (lane < ml[u]) ? dst[ms[u]] : (uint8_t)0;
+#pragma unroll
+                for (int u = 0; u < 4; u++) if (lane < ml[u]) dst[mp[u] + lane] = v[u];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    if (ml[u] > 32) {     // long match: the remaining bytes
+                        const uint32_t j = S.idx[k + u], dj = S.tok[j] & 0xFFFFu;
+                        const uint8_t *from = dst + mp[u] - dj;
+                        if (dj >= ml[u]) { for (uint32_t b = lane + 32; b < ml[u]; b += 32) dst[mp[u] + b] = from[b]; }
+                        else { for (uint32_t b = lane + 32; b < ml[u]; b += 32) dst[mp[u] + b] = from[b % dj]; }
+                    }
+                }
+            }
+            __syncwarp();
+            while (dep) {
+                const int j = __ffs(dep) - 1;
+                dep &= dep - 1;
+                const uint32_t tj = S.tok[j], pj = S.pos[j];
+                const uint32_t lj = (tj >> 16) & 0x1FFu, dj = tj & 0xFFFFu;
                 const uint8_t *from = dst + pj - dj;
                 if (dj >= lj) { for (uint32_t b = lane; b < lj; b += 32) dst[pj + b] = from[b]; }
                 else { for (uint32_t b = lane; b < lj; b += 32) dst[pj + b] = from[b % dj]; }    // overlapping copy = periodic extension

@@ -199,6 +199,13 @@ int gzpb_decoder_set_profiling(gzpb_decoder *d, int on);
 int gzpb_decoder_kernel_ms(gzpb_decoder *d, double *total_ms, uint64_t *launches);
 uint64_t gzpb_decoder_launch_count(gzpb_decoder *d);
 
+/* BGZF block index (.gzi, the layout htslib's `bgzip -i` writes: u64 count, then {u64 compressed offset,
+ * u64 uncompressed offset} per data block after the first) and virtual offsets (block_offset << 16 |
+ * offset within the block) — SURVEY.md §8(f) rank 2; a TODO of the reference (README.md:161).
+ * `out` may be NULL to size the index. */
+int gzpb_bgzf_index(const void *bgzf, size_t len, void *out, size_t out_cap, size_t *out_len);
+uint64_t gzpb_bgzf_virtual_offset(uint64_t block_offset, uint32_t within_block);
+
 const char *gzpb_strerror(int code);
 const char *gzpb_version(void);
 

@@ -128,3 +128,24 @@ def test_drop_finishes_the_stream(monkeypatch):
     with gzp_b200.ParCompressBuilder(gzp_b200.Gzip).from_writer(sink) as pc:
         pc.write(b"This is a first test line\nThis is a second test line\n")
     assert gzip.decompress(sink.getvalue()) == b"This is a first test line\nThis is a second test line\n"
+
+
+def test_bgzf_gzi_index_and_virtual_offsets():
+    """The .gzi entries (htslib layout) address real members: decoding the member at every
+    compressed offset yields the input from the matching uncompressed offset."""
+    import struct
+    data = bytes(random.Random(9).getrandbits(8) for _ in range(1000)) * 300
+    stream = oracle.compress_stream(oracle.BGZF, 6, 65280, [data[:100000], b"", data[100000:]], flushes={0, 1})
+    idx = gzp_b200.bgzf_index(stream)
+    n, = struct.unpack_from("<Q", idx, 0)
+    assert len(idx) == 8 + 16 * n and n >= 3
+    prev_u = 0
+    for i in range(n):
+        c, u = struct.unpack_from("<QQ", idx, 8 + 16 * i)
+        assert u > prev_u
+        prev_u = u
+        size = struct.unpack_from("<H", stream, c + 16)[0] + 1
+        member = zlib.decompressobj(31).decompress(stream[c:c + size])
+        assert member == data[u:u + len(member)] and len(member) > 0
+    assert gzp_b200.bgzf_virtual_offset(0x1234, 77) == (0x1234 << 16) | 77
+    assert gzp_b200.bgzf_index(oracle.compress_stream(oracle.BGZF, 6, 65280, [b""])) == struct.pack("<Q", 0)
