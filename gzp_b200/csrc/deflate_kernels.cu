@@ -220,7 +220,7 @@ constexpr int kLsStride = 32;            // list_start entries per sub-unit: [0.
 
 __global__ void __launch_bounds__(kSplitThreads)
 k_split(const __grid_constant__ Geo g, uint32_t *__restrict__ lists, uint32_t *__restrict__ list_start,
-        uint16_t *__restrict__ next4, uint16_t *__restrict__ prev3)
+        uint16_t *__restrict__ next4, uint16_t *__restrict__ prev3, int ht)
 {
     __shared__ uint32_t s_w[32][kSplitLists];     // per-warp member counts, then running bases
     __shared__ uint32_t s_start[kSplitLists];
@@ -241,7 +241,7 @@ k_split(const __grid_constant__ Geo g, uint32_t *__restrict__ lists, uint32_t *_
         const uint32_t p = t * 32 + lane;
         const bool act = p < ninsert;
         const uint32_t v = act ? ldg32u(inw, p) : 0;
-        uint32_t h4 = lz_hash(v, 16), h3 = lz_hash(v & 0xFFFFFFu, 15);
+        uint32_t h4 = ht ? (lz_hash(v, 15) << 1) : lz_hash(v, 16), h3 = lz_hash(v & 0xFFFFFFu, 15);   // level 1: 15-bit buckets (even slots)
         if (p == 0 && sb.quirk) { h4 = 0; h3 = 0; }
         const uint32_t q4 = h4 >> kBits4, q3 = h3 >> kBits3;
         const uint32_t m4 = __match_any_sync(0xFFFFFFFFu, act ? q4 : 64u);
@@ -273,7 +273,7 @@ k_split(const __grid_constant__ Geo g, uint32_t *__restrict__ lists, uint32_t *_
         const uint32_t p = t * 32 + lane;
         const bool act = p < ninsert;
         const uint32_t v = act ? ldg32u(inw, p) : 0;
-        uint32_t h4 = lz_hash(v, 16), h3 = lz_hash(v & 0xFFFFFFu, 15);
+        uint32_t h4 = ht ? (lz_hash(v, 15) << 1) : lz_hash(v, 16), h3 = lz_hash(v & 0xFFFFFFu, 15);   // level 1: 15-bit buckets (even slots)
         if (p == 0 && sb.quirk) { h4 = 0; h3 = 0; }
         const uint32_t q4 = h4 >> kBits4, q3 = h3 >> kBits3;
         const uint32_t m4 = __match_any_sync(0xFFFFFFFFu, act ? q4 : 64u);
@@ -401,7 +401,7 @@ __device__ __forceinline__ uint32_t lz_extend(const uint32_t *s_in, uint32_t p, 
 __global__ void __launch_bounds__(kMatchThreads, 1)
 k_match(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, const uint16_t *__restrict__ prev3g,
         uint64_t *__restrict__ mtab, uint32_t *__restrict__ mtab2, uint8_t *__restrict__ clen_g, uint16_t *__restrict__ order_g,
-        int depth, int nice, int lazy, int have_est)
+        int depth, int nice, int lazy, int have_est, int ht)
 {
     GZPB_DYN_SMEM(smem);
     uint32_t *s_in = (uint32_t *)smem;
@@ -491,9 +491,10 @@ k_match(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, cons
         const uint32_t nicep = min((uint32_t)nice, maxlen);
         const uint32_t seq4 = ld32u(s_in, p);
         const uint32_t w1 = ld32u(s_in, p + 4), w2 = ld32u(s_in, p + 8);   // bytes 4..11 of this position, for the inline extension
-        uint32_t d3 = p3[p];
+        // level 1 (ht_matchfinder) has no hash3 table: the parser must see "bucket usable, no 3-byte match"
+        uint32_t d3 = ht ? 1u : p3[p];
         uint32_t off3 = 0;
-        if (d3 && d3 <= 8192u && ((ld32u(s_in, p - d3) ^ seq4) & 0xFFFFFFu) == 0) off3 = d3;
+        if (!ht && d3 && d3 <= 8192u && ((ld32u(s_in, p - d3) ^ seq4) & 0xFFFFFFu) == 0) off3 = d3;
 
         uint32_t best = 3, boff = 0, lenB = 0, offB = 0, lenC = 0, offC = 0;
         bool haveB = !lazy, haveC = (lazy != 2);
@@ -814,6 +815,11 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
     uint32_t *payload = (uint32_t *)(slot + kOutPayloadOff);
     const bool sync_flush = (flags & 2u) != 0;    // Gzip/Zlib non-last and RawDeflate: no BFINAL, sync marker
     const bool final_block = !sync_flush;
+    // level 1 = deflate_compress_fastest: greedy over the depth-2 table, min match 4, no split statistics,
+    // blocks end at 65535 bytes or 8192 matches
+    const bool fast = (level == 1);
+    const uint32_t soft_max = fast ? (uint32_t)kFastSoftMaxBlockLength : (uint32_t)kSoftMaxBlockLength;
+    const uint32_t seq_limit = fast ? (uint32_t)kFastSeqStoreLength : (uint32_t)kSeqStoreLength;
 
     Parser P;
     P.mt_g = mtab + (size_t)u * g.m_stride; P.in_g = in; P.S = &S; P.n = n;
@@ -862,7 +868,7 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
             __syncthreads();
             const uint32_t bb = S.blk_begin;
             if (bb >= n) break;
-            const uint32_t max_block_end = (n - bb < (uint32_t)(kSoftMaxBlockLength + kMinBlockLength)) ? n : bb + kSoftMaxBlockLength;
+            const uint32_t max_block_end = (n - bb < soft_max + (uint32_t)kMinBlockLength) ? n : bb + soft_max;
             for (uint32_t i = tid; i < kNumLitlen; i += kEmitThreads) S.fl[i] = 0;
             if (tid < kNumOffset) S.fo[tid] = 0;
             if (tid < 10) { S.obs[tid] = 0; S.new_obs[tid] = 0; }
@@ -884,7 +890,8 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
             // change parser state (min_len recalculation, block-split checks).
             if (tid < 32) {
                 const uint32_t lane = tid;
-                if (max_block_end - bb < 512) min_len = 3;
+                if (fast) min_len = 4;
+                else if (max_block_end - bb < 512) min_len = 3;
                 else {
                     uint32_t nu = 0;
                     for (int i = 0; i < 8; i++) nu += __popc(S.used[i]);
@@ -1062,16 +1069,16 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
                     uint32_t commit_mask = vis, next_p = p + c, next_h = st_h;
                     int event = 0;   // 1 = recalc before lane Lr, 2 = block check after lane Lc, 3 = sequence store full after lane Ls
                     uint32_t mmask = __ballot_sync(0xFFFFFFFFu, onpath && ((myw >> 10) & 1));
-                    const bool may_check = (num_new_obs + 32 >= (uint32_t)kObsPerCheck) && (p + 32 + 258 - bb >= (uint32_t)kMinBlockLength) && (n - p > (uint32_t)kMinBlockLength);
+                    const bool may_check = !fast && (num_new_obs + 32 >= (uint32_t)kObsPerCheck) && (p + 32 + 258 - bb >= (uint32_t)kMinBlockLength) && (n - p > (uint32_t)kMinBlockLength);
                     const bool may_recalc = (mode != 0) && (p + 32 > next_recalc);
-                    const bool may_seq = nmatch + 32 >= (uint32_t)kSeqStoreLength;
+                    const bool may_seq = nmatch + 32 >= seq_limit;
                     if (may_check || may_recalc || may_seq) {
                         uint32_t rmask = may_recalc ? __ballot_sync(0xFFFFFFFFu, onpath && !asH && q >= next_recalc) : 0u;
-                        uint32_t cmask = __ballot_sync(0xFFFFFFFFu, onpath && ends_iter && (num_new_obs + incl >= (uint32_t)kObsPerCheck) &&
+                        uint32_t cmask = __ballot_sync(0xFFFFFFFFu, !fast && onpath && ends_iter && (num_new_obs + incl >= (uint32_t)kObsPerCheck) &&
                                                                          (e_l - bb >= (uint32_t)kMinBlockLength) && (n - e_l >= (uint32_t)kMinBlockLength));
                         // sequence store full (SEQ_STORE_LENGTH matches in this DEFLATE block): the block ends
                         const uint32_t mincl = __popc(mmask & (lane == 31 ? 0xFFFFFFFFu : ((2u << lane) - 1)));
-                        uint32_t smask = __ballot_sync(0xFFFFFFFFu, onpath && ends_iter && (nmatch + mincl >= (uint32_t)kSeqStoreLength));
+                        uint32_t smask = __ballot_sync(0xFFFFFFFFu, onpath && ends_iter && (nmatch + mincl >= seq_limit));
                         int Lr = rmask ? __ffs(rmask) - 1 : 64, Lc = cmask ? __ffs(cmask) - 1 : 64, Ls = smask ? __ffs(smask) - 1 : 64;
                         if (Lr <= Lc && Lr <= Ls && Lr < 64) { event = 1; commit_mask = vis & ((1u << Lr) - 1); next_p = p + Lr; next_h = 0; }
                         else if (Ls <= Lc && Ls < 64) { event = 3; commit_mask = vis & (Ls == 31 ? 0xFFFFFFFFu : ((2u << Ls) - 1)); next_p = __shfl_sync(0xFFFFFFFFu, e_l, Ls); next_h = 0; }
@@ -1610,16 +1617,17 @@ cudaError_t launch_deflate_pipeline(const DeflateBatch &b, cudaStream_t st)
     if (lp.mode >= 0) {
         if (b.timer) b.timer->start(KT_CHAIN, st);
         if (b.lists) {
-            GZPB_LAUNCH(k_split, b.nunits * b.spu, kSplitThreads, 0, st, g, b.lists, b.list_start, b.next4, b.prev3);
+            GZPB_LAUNCH(k_split, b.nunits * b.spu, kSplitThreads, 0, st, g, b.lists, b.list_start, b.next4, b.prev3, lp.ht);
             DBG_SYNC("k_split");
             GZPB_LAUNCH(k_link, b.nunits * b.spu * kSplitLists, 32, 0, st, g, b.lists, b.list_start, b.next4, b.prev3, b.clen);
             DBG_SYNC("k_link");
         } else {
+            if (lp.ht) return cudaErrorInvalidValue;   // the legacy k_chain path has no 15-bit mode
             GZPB_LAUNCH(k_chain, b.nunits * b.spu, kChainThreads, chain_smem, st, g, b.next4, b.prev3);
             DBG_SYNC("k_chain");
         }
         if (b.timer) { b.timer->stop(st); b.timer->start(KT_MATCH, st); }
-        GZPB_LAUNCH(k_match, b.nunits * b.spu, kMatchThreads, match_smem, st, g, b.next4, b.prev3, b.mtab, b.mtab2, b.clen, b.order, lp.depth, lp.nice, lp.mode, b.lists != nullptr);
+        GZPB_LAUNCH(k_match, b.nunits * b.spu, kMatchThreads, match_smem, st, g, b.next4, b.prev3, b.mtab, b.mtab2, b.clen, b.order, lp.depth, lp.nice, lp.mode, b.lists != nullptr, lp.ht);
         DBG_SYNC("k_match");
         if (b.timer) b.timer->stop(st);
     }

@@ -22,6 +22,8 @@ constexpr int kWindow = 32768;
 constexpr int kMinBlockLength = 5000;
 constexpr int kSoftMaxBlockLength = 300000;
 constexpr int kSeqStoreLength = 50000;
+constexpr int kFastSoftMaxBlockLength = 65535;   // level 1 (deflate_compress_fastest)
+constexpr int kFastSeqStoreLength = 8192;
 constexpr int kObsPerCheck = 512;
 
 // ---- HBM layout of one encode unit (one gzp block) ---------------------------
@@ -51,13 +53,16 @@ struct LevelParams {
     int depth;  // max_search_depth
     int nice;   // nice_match_length
     int level;
+    int ht;     // 1 = level 1: ht_matchfinder (15-bit hash4, 2-entry buckets = a depth-2 chain), fastest parser
 };
 
 __host__ __device__ inline bool level_params(int level, LevelParams *lp)
 {
     lp->level = level;
+    lp->ht = 0;
     switch (level) {
     case 0: lp->mode = -1; lp->depth = 0; lp->nice = 0; return true;
+    case 1: lp->mode = 0; lp->depth = 2; lp->nice = 32; lp->ht = 1; return true;
     case 2: lp->mode = 0; lp->depth = 6; lp->nice = 10; return true;
     case 3: lp->mode = 0; lp->depth = 12; lp->nice = 14; return true;
     case 4: lp->mode = 0; lp->depth = 16; lp->nice = 30; return true;

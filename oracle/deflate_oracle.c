@@ -631,6 +631,103 @@ static void compress_hc(comp_t *c, const uint8_t *in, size_t start, size_t n, bi
     } while (p != n && !w->overflow);
 }
 
+
+/* ---- level 1: deflate_compress_fastest() + ht_matchfinder restated ---------------------------
+ * Hash table of 2-entry buckets keyed by a 15-bit hash of 4 bytes (HT_MATCHFINDER_HASH_ORDER 15,
+ * BUCKET_SIZE 2, MIN_MATCH_LEN 4, REQUIRED_NBYTES 5); every position is inserted (searched ones by
+ * longest_match, skipped ones by skip_bytes), position 0 under hash 0 because next_hash starts at 0.
+ * Greedy parse, nice_match_length 32, no min_len heuristics, no split statistics; a block ends at
+ * FAST_SOFT_MAX_BLOCK_LENGTH (65535) bytes or FAST_SEQ_STORE_LENGTH (8192) matches. */
+#define FAST_SOFT_MAX_BLOCK_LENGTH 65535
+#define FAST_SEQ_STORE_LENGTH 8192
+#define HT_ORDER 15
+
+static unsigned ht_longest_match(int32_t (*tab)[2], const uint8_t *in, size_t p, unsigned max_len, unsigned nice_len,
+                                 uint32_t *next_hash, unsigned *off_ret)
+{
+    unsigned best_len = 0;
+    size_t best_q = p;
+    uint32_t hash = *next_hash;
+    *next_hash = lz_hash(ld32(in + p + 1), HT_ORDER);
+    uint32_t seq = ld32(in + p);
+    int32_t cur = tab[hash][0];
+    tab[hash][0] = (int32_t)p;
+    if (!INWIN(cur)) goto out;
+    {
+        int32_t to_insert = cur;
+        int32_t second = tab[hash][1];
+        tab[hash][1] = to_insert;
+        if (ld32(in + cur) == seq) {
+            best_len = lz_extend(in + p, in + cur, 4, max_len);
+            best_q = (size_t)cur;
+            if (!INWIN(second) || best_len >= nice_len) goto out;
+            if (ld32(in + second) == seq && ld32(in + second + best_len - 3) == ld32(in + p + best_len - 3)) {
+                unsigned len = lz_extend(in + p, in + second, 4, max_len);
+                if (len > best_len) { best_len = len; best_q = (size_t)second; }
+            }
+        } else {
+            if (!INWIN(second)) goto out;
+            if (ld32(in + second) == seq) { best_len = lz_extend(in + p, in + second, 4, max_len); best_q = (size_t)second; }
+        }
+    }
+out:
+    *off_ret = (unsigned)(p - best_q);
+    return best_len;
+}
+
+static void ht_skip_bytes(int32_t (*tab)[2], const uint8_t *in, size_t n, size_t p, unsigned count, uint32_t *next_hash)
+{
+    if ((size_t)count + 5 > n - p) return;
+    uint32_t hash = *next_hash;
+    do {
+        tab[hash][1] = tab[hash][0];
+        tab[hash][0] = (int32_t)p;
+        p++;
+        hash = lz_hash(ld32(in + p), HT_ORDER);
+    } while (--count);
+    *next_hash = hash;
+}
+
+static void compress_fastest(comp_t *c, const uint8_t *in, size_t start, size_t n, bitw_t *w, int final_block)
+{
+    int32_t (*tab)[2] = (int32_t (*)[2])c->head4;     /* 32768 buckets x 2 = the 65536-entry scratch */
+    uint32_t next_hash = 0;
+    size_t p = start;
+    unsigned max_len = MAX_MATCH, nice_len = c->nice < MAX_MATCH ? c->nice : MAX_MATCH;
+    for (size_t i = 0; i < 32768; i++) tab[i][0] = tab[i][1] = -1;
+    if (start) {
+        next_hash = lz_hash(ld32(in), HT_ORDER);
+        ht_skip_bytes(tab, in, n, 0, (unsigned)start, &next_hash);
+        if ((size_t)start + 5 > n) next_hash = 0;
+    }
+    do {
+        const size_t block_begin = p;
+        const size_t max_block_end = (n - p < FAST_SOFT_MAX_BLOCK_LENGTH + MIN_BLOCK_LENGTH) ? n : p + FAST_SOFT_MAX_BLOCK_LENGTH;
+        begin_block(c);
+        do {
+            size_t remaining = n - p;
+            unsigned length, offset;
+            if (remaining < MAX_MATCH) {
+                max_len = (unsigned)remaining;
+                if (max_len < 5) {
+                    do { choose_literal(c, in[p++]); } while (--max_len);
+                    break;
+                }
+                if (nice_len > max_len) nice_len = max_len;
+            }
+            length = ht_longest_match(tab, in, p, max_len, nice_len, &next_hash, &offset);
+            if (length) {
+                choose_match(c, length, offset);
+                ht_skip_bytes(tab, in, n, p + 1, length - 1, &next_hash);
+                p += length;
+            } else {
+                choose_literal(c, in[p++]);
+            }
+        } while (p < max_block_end && c->nmatch < FAST_SEQ_STORE_LENGTH);
+        finish_block(c, w, in, block_begin, p - block_begin, final_block && p == n);
+    } while (p != n && !w->overflow);
+}
+
 static void compress_none(const uint8_t *in, size_t n, bitw_t *w, int final_block)
 {
     size_t pos = 0;
@@ -648,6 +745,7 @@ static void compress_none(const uint8_t *in, size_t n, bitw_t *w, int final_bloc
 static int level_params(int level, unsigned *depth, unsigned *nice, int *mode)
 {
     switch (level) {
+    case 1: *mode = 3; *depth = 2; *nice = 32; return 0;    /* deflate_compress_fastest (ht_matchfinder) */
     case 2: *mode = 0; *depth = 6; *nice = 10; return 0;
     case 3: *mode = 0; *depth = 12; *nice = 14; return 0;
     case 4: *mode = 0; *depth = 16; *nice = 30; return 0;
@@ -701,7 +799,8 @@ size_t oracle_deflate_ex(const uint8_t *in, size_t dict_len, size_t n, int level
         }
         c.head3 = t_head3; c.head4 = t_head4; c.next = t_next; c.tokens = t_tokens;
         init_static(&c);
-        compress_hc(&c, in, dict_len, tot, &w, final_block);
+        if (c.mode == 3) compress_fastest(&c, in, dict_len, tot, &w, final_block);
+        else compress_hc(&c, in, dict_len, tot, &w, final_block);
     }
     if (flush == 1) {
         /* Z_SYNC_FLUSH marker: empty stored block, byte aligned: 00 00 ff ff */

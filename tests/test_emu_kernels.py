@@ -31,7 +31,7 @@ def _run(fmt, level, bs, data):
     return got
 
 
-@pytest.mark.parametrize("level", [0, 2, 3, 4, 5, 6, 7, 8, 9])
+@pytest.mark.parametrize("level", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9])
 def test_emu_bgzf_levels(level):
     got = _run(oracle.BGZF, level, 0, TEXT[:140000])
     assert gzip.decompress(got) == TEXT[:140000]
@@ -57,6 +57,16 @@ def test_emu_dictionary_formats():
     assert zlib.decompress(_run(oracle.ZLIB, 4, 40000, TEXT[:130000])) == TEXT[:130000]
     raw = _run(oracle.RAWDEFLATE, 6, 32768, TEXT[:100000])
     assert zlib.decompressobj(-15).decompress(raw) == TEXT[:100000]
+
+
+def test_emu_level1_fastest_all_formats():
+    """Level 1 = deflate_compress_fastest (ht_matchfinder): 15-bit buckets, depth-2 chains, 65535-byte /
+    8192-match DEFLATE blocks — long units, dictionary carry and the passthrough threshold (51 bytes)."""
+    for d in (TEXT[:51], TEXT[:52], synth.fastq(120000), bytes(70000)):
+        assert gzip.decompress(_run(oracle.BGZF, 1, 0, d)) == d
+    assert gzip.decompress(_run(oracle.MGZIP, 1, 131072, TEXT)) == TEXT
+    assert gzip.decompress(_run(oracle.GZIP, 1, 131072, TEXT)) == TEXT
+    assert zlib.decompress(_run(oracle.ZLIB, 1, 40000, TEXT[:130000])) == TEXT[:130000]
 
 
 def test_emu_snap():

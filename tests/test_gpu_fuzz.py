@@ -57,6 +57,21 @@ def test_random_streams_all_formats(text_corpus, seed):
         ctx.close()
 
 
+def test_random_streams_level1(text_corpus):
+    """Level 1 (ht_matchfinder / fastest parser) over random formats, buffer sizes and inputs."""
+    rnd = random.Random(101)
+    for _ in range(8):
+        fmt = rnd.choice([BGZF, MGZIP, GZIP, ZLIB, RAWDEFLATE])
+        bs = rnd.randrange(32768, 65280) if fmt == BGZF else rnd.randrange(32768, 300000)
+        n = rnd.randrange(0, 400000)
+        data = _gen(rnd, n, text_corpus)[:n]
+        ctx = gzp_b200.Context(fmt, 1, max_block_bytes=bs, max_blocks_in_flight=rnd.choice([1, 3, 8]))
+        got = ctx.encode_stream(data, bs)
+        want = oracle.compress_stream(fmt, 1, bs, [data])
+        assert got == want, f"fmt {fmt} bs {bs} n {n}"
+        ctx.close()
+
+
 def test_parcompress_mirror_on_gpu_random_writes(text_corpus):
     import io
     rnd = random.Random(77)

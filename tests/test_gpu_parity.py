@@ -25,7 +25,7 @@ def _edge_blocks():
     return blocks
 
 
-@pytest.mark.parametrize("level", [6, 2, 3, 4, 5, 7, 0])
+@pytest.mark.parametrize("level", [6, 2, 3, 4, 5, 7, 0, 1])
 def test_bgzf_blocks_bit_exact(text_corpus, level):
     ctx = gzp_b200.Context(BGZF, level, max_blocks_in_flight=64)
     blocks = [text_corpus[i:i + 65280] for i in range(0, 20 * 65280, 65280)] if level == 6 else \
