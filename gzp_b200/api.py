@@ -12,6 +12,7 @@ final is_last block, the 32 KiB dictionary rule); the worker pool is replaced by
 device batches handed to gzpb_encode_batch.
 """
 import ctypes as C
+import os
 
 from . import _lib
 from ._lib import BGZF, GZIP, MGZIP, RAWDEFLATE, SNAP, ZLIB, BlockIn, BlockOut
@@ -388,6 +389,7 @@ class ZBuilder:
 
     def __init__(self, fmt=Gzip):
         self._b = ParCompressBuilder(fmt)
+        self._threads = os.cpu_count() or 1     # num_cpus::get() (lib.rs:199)
 
     @classmethod
     def new(cls, fmt=Gzip):
@@ -402,6 +404,7 @@ class ZBuilder:
         return self
 
     def num_threads(self, n):
+        self._threads = int(n)
         self._b._num_threads = int(n)
         return self
 
@@ -410,9 +413,148 @@ class ZBuilder:
         return self
 
     def from_writer(self, writer):
-        if self._b._buffer_size < DICT_SIZE:
-            raise GzpError(-1, f"Invalid buffer size ({self._b._buffer_size}), must be >= {DICT_SIZE}")
-        return self._b.from_writer(writer)
+        # lib.rs:242-264: more than one thread -> ParCompress, otherwise the synchronous writer
+        # (quirk 8 of SURVEY App. D: num_threads == 1 goes to SyncZ, not to a 1-worker ParCompress)
+        if self._threads > 1:
+            if self._b._buffer_size < DICT_SIZE:
+                raise GzpError(-1, f"Invalid buffer size ({self._b._buffer_size}), must be >= {DICT_SIZE}")
+            return self._b.from_writer(writer)
+        return SyncZBuilder(self._b.format).compression_level(self._b._level).device(self._b._device).from_writer(writer)
+
+
+BGZF_EOF = bytes([0x1f, 0x8b, 0x08, 0x04, 0, 0, 0, 0, 0, 0xff, 0x06, 0, 0x42, 0x43, 0x02, 0, 0x1b, 0, 0x03, 0, 0, 0, 0, 0, 0, 0, 0, 0])  # bgzf.rs:24-38
+
+
+class _BlockSyncWriter:
+    """BgzfSyncWriter / MgzipSyncWriter (bgzf.rs:92-145, 315-355; mgzip.rs:74-125, 286-325): the single-threaded
+    block writers behind SyncZ.  Every block goes through the same per-block encode path (`compress`,
+    bgzf.rs:204-237 / mgzip.rs:187-218) — here one unit on the GPU.  The reference's quirks are kept:
+    `write` emits at most ONE block per call, and only once `blocksize` bytes are buffered."""
+
+    FORMAT = None
+
+    def __init__(self, writer, level, blocksize, device=0):
+        self.writer = writer
+        self.level = level
+        self.blocksize = int(blocksize)
+        self._buf = bytearray()
+        self._ctx = None
+        self._device = device
+
+    def _compress(self, block):
+        if self._ctx is None:
+            self._ctx = Context(self.FORMAT, self.level, self._device, max(self.blocksize, DICT_SIZE), 4)
+        return self._ctx.encode_blocks([(bytes(block), None, False)])[0][0]
+
+    def write(self, data):
+        self._buf.extend(data)
+        if len(self._buf) >= self.blocksize:                    # `if`, not `while` (bgzf.rs:322, mgzip.rs:293)
+            b = bytes(self._buf[:self.blocksize])
+            del self._buf[:self.blocksize]
+            self.writer.write(self._compress(b))
+        return len(data)
+
+    def finish(self):
+        self.flush()
+        if self._ctx is not None:
+            self._ctx.close()
+            self._ctx = None
+        return self.writer
+
+
+class BgzfSyncWriter(_BlockSyncWriter):
+    FORMAT = BGZF
+
+    def __init__(self, writer, level, blocksize=65280, device=0):
+        assert blocksize <= 65280                               # bgzf.rs:124
+        super().__init__(writer, level, blocksize, device)
+
+    def flush(self):
+        # BGZF_EOF after EVERY remaining block, none when nothing is buffered (bgzf.rs:334-343; App. D quirk 3)
+        while self._buf:
+            k = min(len(self._buf), 65280)
+            b = bytes(self._buf[:k])
+            del self._buf[:k]
+            self.writer.write(self._compress(b))
+            self.writer.write(BGZF_EOF)
+        if hasattr(self.writer, "flush"):
+            self.writer.flush()
+
+
+class MgzipSyncWriter(_BlockSyncWriter):
+    FORMAT = MGZIP
+
+    def __init__(self, writer, level, blocksize=BUFSIZE, device=0):
+        super().__init__(writer, level, blocksize, device)
+
+    def _compress(self, block):
+        if self._ctx is None or len(block) > self._ctx_cap:     # flush() sends everything buffered as one block (mgzip.rs:309-315)
+            if self._ctx is not None:
+                self._ctx.close()
+            self._ctx_cap = max(len(block), self.blocksize, DICT_SIZE)
+            self._ctx = Context(self.FORMAT, self.level, self._device, self._ctx_cap, 4)
+        return self._ctx.encode_blocks([(bytes(block), None, False)])[0][0]
+
+    def flush(self):
+        if self._buf:
+            b = bytes(self._buf)
+            self._buf.clear()
+            self.writer.write(self._compress(b))
+        if hasattr(self.writer, "flush"):
+            self.writer.flush()
+
+
+class SyncZ:
+    """SyncZ<W> (syncz.rs:59-87): `write` / `flush` / `finish` over the format's synchronous writer."""
+
+    def __init__(self, inner):
+        self.inner = inner
+
+    @staticmethod
+    def builder(fmt=Gzip):
+        return SyncZBuilder(fmt)
+
+    def write(self, data):
+        return self.inner.write(data)
+
+    def flush(self):
+        return self.inner.flush()
+
+    def finish(self):
+        inner, self.inner = self.inner, None
+        return inner.finish()
+
+
+class SyncZBuilder:
+    """SyncZBuilder<F, W> (syncz.rs:12-57).  Bgzf / Mgzip get their block sync writers.  For Gzip / Zlib /
+    RawDeflate the reference wraps flate2's streaming encoders (deflate.rs:145-154, 255-264, 334-343) — one
+    continuous zlib-ng stream; this engine has no such single-stream encoder, so those formats are served by a
+    ParCompress with the format's default block size: same container, decodable by the same readers, not the
+    same bytes as flate2's stream."""
+
+    def __init__(self, fmt=Gzip):
+        self.format = fmt() if isinstance(fmt, type) else fmt
+        self._level = Compression.new(3)                          # syncz.rs:32
+        self._device = 0
+
+    @classmethod
+    def new(cls, fmt=Gzip):
+        return cls(fmt)
+
+    def compression_level(self, level):
+        self._level = level if isinstance(level, Compression) else Compression.new(level)
+        return self
+
+    def device(self, index):
+        self._device = int(index)
+        return self
+
+    def from_writer(self, writer):
+        if self.format.ID == BGZF:
+            return SyncZ(BgzfSyncWriter(writer, self._level, device=self._device))
+        if self.format.ID == MGZIP:
+            return SyncZ(MgzipSyncWriter(writer, self._level, device=self._device))
+        return SyncZ(ParCompress(self.format, writer, self._level, self.format.DEFAULT_BUFSIZE, self._device, 16))
 
 
 def bgzf_index(stream):

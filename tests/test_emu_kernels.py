@@ -198,3 +198,44 @@ def test_emu_pardecompress_mirror(emu_backend):
         gzp_b200.ParDecompressBuilder(gzp_b200.Bgzf).num_threads(0)
     with pytest.raises(gzp_b200.GzpError):
         gzp_b200.ParDecompressBuilder(gzp_b200.Bgzf).buffer_size(100)
+
+
+def test_emu_syncz_block_writers_keep_the_reference_quirks(emu_backend):
+    """BgzfSyncWriter / MgzipSyncWriter behind SyncZ / ZBuilder(num_threads <= 1): one block per write() call
+    at most, BGZF_EOF after every block flushed, nothing for an empty flush."""
+    import gzp_b200
+    data = TEXT[:200000]
+
+    def model(fmt, writes, blocksize, level):
+        """Pure-Python restatement on top of the oracle's per-block encoder."""
+        out, buf = bytearray(), bytearray()
+        for w in writes:
+            buf.extend(w)
+            if len(buf) >= blocksize:
+                out += oracle.encode_block(fmt, level, bytes(buf[:blocksize]), None, False)
+                del buf[:blocksize]
+        if fmt == oracle.BGZF:
+            while buf:
+                k = min(len(buf), 65280)
+                out += oracle.encode_block(fmt, level, bytes(buf[:k]), None, False) + gzp_b200.BGZF_EOF
+                del buf[:k]
+        elif buf:
+            out += oracle.encode_block(fmt, level, bytes(buf), None, False)
+        return bytes(out)
+
+    writes = [data[i:i + 50000] for i in range(0, len(data), 50000)]
+    for fmt, F, bs in ((oracle.BGZF, gzp_b200.Bgzf, 65280), (oracle.MGZIP, gzp_b200.Mgzip, 131072)):
+        sink = io.BytesIO()
+        z = gzp_b200.ZBuilder(F).num_threads(1).compression_level(4).from_writer(sink)
+        assert isinstance(z, gzp_b200.SyncZ)
+        for w in writes:
+            z.write(w)
+        z.finish()
+        assert sink.getvalue() == model(fmt, writes, bs, 4)
+        assert gzip.decompress(sink.getvalue()) == data
+    # an empty BGZF sync stream is empty: no EOF marker at all
+    sink = io.BytesIO()
+    gzp_b200.SyncZBuilder(gzp_b200.Bgzf).from_writer(sink).finish()
+    assert sink.getvalue() == b""
+    # more than one thread -> ParCompress (lib.rs:246)
+    assert isinstance(gzp_b200.ZBuilder(gzp_b200.Bgzf).num_threads(4).from_writer(io.BytesIO()), gzp_b200.ParCompress)
