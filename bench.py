@@ -6,9 +6,10 @@ Metric (BASELINE.json): compressed GiB/s of INPUT bytes, ParCompress<Bgzf> level
 shakespeare.txt x N (period 5 465 394 B; the reference corpus itself does not
 travel to the GPU box, see gzp_b200/synth.py).
 
-A "step" = one pass of the hot path over one batch of `--blocks` consecutive
-blocks of that stream (a different window of the stream every step, each batch
-larger than L2).  Per JSON line:
+A "step" = one pass of the hot path over `--blocks` consecutive blocks of that
+stream (default 16 280 blocks = 1.06 GB = five device batches of `--inflight`
+3 256 blocks, i.e. one full wave of k_emit CTAs on 148 SMs; a different window of
+the stream every step, each step far larger than L2).  Per JSON line:
   value      device-resident throughput: inputs already in HBM (unit layout),
              gzpb_encode_device on the launching stream, CUDA-event timed.
   e2e        the same batches through the reference-facing C-ABI call
@@ -36,6 +37,7 @@ BLOCK = 65280
 LEVEL = 6
 METRIC = "bgzf_l6_compress_input_throughput"
 UNIT = "GiB/s"
+WORKLOAD = "ParCompress<Bgzf> level 6, 65280-B blocks, synthetic text stream (period 5465394 B; BASELINE configs[1] shape)"
 GIB = float(1 << 30)
 # k_match algorithmic HBM bytes per input byte: input 1 + next4 2 + prev3 2 read, match table 8 written
 MATCH_BYTES_PER_INPUT_BYTE = 13.0
@@ -45,13 +47,22 @@ MATCH_BYTES_PER_INPUT_BYTE = 13.0
 MATCH_TRAFFIC_PER_INPUT_BYTE = 4.815e9 / (2368 * 65280)
 
 
+_T0 = time.perf_counter()
+
+
+def log(msg):
+    """Stage progress on stderr (stdout carries only the JSON line)."""
+    print("[bench %7.2fs] %s" % (time.perf_counter() - _T0, msg), file=sys.stderr, flush=True)
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--blocks", type=int, default=4096, help="gzp blocks per step and GPU")
+    ap.add_argument("--blocks", type=int, default=16280, help="gzp blocks per step and GPU (default: 5 device batches, 1.06 GB)")
+    ap.add_argument("--inflight", type=int, default=3256, help="blocks per device batch = 148 SMs x 22 resident k_emit CTAs")
     ap.add_argument("--cpu-sample-mb", type=float, default=0.0, help="override the CPU baseline sample size")
     return ap.parse_args()
 
@@ -165,7 +176,7 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": f"ParCompress<Bgzf> level {LEVEL}, {BLOCK}-B blocks, synthetic text stream (period 5465394 B)",
+            "config": {"workload": WORKLOAD,
                        "sample_blocks_per_step": nblocks, "host_threads": threads},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": f"{nblocks} blocks ({nbytes} B) per step: oracle port of gzp's ParCompress topology + libdeflate-style L6 (reference not buildable here: no Rust toolchain)"},
@@ -182,6 +193,11 @@ def main():
         run_reference(args, rank, world)
         return
 
+    import faulthandler
+    faulthandler.enable()
+    if os.environ.get("GZPB_BENCH_WATCHDOG"):
+        faulthandler.dump_traceback_later(int(os.environ["GZPB_BENCH_WATCHDOG"]), repeat=True)
+    log("importing torch")
     import torch
     import torch.distributed as dist
     import gzp_b200
@@ -194,6 +210,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    log("cuda ready")
     L = _lib.load()
     nblk = args.blocks
     step_bytes = nblk * BLOCK
@@ -202,7 +219,9 @@ def main():
     stream = synth.text_stream(step_bytes + nwin * shift + rank * 131 * BLOCK)
     base_off = rank * 131 * BLOCK                        # every rank compresses a different part of the stream
 
-    ctx = gzp_b200.Context(gzp_b200.BGZF, LEVEL, device=local_rank, max_block_bytes=BLOCK, max_blocks_in_flight=min(nblk, 2048))
+    log("stream synthesised (%d B)" % len(stream))
+    ctx = gzp_b200.Context(gzp_b200.BGZF, LEVEL, device=local_rank, max_block_bytes=BLOCK, max_blocks_in_flight=min(nblk, args.inflight))
+    log("context created")
 
     # ---------------- device-resident arm ----------------
     host_all = torch.frombuffer(bytearray(stream), dtype=torch.uint8)
@@ -230,9 +249,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    log("device inputs staged; warm-up")
     for i in range(args.warmup):
         dev_step(i)
     torch.cuda.synchronize()
+    log("device warm-up done")
     assert int(d_status.abs().max().item()) == 0
     out_bytes_dev = int(d_off[nblk].item())
 
@@ -249,6 +270,7 @@ def main():
     barrier()
     clocks = sampler.stop()
     dev_ms = e0.elapsed_time(e1)
+    log("device arm timed: %.1f ms for %d steps" % (dev_ms, args.steps))
     launches = ctx.launch_count() - launches0
     kms = {k: ctx.kernel_ms(k) for k in ("chain", "match", "emit", "gather")}
     ctx.set_profiling(False)
@@ -269,25 +291,32 @@ def main():
         if rc != 0:
             raise RuntimeError("gzpb_encode_stream: " + L.gzpb_strerror(rc).decode())
 
+    log("e2e buffers pinned; warm-up")
     for i in range(args.warmup):
         e2e_step(i)
     barrier()
+    log("e2e warm-up done")
     t0 = time.perf_counter()
     for i in range(args.steps):
         e2e_step(args.warmup + i)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    log("e2e arm timed: %.1f ms for %d steps" % (e2e_s * 1e3, args.steps))
     out_bytes = olen.value
     if world > 1:
         t = torch.tensor([e2e_s], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); e2e_s = float(t.item())
 
-    # correctness spot check of what was timed: the e2e stream of the last step decodes to its input
+    # correctness check of what was timed: the e2e stream of the last step decodes to its input with the stock
+    # zlib decoder (streamed member by member: gzip.decompress() re-copies the tail for every member, which is
+    # quadratic over thousands of BGZF members)
     if rank == 0:
-        import gzip
+        import gzip, io
         last = (args.warmup + args.steps - 1) % nwin
-        got = gzip.decompress(C.string_at(h_out, out_bytes))
         want = stream[base_off + last * shift: base_off + last * shift + step_bytes]
+        got = gzip.GzipFile(fileobj=io.BytesIO(C.string_at(h_out, out_bytes))).read()
         assert got == want, "e2e output does not decode to the input"
+        del got, want
+        log("e2e output verified with the stock gzip decoder")
 
     total_in = step_bytes * args.steps * world
     value = total_in / (dev_ms / 1e3) / GIB
@@ -301,15 +330,17 @@ def main():
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        per_launch_bytes = MATCH_BYTES_PER_INPUT_BYTE * BLOCK * min(nblk, 2048)
+        per_launch_bytes = MATCH_BYTES_PER_INPUT_BYTE * BLOCK * min(nblk, args.inflight)
         achieved = per_launch_bytes / (match_ms / max(match_n, 1) / 1e3) / 1e9 if match_n else 0.0
+        log("timing the CPU baseline")
         cpu, _ = cpu_baseline(stream, host_threads(), args.cpu_sample_mb)
+        log("cpu baseline done")
         share = {k: round(v[0] / max(sum(x[0] for x in kms.values()), 1e-9), 4) for k, v in kms.items()}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
-            "config": {"workload": f"ParCompress<Bgzf> level {LEVEL}, {BLOCK}-B blocks, synthetic text stream (period 5465394 B; BASELINE configs[1] shape)",
+            "config": {"workload": WORKLOAD,
                        "blocks_per_step_per_gpu": nblk, "bytes_per_step_per_gpu": step_bytes, "ratio": out_bytes_dev / step_bytes,
                        "l2": "each step's input (%.0f MB) exceeds L2 and rotates over %d stream windows" % (step_bytes / 1e6, nwin),
                        "parallelism": f"independent blocks sharded over {world} GPU(s), no data collective"},
@@ -318,7 +349,7 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_match", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": MATCH_TRAFFIC_PER_INPUT_BYTE * BLOCK * min(nblk, 2048) / 1e9, "traffic_unit": "GB per launch (ncu dram__bytes_read+write, profiles/r1_final_ncu_full_summary.txt)",
+                         "frac": achieved / peak, "traffic": MATCH_TRAFFIC_PER_INPUT_BYTE * BLOCK * min(nblk, args.inflight) / 1e9, "traffic_unit": "GB per launch (ncu dram__bytes_read+write, profiles/r1_final_ncu_full_summary.txt)",
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650 GB/s",
                          "note": "k_match is instruction-issue bound (ncu: 64 % issue-active, 7.5 % of DRAM peak; profiles/), not HBM bound; algorithmic bytes = 13 B per input byte",
                          "kernel_ms_per_launch": {k: v[0] / max(v[1], 1) for k, v in kms.items()}, "kernel_time_share": share},

@@ -580,7 +580,7 @@ class Decoder:
     """One device decoder = the per-worker `Decompressor` of the reference
     (BlockFormatSpec::create_decompressor, deflate.rs:372-381, 521-530), for a whole GPU."""
 
-    def __init__(self, fmt, device=0, max_blocks_in_flight=2048):
+    def __init__(self, fmt, device=0, max_blocks_in_flight=5328):
         self._lib = _lib.load()
         self.fmt = fmt.ID if isinstance(fmt, _Format) or (isinstance(fmt, type) and issubclass(fmt, _Format)) else int(fmt)
         h = C.c_void_p()
@@ -643,7 +643,7 @@ class ParDecompressBuilder:
         self._num_threads = 1
         self._pin = None
         self._device = 0
-        self._blocks_in_flight = 2048
+        self._blocks_in_flight = 5328
 
     @classmethod
     def new(cls, fmt=Bgzf):
@@ -693,7 +693,7 @@ class ParDecompress:
 
     _CHUNK = 8 << 20
 
-    def __init__(self, fmt, reader, buffer_size=BUFSIZE, device=0, blocks_in_flight=2048):
+    def __init__(self, fmt, reader, buffer_size=BUFSIZE, device=0, blocks_in_flight=5328):
         self.format = fmt
         self.reader = reader
         self.buffer_size = buffer_size

@@ -136,7 +136,7 @@ extern "C" int gzpb_decoder_create(gzpb_decoder **out, int device, int format, s
     if (!out) return GZPB_EINVAL;
     *out = nullptr;
     if (format != GZPB_BGZF && format != GZPB_MGZIP) return GZPB_EINVAL;   // BlockFormatSpec is implemented for these two (deflate.rs:359, 508)
-    if (max_blocks_in_flight == 0) max_blocks_in_flight = 2048;
+    if (max_blocks_in_flight == 0) max_blocks_in_flight = 5328;   // 148 SMs x 36 resident decode warps
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return GZPB_ECUDA;
     DCK(cudaSetDevice(device));

@@ -17,7 +17,7 @@ from gzp_b200 import _lib, synth
 
 L = _lib.load()
 GIB = float(1 << 30)
-nblk = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+nblk = int(sys.argv[1]) if len(sys.argv) > 1 else 10656
 level = int(sys.argv[2]) if len(sys.argv) > 2 else 6
 steps = 5
 data = synth.text_stream(65280 * nblk)
@@ -26,7 +26,7 @@ comp = ctx.encode_stream(data)
 ctx.close()
 n, clen = len(data), len(comp)
 
-dec = gzp_b200.Decoder(gzp_b200.BGZF, max_blocks_in_flight=max(nblk + 1, 16))
+dec = gzp_b200.Decoder(gzp_b200.BGZF, max_blocks_in_flight=5328)
 nb = C.c_size_t(0); total = C.c_uint64(0)
 L.gzpb_scan_blocks(gzp_b200.BGZF, comp, clen, None, 0, C.byref(nb), None, C.byref(total))
 descs = (_lib.BlockDesc * nb.value)()
@@ -45,9 +45,11 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
 
 def dev_step():
-    rc = L.gzpb_decode_device(dec._h, d_comp.data_ptr(), d_desc.data_ptr(), nb.value, d_out.data_ptr(), d_status.data_ptr(),
-                              d_crc.data_ptr(), st.cuda_stream)
-    assert rc == 0
+    for b0 in range(0, nb.value, 5328):          # one launch per 5328 members = 148 SMs x 36 resident warps
+        k = min(5328, nb.value - b0)
+        rc = L.gzpb_decode_device(dec._h, d_comp.data_ptr(), d_desc.data_ptr() + 32 * b0, k, d_out.data_ptr(), d_status.data_ptr() + 4 * b0,
+                                  d_crc.data_ptr() + 4 * b0, st.cuda_stream)
+        assert rc == 0
 
 
 for _ in range(3):
@@ -87,7 +89,7 @@ for i in range(sample_blocks):
     zlib.decompressobj(-15).decompress(comp[descs[i].in_off:descs[i].in_off + descs[i].in_len])
 t_z = time.perf_counter() - t0
 line = {"metric": "bgzf_decode_output_throughput", "unit": "GiB/s", "blocks": nb.value, "level": level, "bytes_out": n, "ratio": clen / n,
-        "device": {"value": n / (dev_ms / 1e3) / GIB, "ms_per_launch": dev_ms, "l2": "256 MiB flush between iterations",
+        "device": {"value": n / (dev_ms / 1e3) / GIB, "ms_per_pass": dev_ms, "l2": "256 MiB flush between iterations",
                    "algorithmic_bytes": clen + 2 * n, "hbm_gbs": (clen + 2 * n) / (dev_ms / 1e3) / 1e9},
         "e2e": {"value": n / best / GIB, "api": "gzpb_decode_stream (pinned host in/out)", "h2d_bytes": clen, "d2h_bytes": n},
         "cpu_one_core": {"oracle_inflate": len(out) / t_or / GIB, "zlib_inflate": len(out) / t_z / GIB, "sample_blocks": sample_blocks}}
