@@ -91,7 +91,7 @@ __device__ __forceinline__ uint32_t ld32u(const uint32_t *words, uint32_t byte_p
 #define GZPB_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #define GZPB_DYN_SMEM(name) extern __shared__ __align__(128) uint8_t name[]
 #else
-#define GZPB_LAUNCH(kernel, grid, block, smem, stream, ...) gzpb_emu::launch(dim3(grid), dim3(block), (smem), [&]() { kernel(__VA_ARGS__); })
+#define GZPB_LAUNCH(kernel, grid, block, smem, stream, ...) gzpb_emu::launch_async((void *)(stream), dim3(grid), dim3(block), (smem), [=]() { kernel(__VA_ARGS__); })
 #define GZPB_DYN_SMEM(name) uint8_t *name = gzpb_emu::dyn_smem()
 #endif
 

@@ -228,44 +228,138 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> &bod
 }  // namespace gzpb_emu
 
 // ---- CUDA runtime subset: host memory stands in for device memory ------------------
+//
+// Streams are LAZY by default: every asynchronous call (cudaMemcpyAsync between device and pinned
+// memory, cudaMemsetAsync, kernel launch, event record / wait) is queued on its stream and executed
+// only when the host synchronises with it (cudaEventSynchronize, cudaStreamSynchronize,
+// cudaDeviceSynchronize, cudaFree*, a blocking copy) — and then only as far as that synchronisation
+// requires.  Host code that reuses a pinned source before its copy ran, or reads a result before
+// waiting for it, therefore produces wrong bytes here just as it would (sometimes) on a GPU.
+// GZPB_EMU_EAGER=1 restores immediate execution; GZPB_EMU_DEVICES=n exposes n devices.
+#include <deque>
+#include <set>
+
 namespace {
-std::map<uintptr_t, size_t> g_pinned;
+std::map<uintptr_t, size_t> g_pinned, g_device;
 struct Fill { static void garbage(void *p, size_t n) { memset(p, 0xA5, n); } };
+int g_cur_device = 0;
+bool env_flag(const char *name) { const char *v = getenv(name); return v && *v && *v != '0'; }
+int env_devices() { const char *v = getenv("GZPB_EMU_DEVICES"); int n = v ? atoi(v) : 1; return n < 1 ? 1 : n > 16 ? 16 : n; }
+bool lazy() { static const bool l = !env_flag("GZPB_EMU_EAGER"); return l; }
+bool in_map(const std::map<uintptr_t, size_t> &m, const void *p)
+{
+    auto it = m.upper_bound((uintptr_t)p);
+    if (it == m.begin()) return false;
+    --it;
+    return (uintptr_t)p < it->first + it->second;
+}
+bool pageable(const void *p) { return !in_map(g_pinned, p) && !in_map(g_device, p); }
+}  // namespace
+
+struct emu_event { uint64_t recorded = 0, completed = 0; emu_stream *last = nullptr; int device = 0; };
+struct emu_op { int kind; std::function<void()> fn; emu_event *ev; uint64_t target; };   // 0 work, 1 record, 2 wait
+struct emu_stream { std::deque<emu_op> q; int device = 0; };
+
+namespace {
+std::set<emu_stream *> g_streams;
+unsigned long long g_deferred = 0;
+emu_stream *legacy_stream()
+{
+    static emu_stream *s = nullptr;
+    if (!s) { s = new emu_stream(); g_streams.insert(s); }
+    return s;
+}
+emu_stream *S(cudaStream_t s) { return s ? s : legacy_stream(); }
+
+void complete_event(emu_event *e, uint64_t target, int depth);
+
+// executes the head op of `s`; a wait first forces the awaited record (on whichever stream holds it)
+void step(emu_stream *s, int depth)
+{
+    if (depth > 64) gzpb_emu::trap("emulated streams: event wait cycle");
+    emu_op op = std::move(s->q.front());
+    s->q.pop_front();
+    if (op.kind == 0) op.fn();
+    else if (op.kind == 1) { if (op.ev->completed < op.target) op.ev->completed = op.target; }
+    else complete_event(op.ev, op.target, depth + 1);
 }
 
-struct emu_stream { int id; };
-struct emu_event { int id; };
+void complete_event(emu_event *e, uint64_t target, int depth)
+{
+    while (e->completed < target) {
+        emu_stream *s = e->last;
+        if (!s || s->q.empty()) gzpb_emu::trap("emulated streams: waiting for an event whose record is not queued anywhere");
+        step(s, depth);
+    }
+}
+
+void drain(emu_stream *s) { while (!s->q.empty()) step(s, 0); }
+void drain_all() { for (emu_stream *s : g_streams) drain(s); }
+
+void enqueue(cudaStream_t st, std::function<void()> fn)
+{
+    if (!lazy()) { fn(); return; }
+    g_deferred++;
+    S(st)->q.push_back(emu_op{0, std::move(fn), nullptr, 0});
+}
+}  // namespace
+
+// test hook: how many operations were queued on lazy streams so far (0 in eager mode)
+extern "C" unsigned long long gzpb_emu_deferred_ops() { return g_deferred; }
+
+namespace gzpb_emu {
+void launch_async(void *stream, dim3 grid, dim3 block, size_t smem, std::function<void()> body)
+{
+    emu_stream *s = S((cudaStream_t)stream);
+    if (s->device != g_cur_device && s != legacy_stream()) trap("kernel launch on a stream of another device (missing cudaSetDevice)");
+    enqueue((cudaStream_t)stream, [=]() { launch(grid, block, smem, body); });
+}
+}  // namespace gzpb_emu
 
 cudaError_t cudaMalloc(void **p, size_t n)
 {
     void *m = aligned_alloc(256, (n + 255) & ~(size_t)255);
     if (!m) return cudaErrorMemoryAllocation;
     Fill::garbage(m, n);          // device memory is not zero-initialised
+    g_device[(uintptr_t)m] = n ? n : 1;
     *p = m;
     return cudaSuccess;
 }
-cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
+cudaError_t cudaFree(void *p) { if (p) { drain_all(); g_device.erase((uintptr_t)p); free(p); } return cudaSuccess; }
 cudaError_t cudaHostAlloc(void **p, size_t n, unsigned)
 {
     void *m = aligned_alloc(256, (n + 255) & ~(size_t)255);
     if (!m) return cudaErrorMemoryAllocation;
     Fill::garbage(m, n);
-    g_pinned[(uintptr_t)m] = n;
+    g_pinned[(uintptr_t)m] = n ? n : 1;
     *p = m;
     return cudaSuccess;
 }
-cudaError_t cudaFreeHost(void *p) { if (p) { g_pinned.erase((uintptr_t)p); free(p); } return cudaSuccess; }
-cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { memmove(d, s, n); return cudaSuccess; }
-cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t) { memmove(d, s, n); return cudaSuccess; }
-cudaError_t cudaMemcpy2DAsync(void *d, size_t dp, const void *s, size_t sp, size_t w, size_t h, cudaMemcpyKind, cudaStream_t)
+cudaError_t cudaFreeHost(void *p) { if (p) { drain_all(); g_pinned.erase((uintptr_t)p); free(p); } return cudaSuccess; }
+// blocking copies run on the legacy stream: everything queued before them is visible to them
+cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { drain_all(); memmove(d, s, n); return cudaSuccess; }
+cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t st)
 {
-    for (size_t r = 0; r < h; r++) memmove((uint8_t *)d + r * dp, (const uint8_t *)s + r * sp, w);
+    if (pageable(d) || pageable(s)) {       // pageable host memory: the call returns after the bytes were staged / delivered
+        drain(S(st));
+        memmove(d, s, n);
+        return cudaSuccess;
+    }
+    enqueue(st, [=]() { memmove(d, s, n); });
     return cudaSuccess;
 }
-cudaError_t cudaMemset(void *d, int v, size_t n) { memset(d, v, n); return cudaSuccess; }
-cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t) { memset(d, v, n); return cudaSuccess; }
-cudaError_t cudaSetDevice(int) { return cudaSuccess; }
-cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
+cudaError_t cudaMemcpy2DAsync(void *d, size_t dp, const void *s, size_t sp, size_t w, size_t h, cudaMemcpyKind, cudaStream_t st)
+{
+    auto fn = [=]() { for (size_t r = 0; r < h; r++) memmove((uint8_t *)d + r * dp, (const uint8_t *)s + r * sp, w); };
+    if (pageable(d) || pageable(s)) { drain(S(st)); fn(); return cudaSuccess; }
+    enqueue(st, fn);
+    return cudaSuccess;
+}
+cudaError_t cudaMemset(void *d, int v, size_t n) { drain_all(); memset(d, v, n); return cudaSuccess; }
+cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t st) { enqueue(st, [=]() { memset(d, v, n); }); return cudaSuccess; }
+cudaError_t cudaSetDevice(int d) { if (d < 0 || d >= env_devices()) return cudaErrorInvalidValue; g_cur_device = d; return cudaSuccess; }
+cudaError_t cudaGetDevice(int *d) { *d = g_cur_device; return cudaSuccess; }
+cudaError_t cudaGetDeviceCount(int *n) { *n = env_devices(); return cudaSuccess; }
 cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int)
 {
     memset(p, 0, sizeof *p);
@@ -273,28 +367,45 @@ cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int)
     p->major = 10; p->minor = 0; p->multiProcessorCount = 148;
     return cudaSuccess;
 }
-cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+cudaError_t cudaDeviceSynchronize() { drain_all(); return cudaSuccess; }
 cudaError_t cudaGetLastError() { return cudaSuccess; }
 const char *cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "emulated CUDA error"; }
-cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = new emu_stream{0}; return cudaSuccess; }
-cudaError_t cudaStreamDestroy(cudaStream_t s) { delete s; return cudaSuccess; }
-cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
-cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
-cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = new emu_event{0}; return cudaSuccess; }
-cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { *e = new emu_event{0}; return cudaSuccess; }
-cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
-cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
-cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
-cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t, cudaEvent_t) { *ms = 0.0f; return cudaSuccess; }
+cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = new emu_stream(); (*s)->device = g_cur_device; g_streams.insert(*s); return cudaSuccess; }
+cudaError_t cudaStreamDestroy(cudaStream_t s) { if (s) { drain(s); g_streams.erase(s); delete s; } return cudaSuccess; }
+cudaError_t cudaStreamSynchronize(cudaStream_t s) { drain(S(s)); return cudaSuccess; }
+cudaError_t cudaStreamWaitEvent(cudaStream_t s, cudaEvent_t e, unsigned)
+{
+    if (!lazy() || e->recorded == 0) return cudaSuccess;
+    S(s)->q.push_back(emu_op{2, nullptr, e, e->recorded});
+    return cudaSuccess;
+}
+cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = new emu_event(); (*e)->device = g_cur_device; return cudaSuccess; }
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { return cudaEventCreate(e); }
+cudaError_t cudaEventDestroy(cudaEvent_t e) { if (e) { if (e->completed < e->recorded) complete_event(e, e->recorded, 0); delete e; } return cudaSuccess; }
+cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s)
+{
+    emu_stream *st = S(s);
+    if (st != legacy_stream() && st->device != e->device) return cudaErrorInvalidValue;   // event and stream must share a device
+    e->recorded++;
+    if (!lazy()) { e->completed = e->recorded; return cudaSuccess; }
+    e->last = st;
+    st->q.push_back(emu_op{1, nullptr, e, e->recorded});
+    return cudaSuccess;
+}
+cudaError_t cudaEventSynchronize(cudaEvent_t e) { complete_event(e, e->recorded, 0); return cudaSuccess; }
+cudaError_t cudaEventQuery(cudaEvent_t e) { return e->completed >= e->recorded ? cudaSuccess : cudaErrorNotReady; }
+cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b)
+{
+    complete_event(a, a->recorded, 0); complete_event(b, b->recorded, 0);
+    *ms = 0.0f;
+    return cudaSuccess;
+}
 cudaError_t cudaPointerGetAttributes(cudaPointerAttributes *a, const void *p)
 {
     memset(a, 0, sizeof *a);
     a->type = cudaMemoryTypeUnregistered;
-    auto it = g_pinned.upper_bound((uintptr_t)p);
-    if (it != g_pinned.begin()) {
-        --it;
-        if ((uintptr_t)p < it->first + it->second) { a->type = cudaMemoryTypeHost; a->hostPointer = (void *)p; a->devicePointer = (void *)p; }
-    }
+    if (in_map(g_pinned, p)) { a->type = cudaMemoryTypeHost; a->hostPointer = (void *)p; a->devicePointer = (void *)p; }
+    else if (in_map(g_device, p)) { a->type = cudaMemoryTypeDevice; a->devicePointer = (void *)p; }
     return cudaSuccess;
 }
 cudaError_t cudaHostGetDevicePointer(void **d, void *h, unsigned) { *d = h; return cudaSuccess; }

@@ -40,7 +40,7 @@ static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) {
 
 // ---- runtime API subset -----------------------------------------------------
 typedef int cudaError_t;
-enum { cudaSuccess = 0, cudaErrorInvalidValue = 1, cudaErrorMemoryAllocation = 2 };
+enum { cudaSuccess = 0, cudaErrorInvalidValue = 1, cudaErrorMemoryAllocation = 2, cudaErrorNotReady = 600 };
 typedef struct emu_stream *cudaStream_t;
 typedef struct emu_event *cudaEvent_t;
 enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3, cudaMemcpyDefault = 4 };
@@ -60,6 +60,7 @@ cudaError_t cudaMemcpy2DAsync(void *d, size_t dp, const void *s, size_t sp, size
 cudaError_t cudaMemset(void *d, int v, size_t n);
 cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t st = nullptr);
 cudaError_t cudaSetDevice(int d);
+cudaError_t cudaGetDevice(int *d);
 cudaError_t cudaGetDeviceCount(int *n);
 cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int d);
 cudaError_t cudaDeviceSynchronize();
@@ -74,6 +75,7 @@ cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned flags);
 cudaError_t cudaEventDestroy(cudaEvent_t e);
 cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s = nullptr);
 cudaError_t cudaEventSynchronize(cudaEvent_t e);
+cudaError_t cudaEventQuery(cudaEvent_t e);
 cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b);
 cudaError_t cudaPointerGetAttributes(cudaPointerAttributes *a, const void *p);
 cudaError_t cudaHostGetDevicePointer(void **d, void *h, unsigned flags);
@@ -93,6 +95,7 @@ void note_progress();
 uint8_t *dyn_smem();
 long long clock();
 void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> &body);
+void launch_async(void *stream, dim3 grid, dim3 block, size_t smem, std::function<void()> body);   // queued on the (lazy) stream
 [[noreturn]] void trap(const char *why);
 }  // namespace gzpb_emu
 
