@@ -8,6 +8,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <deque>
 #include <vector>
 
 #include "../../include/gzpb.h"
@@ -68,6 +69,11 @@ struct gzpb_ctx {
     KernelTimer timer;
     bool profiling = false;
     uint64_t launches = 0;
+    // gzpb_submit / gzpb_poll: batches in flight, oldest first (tickets complete in submission order)
+    struct Ticket { uint64_t id; const gzpb_block_in *in; gzpb_block_out *out; size_t count; int lane; };
+    std::deque<Ticket> tickets;
+    uint64_t next_ticket = 1;
+    int next_lane = 0;
 };
 
 static bool is_deflate_format(int f) { return f == GZPB_GZIP || f == GZPB_ZLIB || f == GZPB_RAWDEFLATE || f == GZPB_MGZIP || f == GZPB_BGZF; }
@@ -426,8 +432,11 @@ namespace {
 struct UnitRef { const uint8_t *ptr; size_t len; const uint8_t *dict; size_t dict_len; int is_last; };
 }
 
-// Launch one batch on a lane: H2D + kernels (+ scan/gather when `packed` is given).
-static int lane_launch(gzpb_ctx *c, Lane &L, const UnitRef *units, size_t n, bool contig, size_t pitch, bool src_pinned)
+// Launch one batch on a lane: H2D + kernels.  `src_pinned`: every unit (and dictionary) lies in pinned host
+// memory, so the units go H2D straight from where they are — maximal runs of equally sized units at a
+// constant pitch (consecutive blocks of one buffer) as ONE strided DMA, everything else unit by unit.
+// Pageable sources are packed into the lane's pinned staging buffer first.
+static int lane_launch(gzpb_ctx *c, Lane &L, const UnitRef *units, size_t n, bool src_pinned)
 {
     const size_t IS = c->in_stride;
     for (size_t i = 0; i < n; i++) {
@@ -435,24 +444,36 @@ static int lane_launch(gzpb_ctx *c, Lane &L, const UnitRef *units, size_t n, boo
         L.h_dict[i] = (uint32_t)units[i].dict_len;
         L.h_flags[i] = unit_flags_for(c->format, units[i].is_last);
     }
-    if (contig && src_pinned && n > 0) {
-        // blocks are consecutive slices of ONE pinned buffer (dictionary = the 32 KiB right before the
-        // block, so dict||data is contiguous too): strided DMA for the uniform units, plain copies for
-        // the stream's first block (no dictionary) and a short last block.
-        size_t first = 0, last = n;
-        if (units[0].dict_len != units[n > 1 ? 1 : 0].dict_len || (n == 1)) first = 1;
-        if (n > 1 && units[n - 1].len != pitch) last = n - 1;
-        if (first > last) first = last;
-        for (size_t i = 0; i < first; i++)
-            if (L.h_len[i]) CK(cudaMemcpyAsync(L.d_in + i * IS, units[i].ptr - units[i].dict_len, L.h_len[i], cudaMemcpyHostToDevice, L.st));
-        if (last > first) {
-            // rows may not overlap in a 2-D copy: dictionary columns and data columns go separately
-            const size_t dl = units[first].dict_len;
-            if (dl) CK(cudaMemcpy2DAsync(L.d_in + first * IS, IS, units[first].ptr - dl, pitch, dl, last - first, cudaMemcpyHostToDevice, L.st));
-            CK(cudaMemcpy2DAsync(L.d_in + first * IS + dl, IS, units[first].ptr, pitch, pitch, last - first, cudaMemcpyHostToDevice, L.st));
+    if (src_pinned) {
+        auto adjacent = [](const UnitRef &u) { return u.dict_len == 0 || u.dict + u.dict_len == u.ptr; };
+        size_t i = 0;
+        while (i < n) {
+            const UnitRef &u = units[i];
+            const bool adj = adjacent(u);
+            size_t j = i + 1;
+            size_t P = 0;
+            if (adj && u.len > 0 && j < n && (uintptr_t)units[j].ptr > (uintptr_t)u.ptr) {
+                P = (size_t)((uintptr_t)units[j].ptr - (uintptr_t)u.ptr);
+                while (j < n && units[j].len == u.len && units[j].dict_len == u.dict_len && adjacent(units[j]) &&
+                       (uintptr_t)units[j].ptr - (uintptr_t)units[j - 1].ptr == P)
+                    j++;
+            }
+            if (j - i >= 2 && P >= u.len && P >= u.dict_len) {
+                // rows of a 2-D copy may not overlap: dictionary columns and data columns go separately
+                const size_t rows = j - i;
+                if (u.dict_len) CK(cudaMemcpy2DAsync(L.d_in + i * IS, IS, u.ptr - u.dict_len, P, u.dict_len, rows, cudaMemcpyHostToDevice, L.st));
+                CK(cudaMemcpy2DAsync(L.d_in + i * IS + u.dict_len, IS, u.ptr, P, u.len, rows, cudaMemcpyHostToDevice, L.st));
+            } else {
+                j = i + 1;
+                if (adj) {
+                    if (u.dict_len + u.len) CK(cudaMemcpyAsync(L.d_in + i * IS, u.ptr - u.dict_len, u.dict_len + u.len, cudaMemcpyHostToDevice, L.st));
+                } else {
+                    CK(cudaMemcpyAsync(L.d_in + i * IS, u.dict, u.dict_len, cudaMemcpyHostToDevice, L.st));
+                    if (u.len) CK(cudaMemcpyAsync(L.d_in + i * IS + u.dict_len, u.ptr, u.len, cudaMemcpyHostToDevice, L.st));
+                }
+            }
+            i = j;
         }
-        for (size_t i = last; i < n; i++)
-            if (L.h_len[i]) CK(cudaMemcpyAsync(L.d_in + i * IS, units[i].ptr - units[i].dict_len, L.h_len[i], cudaMemcpyHostToDevice, L.st));
     } else {
         if (!L.h_in) CK(cudaHostAlloc((void **)&L.h_in, c->max_units * IS, cudaHostAllocPortable));
         size_t used = 0;
@@ -520,9 +541,35 @@ static int lane_wait(gzpb_ctx *c, Lane &L)
     return GZPB_OK;
 }
 
-extern "C" int gzpb_encode_batch(gzpb_ctx *c, size_t n, const gzpb_block_in *in, gzpb_block_out *out)
+// completes the oldest ticket: wait for its lane, scatter the compacted blocks into the caller's buffers
+static int ticket_retire(gzpb_ctx *c)
 {
-    if (!c || (n && (!in || !out))) return GZPB_EINVAL;
+    const gzpb_ctx::Ticket t = c->tickets.front();
+    c->tickets.pop_front();
+    Lane &L = c->lanes[t.lane];
+    int r = lane_wait(c, L);
+    if (r != GZPB_OK) return r;
+    if (*L.h_overflow) return GZPB_ECUDA;
+    for (size_t i = 0; i < t.count; i++) {
+        gzpb_block_out &o = t.out[i];
+        o.status = L.h_status[i];
+        const size_t o0 = (size_t)L.h_offsets[i * c->cpu], o1 = (size_t)L.h_offsets[(i + 1) * c->cpu];
+        const size_t len = o1 - o0;
+        o.out_len = 0; o.check_sum = 0; o.check_amount = 0;
+        if (o.status == GZPB_OK) {
+            if (len > o.cap) { o.status = GZPB_ECOMPRESS; continue; }
+            memcpy(o.dst, L.h_packed + o0, len);
+            o.out_len = len;
+            if (c->format == GZPB_GZIP || c->format == GZPB_ZLIB) { o.check_sum = L.h_crc[i]; o.check_amount = (uint32_t)t.in[i].len; }
+        }
+    }
+    return GZPB_OK;
+}
+
+extern "C" int gzpb_submit(gzpb_ctx *c, size_t n, const gzpb_block_in *in, gzpb_block_out *out, gzpb_ticket *ticket)
+{
+    if (!c || !ticket || n == 0 || !in || !out) return GZPB_EINVAL;
+    if (n > c->max_units) return GZPB_EINVAL;
     CK(cudaSetDevice(c->device));
     const bool dict_fmt = gzpb_needs_dict(c->format);
     for (size_t i = 0; i < n; i++) {
@@ -530,55 +577,63 @@ extern "C" int gzpb_encode_batch(gzpb_ctx *c, size_t n, const gzpb_block_in *in,
         if (dl > c->dict_cap || in[i].len > c->max_block_bytes) return GZPB_EBUFFERSIZE;
         if (out[i].cap < gzpb_encode_capacity(c->format, in[i].len)) return GZPB_EINVAL;
     }
-    int rc = GZPB_OK;
-    std::vector<UnitRef> units;
-    size_t done = 0;
-    int li = 0;
-    struct Pending { size_t first, count; int lane; };
-    std::vector<Pending> pend;
-    auto retire = [&](const Pending &p) -> int {
-        Lane &L = c->lanes[p.lane];
-        int r = lane_wait(c, L);
-        if (r != GZPB_OK) return r;
-        if (*L.h_overflow) return GZPB_ECUDA;
-        for (size_t i = 0; i < p.count; i++) {
-            gzpb_block_out &o = out[p.first + i];
-            o.status = L.h_status[i];
-            const size_t o0 = (size_t)L.h_offsets[i * c->cpu], o1 = (size_t)L.h_offsets[(i + 1) * c->cpu];
-            size_t len = o1 - o0;
-            o.out_len = 0; o.check_sum = 0; o.check_amount = 0;
-            if (o.status == GZPB_OK) {
-                if (len > o.cap) { o.status = GZPB_ECOMPRESS; continue; }
-                memcpy(o.dst, L.h_packed + o0, len);
-                o.out_len = len;
-                if (c->format == GZPB_GZIP || c->format == GZPB_ZLIB) { o.check_sum = L.h_crc[i]; o.check_amount = (uint32_t)in[p.first + i].len; }
-            }
-        }
-        return GZPB_OK;
-    };
-    while (done < n) {
-        size_t cnt = std::min(c->max_units, n - done);
-        Lane &L = c->lanes[li];
-        if (L.busy) {
-            rc = retire(pend.front()); pend.erase(pend.begin());
-            if (rc != GZPB_OK) return rc;
-        }
-        units.resize(cnt);
-        for (size_t i = 0; i < cnt; i++) {
-            const gzpb_block_in &b = in[done + i];
-            size_t dl = (dict_fmt && b.dict) ? b.dict_len : 0;
-            units[i] = UnitRef{(const uint8_t *)b.ptr, b.len, (const uint8_t *)b.dict, dl, b.is_last};
-        }
-        rc = lane_launch(c, L, units.data(), cnt, false, 0, false);
-        if (rc != GZPB_OK) return rc;
-        rc = lane_pack(c, L, L.h_packed, (uint64_t)c->max_units * c->cpu * c->out_stride, nullptr, nullptr);
-        if (rc != GZPB_OK) return rc;
-        pend.push_back(Pending{done, cnt, li});
-        done += cnt;
-        li = (li + 1) % kLanes;
+    Lane &L = c->lanes[c->next_lane];
+    if (L.busy) return GZPB_EAGAIN;                         // all lanes in flight: the bounded channel is full
+    std::vector<UnitRef> units(n);
+    bool pinned = true;
+    for (size_t i = 0; i < n; i++) {
+        const gzpb_block_in &b = in[i];
+        size_t dl = (dict_fmt && b.dict) ? b.dict_len : 0;
+        units[i] = UnitRef{(const uint8_t *)b.ptr, b.len, (const uint8_t *)b.dict, dl, b.is_last};
+        if (pinned && ((b.len && !is_pinned(b.ptr)) || (dl && !is_pinned(b.dict)))) pinned = false;
     }
-    for (auto &p : pend) { rc = retire(p); if (rc != GZPB_OK) return rc; }
+    int rc = lane_launch(c, L, units.data(), n, pinned);
+    if (rc != GZPB_OK) return rc;
+    rc = lane_pack(c, L, L.h_packed, (uint64_t)c->max_units * c->cpu * c->out_stride, nullptr, nullptr);
+    if (rc != GZPB_OK) return rc;
+    *ticket = c->next_ticket++;
+    c->tickets.push_back(gzpb_ctx::Ticket{*ticket, in, out, n, c->next_lane});
+    c->next_lane = (c->next_lane + 1) % kLanes;
     return GZPB_OK;
+}
+
+extern "C" int gzpb_poll(gzpb_ctx *c, gzpb_ticket ticket, int wait)
+{
+    if (!c || ticket == 0 || ticket >= c->next_ticket) return GZPB_EINVAL;
+    CK(cudaSetDevice(c->device));
+    while (!c->tickets.empty() && c->tickets.front().id <= ticket) {
+        if (!wait) {
+            cudaError_t q = cudaEventQuery(c->lanes[c->tickets.front().lane].ev_done);
+            if (q == cudaErrorNotReady) return GZPB_EAGAIN;
+            CK(q);
+        }
+        int rc = ticket_retire(c);
+        if (rc != GZPB_OK) return rc;
+    }
+    return GZPB_OK;
+}
+
+extern "C" int gzpb_encode_batch(gzpb_ctx *c, size_t n, const gzpb_block_in *in, gzpb_block_out *out)
+{
+    if (!c || (n && (!in || !out))) return GZPB_EINVAL;
+    if (!c->tickets.empty()) return GZPB_EAGAIN;            // finish the asynchronous tickets first
+    size_t done = 0;
+    gzpb_ticket last = 0;
+    int rc = GZPB_OK;
+    while (done < n && rc == GZPB_OK) {
+        const size_t cnt = std::min(c->max_units, n - done);
+        gzpb_ticket t = 0;
+        rc = gzpb_submit(c, cnt, in + done, out + done, &t);
+        if (rc == GZPB_EAGAIN) { rc = gzpb_poll(c, c->tickets.front().id, 1); continue; }
+        if (rc == GZPB_OK) { last = t; done += cnt; }
+    }
+    if (last) { int r = gzpb_poll(c, last, 1); if (rc == GZPB_OK) rc = r; }
+    if (rc != GZPB_OK) {                                    // leave no batch half-finished behind an error
+        cudaDeviceSynchronize();
+        c->tickets.clear();
+        for (int i = 0; i < kLanes; i++) c->lanes[i].busy = false;
+    }
+    return rc;
 }
 
 extern "C" int gzpb_encode_stream(gzpb_ctx *c, const void *in_v, size_t in_len, size_t buffer_size, void *out_v,
@@ -588,6 +643,7 @@ extern "C" int gzpb_encode_stream(gzpb_ctx *c, const void *in_v, size_t in_len, 
     if (buffer_size == 0) buffer_size = c->max_block_bytes;
     if (buffer_size < GZPB_DICT_SIZE) return GZPB_EBUFFERSIZE;   // par/compress.rs:68-74
     if (buffer_size > c->max_block_bytes) return GZPB_EBUFFERSIZE;
+    if (!c->tickets.empty()) return GZPB_EAGAIN;
     CK(cudaSetDevice(c->device));
     const uint8_t *in = (const uint8_t *)in_v;
     uint8_t *out = (uint8_t *)out_v;
@@ -660,7 +716,7 @@ extern "C" int gzpb_encode_stream(gzpb_ctx *c, const void *in_v, size_t in_len, 
             const uint8_t *d = (dict_fmt && bi > 0) ? in + b0 - GZPB_DICT_SIZE : nullptr;
             units[i] = UnitRef{in + b0, len, d, d ? (size_t)GZPB_DICT_SIZE : 0, bi + 1 == nblocks};
         }
-        rc = lane_launch(c, L, units.data(), cnt, true, buffer_size, in_pinned);
+        rc = lane_launch(c, L, units.data(), cnt, in_pinned);
         if (rc != GZPB_OK) break;
         if (out_pinned) rc = lane_pack(c, L, dev_out, out_cap, prev_end, prev);
         else rc = lane_pack(c, L, L.h_packed, (uint64_t)c->max_units * c->cpu * c->out_stride, nullptr, nullptr);
@@ -687,92 +743,168 @@ extern "C" int gzpb_encode_stream(gzpb_ctx *c, const void *in_v, size_t in_len, 
 
 
 // ---- incremental writer: ParCompress<F, W> as a C object ---------------------------------
+//
+// The caller's bytes are copied ONCE, straight into a pinned slab (the reference's single
+// `buffer.extend_from_slice`, par/compress.rs:414); blocks are cut in place, so a batch is a run of
+// consecutive slices of the slab and goes H2D as one strided DMA.  Batches are dealt round-robin over
+// the writer's devices and their lanes and stay in flight while the caller keeps writing;
+// they retire strictly in submission order — the ticket FIFO of par/compress.rs:303-313 — each with ONE
+// sink call on the lane's compacted pinned output.
 struct gzpb_writer {
-    gzpb_ctx *ctx = nullptr;
+    std::vector<gzpb_ctx *> ctx;                                 // one per device
     int format = 0, level = 0;
-    size_t buffer_size = 0, max_pending = 0;
+    size_t buffer_size = 0, batch_blocks = 0;
     gzpb_sink_fn sink = nullptr;
     void *user = nullptr;
-    std::vector<uint8_t> buf;                                    // bytes not yet cut into blocks
-    struct Msg { std::vector<uint8_t> data, dict; bool is_last; };
-    std::vector<Msg> pending;                                    // FIFO of messages = ticket order
-    std::vector<uint8_t> dict;                                   // dictionary for the next block
-    bool have_dict = false, wrote_header = false, finished = false;
+    // slabs: [32 KiB dictionary prefix | (batch_blocks + 1) * buffer_size bytes of stream]
+    std::vector<uint8_t *> slabs;
+    size_t slab_cap = 0;                                         // stream bytes per slab
+    size_t cur = 0;                                              // slab being filled
+    size_t fill = 0, cut = 0;                                    // bytes written / bytes already cut into blocks
+    std::vector<UnitRef> msgs;                                   // blocks cut from the current slab (FIFO = ticket order)
+    bool have_dict = false;                                      // the next block takes the 32 KiB before `cut` as dictionary
+    struct Flight { int dev, lane; size_t count; };
+    std::deque<Flight> flights;                                  // batches in flight, oldest first
+    uint64_t nbatches = 0;
+    bool wrote_header = false, finished = false;
     uint32_t sum = 0, amount = 0;
     int error = GZPB_OK;
+    uint64_t sink_calls = 0, bytes_in = 0, bytes_out = 0;
 };
 
 static int writer_emit(gzpb_writer *w, const void *p, size_t n)
 {
     if (n == 0) return GZPB_OK;
+    w->sink_calls++; w->bytes_out += n;
     if (w->sink(w->user, p, n) != 0) { w->error = GZPB_EIO; return GZPB_EIO; }
     return GZPB_OK;
 }
 
+static int writer_header(gzpb_writer *w)
+{
+    if (w->wrote_header) return GZPB_OK;
+    uint8_t hb[16];
+    size_t hl = gzpb_header(w->format, w->level, hb);
+    w->wrote_header = true;
+    return writer_emit(w, hb, hl);
+}
+
+// the writer loop body (par/compress.rs:305-311) for the oldest batch in flight
+static int writer_retire(gzpb_writer *w)
+{
+    const gzpb_writer::Flight f = w->flights.front();
+    w->flights.pop_front();
+    gzpb_ctx *c = w->ctx[f.dev];
+    Lane &L = c->lanes[f.lane];
+    if (cudaSetDevice(c->device) != cudaSuccess) return w->error = GZPB_ECUDA;
+    int r = lane_wait(c, L);
+    if (r != GZPB_OK) return w->error = r;
+    if (*L.h_overflow) return w->error = GZPB_ECOMPRESS;
+    if (c->format != GZPB_SNAP)
+        for (size_t i = 0; i < f.count; i++)
+            if (L.h_status[i] != GZPB_OK) return w->error = L.h_status[i];          // a failed block fails the stream
+    if (w->format == GZPB_GZIP || w->format == GZPB_ZLIB) {
+        const uint64_t blen = (uint64_t)L.h_comb[1] | ((uint64_t)L.h_comb[2] << 32);
+        if (blen) w->sum = w->format == GZPB_GZIP ? gzpb_crc32_combine(w->sum, L.h_comb[0], blen)
+                                                  : gzpb_adler32_combine(w->sum, L.h_comb[0], blen);
+        w->amount += (uint32_t)blen;
+    }
+    return writer_emit(w, L.h_packed, (size_t)L.h_offsets[f.count * c->cpu]);
+}
+
 static int writer_drain(gzpb_writer *w)
 {
-    if (w->error) return w->error;
-    if (!w->wrote_header) {
-        uint8_t hb[16];
-        size_t hl = gzpb_header(w->format, w->level, hb);
-        w->wrote_header = true;
-        int r = writer_emit(w, hb, hl);
-        if (r) return r;
-    }
-    const size_t n = w->pending.size();
-    if (n == 0) return GZPB_OK;
-    std::vector<gzpb_block_in> in(n);
-    std::vector<gzpb_block_out> out(n);
-    std::vector<std::vector<uint8_t>> bufs(n);
-    for (size_t i = 0; i < n; i++) {
-        auto &m = w->pending[i];
-        in[i] = gzpb_block_in{m.data.data(), m.data.size(), m.dict.empty() ? nullptr : m.dict.data(), m.dict.size(), m.is_last ? 1 : 0};
-        bufs[i].resize(gzpb_encode_capacity(w->format, m.data.size()) + 64);
-        out[i] = gzpb_block_out{bufs[i].data(), bufs[i].size(), 0, 0, 0, 0};
-    }
-    int rc = gzpb_encode_batch(w->ctx, n, in.data(), out.data());
-    if (rc != GZPB_OK) { w->error = rc; return rc; }
-    for (size_t i = 0; i < n; i++) {
-        if (out[i].status != GZPB_OK) { w->error = out[i].status; return w->error; }   // a failed block fails the stream
-        const size_t len = w->pending[i].data.size();
-        if (w->format == GZPB_GZIP) w->sum = gzpb_crc32_combine(w->sum, out[i].check_sum, len);
-        else if (w->format == GZPB_ZLIB) w->sum = gzpb_adler32_combine(w->sum, out[i].check_sum, len);
-        if (w->format == GZPB_GZIP || w->format == GZPB_ZLIB) w->amount += (uint32_t)len;
-        int r = writer_emit(w, bufs[i].data(), out[i].out_len);
-        if (r) return r;
-    }
-    w->pending.clear();
+    while (!w->flights.empty()) { int r = writer_retire(w); if (r != GZPB_OK) return r; }
     return GZPB_OK;
 }
 
-static int writer_send(gzpb_writer *w, const uint8_t *p, size_t n, bool is_last)
+// hand the blocks cut so far to the next device lane and continue in the next slab
+static int writer_submit(gzpb_writer *w)
 {
-    gzpb_writer::Msg m;
-    m.data.assign(p, p + n);
-    if (w->have_dict) m.dict = w->dict;
-    m.is_last = is_last;
-    w->have_dict = false;
-    w->pending.push_back(std::move(m));
-    if (w->pending.size() >= w->max_pending) return writer_drain(w);
+    if (w->error) return w->error;
+    int r = writer_header(w);
+    if (r != GZPB_OK) return r;
+    if (w->msgs.empty()) return GZPB_OK;
+    const size_t G = w->ctx.size();
+    const int dev = (int)(w->nbatches % G), lane = (int)((w->nbatches / G) % kLanes);
+    gzpb_ctx *c = w->ctx[dev];
+    Lane &L = c->lanes[lane];
+    // batches that are already finished leave now (keeps the sink fed); a busy lane is back-pressure
+    while (!w->flights.empty()) {
+        const gzpb_writer::Flight &f = w->flights.front();
+        if (!L.busy && cudaEventQuery(w->ctx[f.dev]->lanes[f.lane].ev_done) != cudaSuccess) break;
+        r = writer_retire(w);
+        if (r != GZPB_OK) return r;
+    }
+    cudaGetLastError();
+    if (cudaSetDevice(c->device) != cudaSuccess) return w->error = GZPB_ECUDA;
+    r = lane_launch(c, L, w->msgs.data(), w->msgs.size(), true);
+    if (r == GZPB_OK) r = lane_pack(c, L, L.h_packed, (uint64_t)c->max_units * c->cpu * c->out_stride, nullptr, nullptr);
+    if (r != GZPB_OK) return w->error = r;
+    w->flights.push_back(gzpb_writer::Flight{dev, lane, w->msgs.size()});
+    w->nbatches++;
+    w->msgs.clear();
+    // next slab: carry the dictionary (the 32 KiB before `cut`) and the bytes not yet cut
+    uint8_t *from = w->slabs[w->cur];
+    w->cur = (w->cur + 1) % w->slabs.size();
+    uint8_t *to = w->slabs[w->cur];
+    const size_t rem = w->fill - w->cut;
+    if (w->have_dict) memcpy(to - GZPB_DICT_SIZE, from + w->cut - GZPB_DICT_SIZE, GZPB_DICT_SIZE + rem);
+    else if (rem) memcpy(to, from + w->cut, rem);
+    w->fill = rem; w->cut = 0;
+    return GZPB_OK;
+}
+
+// cut [cut, cut + k) as one message (Message{buffer, dictionary, is_last}, lib.rs:282-312)
+static int writer_cut(gzpb_writer *w, size_t k, bool is_last, bool next_has_dict)
+{
+    uint8_t *base = w->slabs[w->cur];
+    UnitRef u{base + w->cut, k, nullptr, 0, is_last ? 1 : 0};
+    if (w->have_dict) { u.dict = base + w->cut - GZPB_DICT_SIZE; u.dict_len = GZPB_DICT_SIZE; }
+    w->msgs.push_back(u);
+    w->cut += k;
+    w->have_dict = next_has_dict;
+    if (w->msgs.size() >= w->batch_blocks) return writer_submit(w);
+    return GZPB_OK;
+}
+
+extern "C" int gzpb_writer_create_multi(gzpb_writer **out, const int *devices, size_t ndevices, int format, int level,
+                                        size_t buffer_size, size_t blocks_in_flight, gzpb_sink_fn sink, void *user)
+{
+    if (!out || !sink || !devices || ndevices == 0 || ndevices > 64) return GZPB_EINVAL;
+    *out = nullptr;
+    if (buffer_size == 0) buffer_size = gzpb_default_bufsize(format);
+    if (buffer_size < GZPB_DICT_SIZE) return GZPB_EBUFFERSIZE;   // par/compress.rs:68-74
+    if (blocks_in_flight == 0) blocks_in_flight = 1184;          // 8 CTAs per SM on 148 SMs per batch
+    gzpb_writer *w = new gzpb_writer();
+    w->format = format; w->level = level; w->buffer_size = buffer_size; w->batch_blocks = blocks_in_flight;
+    w->sink = sink; w->user = user;
+    w->sum = (format == GZPB_ZLIB) ? 1u : 0u;
+    for (size_t i = 0; i < ndevices; i++) {
+        gzpb_ctx *c = nullptr;
+        int rc = gzpb_create(&c, devices[i], format, level, buffer_size, blocks_in_flight);
+        if (rc != GZPB_OK) { gzpb_writer_destroy(w); return rc; }
+        w->ctx.push_back(c);
+    }
+    w->slab_cap = (blocks_in_flight + 1) * buffer_size;
+    const size_t nslabs = ndevices * kLanes + 1;                 // every batch in flight keeps its slab + the one being filled
+    for (size_t i = 0; i < nslabs; i++) {
+        uint8_t *p = nullptr;
+        if (cudaHostAlloc((void **)&p, GZPB_DICT_SIZE + w->slab_cap, cudaHostAllocPortable) != cudaSuccess) {
+            cudaGetLastError();
+            gzpb_writer_destroy(w);
+            return GZPB_ENOMEM;
+        }
+        w->slabs.push_back(p + GZPB_DICT_SIZE);
+    }
+    *out = w;
     return GZPB_OK;
 }
 
 extern "C" int gzpb_writer_create(gzpb_writer **out, int device, int format, int level, size_t buffer_size,
                                   size_t blocks_in_flight, gzpb_sink_fn sink, void *user)
 {
-    if (!out || !sink) return GZPB_EINVAL;
-    *out = nullptr;
-    if (buffer_size == 0) buffer_size = gzpb_default_bufsize(format);
-    if (buffer_size < GZPB_DICT_SIZE) return GZPB_EBUFFERSIZE;   // par/compress.rs:68-74
-    if (blocks_in_flight == 0) blocks_in_flight = 256;
-    gzpb_writer *w = new gzpb_writer();
-    int rc = gzpb_create(&w->ctx, device, format, level, buffer_size, blocks_in_flight);
-    if (rc != GZPB_OK) { delete w; return rc; }
-    w->format = format; w->level = level; w->buffer_size = buffer_size; w->max_pending = blocks_in_flight;
-    w->sink = sink; w->user = user;
-    w->sum = (format == GZPB_ZLIB) ? 1u : 0u;
-    *out = w;
-    return GZPB_OK;
+    return gzpb_writer_create_multi(out, &device, 1, format, level, buffer_size, blocks_in_flight, sink, user);
 }
 
 extern "C" int gzpb_writer_write(gzpb_writer *w, const void *data, size_t len)
@@ -781,44 +913,38 @@ extern "C" int gzpb_writer_write(gzpb_writer *w, const void *data, size_t len)
     if (w->finished) return GZPB_ECHANNEL;
     if (w->error) return w->error;
     const uint8_t *p = (const uint8_t *)data;
-    w->buf.insert(w->buf.end(), p, p + len);
-    size_t off = 0;
-    while (w->buf.size() - off > w->buffer_size) {                // strict '>' (par/compress.rs:415)
-        int rc = writer_send(w, w->buf.data() + off, w->buffer_size, false);
-        if (gzpb_needs_dict(w->format)) {
-            w->dict.assign(w->buf.data() + off + w->buffer_size - GZPB_DICT_SIZE, w->buf.data() + off + w->buffer_size);
-            w->have_dict = true;
+    const bool dict_fmt = gzpb_needs_dict(w->format) != 0;
+    w->bytes_in += len;
+    while (len) {
+        const size_t k = std::min(len, w->slab_cap - w->fill);
+        memcpy(w->slabs[w->cur] + w->fill, p, k);
+        w->fill += k; p += k; len -= k;
+        while (w->fill - w->cut > w->buffer_size) {               // strict '>' (par/compress.rs:415)
+            int rc = writer_cut(w, w->buffer_size, false, dict_fmt);   // dictionary = last 32 KiB of this block (:419-423)
+            if (rc != GZPB_OK) return rc;
         }
-        off += w->buffer_size;
-        if (rc != GZPB_OK) { w->buf.erase(w->buf.begin(), w->buf.begin() + off); return rc; }
     }
-    if (off) w->buf.erase(w->buf.begin(), w->buf.begin() + off);
     return GZPB_OK;
 }
 
 static int writer_flush_last(gzpb_writer *w, bool is_last)
 {
-    size_t off = 0;
+    const bool dict_fmt = gzpb_needs_dict(w->format) != 0;
     for (;;) {                                                     // par/compress.rs:332-362
-        const size_t k = std::min(w->buf.size() - off, w->buffer_size);
-        const bool last = is_last && (off + k == w->buf.size());
-        int rc = writer_send(w, w->buf.data() + off, k, last);
-        if (k >= GZPB_DICT_SIZE && !last && gzpb_needs_dict(w->format)) {
-            w->dict.assign(w->buf.data() + off + k - GZPB_DICT_SIZE, w->buf.data() + off + k);
-            w->have_dict = true;
-        }
-        off += k;
-        if (rc != GZPB_OK) { w->buf.erase(w->buf.begin(), w->buf.begin() + off); return rc; }
-        if (off == w->buf.size()) break;
+        const size_t k = std::min(w->fill - w->cut, w->buffer_size);
+        const bool last = is_last && (w->cut + k == w->fill);
+        int rc = writer_cut(w, k, last, k >= GZPB_DICT_SIZE && !last && dict_fmt);   // :343-345
+        if (rc != GZPB_OK) return rc;
+        if (w->cut == w->fill) break;
     }
-    w->buf.clear();
-    return GZPB_OK;
+    return writer_submit(w);
 }
 
 extern "C" int gzpb_writer_flush(gzpb_writer *w)
 {
     if (!w) return GZPB_EINVAL;
     if (w->finished) return GZPB_ECHANNEL;
+    if (w->error) return w->error;
     int rc = writer_flush_last(w, false);
     if (rc != GZPB_OK) return rc;
     return writer_drain(w);
@@ -828,7 +954,8 @@ extern "C" int gzpb_writer_finish(gzpb_writer *w)
 {
     if (!w) return GZPB_EINVAL;
     if (w->finished) return GZPB_ECHANNEL;
-    int rc = writer_flush_last(w, true);
+    int rc = w->error;
+    if (rc == GZPB_OK) rc = writer_flush_last(w, true);
     if (rc == GZPB_OK) rc = writer_drain(w);
     if (rc == GZPB_OK) {
         uint8_t fb[16];
@@ -839,9 +966,26 @@ extern "C" int gzpb_writer_finish(gzpb_writer *w)
     return rc;
 }
 
+extern "C" int gzpb_writer_stats(gzpb_writer *w, uint64_t *bytes_in, uint64_t *bytes_out, uint64_t *batches, uint64_t *sink_calls)
+{
+    if (!w) return GZPB_EINVAL;
+    if (bytes_in) *bytes_in = w->bytes_in;
+    if (bytes_out) *bytes_out = w->bytes_out;
+    if (batches) *batches = w->nbatches;
+    if (sink_calls) *sink_calls = w->sink_calls;
+    return GZPB_OK;
+}
+
 extern "C" void gzpb_writer_destroy(gzpb_writer *w)
 {
     if (!w) return;
-    if (w->ctx) gzpb_destroy(w->ctx);
+    for (gzpb_ctx *c : w->ctx) {                                   // batches still in flight read the slabs
+        if (!c) continue;
+        cudaSetDevice(c->device);
+        cudaDeviceSynchronize();
+        for (int i = 0; i < kLanes; i++) c->lanes[i].busy = false;
+    }
+    for (uint8_t *p : w->slabs) cudaFreeHost(p - GZPB_DICT_SIZE);
+    for (gzpb_ctx *c : w->ctx) gzpb_destroy(c);
     delete w;
 }

@@ -47,7 +47,9 @@ enum gzpb_status {
     GZPB_EHEADER = -11,     /* InvalidHeader: "Extra field flag not set" / "Bad SID" (src/deflate.rs:407-417, 555-565) */
     GZPB_ECHECK = -12,      /* InvalidCheck{found, expected} (src/par/decompress.rs:176-181) */
     GZPB_EDECOMPRESS = -13, /* LibDelfaterDecompress / DecompressError: corrupt DEFLATE data (src/deflate.rs:393, 541) */
-    GZPB_EBLOCK = -14       /* InvalidBlockSize: a member shorter than its own header + footer */
+    GZPB_EBLOCK = -14,      /* InvalidBlockSize: a member shorter than its own header + footer */
+    GZPB_EAGAIN = -15       /* not an error: every lane is in flight (gzpb_submit) / the ticket is not finished yet
+                               (gzpb_poll without wait) — the bounded channel of src/par/compress.rs:111-112 is full */
 };
 
 /* Constants of the reference (src/lib.rs:105,108; src/bgzf.rs:20,22). */
@@ -95,6 +97,17 @@ void gzpb_destroy(gzpb_ctx *ctx);
  * src/snap.rs:61-74).  Host pointers in, host pointers out; synchronous. */
 int gzpb_encode_batch(gzpb_ctx *ctx, size_t n, const gzpb_block_in *in, gzpb_block_out *out);
 
+/* The same, asynchronous — the device analogue of `tx_compressor.send(msg)` + the oneshot the writer
+ * thread later receives (src/par/compress.rs:283-294, 305-306).  gzpb_submit hands n <= max_blocks_in_flight
+ * blocks to the next free lane and returns a ticket at once (GZPB_EAGAIN while all lanes are in flight);
+ * gzpb_poll(ticket, wait) completes tickets in submission order up to and including `ticket`: GZPB_OK once
+ * its `out[]` entries are filled, GZPB_EAGAIN when `wait` is 0 and the device is not done.  `in`, `out`
+ * and the buffers they point to belong to the library until the ticket completes.  Blocks that lie in
+ * pinned memory (gzpb_host_alloc) go to the device by DMA from where they are; pageable ones are staged. */
+typedef uint64_t gzpb_ticket;
+int gzpb_submit(gzpb_ctx *ctx, size_t n, const gzpb_block_in *in, gzpb_block_out *out, gzpb_ticket *ticket);
+int gzpb_poll(gzpb_ctx *ctx, gzpb_ticket ticket, int wait);
+
 /* ParCompress end to end for an in-memory input: header + write(in) + finish()
  * + footer, i.e. chunking with the reference's strict '>' hold-back and final
  * flush (src/par/compress.rs:413-463, 332-362), ordered output (:303-313).
@@ -107,15 +120,25 @@ int gzpb_encode_stream(gzpb_ctx *ctx, const void *in, size_t in_len, size_t buff
  * 32 KiB dictionary carry :419-423, `flush` = flush_last(false) :466-468 incl. the empty block,
  * `finish` = flush_last(true) + footer :377-388) and hands the encoded blocks to `sink` in stream
  * order (the ordered writer loop :303-313).  `sink` plays `W: Write`: nonzero return = io error
- * (GZPB_EIO is then returned by the next call, like the reference surfaces a BrokenPipe). */
+ * (GZPB_EIO is then returned by the next call, like the reference surfaces a BrokenPipe).
+ * The caller's bytes are copied once into pinned slabs; up to 3 device batches of `blocks_in_flight`
+ * blocks per GPU stay in flight while the caller keeps writing (back-pressure = the bounded channels
+ * of :111-112); `sink` is called once per finished batch, in order, from the calling thread. */
 typedef int (*gzpb_sink_fn)(void *user, const void *data, size_t len);
 typedef struct gzpb_writer gzpb_writer;
 int gzpb_writer_create(gzpb_writer **w, int device, int format, int level, size_t buffer_size,
                        size_t blocks_in_flight, gzpb_sink_fn sink, void *user);
+/* The same writer over several GPUs of one box: device batches of `blocks_in_flight` consecutive blocks
+ * are dealt round-robin to the devices (SURVEY.md §8e — blocks are independent, a batch's first
+ * dictionary comes from host memory, no device-to-device traffic); one ordered sink. */
+int gzpb_writer_create_multi(gzpb_writer **w, const int *devices, size_t ndevices, int format, int level,
+                             size_t buffer_size, size_t blocks_in_flight, gzpb_sink_fn sink, void *user);
 int gzpb_writer_write(gzpb_writer *w, const void *buf, size_t len);
 int gzpb_writer_flush(gzpb_writer *w);
 int gzpb_writer_finish(gzpb_writer *w);
 void gzpb_writer_destroy(gzpb_writer *w);
+/* counters of a writer: bytes written by the caller, bytes handed to the sink, device batches, sink calls */
+int gzpb_writer_stats(gzpb_writer *w, uint64_t *bytes_in, uint64_t *bytes_out, uint64_t *batches, uint64_t *sink_calls);
 
 /* Device-resident form of the same path, asynchronous on `cuda_stream`:
  * d_in holds nunits slots of GZPB_IN_STRIDE bytes, d_len/d_flags one u32 per unit

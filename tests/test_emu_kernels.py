@@ -239,3 +239,160 @@ def test_emu_syncz_block_writers_keep_the_reference_quirks(emu_backend):
     assert sink.getvalue() == b""
     # more than one thread -> ParCompress (lib.rs:246)
     assert isinstance(gzp_b200.ZBuilder(gzp_b200.Bgzf).num_threads(4).from_writer(io.BytesIO()), gzp_b200.ParCompress)
+
+
+def _drive_c_writer(L, fmt, level, bs, batch, data, rnd, devices=(0,), flushes=(2, 7), sink_fail_after=None):
+    """gzpb_writer_* driven with random write sizes; returns (stream bytes, writes, final rc, stats)."""
+    import ctypes as C
+    from gzp_b200 import _lib
+    chunks = bytearray()
+    calls = [0]
+
+    @_lib.SINK_FN
+    def sink(user, ptr, n):
+        calls[0] += 1
+        if sink_fail_after is not None and calls[0] > sink_fail_after:
+            return 1
+        chunks.extend(C.string_at(ptr, n))
+        return 0
+
+    h = C.c_void_p()
+    devs = (C.c_int * len(devices))(*devices)
+    rc = L.gzpb_writer_create_multi(C.byref(h), devs, len(devices), fmt, level, bs, batch, C.cast(sink, C.c_void_p), None)
+    assert rc == 0, rc
+    writes, pos = [], 0
+    while pos < len(data):
+        k = rnd.randrange(1, 10000) if rnd.random() < 0.6 else rnd.randrange(1, 3 * bs)
+        writes.append(data[pos:pos + k]); pos += k
+    rc = 0
+    for i, wdata in enumerate(writes):
+        rc = L.gzpb_writer_write(h, wdata, len(wdata))
+        if rc:
+            break
+        if i in flushes:
+            rc = L.gzpb_writer_flush(h)
+            if rc:
+                break
+    frc = L.gzpb_writer_finish(h)
+    assert L.gzpb_writer_write(h, b"x", 1) == -7              # write after finish: ChannelSend
+    st = [C.c_uint64(0) for _ in range(4)]
+    L.gzpb_writer_stats(h, *[C.byref(x) for x in st])
+    L.gzpb_writer_destroy(h)
+    return bytes(chunks), writes, (rc or frc), [x.value for x in st]
+
+
+def test_emu_pipelined_c_writer_all_formats():
+    """The incremental C writer (pinned slabs, batches in flight on lazy streams, ordered sink) is byte-identical
+    to the oracle's ParCompress model for random write sizes and flushes; batches of 2-3 blocks force slab
+    switches, lane reuse and dictionary carry across slabs."""
+    L = emu.lib()
+    rnd = random.Random(2024)
+    for fmt, bs, batch in ((oracle.BGZF, 65280, 2), (oracle.GZIP, 40000, 3), (oracle.MGZIP, 131072, 1),
+                           (oracle.SNAP, 70000, 2), (oracle.ZLIB, 32768, 3), (oracle.RAWDEFLATE, 50000, 2)):
+        data = (TEXT * 3)[:700000]
+        got, writes, rc, st = _drive_c_writer(L, fmt, 6, bs, batch, data, rnd)
+        assert rc == 0
+        assert got == oracle.compress_stream(fmt, 6, bs, writes, {2, 7}), "fmt %d" % fmt
+        assert st[0] == len(data) and st[1] == len(got) and st[2] >= len(data) // (bs * batch)
+    # empty stream and a stream of exactly buffer_size bytes (strict '>' hold-back)
+    for data in (b"", TEXT[:65280]):
+        got, writes, rc, _ = _drive_c_writer(L, oracle.BGZF, 6, 65280, 2, data, rnd, flushes=())
+        assert rc == 0 and got == oracle.compress_stream(oracle.BGZF, 6, 65280, writes)
+        assert gzip.decompress(got) == data
+
+
+def test_emu_c_writer_two_devices_round_robin(monkeypatch):
+    """gzpb_writer_create_multi: batches dealt round-robin over two (emulated) devices give the same stream."""
+    monkeypatch.setenv("GZPB_EMU_DEVICES", "2")
+    L = emu.lib()
+    rnd = random.Random(7)
+    for fmt, bs in ((oracle.BGZF, 65280), (oracle.GZIP, 32768)):
+        data = (TEXT * 3)[:800000]
+        got, writes, rc, st = _drive_c_writer(L, fmt, 5, bs, 2, data, rnd, devices=(0, 1), flushes=(3,))
+        assert rc == 0
+        assert got == oracle.compress_stream(fmt, 5, bs, writes, {3})
+        assert st[2] >= 6                                      # enough batches to wrap the 2 x 3 lanes
+    import ctypes as C
+    h = C.c_void_p()
+    devs = (C.c_int * 2)(0, 5)
+    from gzp_b200 import _lib
+    sink = _lib.SINK_FN(lambda u, p, n: 0)
+    assert L.gzpb_writer_create_multi(C.byref(h), devs, 2, oracle.BGZF, 6, 0, 2, C.cast(sink, C.c_void_p), None) == -8   # no device 5
+
+
+def test_emu_c_writer_surfaces_sink_errors():
+    """A failing sink (`W: Write` returning an error) fails the stream with GZPB_EIO on the next call (par/compress.rs:428-440)."""
+    L = emu.lib()
+    got, writes, rc, _ = _drive_c_writer(L, oracle.BGZF, 6, 65280, 1, TEXT * 2, random.Random(1), flushes=(1,), sink_fail_after=2)
+    assert rc == -6
+
+
+def test_emu_submit_poll_tickets():
+    """gzpb_submit / gzpb_poll: tickets complete in order, GZPB_EAGAIN when every lane is in flight or the
+    device is not done, outputs equal the synchronous gzpb_encode_batch; pinned blocks go by DMA in place."""
+    import ctypes as C
+    from gzp_b200 import _lib
+    L = emu.lib()
+    EAGAIN = -15
+    h = C.c_void_p()
+    assert L.gzpb_create(C.byref(h), 0, oracle.GZIP, 6, 40000, 4) == 0
+    blocks = [TEXT[i * 40000:(i + 1) * 40000] for i in range(7)]
+    pinned = L.gzpb_host_alloc(8 * 40000)
+    C.memmove(pinned, TEXT[:7 * 40000], 7 * 40000)
+    cap = L.gzpb_encode_capacity(oracle.GZIP, 40000) + 64
+    want = [oracle.encode_block(oracle.GZIP, 6, b, (blocks[i - 1][-32768:] if i else None), i == 6) for i, b in enumerate(blocks)]
+
+    def make(lo, hi, use_pinned):
+        n = hi - lo
+        ins, outs, keep = (_lib.BlockIn * n)(), (_lib.BlockOut * n)(), []
+        for k, i in enumerate(range(lo, hi)):
+            if use_pinned:
+                ins[k].ptr = pinned + i * 40000
+                if i:
+                    ins[k].dict = pinned + i * 40000 - 32768
+            else:
+                src = C.create_string_buffer(blocks[i], 40000); keep.append(src)
+                ins[k].ptr = C.cast(src, C.c_void_p)
+                if i:
+                    d = C.create_string_buffer(blocks[i - 1][-32768:], 32768); keep.append(d)
+                    ins[k].dict = C.cast(d, C.c_void_p)
+            ins[k].len = 40000
+            ins[k].dict_len = 32768 if i else 0
+            ins[k].is_last = int(i == 6)
+            dst = C.create_string_buffer(cap); keep.append(dst)
+            outs[k].dst = C.cast(dst, C.c_void_p); outs[k].cap = cap
+        return ins, outs, keep
+
+    for use_pinned in (True, False):
+        batches = [make(0, 2, use_pinned), make(2, 4, use_pinned), make(4, 7, use_pinned), make(0, 1, use_pinned)]
+        tickets = []
+        for ins, outs, _ in batches[:3]:
+            t = C.c_uint64(0)
+            assert L.gzpb_submit(h, len(ins), ins, outs, C.byref(t)) == 0
+            tickets.append(t.value)
+        assert tickets == sorted(tickets) and len(set(tickets)) == 3
+        t4 = C.c_uint64(0)
+        assert L.gzpb_submit(h, 1, batches[3][0], batches[3][1], C.byref(t4)) == EAGAIN      # three lanes in flight
+        assert L.gzpb_encode_batch(h, 1, batches[3][0], batches[3][1]) == EAGAIN             # tickets pending
+        assert L.gzpb_poll(h, tickets[1], 0) == EAGAIN                                       # lazy device: nothing ran yet
+        assert L.gzpb_poll(h, tickets[1], 1) == 0                                            # completes tickets 0 and 1
+        assert L.gzpb_poll(h, tickets[0], 0) == 0
+        assert L.gzpb_submit(h, 1, batches[3][0], batches[3][1], C.byref(t4)) == 0           # a lane is free again
+        assert L.gzpb_poll(h, t4.value, 1) == 0                                              # also completes ticket 2
+        assert L.gzpb_poll(h, t4.value + 1, 1) == -9                                         # unknown ticket
+        got = []
+        for ins, outs, _ in batches[:3]:
+            for k in range(len(ins)):
+                assert outs[k].status == 0
+                got.append(C.string_at(outs[k].dst, outs[k].out_len))
+                assert outs[k].check_sum == zlib.crc32(blocks[len(got) - 1]) and outs[k].check_amount == 40000
+        assert got == want
+        assert C.string_at(batches[3][1][0].dst, batches[3][1][0].out_len) == oracle.encode_block(oracle.GZIP, 6, blocks[0], None, False)
+    # more blocks than a lane holds: invalid for submit, fine for the synchronous call
+    ins, outs, _ = make(0, 7, False)
+    t = C.c_uint64(0)
+    assert L.gzpb_submit(h, 7, ins, outs, C.byref(t)) == -9
+    assert L.gzpb_encode_batch(h, 7, ins, outs) == 0
+    assert [C.string_at(outs[k].dst, outs[k].out_len) for k in range(7)] == want
+    L.gzpb_host_free(pinned)
+    L.gzpb_destroy(h)
