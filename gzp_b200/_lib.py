@@ -50,6 +50,10 @@ _SIGS = {
     "gzpb_writer_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "gzpb_submit": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(BlockIn), C.POINTER(BlockOut), C.POINTER(C.c_uint64)]),
     "gzpb_poll": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int]),
+    "gzpb_writer_reserve": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+    "gzpb_writer_commit": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "gzpb_compress_file": (C.c_int, [C.POINTER(C.c_int), C.c_size_t, C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_char_p, C.c_char_p,
+                                     C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "gzpb_writer_write": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "gzpb_writer_flush": (C.c_int, [C.c_void_p]),
     "gzpb_writer_finish": (C.c_int, [C.c_void_p]),

@@ -239,6 +239,7 @@ class ParCompressBuilder:
         self._level = Compression.new(3)                      # par/compress.rs:58
         self._pin = None
         self._device = 0
+        self._devices = None
         self._blocks_in_flight = 256
 
     @classmethod
@@ -273,7 +274,17 @@ class ParCompressBuilder:
         self._blocks_in_flight = int(n)
         return self
 
+    def devices(self, indices):
+        """Use the native pipelined writer (gzpb_writer_create_multi) over these GPUs: device batches of
+        `blocks_in_flight` blocks are dealt round-robin, one ordered output."""
+        self._devices = [int(i) for i in indices]
+        if not self._devices:
+            raise GzpError(-9, "devices() needs at least one GPU index")
+        return self
+
     def from_writer(self, writer):
+        if self._devices is not None:
+            return NativeParCompress(self.format, writer, self._level, self._buffer_size, self._devices, self._blocks_in_flight)
         return ParCompress(self.format, writer, self._level, self._buffer_size, self._device, self._blocks_in_flight)
 
     from_borrowed_writer = from_writer
@@ -382,6 +393,95 @@ class ParCompress:
         if not self._finished and exc[0] is None:
             self.finish()
         return False
+
+
+class NativeParCompress:
+    """ParCompress<F, W> on the C writer object (gzpb_writer_*, include/gzpb.h): the chunker, the pinned slabs,
+    the batches in flight on one or several GPUs and the ordered hand-over to `writer.write` all live in
+    libgzpb.so; Python only forwards `write` / `flush` / `finish` (par/compress.rs:377-388, 413-468)."""
+
+    def __init__(self, fmt, writer, level, buffer_size, devices=(0,), blocks_in_flight=0):
+        self._lib = _lib.load()
+        self.format = fmt
+        self.writer = writer
+        self.level = level
+        self.buffer_size = buffer_size
+        self._sink_error = None
+        self._finished = False
+
+        def _sink(_user, ptr, n):
+            try:
+                self.writer.write(C.string_at(ptr, n))
+                return 0
+            except Exception as e:                             # surfaces as GzpError::Io on the next call
+                self._sink_error = e
+                return 1
+
+        self._cb = _lib.SINK_FN(_sink)
+        h = C.c_void_p()
+        devs = (C.c_int * len(devices))(*devices)
+        rc = self._lib.gzpb_writer_create_multi(C.byref(h), devs, len(devices), fmt.ID, _lvl(level), buffer_size,
+                                                blocks_in_flight, C.cast(self._cb, C.c_void_p), None)
+        if rc != 0:
+            raise GzpError(rc)
+        self._h = h
+
+    def _check(self, rc):
+        if rc != 0:
+            err = GzpError(rc)
+            err.__cause__ = self._sink_error
+            raise err
+
+    def write(self, data):
+        if self._h is None:
+            raise GzpError(-7)
+        data = bytes(data)
+        self._check(self._lib.gzpb_writer_write(self._h, data, len(data)))
+        return len(data)
+
+    def flush(self):
+        if self._h is None:
+            raise GzpError(-7)
+        self._check(self._lib.gzpb_writer_flush(self._h))
+
+    def stats(self):
+        v = [C.c_uint64(0) for _ in range(4)]
+        self._lib.gzpb_writer_stats(self._h, *[C.byref(x) for x in v])
+        return dict(zip(("bytes_in", "bytes_out", "batches", "sink_calls"), (x.value for x in v)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.gzpb_writer_destroy(self._h)
+            self._h = None
+            self._cb = None
+
+    def finish(self):
+        if self._h is None:
+            raise GzpError(-7)
+        rc = self._lib.gzpb_writer_finish(self._h)
+        self._finished = True
+        self.close()
+        self._check(rc)
+        if hasattr(self.writer, "flush"):
+            self.writer.flush()
+        return self.writer
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):                                   # Drop -> finish (par/compress.rs:391-402)
+        if self._h is not None:
+            if exc[0] is None:
+                self.finish()
+            else:
+                self.close()
+        return False
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class ZBuilder:
@@ -555,6 +655,19 @@ class SyncZBuilder:
         if self.format.ID == MGZIP:
             return SyncZ(MgzipSyncWriter(writer, self._level, device=self._device))
         return SyncZ(ParCompress(self.format, writer, self._level, self.format.DEFAULT_BUFSIZE, self._device, 16))
+
+
+def compress_file(in_path, out_path, fmt=Gzip, level=3, buffer_size=0, devices=(0,), blocks_in_flight=0):
+    """File -> compressed file through the native writer (gzpb_compress_file): read(2) lands in the pinned
+    slabs, the ordered output is written from pinned memory.  Returns (bytes_in, bytes_out)."""
+    fmt = fmt() if isinstance(fmt, type) else fmt
+    devs = (C.c_int * len(devices))(*devices)
+    bi, bo = C.c_uint64(0), C.c_uint64(0)
+    rc = _lib.load().gzpb_compress_file(devs, len(devices), fmt.ID, _lvl(level), buffer_size, blocks_in_flight,
+                                        os.fsencode(in_path), os.fsencode(out_path), C.byref(bi), C.byref(bo))
+    if rc != 0:
+        raise GzpError(rc)
+    return bi.value, bo.value
 
 
 def bgzf_index(stream):

@@ -907,22 +907,43 @@ extern "C" int gzpb_writer_create(gzpb_writer **out, int device, int format, int
     return gzpb_writer_create_multi(out, &device, 1, format, level, buffer_size, blocks_in_flight, sink, user);
 }
 
+extern "C" int gzpb_writer_reserve(gzpb_writer *w, void **ptr, size_t *room)
+{
+    if (!w || !ptr || !room) return GZPB_EINVAL;
+    if (w->finished) return GZPB_ECHANNEL;
+    if (w->error) return w->error;
+    *ptr = w->slabs[w->cur] + w->fill;
+    *room = w->slab_cap - w->fill;                                // never 0: at most buffer_size bytes are held back uncut
+    return GZPB_OK;
+}
+
+extern "C" int gzpb_writer_commit(gzpb_writer *w, size_t n)
+{
+    if (!w || n > w->slab_cap - w->fill) return GZPB_EINVAL;
+    if (w->finished) return GZPB_ECHANNEL;
+    if (w->error) return w->error;
+    const bool dict_fmt = gzpb_needs_dict(w->format) != 0;
+    w->bytes_in += n;
+    w->fill += n;
+    while (w->fill - w->cut > w->buffer_size) {                   // strict '>' (par/compress.rs:415)
+        int rc = writer_cut(w, w->buffer_size, false, dict_fmt);  // dictionary = last 32 KiB of this block (:419-423)
+        if (rc != GZPB_OK) return rc;
+    }
+    return GZPB_OK;
+}
+
 extern "C" int gzpb_writer_write(gzpb_writer *w, const void *data, size_t len)
 {
     if (!w || (len && !data)) return GZPB_EINVAL;
     if (w->finished) return GZPB_ECHANNEL;
     if (w->error) return w->error;
     const uint8_t *p = (const uint8_t *)data;
-    const bool dict_fmt = gzpb_needs_dict(w->format) != 0;
-    w->bytes_in += len;
     while (len) {
         const size_t k = std::min(len, w->slab_cap - w->fill);
-        memcpy(w->slabs[w->cur] + w->fill, p, k);
-        w->fill += k; p += k; len -= k;
-        while (w->fill - w->cut > w->buffer_size) {               // strict '>' (par/compress.rs:415)
-            int rc = writer_cut(w, w->buffer_size, false, dict_fmt);   // dictionary = last 32 KiB of this block (:419-423)
-            if (rc != GZPB_OK) return rc;
-        }
+        memcpy(w->slabs[w->cur] + w->fill, p, k);                 // the one host copy (par/compress.rs:414)
+        p += k; len -= k;
+        int rc = gzpb_writer_commit(w, k);
+        if (rc != GZPB_OK) return rc;
     }
     return GZPB_OK;
 }
@@ -989,3 +1010,59 @@ extern "C" void gzpb_writer_destroy(gzpb_writer *w)
     for (gzpb_ctx *c : w->ctx) gzpb_destroy(c);
     delete w;
 }
+
+// ---- file ingest / egress around the writer --------------------------------
+// read(2) lands in the writer's pinned slab at its fill position (no intermediate buffer, no second
+// host copy), the ordered device output goes to the output file with write(2) from pinned memory.
+#ifndef GZPB_EMU_NO_FILES
+#include <errno.h>
+#include <fcntl.h>
+#include <unistd.h>
+
+static int file_sink(void *user, const void *data, size_t len)
+{
+    const int fd = *(const int *)user;
+    const uint8_t *p = (const uint8_t *)data;
+    while (len) {
+        ssize_t k = write(fd, p, len);
+        if (k < 0) { if (errno == EINTR) continue; return 1; }
+        p += k; len -= (size_t)k;
+    }
+    return 0;
+}
+
+extern "C" int gzpb_compress_file(const int *devices, size_t ndevices, int format, int level, size_t buffer_size,
+                                  size_t blocks_in_flight, const char *in_path, const char *out_path,
+                                  uint64_t *bytes_in, uint64_t *bytes_out)
+{
+    if (!in_path || !out_path) return GZPB_EINVAL;
+    const int fin = open(in_path, O_RDONLY);
+    if (fin < 0) return GZPB_EIO;
+    int fout = open(out_path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    if (fout < 0) { close(fin); return GZPB_EIO; }
+#ifdef POSIX_FADV_SEQUENTIAL
+    posix_fadvise(fin, 0, 0, POSIX_FADV_SEQUENTIAL);
+#endif
+    gzpb_writer *w = nullptr;
+    int rc = gzpb_writer_create_multi(&w, devices, ndevices, format, level, buffer_size, blocks_in_flight, file_sink, &fout);
+    while (rc == GZPB_OK) {
+        void *p = nullptr;
+        size_t room = 0;
+        rc = gzpb_writer_reserve(w, &p, &room);
+        if (rc != GZPB_OK) break;
+        ssize_t k = read(fin, p, std::min(room, (size_t)16 << 20));
+        if (k < 0) { if (errno == EINTR) continue; rc = GZPB_EIO; break; }
+        if (k == 0) break;
+        rc = gzpb_writer_commit(w, (size_t)k);
+    }
+    if (w) {
+        int r = gzpb_writer_finish(w);
+        if (rc == GZPB_OK) rc = r;
+        gzpb_writer_stats(w, bytes_in, bytes_out, nullptr, nullptr);
+        gzpb_writer_destroy(w);
+    }
+    close(fin);
+    if (close(fout) != 0 && rc == GZPB_OK) rc = GZPB_EIO;
+    return rc;
+}
+#endif

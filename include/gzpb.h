@@ -134,11 +134,25 @@ int gzpb_writer_create(gzpb_writer **w, int device, int format, int level, size_
 int gzpb_writer_create_multi(gzpb_writer **w, const int *devices, size_t ndevices, int format, int level,
                              size_t buffer_size, size_t blocks_in_flight, gzpb_sink_fn sink, void *user);
 int gzpb_writer_write(gzpb_writer *w, const void *buf, size_t len);
+/* Zero-copy form of write for callers that can produce their bytes in place (`Read::read(&mut buf)`, read(2)
+ * from a file): gzpb_writer_reserve returns the writer's fill position inside its pinned slab and how many
+ * contiguous bytes fit there (never 0); gzpb_writer_commit(n) declares the first n of them written and cuts
+ * blocks exactly like write.  Removes the single-caller memcpy of src/par/compress.rs:414 from the path. */
+int gzpb_writer_reserve(gzpb_writer *w, void **ptr, size_t *room);
+int gzpb_writer_commit(gzpb_writer *w, size_t n);
 int gzpb_writer_flush(gzpb_writer *w);
 int gzpb_writer_finish(gzpb_writer *w);
 void gzpb_writer_destroy(gzpb_writer *w);
 /* counters of a writer: bytes written by the caller, bytes handed to the sink, device batches, sink calls */
 int gzpb_writer_stats(gzpb_writer *w, uint64_t *bytes_in, uint64_t *bytes_out, uint64_t *batches, uint64_t *sink_calls);
+
+/* File to file (the ingest / egress step either side of the path): read(2) fills the
+ * writer's pinned slabs directly, the ordered output is written from pinned memory.  What
+ * `ZBuilder::<F, _>::new().from_writer(File::create(out))` + `io::copy(&mut File::open(in), &mut z)` + `finish`
+ * does in the reference (README.md:60-75), on `ndevices` GPUs. */
+int gzpb_compress_file(const int *devices, size_t ndevices, int format, int level, size_t buffer_size,
+                       size_t blocks_in_flight, const char *in_path, const char *out_path, uint64_t *bytes_in,
+                       uint64_t *bytes_out);
 
 /* Device-resident form of the same path, asynchronous on `cuda_stream`:
  * d_in holds nunits slots of GZPB_IN_STRIDE bytes, d_len/d_flags one u32 per unit

@@ -393,7 +393,14 @@ cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s)
     return cudaSuccess;
 }
 cudaError_t cudaEventSynchronize(cudaEvent_t e) { complete_event(e, e->recorded, 0); return cudaSuccess; }
-cudaError_t cudaEventQuery(cudaEvent_t e) { return e->completed >= e->recorded ? cudaSuccess : cudaErrorNotReady; }
+// a query lets "time pass": the stream holding the pending record advances by ONE operation, so polling
+// loops terminate while a query right after a submit still sees cudaErrorNotReady
+cudaError_t cudaEventQuery(cudaEvent_t e)
+{
+    if (e->completed >= e->recorded) return cudaSuccess;
+    if (e->last && !e->last->q.empty()) step(e->last, 0);
+    return e->completed >= e->recorded ? cudaSuccess : cudaErrorNotReady;
+}
 cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b)
 {
     complete_event(a, a->recorded, 0); complete_event(b, b->recorded, 0);

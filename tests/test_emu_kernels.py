@@ -396,3 +396,71 @@ def test_emu_submit_poll_tickets():
     assert [C.string_at(outs[k].dst, outs[k].out_len) for k in range(7)] == want
     L.gzpb_host_free(pinned)
     L.gzpb_destroy(h)
+
+
+def test_emu_native_parcompress_wrapper(emu_backend):
+    """ParCompressBuilder(...).devices([...]) -> NativeParCompress (the C writer behind the reference's writer API)."""
+    import gzp_b200
+    sink = io.BytesIO()
+    w = gzp_b200.ParCompressBuilder(gzp_b200.Gzip).compression_level(6).buffer_size(40000).blocks_in_flight(2).devices([0]).from_writer(sink)
+    assert isinstance(w, gzp_b200.NativeParCompress)
+    writes = [TEXT[:100000], TEXT[100000:100001], TEXT[100001:]]
+    w.write(writes[0]); w.flush(); w.write(writes[1]); w.write(writes[2])
+    st = w.stats()
+    assert st["bytes_in"] == len(TEXT)
+    assert w.finish() is sink
+    assert sink.getvalue() == oracle.compress_stream(oracle.GZIP, 6, 40000, writes, {0})
+    assert gzip.decompress(sink.getvalue()) == TEXT
+    with pytest.raises(gzp_b200.GzpError):
+        w.write(b"x")
+
+    class Broken:
+        def write(self, b):
+            raise OSError("disk full")
+
+    w = gzp_b200.ParCompressBuilder(gzp_b200.Bgzf).blocks_in_flight(1).devices([0]).from_writer(Broken())
+    with pytest.raises(gzp_b200.GzpError) as ei:
+        w.write(TEXT)
+        w.finish()
+    assert ei.value.variant == "Io" and isinstance(ei.value.__cause__, OSError)
+    # Drop finishes the stream (par/compress.rs:391-402)
+    sink = io.BytesIO()
+    with gzp_b200.ParCompressBuilder(gzp_b200.Bgzf).devices([0]).from_writer(sink) as w:
+        w.write(b"abc")
+    assert gzip.decompress(sink.getvalue()) == b"abc"
+
+
+def test_emu_compress_file_and_zero_copy_reserve(emu_backend, tmp_path):
+    """gzpb_compress_file (read(2) into the pinned slabs -> ordered output file) and the reserve/commit form of
+    write produce the oracle's stream."""
+    import ctypes as C
+    import gzp_b200
+    from gzp_b200 import _lib
+    src, dst = tmp_path / "in.txt", tmp_path / "out.gz"
+    src.write_bytes(TEXT * 2)
+    n_in, n_out = gzp_b200.compress_file(src, dst, gzp_b200.Gzip, 6, 40000, devices=(0,), blocks_in_flight=3)
+    got = dst.read_bytes()
+    assert (n_in, n_out) == (2 * len(TEXT), len(got))
+    assert got == oracle.compress_stream(oracle.GZIP, 6, 40000, [TEXT * 2])
+    assert gzip.decompress(got) == TEXT * 2
+    with pytest.raises(gzp_b200.GzpError) as ei:
+        gzp_b200.compress_file(tmp_path / "missing", dst)
+    assert ei.value.variant == "Io"
+    # reserve / commit: bytes produced in place, odd piece sizes
+    L = emu.lib()
+    chunks = bytearray()
+    sink = _lib.SINK_FN(lambda u, p, n: (chunks.extend(C.string_at(p, n)), 0)[1])
+    h = C.c_void_p()
+    assert L.gzpb_writer_create(C.byref(h), 0, oracle.BGZF, 6, 65280, 2, C.cast(sink, C.c_void_p), None) == 0
+    pos, rnd = 0, random.Random(5)
+    while pos < len(TEXT):
+        p, room = C.c_void_p(0), C.c_size_t(0)
+        assert L.gzpb_writer_reserve(h, C.byref(p), C.byref(room)) == 0 and room.value > 0
+        k = min(room.value, len(TEXT) - pos, rnd.randrange(1, 200000))
+        C.memmove(p, TEXT[pos:pos + k], k)
+        assert L.gzpb_writer_commit(h, k) == 0
+        pos += k
+    assert L.gzpb_writer_commit(h, 1 << 40) == -9
+    assert L.gzpb_writer_finish(h) == 0
+    L.gzpb_writer_destroy(h)
+    assert bytes(chunks) == oracle.compress_stream(oracle.BGZF, 6, 65280, [TEXT])
