@@ -1597,13 +1597,16 @@ static Geo make_geo(const DeflateBatch &b)
 
 cudaError_t launch_deflate_pipeline(const DeflateBatch &b, cudaStream_t st)
 {
-    static bool attr_done = false;
+    static bool attr_done[64] = {};          // function attributes are per device (several GPUs in one process)
     const int chain_smem = (65536 + 32768) * 2;
     const int match_smem = kInStride + 65536 * 2;
-    if (!attr_done) {
+    int cur_dev = 0;
+    cudaGetDevice(&cur_dev);
+    if (cur_dev < 0 || cur_dev >= 64) return cudaErrorInvalidValue;
+    if (!attr_done[cur_dev]) {
         cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, chain_smem);
         cudaFuncSetAttribute(k_match, cudaFuncAttributeMaxDynamicSharedMemorySize, match_smem);
-        attr_done = true;
+        attr_done[cur_dev] = true;
     }
     if (b.nunits == 0) return cudaSuccess;
     LevelParams lp;
