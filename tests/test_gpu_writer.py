@@ -96,8 +96,9 @@ def test_native_writer_over_all_gpus():
 def test_submit_poll_tickets_on_gpu(text_corpus):
     L = _lib.load()
     h = C.c_void_p()
-    bs, nblk = 65280, 24
-    assert L.gzpb_create(C.byref(h), 0, BGZF, 6, bs, 8) == 0
+    bs, nblk, per = 65280, 12, 4                                 # 3 batches of 4 blocks = every lane in flight
+    assert nblk * bs <= len(text_corpus)
+    assert L.gzpb_create(C.byref(h), 0, BGZF, 6, bs, per) == 0
     blocks = [text_corpus[i * bs:(i + 1) * bs] for i in range(nblk)]
     want = [oracle.encode_block(BGZF, 6, b, None, False) for b in blocks]
     pinned = L.gzpb_host_alloc(nblk * bs)
@@ -105,9 +106,9 @@ def test_submit_poll_tickets_on_gpu(text_corpus):
     cap = L.gzpb_encode_capacity(BGZF, bs) + 64
     for use_pinned in (True, False):
         keep, batches = [], []
-        for lo in range(0, nblk, 8):
-            ins, outs = (_lib.BlockIn * 8)(), (_lib.BlockOut * 8)()
-            for k in range(8):
+        for lo in range(0, nblk, per):
+            ins, outs = (_lib.BlockIn * per)(), (_lib.BlockOut * per)()
+            for k in range(per):
                 if use_pinned:
                     ins[k].ptr = pinned + (lo + k) * bs
                 else:
@@ -120,16 +121,16 @@ def test_submit_poll_tickets_on_gpu(text_corpus):
         tickets = []
         for ins, outs in batches:
             t = C.c_uint64(0)
-            assert L.gzpb_submit(h, 8, ins, outs, C.byref(t)) == 0
+            assert L.gzpb_submit(h, per, ins, outs, C.byref(t)) == 0
             tickets.append(t.value)
         t = C.c_uint64(0)
-        assert L.gzpb_submit(h, 8, batches[0][0], batches[0][1], C.byref(t)) == -15          # GZPB_EAGAIN: 3 lanes in flight
+        assert L.gzpb_submit(h, per, batches[0][0], batches[0][1], C.byref(t)) == -15          # GZPB_EAGAIN: 3 lanes in flight
         while True:                                                                          # non-blocking poll until done
             rc = L.gzpb_poll(h, tickets[-1], 0)
             if rc != -15:
                 break
         assert rc == 0
-        got = [C.string_at(outs[k].dst, outs[k].out_len) for ins, outs in batches for k in range(8)]
+        got = [C.string_at(outs[k].dst, outs[k].out_len) for ins, outs in batches for k in range(per)]
         assert got == want
     L.gzpb_host_free(pinned)
     L.gzpb_destroy(h)
