@@ -153,9 +153,10 @@ def text_stream(nbytes, seed=0x5EED0001):
     else:
         base = text(TEXT_PERIOD, seed)
         try:
-            with open(cache + ".tmp", "wb") as f:
+            tmp = f"{cache}.{os.getpid()}.tmp"          # several ranks may build the cache at once
+            with open(tmp, "wb") as f:
                 f.write(base)
-            os.replace(cache + ".tmp", cache)
+            os.replace(tmp, cache)
         except OSError:
             pass
     reps = nbytes // TEXT_PERIOD + 1
