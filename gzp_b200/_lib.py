@@ -45,6 +45,7 @@ _SIGS = {
     "gzpb_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "gzpb_kernel_ms": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "gzpb_launch_count": (C.c_uint64, [C.c_void_p]),
+    "gzpb_ctx_variant": (C.c_char_p, [C.c_void_p]),
     "gzpb_writer_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p]),
     "gzpb_writer_create_multi": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_size_t, C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p]),
     "gzpb_writer_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),

@@ -298,13 +298,15 @@ k_split(const __grid_constant__ Geo g, uint32_t *__restrict__ lists, uint32_t *_
 
 __global__ void __launch_bounds__(32)
 k_link(const __grid_constant__ Geo g, const uint32_t *__restrict__ lists, const uint32_t *__restrict__ list_start,
-       uint16_t *__restrict__ next4, uint16_t *__restrict__ prev3, uint8_t *__restrict__ clen_g)
+       uint16_t *__restrict__ next4, uint16_t *__restrict__ prev3, uint8_t *__restrict__ clen_g, int only3)
 {
     // hash4 job: u16 head[4096] + u8 cnt[4096] (occurrences so far per bucket = chain-length estimate);
     // hash3 job: u16 head[8192]
     __shared__ __align__(16) uint16_t head[1 << kBits3];
     uint8_t *cnt = (uint8_t *)(head + (1 << kBits4));
-    const uint32_t sub = blockIdx.x / kSplitLists, job = blockIdx.x % kSplitLists;
+    // only3: the hash4 lists are grouped by k_group (match path v2), this launch links the hash3 lists only
+    const uint32_t sub = only3 ? blockIdx.x / kL3 : blockIdx.x / kSplitLists;
+    const uint32_t job = only3 ? kL4 + blockIdx.x % kL3 : blockIdx.x % kSplitLists;
     const Sub sb = sub_geometry(g, sub);
     if (!sb.valid) return;
     const uint32_t lane = threadIdx.x, lt = lanemask_lt();
@@ -385,6 +387,14 @@ k_link(const __grid_constant__ Geo g, const uint32_t *__restrict__ lists, const 
 // depend on parsing decisions, so all positions are searched in parallel.
 // =============================================================================
 constexpr int kMatchThreads = 1024;
+#ifdef GZPB_EMU
+// emulator-only statistics (tests/emu): chain nodes visited per position and the processing order of the last
+// sub-unit searched, for estimating lock-step lane utilisation without a GPU
+extern "C" { uint16_t gzpb_emu_visited[65536]; uint16_t gzpb_emu_order[65536]; uint32_t gzpb_emu_npos; }
+#define EMU_STAT(p, i, v, np) do { gzpb_emu_visited[p] = (uint16_t)(v); gzpb_emu_order[i] = (uint16_t)(p); gzpb_emu_npos = (np); } while (0)
+#else
+#define EMU_STAT(p, i, v, np) do { } while (0)
+#endif
 
 __device__ __forceinline__ uint32_t lz_extend(const uint32_t *s_in, uint32_t p, uint32_t q, uint32_t len, uint32_t maxlen)
 {
@@ -536,6 +546,231 @@ k_match(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, cons
         if (M2) { if (!haveC) { lenC = lenA; offC = boff; } M2[p] = (lenC ? lenC - 3 : 0) | (offC << 8); }
         if (!lazy) { lenB = 0; offB = 0; }
         M[p] = pack_entry(lenA, boff, lenB, offB, d3 != 0, off3);
+        EMU_STAT(p, i, visited, npos);
+    }
+}
+
+// =============================================================================
+// Match path v2 (GZPB_MATCH_V2=1): hash GROUPS instead of linked chains.
+//
+// k_group: one single-warp job per hash4 list of k_split (4096 consecutive bucket
+// values, entries in position order).  A stable counting sort by bucket turns the
+// list into an array G of positions grouped by hash value, increasing inside a
+// group: the hash chain of position p is then simply G[idx(p) - 1], G[idx(p) - 2],
+// ... down to the start of its group — the same nodes, in the same order, as the
+// linked chain of k_link, but addressable without pointer chasing.  Written per
+// position: idx(p) and occ(p) = number of earlier positions in p's group.
+//
+// k_match2: like k_match, with G staged in shared memory instead of next4[].  The
+// exact number of chain nodes a search may visit (same hash, inside the 32 KiB
+// window, at most `depth`) is known up front, so (1) the counting sort by chain
+// length is exact and the 32 positions a warp walks in lock step finish together,
+// (2) the candidate loads G[idx - k] do not depend on the previous node.
+// Bit-identical results (tests/test_emu_kernels.py::test_emu_match_v2_*).
+// =============================================================================
+constexpr int kGroupWords = (1 << kBits4) + ((1 << kBits4) >> 7);   // one pad word per 128 counters: conflict-free column walks
+__device__ __forceinline__ uint32_t gphys(uint32_t b) { return b + (b >> 7); }
+
+__global__ void __launch_bounds__(32)
+k_group(const __grid_constant__ Geo g, const uint32_t *__restrict__ lists, const uint32_t *__restrict__ list_start,
+        uint16_t *__restrict__ group_g, uint16_t *__restrict__ gidx_g, uint16_t *__restrict__ gocc_g)
+{
+    __shared__ uint32_t cnt[kGroupWords];          // (group start << 16) | members placed so far
+    const uint32_t sub = blockIdx.x / kL4, job = blockIdx.x % kL4;
+    const Sub sb = sub_geometry(g, sub);
+    if (!sb.valid) return;
+    const uint32_t lane = threadIdx.x, lt = lanemask_lt();
+    const uint32_t *ls = list_start + (size_t)sub * kLsStride;
+    const uint32_t *arr = lists + (size_t)sub * 2 * kMaxUnitBytes;
+    const uint32_t beg = ls[job], end = ls[job + 1];
+    uint16_t *G = group_g + (size_t)sub * kMaxUnitBytes;
+    uint16_t *gidx = gidx_g + (size_t)sub * kMaxUnitBytes;
+    uint16_t *gocc = gocc_g + (size_t)sub * kMaxUnitBytes;
+    constexpr uint32_t kMask = (1u << kBits4) - 1;
+    for (uint32_t i = lane; i < (uint32_t)kGroupWords; i += 32) cnt[i] = 0;
+    __syncwarp();
+    // pass 1: group sizes
+    for (uint32_t i = beg + lane; i < end; i += 32) atomicAdd(&cnt[gphys(__ldg(arr + i) & kMask)], 1u);
+    __syncwarp();
+    // exclusive prefix: lane l owns buckets [128 l, 128 l + 128)
+    {
+        uint32_t sum = 0;
+        for (uint32_t j = 0; j < 128; j++) sum += cnt[gphys(lane * 128 + j)];
+        uint32_t inc = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { uint32_t v = __shfl_up_sync(0xFFFFFFFFu, inc, d); if (lane >= (uint32_t)d) inc += v; }
+        uint32_t run = inc - sum;
+        for (uint32_t j = 0; j < 128; j++) { const uint32_t a = gphys(lane * 128 + j); const uint32_t c = cnt[a]; cnt[a] = run << 16; run += c; }
+    }
+    __syncwarp();
+    // pass 2: stable scatter, one tile of 32 list entries at a time (position order)
+    for (uint32_t base0 = beg; base0 < end; base0 += 32) {
+        const uint32_t i = base0 + lane;
+        const bool act = i < end;
+        const uint32_t e = act ? __ldg(arr + i) : 0u;
+        const uint32_t b = e & kMask, p = e >> 16;
+        const uint32_t m = __match_any_sync(0xFFFFFFFFu, act ? b : 0xFFFFu);
+        const uint32_t v = act ? cnt[gphys(b)] : 0u;
+        __syncwarp();                                // every lane has read its counter before a leader advances one
+        if (act && (m & lt) == 0) cnt[gphys(b)] = v + (uint32_t)__popc(m);
+        __syncwarp();
+        if (act) {
+            const uint32_t o = (v & 0xFFFFu) + (uint32_t)__popc(m & lt);
+            const uint32_t slot = beg + (v >> 16) + o;
+            G[slot] = (uint16_t)p;
+            gidx[p] = (uint16_t)slot;
+            gocc[p] = (uint16_t)min(o, 65535u);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kMatchThreads, 1)
+k_match2(const __grid_constant__ Geo g, const uint16_t *__restrict__ group_g, const uint16_t *__restrict__ prev3g,
+         const uint16_t *__restrict__ gidx_g, uint16_t *__restrict__ gocc_g,
+         uint64_t *__restrict__ mtab, uint32_t *__restrict__ mtab2, uint8_t *__restrict__ clen_g, uint16_t *__restrict__ order_g,
+         int depth, int nice, int lazy, int ht)
+{
+    GZPB_DYN_SMEM(smem);
+    uint32_t *s_in = (uint32_t *)smem;
+    uint16_t *s_G = (uint16_t *)(smem + kInStride);
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t s_whist[32][128];
+    __shared__ uint32_t s_tot[128];
+    const uint32_t tid = threadIdx.x;
+    const Sub sb = sub_geometry(g, blockIdx.x);
+    if (!sb.valid) return;
+    const uint32_t n = sb.len;
+    const uint8_t *in = g.in + (size_t)sb.u * g.in_stride + sb.h;
+    uint64_t *M = mtab + (size_t)sb.u * g.m_stride + sb.h;
+    uint32_t *M2 = (lazy == 2) ? mtab2 + (size_t)sb.u * g.m_stride + sb.h : nullptr;   // lazy2: depth/4 column
+
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (n >= 5) {
+        if (tid == 0) {
+            uint32_t bin = (n + 15u) & ~15u, bnx = (n * 2 + 15u) & ~15u;
+            mbar_expect_tx(&bar, bin + bnx);
+            tma_load_1d(s_in, in, bin, &bar);
+            tma_load_1d(s_G, group_g + (size_t)blockIdx.x * kMaxUnitBytes, bnx, &bar);
+        }
+        mbar_wait(&bar, 0);
+    }
+    const uint16_t *p3 = prev3g + (size_t)blockIdx.x * kMaxUnitBytes;
+    const uint16_t *gidx = gidx_g + (size_t)blockIdx.x * kMaxUnitBytes;
+    uint16_t *gocc = gocc_g + (size_t)blockIdx.x * kMaxUnitBytes;
+    const uint32_t depthB = (uint32_t)depth >> 1, depthC = (uint32_t)depth >> 2;
+
+    // ---- phase 1: exact number of chain nodes per position, counting sort by it ----
+    uint8_t *clen = clen_g + (size_t)blockIdx.x * kMaxUnitBytes;
+    uint16_t *order = order_g + (size_t)blockIdx.x * kMaxUnitBytes;
+    const uint32_t warp = tid >> 5;
+    for (uint32_t i = tid; i < 32 * 128; i += kMatchThreads) (&s_whist[0][0])[i] = 0;
+    __syncthreads();
+    for (uint32_t p = sb.nb + tid; p < sb.ne; p += kMatchThreads) {
+        uint32_t c = 0;
+        if (n - p >= 5) {
+            const uint32_t base = gidx[p];
+            c = min((uint32_t)gocc[p], (uint32_t)depth);
+            if (c && p - (uint32_t)s_G[base - c] >= (uint32_t)kWindow) {
+                // the c-th node lies outside the window: nodes get farther with k, find the first one outside
+                uint32_t lo = 1, hi = c;                      // invariant: node hi is outside
+                while (lo < hi) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (p - (uint32_t)s_G[base - mid] >= (uint32_t)kWindow) hi = mid; else lo = mid + 1;
+                }
+                c = hi - 1;
+            }
+        }
+        gocc[p] = (uint16_t)c;                                // from here on: the exact node count of position p
+        const uint32_t key = min(c, 127u);
+        clen[p] = (uint8_t)key;
+        atomicAdd(&s_whist[warp][key], 1u);
+    }
+    __syncthreads();
+    if (tid < 128) {
+        uint32_t acc = 0;
+        for (int w = 0; w < 32; w++) { uint32_t v = s_whist[w][tid]; s_whist[w][tid] = acc; acc += v; }
+        s_tot[tid] = acc;
+    }
+    __syncthreads();
+    if (tid == 0) { uint32_t acc = 0; for (int l = 127; l >= 0; l--) { uint32_t v = s_tot[l]; s_tot[l] = acc; acc += v; } }   // longest first
+    __syncthreads();
+    for (uint32_t p = sb.nb + tid; p < sb.ne; p += kMatchThreads) {
+        uint32_t len = clen[p];
+        uint32_t slot = s_tot[len] + atomicAdd(&s_whist[warp][len], 1u);
+        order[slot] = (uint16_t)p;
+    }
+    __syncthreads();
+
+    // ---- phase 2: the searches, 32 positions of equal node count per warp ----
+    const uint32_t npos = sb.ne - sb.nb;
+    for (uint32_t i = tid; i < npos; i += kMatchThreads) {
+        const uint32_t p = order[i];
+        const uint32_t maxlen = min((uint32_t)kMaxMatch, n - p);
+        if (maxlen < 5) { M[p] = 0; if (M2) M2[p] = 0; continue; }
+        const uint32_t nicep = min((uint32_t)nice, maxlen);
+        const uint32_t seq4 = ld32u(s_in, p);
+        const uint32_t w1 = ld32u(s_in, p + 4), w2 = ld32u(s_in, p + 8);
+        uint32_t d3 = ht ? 1u : p3[p];
+        uint32_t off3 = 0;
+        if (!ht && d3 && d3 <= 8192u && ((ld32u(s_in, p - d3) ^ seq4) & 0xFFFFFFu) == 0) off3 = d3;
+
+        uint32_t best = 3, boff = 0, lenB = 0, offB = 0, lenC = 0, offC = 0;
+        bool haveB = !lazy, haveC = (lazy != 2);
+        const uint32_t base = gidx[p], c = gocc[p];
+        const uint8_t *b8 = (const uint8_t *)s_in;
+        uint32_t pbest = b8[p + 3];                           // byte of p at offset `best`, refreshed when best grows
+        uint32_t qn = c ? (uint32_t)s_G[base - 1] : 0u;       // next candidate, loaded one node ahead
+        uint32_t k = 1;
+        // one chain node; true = a match of nice length ended the search
+        auto node = [&]() -> bool {
+            const uint32_t q = qn;
+            if (k < c) qn = s_G[base - k - 1];
+            bool cand;
+            if (best == 3) cand = (ld32u(s_in, q) == seq4);
+            else cand = (b8[q + best] == pbest) && (ld32u(s_in, q) == seq4);
+            if (cand) {
+                uint32_t len;
+                uint32_t x = ld32u(s_in, q + 4) ^ w1;
+                if (x) len = 4 + ((__ffs(x) - 1) >> 3);
+                else {
+                    x = ld32u(s_in, q + 8) ^ w2;
+                    if (x) len = 8 + ((__ffs(x) - 1) >> 3);
+                    else len = (maxlen > 12) ? lz_extend(s_in, p, q, 12, maxlen) : 12;
+                }
+                len = min(len, maxlen);
+                if (len > best) {
+                    best = len; boff = p - q;
+                    if (len >= nicep) return true;
+                    pbest = b8[p + best];
+                }
+            }
+            return false;
+        };
+        // the walk in up to three stretches, so that the depth/4 and depth/2 snapshots (lazy2 / lazy look-ahead
+        // columns) are taken between loops instead of being tested at every node
+        bool done = false;
+        if (lazy == 2) {
+            const uint32_t e = min(c, depthC);
+            for (; k <= e; k++) if (node()) { done = true; break; }
+            if (!done && c >= depthC) { haveC = true; lenC = best > 3 ? best : 0; offC = boff; }
+        }
+        if (lazy && !done) {
+            const uint32_t e = min(c, depthB);
+            for (; k <= e; k++) if (node()) { done = true; break; }
+            if (!done && c >= depthB) { haveB = true; lenB = best > 3 ? best : 0; offB = boff; }
+        }
+        if (!done)
+            for (; k <= c; k++) if (node()) break;
+        uint32_t lenA = best > 3 ? best : 0;
+        if (!haveB) { lenB = lenA; offB = boff; }
+        if (M2) { if (!haveC) { lenC = lenA; offC = boff; } M2[p] = (lenC ? lenC - 3 : 0) | (offC << 8); }
+        if (!lazy) { lenB = 0; offB = 0; }
+        M[p] = pack_entry(lenA, boff, lenB, offB, d3 != 0, off3);
+        EMU_STAT(p, i, min(k, c), npos);
     }
 }
 
@@ -1606,6 +1841,7 @@ cudaError_t launch_deflate_pipeline(const DeflateBatch &b, cudaStream_t st)
     if (!attr_done[cur_dev]) {
         cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, chain_smem);
         cudaFuncSetAttribute(k_match, cudaFuncAttributeMaxDynamicSharedMemorySize, match_smem);
+        cudaFuncSetAttribute(k_match2, cudaFuncAttributeMaxDynamicSharedMemorySize, match_smem);
         attr_done[cur_dev] = true;
     }
     if (b.nunits == 0) return cudaSuccess;
@@ -1622,7 +1858,14 @@ cudaError_t launch_deflate_pipeline(const DeflateBatch &b, cudaStream_t st)
         if (b.lists) {
             GZPB_LAUNCH(k_split, b.nunits * b.spu, kSplitThreads, 0, st, g, b.lists, b.list_start, b.next4, b.prev3, lp.ht);
             DBG_SYNC("k_split");
-            GZPB_LAUNCH(k_link, b.nunits * b.spu * kSplitLists, 32, 0, st, g, b.lists, b.list_start, b.next4, b.prev3, b.clen);
+            if (b.gidx) {
+                // match path v2: hash4 lists -> groups (k_group), hash3 lists -> links (k_link)
+                GZPB_LAUNCH(k_group, b.nunits * b.spu * kL4, 32, 0, st, g, b.lists, b.list_start, b.next4, b.gidx, b.gocc);
+                DBG_SYNC("k_group");
+                GZPB_LAUNCH(k_link, b.nunits * b.spu * kL3, 32, 0, st, g, b.lists, b.list_start, b.next4, b.prev3, b.clen, 1);
+            } else {
+                GZPB_LAUNCH(k_link, b.nunits * b.spu * kSplitLists, 32, 0, st, g, b.lists, b.list_start, b.next4, b.prev3, b.clen, 0);
+            }
             DBG_SYNC("k_link");
         } else {
             if (lp.ht) return cudaErrorInvalidValue;   // the legacy k_chain path has no 15-bit mode
@@ -1630,7 +1873,10 @@ cudaError_t launch_deflate_pipeline(const DeflateBatch &b, cudaStream_t st)
             DBG_SYNC("k_chain");
         }
         if (b.timer) { b.timer->stop(st); b.timer->start(KT_MATCH, st); }
-        GZPB_LAUNCH(k_match, b.nunits * b.spu, kMatchThreads, match_smem, st, g, b.next4, b.prev3, b.mtab, b.mtab2, b.clen, b.order, lp.depth, lp.nice, lp.mode, b.lists != nullptr, lp.ht);
+        if (b.gidx && b.lists)
+            GZPB_LAUNCH(k_match2, b.nunits * b.spu, kMatchThreads, match_smem, st, g, b.next4, b.prev3, b.gidx, b.gocc, b.mtab, b.mtab2, b.clen, b.order, lp.depth, lp.nice, lp.mode, lp.ht);
+        else
+            GZPB_LAUNCH(k_match, b.nunits * b.spu, kMatchThreads, match_smem, st, g, b.next4, b.prev3, b.mtab, b.mtab2, b.clen, b.order, lp.depth, lp.nice, lp.mode, b.lists != nullptr, lp.ht);
         DBG_SYNC("k_match");
         if (b.timer) b.timer->stop(st);
     }

@@ -47,6 +47,7 @@ struct DeflateBatch {
     uint32_t *mtab2;          // nunits * m_stride, lazy2 levels only (depth/4 column), else NULL
     uint8_t *clen;            // nunits * spu * 65536 (chain lengths, k_match scratch)
     uint16_t *order;          // nunits * spu * 65536 (positions sorted by chain length)
+    uint16_t *gidx, *gocc;    // nunits * spu * 65536 each: match path v2 (k_group / k_match2: `next4` then holds the hash groups), else NULL
     uint32_t *crc;            // nunits
     uint32_t *tokens;         // nunits * kTokStride
     uint8_t *out;             // nunits * kOutStride

@@ -464,3 +464,32 @@ def test_emu_compress_file_and_zero_copy_reserve(emu_backend, tmp_path):
     assert L.gzpb_writer_finish(h) == 0
     L.gzpb_writer_destroy(h)
     assert bytes(chunks) == oracle.compress_stream(oracle.BGZF, 6, 65280, [TEXT])
+
+
+@pytest.fixture()
+def match_v2(monkeypatch):
+    """Select the match path v2 (k_group + k_match2: hash groups instead of linked chains) for contexts created in the test."""
+    monkeypatch.setenv("GZPB_MATCH_V2", "1")
+    yield
+
+
+@pytest.mark.parametrize("level", [1, 2, 4, 5, 6, 7, 9])
+def test_emu_match_v2_bgzf_levels(match_v2, level):
+    ctx = emu.EmuContext(oracle.BGZF, level)
+    assert ctx.L.gzpb_ctx_variant(ctx.h) == b"split+group+match2"
+    ctx.close()
+    got = _run(oracle.BGZF, level, 0, TEXT[:140000])
+    assert gzip.decompress(got) == TEXT[:140000]
+
+
+def test_emu_match_v2_edges_long_units_and_dictionaries(match_v2):
+    rnd = random.Random(5)
+    cases = [b"", b"x", TEXT[:32], TEXT[:33], bytes(70000), b"\xff" * 40000, bytes(rnd.getrandbits(8) for _ in range(50000)),
+             b"abcdefghij" * 6500, TEXT[:4999], TEXT[:65280], synth.low_entropy(65280), synth.fastq(65000)]
+    for d in cases:
+        assert gzip.decompress(_run(oracle.BGZF, 6, 0, d)) == d
+    assert gzip.decompress(_run(oracle.MGZIP, 6, 131072, TEXT)) == TEXT                     # sub-units with a 32 KiB halo
+    assert gzip.decompress(_run(oracle.GZIP, 6, 131072, TEXT)) == TEXT                      # dictionary carry
+    d = synth.fastq(100000) + TEXT[:200000]
+    assert gzip.decompress(_run(oracle.GZIP, 8, 262144, d)) == d                            # lazy2: depth/4 column
+    assert zlib.decompress(_run(oracle.ZLIB, 1, 40000, TEXT[:130000])) == TEXT[:130000]     # ht matchfinder
