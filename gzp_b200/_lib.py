@@ -73,6 +73,7 @@ _SIGS = {
     "gzpb_decoder_kernel_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "gzpb_decoder_launch_count": (C.c_uint64, [C.c_void_p]),
     "gzpb_bgzf_index": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "gzpb_writer_bgzf_index": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "gzpb_bgzf_virtual_offset": (C.c_uint64, [C.c_uint64, C.c_uint32]),
     "gzpb_strerror": (C.c_char_p, [C.c_int]),
     "gzpb_version": (C.c_char_p, []),

@@ -408,6 +408,7 @@ class NativeParCompress:
         self.buffer_size = buffer_size
         self._sink_error = None
         self._finished = False
+        self._index = None
 
         def _sink(_user, ptr, n):
             try:
@@ -449,6 +450,18 @@ class NativeParCompress:
         self._lib.gzpb_writer_stats(self._h, *[C.byref(x) for x in v])
         return dict(zip(("bytes_in", "bytes_out", "batches", "sink_calls"), (x.value for x in v)))
 
+    def bgzf_index(self):
+        """.gzi index of the blocks written so far (Bgzf only); after finish(): of the whole stream."""
+        if self._h is None:
+            return self._index
+        n = C.c_size_t(0)
+        rc = self._lib.gzpb_writer_bgzf_index(self._h, None, 0, C.byref(n))
+        if rc != 0:
+            raise GzpError(rc)
+        out = C.create_string_buffer(n.value)
+        self._check(self._lib.gzpb_writer_bgzf_index(self._h, out, n.value, C.byref(n)))
+        return out.raw[:n.value]
+
     def close(self):
         if getattr(self, "_h", None):
             self._lib.gzpb_writer_destroy(self._h)
@@ -460,6 +473,7 @@ class NativeParCompress:
             raise GzpError(-7)
         rc = self._lib.gzpb_writer_finish(self._h)
         self._finished = True
+        self._index = self.bgzf_index() if self.format.ID == BGZF and rc == 0 else None
         self.close()
         self._check(rc)
         if hasattr(self.writer, "flush"):

@@ -783,6 +783,10 @@ struct gzpb_writer {
     uint32_t sum = 0, amount = 0;
     int error = GZPB_OK;
     uint64_t sink_calls = 0, bytes_in = 0, bytes_out = 0;
+    // BGZF only: the .gzi entries, a by-product of knowing every block's compressed size when its batch retires
+    std::vector<uint64_t> gzi;                                   // {compressed offset, uncompressed offset} pairs
+    uint64_t gzi_upos = 0;
+    bool gzi_first = true;
 };
 
 static int writer_emit(gzpb_writer *w, const void *p, size_t n)
@@ -821,6 +825,16 @@ static int writer_retire(gzpb_writer *w)
         if (blen) w->sum = w->format == GZPB_GZIP ? gzpb_crc32_combine(w->sum, L.h_comb[0], blen)
                                                   : gzpb_adler32_combine(w->sum, L.h_comb[0], blen);
         w->amount += (uint32_t)blen;
+    }
+    if (w->format == GZPB_BGZF) {
+        // same rule as gzpb_bgzf_index: one entry per data block after the first; empty blocks carry no data
+        for (size_t i = 0; i < f.count; i++) {
+            const uint32_t isize = L.h_len[i];
+            if (!isize) continue;
+            if (!w->gzi_first) { w->gzi.push_back(w->bytes_out + L.h_offsets[i]); w->gzi.push_back(w->gzi_upos); }
+            w->gzi_first = false;
+            w->gzi_upos += isize;
+        }
     }
     return writer_emit(w, L.h_packed, (size_t)L.h_offsets[f.count * c->cpu]);
 }
@@ -1007,6 +1021,21 @@ extern "C" int gzpb_writer_stats(gzpb_writer *w, uint64_t *bytes_in, uint64_t *b
     if (bytes_out) *bytes_out = w->bytes_out;
     if (batches) *batches = w->nbatches;
     if (sink_calls) *sink_calls = w->sink_calls;
+    return GZPB_OK;
+}
+
+extern "C" int gzpb_writer_bgzf_index(gzpb_writer *w, void *out_v, size_t out_cap, size_t *out_len)
+{
+    if (!w || !out_len) return GZPB_EINVAL;
+    if (w->format != GZPB_BGZF) return GZPB_EINVAL;
+    const size_t n = w->gzi.size() / 2, need = 8 + 16 * n;
+    *out_len = need;
+    if (!out_v) return GZPB_OK;
+    if (out_cap < need) return GZPB_ECOMPRESS;
+    uint8_t *out = (uint8_t *)out_v;
+    auto put64 = [&](size_t at, uint64_t v) { for (int i = 0; i < 8; i++) out[at + i] = (uint8_t)(v >> (8 * i)); };
+    put64(0, n);
+    for (size_t i = 0; i < 2 * n; i++) put64(8 + 8 * i, w->gzi[i]);
     return GZPB_OK;
 }
 

@@ -244,6 +244,10 @@ uint64_t gzpb_decoder_launch_count(gzpb_decoder *d);
  * offset within the block) — SURVEY.md §8(f) rank 2; a TODO of the reference (README.md:161).
  * `out` may be NULL to size the index. */
 int gzpb_bgzf_index(const void *bgzf, size_t len, void *out, size_t out_cap, size_t *out_len);
+/* The same index straight from a Bgzf writer: it knows every block's compressed size when the block's batch
+ * retires, so the .gzi is a by-product of writing (covers the blocks handed to the sink so far; call after
+ * gzpb_writer_finish for the whole stream).  `out` may be NULL to size the index. */
+int gzpb_writer_bgzf_index(gzpb_writer *w, void *out, size_t out_cap, size_t *out_len);
 uint64_t gzpb_bgzf_virtual_offset(uint64_t block_offset, uint32_t within_block);
 
 const char *gzpb_strerror(int code);

@@ -493,3 +493,29 @@ def test_emu_match_v2_edges_long_units_and_dictionaries(match_v2):
     d = synth.fastq(100000) + TEXT[:200000]
     assert gzip.decompress(_run(oracle.GZIP, 8, 262144, d)) == d                            # lazy2: depth/4 column
     assert zlib.decompress(_run(oracle.ZLIB, 1, 40000, TEXT[:130000])) == TEXT[:130000]     # ht matchfinder
+
+
+def test_emu_writer_emits_the_gzi_index(emu_backend):
+    """The Bgzf writer's own .gzi (collected as batches retire) equals the index scanned from the finished stream,
+    including empty flush blocks and the EOF marker, which carry no entry."""
+    import gzp_b200
+    sink = io.BytesIO()
+    w = gzp_b200.ParCompressBuilder(gzp_b200.Bgzf).compression_level(4).blocks_in_flight(2).devices([0]).from_writer(sink)
+    w.write(TEXT[:70000]); w.flush(); w.flush(); w.write(TEXT[70000:])
+    w.finish()
+    stream = sink.getvalue()
+    assert gzip.decompress(stream) == TEXT
+    idx = w.bgzf_index()
+    assert idx == gzp_b200.bgzf_index(stream)
+    n = int.from_bytes(idx[:8], "little")
+    assert n >= 4 and len(idx) == 8 + 16 * n
+    # every entry points at a member whose decoded bytes start at the recorded uncompressed offset
+    for k in range(n):
+        coff = int.from_bytes(idx[8 + 16 * k:16 + 16 * k], "little")
+        uoff = int.from_bytes(idx[16 + 16 * k:24 + 16 * k], "little")
+        bsize = int.from_bytes(stream[coff + 16:coff + 18], "little") + 1
+        assert gzip.decompress(stream[coff:coff + bsize]) == TEXT[uoff:uoff + len(gzip.decompress(stream[coff:coff + bsize]))]
+    gz = gzp_b200.ParCompressBuilder(gzp_b200.Gzip).devices([0]).from_writer(io.BytesIO())
+    with pytest.raises(gzp_b200.GzpError):
+        gz.bgzf_index()
+    gz.finish()
