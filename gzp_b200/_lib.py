@@ -68,6 +68,11 @@ _SIGS = {
     "gzpb_decode_stream": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t),
                                      C.POINTER(C.c_size_t)]),
     "gzpb_decode_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gzpb_reader_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "gzpb_reader_read": (C.c_long, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "gzpb_reader_last_check": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    "gzpb_reader_finish": (C.c_int, [C.c_void_p]),
+    "gzpb_reader_destroy": (None, [C.c_void_p]),
     "gzpb_decoder_last_check": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]),
     "gzpb_decoder_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "gzpb_decoder_kernel_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
@@ -80,6 +85,7 @@ _SIGS = {
 }
 
 SINK_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t)
+SOURCE_FN = C.CFUNCTYPE(C.c_long, C.c_void_p, C.c_void_p, C.c_size_t)
 EXPORTS = tuple(_SIGS)
 _lib = None
 

@@ -804,13 +804,105 @@ class ParDecompressBuilder:
         self._blocks_in_flight = int(n)
         return self
 
+    def native(self, on=True):
+        """Use the C reader object (gzpb_reader_*) instead of the Python reader loop."""
+        self._native = bool(on)
+        return self
+
     def from_reader(self, reader):
+        if getattr(self, "_native", False):
+            return NativeParDecompress(self.format, reader, self._device, self._blocks_in_flight)
         return ParDecompress(self.format, reader, self._buffer_size, self._device, self._blocks_in_flight)
 
     def maybe_par_from_reader(self, reader):
         # the reference falls back to a single-threaded MultiGzDecoder for 0 threads (:96-102);
         # this engine has no CPU decoder, so the GPU path serves both cases
         return self.from_reader(reader)
+
+
+class NativeParDecompress:
+    """ParDecompress<F> on the C reader object (gzpb_reader_*, include/gzpb.h): the reader loop, the pinned
+    buffers and the member-parallel GPU decode live in libgzpb.so; Python forwards `read` (par/decompress.rs:238-287)."""
+
+    def __init__(self, fmt, reader, device=0, blocks_in_flight=0, chunk_bytes=0):
+        self._lib = _lib.load()
+        self.format = fmt
+        self.reader = reader
+        self._src_error = None
+
+        def _source(_user, buf, cap):
+            try:
+                b = self.reader.read(cap)
+                if not b:
+                    return 0
+                C.memmove(buf, bytes(b), len(b))
+                return len(b)
+            except Exception as e:
+                self._src_error = e
+                return -1
+
+        self._cb = _lib.SOURCE_FN(_source)
+        h = C.c_void_p()
+        rc = self._lib.gzpb_reader_create(C.byref(h), device, fmt.ID, blocks_in_flight, chunk_bytes, C.cast(self._cb, C.c_void_p), None)
+        if rc != 0:
+            raise GzpError(rc)
+        self._h = h
+
+    def _error(self, rc):
+        if rc == -12:
+            f, e = C.c_uint32(0), C.c_uint32(0)
+            self._lib.gzpb_reader_last_check(self._h, C.byref(f), C.byref(e))
+            err = GzpError(rc, f"Invalid checksum, found {f.value}, expected {e.value}")      # lib.rs:139-140
+            err.found, err.expected = f.value, e.value
+            return err
+        err = GzpError(rc)
+        err.__cause__ = self._src_error
+        return err
+
+    def read(self, n=-1):
+        if self._h is None:
+            raise GzpError(-7)
+        out = bytearray()
+        want = n if n is not None and n >= 0 else None
+        while want is None or len(out) < want:
+            k = (1 << 22) if want is None else min(want - len(out), 1 << 26)
+            buf = C.create_string_buffer(k)
+            got = self._lib.gzpb_reader_read(self._h, buf, k)
+            if got < 0:
+                raise self._error(got)
+            if got == 0:
+                break
+            out += buf.raw[:got]
+        return bytes(out)
+
+    def finish(self):
+        """Close things in such a way as to get errors (par/decompress.rs:222-236)."""
+        if self._h is None:
+            return
+        rc = self._lib.gzpb_reader_finish(self._h)
+        err = self._error(rc) if rc != 0 else None
+        self.close()
+        if err:
+            raise err
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.gzpb_reader_destroy(self._h)
+            self._h = None
+            self._cb = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class ParDecompress:

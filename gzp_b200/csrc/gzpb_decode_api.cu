@@ -315,6 +315,120 @@ extern "C" int gzpb_decode_stream(gzpb_decoder *d, const void *in_v, size_t in_l
     return scan_rc;
 }
 
+// ---- incremental reader: ParDecompress<F> as a C object ------------------------------------
+// The reader loop of ParDecompress::run (par/decompress.rs:190-207) pulls bytes from `source` (= `R: Read`) into a
+// pinned buffer, whole members go to the GPU in one gzpb_decode_stream call (straight from / to pinned memory), an
+// incomplete trailing member stays for the next round; `read` hands the decoded bytes out in stream order
+// (:238-287).  A short trailing header is EOF (:193, 205-206), a truncated member is an Io error (:197).
+struct gzpb_reader {
+    gzpb_decoder *dec = nullptr;
+    int format = 0;
+    gzpb_source_fn source = nullptr;
+    void *user = nullptr;
+    uint8_t *in = nullptr, *out = nullptr;       // pinned
+    size_t in_cap = 0, in_len = 0, out_cap = 0, out_len = 0, out_pos = 0, chunk = 0;
+    bool eof = false;
+    int error = GZPB_OK;
+    uint64_t bytes_in = 0, bytes_out = 0;
+};
+
+static int reader_grow(uint8_t **buf, size_t *cap, size_t keep, size_t need)
+{
+    if (need <= *cap) return GZPB_OK;
+    size_t ncap = std::max(need, *cap + *cap / 2);
+    uint8_t *p = nullptr;
+    if (cudaHostAlloc((void **)&p, ncap, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return GZPB_ENOMEM; }
+    if (keep) memcpy(p, *buf, keep);
+    cudaFreeHost(*buf);
+    *buf = p; *cap = ncap;
+    return GZPB_OK;
+}
+
+extern "C" int gzpb_reader_create(gzpb_reader **out, int device, int format, size_t blocks_in_flight, size_t chunk_bytes,
+                                  gzpb_source_fn source, void *user)
+{
+    if (!out || !source) return GZPB_EINVAL;
+    *out = nullptr;
+    if (!header_size(format)) return GZPB_EINVAL;                      // ParDecompress needs a BlockFormatSpec (Mgzip, Bgzf)
+    gzpb_reader *r = new gzpb_reader();
+    int rc = gzpb_decoder_create(&r->dec, device, format, blocks_in_flight ? blocks_in_flight : 5328);
+    if (rc != GZPB_OK) { delete r; return rc; }
+    r->format = format; r->source = source; r->user = user;
+    r->chunk = chunk_bytes ? std::max(chunk_bytes, (size_t)65536) : ((size_t)64 << 20);
+    *out = r;
+    return GZPB_OK;
+}
+
+// one round of the reader loop: pull up to `chunk` bytes, decode the whole members that are there
+static int reader_fill(gzpb_reader *r)
+{
+    int rc = reader_grow(&r->in, &r->in_cap, r->in_len, r->in_len + r->chunk);
+    if (rc != GZPB_OK) return rc;
+    while (!r->eof && r->in_len < r->in_cap) {                          // a source may return short reads
+        const long k = r->source(r->user, r->in + r->in_len, r->in_cap - r->in_len);
+        if (k < 0) return GZPB_EIO;
+        if (k == 0) { r->eof = true; break; }
+        r->in_len += (size_t)k; r->bytes_in += (uint64_t)k;
+        if (r->in_len >= r->chunk) break;
+    }
+    size_t consumed = 0, nb = 0;
+    uint64_t total = 0;
+    rc = gzpb_scan_blocks(r->format, r->in, r->in_len, nullptr, 0, &nb, &consumed, &total);
+    if (rc == GZPB_EIO && !r->eof) rc = GZPB_OK;                        // incomplete trailing member: wait for more bytes
+    if (rc != GZPB_OK) return rc;
+    if (r->eof && r->in_len - consumed >= header_size(r->format)) return GZPB_EIO;
+    if (nb == 0) {
+        if (r->eof) r->in_len = 0;                                      // a short trailing header is EOF
+        return GZPB_OK;                                                 // (a member larger than the chunk: the buffer grows next round)
+    }
+    rc = reader_grow(&r->out, &r->out_cap, 0, (size_t)total + 64);
+    if (rc != GZPB_OK) return rc;
+    size_t olen = 0, used = 0;
+    rc = gzpb_decode_stream(r->dec, r->in, consumed, r->out, r->out_cap, &olen, &used);
+    if (rc != GZPB_OK) return rc;
+    r->out_len = olen; r->out_pos = 0;
+    memmove(r->in, r->in + used, r->in_len - used);
+    r->in_len -= used;
+    return GZPB_OK;
+}
+
+extern "C" long gzpb_reader_read(gzpb_reader *r, void *buf, size_t len)
+{
+    if (!r || (len && !buf)) return GZPB_EINVAL;
+    if (r->error) return r->error;
+    size_t done = 0;
+    while (done < len) {
+        if (r->out_pos == r->out_len) {
+            if (r->eof && r->in_len == 0) break;
+            r->out_pos = r->out_len = 0;
+            const int rc = reader_fill(r);
+            if (rc != GZPB_OK) { r->error = rc; return done ? (long)done : rc; }
+            if (r->out_len == 0 && r->eof && r->in_len == 0) break;
+            continue;
+        }
+        const size_t k = std::min(len - done, r->out_len - r->out_pos);
+        memcpy((uint8_t *)buf + done, r->out + r->out_pos, k);
+        r->out_pos += k; done += k; r->bytes_out += k;
+    }
+    return (long)done;
+}
+
+extern "C" int gzpb_reader_last_check(gzpb_reader *r, uint32_t *found, uint32_t *expected)
+{
+    if (!r) return GZPB_EINVAL;
+    return gzpb_decoder_last_check(r->dec, found, expected, nullptr);
+}
+
+extern "C" int gzpb_reader_finish(gzpb_reader *r) { return r ? r->error : GZPB_EINVAL; }   // "close things in such a way as to get errors" (:222-236)
+
+extern "C" void gzpb_reader_destroy(gzpb_reader *r)
+{
+    if (!r) return;
+    if (r->dec) gzpb_decoder_destroy(r->dec);
+    cudaFreeHost(r->in); cudaFreeHost(r->out);
+    delete r;
+}
+
 // ---- BGZF block index (.gzi) and virtual offsets (a TODO of the reference,
 // /root/reference/README.md:161).  Layout as written by htslib's `bgzip -i`: u64 LE entry count, then per
 // entry {u64 LE compressed offset, u64 LE uncompressed offset} of every data block after the first.

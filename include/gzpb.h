@@ -233,6 +233,19 @@ int gzpb_decode_stream(gzpb_decoder *d, const void *in, size_t in_len, void *out
  * 2 output overrun, 3 input overrun, 4 CRC mismatch; d_crc_found[i] = CRC-32 of the decoded block. */
 int gzpb_decode_device(gzpb_decoder *d, const void *d_comp, const gzpb_block_desc *d_desc, size_t nblocks, void *d_out,
                        int32_t *d_status, uint32_t *d_crc_found, void *cuda_stream);
+/* Incremental reader = `ParDecompress<F>` as a C object (src/par/decompress.rs:113-352): `source` plays
+ * `R: Read` (returns bytes read, 0 at EOF, negative on error); gzpb_reader_read is `Read::read` (:238-287):
+ * decoded bytes in stream order, 0 at the end of the stream, a negative status on error (errors are sticky;
+ * GZPB_ECHECK details through gzpb_reader_last_check).  Compressed bytes are pulled `chunk_bytes` at a time
+ * (0 = 64 MiB) into pinned memory and decoded member-parallel on the GPU. */
+typedef long (*gzpb_source_fn)(void *user, void *buf, size_t cap);
+typedef struct gzpb_reader gzpb_reader;
+int gzpb_reader_create(gzpb_reader **r, int device, int format, size_t blocks_in_flight, size_t chunk_bytes,
+                       gzpb_source_fn source, void *user);
+long gzpb_reader_read(gzpb_reader *r, void *buf, size_t len);
+int gzpb_reader_last_check(gzpb_reader *r, uint32_t *found, uint32_t *expected);
+int gzpb_reader_finish(gzpb_reader *r);
+void gzpb_reader_destroy(gzpb_reader *r);
 /* InvalidCheck{found, expected} of the last GZPB_ECHECK (and the index of the failing block). */
 int gzpb_decoder_last_check(gzpb_decoder *d, uint32_t *found, uint32_t *expected, uint64_t *block_index);
 int gzpb_decoder_set_profiling(gzpb_decoder *d, int on);

@@ -519,3 +519,81 @@ def test_emu_writer_emits_the_gzi_index(emu_backend):
     with pytest.raises(gzp_b200.GzpError):
         gz.bgzf_index()
     gz.finish()
+
+
+def test_emu_c_writer_block_size_exceeded_fails_the_stream():
+    """Bgzf with buffer_size 65536 and incompressible bytes: the stored block (len + 5 + 26) exceeds 65536 ->
+    BlockSizeExceeded (bgzf.rs:218-223); the writer surfaces it on a later call and stays failed (par/compress.rs:428-440)."""
+    import ctypes as C
+    from gzp_b200 import _lib
+    L = emu.lib()
+    rnd = random.Random(11)
+    data = bytes(rnd.getrandbits(8) for _ in range(200000))
+    out = bytearray()
+    sink = _lib.SINK_FN(lambda u, p, n: (out.extend(C.string_at(p, n)), 0)[1])
+    h = C.c_void_p()
+    assert L.gzpb_writer_create(C.byref(h), 0, oracle.BGZF, 6, 65536, 1, C.cast(sink, C.c_void_p), None) == 0
+    rcs = [L.gzpb_writer_write(h, data, len(data)), L.gzpb_writer_flush(h)]
+    assert -3 in rcs, rcs                                     # GZPB_EBLOCKSIZE
+    assert L.gzpb_writer_write(h, b"more", 4) == -3           # the stream stays failed
+    assert L.gzpb_writer_finish(h) == -3
+    L.gzpb_writer_destroy(h)
+    assert len(out) == 0                                      # no partial output after the failing block's batch
+
+
+def test_emu_native_pardecompress_reader_object(emu_backend):
+    """gzpb_reader_* (ParDecompress as a C object) behind NativeParDecompress: members straddling source reads and
+    chunks, both block formats, the error paths of par/decompress.rs:176-181, 193-197."""
+    import gzp_b200
+
+    class Dribble(io.RawIOBase):
+        def __init__(self, data):
+            self.d, self.p, self.k = data, 0, 0
+
+        def read(self, n=-1):
+            self.k += 1
+            step = min(n if n > 0 else 1 << 30, 7919 * (1 + self.k % 5))
+            b = self.d[self.p:self.p + step]
+            self.p += len(b)
+            return b
+
+    for fmt, F, bs in ((oracle.BGZF, gzp_b200.Bgzf, 65280), (oracle.MGZIP, gzp_b200.Mgzip, 131072)):
+        comp = oracle.compress_stream(fmt, 6, bs, [TEXT])
+        r = gzp_b200.NativeParDecompress(F(), Dribble(comp), blocks_in_flight=3, chunk_bytes=65536)
+        got = bytearray()
+        while True:
+            b = r.read(33333)
+            if not b:
+                break
+            got += b
+        r.finish()
+        assert bytes(got) == TEXT
+        r = gzp_b200.ParDecompressBuilder(F).native().from_reader(io.BytesIO(comp))
+        assert isinstance(r, gzp_b200.NativeParDecompress) and r.read() == TEXT
+        r.close()
+    comp = oracle.compress_stream(oracle.BGZF, 6, 65280, [TEXT])
+    assert gzp_b200.NativeParDecompress(gzp_b200.Bgzf(), io.BytesIO(b"")).read() == b""          # empty input = EOF
+    bad = bytearray(comp); bad[-28 - 8] ^= 1                                                       # CRC of the last data block
+    r = gzp_b200.NativeParDecompress(gzp_b200.Bgzf(), io.BytesIO(bytes(bad)))
+    with pytest.raises(gzp_b200.GzpError) as ei:
+        r.read()
+    assert ei.value.variant == "InvalidCheck" and ei.value.found != ei.value.expected
+    with pytest.raises(gzp_b200.GzpError):                                                         # errors are sticky
+        r.read(10)
+    r.close()
+    r = gzp_b200.NativeParDecompress(gzp_b200.Bgzf(), io.BytesIO(comp[:-40]))                      # truncated member
+    with pytest.raises(gzp_b200.GzpError) as ei:
+        r.read()
+    assert ei.value.variant == "Io"
+    hdr = bytearray(comp); hdr[12] = ord("X")                                                      # "Bad SID"
+    with pytest.raises(gzp_b200.GzpError) as ei:
+        gzp_b200.NativeParDecompress(gzp_b200.Bgzf(), io.BytesIO(bytes(hdr))).read()
+    assert ei.value.variant == "InvalidHeader"
+
+    class Failing:
+        def read(self, n):
+            raise OSError("network gone")
+
+    with pytest.raises(gzp_b200.GzpError) as ei:
+        gzp_b200.NativeParDecompress(gzp_b200.Bgzf(), Failing()).read()
+    assert ei.value.variant == "Io" and isinstance(ei.value.__cause__, OSError)

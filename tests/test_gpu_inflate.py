@@ -134,3 +134,29 @@ def test_pardecompress_mirror_reads_like_the_reference():
         got.extend(piece)
     r.finish()
     assert bytes(got) == data
+
+
+def test_native_reader_object_on_gpu():
+    """gzpb_reader_* (ParDecompress as a C object): 40 MB of text through a dribbling source, chunks of 4 MiB."""
+    import io
+    from gzp_b200 import synth
+    data = synth.text_stream(40_000_000)
+    ctx = gzp_b200.Context(gzp_b200.BGZF, 6, max_blocks_in_flight=256)
+    comp = ctx.encode_stream(data)
+    ctx.close()
+
+    class Dribble(io.RawIOBase):
+        def __init__(self, d):
+            self.d, self.p, self.k = d, 0, 0
+
+        def read(self, n=-1):
+            self.k += 1
+            step = min(n, 100003 * (1 + self.k % 7))
+            b = self.d[self.p:self.p + step]
+            self.p += len(b)
+            return b
+
+    r = gzp_b200.NativeParDecompress(gzp_b200.Bgzf(), Dribble(comp), chunk_bytes=4 << 20)
+    got = r.read()
+    r.finish()
+    assert got == data
