@@ -324,6 +324,42 @@ def main():
     if world > 1:
         t = torch.tensor([e2e_s], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); e2e_s = float(t.item())
 
+    # ---------------- the incremental writer (ParCompress::write in 64 KiB pieces, benches/bench.rs:121) ----------------
+    # informational: the same step through gzpb_writer_write from ordinary (pageable) caller memory; never fatal
+    writer = None
+    try:
+        total_out = [0]
+
+        @_lib.SINK_FN
+        def _sink(_u, _p, k):
+            total_out[0] += k
+            return 0
+
+        wh = C.c_void_p()
+        rc = L.gzpb_writer_create(C.byref(wh), local_rank, gzp_b200.BGZF, LEVEL, BLOCK, min(nblk, args.inflight), C.cast(_sink, C.c_void_p), None)
+        if rc != 0:
+            raise RuntimeError("gzpb_writer_create: " + L.gzpb_strerror(rc).decode())
+        src = C.create_string_buffer(bytes(stream[base_off: base_off + step_bytes]), step_bytes)
+        sbase = C.addressof(src)
+        t0 = time.perf_counter()
+        for off in range(0, step_bytes, 65536):
+            rc = L.gzpb_writer_write(wh, sbase + off, min(65536, step_bytes - off))
+            if rc != 0:
+                raise RuntimeError("gzpb_writer_write: " + L.gzpb_strerror(rc).decode())
+        rc = L.gzpb_writer_finish(wh)
+        w_s = time.perf_counter() - t0
+        L.gzpb_writer_destroy(wh)
+        if rc != 0:
+            raise RuntimeError("gzpb_writer_finish: " + L.gzpb_strerror(rc).decode())
+        del src
+        # rank-local on purpose (no collective inside a leg that may be skipped): rank 0's own GPU, all ranks running it at once
+        writer = {"value_per_gpu": step_bytes / w_s / GIB, "unit": UNIT, "out_bytes": total_out[0],
+                  "api": "gzpb_writer_write in 64 KiB pieces from pageable caller memory + gzpb_writer_finish (one pass, pipeline fill included; rank 0's GPU)"}
+        log("incremental writer timed: %.1f ms" % (w_s * 1e3))
+    except Exception as e:                                   # noqa: BLE001 - informational leg, never fatal
+        log("incremental writer leg skipped: %r" % (e,))
+        writer = None
+
     # correctness check of what was timed: the e2e stream of the last step decodes to its input with the stock
     # zlib decoder (streamed member by member: gzip.decompress() re-copies the tail for every member, which is
     # quadratic over thousands of BGZF members)
@@ -363,7 +399,8 @@ def main():
                        "l2": "each step's input (%.0f MB) exceeds L2 and rotates over %d stream windows" % (step_bytes / 1e6, nwin),
                        "parallelism": f"independent blocks sharded over {world} GPU(s), no data collective"},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": step_bytes, "d2h_bytes_per_step": out_bytes,
-                    "ms_per_step": 1e3 * e2e_s / args.steps, "api": "gzpb_encode_stream (pinned host in/out)"},
+                    "ms_per_step": 1e3 * e2e_s / args.steps, "api": "gzpb_encode_stream (pinned host in/out)",
+                    "incremental_writer": writer},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_match", "achieved": achieved, "peak": peak, "unit": "GB/s",
