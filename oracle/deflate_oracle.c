@@ -240,13 +240,24 @@ static unsigned bsr32(uint32_t v) { unsigned r = 0; while (v >>= 1) r++; return 
 /* hc_matchfinder_longest_match restated with absolute positions.  `nh` holds the
  * hashes of the position about to be searched (computed one call earlier; both
  * start at 0 for the first position, as in libdeflate). */
+/* analysis aid (tests/search_stats.py): searches the parser actually asked for, and chain hops inside them */
+static __thread uint64_t g_stat_searches, g_stat_hops;
+void oracle_search_stats(uint64_t *searches, uint64_t *hops, int reset)
+{
+    if (searches) *searches = g_stat_searches;
+    if (hops) *hops = g_stat_hops;
+    if (reset) { g_stat_searches = 0; g_stat_hops = 0; }
+}
+
 static unsigned longest_match(comp_t *c, const uint8_t *in, size_t n, size_t p, unsigned best_len,
                               unsigned max_len, unsigned nice_len, unsigned depth, uint32_t nh[2],
                               unsigned *off_ret)
 {
     size_t best_q = p;
+    const unsigned depth0 = depth;
     (void)n;
     if (max_len < 5) goto out;
+    g_stat_searches++;
     {
         uint32_t h3 = nh[0], h4 = nh[1];
         int32_t c3 = c->head3[h3], c4 = c->head4[h4];
@@ -293,6 +304,7 @@ static unsigned longest_match(comp_t *c, const uint8_t *in, size_t n, size_t p, 
         }
     }
 out:
+    g_stat_hops += depth0 - depth;
     *off_ret = (unsigned)(p - best_q);
     return best_len;
 }
