@@ -14,11 +14,17 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(os.path.dirname(_HERE))
 _CSRC = os.path.join(_ROOT, "gzp_b200", "csrc")
-_BUILD = os.path.join(_HERE, "_build")
+# GZPB_EMU_ASAN=1: AddressSanitizer build in its own directory (run python with LD_PRELOAD=$(gcc -print-file-name=libasan.so)
+# and ASAN_OPTIONS=detect_leaks=0): "device" memory is host heap here, so an out-of-bounds access of a kernel or of the
+# host runtime is reported with the kernel's source line — compute-sanitizer's memcheck without a GPU.
+_ASAN = os.environ.get("GZPB_EMU_ASAN") == "1"
+_BUILD = os.path.join(_HERE, "_build_asan" if _ASAN else "_build")
 SO = os.path.join(_BUILD, "libgzpb_emu.so")
 CXX = os.environ.get("CXX", "g++")
+if os.environ.get("GZPB_EMU_ASAN") == "1" and os.path.exists("/usr/bin/g++"):
+    CXX = "/usr/bin/g++"           # the distribution compiler knows where its libasan lives
 FLAGS = ["-std=c++17", "-O2", "-g", "-fPIC", "-fno-strict-aliasing", "-Wno-unused", "-I", os.path.join(_HERE, "shim"),
-         "-I", _CSRC, "-DGZPB_EMU=1"]
+         "-I", _CSRC, "-DGZPB_EMU=1"] + (["-fsanitize=address", "-fno-omit-frame-pointer"] if _ASAN else [])
 
 
 def build(force=False):
@@ -38,7 +44,7 @@ def build(force=False):
     for p in procs:
         if p.wait() != 0:
             raise RuntimeError("emulator build failed")
-    subprocess.check_call([CXX, "-shared", "-o", SO] + objs + ["-lpthread"])
+    subprocess.check_call([CXX, "-shared", "-o", SO] + objs + ["-lpthread"] + (["-fsanitize=address"] if _ASAN else []))
     return SO
 
 

@@ -181,10 +181,11 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> &bod
     const unsigned n = block.x * block.y * block.z;
     if (n == 0 || n > 1024) trap("launch: bad block size");
     if (g_fibers.size() < n) g_fibers.resize(n);
-    if (smem > g_dyn_cap) {
+    if (smem != g_dyn_cap) {                       // exact size: an access past the launch's dynamic shared memory is an ASan error
         free(g_dyn);
-        g_dyn_cap = (smem + 1023) & ~(size_t)1023;
-        g_dyn = (uint8_t *)aligned_alloc(1024, g_dyn_cap);
+        g_dyn = nullptr;
+        g_dyn_cap = smem;
+        if (smem) { void *m = nullptr; if (posix_memalign(&m, 1024, smem) != 0) trap("out of memory for dynamic shared memory"); g_dyn = (uint8_t *)m; }
     }
     g_body = &body;
     g_nthreads = n;
@@ -318,8 +319,8 @@ void launch_async(void *stream, dim3 grid, dim3 block, size_t smem, std::functio
 
 cudaError_t cudaMalloc(void **p, size_t n)
 {
-    void *m = aligned_alloc(256, (n + 255) & ~(size_t)255);
-    if (!m) return cudaErrorMemoryAllocation;
+    void *m = nullptr;            // exact size: under AddressSanitizer (GZPB_EMU_ASAN=1) the redzone starts right after byte n
+    if (posix_memalign(&m, 256, n ? n : 1) != 0) return cudaErrorMemoryAllocation;
     Fill::garbage(m, n);          // device memory is not zero-initialised
     g_device[(uintptr_t)m] = n ? n : 1;
     *p = m;
@@ -328,8 +329,8 @@ cudaError_t cudaMalloc(void **p, size_t n)
 cudaError_t cudaFree(void *p) { if (p) { drain_all(); g_device.erase((uintptr_t)p); free(p); } return cudaSuccess; }
 cudaError_t cudaHostAlloc(void **p, size_t n, unsigned)
 {
-    void *m = aligned_alloc(256, (n + 255) & ~(size_t)255);
-    if (!m) return cudaErrorMemoryAllocation;
+    void *m = nullptr;
+    if (posix_memalign(&m, 256, n ? n : 1) != 0) return cudaErrorMemoryAllocation;
     Fill::garbage(m, n);
     g_pinned[(uintptr_t)m] = n ? n : 1;
     *p = m;

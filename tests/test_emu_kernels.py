@@ -597,3 +597,24 @@ def test_emu_native_pardecompress_reader_object(emu_backend):
     with pytest.raises(gzp_b200.GzpError) as ei:
         gzp_b200.NativeParDecompress(gzp_b200.Bgzf(), Failing()).read()
     assert ei.value.variant == "Io" and isinstance(ei.value.__cause__, OSError)
+
+
+def test_emu_memcheck_under_address_sanitizer():
+    """compute-sanitizer memcheck without a GPU: the emulator built with -fsanitize=address (exact-size "device",
+    pinned and dynamic-shared allocations) runs edge-size encodes, the ticket API, Snap and the decoder in a
+    subprocess; any out-of-bounds access of a kernel or of the host runtime aborts it with an ASan report."""
+    import os
+    import subprocess
+    import sys
+    asan = subprocess.run(["/usr/bin/gcc", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip() \
+        if os.path.exists("/usr/bin/gcc") else ""
+    if not asan or not os.path.isabs(asan) or not os.path.exists(asan):
+        pytest.skip("no libasan on this machine")
+    env = dict(os.environ, GZPB_EMU_ASAN="1", LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0:detect_stack_use_after_return=0")
+    env.pop("GZPB_MATCH_V2", None)
+    sel = "bgzf_edges or submit_poll or emu_snap or inflate_error_paths or block_size_exceeded"
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-k", sel, "-p", "no:cacheprovider"],
+                       env=env, capture_output=True, text=True, timeout=1500, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert "AddressSanitizer" not in r.stdout + r.stderr, (r.stdout + r.stderr)[-4000:]
+    assert r.returncode == 0, (r.stdout + r.stderr)[-4000:]
+    assert " passed" in r.stdout
