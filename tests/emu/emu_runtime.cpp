@@ -189,6 +189,10 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> &bod
     }
     g_body = &body;
     g_nthreads = n;
+    static const int sched = [] { const char *e = getenv("GZPB_EMU_SCHED"); return !e ? 0 : !strcmp(e, "reverse") ? 1 : !strncmp(e, "random", 6) ? 2 : 0; }();
+    static uint64_t rng_state = [] { const char *e = getenv("GZPB_EMU_SCHED"); const char *c = e ? strchr(e, ':') : nullptr; return c ? strtoull(c + 1, nullptr, 10) * 2 + 1 : 0x9E3779B97F4A7C15ull; }();
+    auto sched_rng = [&]() { rng_state ^= rng_state << 13; rng_state ^= rng_state >> 7; rng_state ^= rng_state << 17; return rng_state; };
+    unsigned rot = 0;
     const unsigned nwarps = (n + 31) / 32;
     for (unsigned bz = 0; bz < grid.z; bz++)
         for (unsigned by = 0; by < grid.y; by++)
@@ -208,7 +212,12 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> &bod
                 }
                 while (g_live > 0) {
                     g_progress = false;
-                    for (unsigned t = 0; t < n; t++) {
+                    for (unsigned i = 0; i < n; i++) {
+                        // scheduling order between rendezvous points: ascending thread index by default; reversed or
+                        // pseudo-random per pass on request — a result that depends on it is a missing barrier
+                        unsigned t = i;
+                        if (sched == 1) t = n - 1 - i;
+                        else if (sched == 2) { if (i == 0) rot = (unsigned)(sched_rng() % n); t = (i + rot) % n; if (rot & 1) t = n - 1 - t; }
                         Fiber &f = g_fibers[t];
                         if (f.done) continue;
                         g_self = &f.self;

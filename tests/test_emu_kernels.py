@@ -618,3 +618,19 @@ def test_emu_memcheck_under_address_sanitizer():
     assert "AddressSanitizer" not in r.stdout + r.stderr, (r.stdout + r.stderr)[-4000:]
     assert r.returncode == 0, (r.stdout + r.stderr)[-4000:]
     assert " passed" in r.stdout
+
+
+@pytest.mark.parametrize("sched", ["reverse", "random:7"])
+def test_emu_results_do_not_depend_on_the_fiber_schedule(sched):
+    """racecheck-lite: between rendezvous points the emulator may run the threads of a CTA in any order; a kernel whose
+    output changes with that order is missing a __syncwarp / __syncthreads.  A subset of the parity tests is repeated in
+    a subprocess with the order reversed and with a pseudo-random order per scheduling pass."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, GZPB_EMU_SCHED=sched)
+    sel = "bgzf_levels and (6 or 9 or 1) or emu_snap or inflate_roundtrip or match_v2_edges"
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-k", sel, "-p", "no:cacheprovider"],
+                       env=env, capture_output=True, text=True, timeout=1500, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, (r.stdout + r.stderr)[-4000:]
+    assert " passed" in r.stdout
