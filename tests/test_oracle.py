@@ -171,3 +171,43 @@ def test_compare_with_real_libdeflate_when_present():
         pytest.xfail("the oracle differs from the real library on this machine: " + r.stdout.strip())
     assert r.returncode == 0, r.stdout + r.stderr
     assert "identical" in r.stdout or "parity unpinned" in r.stdout
+
+
+def _spec_cases(text_corpus):
+    from gzp_b200 import synth
+    rnd = random.Random(77)
+    rand = bytes(rnd.getrandbits(8) for _ in range(30000))
+    few = bytes(rnd.choice(b"ACGT") for _ in range(40000))
+    return [
+        ("text", text_corpus[:65280]), ("text-long", text_corpus[:400000]), ("zeros", bytes(70000)), ("random", rand),
+        ("low-entropy", synth.low_entropy(65280)), ("fastq", synth.fastq(120000)), ("periodic", b"abcdefghij" * 6000),
+        ("short", text_corpus[:700]), ("tiny", text_corpus[:60]),
+        # symbol statistics that change inside one DEFLATE block: min_len re-calculations that really change min_len
+        ("few-then-text", few + text_corpus[:60000]), ("text-then-random-then-few", text_corpus[:30000] + rand + few),
+        ("runs", (b"\x00" * 300 + b"\xff" * 5 + text_corpus[:50]) * 150),
+    ]
+
+
+@pytest.mark.parametrize("level", [2, 3, 4, 5, 6, 7, 8, 9])
+def test_speculative_parse_is_byte_identical(level, text_corpus):
+    """the chunk-speculative organisation of the parser (static chains, chunks parsed independently, stitch,
+    event replay in epochs) produces exactly the bytes of the sequential restatement of libdeflate's parser."""
+    for name, data in _spec_cases(text_corpus):
+        want = oracle.deflate(data, level)
+        for chunk in (64, 256, 1000):
+            got, st = oracle.deflate_spec(data, level, chunk)
+            assert got == want, (name, level, chunk)
+            assert st["positions_speculated"] >= len(data) - 5 or len(data) < 200 or st["chunks_skipped"] > 0, (name, st)
+
+
+def test_speculative_parse_with_dictionary_and_sync_flush(text_corpus):
+    d = text_corpus[100000:100000 + 32768]
+    data = text_corpus[100000 + 32768:100000 + 32768 + 131072]
+    for level in (4, 6, 9):
+        for flush in (0, 1):
+            got, st = oracle.deflate_spec(data, level, 256, dictionary=d, flush=flush)
+            assert got == oracle.deflate_ex(data, level, dictionary=d, flush=flush)
+    # the point of the exercise: the speculative parser searches about as little as the sequential one
+    got, st = oracle.deflate_spec(text_corpus[:65280], 6, 256)
+    assert st["positions_restitched"] < 0.03 * 65280 and st["positions_speculated"] < 1.05 * 65280
+    assert st["searches"] < 0.5 * 65280
