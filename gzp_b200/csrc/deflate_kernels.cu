@@ -27,6 +27,7 @@ __constant__ uint16_t c_static_litlen_cw[288];
 __constant__ uint8_t c_static_litlen_len[288];
 __constant__ uint8_t c_min_lens[80];
 __device__ unsigned long long g_phase[32];   // SM-cycle accounting of kernel phases (debug/profiling aid)
+__device__ unsigned long long g_sparse_stats[2];   // sparse path: units parsed from the sparse table, units that missed an entry
 
 static uint32_t h_bitrev(uint32_t v, int n) { uint32_t r = 0; for (int i = 0; i < n; i++) r |= ((v >> i) & 1u) << (n - 1 - i); return r; }
 
@@ -387,10 +388,14 @@ k_link(const __grid_constant__ Geo g, const uint32_t *__restrict__ lists, const 
 // depend on parsing decisions, so all positions are searched in parallel.
 // =============================================================================
 constexpr int kMatchThreads = 1024;
+// Sparse match table (GZPB_SPARSE=1, k_smatch): entries exist only where a speculative chunk parse searched.
+constexpr uint64_t kValidB = 1ull << 62;      // depth/2 column, hash3 fields
+constexpr uint64_t kValidA = 1ull << 63;      // full-depth column
+constexpr int32_t kStatusMiss = 1000;         // internal unit status: the parse consulted an entry that is not there
 #ifdef GZPB_EMU
 // emulator-only statistics (tests/emu): chain nodes visited per position and the processing order of the last
 // sub-unit searched, for estimating lock-step lane utilisation without a GPU
-extern "C" { uint16_t gzpb_emu_visited[65536]; uint16_t gzpb_emu_order[65536]; uint32_t gzpb_emu_npos; }
+extern "C" { uint16_t gzpb_emu_visited[65536]; uint16_t gzpb_emu_order[65536]; uint32_t gzpb_emu_npos; unsigned long long gzpb_emu_sparse_searches, gzpb_emu_sparse_nodes; }
 #define EMU_STAT(p, i, v, np) do { gzpb_emu_visited[p] = (uint16_t)(v); gzpb_emu_order[i] = (uint16_t)(p); gzpb_emu_npos = (np); } while (0)
 #else
 #define EMU_STAT(p, i, v, np) do { } while (0)
@@ -411,7 +416,7 @@ __device__ __forceinline__ uint32_t lz_extend(const uint32_t *s_in, uint32_t p, 
 __global__ void __launch_bounds__(kMatchThreads, 1)
 k_match(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, const uint16_t *__restrict__ prev3g,
         uint64_t *__restrict__ mtab, uint32_t *__restrict__ mtab2, uint8_t *__restrict__ clen_g, uint16_t *__restrict__ order_g,
-        int depth, int nice, int lazy, int have_est, int ht)
+        int depth, int nice, int lazy, int have_est, int ht, const int32_t *__restrict__ only_status)
 {
     GZPB_DYN_SMEM(smem);
     uint32_t *s_in = (uint32_t *)smem;
@@ -422,6 +427,7 @@ k_match(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, cons
     const uint32_t tid = threadIdx.x;
     const Sub sb = sub_geometry(g, blockIdx.x);
     if (!sb.valid) return;
+    if (only_status && only_status[sb.u] != kStatusMiss) return;   // second pass of the sparse path: only units whose parse missed an entry
     const uint32_t n = sb.len;
     const uint8_t *in = g.in + (size_t)sb.u * g.in_stride + sb.h;
     uint64_t *M = mtab + (size_t)sb.u * g.m_stride + sb.h;
@@ -1032,14 +1038,207 @@ __device__ __forceinline__ void table_search(uint64_t e, uint32_t b, bool useB, 
     } else if (lx > b) { len = lx; off = ox; }
 }
 
+// =============================================================================
+// k_smatch (GZPB_SPARSE=1): the match table only where the parser looks.
+//
+// libdeflate's parser searches ~42 % of the positions of a text block and walks 4.4x fewer chain nodes than a
+// table of every position costs (tests/search_stats.py).  Which positions it searches depends on its own
+// decisions — but a parse started cold at any position re-joins the true parse within a few positions
+// (tests/spec_parse_sim.py; oracle_deflate_spec is the CPU statement of the algorithm).  So: the unit is cut
+// into chunks of kSparseChunk positions, one thread per chunk.  (A) Every thread runs the reference's parser
+// loop from its chunk's first position, computing — and publishing with atomicOr — the table entry of every
+// position it searches (full-depth entries for fresh searches, depth/2 entries for look-aheads), and marks its
+// iteration starts.  (B) Every thread then re-parses from where the previous chunk's last iteration ended until
+// it stands on one of its own iteration starts; chunks that never re-join (a match spanning the chunk) pass their
+// real end to the next chunk in further rounds.  Every position the true parse searches now has its entry —
+// provided min_len is what this kernel assumed (the value at the start of the unit's first DEFLATE block).
+// k_emit checks the valid bits of every entry it commits; a unit that misses one (min_len changed inside the
+// unit) is flagged and redone by k_match + k_emit in a second, filtered pass.  Bit-identical either way.
+// =============================================================================
+constexpr int kSparseThreads = 512;
+constexpr uint32_t kSparseChunk = 128;
+
+// the body of k_match's phase 2 for one position: best match over `depth` nodes with the depth/2 snapshot
+// (full), or over depth/2 nodes only (look-ahead entry: B column + hash3 fields)
+__device__ __forceinline__ uint64_t sparse_entry(const uint32_t *s_in, const uint16_t *s_next, const uint16_t *p3, uint32_t n, uint32_t p,
+                                                 uint32_t depth, uint32_t nice, bool lazy, bool full)
+{
+    const uint32_t maxlen = min((uint32_t)kMaxMatch, n - p);
+    if (maxlen < 5) return kValidA | kValidB;
+    const uint32_t nicep = min(nice, maxlen);
+    const uint32_t seq4 = ld32u(s_in, p);
+    const uint32_t w1 = ld32u(s_in, p + 4), w2 = ld32u(s_in, p + 8);
+    const uint32_t d3 = p3[p];
+    uint32_t off3 = 0;
+    if (d3 && d3 <= 8192u && ((ld32u(s_in, p - d3) ^ seq4) & 0xFFFFFFu) == 0) off3 = d3;
+    const uint32_t depthB = depth >> 1, limit = full ? depth : depthB;
+    const uint8_t *b8 = (const uint8_t *)s_in;
+    uint32_t best = 3, boff = 0, lenB = 0, offB = 0, pbest = 0;
+    bool haveB = !(lazy && full);
+    uint32_t q = p, visited = 0;
+    if (limit) for (;;) {
+        const uint32_t d = s_next[q];
+        if (d == 0) break;
+        q -= d;
+        if (p - q >= (uint32_t)kWindow) break;
+        visited++;
+        bool cand;
+        if (best == 3) cand = (ld32u(s_in, q) == seq4);
+        else cand = (b8[q + best] == pbest) && (ld32u(s_in, q) == seq4);
+        if (cand) {
+            uint32_t len;
+            uint32_t x = ld32u(s_in, q + 4) ^ w1;
+            if (x) len = 4 + ((__ffs(x) - 1) >> 3);
+            else {
+                x = ld32u(s_in, q + 8) ^ w2;
+                if (x) len = 8 + ((__ffs(x) - 1) >> 3);
+                else len = (maxlen > 12) ? lz_extend(s_in, p, q, 12, maxlen) : 12;
+            }
+            len = min(len, maxlen);
+            if (len > best) {
+                best = len; boff = p - q;
+                if (len >= nicep) break;
+                pbest = b8[p + best];
+            }
+        }
+        if (!haveB && visited == depthB) { haveB = true; lenB = best > 3 ? best : 0; offB = boff; }
+        if (visited == limit) break;
+    }
+#ifdef GZPB_EMU
+    gzpb_emu_sparse_searches++; gzpb_emu_sparse_nodes += visited;
+#endif
+    const uint32_t lenA = best > 3 ? best : 0;
+    if (!full) return pack_entry(0, 0, lenA, boff, d3 != 0, off3) | kValidB;
+    if (!haveB) { lenB = lenA; offB = boff; }
+    if (!lazy) { lenB = 0; offB = 0; }
+    return pack_entry(lenA, boff, lenB, offB, d3 != 0, off3) | kValidA | kValidB;
+}
+
+__global__ void __launch_bounds__(kSparseThreads, 1)
+k_smatch(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, const uint16_t *__restrict__ prev3g,
+         uint64_t *__restrict__ mtab, int depth, int nice, int mode)
+{
+    GZPB_DYN_SMEM(smem);
+    uint32_t *s_in = (uint32_t *)smem;
+    uint16_t *s_next = (uint16_t *)(smem + kInStride);
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t s_iter[2048];            // iteration starts of the speculative parses, one bit per position
+    __shared__ uint32_t s_end[kSparseThreads];   // where each chunk's last iteration ends
+    __shared__ uint32_t s_used[8], s_flag;
+    const uint32_t tid = threadIdx.x;
+    const Sub sb = sub_geometry(g, blockIdx.x);  // spu == 1: the sub-unit is the unit
+    if (!sb.valid) return;
+    const uint32_t n = sb.len, nb = sb.nb, ne = sb.ne;
+    const uint8_t *in = g.in + (size_t)sb.u * g.in_stride + sb.h;
+    unsigned long long *M = (unsigned long long *)(mtab + (size_t)sb.u * g.m_stride + sb.h);
+    const uint16_t *p3 = prev3g + (size_t)blockIdx.x * kMaxUnitBytes;
+
+    if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+    for (uint32_t i = tid; i < 2048; i += kSparseThreads) s_iter[i] = 0;
+    if (tid < 8) s_used[tid] = 0;
+    for (uint32_t i = (nb & ~127u) + tid; i < n; i += kSparseThreads) M[i] = 0ull;     // no stale entries from the lane's previous batch
+    __syncthreads();
+    if (n >= 5) {
+        if (tid == 0) {
+            uint32_t bin = (n + 15u) & ~15u, bnx = (n * 2 + 15u) & ~15u;
+            mbar_expect_tx(&bar, bin + bnx);
+            tma_load_1d(s_in, in, bin, &bar);
+            tma_load_1d(s_next, next4g + (size_t)blockIdx.x * kMaxUnitBytes, bnx, &bar);
+        }
+        mbar_wait(&bar, 0);
+    }
+    // min_len at the start of the unit's first DEFLATE block (calculate_min_match_len)
+    uint32_t min_len = 3;
+    if (n - nb >= 512) {
+        const uint32_t span = min(n - nb, 4096u);
+        const uint8_t *b8 = (const uint8_t *)s_in;
+        for (uint32_t i = tid; i < span; i += kSparseThreads) { const uint32_t c = b8[nb + i]; atomicOr(&s_used[c >> 5], 1u << (c & 31)); }
+        __syncthreads();
+        uint32_t nu = 0;
+        for (int i = 0; i < 8; i++) nu += __popc(s_used[i]);
+        min_len = choose_min_match_len(nu, depth);
+    }
+    const bool lazy = mode != 0;
+    // The reference's parser loop (compress_hc, modes 0 and 1) as a state machine that performs exactly ONE search per
+    // trip — a fresh full-depth search at an iteration start, or the depth/2 look-ahead behind a pending match — so that
+    // the lanes of a warp, each parsing its own chunk, meet in the same chain-walk loop.  Runs from iteration start q0
+    // until an iteration ends at or beyond `stop`, or (rejoin) on an iteration start this chunk's speculation marked.
+    auto run = [&](uint32_t q0, uint32_t stop, bool rejoin) -> uint32_t {
+        uint32_t q = q0, m = 0, cl = 0, co = 0;
+        bool in_look = false;
+        for (;;) {
+            if (!in_look) {
+                if (q >= stop || (rejoin && ((s_iter[q >> 5] >> (q & 31)) & 1u))) return q;
+                if (!rejoin) atomicOr(&s_iter[q >> 5], 1u << (q & 31));
+            }
+            const uint32_t pos = in_look ? m + 1 : q;
+            const uint32_t maxlen = pos < n ? min((uint32_t)kMaxMatch, n - pos) : 0u;
+            uint64_t e = 0;
+            if (!in_look || maxlen >= 5) {
+                e = sparse_entry(s_in, s_next, p3, n, pos, (uint32_t)depth, (uint32_t)nice, lazy, !in_look);
+                atomicOr(&M[pos], (unsigned long long)e);
+            }
+            if (!in_look) {
+                table_search(e, min_len - 1, false, maxlen, cl, co);
+                if (mode == 0) { q = (cl >= min_len && (cl > 3 || co <= 4096)) ? q + cl : q + 1; continue; }
+                if (cl < min_len || (cl == 3 && co > 8192)) { q = q + 1; continue; }
+                m = q;
+                if (cl >= min((uint32_t)nice, maxlen)) { q = m + cl; continue; }
+                in_look = true;
+            } else {
+                uint32_t nl, no;
+                table_search(e, cl - 1, true, maxlen, nl, no);
+                if (nl >= cl && 4 * (int)(nl - cl) + ((int)bsr32(co) - (int)bsr32(no)) > 2) {
+                    m++; cl = nl; co = no;                         // literal; the look-ahead match becomes the pending one
+                    if (cl >= min((uint32_t)nice, maxlen)) { q = m + cl; in_look = false; }
+                } else { q = m + cl; in_look = false; }
+            }
+        }
+    };
+    // ---- (A) speculate: chunk `tid` from its first position ----
+    const uint32_t nchunks = (ne - nb + kSparseChunk - 1) / kSparseChunk;
+    const uint32_t s0 = nb + tid * kSparseChunk, s1 = min(ne, s0 + kSparseChunk);
+    uint32_t spec_end = 0;
+    if (tid < nchunks) {
+        spec_end = run(s0, s1, false);
+        s_end[tid] = spec_end;
+    }
+    __syncthreads();
+    // ---- (B) stitch: re-parse from the previous chunk's end until this chunk's own speculation takes over ----
+    uint32_t entry = (tid >= 1 && tid < nchunks) ? s_end[tid - 1] : 0xFFFFFFFFu, done_entry = 0xFFFFFFFFu;
+    for (;;) {
+        if (tid == 0) s_flag = 0;
+        __syncthreads();
+        if (tid >= 1 && tid < nchunks && entry != done_entry) {
+            uint32_t new_end;
+            if (entry >= s1) new_end = entry;                      // the chunk lies inside a match of an earlier one
+            else {
+                const uint32_t q = run(entry, s1, true);
+                new_end = q < s1 ? spec_end : q;
+            }
+            done_entry = entry;
+            if (new_end != s_end[tid]) { s_end[tid] = new_end; s_flag = 1; }
+        }
+        __syncthreads();
+        const bool again = s_flag != 0;
+        if (tid >= 1 && tid < nchunks) entry = s_end[tid - 1];
+        __syncthreads();
+        if (!again) break;
+    }
+}
+
+template <bool kSparse>
 __global__ void __launch_bounds__(kEmitThreads)
 k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
        const uint64_t *__restrict__ mtab, const uint32_t *__restrict__ mtab2, const uint32_t *__restrict__ crc_in, uint32_t *__restrict__ tok_base,
        uint8_t *__restrict__ out_base, uint32_t *__restrict__ out_len, int32_t *__restrict__ out_status,
-       int mode, int depth, int nice, int level, int format)
+       int mode, int depth, int nice, int level, int format, int pass2)
 {
     __shared__ EmitShared S;
     const uint32_t u = blockIdx.x, tid = threadIdx.x;
+    // kSparse: the match table comes from k_smatch — every committed entry's valid bits are checked and a miss flags the
+    // unit (kStatusMiss); pass2: the filtered second pass that redoes exactly those units from k_match's full table
+    if (pass2 && out_status[u] != kStatusMiss) return;
     const uint32_t n = g.unit_len[u];          // dictionary + data
     const uint32_t dict = g.unit_dict[u];      // preset dictionary in front of the data (never emitted)
     const uint32_t dl = n - dict;              // bytes to encode
@@ -1247,6 +1446,7 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
                     //   word = advance (bits 0-8) | next-is-H (bit 9) | token-is-match (bit 10)
                     const uint32_t q = p + lane;
                     uint32_t wF = 1, wH = 1, lenF = 0, offF = 0, lenH = 0, offH = 0;
+                    bool badF = false, badH = false;            // sparse table: this step used an entry that is not there
                     if (q < max_block_end) {
                         const uint64_t e0 = P.M(q);
                         const uint32_t maxlen = min((uint32_t)kMaxMatch, n - q);
@@ -1255,6 +1455,8 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
                         const uint32_t nice_q = min((uint32_t)nice, maxlen);
                         uint32_t cl, co;
                         table_search(e0, min_len - 1, false, maxlen, cl, co);
+                        const bool e1_missing = kSparse && maxlen1 >= 5 && !(e1 & kValidB);
+                        if (kSparse) { badF = !(e0 & kValidA); badH = !(e0 & kValidB); }
                         if (mode == 0) {
                             if (cl >= min_len && (cl > 3 || co <= 4096)) { lenF = cl; offF = co; wF = cl | (1u << 10); }
                         } else {
@@ -1265,6 +1467,7 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
                                     uint32_t nl, no;
                                     table_search(e1, cl - 1, true, maxlen1, nl, no);
                                     take = !(nl >= cl && 4 * (int)(nl - cl) + ((int)bsr32(co) - (int)bsr32(no)) > 2);
+                                    badF = badF || e1_missing;
                                 }
                                 if (take) { lenF = cl; offF = co; wF = cl | (1u << 10); }
                                 else wF = 1u | (1u << 9);
@@ -1279,6 +1482,7 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
                                     uint32_t nl, no;
                                     table_search(e1, hl - 1, true, maxlen1, nl, no);
                                     take = !(nl >= hl && 4 * (int)(nl - hl) + ((int)bsr32(ho) - (int)bsr32(no)) > 2);
+                                    badH = badH || e1_missing;
                                 }
                                 if (take) { lenH = hl; offH = ho; wH = hl | (1u << 10); }
                                 else wH = 1u | (1u << 9);
@@ -1318,6 +1522,10 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
                         if (Lr <= Lc && Lr <= Ls && Lr < 64) { event = 1; commit_mask = vis & ((1u << Lr) - 1); next_p = p + Lr; next_h = 0; }
                         else if (Ls <= Lc && Ls < 64) { event = 3; commit_mask = vis & (Ls == 31 ? 0xFFFFFFFFu : ((2u << Ls) - 1)); next_p = __shfl_sync(0xFFFFFFFFu, e_l, Ls); next_h = 0; }
                         else if (Lc < 64) { event = 2; commit_mask = vis & (Lc == 31 ? 0xFFFFFFFFu : ((2u << Lc) - 1)); next_p = __shfl_sync(0xFFFFFFFFu, e_l, Lc); next_h = 0; }
+                    }
+                    if (kSparse) {
+                        const uint32_t missed = __ballot_sync(0xFFFFFFFFu, ((commit_mask >> lane) & 1u) && (asH ? badH : badF));
+                        if (missed && lane == 0) S.status = kStatusMiss;
                     }
                     // ---- commit ----
                     if ((commit_mask >> lane) & 1u) {
@@ -1630,6 +1838,7 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
             uint32_t avail = dl + max(128u, (uint32_t)((double)dl * 0.1));
             if (nbytes > avail) st = -4;
         }
+        if (kSparse) { atomicAdd(&g_sparse_stats[0], 1ull); if (S.status == kStatusMiss) { atomicAdd(&g_sparse_stats[1], 1ull); st = kStatusMiss; } }
         out_len[u * 2] = total;
         out_len[u * 2 + 1] = hdr_off;
         out_status[u] = st;
@@ -1802,6 +2011,12 @@ cudaError_t launch_check_combine(const uint32_t *sums, const uint32_t *unit_len,
     return cudaGetLastError();
 }
 
+void read_sparse_stats(unsigned long long *out2, bool reset)
+{
+    cudaMemcpyFromSymbol(out2, g_sparse_stats, 2 * sizeof(unsigned long long));
+    if (reset) { unsigned long long z[2] = {0, 0}; cudaMemcpyToSymbol(g_sparse_stats, z, sizeof z); }
+}
+
 void read_phase_counters(unsigned long long *out, bool reset)
 {
     cudaMemcpyFromSymbol(out, g_phase, sizeof(unsigned long long) * 32);
@@ -1842,6 +2057,7 @@ cudaError_t launch_deflate_pipeline(const DeflateBatch &b, cudaStream_t st)
         cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, chain_smem);
         cudaFuncSetAttribute(k_match, cudaFuncAttributeMaxDynamicSharedMemorySize, match_smem);
         cudaFuncSetAttribute(k_match2, cudaFuncAttributeMaxDynamicSharedMemorySize, match_smem);
+        cudaFuncSetAttribute(k_smatch, cudaFuncAttributeMaxDynamicSharedMemorySize, match_smem);
         attr_done[cur_dev] = true;
     }
     if (b.nunits == 0) return cudaSuccess;
@@ -1873,16 +2089,34 @@ cudaError_t launch_deflate_pipeline(const DeflateBatch &b, cudaStream_t st)
             DBG_SYNC("k_chain");
         }
         if (b.timer) { b.timer->stop(st); b.timer->start(KT_MATCH, st); }
+        if (b.sparse && b.lists && b.spu == 1 && !lp.ht && (lp.mode == 0 || lp.mode == 1)) {
+            // sparse path: speculative table, parse with miss detection, then the two filtered fallback launches
+            GZPB_LAUNCH(k_smatch, b.nunits, kSparseThreads, match_smem, st, g, b.next4, b.prev3, b.mtab, lp.depth, lp.nice, lp.mode);
+            DBG_SYNC("k_smatch");
+            if (b.timer) { b.timer->stop(st); b.timer->start(KT_EMIT, st); }
+            GZPB_LAUNCH(k_emit<true>, b.nunits, kEmitThreads, 0, st, g, b.unit_flags, b.mtab, b.mtab2, b.crc, b.tokens, b.out, b.out_len,
+                        b.status, lp.mode, lp.depth, lp.nice, b.level, b.format, 0);
+            DBG_SYNC("k_emit(sparse)");
+            if (b.timer) { b.timer->stop(st); b.timer->start(KT_MATCH, st); }
+            GZPB_LAUNCH(k_match, b.nunits * b.spu, kMatchThreads, match_smem, st, g, b.next4, b.prev3, b.mtab, b.mtab2, b.clen, b.order, lp.depth, lp.nice, lp.mode, 1, lp.ht, b.status);
+            DBG_SYNC("k_match(missed)");
+            if (b.timer) { b.timer->stop(st); b.timer->start(KT_EMIT, st); }
+            GZPB_LAUNCH(k_emit<false>, b.nunits, kEmitThreads, 0, st, g, b.unit_flags, b.mtab, b.mtab2, b.crc, b.tokens, b.out, b.out_len,
+                        b.status, lp.mode, lp.depth, lp.nice, b.level, b.format, 1);
+            DBG_SYNC("k_emit(missed)");
+            if (b.timer) b.timer->stop(st);
+            return cudaGetLastError();
+        }
         if (b.gidx && b.lists)
             GZPB_LAUNCH(k_match2, b.nunits * b.spu, kMatchThreads, match_smem, st, g, b.next4, b.prev3, b.gidx, b.gocc, b.mtab, b.mtab2, b.clen, b.order, lp.depth, lp.nice, lp.mode, lp.ht);
         else
-            GZPB_LAUNCH(k_match, b.nunits * b.spu, kMatchThreads, match_smem, st, g, b.next4, b.prev3, b.mtab, b.mtab2, b.clen, b.order, lp.depth, lp.nice, lp.mode, b.lists != nullptr, lp.ht);
+            GZPB_LAUNCH(k_match, b.nunits * b.spu, kMatchThreads, match_smem, st, g, b.next4, b.prev3, b.mtab, b.mtab2, b.clen, b.order, lp.depth, lp.nice, lp.mode, b.lists != nullptr, lp.ht, (const int32_t *)nullptr);
         DBG_SYNC("k_match");
         if (b.timer) b.timer->stop(st);
     }
     if (b.timer) b.timer->start(KT_EMIT, st);
-    GZPB_LAUNCH(k_emit, b.nunits, kEmitThreads, 0, st, g, b.unit_flags, b.mtab, b.mtab2, b.crc, b.tokens, b.out, b.out_len,
-                                             b.status, lp.mode, lp.depth, lp.nice, b.level, b.format);
+    GZPB_LAUNCH(k_emit<false>, b.nunits, kEmitThreads, 0, st, g, b.unit_flags, b.mtab, b.mtab2, b.crc, b.tokens, b.out, b.out_len,
+                                             b.status, lp.mode, lp.depth, lp.nice, b.level, b.format, 0);
     DBG_SYNC("k_emit");
     if (b.timer) b.timer->stop(st);
     return cudaGetLastError();

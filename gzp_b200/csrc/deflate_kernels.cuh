@@ -62,10 +62,12 @@ struct DeflateBatch {
     uint32_t in_stride, m_stride, tok_stride, out_stride;   // per-unit strides (bytes / entries / tokens / bytes)
     uint32_t spu, seg;        // sub-units per unit and new positions per sub-unit (gzpb_common.cuh: Geo)
     int check_kind;           // -1 none, 0 CRC-32, 1 Adler-32 (written to `crc`)
+    int sparse;               // 1 = sparse match table (k_smatch) where the level and the unit geometry allow it
 };
 
 void upload_deflate_constants();
 void read_phase_counters(unsigned long long *out, bool reset);
+void read_sparse_stats(unsigned long long *out2, bool reset);
 cudaError_t launch_deflate_pipeline(const DeflateBatch &b, cudaStream_t st);
 cudaError_t launch_pack(const DeflateBatch &b, cudaStream_t st);
 cudaError_t launch_check_combine(const uint32_t *sums, const uint32_t *unit_len, const uint32_t *unit_dict, uint32_t nunits, int kind,

@@ -634,3 +634,61 @@ def test_emu_results_do_not_depend_on_the_fiber_schedule(sched):
                        env=env, capture_output=True, text=True, timeout=1500, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert r.returncode == 0, (r.stdout + r.stderr)[-4000:]
     assert " passed" in r.stdout
+
+
+def _sparse_stats(ctx):
+    import ctypes as C
+    u, m = C.c_uint64(0), C.c_uint64(0)
+    ctx.L.gzpb_debug_sparse_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_int]
+    ctx.L.gzpb_debug_sparse_stats(ctx.h, C.byref(u), C.byref(m), 1)
+    return u.value, m.value
+
+
+def _run_sparse(fmt, level, bs, data):
+    ctx = emu.EmuContext(fmt, level, max_block_bytes=bs)
+    try:
+        assert ctx.L.gzpb_ctx_variant(ctx.h) == b"split+link+smatch"
+        got = ctx.encode_stream(data, bs)
+        units, missed = _sparse_stats(ctx)
+    finally:
+        ctx.close()
+    assert got == oracle.compress_stream(fmt, level, bs or oracle.DEFAULT_BUFSIZE[fmt], [data]), (fmt, level, len(data))
+    return units, missed
+
+
+@pytest.mark.parametrize("level", [2, 3, 4, 5, 6, 7])
+def test_emu_sparse_match_table_levels(monkeypatch, level):
+    """GZPB_SPARSE=1 (k_smatch: speculative chunk parses fill the match table only where the parser looks): bit-exact,
+    and plain text never needs the fallback pass."""
+    monkeypatch.setenv("GZPB_SPARSE", "1")
+    units, missed = _run_sparse(oracle.BGZF, level, 0, TEXT[:140000])
+    assert units == 3 and missed == 0
+
+
+def test_emu_sparse_match_table_edges_and_fallback(monkeypatch):
+    monkeypatch.setenv("GZPB_SPARSE", "1")
+    rnd = random.Random(77)
+    rand = bytes(rnd.getrandbits(8) for _ in range(30000))
+    few = bytes(rnd.choice(b"ACGT") for _ in range(40000))
+    clean = [b"", b"x", TEXT[:32], TEXT[:33], TEXT[:700], bytes(70000), b"\xff" * 40000, rand, b"abcdefghij" * 6000, TEXT[:4999], TEXT[:65280],
+             synth.low_entropy(65280), synth.fastq(65000), (b"\x00" * 300 + b"\xff" * 5 + TEXT[:50]) * 150]
+    for d in clean:
+        units, missed = _run_sparse(oracle.BGZF, 6, 0, d)
+        assert missed == 0, len(d)
+    # symbol statistics that change inside the unit change min_len: the parse misses entries, the unit is flagged and
+    # redone from the full table by the filtered second pass — still the oracle's bytes
+    for d in ((few + TEXT[:60000])[:65280], (TEXT[:20000] + rand[:20000] + few)[:65280]):
+        units, missed = _run_sparse(oracle.BGZF, 6, 0, d)
+        assert (units, missed) == (1, 1)
+    # a stream mixing both kinds of unit
+    units, missed = _run_sparse(oracle.BGZF, 5, 0, TEXT[:65280] + (few + TEXT[:60000])[:65280] + TEXT[:30000])
+    assert units == 3 and missed == 1
+    # dictionary formats whose unit (32 KiB dictionary + block) still fits one sub-unit take the sparse path too
+    units, missed = _run_sparse(oracle.GZIP, 6, 32768, TEXT[:150000])
+    assert units >= 4 and missed == 0
+    units, missed = _run_sparse(oracle.ZLIB, 4, 32768, TEXT[:100000])
+    assert missed == 0
+    # long units (sub-units with a halo), lazy2 levels and level 1 keep the full table
+    for fmt, level, bs in ((oracle.MGZIP, 6, 131072), (oracle.BGZF, 9, 0), (oracle.BGZF, 1, 0)):
+        units, missed = _run_sparse(fmt, level, bs, TEXT[:140000])
+        assert units == 0
