@@ -1,6 +1,7 @@
 """A/B of the kernel-set variants on the GPU (not a test; run under gpurun): device-resident BGZF level-L encode of
 `blocks` blocks with the default kernels (k_split + k_link + k_match) and with GZPB_MATCH_V2=1 (k_split + k_group +
-k_link(hash3) + k_match2), per-kernel CUDA-event times, identical output checked.  One JSON line per variant.
+k_link(hash3) + k_match2) and with GZPB_SPARSE=1 (k_split + k_link + k_smatch + k_emit<sparse> + filtered fallback),
+per-kernel CUDA-event times, identical output checked.  One JSON line per variant.
 usage: python tests/perf_variants.py [blocks] [level] [steps]"""
 import ctypes as C
 import json
@@ -33,11 +34,13 @@ def main():
     st = torch.cuda.current_stream()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     ref = None
-    for variant, env in (("split+link+match", None), ("split+group+match2", "1"), ("split+link+match", None), ("split+group+match2", "1")):
+    L.gzpb_debug_sparse_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_int]
+    for variant, env in (("split+link+match", None), ("split+link+smatch", "GZPB_SPARSE"), ("split+group+match2", "GZPB_MATCH_V2"),
+                         ("split+link+match", None), ("split+link+smatch", "GZPB_SPARSE")):
+        os.environ.pop("GZPB_MATCH_V2", None)
+        os.environ.pop("GZPB_SPARSE", None)
         if env:
-            os.environ["GZPB_MATCH_V2"] = env
-        else:
-            os.environ.pop("GZPB_MATCH_V2", None)
+            os.environ[env] = "1"
         ctx = gzp_b200.Context(gzp_b200.BGZF, level, device=0, max_block_bytes=BLOCK, max_blocks_in_flight=min(nblk, 3256))
         assert L.gzpb_ctx_variant(ctx._h).decode() == variant
         d_packed = torch.zeros((nblk * 73728,), dtype=torch.uint8, device=dev)
@@ -67,10 +70,12 @@ def main():
             ms.append(e0.elapsed_time(e1))
         kms = {k: ctx.kernel_ms(k) for k in ("chain", "match", "emit", "gather")}
         ctx.set_profiling(False)
+        su, sm = C.c_uint64(0), C.c_uint64(0)
+        L.gzpb_debug_sparse_stats(ctx._h, C.byref(su), C.byref(sm), 1)
         ctx.close()
         best = min(ms)
         print(json.dumps({"variant": variant, "level": level, "blocks": nblk, "ms_best": best, "ms_all": ms,
-                          "GiB/s": nblk * BLOCK / (best / 1e3) / (1 << 30), "out_bytes": total,
+                          "GiB/s": nblk * BLOCK / (best / 1e3) / (1 << 30), "out_bytes": total, "sparse_units": su.value, "sparse_missed": sm.value,
                           "kernel_ms_per_launch": {k: v[0] / max(v[1], 1) for k, v in kms.items()}}), flush=True)
 
 

@@ -473,7 +473,7 @@ def match_v2(monkeypatch):
     yield
 
 
-@pytest.mark.parametrize("level", [1, 2, 4, 5, 6, 7, 9])
+@pytest.mark.parametrize("level", [1, 4, 6, 9])
 def test_emu_match_v2_bgzf_levels(match_v2, level):
     ctx = emu.EmuContext(oracle.BGZF, level)
     assert ctx.L.gzpb_ctx_variant(ctx.h) == b"split+group+match2"
@@ -656,7 +656,7 @@ def _run_sparse(fmt, level, bs, data):
     return units, missed
 
 
-@pytest.mark.parametrize("level", [2, 3, 4, 5, 6, 7])
+@pytest.mark.parametrize("level", [2, 4, 6, 7])
 def test_emu_sparse_match_table_levels(monkeypatch, level):
     """GZPB_SPARSE=1 (k_smatch: speculative chunk parses fill the match table only where the parser looks): bit-exact,
     and plain text never needs the fallback pass."""

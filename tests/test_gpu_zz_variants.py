@@ -1,0 +1,67 @@
+"""Kernel-set variants on the GPU (runs last: the file name sorts after the other GPU tests).
+
+GZPB_MATCH_V2=1  k_group + k_match2 (hash groups instead of linked chains) — measured in round 1, bit-identical, not
+                 faster (profiles/README.md); kept as a checked alternative.
+GZPB_SPARSE=1    k_smatch + k_emit<sparse> + filtered fallback: the match table only where the parser
+                 looks.  Developed and held bit-exact on the CPU SIMT emulator (tests/test_emu_kernels.py, also under
+                 schedule perturbation and AddressSanitizer); this file is its first contact with real hardware.
+Both are opt-in through the environment at gzpb_create; the default kernel set is untouched by them."""
+import ctypes as C
+import random
+
+import pytest
+
+import oracle
+import gzp_b200
+from gzp_b200 import BGZF, GZIP, _lib, synth
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(180)]
+
+
+def _encode(env, monkeypatch, fmt, level, bs, data, want_variant):
+    for k in ("GZPB_MATCH_V2", "GZPB_SPARSE"):
+        monkeypatch.delenv(k, raising=False)
+    if env:
+        monkeypatch.setenv(env, "1")
+    L = _lib.load()
+    ctx = gzp_b200.Context(fmt, level, max_block_bytes=bs, max_blocks_in_flight=64)
+    try:
+        assert L.gzpb_ctx_variant(ctx._h).decode() == want_variant
+        got = ctx.encode_stream(data, bs)
+        stats = None
+        if env == "GZPB_SPARSE":
+            u, m = C.c_uint64(0), C.c_uint64(0)
+            L.gzpb_debug_sparse_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_int]
+            L.gzpb_debug_sparse_stats(ctx._h, C.byref(u), C.byref(m), 1)
+            stats = (u.value, m.value)
+    finally:
+        ctx.close()
+    return got, stats
+
+
+def test_match_v2_is_bit_identical_on_gpu(monkeypatch, text_corpus):
+    for level in (1, 4, 6, 9):
+        data = text_corpus[:400000]
+        got, _ = _encode("GZPB_MATCH_V2", monkeypatch, BGZF, level, 65280, data, "split+group+match2")
+        assert got == oracle.compress_stream(BGZF, level, 65280, [data]), level
+
+
+def test_sparse_match_table_is_bit_identical_on_gpu(monkeypatch, text_corpus):
+    rnd = random.Random(77)
+    rand = bytes(rnd.getrandbits(8) for _ in range(30000))
+    few = bytes(rnd.choice(b"ACGT") for _ in range(40000))
+    mixed = (few + text_corpus[:60000])[:65280]
+    for level in (2, 4, 5, 6, 7):
+        data = text_corpus[:1_000_000]
+        got, (units, missed) = _encode("GZPB_SPARSE", monkeypatch, BGZF, level, 65280, data, "split+link+smatch")
+        assert got == oracle.compress_stream(BGZF, level, 65280, [data]), level
+        assert units == 16 and missed == 0, (level, units, missed)
+    for data, want_missed in ((bytes(200000), 0), (synth.low_entropy(300000), None), (synth.fastq(200000), None), (rand, 0), (b"", 0),
+                              (text_corpus[:65280] + mixed + text_corpus[:30000], 1)):
+        got, (units, missed) = _encode("GZPB_SPARSE", monkeypatch, BGZF, 6, 65280, data, "split+link+smatch")
+        assert got == oracle.compress_stream(BGZF, 6, 65280, [data]), len(data)
+        if want_missed is not None:
+            assert missed == want_missed, (len(data), units, missed)
+    data = text_corpus[:500000]
+    got, (units, missed) = _encode("GZPB_SPARSE", monkeypatch, GZIP, 6, 32768, data, "split+link+smatch")
+    assert got == oracle.compress_stream(GZIP, 6, 32768, [data]) and missed == 0
