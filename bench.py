@@ -164,6 +164,32 @@ def cpu_baseline(data, threads, sample_mb=0.0):
             "sample": f"{passes} pass(es) over {n} B of the same text stream ({n // BLOCK} blocks), ratio {olen.value / n:.4f}, {total_t:.2f} s"}, val
 
 
+def variant_ab(device_index, blocks):
+    """Informational, never part of `value` / `e2e`: device-resident timing of the opt-in kernel sets (GZPB_SPARSE=1,
+    GZPB_MATCH_V2=1) against the default one on one batch, in a SEPARATE process with a timeout after
+    every measurement of this run is finished and its GPU memory released — a variant that fails cannot touch the
+    numbers above.  Returns the JSON lines of tests/perf_variants.py, or the reason there are none."""
+    try:
+        env = dict(os.environ, CUDA_VISIBLE_DEVICES=str(device_index) if "CUDA_VISIBLE_DEVICES" not in os.environ else os.environ["CUDA_VISIBLE_DEVICES"])
+        for k in ("GZPB_SPARSE", "GZPB_MATCH_V2", "RANK", "WORLD_SIZE", "LOCAL_RANK"):
+            env.pop(k, None)
+        log("variant A/B in a subprocess")
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "perf_variants.py"), str(blocks), str(LEVEL), "3"],
+                           env=env, capture_output=True, text=True, timeout=150)
+        out = []
+        for ln in r.stdout.splitlines():
+            if ln.startswith("{"):
+                d = json.loads(ln)
+                d.pop("ms_all", None)
+                out.append(d)
+        log("variant A/B done (rc %d, %d lines)" % (r.returncode, len(out)))
+        if r.returncode != 0:
+            return {"error": "perf_variants.py rc %d: %s" % (r.returncode, (r.stderr or "").strip()[-300:]), "lines": out}
+        return out
+    except Exception as e:                                   # noqa: BLE001 - informational leg, never fatal
+        return {"error": repr(e)}
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU implementation of the path (oracle port, all host threads)."""
     if rank != 0:
@@ -410,11 +436,14 @@ def main():
                          "kernel_ms_per_launch": {k: v[0] / max(v[1], 1) for k, v in kms.items()}, "kernel_time_share": share},
             "cpu_baseline": cpu,
         }
-        print(json.dumps(line), flush=True)
     L.gzpb_host_free(h_in); L.gzpb_host_free(h_out)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+    if rank == 0:
+        if world == 1 and not os.environ.get("GZPB_BENCH_NO_VARIANTS"):
+            line["variants"] = variant_ab(local_rank, min(nblk, args.inflight))
+        print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":

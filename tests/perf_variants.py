@@ -76,7 +76,8 @@ def main():
         best = min(ms)
         print(json.dumps({"variant": variant, "level": level, "blocks": nblk, "ms_best": best, "ms_all": ms,
                           "GiB/s": nblk * BLOCK / (best / 1e3) / (1 << 30), "out_bytes": total, "sparse_units": su.value, "sparse_missed": sm.value,
-                          "kernel_ms_per_launch": {k: v[0] / max(v[1], 1) for k, v in kms.items()}}), flush=True)
+                          "kernel_ms_per_batch": {k: v[0] / steps for k, v in kms.items()},
+                          "kernel_launches_per_batch": {k: v[1] / steps for k, v in kms.items()}}), flush=True)
 
 
 if __name__ == "__main__":
