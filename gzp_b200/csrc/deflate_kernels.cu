@@ -1056,7 +1056,7 @@ __device__ __forceinline__ void table_search(uint64_t e, uint32_t b, bool useB, 
 // unit) is flagged and redone by k_match + k_emit in a second, filtered pass.  Bit-identical either way.
 // =============================================================================
 constexpr int kSparseThreads = 512;
-constexpr uint32_t kSparseChunk = 128;
+constexpr uint32_t kSparseChunk = 128;          // default positions per chunk (GZPB_SPARSE_CHUNK overrides: 128..4096)
 
 // the body of k_match's phase 2 for one position: best match over `depth` nodes with the depth/2 snapshot
 // (full), or over depth/2 nodes only (look-ahead entry: B column + hash3 fields)
@@ -1116,7 +1116,7 @@ __device__ __forceinline__ uint64_t sparse_entry(const uint32_t *s_in, const uin
 
 __global__ void __launch_bounds__(kSparseThreads, 1)
 k_smatch(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, const uint16_t *__restrict__ prev3g,
-         uint64_t *__restrict__ mtab, int depth, int nice, int mode)
+         uint64_t *__restrict__ mtab, int depth, int nice, int mode, uint32_t chunk)
 {
     GZPB_DYN_SMEM(smem);
     uint32_t *s_in = (uint32_t *)smem;
@@ -1196,8 +1196,8 @@ k_smatch(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, con
         }
     };
     // ---- (A) speculate: chunk `tid` from its first position ----
-    const uint32_t nchunks = (ne - nb + kSparseChunk - 1) / kSparseChunk;
-    const uint32_t s0 = nb + tid * kSparseChunk, s1 = min(ne, s0 + kSparseChunk);
+    const uint32_t nchunks = (ne - nb + chunk - 1) / chunk;       // <= kSparseThreads (the launcher checks)
+    const uint32_t s0 = nb + tid * chunk, s1 = min(ne, s0 + chunk);
     uint32_t spec_end = 0;
     if (tid < nchunks) {
         spec_end = run(s0, s1, false);
@@ -2091,7 +2091,8 @@ cudaError_t launch_deflate_pipeline(const DeflateBatch &b, cudaStream_t st)
         if (b.timer) { b.timer->stop(st); b.timer->start(KT_MATCH, st); }
         if (b.sparse && b.lists && b.spu == 1 && !lp.ht && (lp.mode == 0 || lp.mode == 1)) {
             // sparse path: speculative table, parse with miss detection, then the two filtered fallback launches
-            GZPB_LAUNCH(k_smatch, b.nunits, kSparseThreads, match_smem, st, g, b.next4, b.prev3, b.mtab, lp.depth, lp.nice, lp.mode);
+            const uint32_t chunk = (b.sparse_chunk >= kSparseChunk && b.sparse_chunk <= 4096u) ? b.sparse_chunk : kSparseChunk;   // 512 x 128 covers a unit
+            GZPB_LAUNCH(k_smatch, b.nunits, kSparseThreads, match_smem, st, g, b.next4, b.prev3, b.mtab, lp.depth, lp.nice, lp.mode, chunk);
             DBG_SYNC("k_smatch");
             if (b.timer) { b.timer->stop(st); b.timer->start(KT_EMIT, st); }
             GZPB_LAUNCH(k_emit<true>, b.nunits, kEmitThreads, 0, st, g, b.unit_flags, b.mtab, b.mtab2, b.crc, b.tokens, b.out, b.out_len,

@@ -63,6 +63,7 @@ struct DeflateBatch {
     uint32_t spu, seg;        // sub-units per unit and new positions per sub-unit (gzpb_common.cuh: Geo)
     int check_kind;           // -1 none, 0 CRC-32, 1 Adler-32 (written to `crc`)
     int sparse;               // 1 = sparse match table (k_smatch) where the level and the unit geometry allow it
+    uint32_t sparse_chunk;    // positions per speculative chunk (0 = default)
 };
 
 void upload_deflate_constants();

@@ -63,6 +63,7 @@ struct gzpb_ctx {
     uint32_t dict_cap = 0;                         // 32 KiB for the dictionary formats, else 0
     uint32_t in_stride = 0, m_stride = 0, tok_stride = 0, out_stride = 0, spu = 1, seg = 0;
     int check_kind = -1;
+    uint32_t sparse_chunk = 0;                     // GZPB_SPARSE_CHUNK: positions per speculative chunk (tuning aid)
     bool sparse = false;                           // GZPB_SPARSE=1: k_smatch (speculative sparse match table) + filtered fallback
     bool match_v2 = false;                         // GZPB_MATCH_V2=1: k_group + k_match2 instead of k_link(hash4) + k_match
     uint32_t cpu = 1;                              // gather entries per unit (Snap: 64 KiB chunks per block)
@@ -301,6 +302,7 @@ extern "C" int gzpb_create(gzpb_ctx **out, int device, int format, int level, si
     c->device = device; c->format = format; c->level = level;
     c->max_block_bytes = max_block_bytes; c->max_units = max_blocks_in_flight;
     { const char *e = getenv("GZPB_SPARSE"); c->sparse = e && *e == '1' && !getenv("GZPB_USE_KCHAIN"); }
+    { const char *e = getenv("GZPB_SPARSE_CHUNK"); c->sparse_chunk = e ? (uint32_t)atoi(e) : 0; }
     { const char *e = getenv("GZPB_MATCH_V2"); c->match_v2 = e && *e == '1' && !getenv("GZPB_USE_KCHAIN"); }
     {
         const size_t U = dict + max_block_bytes;
@@ -420,7 +422,7 @@ static void fill_batch(gzpb_ctx *c, Lane &L, DeflateBatch &b, size_t n)
     b.nunits = (uint32_t)n; b.level = c->level; b.format = c->format;
     b.in = L.d_in; b.unit_len = L.d_len; b.unit_dict = L.d_dict; b.unit_flags = L.d_flags;
     b.in_stride = c->in_stride; b.m_stride = c->m_stride; b.tok_stride = c->tok_stride; b.out_stride = c->out_stride;
-    b.spu = c->spu; b.seg = c->seg; b.check_kind = c->check_kind; b.sparse = c->sparse ? 1 : 0;
+    b.spu = c->spu; b.seg = c->seg; b.check_kind = c->check_kind; b.sparse = c->sparse ? 1 : 0; b.sparse_chunk = c->sparse_chunk;
     b.next4 = L.d_next4; b.prev3 = L.d_prev3; b.clen = L.d_clen; b.order = L.d_order; b.mtab = L.d_mtab; b.mtab2 = L.d_mtab2; b.gidx = L.d_gidx; b.gocc = L.d_gocc; b.lists = L.d_lists; b.list_start = L.d_list_start; b.crc = L.d_crc; b.tokens = L.d_tokens;
     b.out = L.d_out; b.out_len = L.d_out_len; b.status = L.d_status; b.offsets = L.d_offsets;
     b.packed = nullptr; b.packed_cap = 0; b.base_ptr = nullptr; b.overflow = L.d_overflow;

@@ -35,12 +35,15 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     ref = None
     L.gzpb_debug_sparse_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_int]
-    for variant, env in (("split+link+match", None), ("split+link+smatch", "GZPB_SPARSE"), ("split+group+match2", "GZPB_MATCH_V2"),
-                         ("split+link+match", None), ("split+link+smatch", "GZPB_SPARSE")):
-        os.environ.pop("GZPB_MATCH_V2", None)
-        os.environ.pop("GZPB_SPARSE", None)
+    for variant, env, chunk in (("split+link+match", None, 0), ("split+link+smatch", "GZPB_SPARSE", 128), ("split+group+match2", "GZPB_MATCH_V2", 0),
+                                ("split+link+match", None, 0), ("split+link+smatch", "GZPB_SPARSE", 128), ("split+link+smatch", "GZPB_SPARSE", 256),
+                                ("split+link+smatch", "GZPB_SPARSE", 512)):
+        for k in ("GZPB_MATCH_V2", "GZPB_SPARSE", "GZPB_SPARSE_CHUNK"):
+            os.environ.pop(k, None)
         if env:
             os.environ[env] = "1"
+        if chunk:
+            os.environ["GZPB_SPARSE_CHUNK"] = str(chunk)
         ctx = gzp_b200.Context(gzp_b200.BGZF, level, device=0, max_block_bytes=BLOCK, max_blocks_in_flight=min(nblk, 3256))
         assert L.gzpb_ctx_variant(ctx._h).decode() == variant
         d_packed = torch.zeros((nblk * 73728,), dtype=torch.uint8, device=dev)
@@ -74,7 +77,7 @@ def main():
         L.gzpb_debug_sparse_stats(ctx._h, C.byref(su), C.byref(sm), 1)
         ctx.close()
         best = min(ms)
-        print(json.dumps({"variant": variant, "level": level, "blocks": nblk, "ms_best": best, "ms_all": ms,
+        print(json.dumps({"variant": variant + (" chunk %d" % chunk if chunk else ""), "level": level, "blocks": nblk, "ms_best": best, "ms_all": ms,
                           "GiB/s": nblk * BLOCK / (best / 1e3) / (1 << 30), "out_bytes": total, "sparse_units": su.value, "sparse_missed": sm.value,
                           "kernel_ms_per_batch": {k: v[0] / steps for k, v in kms.items()},
                           "kernel_launches_per_batch": {k: v[1] / steps for k, v in kms.items()}}), flush=True)

@@ -692,3 +692,11 @@ def test_emu_sparse_match_table_edges_and_fallback(monkeypatch):
     for fmt, level, bs in ((oracle.MGZIP, 6, 131072), (oracle.BGZF, 9, 0), (oracle.BGZF, 1, 0)):
         units, missed = _run_sparse(fmt, level, bs, TEXT[:140000])
         assert units == 0
+
+
+@pytest.mark.parametrize("chunk", ["256", "1000"])
+def test_emu_sparse_chunk_sizes(monkeypatch, chunk):
+    monkeypatch.setenv("GZPB_SPARSE", "1")
+    monkeypatch.setenv("GZPB_SPARSE_CHUNK", chunk)
+    units, missed = _run_sparse(oracle.BGZF, 6, 0, TEXT[:100000] + bytes(30000))
+    assert units == 2 and missed == 0
