@@ -304,6 +304,7 @@ extern "C" int gzpb_create(gzpb_ctx **out, int device, int format, int level, si
     { const char *e = getenv("GZPB_SPARSE"); c->sparse = e && *e == '1' && !getenv("GZPB_USE_KCHAIN"); }
     { const char *e = getenv("GZPB_SPARSE_CHUNK"); c->sparse_chunk = e ? (uint32_t)atoi(e) : 0; }
     { const char *e = getenv("GZPB_MATCH_V2"); c->match_v2 = e && *e == '1' && !getenv("GZPB_USE_KCHAIN"); }
+    if (c->sparse) c->match_v2 = false;            // the variants are alternatives: k_smatch walks k_link's chains, not k_group's arrays
     {
         const size_t U = dict + max_block_bytes;
         c->dict_cap = (uint32_t)dict;
