@@ -818,7 +818,7 @@ struct EmitShared {
     uint32_t scan[kEmitThreads / 32];
     uint32_t used[8];
     // control block written by thread 0
-    uint32_t blk_begin, blk_end, ntok, is_final, min_len;
+    uint32_t blk_begin, blk_end, ntok, is_final, min_len, tok0;
     uint32_t nused, nitems, nlit, noff, nexpl, btype;
     uint32_t cost_dyn, cost_static;
     uint32_t G;        // bit position in the payload
@@ -1056,6 +1056,8 @@ __device__ __forceinline__ void table_search(uint64_t e, uint32_t b, bool useB, 
 // unit) is flagged and redone by k_match + k_emit in a second, filtered pass.  Bit-identical either way.
 // =============================================================================
 constexpr int kSparseThreads = 512;
+constexpr uint32_t kTokEnd = 1u << 30;          // tokens mode: a parser iteration ends after this token
+constexpr uint32_t kSparseListWords = 2 * 204800; // per unit: speculative lists + gap lists, (chunk + 264) words per chunk
 constexpr uint32_t kSparseChunk = 128;          // default positions per chunk (GZPB_SPARSE_CHUNK overrides: 128..4096)
 
 // the body of k_match's phase 2 for one position: best match over `depth` nodes with the depth/2 snapshot
@@ -1116,7 +1118,8 @@ __device__ __forceinline__ uint64_t sparse_entry(const uint32_t *s_in, const uin
 
 __global__ void __launch_bounds__(kSparseThreads, 1)
 k_smatch(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, const uint16_t *__restrict__ prev3g,
-         uint64_t *__restrict__ mtab, int depth, int nice, int mode, uint32_t chunk)
+         uint64_t *__restrict__ mtab, int depth, int nice, int mode, uint32_t chunk,
+         uint32_t *__restrict__ tok_base, uint32_t *__restrict__ lists_g, uint16_t *__restrict__ idx_g, uint32_t *__restrict__ unit_ntok)
 {
     GZPB_DYN_SMEM(smem);
     uint32_t *s_in = (uint32_t *)smem;
@@ -1124,10 +1127,13 @@ k_smatch(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, con
     __shared__ __align__(8) uint64_t bar;
     __shared__ uint32_t s_iter[2048];            // iteration starts of the speculative parses, one bit per position
     __shared__ uint32_t s_end[kSparseThreads];   // where each chunk's last iteration ends
-    __shared__ uint32_t s_used[8], s_flag;
+    __shared__ uint32_t s_used[8], s_flag, s_over, s_wsum[kSparseThreads / 32];
     const uint32_t tid = threadIdx.x;
     const Sub sb = sub_geometry(g, blockIdx.x);  // spu == 1: the sub-unit is the unit
-    if (!sb.valid) return;
+    // tokens mode (GZPB_SPARSE=2): the chunk threads also record their tokens; after the stitch the tokens of the true
+    // parse are compacted, in order, into the unit's token array and k_emit<2> only replays the parser's events over them
+    const bool tokens = tok_base != nullptr;
+    if (!sb.valid) { if (tokens && tid == 0) unit_ntok[blockIdx.x] = 0; return; }
     const uint32_t n = sb.len, nb = sb.nb, ne = sb.ne;
     const uint8_t *in = g.in + (size_t)sb.u * g.in_stride + sb.h;
     unsigned long long *M = (unsigned long long *)(mtab + (size_t)sb.u * g.m_stride + sb.h);
@@ -1136,7 +1142,8 @@ k_smatch(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, con
     if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
     for (uint32_t i = tid; i < 2048; i += kSparseThreads) s_iter[i] = 0;
     if (tid < 8) s_used[tid] = 0;
-    for (uint32_t i = (nb & ~127u) + tid; i < n; i += kSparseThreads) M[i] = 0ull;     // no stale entries from the lane's previous batch
+    if (tid == 0) s_over = 0;
+    if (!tokens) for (uint32_t i = (nb & ~127u) + tid; i < n; i += kSparseThreads) M[i] = 0ull;     // no stale entries from the lane's previous batch
     __syncthreads();
     if (n >= 5) {
         if (tid == 0) {
@@ -1163,35 +1170,46 @@ k_smatch(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, con
     // trip — a fresh full-depth search at an iteration start, or the depth/2 look-ahead behind a pending match — so that
     // the lanes of a warp, each parsing its own chunk, meet in the same chain-walk loop.  Runs from iteration start q0
     // until an iteration ends at or beyond `stop`, or (rejoin) on an iteration start this chunk's speculation marked.
-    auto run = [&](uint32_t q0, uint32_t stop, bool rejoin) -> uint32_t {
+    const uint32_t lcap = chunk + 264;                            // tokens one chunk's parse can produce
+    uint32_t *spec_list = tokens ? lists_g + (size_t)blockIdx.x * kSparseListWords + (size_t)tid * lcap : nullptr;
+    uint32_t *gap_list = tokens ? spec_list + kSparseListWords / 2 : nullptr;
+    uint16_t *idx_at = tokens ? idx_g + (size_t)blockIdx.x * kMaxUnitBytes : nullptr;
+    const uint8_t *b8 = (const uint8_t *)s_in;
+    auto run = [&](uint32_t q0, uint32_t stop, bool rejoin, uint32_t *list, uint32_t &cnt) -> uint32_t {
         uint32_t q = q0, m = 0, cl = 0, co = 0;
         bool in_look = false;
+        auto emit = [&](uint32_t t) { if (list) { if (cnt < lcap) list[cnt] = t; cnt++; } };
         for (;;) {
             if (!in_look) {
                 if (q >= stop || (rejoin && ((s_iter[q >> 5] >> (q & 31)) & 1u))) return q;
-                if (!rejoin) atomicOr(&s_iter[q >> 5], 1u << (q & 31));
+                if (!rejoin) { atomicOr(&s_iter[q >> 5], 1u << (q & 31)); if (list) idx_at[q] = (uint16_t)cnt; }
             }
             const uint32_t pos = in_look ? m + 1 : q;
             const uint32_t maxlen = pos < n ? min((uint32_t)kMaxMatch, n - pos) : 0u;
             uint64_t e = 0;
             if (!in_look || maxlen >= 5) {
                 e = sparse_entry(s_in, s_next, p3, n, pos, (uint32_t)depth, (uint32_t)nice, lazy, !in_look);
-                atomicOr(&M[pos], (unsigned long long)e);
+                if (!tokens) atomicOr(&M[pos], (unsigned long long)e);
             }
             if (!in_look) {
                 table_search(e, min_len - 1, false, maxlen, cl, co);
-                if (mode == 0) { q = (cl >= min_len && (cl > 3 || co <= 4096)) ? q + cl : q + 1; continue; }
-                if (cl < min_len || (cl == 3 && co > 8192)) { q = q + 1; continue; }
+                if (mode == 0) {
+                    if (cl >= min_len && (cl > 3 || co <= 4096)) { emit(kTokEnd | 0x80000000u | (cl << 16) | co); q += cl; }
+                    else { emit(kTokEnd | b8[q]); q += 1; }
+                    continue;
+                }
+                if (cl < min_len || (cl == 3 && co > 8192)) { emit(kTokEnd | b8[q]); q = q + 1; continue; }
                 m = q;
-                if (cl >= min((uint32_t)nice, maxlen)) { q = m + cl; continue; }
+                if (cl >= min((uint32_t)nice, maxlen)) { emit(kTokEnd | 0x80000000u | (cl << 16) | co); q = m + cl; continue; }
                 in_look = true;
             } else {
                 uint32_t nl, no;
                 table_search(e, cl - 1, true, maxlen, nl, no);
                 if (nl >= cl && 4 * (int)(nl - cl) + ((int)bsr32(co) - (int)bsr32(no)) > 2) {
-                    m++; cl = nl; co = no;                         // literal; the look-ahead match becomes the pending one
-                    if (cl >= min((uint32_t)nice, maxlen)) { q = m + cl; in_look = false; }
-                } else { q = m + cl; in_look = false; }
+                    emit(b8[m]);                                   // literal; the look-ahead match becomes the pending one
+                    m++; cl = nl; co = no;
+                    if (cl >= min((uint32_t)nice, maxlen)) { emit(kTokEnd | 0x80000000u | (cl << 16) | co); q = m + cl; in_look = false; }
+                } else { emit(kTokEnd | 0x80000000u | (cl << 16) | co); q = m + cl; in_look = false; }
             }
         }
     };
@@ -1199,8 +1217,9 @@ k_smatch(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, con
     const uint32_t nchunks = (ne - nb + chunk - 1) / chunk;       // <= kSparseThreads (the launcher checks)
     const uint32_t s0 = nb + tid * chunk, s1 = min(ne, s0 + chunk);
     uint32_t spec_end = 0;
+    uint32_t cnt_spec = 0, cnt_gap = 0, gap_q = 0;
     if (tid < nchunks) {
-        spec_end = run(s0, s1, false);
+        spec_end = run(s0, s1, false, spec_list, cnt_spec);
         s_end[tid] = spec_end;
     }
     __syncthreads();
@@ -1213,8 +1232,9 @@ k_smatch(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, con
             uint32_t new_end;
             if (entry >= s1) new_end = entry;                      // the chunk lies inside a match of an earlier one
             else {
-                const uint32_t q = run(entry, s1, true);
-                new_end = q < s1 ? spec_end : q;
+                cnt_gap = 0;
+                gap_q = run(entry, s1, true, gap_list, cnt_gap);
+                new_end = gap_q < s1 ? spec_end : gap_q;
             }
             done_entry = entry;
             if (new_end != s_end[tid]) { s_end[tid] = new_end; s_flag = 1; }
@@ -1225,14 +1245,39 @@ k_smatch(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, con
         __syncthreads();
         if (!again) break;
     }
+    if (!tokens) return;
+    // ---- (C) compact the tokens of the true parse: [gap tokens | this chunk's speculation from the re-join on] ----
+    uint32_t ngap = 0, from = 0, nspec = 0;
+    if (tid < nchunks) {
+        if (tid == 0) nspec = cnt_spec;
+        else if (entry < s1) {
+            ngap = cnt_gap;
+            if (gap_q < s1) { from = idx_at[gap_q]; nspec = cnt_spec - from; }
+        }
+        if (cnt_spec > lcap || ngap > lcap) s_over = 1;
+    }
+    const uint32_t mine = ngap + nspec, lane = tid & 31, warp = tid >> 5;
+    uint32_t incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= (uint32_t)d) incl += v; }
+    if (lane == 31) s_wsum[warp] = incl;
+    __syncthreads();
+    uint32_t base = 0, total = 0;
+    for (int w = 0; w < kSparseThreads / 32; w++) { const uint32_t v = s_wsum[w]; if (w < (int)warp) base += v; total += v; }
+    uint32_t *out = tok_base + (size_t)sb.u * g.tok_stride + (base + incl - mine);
+    if (!s_over && total <= g.tok_stride) {
+        for (uint32_t k = 0; k < ngap; k++) out[k] = gap_list[k];
+        for (uint32_t k = 0; k < nspec; k++) out[ngap + k] = spec_list[from + k];
+    }
+    if (tid == 0) unit_ntok[blockIdx.x] = (s_over || total > g.tok_stride) ? 0xFFFFFFFFu : total;
 }
 
-template <bool kSparse>
+template <int kSparse>
 __global__ void __launch_bounds__(kEmitThreads)
 k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
        const uint64_t *__restrict__ mtab, const uint32_t *__restrict__ mtab2, const uint32_t *__restrict__ crc_in, uint32_t *__restrict__ tok_base,
        uint8_t *__restrict__ out_base, uint32_t *__restrict__ out_len, int32_t *__restrict__ out_status,
-       int mode, int depth, int nice, int level, int format, int pass2)
+       int mode, int depth, int nice, int level, int format, int pass2, const uint32_t *__restrict__ unit_ntok)
 {
     __shared__ EmitShared S;
     const uint32_t u = blockIdx.x, tid = threadIdx.x;
@@ -1296,6 +1341,7 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
     } else if (dl > 0) {
         uint32_t p = dict;           // parser position (warp 0 is authoritative)
         uint32_t next_recalc = 0, min_len = 3;
+        uint32_t tcur = 0, assumed_min_len = 0;   // tokens mode (kSparse == 2): next token of k_smatch's list, the min_len it parsed with
         while (true) {
             // ---------------- block start (all threads) ----------------
             if (tid == 0) S.blk_begin = p;
@@ -1334,6 +1380,106 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
                 next_recalc = bb + min(n - bb, 10000u);
                 uint32_t ntok = 0, nmatch = 0, num_obs = 0, num_new_obs = 0, in_h = 0;
                 bool end_block = false;
+                if (kSparse == 2) {
+                    // ---- replay: the tokens of the true parse are already in tok[] (k_smatch, in order, iteration ends
+                    // flagged); what is left of the parser is its events — min_len re-calculation, block-split checks,
+                    // sequence-store limit — evaluated 32 tokens at a time exactly where the sequential parser would.
+                    const uint32_t total = unit_ntok[u];
+                    if (assumed_min_len == 0) assumed_min_len = min_len;
+                    bool miss = (total == 0xFFFFFFFFu) || (min_len != assumed_min_len);   // k_smatch parsed the whole unit with one min_len
+                    if (lane == 0) S.tok0 = tcur;
+                    do {
+                        const uint32_t ti = tcur + lane;
+                        const bool valid = !miss && ti < total;
+                        const uint32_t t = valid ? tok[ti] : 0u;
+                        const bool isM = (t >> 31) & 1u, ends_iter = (t >> 30) & 1u;
+                        const uint32_t mlen = isM ? (t >> 16) & 0x1FF : 1u, moff = t & 0xFFFF, lit = t & 0xFF;
+                        const uint32_t len = valid ? mlen : 0u;
+                        uint32_t pincl = len;
+#pragma unroll
+                        for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, pincl, d); if (lane >= (uint32_t)d) pincl += v; }
+                        const uint32_t q = p + pincl - len, e_l = p + pincl;
+                        const uint32_t prev_ends = __shfl_up_sync(0xFFFFFFFFu, (uint32_t)ends_iter, 1);
+                        const bool starts_iter = lane == 0 ? (in_h == 0) : (prev_ends != 0);
+                        const uint32_t vis = __ballot_sync(0xFFFFFFFFu, valid);
+                        if (vis == 0) { miss = true; break; }                 // the list ended before the data did
+                        const uint32_t incl = lane + 1;                       // tokens up to and including mine
+                        uint32_t commit_mask = vis;
+                        uint32_t next_p = __shfl_sync(0xFFFFFFFFu, e_l, 31 - __clz(vis));
+                        uint32_t next_h = __shfl_sync(0xFFFFFFFFu, (uint32_t)!ends_iter, 31 - __clz(vis));
+                        int event = 0;
+                        const uint32_t mmask = __ballot_sync(0xFFFFFFFFu, valid && isM);
+                        const bool may_check = (num_new_obs + 32 >= (uint32_t)kObsPerCheck) && (next_p - bb >= (uint32_t)kMinBlockLength) && (n - p > (uint32_t)kMinBlockLength);
+                        const bool may_recalc = (mode != 0) && (next_p > next_recalc);
+                        const bool may_seq = nmatch + 32 >= seq_limit;
+                        if (may_check || may_recalc || may_seq) {
+                            const uint32_t rmask = may_recalc ? __ballot_sync(0xFFFFFFFFu, valid && starts_iter && q >= next_recalc) : 0u;
+                            const uint32_t cmask = __ballot_sync(0xFFFFFFFFu, valid && ends_iter && (num_new_obs + incl >= (uint32_t)kObsPerCheck) &&
+                                                                             (e_l - bb >= (uint32_t)kMinBlockLength) && (n - e_l >= (uint32_t)kMinBlockLength));
+                            const uint32_t mincl = __popc(mmask & (lane == 31 ? 0xFFFFFFFFu : ((2u << lane) - 1)));
+                            const uint32_t smask = __ballot_sync(0xFFFFFFFFu, valid && ends_iter && (nmatch + mincl >= seq_limit));
+                            const int Lr = rmask ? __ffs(rmask) - 1 : 64, Lc = cmask ? __ffs(cmask) - 1 : 64, Ls = smask ? __ffs(smask) - 1 : 64;
+                            if (Lr <= Lc && Lr <= Ls && Lr < 64) { event = 1; commit_mask = vis & ((1u << Lr) - 1); next_p = __shfl_sync(0xFFFFFFFFu, q, Lr); next_h = 0; }
+                            else if (Ls <= Lc && Ls < 64) { event = 3; commit_mask = vis & (Ls == 31 ? 0xFFFFFFFFu : ((2u << Ls) - 1)); next_p = __shfl_sync(0xFFFFFFFFu, e_l, Ls); next_h = 0; }
+                            else if (Lc < 64) { event = 2; commit_mask = vis & (Lc == 31 ? 0xFFFFFFFFu : ((2u << Lc) - 1)); next_p = __shfl_sync(0xFFFFFFFFu, e_l, Lc); next_h = 0; }
+                        }
+                        if ((commit_mask >> lane) & 1u) {
+                            const uint32_t lsym = isM ? kFirstLenSym + len_slot_only(mlen) : lit;
+                            const uint32_t ocls = isM ? 8 + (mlen >= 9) : (((lit >> 5) & 6) | (lit & 1));
+                            atomicAdd(&S.fl[lsym], 1u);
+                            atomicAdd(&S.new_obs[ocls], 1u);
+                            if (isM) atomicAdd(&S.fo[off_slot_only(moff)], 1u);
+                            tok[ti] = isM ? (0x80000000u | (mlen << 16) | moff) : lit;      // the flag bit goes
+                        }
+                        {
+                            const uint32_t added = __popc(commit_mask);
+                            ntok += added; num_new_obs += added; tcur += added;
+                            nmatch += __popc(commit_mask & mmask);
+                        }
+                        in_h = next_h;
+                        p = next_p;
+                        __syncwarp();
+                        if (event == 1) {
+                            uint32_t tot = 0;
+                            for (int i = 0; i < 8; i++) tot += S.fl[lane * 8 + i];
+                            for (int o = 16; o; o >>= 1) tot += __shfl_xor_sync(0xFFFFFFFFu, tot, o);
+                            uint32_t cutoff = tot >> 10, nu = 0;
+                            for (int i = 0; i < 8; i++) nu += (S.fl[lane * 8 + i] > cutoff);
+                            for (int o = 16; o; o >>= 1) nu += __shfl_xor_sync(0xFFFFFFFFu, nu, o);
+                            min_len = choose_min_match_len(nu, depth);
+                            next_recalc += min(n - next_recalc, p - bb);
+                            if (min_len != assumed_min_len) miss = true;        // the tokens behind this point were parsed with another min_len
+                        } else if (event == 2) {
+                            uint32_t block_length = p - bb;
+                            if (num_obs > 0) {
+                                uint32_t d = 0;
+                                if (lane < 10) {
+                                    uint32_t expected = S.obs[lane] * num_new_obs, actual = S.new_obs[lane] * num_obs;
+                                    d = actual > expected ? actual - expected : expected - actual;
+                                }
+                                for (int o = 16; o; o >>= 1) d += __shfl_xor_sync(0xFFFFFFFFu, d, o);
+                                uint32_t num_items = num_obs + num_new_obs;
+                                uint32_t cutoff = num_new_obs * 200 / 512 * num_obs;
+                                if (block_length < 10000 && num_items < 8192)
+                                    cutoff += (uint32_t)((uint64_t)cutoff * (8192 - num_items) / 8192);
+                                if (d + (block_length / 4096) * num_obs >= cutoff) end_block = true;
+                            }
+                            if (!end_block) {
+                                if (lane < 10) { S.obs[lane] += S.new_obs[lane]; S.new_obs[lane] = 0; }
+                                num_obs += num_new_obs; num_new_obs = 0;
+                            }
+                            __syncwarp();
+                        } else if (event == 3) {
+                            end_block = true;
+                        }
+                    } while (p < max_block_end && !end_block && !miss);
+                    if (miss) {
+                        // flag the unit (redone from the full table by the second pass) and close this block at the end of
+                        // the data so that the rest of the kernel stays well-formed
+                        if (lane == 0) S.status = kStatusMiss;
+                        p = n;
+                    }
+                } else
                 if (mode == 2) {
                     // lazy2 (levels 8-9): the reference's loop restated one iteration at a time; every lane
                     // runs the same (uniform) control flow, lane 0 commits.  These levels are bound by the
@@ -1455,8 +1601,8 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
                         const uint32_t nice_q = min((uint32_t)nice, maxlen);
                         uint32_t cl, co;
                         table_search(e0, min_len - 1, false, maxlen, cl, co);
-                        const bool e1_missing = kSparse && maxlen1 >= 5 && !(e1 & kValidB);
-                        if (kSparse) { badF = !(e0 & kValidA); badH = !(e0 & kValidB); }
+                        const bool e1_missing = kSparse == 1 && maxlen1 >= 5 && !(e1 & kValidB);
+                        if (kSparse == 1) { badF = !(e0 & kValidA); badH = !(e0 & kValidB); }
                         if (mode == 0) {
                             if (cl >= min_len && (cl > 3 || co <= 4096)) { lenF = cl; offF = co; wF = cl | (1u << 10); }
                         } else {
@@ -1523,7 +1669,7 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
                         else if (Ls <= Lc && Ls < 64) { event = 3; commit_mask = vis & (Ls == 31 ? 0xFFFFFFFFu : ((2u << Ls) - 1)); next_p = __shfl_sync(0xFFFFFFFFu, e_l, Ls); next_h = 0; }
                         else if (Lc < 64) { event = 2; commit_mask = vis & (Lc == 31 ? 0xFFFFFFFFu : ((2u << Lc) - 1)); next_p = __shfl_sync(0xFFFFFFFFu, e_l, Lc); next_h = 0; }
                     }
-                    if (kSparse) {
+                    if (kSparse == 1) {
                         const uint32_t missed = __ballot_sync(0xFFFFFFFFu, ((commit_mask >> lane) & 1u) && (asH ? badH : badF));
                         if (missed && lane == 0) S.status = kStatusMiss;
                     }
@@ -1745,7 +1891,7 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
                         uint32_t ti = t0 + tid * kTokPerThread + k;
                         uint64_t c = 0; uint32_t l = 0;
                         if (ti < ntok) {
-                            uint32_t t = tok[ti];
+                            uint32_t t = tok[(kSparse == 2 ? S.tok0 : 0u) + ti];
                             if (!(t & 0x80000000u)) {
                                 c = dynamic ? S.lcw[t] : c_static_litlen_cw[t];
                                 l = dynamic ? ll[t] : c_static_litlen_len[t];
@@ -1838,7 +1984,7 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
             uint32_t avail = dl + max(128u, (uint32_t)((double)dl * 0.1));
             if (nbytes > avail) st = -4;
         }
-        if (kSparse) { atomicAdd(&g_sparse_stats[0], 1ull); if (S.status == kStatusMiss) { atomicAdd(&g_sparse_stats[1], 1ull); st = kStatusMiss; } }
+        if (kSparse != 0) { atomicAdd(&g_sparse_stats[0], 1ull); if (S.status == kStatusMiss) { atomicAdd(&g_sparse_stats[1], 1ull); st = kStatusMiss; } }
         out_len[u * 2] = total;
         out_len[u * 2 + 1] = hdr_off;
         out_status[u] = st;
@@ -2092,18 +2238,24 @@ cudaError_t launch_deflate_pipeline(const DeflateBatch &b, cudaStream_t st)
         if (b.sparse && b.lists && b.spu == 1 && !lp.ht && (lp.mode == 0 || lp.mode == 1)) {
             // sparse path: speculative table, parse with miss detection, then the two filtered fallback launches
             const uint32_t chunk = (b.sparse_chunk >= kSparseChunk && b.sparse_chunk <= 4096u) ? b.sparse_chunk : kSparseChunk;   // 512 x 128 covers a unit
-            GZPB_LAUNCH(k_smatch, b.nunits, kSparseThreads, match_smem, st, g, b.next4, b.prev3, b.mtab, lp.depth, lp.nice, lp.mode, chunk);
+            const bool tokens = b.sparse == 2 && b.slists && b.sidx && b.sntok;
+            GZPB_LAUNCH(k_smatch, b.nunits, kSparseThreads, match_smem, st, g, b.next4, b.prev3, b.mtab, lp.depth, lp.nice, lp.mode, chunk,
+                        tokens ? b.tokens : (uint32_t *)nullptr, b.slists, b.sidx, b.sntok);
             DBG_SYNC("k_smatch");
             if (b.timer) { b.timer->stop(st); b.timer->start(KT_EMIT, st); }
-            GZPB_LAUNCH(k_emit<true>, b.nunits, kEmitThreads, 0, st, g, b.unit_flags, b.mtab, b.mtab2, b.crc, b.tokens, b.out, b.out_len,
-                        b.status, lp.mode, lp.depth, lp.nice, b.level, b.format, 0);
+            if (tokens)
+                GZPB_LAUNCH(k_emit<2>, b.nunits, kEmitThreads, 0, st, g, b.unit_flags, b.mtab, b.mtab2, b.crc, b.tokens, b.out, b.out_len,
+                            b.status, lp.mode, lp.depth, lp.nice, b.level, b.format, 0, b.sntok);
+            else
+                GZPB_LAUNCH(k_emit<1>, b.nunits, kEmitThreads, 0, st, g, b.unit_flags, b.mtab, b.mtab2, b.crc, b.tokens, b.out, b.out_len,
+                            b.status, lp.mode, lp.depth, lp.nice, b.level, b.format, 0, (const uint32_t *)nullptr);
             DBG_SYNC("k_emit(sparse)");
             if (b.timer) { b.timer->stop(st); b.timer->start(KT_MATCH, st); }
             GZPB_LAUNCH(k_match, b.nunits * b.spu, kMatchThreads, match_smem, st, g, b.next4, b.prev3, b.mtab, b.mtab2, b.clen, b.order, lp.depth, lp.nice, lp.mode, 1, lp.ht, b.status);
             DBG_SYNC("k_match(missed)");
             if (b.timer) { b.timer->stop(st); b.timer->start(KT_EMIT, st); }
-            GZPB_LAUNCH(k_emit<false>, b.nunits, kEmitThreads, 0, st, g, b.unit_flags, b.mtab, b.mtab2, b.crc, b.tokens, b.out, b.out_len,
-                        b.status, lp.mode, lp.depth, lp.nice, b.level, b.format, 1);
+            GZPB_LAUNCH(k_emit<0>, b.nunits, kEmitThreads, 0, st, g, b.unit_flags, b.mtab, b.mtab2, b.crc, b.tokens, b.out, b.out_len,
+                        b.status, lp.mode, lp.depth, lp.nice, b.level, b.format, 1, (const uint32_t *)nullptr);
             DBG_SYNC("k_emit(missed)");
             if (b.timer) b.timer->stop(st);
             return cudaGetLastError();
@@ -2116,8 +2268,8 @@ cudaError_t launch_deflate_pipeline(const DeflateBatch &b, cudaStream_t st)
         if (b.timer) b.timer->stop(st);
     }
     if (b.timer) b.timer->start(KT_EMIT, st);
-    GZPB_LAUNCH(k_emit<false>, b.nunits, kEmitThreads, 0, st, g, b.unit_flags, b.mtab, b.mtab2, b.crc, b.tokens, b.out, b.out_len,
-                                             b.status, lp.mode, lp.depth, lp.nice, b.level, b.format, 0);
+    GZPB_LAUNCH(k_emit<0>, b.nunits, kEmitThreads, 0, st, g, b.unit_flags, b.mtab, b.mtab2, b.crc, b.tokens, b.out, b.out_len,
+                                             b.status, lp.mode, lp.depth, lp.nice, b.level, b.format, 0, (const uint32_t *)nullptr);
     DBG_SYNC("k_emit");
     if (b.timer) b.timer->stop(st);
     return cudaGetLastError();

@@ -62,10 +62,12 @@ struct DeflateBatch {
     uint32_t in_stride, m_stride, tok_stride, out_stride;   // per-unit strides (bytes / entries / tokens / bytes)
     uint32_t spu, seg;        // sub-units per unit and new positions per sub-unit (gzpb_common.cuh: Geo)
     int check_kind;           // -1 none, 0 CRC-32, 1 Adler-32 (written to `crc`)
-    int sparse;               // 1 = sparse match table (k_smatch) where the level and the unit geometry allow it
+    int sparse;               // 1 = sparse match table (k_smatch) where the level and the unit geometry allow it, 2 = k_smatch also hands over the tokens
+    uint32_t *slists; uint16_t *sidx; uint32_t *sntok;   // sparse == 2: per-chunk token lists (kSparseListWords per unit), iteration index per position, tokens per unit
     uint32_t sparse_chunk;    // positions per speculative chunk (0 = default)
 };
 
+constexpr size_t kSparseListWordsPerUnit = 2 * 204800;
 void upload_deflate_constants();
 void read_phase_counters(unsigned long long *out, bool reset);
 void read_sparse_stats(unsigned long long *out2, bool reset);

@@ -35,13 +35,14 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     ref = None
     L.gzpb_debug_sparse_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_int]
-    for variant, env, chunk in (("split+link+match", None, 0), ("split+link+smatch", "GZPB_SPARSE", 128), ("split+group+match2", "GZPB_MATCH_V2", 0),
-                                ("split+link+match", None, 0), ("split+link+smatch", "GZPB_SPARSE", 128), ("split+link+smatch", "GZPB_SPARSE", 256),
-                                ("split+link+smatch", "GZPB_SPARSE", 512)):
+    for variant, env, chunk in (("split+link+match", None, 0), ("split+link+smatch", "GZPB_SPARSE=1", 128), ("split+link+smatch+replay", "GZPB_SPARSE=2", 128),
+                                ("split+group+match2", "GZPB_MATCH_V2=1", 0), ("split+link+match", None, 0), ("split+link+smatch", "GZPB_SPARSE=1", 128),
+                                ("split+link+smatch+replay", "GZPB_SPARSE=2", 128), ("split+link+smatch+replay", "GZPB_SPARSE=2", 256),
+                                ("split+link+smatch+replay", "GZPB_SPARSE=2", 512)):
         for k in ("GZPB_MATCH_V2", "GZPB_SPARSE", "GZPB_SPARSE_CHUNK"):
             os.environ.pop(k, None)
         if env:
-            os.environ[env] = "1"
+            os.environ[env.split("=")[0]] = env.split("=")[1]
         if chunk:
             os.environ["GZPB_SPARSE_CHUNK"] = str(chunk)
         ctx = gzp_b200.Context(gzp_b200.BGZF, level, device=0, max_block_bytes=BLOCK, max_blocks_in_flight=min(nblk, 3256))

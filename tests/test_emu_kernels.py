@@ -647,7 +647,7 @@ def _sparse_stats(ctx):
 def _run_sparse(fmt, level, bs, data):
     ctx = emu.EmuContext(fmt, level, max_block_bytes=bs)
     try:
-        assert ctx.L.gzpb_ctx_variant(ctx.h) == b"split+link+smatch"
+        assert ctx.L.gzpb_ctx_variant(ctx.h) in (b"split+link+smatch", b"split+link+smatch+replay")
         got = ctx.encode_stream(data, bs)
         units, missed = _sparse_stats(ctx)
     finally:
@@ -698,5 +698,36 @@ def test_emu_sparse_match_table_edges_and_fallback(monkeypatch):
 def test_emu_sparse_chunk_sizes(monkeypatch, chunk):
     monkeypatch.setenv("GZPB_SPARSE", "1")
     monkeypatch.setenv("GZPB_SPARSE_CHUNK", chunk)
+    units, missed = _run_sparse(oracle.BGZF, 6, 0, TEXT[:100000] + bytes(30000))
+    assert units == 2 and missed == 0
+
+
+@pytest.mark.parametrize("level", [2, 5, 6, 7])
+def test_emu_sparse_tokens_and_replay_levels(monkeypatch, level):
+    """GZPB_SPARSE=2: k_smatch also hands over the stitched, compacted tokens of the true parse and k_emit<2> only
+    replays the parser's events over them (min_len re-calculation, block-split checks, sequence-store limit)."""
+    monkeypatch.setenv("GZPB_SPARSE", "2")
+    units, missed = _run_sparse(oracle.BGZF, level, 0, TEXT[:140000])
+    assert units == 3 and missed == 0
+
+
+def test_emu_sparse_tokens_and_replay_edges_and_fallback(monkeypatch):
+    monkeypatch.setenv("GZPB_SPARSE", "2")
+    rnd = random.Random(77)
+    rand = bytes(rnd.getrandbits(8) for _ in range(30000))
+    few = bytes(rnd.choice(b"ACGT") for _ in range(40000))
+    clean = [b"", b"x", TEXT[:33], TEXT[:700], bytes(70000), rand, b"abcdefghij" * 6000, TEXT[:4999], TEXT[:65280],
+             synth.low_entropy(65280), synth.fastq(65000), (b"\x00" * 300 + b"\xff" * 5 + TEXT[:50]) * 150]
+    for d in clean:
+        units, missed = _run_sparse(oracle.BGZF, 6, 0, d)
+        assert missed == 0, len(d)
+    for d in ((few + TEXT[:60000])[:65280], (TEXT[:20000] + rand[:20000] + few)[:65280]):
+        units, missed = _run_sparse(oracle.BGZF, 6, 0, d)
+        assert (units, missed) == (1, 1)
+    units, missed = _run_sparse(oracle.BGZF, 4, 0, TEXT[:65280] + (few + TEXT[:60000])[:65280] + TEXT[:30000])
+    assert units == 3 and missed == 1
+    units, missed = _run_sparse(oracle.GZIP, 6, 32768, TEXT[:150000])               # dictionary in front of the unit
+    assert units >= 4 and missed == 0
+    monkeypatch.setenv("GZPB_SPARSE_CHUNK", "512")
     units, missed = _run_sparse(oracle.BGZF, 6, 0, TEXT[:100000] + bytes(30000))
     assert units == 2 and missed == 0

@@ -18,11 +18,11 @@ from gzp_b200 import BGZF, GZIP, _lib, synth
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(180)]
 
 
-def _encode(env, monkeypatch, fmt, level, bs, data, want_variant):
+def _encode(env, monkeypatch, fmt, level, bs, data, want_variant, value="1"):
     for k in ("GZPB_MATCH_V2", "GZPB_SPARSE"):
         monkeypatch.delenv(k, raising=False)
     if env:
-        monkeypatch.setenv(env, "1")
+        monkeypatch.setenv(env, value)
     L = _lib.load()
     ctx = gzp_b200.Context(fmt, level, max_block_bytes=bs, max_blocks_in_flight=64)
     try:
@@ -65,3 +65,21 @@ def test_sparse_match_table_is_bit_identical_on_gpu(monkeypatch, text_corpus):
     data = text_corpus[:500000]
     got, (units, missed) = _encode("GZPB_SPARSE", monkeypatch, GZIP, 6, 32768, data, "split+link+smatch")
     assert got == oracle.compress_stream(GZIP, 6, 32768, [data]) and missed == 0
+
+
+def test_sparse_tokens_and_replay_is_bit_identical_on_gpu(monkeypatch, text_corpus):
+    """GZPB_SPARSE=2: k_smatch hands the stitched tokens of the true parse to k_emit<2>, which only replays the events."""
+    rnd = random.Random(77)
+    few = bytes(rnd.choice(b"ACGT") for _ in range(40000))
+    mixed = (few + text_corpus[:60000])[:65280]
+    for level in (2, 5, 6, 7):
+        data = text_corpus[:1_000_000]
+        got, (units, missed) = _encode("GZPB_SPARSE", monkeypatch, BGZF, level, 65280, data, "split+link+smatch+replay", "2")
+        assert got == oracle.compress_stream(BGZF, level, 65280, [data]), level
+        assert units == 16 and missed == 0, (level, units, missed)
+    for data, want_missed in ((bytes(200000), 0), (synth.low_entropy(300000), None), (synth.fastq(200000), None), (b"", 0),
+                              (text_corpus[:65280] + mixed + text_corpus[:30000], 1)):
+        got, (units, missed) = _encode("GZPB_SPARSE", monkeypatch, BGZF, 6, 65280, data, "split+link+smatch+replay", "2")
+        assert got == oracle.compress_stream(BGZF, 6, 65280, [data]), len(data)
+        if want_missed is not None:
+            assert missed == want_missed, (len(data), units, missed)
