@@ -57,13 +57,13 @@ def main():
         for _ in range(3):
             step()
         torch.cuda.synchronize()
-        assert int(d_status.abs().max().item()) == 0
+        status_ok = int(d_status.abs().max().item()) == 0
         total = int(d_off[nblk].item())
         out = d_packed[:total].clone()
         if ref is None:
+            assert status_ok
             ref = out
-        else:
-            assert torch.equal(ref, out), "variants disagree"
+        identical = bool(status_ok and out.numel() == ref.numel() and torch.equal(ref, out))    # recorded, not fatal: measure the rest too
         ctx.set_profiling(True)
         ms = []
         for _ in range(steps):
@@ -79,7 +79,7 @@ def main():
         ctx.close()
         best = min(ms)
         print(json.dumps({"variant": variant + (" chunk %d" % chunk if chunk else ""), "level": level, "blocks": nblk, "ms_best": best, "ms_all": ms,
-                          "GiB/s": nblk * BLOCK / (best / 1e3) / (1 << 30), "out_bytes": total, "sparse_units": su.value, "sparse_missed": sm.value,
+                          "GiB/s": nblk * BLOCK / (best / 1e3) / (1 << 30), "out_bytes": total, "identical_to_default": identical, "sparse_units": su.value, "sparse_missed": sm.value,
                           "kernel_ms_per_batch": {k: v[0] / steps for k, v in kms.items()},
                           "kernel_launches_per_batch": {k: v[1] / steps for k, v in kms.items()}}), flush=True)
 
