@@ -731,3 +731,38 @@ def test_emu_sparse_tokens_and_replay_edges_and_fallback(monkeypatch):
     monkeypatch.setenv("GZPB_SPARSE_CHUNK", "512")
     units, missed = _run_sparse(oracle.BGZF, 6, 0, TEXT[:100000] + bytes(30000))
     assert units == 2 and missed == 0
+
+
+def test_emu_sparse_fuzz(monkeypatch):
+    """Random formats / levels / block sizes / chunk sizes / data kinds through the tokens + replay path (and its fallbacks)."""
+    monkeypatch.setenv("GZPB_SPARSE", "2")
+    rnd = random.Random(2025)
+
+    def gen(n):
+        k = rnd.randrange(5)
+        if k == 0:
+            return bytes(rnd.randrange(255) for _ in range(n))
+        if k == 1:
+            o = rnd.randrange(0, len(TEXT) - min(n, len(TEXT) - 1))
+            return (TEXT[o:] + TEXT)[:n]
+        if k == 2:
+            return ((bytes([rnd.randrange(256)]) * rnd.randrange(1, 700) + bytes(rnd.randrange(4) for _ in range(rnd.randrange(1, 50)))) * (n // 20 + 1))[:n]
+        if k == 3:
+            return synth.low_entropy(n, seed=rnd.randrange(1 << 30))
+        out = bytearray()
+        while len(out) < n:
+            out += gen(rnd.randrange(1, 4000))
+        return bytes(out[:n])
+
+    for _ in range(8):
+        fmt = rnd.choice([oracle.BGZF, oracle.BGZF, oracle.GZIP, oracle.ZLIB, oracle.RAWDEFLATE])
+        level = rnd.choice([2, 4, 5, 6, 7])
+        bs = rnd.randrange(32768, 65280) if fmt == oracle.BGZF else rnd.randrange(32768, 80000)
+        d = gen(rnd.randrange(0, 150000))
+        monkeypatch.setenv("GZPB_SPARSE_CHUNK", str(rnd.choice([128, 200, 256, 512])))
+        ctx = emu.EmuContext(fmt, level, max_block_bytes=bs, max_blocks_in_flight=rnd.choice([1, 2, 5]))
+        try:
+            got = ctx.encode_stream(d, bs)
+        finally:
+            ctx.close()
+        assert got == oracle.compress_stream(fmt, level, bs, [d]), (fmt, level, bs, len(d))
