@@ -23,6 +23,7 @@ namespace gzpb {
 
 __constant__ uint32_t c_crc_tab[4][256];      // slicing-by-4, reflected 0xEDB88320
 __constant__ uint32_t c_xpow512[1024];        // x^(8*512*j) mod P
+__constant__ uint32_t c_xpow512k[16];         // x^(8*512*1024*t) mod P: units longer than 512 KiB (up to 4 MiB + dictionary)
 __constant__ uint16_t c_static_litlen_cw[288];
 __constant__ uint8_t c_static_litlen_len[288];
 __constant__ uint8_t c_min_lens[80];
@@ -45,6 +46,9 @@ void upload_deflate_constants()
     static uint32_t xp[1024];
     for (int j = 0; j < 1024; j++) xp[j] = gf2_xpow8((uint64_t)512 * j, kCrcPoly);
     cudaMemcpyToSymbol(c_xpow512, xp, sizeof xp);
+    static uint32_t xpk[16];
+    for (int t = 0; t < 16; t++) xpk[t] = gf2_xpow8((uint64_t)512 * 1024 * t, kCrcPoly);
+    cudaMemcpyToSymbol(c_xpow512k, xpk, sizeof xpk);
     uint16_t cw[288]; uint8_t ln[288];
     for (int s = 0; s < 288; s++) {
         uint32_t code; int len;
@@ -1129,35 +1133,46 @@ k_smatch(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, con
     __shared__ uint32_t s_end[kSparseThreads];   // where each chunk's last iteration ends
     __shared__ uint32_t s_used[8], s_flag, s_over, s_wsum[kSparseThreads / 32];
     const uint32_t tid = threadIdx.x;
-    const Sub sb = sub_geometry(g, blockIdx.x);  // spu == 1: the sub-unit is the unit
     // tokens mode (GZPB_SPARSE=2): the chunk threads also record their tokens; after the stitch the tokens of the true
     // parse are compacted, in order, into the unit's token array and k_emit<2> only replays the parser's events over them
     const bool tokens = tok_base != nullptr;
-    if (!sb.valid) { if (tokens && tid == 0) unit_ntok[blockIdx.x] = 0; return; }
+    // One CTA per unit.  A long unit (tokens mode only) is walked sub-unit by sub-unit — [32 KiB halo | new positions |
+    // look-ahead], the geometry k_split / k_link built their chains for — and the parse is carried across: where the
+    // last iteration of one sub-unit ends is where the first chunk of the next one enters.
+    const uint32_t u = blockIdx.x;
+    uint32_t min_len = 3, tok_run = 0, carry = 0xFFFFFFFFu;       // carry: unit position at which the true parse stands
+    if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); s_over = 0; }
+    if (tid < 8) s_used[tid] = 0;
+    __syncthreads();
+    for (uint32_t k = 0; k < g.spu; k++) {
+    const Sub sb = sub_geometry(g, u * g.spu + k);
+    if (!sb.valid) break;                                          // uniform: the unit ends before this sub-unit
     const uint32_t n = sb.len, nb = sb.nb, ne = sb.ne;
     const uint8_t *in = g.in + (size_t)sb.u * g.in_stride + sb.h;
     unsigned long long *M = (unsigned long long *)(mtab + (size_t)sb.u * g.m_stride + sb.h);
-    const uint16_t *p3 = prev3g + (size_t)blockIdx.x * kMaxUnitBytes;
+    const uint16_t *p3 = prev3g + (size_t)(u * g.spu + k) * kMaxUnitBytes;
+    // positions at or beyond `safe` cannot be searched from this sub-unit's window (their matches would be cut short):
+    // only a parse that drifts more than 4 positions past the sub-unit's new range gets there — flagged, unit redone
+    const bool last_sub = (size_t)sb.h + n >= g.unit_len[sb.u];
+    const uint32_t safe = last_sub ? 0xFFFFFFFFu : ne + 4;
 
-    if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+    __syncthreads();                                               // the previous sub-unit's readers are done with shared memory
     for (uint32_t i = tid; i < 2048; i += kSparseThreads) s_iter[i] = 0;
-    if (tid < 8) s_used[tid] = 0;
-    if (tid == 0) s_over = 0;
     if (!tokens) for (uint32_t i = (nb & ~127u) + tid; i < n; i += kSparseThreads) M[i] = 0ull;     // no stale entries from the lane's previous batch
     __syncthreads();
     if (n >= 5) {
         if (tid == 0) {
             uint32_t bin = (n + 15u) & ~15u, bnx = (n * 2 + 15u) & ~15u;
+            fence_proxy_async();                                   // shared memory is reused from sub-unit to sub-unit
             mbar_expect_tx(&bar, bin + bnx);
             tma_load_1d(s_in, in, bin, &bar);
-            tma_load_1d(s_next, next4g + (size_t)blockIdx.x * kMaxUnitBytes, bnx, &bar);
+            tma_load_1d(s_next, next4g + (size_t)(u * g.spu + k) * kMaxUnitBytes, bnx, &bar);
         }
-        mbar_wait(&bar, 0);
+        mbar_wait(&bar, k & 1);
     }
     // min_len at the start of the unit's first DEFLATE block (calculate_min_match_len)
-    uint32_t min_len = 3;
-    if (n - nb >= 512) {
-        const uint32_t span = min(n - nb, 4096u);
+    if (k == 0 && g.unit_len[sb.u] - g.unit_dict[sb.u] >= 512) {
+        const uint32_t span = min(min(g.unit_len[sb.u] - g.unit_dict[sb.u], n - nb), 4096u);
         const uint8_t *b8 = (const uint8_t *)s_in;
         for (uint32_t i = tid; i < span; i += kSparseThreads) { const uint32_t c = b8[nb + i]; atomicOr(&s_used[c >> 5], 1u << (c & 31)); }
         __syncthreads();
@@ -1171,9 +1186,9 @@ k_smatch(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, con
     // the lanes of a warp, each parsing its own chunk, meet in the same chain-walk loop.  Runs from iteration start q0
     // until an iteration ends at or beyond `stop`, or (rejoin) on an iteration start this chunk's speculation marked.
     const uint32_t lcap = chunk + 264;                            // tokens one chunk's parse can produce
-    uint32_t *spec_list = tokens ? lists_g + (size_t)blockIdx.x * kSparseListWords + (size_t)tid * lcap : nullptr;
+    uint32_t *spec_list = tokens ? lists_g + (size_t)u * kSparseListWords + (size_t)tid * lcap : nullptr;
     uint32_t *gap_list = tokens ? spec_list + kSparseListWords / 2 : nullptr;
-    uint16_t *idx_at = tokens ? idx_g + (size_t)blockIdx.x * kMaxUnitBytes : nullptr;
+    uint16_t *idx_at = tokens ? idx_g + (size_t)u * kMaxUnitBytes : nullptr;
     const uint8_t *b8 = (const uint8_t *)s_in;
     auto run = [&](uint32_t q0, uint32_t stop, bool rejoin, uint32_t *list, uint32_t &cnt) -> uint32_t {
         uint32_t q = q0, m = 0, cl = 0, co = 0;
@@ -1185,6 +1200,7 @@ k_smatch(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, con
                 if (!rejoin) { atomicOr(&s_iter[q >> 5], 1u << (q & 31)); if (list) idx_at[q] = (uint16_t)cnt; }
             }
             const uint32_t pos = in_look ? m + 1 : q;
+            if (pos >= safe) s_over = 1;
             const uint32_t maxlen = pos < n ? min((uint32_t)kMaxMatch, n - pos) : 0u;
             uint64_t e = 0;
             if (!in_look || maxlen >= 5) {
@@ -1224,11 +1240,13 @@ k_smatch(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, con
     }
     __syncthreads();
     // ---- (B) stitch: re-parse from the previous chunk's end until this chunk's own speculation takes over ----
-    uint32_t entry = (tid >= 1 && tid < nchunks) ? s_end[tid - 1] : 0xFFFFFFFFu, done_entry = 0xFFFFFFFFu;
+    // chunk 0 of a later sub-unit enters where the previous sub-unit's parse ended (unit position -> local position)
+    const bool chained0 = tid == 0 && carry != 0xFFFFFFFFu;
+    uint32_t entry = (tid >= 1 && tid < nchunks) ? s_end[tid - 1] : chained0 ? carry - sb.h : 0xFFFFFFFFu, done_entry = 0xFFFFFFFFu;
     for (;;) {
         if (tid == 0) s_flag = 0;
         __syncthreads();
-        if (tid >= 1 && tid < nchunks && entry != done_entry) {
+        if ((tid >= 1 || chained0) && tid < nchunks && entry != done_entry) {
             uint32_t new_end;
             if (entry >= s1) new_end = entry;                      // the chunk lies inside a match of an earlier one
             else {
@@ -1245,11 +1263,11 @@ k_smatch(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, con
         __syncthreads();
         if (!again) break;
     }
-    if (!tokens) return;
+    if (!tokens) return;                                           // table mode: single sub-unit
     // ---- (C) compact the tokens of the true parse: [gap tokens | this chunk's speculation from the re-join on] ----
     uint32_t ngap = 0, from = 0, nspec = 0;
     if (tid < nchunks) {
-        if (tid == 0) nspec = cnt_spec;
+        if (tid == 0 && !chained0) nspec = cnt_spec;
         else if (entry < s1) {
             ngap = cnt_gap;
             if (gap_q < s1) { from = idx_at[gap_q]; nspec = cnt_spec - from; }
@@ -1264,12 +1282,17 @@ k_smatch(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, con
     __syncthreads();
     uint32_t base = 0, total = 0;
     for (int w = 0; w < kSparseThreads / 32; w++) { const uint32_t v = s_wsum[w]; if (w < (int)warp) base += v; total += v; }
-    uint32_t *out = tok_base + (size_t)sb.u * g.tok_stride + (base + incl - mine);
-    if (!s_over && total <= g.tok_stride) {
-        for (uint32_t k = 0; k < ngap; k++) out[k] = gap_list[k];
-        for (uint32_t k = 0; k < nspec; k++) out[ngap + k] = spec_list[from + k];
+    uint32_t *out = tok_base + (size_t)sb.u * g.tok_stride + tok_run + (base + incl - mine);
+    if (!s_over && tok_run + total <= g.tok_stride) {
+        for (uint32_t j = 0; j < ngap; j++) out[j] = gap_list[j];
+        for (uint32_t j = 0; j < nspec; j++) out[ngap + j] = spec_list[from + j];
     }
-    if (tid == 0) unit_ntok[blockIdx.x] = (s_over || total > g.tok_stride) ? 0xFFFFFFFFu : total;
+    if (tok_run + total > g.tok_stride) s_over = 1;
+    tok_run += total;
+    carry = sb.h + s_end[nchunks - 1];                             // read before the next sub-unit's barrier lets anyone overwrite it
+    }
+    __syncthreads();
+    if (tokens && tid == 0) unit_ntok[u] = s_over ? 0xFFFFFFFFu : tok_run;
 }
 
 template <int kSparse>
@@ -1412,12 +1435,14 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
                         const bool may_check = (num_new_obs + 32 >= (uint32_t)kObsPerCheck) && (next_p - bb >= (uint32_t)kMinBlockLength) && (n - p > (uint32_t)kMinBlockLength);
                         const bool may_recalc = (mode != 0) && (next_p > next_recalc);
                         const bool may_seq = nmatch + 32 >= seq_limit;
-                        if (may_check || may_recalc || may_seq) {
+                        const bool may_max = next_p >= max_block_end && max_block_end < n;       // SOFT_MAX_BLOCK_LENGTH reached inside this window
+                        if (may_check || may_recalc || may_seq || may_max) {
                             const uint32_t rmask = may_recalc ? __ballot_sync(0xFFFFFFFFu, valid && starts_iter && q >= next_recalc) : 0u;
                             const uint32_t cmask = __ballot_sync(0xFFFFFFFFu, valid && ends_iter && (num_new_obs + incl >= (uint32_t)kObsPerCheck) &&
                                                                              (e_l - bb >= (uint32_t)kMinBlockLength) && (n - e_l >= (uint32_t)kMinBlockLength));
                             const uint32_t mincl = __popc(mmask & (lane == 31 ? 0xFFFFFFFFu : ((2u << lane) - 1)));
-                            const uint32_t smask = __ballot_sync(0xFFFFFFFFu, valid && ends_iter && (nmatch + mincl >= seq_limit));
+                            // the loop condition `p < max_block_end` and the sequence-store limit both end the block after the iteration
+                            const uint32_t smask = __ballot_sync(0xFFFFFFFFu, valid && ends_iter && ((nmatch + mincl >= seq_limit) || e_l >= max_block_end));
                             const int Lr = rmask ? __ffs(rmask) - 1 : 64, Lc = cmask ? __ffs(cmask) - 1 : 64, Ls = smask ? __ffs(smask) - 1 : 64;
                             if (Lr <= Lc && Lr <= Ls && Lr < 64) { event = 1; commit_mask = vis & ((1u << Lr) - 1); next_p = __shfl_sync(0xFFFFFFFFu, q, Lr); next_h = 0; }
                             else if (Ls <= Lc && Ls < 64) { event = 3; commit_mask = vis & (Ls == 31 ? 0xFFFFFFFFu : ((2u << Ls) - 1)); next_p = __shfl_sync(0xFFFFFFFFu, e_l, Ls); next_h = 0; }
@@ -2072,7 +2097,8 @@ k_check(const __grid_constant__ Geo g, uint32_t *__restrict__ sum_out, int kind)
             }
             while (pos < end) { c = (c >> 8) ^ s_tab[0][(c ^ in[pos]) & 0xFF]; pos++; }
             c = ~c;
-            acc ^= (j == 0) ? c : gf2_mulmod(c, c_xpow512[j], kCrcPoly);
+            if (j >= 1024) c = gf2_mulmod(c, c_xpow512k[(j >> 10) & 15], kCrcPoly);      // beyond the 512 KiB the first table spans
+            acc ^= (j == 0) ? c : gf2_mulmod(c, c_xpow512[j & 1023], kCrcPoly);
         }
         for (int o = 16; o; o >>= 1) acc ^= __shfl_xor_sync(0xFFFFFFFFu, acc, o);
         if ((tid & 31) == 0 && acc) atomicXor(&s_crc, acc);
@@ -2235,10 +2261,11 @@ cudaError_t launch_deflate_pipeline(const DeflateBatch &b, cudaStream_t st)
             DBG_SYNC("k_chain");
         }
         if (b.timer) { b.timer->stop(st); b.timer->start(KT_MATCH, st); }
-        if (b.sparse && b.lists && b.spu == 1 && !lp.ht && (lp.mode == 0 || lp.mode == 1)) {
+        const bool sparse_tokens = b.sparse == 2 && b.slists && b.sidx && b.sntok;
+        if (b.sparse && b.lists && (b.spu == 1 || sparse_tokens) && !lp.ht && (lp.mode == 0 || lp.mode == 1)) {
             // sparse path: speculative table, parse with miss detection, then the two filtered fallback launches
             const uint32_t chunk = (b.sparse_chunk >= kSparseChunk && b.sparse_chunk <= 4096u) ? b.sparse_chunk : kSparseChunk;   // 512 x 128 covers a unit
-            const bool tokens = b.sparse == 2 && b.slists && b.sidx && b.sntok;
+            const bool tokens = sparse_tokens;
             GZPB_LAUNCH(k_smatch, b.nunits, kSparseThreads, match_smem, st, g, b.next4, b.prev3, b.mtab, lp.depth, lp.nice, lp.mode, chunk,
                         tokens ? b.tokens : (uint32_t *)nullptr, b.slists, b.sidx, b.sntok);
             DBG_SYNC("k_smatch");

@@ -229,7 +229,7 @@ static int lane_alloc(gzpb_ctx *c, Lane &L, bool with_io)
     if (!getenv("GZPB_USE_KCHAIN")) {
         CK(dmalloc(&L.d_lists, U * c->spu * 2 * kMaxUnitBytes));
         CK(dmalloc(&L.d_list_start, U * c->spu * 32));
-        if (c->sparse == 2 && c->spu == 1) {
+        if (c->sparse == 2) {
             CK(dmalloc(&L.d_slists, U * kSparseListWordsPerUnit));
             CK(dmalloc(&L.d_sidx, U * (size_t)kMaxUnitBytes));
             CK(dmalloc(&L.d_sntok, U));

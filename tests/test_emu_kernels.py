@@ -766,3 +766,22 @@ def test_emu_sparse_fuzz(monkeypatch):
         finally:
             ctx.close()
         assert got == oracle.compress_stream(fmt, level, bs, [d]), (fmt, level, bs, len(d))
+
+
+def test_emu_units_longer_than_512k_checksum():
+    """Regression: k_check's x^(8*512*j) table spans 512 KiB; longer units (up to 4 MiB) need the second table —
+    the Mgzip / Gzip CRC-32 of a 590 000-byte block was wrong before."""
+    big = (TEXT * 3)[:600000]
+    assert gzip.decompress(_run(oracle.MGZIP, 4, 590000, big)) == big
+    assert gzip.decompress(_run(oracle.GZIP, 2, 560000, big)) == big
+
+
+def test_emu_sparse_tokens_long_units(monkeypatch):
+    """GZPB_SPARSE=2 on long units: k_smatch walks the unit sub-unit by sub-unit and carries the parse across; the
+    replay also ends a DEFLATE block at SOFT_MAX_BLOCK_LENGTH (units above 300 000 bytes)."""
+    monkeypatch.setenv("GZPB_SPARSE", "2")
+    for fmt, level, bs, d in ((oracle.MGZIP, 6, 131072, TEXT + TEXT[:50000]), (oracle.GZIP, 6, 131072, TEXT), (oracle.ZLIB, 5, 100000, TEXT[:250000]),
+                              (oracle.RAWDEFLATE, 6, 262144, synth.fastq(300000)), (oracle.MGZIP, 2, 131072, bytes(200000)),
+                              (oracle.MGZIP, 6, 400000, (TEXT * 3)[:820000])):
+        units, missed = _run_sparse(fmt, level, bs, d)
+        assert units >= 2 and missed == 0, (fmt, level, bs)
