@@ -199,3 +199,16 @@ def test_bgzf_block_size_exceeded_error():
     ok = ctx.encode_blocks([(b"hello " * 1000, None, True)])[0][0]
     assert ok == oracle.encode_block(oracle.BGZF, 6, b"hello " * 1000, None, True)
     ctx.close()
+
+
+def test_units_longer_than_512k_have_the_right_checksum(text_corpus):
+    """Regression (found on the emulator): k_check's x^(8*512*j) table spans 512 KiB; a 600 000-byte Mgzip / Gzip block
+    needs the second table for its CRC-32."""
+    import gzip
+    for fmt, level, bs in ((MGZIP, 4, 600000), (GZIP, 6, 560000)):
+        data = text_corpus[:bs + 7000]
+        ctx = gzp_b200.Context(fmt, level, max_block_bytes=bs, max_blocks_in_flight=2)
+        got = ctx.encode_stream(data, bs)
+        ctx.close()
+        assert got == oracle.compress_stream(fmt, level, bs, [data])
+        assert gzip.decompress(got) == data
