@@ -1067,7 +1067,7 @@ constexpr uint32_t kSparseChunk = 128;          // default positions per chunk (
 // the body of k_match's phase 2 for one position: best match over `depth` nodes with the depth/2 snapshot
 // (full), or over depth/2 nodes only (look-ahead entry: B column + hash3 fields)
 __device__ __forceinline__ uint64_t sparse_entry(const uint32_t *s_in, const uint16_t *s_next, const uint16_t *p3, uint32_t n, uint32_t p,
-                                                 uint32_t depth, uint32_t nice, bool lazy, bool full)
+                                                 uint32_t depth, uint32_t nice, bool lazy, bool full, uint32_t limit)
 {
     const uint32_t maxlen = min((uint32_t)kMaxMatch, n - p);
     if (maxlen < 5) return kValidA | kValidB;
@@ -1077,7 +1077,7 @@ __device__ __forceinline__ uint64_t sparse_entry(const uint32_t *s_in, const uin
     const uint32_t d3 = p3[p];
     uint32_t off3 = 0;
     if (d3 && d3 <= 8192u && ((ld32u(s_in, p - d3) ^ seq4) & 0xFFFFFFu) == 0) off3 = d3;
-    const uint32_t depthB = depth >> 1, limit = full ? depth : depthB;
+    const uint32_t depthB = depth >> 1;              // limit: nodes to walk (depth for a fresh search, depth/2 or depth/4 for the look-aheads)
     const uint8_t *b8 = (const uint8_t *)s_in;
     uint32_t best = 3, boff = 0, lenB = 0, offB = 0, pbest = 0;
     bool haveB = !(lazy && full);
@@ -1192,19 +1192,19 @@ k_smatch(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, con
     const uint8_t *b8 = (const uint8_t *)s_in;
     auto run = [&](uint32_t q0, uint32_t stop, bool rejoin, uint32_t *list, uint32_t &cnt) -> uint32_t {
         uint32_t q = q0, m = 0, cl = 0, co = 0;
-        bool in_look = false;
+        uint32_t in_look = 0;                                      // 0 fresh search, 1 look-ahead at m + 1 (depth/2), 2 at m + 2 (depth/4, lazy2)
         auto emit = [&](uint32_t t) { if (list) { if (cnt < lcap) list[cnt] = t; cnt++; } };
         for (;;) {
             if (!in_look) {
                 if (q >= stop || (rejoin && ((s_iter[q >> 5] >> (q & 31)) & 1u))) return q;
                 if (!rejoin) { atomicOr(&s_iter[q >> 5], 1u << (q & 31)); if (list) idx_at[q] = (uint16_t)cnt; }
             }
-            const uint32_t pos = in_look ? m + 1 : q;
+            const uint32_t pos = in_look ? m + in_look : q;
             if (pos >= safe) s_over = 1;
             const uint32_t maxlen = pos < n ? min((uint32_t)kMaxMatch, n - pos) : 0u;
             uint64_t e = 0;
             if (!in_look || maxlen >= 5) {
-                e = sparse_entry(s_in, s_next, p3, n, pos, (uint32_t)depth, (uint32_t)nice, lazy, !in_look);
+                e = sparse_entry(s_in, s_next, p3, n, pos, (uint32_t)depth, (uint32_t)nice, lazy, !in_look, (uint32_t)depth >> in_look);
                 if (!tokens) atomicOr(&M[pos], (unsigned long long)e);
             }
             if (!in_look) {
@@ -1217,15 +1217,18 @@ k_smatch(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, con
                 if (cl < min_len || (cl == 3 && co > 8192)) { emit(kTokEnd | b8[q]); q = q + 1; continue; }
                 m = q;
                 if (cl >= min((uint32_t)nice, maxlen)) { emit(kTokEnd | 0x80000000u | (cl << 16) | co); q = m + cl; continue; }
-                in_look = true;
+                in_look = 1;
             } else {
                 uint32_t nl, no;
                 table_search(e, cl - 1, true, maxlen, nl, no);
-                if (nl >= cl && 4 * (int)(nl - cl) + ((int)bsr32(co) - (int)bsr32(no)) > 2) {
-                    emit(b8[m]);                                   // literal; the look-ahead match becomes the pending one
-                    m++; cl = nl; co = no;
-                    if (cl >= min((uint32_t)nice, maxlen)) { emit(kTokEnd | 0x80000000u | (cl << 16) | co); q = m + cl; in_look = false; }
-                } else { emit(kTokEnd | 0x80000000u | (cl << 16) | co); q = m + cl; in_look = false; }
+                if (nl >= cl && 4 * (int)(nl - cl) + ((int)bsr32(co) - (int)bsr32(no)) > (in_look == 1 ? 2 : 6)) {
+                    emit(b8[m]);                                   // literal(s); the look-ahead match becomes the pending one
+                    if (in_look == 2) emit(b8[m + 1]);
+                    m += in_look; cl = nl; co = no;
+                    if (cl >= min((uint32_t)nice, maxlen)) { emit(kTokEnd | 0x80000000u | (cl << 16) | co); q = m + cl; in_look = 0; }
+                    else in_look = 1;
+                } else if (mode == 2 && in_look == 1) in_look = 2;   // lazy2: one more look, two positions ahead
+                else { emit(kTokEnd | 0x80000000u | (cl << 16) | co); q = m + cl; in_look = 0; }
             }
         }
     };
@@ -2262,7 +2265,7 @@ cudaError_t launch_deflate_pipeline(const DeflateBatch &b, cudaStream_t st)
         }
         if (b.timer) { b.timer->stop(st); b.timer->start(KT_MATCH, st); }
         const bool sparse_tokens = b.sparse == 2 && b.slists && b.sidx && b.sntok;
-        if (b.sparse && b.lists && (b.spu == 1 || sparse_tokens) && !lp.ht && (lp.mode == 0 || lp.mode == 1)) {
+        if (b.sparse && b.lists && (b.spu == 1 || sparse_tokens) && !lp.ht && (lp.mode == 0 || lp.mode == 1 || (lp.mode == 2 && sparse_tokens))) {
             // sparse path: speculative table, parse with miss detection, then the two filtered fallback launches
             const uint32_t chunk = (b.sparse_chunk >= kSparseChunk && b.sparse_chunk <= 4096u) ? b.sparse_chunk : kSparseChunk;   // 512 x 128 covers a unit
             const bool tokens = sparse_tokens;

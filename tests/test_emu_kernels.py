@@ -702,7 +702,7 @@ def test_emu_sparse_chunk_sizes(monkeypatch, chunk):
     assert units == 2 and missed == 0
 
 
-@pytest.mark.parametrize("level", [2, 5, 6, 7])
+@pytest.mark.parametrize("level", [2, 5, 6, 7, 9])
 def test_emu_sparse_tokens_and_replay_levels(monkeypatch, level):
     """GZPB_SPARSE=2: k_smatch also hands over the stitched, compacted tokens of the true parse and k_emit<2> only
     replays the parser's events over them (min_len re-calculation, block-split checks, sequence-store limit)."""
@@ -782,6 +782,7 @@ def test_emu_sparse_tokens_long_units(monkeypatch):
     monkeypatch.setenv("GZPB_SPARSE", "2")
     for fmt, level, bs, d in ((oracle.MGZIP, 6, 131072, TEXT + TEXT[:50000]), (oracle.GZIP, 6, 131072, TEXT), (oracle.ZLIB, 5, 100000, TEXT[:250000]),
                               (oracle.RAWDEFLATE, 6, 262144, synth.fastq(300000)), (oracle.MGZIP, 2, 131072, bytes(200000)),
-                              (oracle.MGZIP, 6, 400000, (TEXT * 3)[:820000])):
+                              (oracle.MGZIP, 6, 400000, (TEXT * 3)[:820000]),
+                              (oracle.GZIP, 9, 262144, synth.fastq(100000) + TEXT[:250000])):          # BASELINE configs[4] shape: lazy2 on long units
         units, missed = _run_sparse(fmt, level, bs, d)
         assert units >= 2 and missed == 0, (fmt, level, bs)

@@ -72,7 +72,7 @@ def test_sparse_tokens_and_replay_is_bit_identical_on_gpu(monkeypatch, text_corp
     rnd = random.Random(77)
     few = bytes(rnd.choice(b"ACGT") for _ in range(40000))
     mixed = (few + text_corpus[:60000])[:65280]
-    for level in (2, 5, 6, 7):
+    for level in (2, 5, 6, 7, 9):
         data = text_corpus[:1_000_000]
         got, (units, missed) = _encode("GZPB_SPARSE", monkeypatch, BGZF, level, 65280, data, "split+link+smatch+replay", "2")
         assert got == oracle.compress_stream(BGZF, level, 65280, [data]), level
@@ -83,3 +83,9 @@ def test_sparse_tokens_and_replay_is_bit_identical_on_gpu(monkeypatch, text_corp
         assert got == oracle.compress_stream(BGZF, 6, 65280, [data]), len(data)
         if want_missed is not None:
             assert missed == want_missed, (len(data), units, missed)
+    # long units: Mgzip 131 072-byte blocks (configs[2]) and Gzip level 9 with 262 144-byte blocks on FASTQ-shaped data (configs[4])
+    from gzp_b200 import MGZIP
+    for fmt, level, bs, data in ((MGZIP, 6, 131072, text_corpus[:1_200_000]), (GZIP, 9, 262144, synth.fastq(1_000_000))):
+        got, (units, missed) = _encode("GZPB_SPARSE", monkeypatch, fmt, level, bs, data, "split+link+smatch+replay", "2")
+        assert got == oracle.compress_stream(fmt, level, bs, [data]), (fmt, level)
+        assert units >= 4 and missed == 0
