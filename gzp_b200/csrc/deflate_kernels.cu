@@ -1414,10 +1414,12 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
                     if (assumed_min_len == 0) assumed_min_len = min_len;
                     bool miss = (total == 0xFFFFFFFFu) || (min_len != assumed_min_len);   // k_smatch parsed the whole unit with one min_len
                     if (lane == 0) S.tok0 = tcur;
+                    uint32_t tpre = (!miss && tcur + lane < total) ? tok[tcur + lane] : 0u;      // this window's token, loaded one window ahead
                     do {
                         const uint32_t ti = tcur + lane;
                         const bool valid = !miss && ti < total;
-                        const uint32_t t = valid ? tok[ti] : 0u;
+                        const uint32_t t = valid ? tpre : 0u;
+                        const uint32_t tfut = (!miss && ti + 32 < total) ? tok[ti + 32] : 0u;      // the usual next window (all 32 tokens commit)
                         const bool isM = (t >> 31) & 1u, ends_iter = (t >> 30) & 1u;
                         const uint32_t mlen = isM ? (t >> 16) & 0x1FF : 1u, moff = t & 0xFFFF, lit = t & 0xFF;
                         const uint32_t len = valid ? mlen : 0u;
@@ -1463,6 +1465,8 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
                             const uint32_t added = __popc(commit_mask);
                             ntok += added; num_new_obs += added; tcur += added;
                             nmatch += __popc(commit_mask & mmask);
+                            __syncwarp();
+                            tpre = added == 32 ? tfut : ((tcur + lane < total) ? tok[tcur + lane] : 0u);   // an event cut the window short: reload
                         }
                         in_h = next_h;
                         p = next_p;
