@@ -1185,7 +1185,7 @@ k_smatch(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, con
     // trip — a fresh full-depth search at an iteration start, or the depth/2 look-ahead behind a pending match — so that
     // the lanes of a warp, each parsing its own chunk, meet in the same chain-walk loop.  Runs from iteration start q0
     // until an iteration ends at or beyond `stop`, or (rejoin) on an iteration start this chunk's speculation marked.
-    const uint32_t lcap = chunk + 264;                            // tokens one chunk's parse can produce
+    const uint32_t lcap = (chunk + 264 + 3) & ~3u;                // tokens one chunk's parse can produce (multiple of 4: 16-byte stores)
     uint32_t *spec_list = tokens ? lists_g + (size_t)u * kSparseListWords + (size_t)tid * lcap : nullptr;
     uint32_t *gap_list = tokens ? spec_list + kSparseListWords / 2 : nullptr;
     uint16_t *idx_at = tokens ? idx_g + (size_t)u * kMaxUnitBytes : nullptr;
@@ -1193,10 +1193,25 @@ k_smatch(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, con
     auto run = [&](uint32_t q0, uint32_t stop, bool rejoin, uint32_t *list, uint32_t &cnt) -> uint32_t {
         uint32_t q = q0, m = 0, cl = 0, co = 0;
         uint32_t in_look = 0;                                      // 0 fresh search, 1 look-ahead at m + 1 (depth/2), 2 at m + 2 (depth/4, lazy2)
-        auto emit = [&](uint32_t t) { if (list) { if (cnt < lcap) list[cnt] = t; cnt++; } };
+        // tokens leave in 16-byte stores: four at a time through a register buffer (lists are 16-byte aligned, lcap % 4 == 0)
+        uint32_t eb0 = 0, eb1 = 0, eb2 = 0;
+        auto emit = [&](uint32_t t) {
+            if (!list) return;
+            const uint32_t k = cnt & 3u;
+            if (k == 0) eb0 = t; else if (k == 1) eb1 = t; else if (k == 2) eb2 = t;
+            else if (cnt < lcap) *(uint4 *)(list + (cnt - 3)) = make_uint4(eb0, eb1, eb2, t);
+            cnt++;
+        };
+        auto flush = [&]() {
+            if (!list) return;
+            const uint32_t k = cnt & 3u, b = cnt - k;
+            if (k >= 1 && b < lcap) list[b] = eb0;
+            if (k >= 2 && b + 1 < lcap) list[b + 1] = eb1;
+            if (k >= 3 && b + 2 < lcap) list[b + 2] = eb2;
+        };
         for (;;) {
             if (!in_look) {
-                if (q >= stop || (rejoin && ((s_iter[q >> 5] >> (q & 31)) & 1u))) return q;
+                if (q >= stop || (rejoin && ((s_iter[q >> 5] >> (q & 31)) & 1u))) { flush(); return q; }
                 if (!rejoin) { atomicOr(&s_iter[q >> 5], 1u << (q & 31)); if (list) idx_at[q] = (uint16_t)cnt; }
             }
             const uint32_t pos = in_look ? m + in_look : q;
@@ -1285,10 +1300,18 @@ k_smatch(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, con
     __syncthreads();
     uint32_t base = 0, total = 0;
     for (int w = 0; w < kSparseThreads / 32; w++) { const uint32_t v = s_wsum[w]; if (w < (int)warp) base += v; total += v; }
-    uint32_t *out = tok_base + (size_t)sb.u * g.tok_stride + tok_run + (base + incl - mine);
+    // every warp copies the lists of its 32 chunks one after another, lanes striding over the tokens (coalesced both ways)
     if (!s_over && tok_run + total <= g.tok_stride) {
-        for (uint32_t j = 0; j < ngap; j++) out[j] = gap_list[j];
-        for (uint32_t j = 0; j < nspec; j++) out[ngap + j] = spec_list[from + j];
+        uint32_t *unit_tok = tok_base + (size_t)sb.u * g.tok_stride + tok_run;
+        const uint32_t my_off = base + incl - mine;
+        for (uint32_t c = 0; c < 32; c++) {
+            const uint32_t c_gap = __shfl_sync(0xFFFFFFFFu, ngap, c), c_spec = __shfl_sync(0xFFFFFFFFu, nspec, c);
+            const uint32_t c_from = __shfl_sync(0xFFFFFFFFu, from, c), c_off = __shfl_sync(0xFFFFFFFFu, my_off, c);
+            const uint32_t *c_gl = lists_g + (size_t)u * kSparseListWords + kSparseListWords / 2 + (size_t)(warp * 32 + c) * lcap;
+            const uint32_t *c_sl = lists_g + (size_t)u * kSparseListWords + (size_t)(warp * 32 + c) * lcap;
+            for (uint32_t j = lane; j < c_gap; j += 32) unit_tok[c_off + j] = c_gl[j];
+            for (uint32_t j = lane; j < c_spec; j += 32) unit_tok[c_off + c_gap + j] = c_sl[c_from + j];
+        }
     }
     if (tok_run + total > g.tok_stride) s_over = 1;
     tok_run += total;
