@@ -123,7 +123,8 @@ int gzpb_encode_stream(gzpb_ctx *ctx, const void *in, size_t in_len, size_t buff
  * (GZPB_EIO is then returned by the next call, like the reference surfaces a BrokenPipe).
  * The caller's bytes are copied once into pinned slabs; up to 3 device batches of `blocks_in_flight`
  * blocks per GPU stay in flight while the caller keeps writing (back-pressure = the bounded channels
- * of :111-112); `sink` is called once per finished batch, in order, from the calling thread. */
+ * of :111-112); `sink` is called once per finished batch, in order, from the calling thread.
+ * buffer_size 0 = the format's default; blocks_in_flight 0 = 1184 (8 thread blocks per SM on 148 SMs). */
 typedef int (*gzpb_sink_fn)(void *user, const void *data, size_t len);
 typedef struct gzpb_writer gzpb_writer;
 int gzpb_writer_create(gzpb_writer **w, int device, int format, int level, size_t buffer_size,
