@@ -647,6 +647,7 @@ def _run_sparse(fmt, level, bs, data):
     ctx = emu.EmuContext(fmt, level, max_block_bytes=bs)
     try:
         assert ctx.L.gzpb_ctx_variant(ctx.h) in (b"split+link+smatch", b"split+link+smatch+replay")
+        _sparse_stats(ctx)                                        # device-wide counters: start from zero
         got = ctx.encode_stream(data, bs)
         units, missed = _sparse_stats(ctx)
     finally:

@@ -27,6 +27,8 @@ def _encode(env, monkeypatch, fmt, level, bs, data, want_variant, value="1"):
     ctx = gzp_b200.Context(fmt, level, max_block_bytes=bs, max_blocks_in_flight=64)
     try:
         assert L.gzpb_ctx_variant(ctx._h).decode() == want_variant
+        L.gzpb_debug_sparse_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_int]
+        L.gzpb_debug_sparse_stats(ctx._h, None, None, 1)          # device-wide counters: start from zero
         got = ctx.encode_stream(data, bs)
         stats = None
         if env == "GZPB_SPARSE":
