@@ -20,6 +20,6 @@ GZPB_BENCH_NO_VARIANTS=1 timeout 200 ncu --metrics gpu__time_duration.sum --cloc
     python bench.py --steps 2 --warmup 1 --blocks 3256 --cpu-sample-mb 8 > gpurun_out/ncu_bench.log 2>&1
 timeout 200 ncu --set full --clock-control none --import-source on -k regex:"k_emit|k_match|k_split|k_link" -c 4 -o gpurun_out/full_default -f \
     python tests/prof_run.py 2368 > gpurun_out/ncu_full_default.log 2>&1
-GZPB_SPARSE=1 timeout 200 ncu --set full --clock-control none --import-source on -k regex:"k_emit|k_smatch" -c 2 -o gpurun_out/full_sparse -f \
+GZPB_SPARSE=2 timeout 200 ncu --set full --clock-control none --import-source on -k regex:"k_emit|k_smatch" -c 2 -o gpurun_out/full_sparse -f \
     python tests/prof_run.py 2368 > gpurun_out/ncu_full_sparse.log 2>&1
 tail -5 gpurun_out/pytest_gpu.log; head -c 900 gpurun_out/bench.json; echo; cat gpurun_out/variants_l6.jsonl | cut -c1-400; tail -2 gpurun_out/variants_l6.err
