@@ -1132,6 +1132,8 @@ k_smatch(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, con
     __shared__ uint32_t s_iter[2048];            // iteration starts of the speculative parses, one bit per position
     __shared__ uint32_t s_end[kSparseThreads];   // where each chunk's last iteration ends
     __shared__ uint32_t s_used[8], s_flag, s_over, s_wsum[kSparseThreads / 32];
+    __shared__ uint32_t s_fl[256], s_obs[10], s_nobs[10];      // event scan: literal frequencies and split statistics of the current DEFLATE block
+    __shared__ uint32_t s_chg[4];                               // event scan -> all threads: {changed, token index, unit position, new min_len}
     const uint32_t tid = threadIdx.x;
     // tokens mode (GZPB_SPARSE=2): the chunk threads also record their tokens; after the stitch the tokens of the true
     // parse are compacted, in order, into the unit's token array and k_emit<2> only replays the parser's events over them
@@ -1141,6 +1143,13 @@ k_smatch(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, con
     // last iteration of one sub-unit ends is where the first chunk of the next one enters.
     const uint32_t u = blockIdx.x;
     uint32_t min_len = 3, tok_run = 0, carry = 0xFFFFFFFFu;       // carry: unit position at which the true parse stands
+    // event scan (warp 0, tokens mode): the parser's state that outlives an iteration — replayed over the stitched tokens to
+    // find the places where min_len changes (re-calculation schedule, start of a new DEFLATE block); unit coordinates
+    const uint32_t unit_n = g.unit_len[u], unit_dict = g.unit_dict[u];
+    uint32_t rt = 0, rp = unit_dict, bb = unit_dict, next_recalc = unit_dict + min(unit_n - unit_dict, 10000u);
+    uint32_t num_obs = 0, num_new_obs = 0, nmatch = 0, in_h = 0;
+    if (tid < 256) s_fl[tid] = 0;
+    if (tid < 10) { s_obs[tid] = 0; s_nobs[tid] = 0; }
     if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); s_over = 0; }
     if (tid < 8) s_used[tid] = 0;
     __syncthreads();
@@ -1247,9 +1256,18 @@ k_smatch(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, con
             }
         }
     };
+    // An epoch = one speculation + stitch of [E, ne) with one min_len.  The event scan below ends it early where min_len
+    // changes; the rest of the sub-unit is then speculated again from there (tokens mode; the table form has one epoch).
+    uint32_t E = nb, epoch_entry = (carry != 0xFFFFFFFFu) ? carry - sb.h : nb;
+    for (uint32_t epoch = 0;; epoch++) {
+    if (epoch) {
+        __syncthreads();
+        for (uint32_t i = tid; i < 2048; i += kSparseThreads) s_iter[i] = 0;
+        __syncthreads();
+    }
     // ---- (A) speculate: chunk `tid` from its first position ----
-    const uint32_t nchunks = (ne - nb + chunk - 1) / chunk;       // <= kSparseThreads (the launcher checks)
-    const uint32_t s0 = nb + tid * chunk, s1 = min(ne, s0 + chunk);
+    const uint32_t nchunks = (ne - E + chunk - 1) / chunk;        // <= kSparseThreads (the launcher checks)
+    const uint32_t s0 = E + tid * chunk, s1 = min(ne, s0 + chunk);
     uint32_t spec_end = 0;
     uint32_t cnt_spec = 0, cnt_gap = 0, gap_q = 0;
     if (tid < nchunks) {
@@ -1259,8 +1277,8 @@ k_smatch(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, con
     __syncthreads();
     // ---- (B) stitch: re-parse from the previous chunk's end until this chunk's own speculation takes over ----
     // chunk 0 of a later sub-unit enters where the previous sub-unit's parse ended (unit position -> local position)
-    const bool chained0 = tid == 0 && carry != 0xFFFFFFFFu;
-    uint32_t entry = (tid >= 1 && tid < nchunks) ? s_end[tid - 1] : chained0 ? carry - sb.h : 0xFFFFFFFFu, done_entry = 0xFFFFFFFFu;
+    const bool chained0 = tid == 0 && epoch_entry != E;
+    uint32_t entry = (tid >= 1 && tid < nchunks) ? s_end[tid - 1] : chained0 ? epoch_entry : 0xFFFFFFFFu, done_entry = 0xFFFFFFFFu;
     for (;;) {
         if (tid == 0) s_flag = 0;
         __syncthreads();
@@ -1315,7 +1333,116 @@ k_smatch(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, con
     }
     if (tok_run + total > g.tok_stride) s_over = 1;
     tok_run += total;
-    carry = sb.h + s_end[nchunks - 1];                             // read before the next sub-unit's barrier lets anyone overwrite it
+    const uint32_t sub_end = sb.h + s_end[nchunks - 1];            // unit position where this epoch's parse ends
+    __syncthreads();                                               // the compacted tokens are visible to warp 0
+    // ---- (D) event scan (warp 0): replay what outlives an iteration over the new tokens, stop where min_len changes ----
+    if (warp == 0) {
+        const uint32_t *ut = tok_base + (size_t)sb.u * g.tok_stride;
+        const uint32_t limit_t = s_over ? rt : tok_run;
+        bool changed = false;
+        uint32_t new_min = min_len;
+        while (rt < limit_t && !changed) {
+            const uint32_t max_block_end = (unit_n - bb < (uint32_t)kSoftMaxBlockLength + (uint32_t)kMinBlockLength) ? unit_n : bb + (uint32_t)kSoftMaxBlockLength;
+            const uint32_t ti = rt + lane;
+            const bool valid = ti < limit_t;
+            const uint32_t t = valid ? ut[ti] : 0u;
+            const bool isM = (t >> 31) & 1u, ends_iter = (t >> 30) & 1u;
+            const uint32_t mlen = isM ? (t >> 16) & 0x1FF : 1u, lit = t & 0xFF;
+            const uint32_t len = valid ? mlen : 0u;
+            uint32_t pincl = len;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, pincl, d); if (lane >= (uint32_t)d) pincl += v; }
+            const uint32_t q = rp + pincl - len, e_l = rp + pincl;
+            const uint32_t prev_ends = __shfl_up_sync(0xFFFFFFFFu, (uint32_t)ends_iter, 1);
+            const bool starts_iter = lane == 0 ? (in_h == 0) : (prev_ends != 0);
+            const uint32_t vis = __ballot_sync(0xFFFFFFFFu, valid);
+            const uint32_t lastl = 31 - __clz(vis);
+            uint32_t commit_mask = vis, next_p = __shfl_sync(0xFFFFFFFFu, e_l, lastl), next_h = __shfl_sync(0xFFFFFFFFu, (uint32_t)!ends_iter, lastl);
+            int event = 0;
+            const uint32_t mmask = __ballot_sync(0xFFFFFFFFu, valid && isM);
+            const uint32_t rmask = (mode != 0) ? __ballot_sync(0xFFFFFFFFu, valid && starts_iter && q >= next_recalc) : 0u;
+            const uint32_t cmask = __ballot_sync(0xFFFFFFFFu, valid && ends_iter && (num_new_obs + lane + 1 >= (uint32_t)kObsPerCheck) &&
+                                                             (e_l - bb >= (uint32_t)kMinBlockLength) && (unit_n - e_l >= (uint32_t)kMinBlockLength));
+            const uint32_t mincl = __popc(mmask & (lane == 31 ? 0xFFFFFFFFu : ((2u << lane) - 1)));
+            const uint32_t smask = __ballot_sync(0xFFFFFFFFu, valid && ends_iter && ((nmatch + mincl >= (uint32_t)kSeqStoreLength) || e_l >= max_block_end));
+            const int Lr = rmask ? __ffs(rmask) - 1 : 64, Lc = cmask ? __ffs(cmask) - 1 : 64, Ls = smask ? __ffs(smask) - 1 : 64;
+            if (Lr <= Lc && Lr <= Ls && Lr < 64) { event = 1; commit_mask = vis & ((1u << Lr) - 1); next_p = __shfl_sync(0xFFFFFFFFu, q, Lr); next_h = 0; }
+            else if (Ls <= Lc && Ls < 64) { event = 3; commit_mask = vis & (Ls == 31 ? 0xFFFFFFFFu : ((2u << Ls) - 1)); next_p = __shfl_sync(0xFFFFFFFFu, e_l, Ls); next_h = 0; }
+            else if (Lc < 64) { event = 2; commit_mask = vis & (Lc == 31 ? 0xFFFFFFFFu : ((2u << Lc) - 1)); next_p = __shfl_sync(0xFFFFFFFFu, e_l, Lc); next_h = 0; }
+            if ((commit_mask >> lane) & 1u) {
+                if (!isM) atomicAdd(&s_fl[lit], 1u);
+                atomicAdd(&s_nobs[isM ? 8 + (mlen >= 9) : (((lit >> 5) & 6) | (lit & 1))], 1u);
+            }
+            const uint32_t added = __popc(commit_mask);
+            num_new_obs += added; rt += added; nmatch += __popc(commit_mask & mmask);
+            in_h = next_h; rp = next_p;
+            __syncwarp();
+            bool end_block = false;
+            if (event == 1) {
+                uint32_t tot = 0;
+                for (int i = 0; i < 8; i++) tot += s_fl[lane * 8 + i];
+                for (int o = 16; o; o >>= 1) tot += __shfl_xor_sync(0xFFFFFFFFu, tot, o);
+                uint32_t cutoff = tot >> 10, nu = 0;
+                for (int i = 0; i < 8; i++) nu += (s_fl[lane * 8 + i] > cutoff);
+                for (int o = 16; o; o >>= 1) nu += __shfl_xor_sync(0xFFFFFFFFu, nu, o);
+                new_min = choose_min_match_len(nu, depth);
+                next_recalc += min(unit_n - next_recalc, rp - bb);
+                if (new_min != min_len) changed = true;
+            } else if (event == 2) {
+                const uint32_t block_length = rp - bb;
+                if (num_obs > 0) {
+                    uint32_t d = 0;
+                    if (lane < 10) {
+                        const uint32_t expected = s_obs[lane] * num_new_obs, actual = s_nobs[lane] * num_obs;
+                        d = actual > expected ? actual - expected : expected - actual;
+                    }
+                    for (int o = 16; o; o >>= 1) d += __shfl_xor_sync(0xFFFFFFFFu, d, o);
+                    const uint32_t num_items = num_obs + num_new_obs;
+                    uint32_t cutoff = num_new_obs * 200 / 512 * num_obs;
+                    if (block_length < 10000 && num_items < 8192) cutoff += (uint32_t)((uint64_t)cutoff * (8192 - num_items) / 8192);
+                    if (d + (block_length / 4096) * num_obs >= cutoff) end_block = true;
+                }
+                if (!end_block) {
+                    if (lane < 10) { s_obs[lane] += s_nobs[lane]; s_nobs[lane] = 0; }
+                    num_obs += num_new_obs; num_new_obs = 0;
+                }
+                __syncwarp();
+            } else if (event == 3) end_block = true;
+            if (end_block && rp < unit_n) {
+                // a new DEFLATE block starts at rp: fresh statistics, calculate_min_match_len over its first <= 4096 bytes
+                bb = rp; next_recalc = bb + min(unit_n - bb, 10000u);
+                num_obs = 0; num_new_obs = 0; nmatch = 0;
+                for (int i = 0; i < 8; i++) s_fl[lane * 8 + i] = 0;
+                if (lane < 10) { s_obs[lane] = 0; s_nobs[lane] = 0; }
+                const uint32_t mbe = (unit_n - bb < (uint32_t)kSoftMaxBlockLength + (uint32_t)kMinBlockLength) ? unit_n : bb + (uint32_t)kSoftMaxBlockLength;
+                new_min = 3;
+                if (mbe - bb >= 512) {
+                    const uint8_t *ub = g.in + (size_t)sb.u * g.in_stride;
+                    const uint32_t span = min(mbe - bb, 4096u);
+                    uint32_t used[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                    for (uint32_t i = lane; i < span; i += 32) { const uint32_t c = ub[bb + i]; used[c >> 5] |= 1u << (c & 31); }
+                    uint32_t nu = 0;
+                    for (int w = 0; w < 8; w++) { uint32_t v = used[w]; for (int o = 16; o; o >>= 1) v |= __shfl_xor_sync(0xFFFFFFFFu, v, o); nu += __popc(v); }
+                    new_min = choose_min_match_len(nu, depth);
+                }
+                __syncwarp();
+                if (new_min != min_len) changed = true;
+            }
+        }
+        if (lane == 0) { s_chg[0] = changed ? 1u : 0u; s_chg[1] = rt; s_chg[2] = rp; s_chg[3] = new_min; }
+    }
+    __syncthreads();
+    if (s_chg[0]) {
+        // min_len changes at unit position s_chg[2] (token s_chg[1]): what was parsed behind it is void
+        tok_run = s_chg[1]; min_len = s_chg[3];
+        const uint32_t newE = s_chg[2] - sb.h;
+        if (newE >= ne) { carry = s_chg[2]; break; }               // the change falls on the sub-unit's end: nothing to redo here
+        E = newE; epoch_entry = newE;
+        continue;
+    }
+    carry = sub_end;
+    break;
+    }   // epochs
     }
     __syncthreads();
     if (tokens && tid == 0) unit_ntok[u] = s_over ? 0xFFFFFFFFu : tok_run;
@@ -1390,7 +1517,7 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
     } else if (dl > 0) {
         uint32_t p = dict;           // parser position (warp 0 is authoritative)
         uint32_t next_recalc = 0, min_len = 3;
-        uint32_t tcur = 0, assumed_min_len = 0;   // tokens mode (kSparse == 2): next token of k_smatch's list, the min_len it parsed with
+        uint32_t tcur = 0;                        // tokens mode (kSparse == 2): next token of k_smatch's list
         while (true) {
             // ---------------- block start (all threads) ----------------
             if (tid == 0) S.blk_begin = p;
@@ -1431,11 +1558,12 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
                 bool end_block = false;
                 if (kSparse == 2) {
                     // ---- replay: the tokens of the true parse are already in tok[] (k_smatch, in order, iteration ends
-                    // flagged); what is left of the parser is its events — min_len re-calculation, block-split checks,
-                    // sequence-store limit — evaluated 32 tokens at a time exactly where the sequential parser would.
+                    // flagged); what is left of the parser here is where its DEFLATE blocks end — block-split checks, the
+                    // sequence-store limit, SOFT_MAX_BLOCK_LENGTH — evaluated 32 tokens at a time exactly where the sequential
+                    // parser would.
+                    // (min_len and its re-calculation schedule only steer the parser: k_smatch has replayed them already)
                     const uint32_t total = unit_ntok[u];
-                    if (assumed_min_len == 0) assumed_min_len = min_len;
-                    bool miss = (total == 0xFFFFFFFFu) || (min_len != assumed_min_len);   // k_smatch parsed the whole unit with one min_len
+                    bool miss = (total == 0xFFFFFFFFu);                                  // k_smatch gave up on this unit
                     if (lane == 0) S.tok0 = tcur;
                     uint32_t tpre = (!miss && tcur + lane < total) ? tok[tcur + lane] : 0u;      // this window's token, loaded one window ahead
                     do {
@@ -1450,8 +1578,6 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
 #pragma unroll
                         for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, pincl, d); if (lane >= (uint32_t)d) pincl += v; }
                         const uint32_t q = p + pincl - len, e_l = p + pincl;
-                        const uint32_t prev_ends = __shfl_up_sync(0xFFFFFFFFu, (uint32_t)ends_iter, 1);
-                        const bool starts_iter = lane == 0 ? (in_h == 0) : (prev_ends != 0);
                         const uint32_t vis = __ballot_sync(0xFFFFFFFFu, valid);
                         if (vis == 0) { miss = true; break; }                 // the list ended before the data did
                         const uint32_t incl = lane + 1;                       // tokens up to and including mine
@@ -1461,19 +1587,16 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
                         int event = 0;
                         const uint32_t mmask = __ballot_sync(0xFFFFFFFFu, valid && isM);
                         const bool may_check = (num_new_obs + 32 >= (uint32_t)kObsPerCheck) && (next_p - bb >= (uint32_t)kMinBlockLength) && (n - p > (uint32_t)kMinBlockLength);
-                        const bool may_recalc = (mode != 0) && (next_p > next_recalc);
                         const bool may_seq = nmatch + 32 >= seq_limit;
                         const bool may_max = next_p >= max_block_end && max_block_end < n;       // SOFT_MAX_BLOCK_LENGTH reached inside this window
-                        if (may_check || may_recalc || may_seq || may_max) {
-                            const uint32_t rmask = may_recalc ? __ballot_sync(0xFFFFFFFFu, valid && starts_iter && q >= next_recalc) : 0u;
+                        if (may_check || may_seq || may_max) {
                             const uint32_t cmask = __ballot_sync(0xFFFFFFFFu, valid && ends_iter && (num_new_obs + incl >= (uint32_t)kObsPerCheck) &&
                                                                              (e_l - bb >= (uint32_t)kMinBlockLength) && (n - e_l >= (uint32_t)kMinBlockLength));
                             const uint32_t mincl = __popc(mmask & (lane == 31 ? 0xFFFFFFFFu : ((2u << lane) - 1)));
                             // the loop condition `p < max_block_end` and the sequence-store limit both end the block after the iteration
                             const uint32_t smask = __ballot_sync(0xFFFFFFFFu, valid && ends_iter && ((nmatch + mincl >= seq_limit) || e_l >= max_block_end));
-                            const int Lr = rmask ? __ffs(rmask) - 1 : 64, Lc = cmask ? __ffs(cmask) - 1 : 64, Ls = smask ? __ffs(smask) - 1 : 64;
-                            if (Lr <= Lc && Lr <= Ls && Lr < 64) { event = 1; commit_mask = vis & ((1u << Lr) - 1); next_p = __shfl_sync(0xFFFFFFFFu, q, Lr); next_h = 0; }
-                            else if (Ls <= Lc && Ls < 64) { event = 3; commit_mask = vis & (Ls == 31 ? 0xFFFFFFFFu : ((2u << Ls) - 1)); next_p = __shfl_sync(0xFFFFFFFFu, e_l, Ls); next_h = 0; }
+                            const int Lc = cmask ? __ffs(cmask) - 1 : 64, Ls = smask ? __ffs(smask) - 1 : 64;
+                            if (Ls <= Lc && Ls < 64) { event = 3; commit_mask = vis & (Ls == 31 ? 0xFFFFFFFFu : ((2u << Ls) - 1)); next_p = __shfl_sync(0xFFFFFFFFu, e_l, Ls); next_h = 0; }
                             else if (Lc < 64) { event = 2; commit_mask = vis & (Lc == 31 ? 0xFFFFFFFFu : ((2u << Lc) - 1)); next_p = __shfl_sync(0xFFFFFFFFu, e_l, Lc); next_h = 0; }
                         }
                         if ((commit_mask >> lane) & 1u) {
@@ -1494,17 +1617,7 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
                         in_h = next_h;
                         p = next_p;
                         __syncwarp();
-                        if (event == 1) {
-                            uint32_t tot = 0;
-                            for (int i = 0; i < 8; i++) tot += S.fl[lane * 8 + i];
-                            for (int o = 16; o; o >>= 1) tot += __shfl_xor_sync(0xFFFFFFFFu, tot, o);
-                            uint32_t cutoff = tot >> 10, nu = 0;
-                            for (int i = 0; i < 8; i++) nu += (S.fl[lane * 8 + i] > cutoff);
-                            for (int o = 16; o; o >>= 1) nu += __shfl_xor_sync(0xFFFFFFFFu, nu, o);
-                            min_len = choose_min_match_len(nu, depth);
-                            next_recalc += min(n - next_recalc, p - bb);
-                            if (min_len != assumed_min_len) miss = true;        // the tokens behind this point were parsed with another min_len
-                        } else if (event == 2) {
+                        if (event == 2) {
                             uint32_t block_length = p - bb;
                             if (num_obs > 0) {
                                 uint32_t d = 0;

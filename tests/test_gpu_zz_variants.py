@@ -80,7 +80,7 @@ def test_sparse_tokens_and_replay_is_bit_identical_on_gpu(monkeypatch, text_corp
         assert got == oracle.compress_stream(BGZF, level, 65280, [data]), level
         assert units == 16 and missed == 0, (level, units, missed)
     for data, want_missed in ((bytes(200000), 0), (synth.low_entropy(300000), None), (synth.fastq(200000), None), (b"", 0),
-                              (text_corpus[:65280] + mixed + text_corpus[:30000], 1)):
+                              (text_corpus[:65280] + mixed + text_corpus[:30000], 0)):        # min_len changes: a new epoch, no fallback
         got, (units, missed) = _encode("GZPB_SPARSE", monkeypatch, BGZF, 6, 65280, data, "split+link+smatch+replay", "2")
         assert got == oracle.compress_stream(BGZF, 6, 65280, [data]), len(data)
         if want_missed is not None:
