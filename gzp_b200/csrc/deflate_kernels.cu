@@ -1577,7 +1577,7 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
                         uint32_t pincl = len;
 #pragma unroll
                         for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, pincl, d); if (lane >= (uint32_t)d) pincl += v; }
-                        const uint32_t q = p + pincl - len, e_l = p + pincl;
+                        const uint32_t e_l = p + pincl;
                         const uint32_t vis = __ballot_sync(0xFFFFFFFFu, valid);
                         if (vis == 0) { miss = true; break; }                 // the list ended before the data did
                         const uint32_t incl = lane + 1;                       // tokens up to and including mine
