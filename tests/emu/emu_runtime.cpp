@@ -47,6 +47,7 @@ struct Fiber {
     void *sp = nullptr;
     uint8_t *stack = nullptr;
     bool done = false;
+    long bar_wait = -1;      // generation of the CTA barrier this fiber sleeps on (-1 = runnable): the scheduler skips sleepers
 };
 
 struct WarpState {
@@ -137,7 +138,9 @@ void syncthreads()
     g_bar_count++;
     g_progress = true;
     release_barrier_if_complete();
-    while (g_bar_gen == gen) yield_to_scheduler();
+    Fiber &f = g_fibers[g_self->linear];
+    while (g_bar_gen == gen) { f.bar_wait = (long)gen; yield_to_scheduler(); }
+    f.bar_wait = -1;
 }
 
 uint64_t collective(int op, unsigned mask, uint64_t val, uint64_t *all32)
@@ -206,7 +209,7 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> &bod
                     f.self.bid = uint3{bx, by, bz};
                     f.self.bdim = uint3{block.x, block.y, block.z};
                     f.self.gdim = uint3{grid.x, grid.y, grid.z};
-                    f.self.linear = t; f.self.lane = t & 31; f.self.warp = t >> 5;
+                    f.self.linear = t; f.self.lane = t & 31; f.self.warp = t >> 5; f.bar_wait = -1;
                     g_warps[t >> 5].exist |= 1u << (t & 31);
                     prepare(f);
                 }
@@ -220,6 +223,7 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> &bod
                         else if (sched == 2) { if (i == 0) rot = (unsigned)(sched_rng() % n); t = (i + rot) % n; if (rot & 1) t = n - 1 - t; }
                         Fiber &f = g_fibers[t];
                         if (f.done) continue;
+                        if (f.bar_wait >= 0 && (unsigned)f.bar_wait == g_bar_gen) continue;   // still asleep on __syncthreads
                         g_self = &f.self;
                         gzpb_emu_switch(&g_sched_sp, &f.sp);
                     }
