@@ -30,6 +30,8 @@ _SIGS = {
     "gzpb_encode_batch": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(BlockIn), C.POINTER(BlockOut)]),
     "gzpb_encode_stream": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t,
                                      C.POINTER(C.c_size_t)]),
+    "gzpb_encode_stream_multi": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t,
+                                           C.POINTER(C.c_size_t)]),
     "gzpb_encode_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_void_p]),
     "gzpb_encode_capacity": (C.c_size_t, [C.c_int, C.c_size_t]),

@@ -2165,7 +2165,7 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
 // =============================================================================
 __global__ void __launch_bounds__(1024)
 k_scan(const uint32_t *__restrict__ out_len, uint64_t *__restrict__ offsets, uint32_t nunits,
-       const uint64_t *__restrict__ base_ptr, uint64_t cap, int32_t *__restrict__ overflow)
+       const uint64_t *__restrict__ base_ptr, uint64_t cap, int32_t *__restrict__ overflow, uint64_t *end_mirror)
 {
     __shared__ uint64_t part[1024];
     const uint32_t tid = threadIdx.x;
@@ -2179,6 +2179,7 @@ k_scan(const uint32_t *__restrict__ out_len, uint64_t *__restrict__ offsets, uin
         uint64_t acc = base;
         for (int i = 0; i < 1024; i++) { uint64_t v = part[i]; part[i] = acc; acc += v; }
         offsets[nunits] = acc;
+        if (end_mirror) { *(volatile uint64_t *)end_mirror = acc; __threadfence_system(); }
         *overflow = (acc > cap) ? 1 : 0;
     }
     __syncthreads();
@@ -2451,7 +2452,7 @@ cudaError_t launch_pack(const DeflateBatch &b, cudaStream_t st)
 {
     if (b.nunits == 0) return cudaSuccess;
     if (b.timer) b.timer->start(KT_GATHER, st);
-    GZPB_LAUNCH(k_scan, 1, 1024, 0, st, b.out_len, b.offsets, b.nunits, b.base_ptr, b.packed_cap, b.overflow);
+    GZPB_LAUNCH(k_scan, 1, 1024, 0, st, b.out_len, b.offsets, b.nunits, b.base_ptr, b.packed_cap, b.overflow, b.end_mirror);
     GZPB_LAUNCH(k_gather, b.nunits, 256, 0, st, b.out, b.out_len, b.offsets, b.packed, b.overflow, b.out_stride);
     DBG_SYNC("k_scan+k_gather");
     if (b.timer) b.timer->stop(st);

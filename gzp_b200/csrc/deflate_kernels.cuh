@@ -56,7 +56,8 @@ struct DeflateBatch {
     uint64_t *offsets;        // nunits + 1 (exclusive scan of sizes; [nunits] = total)
     uint8_t *packed;          // compacted stream (device memory or mapped pinned host memory)
     uint64_t packed_cap;      // bytes available at `packed`
-    const uint64_t *base_ptr; // device address holding this batch's first offset (NULL = 0)
+    const uint64_t *base_ptr; // device-visible address holding this batch's first offset (NULL = 0)
+    uint64_t *end_mirror;     // optional second copy of offsets[nunits] (mapped pinned host memory: the next batch of a multi-device stream reads its base there)
     int32_t *overflow;        // set to 1 by k_scan when the batch would exceed packed_cap
     KernelTimer *timer;       // optional
     uint32_t in_stride, m_stride, tok_stride, out_stride;   // per-unit strides (bytes / entries / tokens / bytes)

@@ -47,6 +47,7 @@ struct Lane {
     uint8_t *d_out = nullptr, *d_packed = nullptr;
     int32_t *d_status = nullptr, *d_overflow = nullptr;
     uint32_t *d_comb = nullptr, *h_comb = nullptr;   // batch-combined check {sum, len lo, len hi}
+    uint64_t *h_end = nullptr;                       // mapped pinned: stream offset behind this lane's batch (the offset chain of a multi-device stream)
     // pinned host
     uint8_t *h_in = nullptr, *h_packed = nullptr;
     uint32_t *h_len = nullptr, *h_dict = nullptr, *h_flags = nullptr, *h_crc = nullptr;
@@ -69,6 +70,7 @@ struct gzpb_ctx {
     bool match_v2 = false;                         // GZPB_MATCH_V2=1: k_group + k_match2 instead of k_link(hash4) + k_match
     uint32_t cpu = 1;                              // gather entries per unit (Snap: 64 KiB chunks per block)
     Lane lanes[kLanes];
+    uint64_t *d_base0 = nullptr, *h_base0 = nullptr; // first stream offset of a gzpb_encode_stream call: device copy / mapped pinned copy
     bool scratch_only = false;
     KernelTimer timer;
     bool profiling = false;
@@ -218,7 +220,7 @@ static int lane_alloc(gzpb_ctx *c, Lane &L, bool with_io)
         CK(hmalloc(&L.h_offsets, E + 1));
         CK(hmalloc(&L.h_status, U));
         CK(hmalloc(&L.h_overflow, 1));
-        CK(hmalloc(&L.h_packed, E * c->out_stride));
+        CK(hmalloc(&L.h_end, 2));
         memset(L.h_status, 0, U * sizeof(int32_t));
         memset(L.h_crc, 0, U * sizeof(uint32_t));
         return GZPB_OK;
@@ -265,7 +267,7 @@ static int lane_alloc(gzpb_ctx *c, Lane &L, bool with_io)
         CK(hmalloc(&L.h_offsets, U + 1));
         CK(hmalloc(&L.h_status, U));
         CK(hmalloc(&L.h_overflow, 1));
-        CK(hmalloc(&L.h_packed, U * c->out_stride));
+        CK(hmalloc(&L.h_end, 2));
     }
     return GZPB_OK;
 }
@@ -276,7 +278,7 @@ static void lane_free(Lane &L)
     cudaFree(L.d_slists); cudaFree(L.d_sidx); cudaFree(L.d_sntok); cudaFree(L.d_gidx); cudaFree(L.d_gocc); cudaFree(L.d_next4); cudaFree(L.d_prev3); cudaFree(L.d_order); cudaFree(L.d_clen); cudaFree(L.d_mtab2); cudaFree(L.d_lists); cudaFree(L.d_list_start); cudaFree(L.d_mtab); cudaFree(L.d_offsets); cudaFree(L.d_out); cudaFree(L.d_packed);
     cudaFree(L.d_status); cudaFree(L.d_overflow); cudaFree(L.d_comb); cudaFreeHost(L.h_comb);
     cudaFreeHost(L.h_in); cudaFreeHost(L.h_packed); cudaFreeHost(L.h_len); cudaFreeHost(L.h_dict); cudaFreeHost(L.h_flags); cudaFreeHost(L.h_crc);
-    cudaFreeHost(L.h_offsets); cudaFreeHost(L.h_status); cudaFreeHost(L.h_overflow);
+    cudaFreeHost(L.h_offsets); cudaFreeHost(L.h_status); cudaFreeHost(L.h_overflow); cudaFreeHost(L.h_end);
     if (L.ev_scan) cudaEventDestroy(L.ev_scan);
     if (L.ev_done) cudaEventDestroy(L.ev_done);
     if (L.st) cudaStreamDestroy(L.st);
@@ -338,6 +340,7 @@ extern "C" int gzpb_create(gzpb_ctx **out, int device, int format, int level, si
         int r = lane_alloc(c, c->lanes[i], true);
         if (r != GZPB_OK) { gzpb_destroy(c); return r; }
     }
+    if (cudaMalloc((void **)&c->d_base0, sizeof(uint64_t)) != cudaSuccess || hmalloc(&c->h_base0, 2) != cudaSuccess) { gzpb_destroy(c); return GZPB_ENOMEM; }
     CK(cudaDeviceSynchronize());
     *out = c;
     return GZPB_OK;
@@ -349,6 +352,7 @@ extern "C" void gzpb_destroy(gzpb_ctx *c)
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     for (int i = 0; i < kLanes; i++) lane_free(c->lanes[i]);
+    cudaFree(c->d_base0); cudaFreeHost(c->h_base0);
     c->timer.collect();
     for (auto e : c->timer.pool) cudaEventDestroy(e);
     delete c;
@@ -433,7 +437,7 @@ static void fill_batch(gzpb_ctx *c, Lane &L, DeflateBatch &b, size_t n)
     b.spu = c->spu; b.seg = c->seg; b.check_kind = c->check_kind; b.sparse = c->sparse; b.sparse_chunk = c->sparse_chunk; b.slists = L.d_slists; b.sidx = L.d_sidx; b.sntok = L.d_sntok;
     b.next4 = L.d_next4; b.prev3 = L.d_prev3; b.clen = L.d_clen; b.order = L.d_order; b.mtab = L.d_mtab; b.mtab2 = L.d_mtab2; b.gidx = L.d_gidx; b.gocc = L.d_gocc; b.lists = L.d_lists; b.list_start = L.d_list_start; b.crc = L.d_crc; b.tokens = L.d_tokens;
     b.out = L.d_out; b.out_len = L.d_out_len; b.status = L.d_status; b.offsets = L.d_offsets;
-    b.packed = nullptr; b.packed_cap = 0; b.base_ptr = nullptr; b.overflow = L.d_overflow;
+    b.packed = nullptr; b.packed_cap = 0; b.base_ptr = nullptr; b.end_mirror = nullptr; b.overflow = L.d_overflow;
     b.timer = c->profiling ? &c->timer : nullptr;
 }
 
@@ -545,14 +549,24 @@ static int lane_launch(gzpb_ctx *c, Lane &L, const UnitRef *units, size_t n, boo
     return GZPB_OK;
 }
 
-// scan + gather into `packed` (device-visible), chained after `prev` lane's scan
-static int lane_pack(gzpb_ctx *c, Lane &L, uint8_t *packed, uint64_t cap, const uint64_t *base_ptr, Lane *prev)
+// The lane's own pinned output buffer (ticket / writer / pageable-output paths).  Allocated on first use: the
+// zero-copy stream path gathers straight into the caller's pinned buffer and never needs it.
+static int lane_host_packed(gzpb_ctx *c, Lane &L)
+{
+    if (!L.h_packed) CK(hmalloc(&L.h_packed, c->max_units * c->cpu * (size_t)c->out_stride));
+    return GZPB_OK;
+}
+
+// scan + gather into `packed` (device-visible), chained after `prev` lane's scan (`prev` may belong to another
+// device: the event wait is cross-device and `base_ptr` then points into mapped pinned host memory, where the
+// previous lane's k_scan mirrored its end offset through `end_mirror`)
+static int lane_pack(gzpb_ctx *c, Lane &L, uint8_t *packed, uint64_t cap, const uint64_t *base_ptr, Lane *prev, uint64_t *end_mirror = nullptr)
 {
     DeflateBatch b;
     fill_batch(c, L, b, L.nunits);
     const size_t entries = L.nunits * c->cpu;
     b.nunits = (uint32_t)entries;
-    b.packed = packed; b.packed_cap = cap; b.base_ptr = base_ptr;
+    b.packed = packed; b.packed_cap = cap; b.base_ptr = base_ptr; b.end_mirror = end_mirror;
     if (prev) CK(cudaStreamWaitEvent(L.st, prev->ev_scan, 0));
     CK(launch_pack(b, L.st));
     CK(cudaEventRecord(L.ev_scan, L.st));
@@ -627,7 +641,9 @@ extern "C" int gzpb_submit(gzpb_ctx *c, size_t n, const gzpb_block_in *in, gzpb_
         units[i] = UnitRef{(const uint8_t *)b.ptr, b.len, (const uint8_t *)b.dict, dl, b.is_last};
         if (pinned && ((b.len && !is_pinned(b.ptr)) || (dl && !is_pinned(b.dict)))) pinned = false;
     }
-    int rc = lane_launch(c, L, units.data(), n, pinned);
+    int rc = lane_host_packed(c, L);
+    if (rc != GZPB_OK) return rc;
+    rc = lane_launch(c, L, units.data(), n, pinned);
     if (rc != GZPB_OK) return rc;
     rc = lane_pack(c, L, L.h_packed, (uint64_t)c->max_units * c->cpu * c->out_stride, nullptr, nullptr);
     if (rc != GZPB_OK) return rc;
@@ -676,63 +692,81 @@ extern "C" int gzpb_encode_batch(gzpb_ctx *c, size_t n, const gzpb_block_in *in,
     return rc;
 }
 
-extern "C" int gzpb_encode_stream(gzpb_ctx *c, const void *in_v, size_t in_len, size_t buffer_size, void *out_v,
-                                  size_t out_cap, size_t *out_len)
+// ParCompress end to end over an in-memory input, on one or several GPUs.  Device batches of max_units
+// consecutive blocks are dealt round-robin: batch k runs on context k % G, lane (k / G) % kLanes (SURVEY §8e —
+// blocks are independent; the dictionary of a batch's first block comes from the host input, so there is no
+// device-to-device traffic).  With pinned `out` the ordered writer (par/compress.rs:303-313) is the offset
+// chain: every batch's k_scan waits for the previous batch's k_scan (an event wait, cross-device when G > 1),
+// takes its first stream offset from where that one ended and k_gather writes the blocks at their final
+// stream position in the caller's buffer.  One host thread drives all devices: per batch it issues ~25
+// asynchronous calls and the retire reads a few status words.
+static int encode_stream_impl(gzpb_ctx *const *cs, size_t G, const void *in_v, size_t in_len, size_t buffer_size, void *out_v,
+                              size_t out_cap, size_t *out_len)
 {
-    if (!c || !out_v || !out_len || (in_len && !in_v)) return GZPB_EINVAL;
-    if (buffer_size == 0) buffer_size = c->max_block_bytes;
+    gzpb_ctx *c0 = cs[0];
+    if (buffer_size == 0) buffer_size = c0->max_block_bytes;
     if (buffer_size < GZPB_DICT_SIZE) return GZPB_EBUFFERSIZE;   // par/compress.rs:68-74
-    if (buffer_size > c->max_block_bytes) return GZPB_EBUFFERSIZE;
-    if (!c->tickets.empty()) return GZPB_EAGAIN;
-    CK(cudaSetDevice(c->device));
+    for (size_t g = 0; g < G; g++) {
+        gzpb_ctx *c = cs[g];
+        if (!c || c->format != c0->format || c->level != c0->level || c->max_units != c0->max_units ||
+            c->max_block_bytes != c0->max_block_bytes)
+            return GZPB_EINVAL;
+        if (buffer_size > c->max_block_bytes) return GZPB_EBUFFERSIZE;
+        if (!c->tickets.empty()) return GZPB_EAGAIN;
+        for (size_t h = 0; h < g; h++) if (cs[h] == c) return GZPB_EINVAL;
+    }
+    const int format = c0->format;
+    const uint32_t cpu = c0->cpu;
     const uint8_t *in = (const uint8_t *)in_v;
     uint8_t *out = (uint8_t *)out_v;
-    const bool dict_fmt = gzpb_needs_dict(c->format);
+    const bool dict_fmt = gzpb_needs_dict(format);
     const bool in_pinned = in_len && is_pinned(in);
     const bool out_pinned = is_pinned(out);
 
     // ParCompress::write + finish: full blocks while MORE than buffer_size bytes remain,
     // then flush_last(true) — always at least one (possibly empty) is_last block.
-    size_t nblocks = 0;
-    { size_t rem = in_len; while (rem > buffer_size) { rem -= buffer_size; nblocks++; } nblocks++; }
+    size_t nblocks = (in_len > buffer_size) ? (in_len - 1) / buffer_size + 1 : 1;
 
     if (out_cap < 64) return GZPB_ECOMPRESS;
-    size_t pos_out = gzpb_header(c->format, c->level, out);
+    size_t pos_out = gzpb_header(format, c0->level, out);
     uint8_t *dev_out = nullptr;
+    CK(cudaSetDevice(c0->device));
     if (out_pinned) CK(cudaHostGetDevicePointer((void **)&dev_out, out, 0));
 
-    // device-side running offset lives in each lane's d_offsets[nunits]; batch 0 starts at the header size
-    uint64_t *d_base0 = nullptr;
-    CK(cudaMalloc((void **)&d_base0, sizeof(uint64_t)));
-    uint64_t base0 = out_pinned ? pos_out : 0;
-    CK(cudaMemcpy(d_base0, &base0, sizeof base0, cudaMemcpyHostToDevice));
+    // first stream offset: a device word for one GPU, a mapped pinned word (visible to every GPU) for several
+    const uint64_t base0 = out_pinned ? pos_out : 0;
+    const uint64_t *first_base;
+    if (G == 1) { CK(cudaMemcpy(c0->d_base0, &base0, sizeof base0, cudaMemcpyHostToDevice)); first_base = c0->d_base0; }
+    else { *c0->h_base0 = base0; first_base = c0->h_base0; }
 
-    struct Pending { size_t first, count; int lane; };
-    std::vector<Pending> pend;
+    struct Pending { size_t count; int dev, lane; };
+    std::deque<Pending> pend;
     std::vector<UnitRef> units;
-    uint32_t run_sum = (c->format == GZPB_ZLIB) ? 1u : 0u, run_amount = 0;
+    uint32_t run_sum = (format == GZPB_ZLIB) ? 1u : 0u, run_amount = 0;
     int rc = GZPB_OK;
     Lane *prev = nullptr;
-    const uint64_t *prev_end = d_base0;
+    const uint64_t *prev_end = first_base;
 
     auto retire = [&](const Pending &p) -> int {
+        gzpb_ctx *c = cs[p.dev];
         Lane &L = c->lanes[p.lane];
         int r = lane_wait(c, L);
         if (r != GZPB_OK) return r;
         if (*L.h_overflow) return GZPB_ECOMPRESS;
-        for (size_t i = 0; i < p.count; i++)
-            if (L.h_status[i] != GZPB_OK) return L.h_status[i];
-        if (c->format == GZPB_GZIP || c->format == GZPB_ZLIB) {
+        if (format != GZPB_SNAP)
+            for (size_t i = 0; i < p.count; i++)
+                if (L.h_status[i] != GZPB_OK) return L.h_status[i];
+        if (format == GZPB_GZIP || format == GZPB_ZLIB) {
             // k_check_combine folded the batch; fold the batch into the running check (par/compress.rs:308)
             const uint64_t blen = (uint64_t)L.h_comb[1] | ((uint64_t)L.h_comb[2] << 32);
-            if (blen) run_sum = c->format == GZPB_GZIP ? gzpb_crc32_combine(run_sum, L.h_comb[0], blen)
-                                                       : gzpb_adler32_combine(run_sum, L.h_comb[0], blen);
+            if (blen) run_sum = format == GZPB_GZIP ? gzpb_crc32_combine(run_sum, L.h_comb[0], blen)
+                                                    : gzpb_adler32_combine(run_sum, L.h_comb[0], blen);
             run_amount += (uint32_t)blen;
         }
         if (out_pinned) {
-            pos_out = (size_t)L.h_offsets[p.count * c->cpu];
+            pos_out = (size_t)L.h_offsets[p.count * cpu];
         } else {
-            size_t len = (size_t)L.h_offsets[p.count * c->cpu];
+            size_t len = (size_t)L.h_offsets[p.count * cpu];
             if (pos_out + len > out_cap) return GZPB_ECOMPRESS;
             memcpy(out + pos_out, L.h_packed, len);
             pos_out += len;
@@ -740,15 +774,15 @@ extern "C" int gzpb_encode_stream(gzpb_ctx *c, const void *in_v, size_t in_len, 
         return GZPB_OK;
     };
 
-    size_t done = 0;
-    int li = 0;
+    size_t done = 0, k = 0;
     while (done < nblocks && rc == GZPB_OK) {
-        size_t cnt = std::min(c->max_units, nblocks - done);
+        const int dev = (int)(k % G), li = (int)((k / G) % kLanes);
+        gzpb_ctx *c = cs[dev];
+        const size_t cnt = std::min(c->max_units, nblocks - done);
         Lane &L = c->lanes[li];
-        if (L.busy) {
-            rc = retire(pend.front()); pend.erase(pend.begin());
-            if (rc != GZPB_OK) break;
-        }
+        while (L.busy && rc == GZPB_OK) { rc = retire(pend.front()); pend.pop_front(); }   // in-order drain up to this lane's batch
+        if (rc != GZPB_OK) break;
+        if (cudaSetDevice(c->device) != cudaSuccess) { rc = GZPB_ECUDA; break; }
         units.resize(cnt);
         for (size_t i = 0; i < cnt; i++) {
             size_t bi = done + i, b0 = bi * buffer_size;
@@ -758,27 +792,45 @@ extern "C" int gzpb_encode_stream(gzpb_ctx *c, const void *in_v, size_t in_len, 
         }
         rc = lane_launch(c, L, units.data(), cnt, in_pinned);
         if (rc != GZPB_OK) break;
-        if (out_pinned) rc = lane_pack(c, L, dev_out, out_cap, prev_end, prev);
-        else rc = lane_pack(c, L, L.h_packed, (uint64_t)c->max_units * c->cpu * c->out_stride, nullptr, nullptr);
+        if (out_pinned) rc = lane_pack(c, L, dev_out, out_cap, prev_end, prev, G > 1 ? L.h_end : nullptr);
+        else { rc = lane_host_packed(c, L); if (rc == GZPB_OK) rc = lane_pack(c, L, L.h_packed, (uint64_t)c->max_units * cpu * c->out_stride, nullptr, nullptr); }
         if (rc != GZPB_OK) break;
-        prev = &L; prev_end = L.d_offsets + cnt * c->cpu;
-        pend.push_back(Pending{done, cnt, li});
-        done += cnt;
-        li = (li + 1) % kLanes;
+        prev = &L; prev_end = (G > 1) ? L.h_end : L.d_offsets + cnt * cpu;
+        pend.push_back(Pending{cnt, dev, li});
+        done += cnt; k++;
     }
-    for (auto &p : pend) {
-        int r = retire(p);
+    while (!pend.empty()) {
+        int r = retire(pend.front()); pend.pop_front();
         if (rc == GZPB_OK) rc = r;
     }
-    cudaFree(d_base0);
-    if (rc != GZPB_OK) { for (int i = 0; i < kLanes; i++) c->lanes[i].busy = false; cudaDeviceSynchronize(); return rc; }
+    if (rc != GZPB_OK) {                                          // leave no batch half-finished behind an error
+        for (size_t g = 0; g < G; g++) {
+            cudaSetDevice(cs[g]->device); cudaDeviceSynchronize();
+            for (int i = 0; i < kLanes; i++) cs[g]->lanes[i].busy = false;
+        }
+        return rc;
+    }
     uint8_t foot[16];
-    size_t fl = gzpb_footer(c->format, run_sum, run_amount, foot);
+    size_t fl = gzpb_footer(format, run_sum, run_amount, foot);
     if (pos_out + fl > out_cap) return GZPB_ECOMPRESS;
     memcpy(out + pos_out, foot, fl);
     pos_out += fl;
     *out_len = pos_out;
     return GZPB_OK;
+}
+
+extern "C" int gzpb_encode_stream(gzpb_ctx *c, const void *in_v, size_t in_len, size_t buffer_size, void *out_v,
+                                  size_t out_cap, size_t *out_len)
+{
+    if (!c || !out_v || !out_len || (in_len && !in_v)) return GZPB_EINVAL;
+    return encode_stream_impl(&c, 1, in_v, in_len, buffer_size, out_v, out_cap, out_len);
+}
+
+extern "C" int gzpb_encode_stream_multi(gzpb_ctx *const *ctxs, size_t nctx, const void *in_v, size_t in_len, size_t buffer_size,
+                                        void *out_v, size_t out_cap, size_t *out_len)
+{
+    if (!ctxs || nctx == 0 || nctx > 64 || !out_v || !out_len || (in_len && !in_v)) return GZPB_EINVAL;
+    return encode_stream_impl(ctxs, nctx, in_v, in_len, buffer_size, out_v, out_cap, out_len);
 }
 
 
@@ -892,7 +944,8 @@ static int writer_submit(gzpb_writer *w)
     }
     cudaGetLastError();
     if (cudaSetDevice(c->device) != cudaSuccess) return w->error = GZPB_ECUDA;
-    r = lane_launch(c, L, w->msgs.data(), w->msgs.size(), true);
+    r = lane_host_packed(c, L);
+    if (r == GZPB_OK) r = lane_launch(c, L, w->msgs.data(), w->msgs.size(), true);
     if (r == GZPB_OK) r = lane_pack(c, L, L.h_packed, (uint64_t)c->max_units * c->cpu * c->out_stride, nullptr, nullptr);
     if (r != GZPB_OK) return w->error = r;
     w->flights.push_back(gzpb_writer::Flight{dev, lane, w->msgs.size()});

@@ -115,6 +115,16 @@ int gzpb_poll(gzpb_ctx *ctx, gzpb_ticket ticket, int wait);
 int gzpb_encode_stream(gzpb_ctx *ctx, const void *in, size_t in_len, size_t buffer_size, void *out,
                        size_t out_cap, size_t *out_len);
 
+/* The same stream over several GPUs of one box: device batches of max_blocks_in_flight consecutive
+ * blocks are dealt round-robin to the contexts (one per GPU, all created with the same format, level and sizes);
+ * blocks are independent and a batch's first dictionary comes from the host input, so no data moves between GPUs.
+ * The ordered writer thread of src/par/compress.rs:303-313 is an offset chain: with pinned `in` / `out`
+ * (gzpb_host_alloc) every batch's scan waits for the previous batch's scan — on whichever GPU it ran — and its
+ * blocks land at their final stream position in `out` by DMA.  Byte-identical to gzpb_encode_stream on one GPU.
+ * One calling thread drives all contexts. */
+int gzpb_encode_stream_multi(gzpb_ctx *const *ctxs, size_t nctx, const void *in, size_t in_len, size_t buffer_size,
+                             void *out, size_t out_cap, size_t *out_len);
+
 /* Incremental writer = `ParCompress<F, W>` as a C object (src/par/compress.rs:221-233): the caller
  * `write`s bytes, the writer cuts blocks with the reference's semantics (strict '>' hold-back :415,
  * 32 KiB dictionary carry :419-423, `flush` = flush_last(false) :466-468 incl. the empty block,

@@ -171,6 +171,7 @@ static inline void __trap() { gzpb_emu::trap("__trap()"); }
 static inline void __nanosleep(unsigned) { gzpb_emu::wait_yield(); }
 static inline void __threadfence() {}
 static inline void __threadfence_block() {}
+static inline void __threadfence_system() {}
 
 // ---- atomics (one OS thread: plain read-modify-write) ---------------------------
 #define EMU_ATOMIC(name, T, expr) static inline T name(T *p, T v) { T old = *p; *p = (expr); return old; }

@@ -788,3 +788,43 @@ def test_emu_sparse_tokens_long_units(monkeypatch):
                               (oracle.GZIP, 9, 262144, synth.fastq(60000) + TEXT[:230000])):             # BASELINE configs[4] shape: lazy2 on long units
         units, missed = _run_sparse(fmt, level, bs, d)
         assert units >= 2 and missed == 0, (fmt, level, bs)
+
+
+def test_emu_encode_stream_multi_devices(monkeypatch):
+    """gzpb_encode_stream_multi: ONE ordered stream whose device batches are dealt round-robin over three (emulated)
+    GPUs — the offset chain crosses devices through mapped pinned memory — is byte-identical to the single-device
+    stream and to the oracle, for pinned (zero-copy gather) and pageable buffers, all container families."""
+    import ctypes as C
+    monkeypatch.setenv("GZPB_EMU_DEVICES", "3")
+    L = emu.lib()
+    for fmt, lvl, bs, n in ((oracle.BGZF, 6, 65280, 1_300_000), (oracle.GZIP, 5, 32768, 700_000), (oracle.ZLIB, 4, 40000, 500_000),
+                            (oracle.MGZIP, 6, 65536, 600_000), (oracle.SNAP, 0, 65536, 900_000)):
+        data = (TEXT * (n // len(TEXT) + 1))[:n]
+        want = oracle.compress_stream(fmt, lvl, bs, [data])
+        hs = (C.c_void_p * 3)()
+        for d in range(3):
+            h = C.c_void_p()
+            assert L.gzpb_create(C.byref(h), d, fmt, lvl, bs, 2) == 0
+            hs[d] = h
+        cap = n + n // 4 + (1 << 16)
+        olen = C.c_size_t(0)
+        # pageable in / out
+        out = C.create_string_buffer(cap)
+        assert L.gzpb_encode_stream_multi(hs, 3, data, n, bs, out, cap, C.byref(olen)) == 0
+        assert out.raw[:olen.value] == want
+        # pinned in / out: zero-copy gather at the final stream offsets, chained across devices
+        pin_in, pin_out = L.gzpb_host_alloc(n), L.gzpb_host_alloc(cap)
+        C.memmove(pin_in, data, n)
+        assert L.gzpb_encode_stream_multi(hs, 3, pin_in, n, bs, pin_out, cap, C.byref(olen)) == 0
+        assert C.string_at(pin_out, olen.value) == want
+        # the same contexts, two of them; and one (= gzpb_encode_stream)
+        assert L.gzpb_encode_stream_multi(hs, 2, pin_in, n, bs, pin_out, cap, C.byref(olen)) == 0
+        assert C.string_at(pin_out, olen.value) == want
+        assert L.gzpb_encode_stream(hs[2], pin_in, n, bs, pin_out, cap, C.byref(olen)) == 0
+        assert C.string_at(pin_out, olen.value) == want
+        # a context listed twice is refused
+        dup = (C.c_void_p * 2)(hs[0], hs[0])
+        assert L.gzpb_encode_stream_multi(dup, 2, pin_in, n, bs, pin_out, cap, C.byref(olen)) == -9
+        L.gzpb_host_free(pin_in); L.gzpb_host_free(pin_out)
+        for d in range(3):
+            L.gzpb_destroy(hs[d])
