@@ -4,7 +4,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libgzpb.so")
+# GZPB_LIB selects another build of the same library for A/B measurements (tests/perf_*.py); the default is the in-tree one
+SO_PATH = os.environ.get("GZPB_LIB") or os.path.join(_HERE, "libgzpb.so")
 
 GZIP, ZLIB, RAWDEFLATE, MGZIP, BGZF, SNAP = 0, 1, 2, 3, 4, 5
 
@@ -34,6 +35,9 @@ _SIGS = {
                                            C.POINTER(C.c_size_t)]),
     "gzpb_encode_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gzpb_encode_device_ex": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gzpb_unit_stride": (C.c_size_t, [C.c_void_p]),
     "gzpb_encode_capacity": (C.c_size_t, [C.c_int, C.c_size_t]),
     "gzpb_header": (C.c_size_t, [C.c_int, C.c_int, C.c_void_p]),
     "gzpb_footer": (C.c_size_t, [C.c_int, C.c_uint32, C.c_uint32, C.c_void_p]),
@@ -57,6 +61,7 @@ _SIGS = {
     "gzpb_writer_commit": (C.c_int, [C.c_void_p, C.c_size_t]),
     "gzpb_compress_file": (C.c_int, [C.POINTER(C.c_int), C.c_size_t, C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_char_p, C.c_char_p,
                                      C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "gzpb_writer_set_copy_threads": (C.c_int, [C.c_void_p, C.c_int]),
     "gzpb_writer_write": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "gzpb_writer_flush": (C.c_int, [C.c_void_p]),
     "gzpb_writer_finish": (C.c_int, [C.c_void_p]),
@@ -102,6 +107,8 @@ def load():
                 "gzp_b200 has no CPU fallback.")
         lib = C.CDLL(SO_PATH)
         for name, (res, args) in _SIGS.items():
+            if os.environ.get("GZPB_LIB") and not hasattr(lib, name):
+                continue                                        # an older A/B build may lack the newest entry points
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args

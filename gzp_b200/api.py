@@ -131,6 +131,11 @@ def crc32_combine(a, b, len_b):
     return _lib.load().gzpb_crc32_combine(a, b, len_b)
 
 
+def adler32_combine(a, b, len_b):
+    """Check::combine for Adler32 (check.rs:121-128)."""
+    return _lib.load().gzpb_adler32_combine(a, b, len_b)
+
+
 def encode_capacity(fmt, n):
     return _lib.load().gzpb_encode_capacity(fmt, n)
 
@@ -331,8 +336,13 @@ class ParCompress:
             self._error = e
             raise
         for (data, _d, _l), (enc, s, a) in zip(msgs, res):
+            # running_check.combine(&check) (par/compress.rs:308): CRC-32 for Gzip (check.rs:162), Adler-32 for Zlib (:121-128)
             if self.format.ID == GZIP:
                 self._sum = crc32_combine(self._sum, s, len(data))
+                self._amount = (self._amount + len(data)) & 0xFFFFFFFF
+            elif self.format.ID == ZLIB:
+                if len(data):
+                    self._sum = adler32_combine(self._sum, s, len(data))
                 self._amount = (self._amount + len(data)) & 0xFFFFFFFF
             self.writer.write(enc)
 

@@ -345,37 +345,27 @@ k_link(const __grid_constant__ Geo g, const uint32_t *__restrict__ lists, const 
             if (base0 + 32 * k >= end) break;
             const bool act = i < end;
             const uint32_t b = e[k] & (is4 ? ((1u << kBits4) - 1) : ((1u << kBits3) - 1)), p = e[k] >> 16;
-            uint32_t prev = act ? (uint32_t)head[b] : kNone16;
-            uint32_t occ = (act && is4) ? (uint32_t)cnt[b] : 0u, gsize = 1;
-            __syncwarp();   // every lane has read its bucket before any lane overwrites one
-            if (act) head[b] = (uint16_t)p;
-            __syncwarp();
-            bool lost = act && head[b] != (uint16_t)p;
-            uint32_t lostmask = __ballot_sync(0xFFFFFFFFu, lost);
-            while (lostmask) {
-                const int j = __ffs(lostmask) - 1;
-                const uint32_t bj = __shfl_sync(0xFFFFFFFFu, b, j);
-                const bool member = act && b == bj;
-                const uint32_t grp = __ballot_sync(0xFFFFFFFFu, member);
-                const uint32_t lower = grp & lt;
-                const uint32_t pl = __shfl_sync(0xFFFFFFFFu, p, lower ? 31 - __clz(lower) : lane);
-                if (member) {
-                    if (lower) prev = pl;
-                    if ((grp >> lane) == 1u) head[b] = (uint16_t)p;
-                    occ += __popc(lower);
-                    gsize = ((grp >> lane) == 1u) ? (uint32_t)__popc(grp) : 0u;   // only the last member updates the count
-                }
-                lostmask &= ~grp;
-            }
-            __syncwarp();
+            // Entries of one tile that share a bucket are ordered by lane (= position order): MATCH.ANY gives every
+            // lane its group; the predecessor is the nearest lower member, or the bucket head for the group's first
+            // member; the group's last member becomes the new head.
+            const uint32_t grp = __match_any_sync(0xFFFFFFFFu, act ? b : (0x10000u + lane));
+            const uint32_t lower = grp & lt;
+            const uint32_t pl = __shfl_sync(0xFFFFFFFFu, p, lower ? 31 - __clz(lower) : lane);
+            uint32_t prev = kNone16, occ = 0;
             if (act) {
+                prev = lower ? pl : (uint32_t)head[b];
+                if (is4) occ = (uint32_t)cnt[b] + (uint32_t)__popc(lower);
+            }
+            __syncwarp();   // every lane has read its bucket before a group's last member overwrites it
+            if (act) {
+                if ((grp >> lane) == 1u) {
+                    head[b] = (uint16_t)p;
+                    if (is4) cnt[b] = (uint8_t)min(occ + 1u, 255u);   // occurrences so far
+                }
                 uint32_t dist = (prev != kNone16) ? p - prev : 0;
                 if (dist >= (uint32_t)kWindow) dist = 0;
                 out[p] = (uint16_t)dist;
-                if (is4) {
-                    clen[p] = (uint8_t)min(occ, 127u);
-                    if (gsize) cnt[b] = (uint8_t)min(occ + 1u, 255u);   // occ of the last member + 1 = occurrences so far
-                }
+                if (is4) clen[p] = (uint8_t)min(occ, 127u);
             }
             __syncwarp();
         }
@@ -1120,9 +1110,13 @@ __device__ __forceinline__ uint64_t sparse_entry(const uint32_t *s_in, const uin
     return pack_entry(lenA, boff, lenB, offB, d3 != 0, off3) | kValidA | kValidB;
 }
 
-__global__ void __launch_bounds__(kSparseThreads, 1)
+// kTable (k_smatch<true>, "k_tparse"): the same chunked speculation + stitch + event scan, fed from k_match's FULL match
+// table instead of its own searches — no chain walks at all, every `search` is one table entry (tokens mode only).  It
+// turns k_emit's sequential windowed parse (one warp per unit, ~70 % of k_emit) into 512 chunk parses per unit.
+template <bool kTable>
+__global__ void __launch_bounds__(kSparseThreads, kTable ? 2 : 1)
 k_smatch(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, const uint16_t *__restrict__ prev3g,
-         uint64_t *__restrict__ mtab, int depth, int nice, int mode, uint32_t chunk,
+         uint64_t *__restrict__ mtab, const uint32_t *__restrict__ mtab2, int depth, int nice, int mode, uint32_t chunk,
          uint32_t *__restrict__ tok_base, uint32_t *__restrict__ lists_g, uint16_t *__restrict__ idx_g, uint32_t *__restrict__ unit_ntok)
 {
     GZPB_DYN_SMEM(smem);
@@ -1163,13 +1157,14 @@ k_smatch(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, con
     // positions at or beyond `safe` cannot be searched from this sub-unit's window (their matches would be cut short):
     // only a parse that drifts more than 4 positions past the sub-unit's new range gets there — flagged, unit redone
     const bool last_sub = (size_t)sb.h + n >= g.unit_len[sb.u];
-    const uint32_t safe = last_sub ? 0xFFFFFFFFu : ne + 4;
+    const uint32_t safe = (last_sub || kTable) ? 0xFFFFFFFFu : ne + 4;    // the full table holds every position's true entry
+    const uint32_t *M2 = (kTable && mode == 2) ? mtab2 + (size_t)sb.u * g.m_stride + sb.h : nullptr;
 
     __syncthreads();                                               // the previous sub-unit's readers are done with shared memory
     for (uint32_t i = tid; i < 2048; i += kSparseThreads) s_iter[i] = 0;
     if (!tokens) for (uint32_t i = (nb & ~127u) + tid; i < n; i += kSparseThreads) M[i] = 0ull;     // no stale entries from the lane's previous batch
     __syncthreads();
-    if (n >= 5) {
+    if (!kTable && n >= 5) {
         if (tid == 0) {
             uint32_t bin = (n + 15u) & ~15u, bnx = (n * 2 + 15u) & ~15u;
             fence_proxy_async();                                   // shared memory is reused from sub-unit to sub-unit
@@ -1182,7 +1177,7 @@ k_smatch(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, con
     // min_len at the start of the unit's first DEFLATE block (calculate_min_match_len)
     if (k == 0 && g.unit_len[sb.u] - g.unit_dict[sb.u] >= 512) {
         const uint32_t span = min(min(g.unit_len[sb.u] - g.unit_dict[sb.u], n - nb), 4096u);
-        const uint8_t *b8 = (const uint8_t *)s_in;
+        const uint8_t *b8 = kTable ? in : (const uint8_t *)s_in;
         for (uint32_t i = tid; i < span; i += kSparseThreads) { const uint32_t c = b8[nb + i]; atomicOr(&s_used[c >> 5], 1u << (c & 31)); }
         __syncthreads();
         uint32_t nu = 0;
@@ -1198,7 +1193,7 @@ k_smatch(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, con
     uint32_t *spec_list = tokens ? lists_g + (size_t)u * kSparseListWords + (size_t)tid * lcap : nullptr;
     uint32_t *gap_list = tokens ? spec_list + kSparseListWords / 2 : nullptr;
     uint16_t *idx_at = tokens ? idx_g + (size_t)u * kMaxUnitBytes : nullptr;
-    const uint8_t *b8 = (const uint8_t *)s_in;
+    const uint8_t *b8 = kTable ? in : (const uint8_t *)s_in;
     auto run = [&](uint32_t q0, uint32_t stop, bool rejoin, uint32_t *list, uint32_t &cnt) -> uint32_t {
         uint32_t q = q0, m = 0, cl = 0, co = 0;
         uint32_t in_look = 0;                                      // 0 fresh search, 1 look-ahead at m + 1 (depth/2), 2 at m + 2 (depth/4, lazy2)
@@ -1228,8 +1223,16 @@ k_smatch(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, con
             const uint32_t maxlen = pos < n ? min((uint32_t)kMaxMatch, n - pos) : 0u;
             uint64_t e = 0;
             if (!in_look || maxlen >= 5) {
-                e = sparse_entry(s_in, s_next, p3, n, pos, (uint32_t)depth, (uint32_t)nice, lazy, !in_look, (uint32_t)depth >> in_look);
-                if (!tokens) atomicOr(&M[pos], (unsigned long long)e);
+                if (kTable) {
+                    e = maxlen >= 5 ? (uint64_t)M[pos] : 0ull;
+                    if (in_look == 2) {                            // lazy2's second look-ahead: the depth/4 column takes the place of depth/2
+                        const uint64_t c2 = M2[pos];
+                        e = (e & ~(0x7FFFFFull << 23)) | ((c2 & 0xFFull) << 23) | (((c2 >> 8) & 0x7FFFull) << 31);
+                    }
+                } else {
+                    e = sparse_entry(s_in, s_next, p3, n, pos, (uint32_t)depth, (uint32_t)nice, lazy, !in_look, (uint32_t)depth >> in_look);
+                    if (!tokens) atomicOr(&M[pos], (unsigned long long)e);
+                }
             }
             if (!in_look) {
                 table_search(e, min_len - 1, false, maxlen, cl, co);
@@ -2130,7 +2133,9 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
                 h[10] = 6; h[11] = 0; h[12] = 'B'; h[13] = 'C'; h[14] = 2; h[15] = 0;
                 uint32_t bs = (uint16_t)((uint16_t)nbytes + 26 - 1);
                 h[16] = (uint8_t)bs; h[17] = (uint8_t)(bs >> 8);
-                if (nbytes >= 65536) st = -3;     // GZPB_EBLOCKSIZE (bgzf.rs:218-223)
+                // GZPB_EBLOCKSIZE (bgzf.rs:218-223 tests the payload against 65536; the member — payload + 26 — must fit, or the
+                // u16 BSIZE above wraps and a corrupt block would be reported as success: deliberate deviation)
+                if (nbytes + 26 > 65536) st = -3;
             } else {
                 h[10] = 8; h[11] = 0; h[12] = 'I'; h[13] = 'G'; h[14] = 4; h[15] = 0;
                 uint32_t bs = nbytes + 28;
@@ -2373,7 +2378,7 @@ cudaError_t launch_deflate_pipeline(const DeflateBatch &b, cudaStream_t st)
         cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, chain_smem);
         cudaFuncSetAttribute(k_match, cudaFuncAttributeMaxDynamicSharedMemorySize, match_smem);
         cudaFuncSetAttribute(k_match2, cudaFuncAttributeMaxDynamicSharedMemorySize, match_smem);
-        cudaFuncSetAttribute(k_smatch, cudaFuncAttributeMaxDynamicSharedMemorySize, match_smem);
+        cudaFuncSetAttribute(k_smatch<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, match_smem);
         attr_done[cur_dev] = true;
     }
     if (b.nunits == 0) return cudaSuccess;
@@ -2406,11 +2411,11 @@ cudaError_t launch_deflate_pipeline(const DeflateBatch &b, cudaStream_t st)
         }
         if (b.timer) { b.timer->stop(st); b.timer->start(KT_MATCH, st); }
         const bool sparse_tokens = b.sparse == 2 && b.slists && b.sidx && b.sntok;
-        if (b.sparse && b.lists && (b.spu == 1 || sparse_tokens) && !lp.ht && (lp.mode == 0 || lp.mode == 1 || (lp.mode == 2 && sparse_tokens))) {
+        if (b.sparse && b.sparse != 3 && b.lists && (b.spu == 1 || sparse_tokens) && !lp.ht && (lp.mode == 0 || lp.mode == 1 || (lp.mode == 2 && sparse_tokens))) {
             // sparse path: speculative table, parse with miss detection, then the two filtered fallback launches
             const uint32_t chunk = (b.sparse_chunk >= kSparseChunk && b.sparse_chunk <= 4096u) ? b.sparse_chunk : kSparseChunk;   // 512 x 128 covers a unit
             const bool tokens = sparse_tokens;
-            GZPB_LAUNCH(k_smatch, b.nunits, kSparseThreads, match_smem, st, g, b.next4, b.prev3, b.mtab, lp.depth, lp.nice, lp.mode, chunk,
+            GZPB_LAUNCH(k_smatch<false>, b.nunits, kSparseThreads, match_smem, st, g, b.next4, b.prev3, b.mtab, (const uint32_t *)nullptr, lp.depth, lp.nice, lp.mode, chunk,
                         tokens ? b.tokens : (uint32_t *)nullptr, b.slists, b.sidx, b.sntok);
             DBG_SYNC("k_smatch");
             if (b.timer) { b.timer->stop(st); b.timer->start(KT_EMIT, st); }
@@ -2437,6 +2442,23 @@ cudaError_t launch_deflate_pipeline(const DeflateBatch &b, cudaStream_t st)
             GZPB_LAUNCH(k_match, b.nunits * b.spu, kMatchThreads, match_smem, st, g, b.next4, b.prev3, b.mtab, b.mtab2, b.clen, b.order, lp.depth, lp.nice, lp.mode, b.lists != nullptr, lp.ht, (const int32_t *)nullptr);
         DBG_SYNC("k_match");
         if (b.timer) b.timer->stop(st);
+        if (b.sparse == 3 && b.slists && b.sidx && b.sntok && !lp.ht) {
+            // table-fed chunk parse: tokens of the true parse from k_match's full table (k_smatch<true>), k_emit<2> ends the
+            // DEFLATE blocks and packs; a unit whose chunk lists overflowed is redone by the sequential parser (pass 2)
+            const uint32_t chunk = (b.sparse_chunk >= kSparseChunk && b.sparse_chunk <= 4096u) ? b.sparse_chunk : kSparseChunk;
+            if (b.timer) b.timer->start(KT_EMIT, st);
+            GZPB_LAUNCH(k_smatch<true>, b.nunits, kSparseThreads, 0, st, g, b.next4, b.prev3, b.mtab, b.mtab2, lp.depth, lp.nice, lp.mode, chunk,
+                        b.tokens, b.slists, b.sidx, b.sntok);
+            DBG_SYNC("k_tparse");
+            GZPB_LAUNCH(k_emit<2>, b.nunits, kEmitThreads, 0, st, g, b.unit_flags, b.mtab, b.mtab2, b.crc, b.tokens, b.out, b.out_len,
+                        b.status, lp.mode, lp.depth, lp.nice, b.level, b.format, 0, b.sntok);
+            DBG_SYNC("k_emit<2>");
+            GZPB_LAUNCH(k_emit<0>, b.nunits, kEmitThreads, 0, st, g, b.unit_flags, b.mtab, b.mtab2, b.crc, b.tokens, b.out, b.out_len,
+                        b.status, lp.mode, lp.depth, lp.nice, b.level, b.format, 1, (const uint32_t *)nullptr);
+            DBG_SYNC("k_emit(missed)");
+            if (b.timer) b.timer->stop(st);
+            return cudaGetLastError();
+        }
     }
     if (b.timer) b.timer->start(KT_EMIT, st);
     GZPB_LAUNCH(k_emit<0>, b.nunits, kEmitThreads, 0, st, g, b.unit_flags, b.mtab, b.mtab2, b.crc, b.tokens, b.out, b.out_len,

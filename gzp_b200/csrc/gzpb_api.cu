@@ -8,7 +8,11 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
 #include <deque>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 #include "../../include/gzpb.h"
@@ -231,7 +235,7 @@ static int lane_alloc(gzpb_ctx *c, Lane &L, bool with_io)
     if (!getenv("GZPB_USE_KCHAIN")) {
         CK(dmalloc(&L.d_lists, U * c->spu * 2 * kMaxUnitBytes));
         CK(dmalloc(&L.d_list_start, U * c->spu * 32));
-        if (c->sparse == 2) {
+        if (c->sparse >= 2) {
             CK(dmalloc(&L.d_slists, U * kSparseListWordsPerUnit));
             CK(dmalloc(&L.d_sidx, U * (size_t)kMaxUnitBytes));
             CK(dmalloc(&L.d_sntok, U));
@@ -309,7 +313,7 @@ extern "C" int gzpb_create(gzpb_ctx **out, int device, int format, int level, si
     gzpb_ctx *c = new gzpb_ctx();
     c->device = device; c->format = format; c->level = level;
     c->max_block_bytes = max_block_bytes; c->max_units = max_blocks_in_flight;
-    { const char *e = getenv("GZPB_SPARSE"); c->sparse = (e && (*e == '1' || *e == '2') && !getenv("GZPB_USE_KCHAIN")) ? *e - '0' : 0; }
+    { const char *e = getenv("GZPB_SPARSE"); c->sparse = (e && (*e == '1' || *e == '2' || *e == '3') && !getenv("GZPB_USE_KCHAIN")) ? *e - '0' : 0; }
     { const char *e = getenv("GZPB_SPARSE_CHUNK"); c->sparse_chunk = e ? (uint32_t)atoi(e) : 0; }
     { const char *e = getenv("GZPB_MATCH_V2"); c->match_v2 = e && *e == '1' && !getenv("GZPB_USE_KCHAIN"); }
     if (c->sparse) c->match_v2 = false;            // the variants are alternatives: k_smatch walks k_link's chains, not k_group's arrays
@@ -390,6 +394,7 @@ extern "C" const char *gzpb_ctx_variant(gzpb_ctx *c)
 {
     if (!c) return "";
     if (c->format == GZPB_SNAP) return "snap";
+    if (c->sparse == 3) return "split+link+match+tparse";
     if (c->sparse == 2) return "split+link+smatch+replay";
     if (c->sparse) return "split+link+smatch";
     return c->match_v2 ? "split+group+match2" : (c->lanes[0].d_lists ? "split+link+match" : "chain+match");
@@ -448,11 +453,18 @@ static bool is_pinned(const void *p)
     return a.type == cudaMemoryTypeHost;
 }
 
-extern "C" int gzpb_encode_device(gzpb_ctx *c, const void *d_in, const uint32_t *d_len, const uint32_t *d_flags,
-                                  size_t nunits, void *d_packed, uint64_t *d_offsets, int32_t *d_status,
-                                  void *cuda_stream)
+extern "C" size_t gzpb_unit_stride(gzpb_ctx *c) { return c ? c->in_stride : 0; }
+
+// Device-resident form for every format.  d_in: nunits slots of gzpb_unit_stride(ctx) bytes, each [dictionary | data];
+// d_len[i] = dictionary + data bytes, d_dict[i] = dictionary bytes (NULL = none), d_flags as gzpb_encode_device.
+// Snap: d_offsets / the packed stream have one entry per 64 KiB chunk (ceil(max_block_bytes / 65536) per unit).
+extern "C" int gzpb_encode_device_ex(gzpb_ctx *c, const void *d_in, const uint32_t *d_len, const uint32_t *d_dict,
+                                     const uint32_t *d_flags, size_t nunits, void *d_packed, uint64_t *d_offsets,
+                                     int32_t *d_status, void *cuda_stream)
 {
-    if (!c || !is_deflate_format(c->format) || c->dict_cap) return GZPB_EINVAL;   // device path: formats without dictionary
+    if (!c || !d_in || !d_len || !d_packed || !d_offsets) return GZPB_EINVAL;
+    if (c->format != GZPB_SNAP && (!d_flags || !d_status)) return GZPB_EINVAL;
+    if (c->dict_cap == 0 && d_dict) return GZPB_EINVAL;
     CK(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t)cuda_stream;
     Lane &L = c->lanes[0];
@@ -461,14 +473,34 @@ extern "C" int gzpb_encode_device(gzpb_ctx *c, const void *d_in, const uint32_t 
         size_t n = std::min(c->max_units, nunits - done);
         DeflateBatch b;
         fill_batch(c, L, b, n);
-        b.in = (const uint8_t *)d_in + done * (size_t)c->in_stride; b.unit_len = d_len + done; b.unit_flags = d_flags + done;
-        b.status = d_status + done; b.offsets = d_offsets + done; b.base_ptr = d_offsets + done;
+        const uint8_t *in = (const uint8_t *)d_in + done * (size_t)c->in_stride;
+        if (c->format == GZPB_SNAP) {
+            SnapBatch sb;
+            sb.nunits = (uint32_t)n; sb.cpu = c->cpu; sb.in = in; sb.unit_len = d_len + done; sb.in_stride = c->in_stride;
+            sb.out = L.d_out; sb.out_stride = c->out_stride; sb.out_len = L.d_out_len; sb.timer = c->profiling ? &c->timer : nullptr;
+            CK(launch_snap(sb, st));
+            b.nunits = (uint32_t)(n * c->cpu);
+            b.offsets = d_offsets + done * c->cpu; b.base_ptr = d_offsets + done * c->cpu;
+            c->launches += 3;   // k_snap, k_scan, k_gather
+        } else {
+            b.in = in; b.unit_len = d_len + done; b.unit_flags = d_flags + done;
+            if (d_dict) b.unit_dict = d_dict + done;
+            b.status = d_status + done; b.offsets = d_offsets + done; b.base_ptr = d_offsets + done;
+            CK(launch_deflate_pipeline(b, st));
+            c->launches += 6 + (c->check_kind >= 0 ? 1 : 0);   // [k_check,] k_split, k_link, k_match, k_emit, k_scan, k_gather
+        }
         b.packed = (uint8_t *)d_packed; b.packed_cap = ~0ull;
-        CK(launch_deflate_pipeline(b, st));
         CK(launch_pack(b, st));
-        c->launches += 7;   // k_check, k_split, k_link, k_match, k_emit, k_scan, k_gather
     }
     return GZPB_OK;
+}
+
+extern "C" int gzpb_encode_device(gzpb_ctx *c, const void *d_in, const uint32_t *d_len, const uint32_t *d_flags,
+                                  size_t nunits, void *d_packed, uint64_t *d_offsets, int32_t *d_status,
+                                  void *cuda_stream)
+{
+    if (!c || !is_deflate_format(c->format) || c->dict_cap) return GZPB_EINVAL;   // formats without dictionary
+    return gzpb_encode_device_ex(c, d_in, d_len, nullptr, d_flags, nunits, d_packed, d_offsets, d_status, cuda_stream);
 }
 
 // ---- host-buffer paths ---------------------------------------------------------
@@ -602,8 +634,14 @@ static int ticket_retire(gzpb_ctx *c)
     c->tickets.pop_front();
     Lane &L = c->lanes[t.lane];
     int r = lane_wait(c, L);
-    if (r != GZPB_OK) return r;
-    if (*L.h_overflow) return GZPB_ECUDA;
+    if (r == GZPB_OK && *L.h_overflow) r = GZPB_ECOMPRESS;
+    if (r != GZPB_OK) {
+        // the batch is lost as a whole: the lane is free again (after the device went idle) and every block says why
+        cudaStreamSynchronize(L.st);
+        L.busy = false;
+        for (size_t i = 0; i < t.count; i++) { t.out[i].status = r; t.out[i].out_len = 0; t.out[i].check_sum = 0; t.out[i].check_amount = 0; }
+        return r;
+    }
     for (size_t i = 0; i < t.count; i++) {
         gzpb_block_out &o = t.out[i];
         o.status = L.h_status[i];
@@ -842,8 +880,73 @@ extern "C" int gzpb_encode_stream_multi(gzpb_ctx *const *ctxs, size_t nctx, cons
 // the writer's devices and their lanes and stay in flight while the caller keeps writing;
 // they retire strictly in submission order — the ticket FIFO of par/compress.rs:303-313 — each with ONE
 // sink call on the lane's compacted pinned output.
+// Helper threads for the one host copy of ParCompress::write (par/compress.rs:414).  A single core copies
+// ~10 GB/s, one B200 compresses ~9 GiB/s and a box has eight: large writes are cut into 2 MiB pieces that
+// the caller and `n - 1` helpers copy side by side into the pinned slab.  Pure memcpy — no CUDA calls.
+namespace {
+struct CopyPool {
+    std::vector<std::thread> th;
+    std::mutex m;
+    std::condition_variable cv, cv_done;
+    const uint8_t *src = nullptr;
+    uint8_t *dst = nullptr;
+    size_t len = 0;
+    std::atomic<size_t> next{0};
+    uint64_t gen = 0;
+    int working = 0;
+    bool stop = false;
+    static constexpr size_t kPiece = 2u << 20;
+    explicit CopyPool(int helpers)
+    {
+        for (int i = 0; i < helpers; i++) th.emplace_back([this] { loop(); });
+    }
+    ~CopyPool()
+    {
+        { std::lock_guard<std::mutex> g(m); stop = true; }
+        cv.notify_all();
+        for (auto &t : th) t.join();
+    }
+    void pieces()
+    {
+        for (;;) {
+            const size_t o = next.fetch_add(kPiece);
+            if (o >= len) return;
+            memcpy(dst + o, src + o, std::min(kPiece, len - o));
+        }
+    }
+    void loop()
+    {
+        uint64_t seen = 0;
+        std::unique_lock<std::mutex> g(m);
+        for (;;) {
+            cv.wait(g, [&] { return stop || gen != seen; });
+            if (stop) return;
+            seen = gen;
+            g.unlock();
+            pieces();
+            g.lock();
+            if (--working == 0) cv_done.notify_one();
+        }
+    }
+    void copy(uint8_t *d, const uint8_t *s, size_t n)
+    {
+        {
+            std::lock_guard<std::mutex> g(m);
+            dst = d; src = s; len = n; next.store(0);
+            working = (int)th.size();
+            gen++;
+        }
+        cv.notify_all();
+        pieces();
+        std::unique_lock<std::mutex> g(m);
+        cv_done.wait(g, [&] { return working == 0; });
+    }
+};
+}  // namespace
+
 struct gzpb_writer {
     std::vector<gzpb_ctx *> ctx;                                 // one per device
+    CopyPool *pool = nullptr;                                    // gzpb_writer_set_copy_threads
     int format = 0, level = 0;
     size_t buffer_size = 0, batch_blocks = 0;
     gzpb_sink_fn sink = nullptr;
@@ -1014,6 +1117,14 @@ extern "C" int gzpb_writer_create(gzpb_writer **out, int device, int format, int
     return gzpb_writer_create_multi(out, &device, 1, format, level, buffer_size, blocks_in_flight, sink, user);
 }
 
+extern "C" int gzpb_writer_set_copy_threads(gzpb_writer *w, int nthreads)
+{
+    if (!w || nthreads < 1 || nthreads > 256) return GZPB_EINVAL;
+    delete w->pool;
+    w->pool = nthreads > 1 ? new CopyPool(nthreads - 1) : nullptr;
+    return GZPB_OK;
+}
+
 extern "C" int gzpb_writer_reserve(gzpb_writer *w, void **ptr, size_t *room)
 {
     if (!w || !ptr || !room) return GZPB_EINVAL;
@@ -1047,7 +1158,8 @@ extern "C" int gzpb_writer_write(gzpb_writer *w, const void *data, size_t len)
     const uint8_t *p = (const uint8_t *)data;
     while (len) {
         const size_t k = std::min(len, w->slab_cap - w->fill);
-        memcpy(w->slabs[w->cur] + w->fill, p, k);                 // the one host copy (par/compress.rs:414)
+        if (w->pool && k >= 4 * CopyPool::kPiece) w->pool->copy(w->slabs[w->cur] + w->fill, p, k);
+        else memcpy(w->slabs[w->cur] + w->fill, p, k);            // the one host copy (par/compress.rs:414)
         p += k; len -= k;
         int rc = gzpb_writer_commit(w, k);
         if (rc != GZPB_OK) return rc;
@@ -1130,6 +1242,7 @@ extern "C" void gzpb_writer_destroy(gzpb_writer *w)
     }
     for (uint8_t *p : w->slabs) cudaFreeHost(p - GZPB_DICT_SIZE);
     for (gzpb_ctx *c : w->ctx) gzpb_destroy(c);
+    delete w->pool;
     delete w;
 }
 

@@ -78,7 +78,9 @@ struct BitReader {
     uint64_t bb;          // bit buffer, next bit = bit 0
     uint32_t bc;          // valid bits
     const uint8_t *ip;    // next byte to load
-    __device__ __forceinline__ void refill() { if (bc < 32) { bb |= (uint64_t)gld32(ip) << bc; ip += 4; bc += 32; } }
+    const uint8_t *lim;   // end of the member's payload: loads start below it (a truncated or hostile member never pulls
+                          // the reader through memory; past `lim` the reader is fed zeros and the callers report INF_IN_OVERRUN)
+    __device__ __forceinline__ void refill() { if (bc < 32) { const uint32_t v = ip < lim ? gld32(ip) : 0u; bb |= (uint64_t)v << bc; ip += 4; bc += 32; } }
     __device__ __forceinline__ uint32_t peek(uint32_t n) const { return (uint32_t)bb & ((1u << n) - 1u); }
     __device__ __forceinline__ void drop(uint32_t n) { bb >>= n; bc -= n; }
     __device__ __forceinline__ uint32_t take(uint32_t n) { uint32_t v = peek(n); drop(n); return v; }
@@ -165,7 +167,7 @@ k_inflate(const uint8_t *__restrict__ comp, const InflateDesc *__restrict__ desc
     const uint32_t out_len = d.out_len;
 
     BitReader br;
-    br.bb = 0; br.bc = 0; br.ip = in0;
+    br.bb = 0; br.bc = 0; br.ip = in0; br.lim = in_end;
     uint32_t opos = 0;          // bytes written so far (uniform across the warp)
     int32_t err = INF_OK;
     uint32_t bfinal = 0;
@@ -243,6 +245,7 @@ k_inflate(const uint8_t *__restrict__ comp, const InflateDesc *__restrict__ desc
                     if (i + rep > total) { err = INF_BAD_DATA; break; }
                     while (rep--) S.lens[i++] = (uint8_t)val;
                 }
+                if (err == INF_OK && br.ip > in_end + 8) err = INF_IN_OVERRUN;  // the header ran past the payload (fed zeros since)
                 if (err == INF_OK && S.lens[256] == 0) err = INF_BAD_DATA;    // no end-of-block code
             }
             err = __shfl_sync(0xFFFFFFFFu, err, 0);

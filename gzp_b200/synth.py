@@ -161,3 +161,34 @@ def text_stream(nbytes, seed=0x5EED0001):
             pass
     reps = nbytes // TEXT_PERIOD + 1
     return (base * reps)[:nbytes]
+
+
+CORPUS_BYTES = 5465394
+CORPUS_SHA256 = "8a304827e5ed421e8f7bfb0f66e8f87adf0130958cb88dcb187cbe06aea4be1f"
+_corpus = None
+
+
+def corpus():
+    """The reference's benchmark corpus itself — bench-data/shakespeare.txt (5 465 394 bytes), the file every
+    BASELINE.json config names — from the committed fixture tests/golden/shakespeare.txt.gz
+    (tests/golden/make_corpus.py made it; the reference tree does not exist on the GPU box)."""
+    global _corpus
+    if _corpus is None:
+        import gzip
+        import hashlib
+        import os
+        path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "shakespeare.txt.gz")
+        data = gzip.open(path, "rb").read()
+        if len(data) != CORPUS_BYTES or hashlib.sha256(data).hexdigest() != CORPUS_SHA256:
+            raise RuntimeError("tests/golden/shakespeare.txt.gz does not hold the reference corpus")
+        _corpus = data
+    return _corpus
+
+
+def corpus_stream(nbytes, start=0):
+    """`nbytes` of shakespeare.txt repeated end to end, from stream offset `start` — BASELINE.json's
+    "shakespeare x N" streams (benches/bench.rs, README.md:166-167), any window of them."""
+    base = corpus()
+    start %= CORPUS_BYTES
+    reps = (start + nbytes) // CORPUS_BYTES + 1
+    return (base * reps)[start:start + nbytes]

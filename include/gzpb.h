@@ -145,6 +145,10 @@ int gzpb_writer_create(gzpb_writer **w, int device, int format, int level, size_
 int gzpb_writer_create_multi(gzpb_writer **w, const int *devices, size_t ndevices, int format, int level,
                              size_t buffer_size, size_t blocks_in_flight, gzpb_sink_fn sink, void *user);
 int gzpb_writer_write(gzpb_writer *w, const void *buf, size_t len);
+/* The one host copy of `write` (src/par/compress.rs:414) is what bounds a single caller: one core copies about as
+ * fast as ONE B200 compresses.  With nthreads > 1, writes of 8 MiB and more are copied into the pinned slab by the
+ * caller and nthreads - 1 helper threads side by side (default 1 = the reference's behaviour). */
+int gzpb_writer_set_copy_threads(gzpb_writer *w, int nthreads);
 /* Zero-copy form of write for callers that can produce their bytes in place (`Read::read(&mut buf)`, read(2)
  * from a file): gzpb_writer_reserve returns the writer's fill position inside its pinned slab and how many
  * contiguous bytes fit there (never 0); gzpb_writer_commit(n) declares the first n of them written and cuts
@@ -173,6 +177,14 @@ int gzpb_compress_file(const int *devices, size_t ndevices, int format, int leve
 int gzpb_encode_device(gzpb_ctx *ctx, const void *d_in, const uint32_t *d_len, const uint32_t *d_flags,
                        size_t nunits, void *d_packed, uint64_t *d_offsets, int32_t *d_status,
                        void *cuda_stream);
+
+/* The same for every format: slots of gzpb_unit_stride(ctx) bytes, each [dictionary | data]; d_len[i] = dictionary +
+ * data bytes, d_dict[i] = dictionary bytes (NULL when the format takes none).  Snap: d_offsets and the packed stream
+ * have one entry per 64 KiB chunk, ceil(max_block_bytes / 65536) per unit; d_flags / d_status may be NULL. */
+int gzpb_encode_device_ex(gzpb_ctx *ctx, const void *d_in, const uint32_t *d_len, const uint32_t *d_dict,
+                          const uint32_t *d_flags, size_t nunits, void *d_packed, uint64_t *d_offsets,
+                          int32_t *d_status, void *cuda_stream);
+size_t gzpb_unit_stride(gzpb_ctx *ctx);
 
 /* Capacity contract of the reference's output Vec (src/bgzf.rs:211-212,
  * src/mgzip.rs:194-195, src/deflate.rs:50-53). */
@@ -241,7 +253,9 @@ void gzpb_decoder_destroy(gzpb_decoder *d);
 int gzpb_decode_stream(gzpb_decoder *d, const void *in, size_t in_len, void *out, size_t out_cap, size_t *out_len,
                        size_t *consumed);
 /* Device-resident form, asynchronous on `cuda_stream`: d_status[i] = 0 ok, 1 bad data,
- * 2 output overrun, 3 input overrun, 4 CRC mismatch; d_crc_found[i] = CRC-32 of the decoded block. */
+ * 2 output overrun, 3 input overrun, 4 CRC mismatch; d_crc_found[i] = CRC-32 of the decoded block.
+ * d_comp must be readable for 8 bytes past the last member's payload (the bit reader loads aligned 32-bit word
+ * pairs; it never starts a load at or beyond a member's end, whatever the data says). */
 int gzpb_decode_device(gzpb_decoder *d, const void *d_comp, const gzpb_block_desc *d_desc, size_t nblocks, void *d_out,
                        int32_t *d_status, uint32_t *d_crc_found, void *cuda_stream);
 /* Incremental reader = `ParDecompress<F>` as a C object (src/par/decompress.rs:113-352): `source` plays

@@ -59,7 +59,10 @@ long oracle_encode_block(int format, int level, const uint8_t *in, size_t n, con
         if (out_cap < hs + avail) return E_INVAL;
         size_t w = oracle_deflate(in, n, level, out + hs, avail);
         if (w == 0) return E_COMPRESS;
-        if (format == ORACLE_FMT_BGZF && w >= 65536) return E_BLOCKSIZE;
+        /* bgzf.rs:218-223 tests `>= 65536` on the payload, but BSIZE = payload + 26 - 1 is a u16 (bgzf.rs:299): payloads of
+         * 65511..65535 bytes wrap it and the reference (release build) hands back a corrupt member as Ok.  Deliberate
+         * deviation, shared with the CUDA path: a member that does not fit 65536 bytes is BlockSizeExceeded. */
+        if (format == ORACLE_FMT_BGZF && w + 26 > 65536) return E_BLOCKSIZE;
         uint8_t *h = out;
         h[0] = 31; h[1] = 139; h[2] = 8; h[3] = 4; put32(h + 4, 0); h[8] = (uint8_t)xfl(level); h[9] = 255;
         if (format == ORACLE_FMT_BGZF) {

@@ -86,15 +86,15 @@ class _OracleContext:
         out = []
         for data, d, last in blocks:
             enc = oracle.encode_block(self.fmt, self.level, data, d, last)
-            s = zlib.crc32(data) if self.fmt == oracle.GZIP else 0
-            out.append((enc, s, len(data) if self.fmt == oracle.GZIP else 0))
+            s = zlib.crc32(data) if self.fmt == oracle.GZIP else zlib.adler32(data) if self.fmt == oracle.ZLIB else 0
+            out.append((enc, s, len(data) if self.fmt in (oracle.GZIP, oracle.ZLIB) else 0))
         return out
 
     def close(self):
         pass
 
 
-@pytest.mark.parametrize("fmt", [gzp_b200.Bgzf, gzp_b200.Gzip, gzp_b200.Mgzip, gzp_b200.RawDeflate])
+@pytest.mark.parametrize("fmt", [gzp_b200.Bgzf, gzp_b200.Gzip, gzp_b200.Zlib, gzp_b200.Mgzip, gzp_b200.RawDeflate, gzp_b200.Snap])
 def test_parcompress_mirror_chunks_like_the_reference(monkeypatch, fmt, text_corpus):
     monkeypatch.setattr(api, "Context", _OracleContext)
     rnd = random.Random(11)
@@ -116,6 +116,8 @@ def test_parcompress_mirror_chunks_like_the_reference(monkeypatch, fmt, text_cor
     want_msgs = oracle.chunk_stream(fmt.ID, bs, writes, flushes)
     assert [(bytes(b), d, l) for b, d, l in _OracleContext.log] == want_msgs
     assert sink.getvalue() == oracle.compress_stream(fmt.ID, 6, bs, writes, flushes)
+    if fmt is gzp_b200.Zlib:                                               # the Adler-32 footer folds per block (check.rs:121-128)
+        assert zlib.decompress(sink.getvalue()) == data
     with pytest.raises(gzp_b200.GzpError):
         pc.write(b"x")                                                     # write after finish
 

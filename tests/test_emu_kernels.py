@@ -646,7 +646,7 @@ def _sparse_stats(ctx):
 def _run_sparse(fmt, level, bs, data):
     ctx = emu.EmuContext(fmt, level, max_block_bytes=bs)
     try:
-        assert ctx.L.gzpb_ctx_variant(ctx.h) in (b"split+link+smatch", b"split+link+smatch+replay")
+        assert ctx.L.gzpb_ctx_variant(ctx.h) in (b"split+link+smatch", b"split+link+smatch+replay", b"split+link+match+tparse")
         _sparse_stats(ctx)                                        # device-wide counters: start from zero
         got = ctx.encode_stream(data, bs)
         units, missed = _sparse_stats(ctx)
@@ -701,17 +701,20 @@ def test_emu_sparse_chunk_sizes(monkeypatch, chunk):
     assert units == 2 and missed == 0
 
 
+@pytest.mark.parametrize("sparse", ["2", "3"])
 @pytest.mark.parametrize("level", [2, 5, 6, 7, 9])
-def test_emu_sparse_tokens_and_replay_levels(monkeypatch, level):
+def test_emu_sparse_tokens_and_replay_levels(monkeypatch, level, sparse):
     """GZPB_SPARSE=2: k_smatch also hands over the stitched, compacted tokens of the true parse and k_emit<2> only
-    replays the parser's events over them (min_len re-calculation, block-split checks, sequence-store limit)."""
-    monkeypatch.setenv("GZPB_SPARSE", "2")
+    replays the parser's events over them (min_len re-calculation, block-split checks, sequence-store limit).
+    GZPB_SPARSE=3: the same chunked parse fed from k_match's full table (k_smatch<true>) — no searches of its own."""
+    monkeypatch.setenv("GZPB_SPARSE", sparse)
     units, missed = _run_sparse(oracle.BGZF, level, 0, TEXT[:140000])
     assert units == 3 and missed == 0
 
 
-def test_emu_sparse_tokens_and_replay_edges_and_fallback(monkeypatch):
-    monkeypatch.setenv("GZPB_SPARSE", "2")
+@pytest.mark.parametrize("sparse", ["2", "3"])
+def test_emu_sparse_tokens_and_replay_edges_and_fallback(monkeypatch, sparse):
+    monkeypatch.setenv("GZPB_SPARSE", sparse)
     rnd = random.Random(77)
     rand = bytes(rnd.getrandbits(8) for _ in range(30000))
     few = bytes(rnd.choice(b"ACGT") for _ in range(40000))
