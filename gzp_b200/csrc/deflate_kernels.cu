@@ -5,7 +5,8 @@
 // src/mgzip.rs:187-218).  One thread block per gzp block.
 //
 // Pipeline per batch of units (a unit = one gzp block, <= 65536 positions):
-//   k_chain  : hash-chain links (hash4 -> next4[], hash3 -> prev3[]) + CRC-32
+//   k_check  : CRC-32 / Adler-32 of the unit's data (Check::update)
+//   k_split + k_link : hash-chain links of every position (hash4 -> next4[], hash3 -> prev3[])
 //   k_match  : TMA-staged input + chains in shared memory; per-position longest
 //              match for search depth D and D/2 (parse-independent)
 //   k_emit   : sequential lazy/greedy parse over the match table, block
@@ -28,7 +29,6 @@ __constant__ uint16_t c_static_litlen_cw[288];
 __constant__ uint8_t c_static_litlen_len[288];
 __constant__ uint8_t c_min_lens[80];
 __device__ unsigned long long g_phase[32];   // SM-cycle accounting of kernel phases (debug/profiling aid)
-__device__ unsigned long long g_sparse_stats[2];   // sparse path: units parsed from the sparse table, units that missed an entry
 
 static uint32_t h_bitrev(uint32_t v, int n) { uint32_t r = 0; for (int i = 0; i < n; i++) r |= ((v >> i) & 1u) << (n - 1 - i); return r; }
 
@@ -100,16 +100,6 @@ __device__ __forceinline__ Sub sub_geometry(const Geo &g, uint32_t sub)
     return r;
 }
 
-// =============================================================================
-// k_chain: hash chains.  1 CTA (256 threads) per unit, 1 CTA per SM.
-//   warp 0      : hash4 buckets -> next4[p] = distance to the previous position
-//                 with the same 16-bit hash (0 = none / outside the 32 KiB window)
-//   warp 1      : hash3 buckets -> prev3[p] likewise (15-bit hash of 3 bytes)
-// Shared memory: head4 u16[65536] + head3 u16[32768] = 192 KiB.
-// Restates the insertion side of libdeflate's hc_matchfinder: every position
-// p <= n-5 is inserted, position 0 under hash 0 (next_hashes starts at {0,0}).
-// =============================================================================
-constexpr int kChainThreads = 64;
 constexpr uint32_t kNone16 = 0xFFFFu;
 
 __device__ __forceinline__ uint32_t ldg32u(const uint32_t *__restrict__ words, uint32_t byte_pos)
@@ -118,104 +108,15 @@ __device__ __forceinline__ uint32_t ldg32u(const uint32_t *__restrict__ words, u
     return __funnelshift_r(__ldg(words + w), __ldg(words + w + 1), s);
 }
 
-template <int HASH_BITS, bool H3>
-__device__ __forceinline__ void chain_warp(const uint32_t *__restrict__ inw, uint32_t n, uint32_t dict0,
-                                           uint16_t *head, uint16_t *__restrict__ gout)
-{
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t ninsert = n >= 5 ? n - 4 : 0;
-    const uint32_t lt = lanemask_lt();
-    constexpr int G = 16;  // tiles per register group (prefetched one group ahead)
-    uint32_t v[G], vn[G];
-#pragma unroll
-    for (int k = 0; k < G; k++) { uint32_t p = 32 * k + lane; vn[k] = p < ninsert ? ldg32u(inw, p) : 0; }
-    for (uint32_t base0 = 0; base0 < n; base0 += 32 * G) {
-#pragma unroll
-        for (int k = 0; k < G; k++) v[k] = vn[k];
-#pragma unroll
-        for (int k = 0; k < G; k++) { uint32_t p = base0 + 32 * (G + k) + lane; vn[k] = p < ninsert ? ldg32u(inw, p) : 0; }
-#pragma unroll
-        for (int k = 0; k < G; k++) {
-            const uint32_t base = base0 + 32 * k;
-            if (base >= n) break;
-            const uint32_t p = base + lane;
-            const bool act = p < ninsert;
-            uint32_t seq = H3 ? (v[k] & 0xFFFFFFu) : v[k];
-            uint32_t h = lz_hash(seq, HASH_BITS);
-            if (p == 0 && !dict0) h = 0;
-            // Optimistic insert: every lane reads the bucket, then all store their
-            // position.  If each lane reads its own position back there were no equal
-            // hashes inside the tile (the common case) and `old` is the predecessor.
-            // Otherwise order each group of duplicates with ballots.
-            uint32_t old = act ? (uint32_t)head[h] : kNone16;
-            __syncwarp();   // every lane has read its bucket before any lane overwrites one
-            if (act) head[h] = (uint16_t)p;
-            __syncwarp();
-            bool lost = act && head[h] != (uint16_t)p;
-            uint32_t prev = old;
-            uint32_t lostmask = __ballot_sync(0xFFFFFFFFu, lost);
-            while (lostmask) {
-                // one iteration per group of equal hashes: order its members by lane
-                const int j = __ffs(lostmask) - 1;
-                const uint32_t hj = __shfl_sync(0xFFFFFFFFu, h, j);
-                const bool member = act && h == hj;
-                const uint32_t grp = __ballot_sync(0xFFFFFFFFu, member);
-                if (member) {
-                    uint32_t lower = grp & lt;
-                    if (lower) prev = base + 31 - __clz(lower);
-                    if ((grp >> lane) == 1u) head[h] = (uint16_t)p;  // highest lane of the group wins
-                }
-                lostmask &= ~grp;
-            }
-            __syncwarp();
-            uint32_t dist = (prev != kNone16) ? p - prev : 0;
-            if (dist >= (uint32_t)kWindow) dist = 0;
-            if (p < n) gout[p] = (uint16_t)dist;
-        }
-    }
-}
-
-__global__ void __launch_bounds__(kChainThreads, 1)
-k_chain(const __grid_constant__ Geo g, uint16_t *__restrict__ next4, uint16_t *__restrict__ prev3)
-{
-    GZPB_DYN_SMEM(smem);
-    uint16_t *head4 = (uint16_t *)smem;
-    uint16_t *head3 = head4 + 65536;
-    const Sub sb = sub_geometry(g, blockIdx.x);
-    if (!sb.valid) return;
-    const uint32_t n = sb.len;
-    const uint8_t *in = g.in + (size_t)sb.u * g.in_stride + sb.h;
-    const uint32_t *inw = (const uint32_t *)in;
-    const uint32_t tid = threadIdx.x, warp = tid >> 5;
-
-    const long long t_start = clock64();
-    // pull the sub-unit into L2 ahead of the dependent loads
-    for (uint32_t off = tid * 128; off < n; off += kChainThreads * 128)
-        prefetch_l2(in + off);
-    {
-        uint4 ones = make_uint4(~0u, ~0u, ~0u, ~0u);
-        uint4 *h = (uint4 *)smem;
-        for (uint32_t i = tid; i < (65536 + 32768) * 2 / 16; i += kChainThreads) h[i] = ones;
-    }
-    __syncthreads();
-
-    if (warp == 0) {
-        chain_warp<16, false>(inw, n, !sb.quirk, head4, next4 + (size_t)blockIdx.x * kMaxUnitBytes);
-        if (tid == 0) atomicAdd(&g_phase[16], (unsigned long long)(clock64() - t_start));
-    } else if (warp == 1) {
-        chain_warp<15, true>(inw, n, !sb.quirk, head3, prev3 + (size_t)blockIdx.x * kMaxUnitBytes);
-    }
-}
-
 // =============================================================================
-// k_split + k_link: the same hash-chain links as k_chain, restructured for
-// concurrency.  k_chain keeps only two latency-bound warps busy per SM (its
-// 192 KiB of bucket tables allow one CTA per SM).  Here a fully parallel pass
-// (k_split) partitions the positions of a sub-unit by bucket range into
-// position-ordered lists (4 quarters of the hash4 space, 2 halves of the hash3
-// space), and each list is linked by its own single-warp job (k_link) that needs
-// only a 32 KiB table, so seven jobs share an SM.  Same optimistic-insert /
-// ballot-ordering logic per tile of 32 list entries; identical links.
+// k_split + k_link: hash-chain links (hash4 -> next4[], hash3 -> prev3[]) of every position — the insertion side of
+// libdeflate's hc_matchfinder restated: every position p <= n-5 is inserted, position 0 under hash 0 (next_hashes
+// starts at {0,0}); next4[p] = distance to the previous position with the same 16-bit hash (0 = none / outside the
+// 32 KiB window), prev3[p] likewise for the 15-bit hash of 3 bytes.
+// A fully parallel pass (k_split) partitions the positions of a sub-unit stably by bucket range into position-ordered
+// lists (16 ranges of the hash4 space, 4 of the hash3 space); each list is linked by its own single-warp job (k_link)
+// that needs only an 8-16 KiB bucket table, so 14 jobs share an SM.  (The first design, one CTA per unit with the whole
+// 192 KiB of bucket tables in shared memory, kept two latency-bound warps per SM busy: 6.7 ms vs 4.7 ms per batch.)
 // =============================================================================
 constexpr int kSplitThreads = 1024;
 constexpr int kL4 = 16, kL3 = 4;         // lists: hash4 space in 16ths, hash3 space in quarters
@@ -303,15 +204,13 @@ k_split(const __grid_constant__ Geo g, uint32_t *__restrict__ lists, uint32_t *_
 
 __global__ void __launch_bounds__(32)
 k_link(const __grid_constant__ Geo g, const uint32_t *__restrict__ lists, const uint32_t *__restrict__ list_start,
-       uint16_t *__restrict__ next4, uint16_t *__restrict__ prev3, uint8_t *__restrict__ clen_g, int only3)
+       uint16_t *__restrict__ next4, uint16_t *__restrict__ prev3, uint8_t *__restrict__ clen_g)
 {
     // hash4 job: u16 head[4096] + u8 cnt[4096] (occurrences so far per bucket = chain-length estimate);
     // hash3 job: u16 head[8192]
     __shared__ __align__(16) uint16_t head[1 << kBits3];
     uint8_t *cnt = (uint8_t *)(head + (1 << kBits4));
-    // only3: the hash4 lists are grouped by k_group (match path v2), this launch links the hash3 lists only
-    const uint32_t sub = only3 ? blockIdx.x / kL3 : blockIdx.x / kSplitLists;
-    const uint32_t job = only3 ? kL4 + blockIdx.x % kL3 : blockIdx.x % kSplitLists;
+    const uint32_t sub = blockIdx.x / kSplitLists, job = blockIdx.x % kSplitLists;
     const Sub sb = sub_geometry(g, sub);
     if (!sb.valid) return;
     const uint32_t lane = threadIdx.x, lt = lanemask_lt();
@@ -382,19 +281,6 @@ k_link(const __grid_constant__ Geo g, const uint32_t *__restrict__ lists, const 
 // depend on parsing decisions, so all positions are searched in parallel.
 // =============================================================================
 constexpr int kMatchThreads = 1024;
-// Sparse match table (GZPB_SPARSE=1, k_smatch): entries exist only where a speculative chunk parse searched.
-constexpr uint64_t kValidB = 1ull << 62;      // depth/2 column, hash3 fields
-constexpr uint64_t kValidA = 1ull << 63;      // full-depth column
-constexpr int32_t kStatusMiss = 1000;         // internal unit status: the parse consulted an entry that is not there
-#ifdef GZPB_EMU
-// emulator-only statistics (tests/emu): chain nodes visited per position and the processing order of the last
-// sub-unit searched, for estimating lock-step lane utilisation without a GPU
-extern "C" { uint16_t gzpb_emu_visited[65536]; uint16_t gzpb_emu_order[65536]; uint32_t gzpb_emu_npos; unsigned long long gzpb_emu_sparse_searches, gzpb_emu_sparse_nodes; }
-#define EMU_STAT(p, i, v, np) do { gzpb_emu_visited[p] = (uint16_t)(v); gzpb_emu_order[i] = (uint16_t)(p); gzpb_emu_npos = (np); } while (0)
-#else
-#define EMU_STAT(p, i, v, np) do { } while (0)
-#endif
-
 __device__ __forceinline__ uint32_t lz_extend(const uint32_t *s_in, uint32_t p, uint32_t q, uint32_t len, uint32_t maxlen)
 {
     const uint8_t *b = (const uint8_t *)s_in;
@@ -410,7 +296,7 @@ __device__ __forceinline__ uint32_t lz_extend(const uint32_t *s_in, uint32_t p, 
 __global__ void __launch_bounds__(kMatchThreads, 1)
 k_match(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, const uint16_t *__restrict__ prev3g,
         uint64_t *__restrict__ mtab, uint32_t *__restrict__ mtab2, uint8_t *__restrict__ clen_g, uint16_t *__restrict__ order_g,
-        int depth, int nice, int lazy, int have_est, int ht, const int32_t *__restrict__ only_status)
+        int depth, int nice, int lazy, int ht)
 {
     GZPB_DYN_SMEM(smem);
     uint32_t *s_in = (uint32_t *)smem;
@@ -421,7 +307,6 @@ k_match(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, cons
     const uint32_t tid = threadIdx.x;
     const Sub sb = sub_geometry(g, blockIdx.x);
     if (!sb.valid) return;
-    if (only_status && only_status[sb.u] != kStatusMiss) return;   // second pass of the sparse path: only units whose parse missed an entry
     const uint32_t n = sb.len;
     const uint8_t *in = g.in + (size_t)sb.u * g.in_stride + sb.h;
     uint64_t *M = mtab + (size_t)sb.u * g.m_stride + sb.h;
@@ -459,17 +344,7 @@ k_match(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, cons
     for (uint32_t p = sb.nb + tid; p < sb.ne; p += kMatchThreads) {
         uint32_t len = 0;
         if (n - p >= 5) {
-            if (have_est) len = min((uint32_t)clen[p], (uint32_t)depth);   // occurrence index in the bucket (k_link)
-            else {
-                uint32_t q = p;
-                while (len < (uint32_t)depth) {
-                    uint32_t d = s_next[q];
-                    if (d == 0) break;
-                    q -= d;
-                    if (p - q >= (uint32_t)kWindow) break;
-                    len++;
-                }
-            }
+            len = min((uint32_t)clen[p], (uint32_t)depth);   // occurrence index in the bucket (k_link): the chain-length estimate
         }
         len = min(len, 127u);
         clen[p] = (uint8_t)len;
@@ -509,6 +384,10 @@ k_match(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, cons
         uint32_t best = 3, boff = 0, lenB = 0, offB = 0, lenC = 0, offC = 0;
         bool haveB = !lazy, haveC = (lazy != 2);
         uint32_t q = p, visited = 0;
+        uint32_t pbest = 0;                    // the byte of p a longer match must reach: b[p + best], kept in a register
+        const uint8_t *b = (const uint8_t *)s_in;
+        // the visit count at which the next snapshot (depth/4, depth/2) or the depth limit falls: one compare per node
+        uint32_t snap = (!haveC && depthC) ? depthC : (!haveB && depthB) ? depthB : (uint32_t)depth;
         for (;;) {
             uint32_t d = s_next[q];
             if (d == 0) break;
@@ -517,10 +396,7 @@ k_match(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, cons
             visited++;
             bool cand;
             if (best == 3) cand = (ld32u(s_in, q) == seq4);
-            else {
-                const uint8_t *b = (const uint8_t *)s_in;
-                cand = (b[q + best] == b[p + best]) && (ld32u(s_in, q) == seq4);
-            }
+            else cand = (b[q + best] == pbest) && (ld32u(s_in, q) == seq4);
             if (cand) {
                 // most matches are short: first 8 bytes of the extension inline, the rest in lz_extend
                 uint32_t len;
@@ -535,254 +411,32 @@ k_match(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, cons
                 if (len > best) {
                     best = len; boff = p - q;
                     if (len >= nicep) break;
+                    pbest = b[p + best];
                 }
             }
-            if (!haveC && visited == depthC) { haveC = true; lenC = best > 3 ? best : 0; offC = boff; }
-            if (!haveB && visited == depthB) { haveB = true; lenB = best > 3 ? best : 0; offB = boff; }
-            if (visited == (uint32_t)depth) break;
+            if (visited == snap) {
+                if (!haveC && visited == depthC) { haveC = true; lenC = best > 3 ? best : 0; offC = boff; }
+                if (!haveB && visited == depthB) { haveB = true; lenB = best > 3 ? best : 0; offB = boff; }
+                if (visited == (uint32_t)depth) break;
+                snap = (!haveC && depthC > visited) ? depthC : (!haveB && depthB > visited) ? depthB : (uint32_t)depth;
+            }
         }
         uint32_t lenA = best > 3 ? best : 0;
         if (!haveB) { lenB = lenA; offB = boff; }
         if (M2) { if (!haveC) { lenC = lenA; offC = boff; } M2[p] = (lenC ? lenC - 3 : 0) | (offC << 8); }
         if (!lazy) { lenB = 0; offB = 0; }
         M[p] = pack_entry(lenA, boff, lenB, offB, d3 != 0, off3);
-        EMU_STAT(p, i, visited, npos);
     }
 }
 
 // =============================================================================
-// Match path v2 (GZPB_MATCH_V2=1): hash GROUPS instead of linked chains.
-//
-// k_group: one single-warp job per hash4 list of k_split (4096 consecutive bucket
-// values, entries in position order).  A stable counting sort by bucket turns the
-// list into an array G of positions grouped by hash value, increasing inside a
-// group: the hash chain of position p is then simply G[idx(p) - 1], G[idx(p) - 2],
-// ... down to the start of its group — the same nodes, in the same order, as the
-// linked chain of k_link, but addressable without pointer chasing.  Written per
-// position: idx(p) and occ(p) = number of earlier positions in p's group.
-//
-// k_match2: like k_match, with G staged in shared memory instead of next4[].  The
-// exact number of chain nodes a search may visit (same hash, inside the 32 KiB
-// window, at most `depth`) is known up front, so (1) the counting sort by chain
-// length is exact and the 32 positions a warp walks in lock step finish together,
-// (2) the candidate loads G[idx - k] do not depend on the previous node.
-// Bit-identical results (tests/test_emu_kernels.py::test_emu_match_v2_*).
-// =============================================================================
-constexpr int kGroupWords = (1 << kBits4) + ((1 << kBits4) >> 7);   // one pad word per 128 counters: conflict-free column walks
-__device__ __forceinline__ uint32_t gphys(uint32_t b) { return b + (b >> 7); }
-
-__global__ void __launch_bounds__(32)
-k_group(const __grid_constant__ Geo g, const uint32_t *__restrict__ lists, const uint32_t *__restrict__ list_start,
-        uint16_t *__restrict__ group_g, uint16_t *__restrict__ gidx_g, uint16_t *__restrict__ gocc_g)
-{
-    __shared__ uint32_t cnt[kGroupWords];          // (group start << 16) | members placed so far
-    const uint32_t sub = blockIdx.x / kL4, job = blockIdx.x % kL4;
-    const Sub sb = sub_geometry(g, sub);
-    if (!sb.valid) return;
-    const uint32_t lane = threadIdx.x, lt = lanemask_lt();
-    const uint32_t *ls = list_start + (size_t)sub * kLsStride;
-    const uint32_t *arr = lists + (size_t)sub * 2 * kMaxUnitBytes;
-    const uint32_t beg = ls[job], end = ls[job + 1];
-    uint16_t *G = group_g + (size_t)sub * kMaxUnitBytes;
-    uint16_t *gidx = gidx_g + (size_t)sub * kMaxUnitBytes;
-    uint16_t *gocc = gocc_g + (size_t)sub * kMaxUnitBytes;
-    constexpr uint32_t kMask = (1u << kBits4) - 1;
-    for (uint32_t i = lane; i < (uint32_t)kGroupWords; i += 32) cnt[i] = 0;
-    __syncwarp();
-    // pass 1: group sizes
-    for (uint32_t i = beg + lane; i < end; i += 32) atomicAdd(&cnt[gphys(__ldg(arr + i) & kMask)], 1u);
-    __syncwarp();
-    // exclusive prefix: lane l owns buckets [128 l, 128 l + 128)
-    {
-        uint32_t sum = 0;
-        for (uint32_t j = 0; j < 128; j++) sum += cnt[gphys(lane * 128 + j)];
-        uint32_t inc = sum;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { uint32_t v = __shfl_up_sync(0xFFFFFFFFu, inc, d); if (lane >= (uint32_t)d) inc += v; }
-        uint32_t run = inc - sum;
-        for (uint32_t j = 0; j < 128; j++) { const uint32_t a = gphys(lane * 128 + j); const uint32_t c = cnt[a]; cnt[a] = run << 16; run += c; }
-    }
-    __syncwarp();
-    // pass 2: stable scatter, one tile of 32 list entries at a time (position order)
-    for (uint32_t base0 = beg; base0 < end; base0 += 32) {
-        const uint32_t i = base0 + lane;
-        const bool act = i < end;
-        const uint32_t e = act ? __ldg(arr + i) : 0u;
-        const uint32_t b = e & kMask, p = e >> 16;
-        const uint32_t m = __match_any_sync(0xFFFFFFFFu, act ? b : 0xFFFFu);
-        const uint32_t v = act ? cnt[gphys(b)] : 0u;
-        __syncwarp();                                // every lane has read its counter before a leader advances one
-        if (act && (m & lt) == 0) cnt[gphys(b)] = v + (uint32_t)__popc(m);
-        __syncwarp();
-        if (act) {
-            const uint32_t o = (v & 0xFFFFu) + (uint32_t)__popc(m & lt);
-            const uint32_t slot = beg + (v >> 16) + o;
-            G[slot] = (uint16_t)p;
-            gidx[p] = (uint16_t)slot;
-            gocc[p] = (uint16_t)min(o, 65535u);
-        }
-    }
-}
-
-__global__ void __launch_bounds__(kMatchThreads, 1)
-k_match2(const __grid_constant__ Geo g, const uint16_t *__restrict__ group_g, const uint16_t *__restrict__ prev3g,
-         const uint16_t *__restrict__ gidx_g, uint16_t *__restrict__ gocc_g,
-         uint64_t *__restrict__ mtab, uint32_t *__restrict__ mtab2, uint8_t *__restrict__ clen_g, uint16_t *__restrict__ order_g,
-         int depth, int nice, int lazy, int ht)
-{
-    GZPB_DYN_SMEM(smem);
-    uint32_t *s_in = (uint32_t *)smem;
-    uint16_t *s_G = (uint16_t *)(smem + kInStride);
-    __shared__ __align__(8) uint64_t bar;
-    __shared__ uint32_t s_whist[32][128];
-    __shared__ uint32_t s_tot[128];
-    const uint32_t tid = threadIdx.x;
-    const Sub sb = sub_geometry(g, blockIdx.x);
-    if (!sb.valid) return;
-    const uint32_t n = sb.len;
-    const uint8_t *in = g.in + (size_t)sb.u * g.in_stride + sb.h;
-    uint64_t *M = mtab + (size_t)sb.u * g.m_stride + sb.h;
-    uint32_t *M2 = (lazy == 2) ? mtab2 + (size_t)sb.u * g.m_stride + sb.h : nullptr;   // lazy2: depth/4 column
-
-    if (tid == 0) {
-        mbar_init(&bar, 1);
-        fence_mbar_init();
-    }
-    __syncthreads();
-    if (n >= 5) {
-        if (tid == 0) {
-            uint32_t bin = (n + 15u) & ~15u, bnx = (n * 2 + 15u) & ~15u;
-            mbar_expect_tx(&bar, bin + bnx);
-            tma_load_1d(s_in, in, bin, &bar);
-            tma_load_1d(s_G, group_g + (size_t)blockIdx.x * kMaxUnitBytes, bnx, &bar);
-        }
-        mbar_wait(&bar, 0);
-    }
-    const uint16_t *p3 = prev3g + (size_t)blockIdx.x * kMaxUnitBytes;
-    const uint16_t *gidx = gidx_g + (size_t)blockIdx.x * kMaxUnitBytes;
-    uint16_t *gocc = gocc_g + (size_t)blockIdx.x * kMaxUnitBytes;
-    const uint32_t depthB = (uint32_t)depth >> 1, depthC = (uint32_t)depth >> 2;
-
-    // ---- phase 1: exact number of chain nodes per position, counting sort by it ----
-    uint8_t *clen = clen_g + (size_t)blockIdx.x * kMaxUnitBytes;
-    uint16_t *order = order_g + (size_t)blockIdx.x * kMaxUnitBytes;
-    const uint32_t warp = tid >> 5;
-    for (uint32_t i = tid; i < 32 * 128; i += kMatchThreads) (&s_whist[0][0])[i] = 0;
-    __syncthreads();
-    for (uint32_t p = sb.nb + tid; p < sb.ne; p += kMatchThreads) {
-        uint32_t c = 0;
-        if (n - p >= 5) {
-            const uint32_t base = gidx[p];
-            c = min((uint32_t)gocc[p], (uint32_t)depth);
-            if (c && p - (uint32_t)s_G[base - c] >= (uint32_t)kWindow) {
-                // the c-th node lies outside the window: nodes get farther with k, find the first one outside
-                uint32_t lo = 1, hi = c;                      // invariant: node hi is outside
-                while (lo < hi) {
-                    const uint32_t mid = (lo + hi) >> 1;
-                    if (p - (uint32_t)s_G[base - mid] >= (uint32_t)kWindow) hi = mid; else lo = mid + 1;
-                }
-                c = hi - 1;
-            }
-        }
-        gocc[p] = (uint16_t)c;                                // from here on: the exact node count of position p
-        const uint32_t key = min(c, 127u);
-        clen[p] = (uint8_t)key;
-        atomicAdd(&s_whist[warp][key], 1u);
-    }
-    __syncthreads();
-    if (tid < 128) {
-        uint32_t acc = 0;
-        for (int w = 0; w < 32; w++) { uint32_t v = s_whist[w][tid]; s_whist[w][tid] = acc; acc += v; }
-        s_tot[tid] = acc;
-    }
-    __syncthreads();
-    if (tid == 0) { uint32_t acc = 0; for (int l = 127; l >= 0; l--) { uint32_t v = s_tot[l]; s_tot[l] = acc; acc += v; } }   // longest first
-    __syncthreads();
-    for (uint32_t p = sb.nb + tid; p < sb.ne; p += kMatchThreads) {
-        uint32_t len = clen[p];
-        uint32_t slot = s_tot[len] + atomicAdd(&s_whist[warp][len], 1u);
-        order[slot] = (uint16_t)p;
-    }
-    __syncthreads();
-
-    // ---- phase 2: the searches, 32 positions of equal node count per warp ----
-    const uint32_t npos = sb.ne - sb.nb;
-    for (uint32_t i = tid; i < npos; i += kMatchThreads) {
-        const uint32_t p = order[i];
-        const uint32_t maxlen = min((uint32_t)kMaxMatch, n - p);
-        if (maxlen < 5) { M[p] = 0; if (M2) M2[p] = 0; continue; }
-        const uint32_t nicep = min((uint32_t)nice, maxlen);
-        const uint32_t seq4 = ld32u(s_in, p);
-        const uint32_t w1 = ld32u(s_in, p + 4), w2 = ld32u(s_in, p + 8);
-        uint32_t d3 = ht ? 1u : p3[p];
-        uint32_t off3 = 0;
-        if (!ht && d3 && d3 <= 8192u && ((ld32u(s_in, p - d3) ^ seq4) & 0xFFFFFFu) == 0) off3 = d3;
-
-        uint32_t best = 3, boff = 0, lenB = 0, offB = 0, lenC = 0, offC = 0;
-        bool haveB = !lazy, haveC = (lazy != 2);
-        const uint32_t base = gidx[p], c = gocc[p];
-        const uint8_t *b8 = (const uint8_t *)s_in;
-        uint32_t pbest = b8[p + 3];                           // byte of p at offset `best`, refreshed when best grows
-        uint32_t qn = c ? (uint32_t)s_G[base - 1] : 0u;       // next candidate, loaded one node ahead
-        uint32_t k = 1;
-        // one chain node; true = a match of nice length ended the search
-        auto node = [&]() -> bool {
-            const uint32_t q = qn;
-            if (k < c) qn = s_G[base - k - 1];
-            bool cand;
-            if (best == 3) cand = (ld32u(s_in, q) == seq4);
-            else cand = (b8[q + best] == pbest) && (ld32u(s_in, q) == seq4);
-            if (cand) {
-                uint32_t len;
-                uint32_t x = ld32u(s_in, q + 4) ^ w1;
-                if (x) len = 4 + ((__ffs(x) - 1) >> 3);
-                else {
-                    x = ld32u(s_in, q + 8) ^ w2;
-                    if (x) len = 8 + ((__ffs(x) - 1) >> 3);
-                    else len = (maxlen > 12) ? lz_extend(s_in, p, q, 12, maxlen) : 12;
-                }
-                len = min(len, maxlen);
-                if (len > best) {
-                    best = len; boff = p - q;
-                    if (len >= nicep) return true;
-                    pbest = b8[p + best];
-                }
-            }
-            return false;
-        };
-        // the walk in up to three stretches, so that the depth/4 and depth/2 snapshots (lazy2 / lazy look-ahead
-        // columns) are taken between loops instead of being tested at every node
-        bool done = false;
-        if (lazy == 2) {
-            const uint32_t e = min(c, depthC);
-            for (; k <= e; k++) if (node()) { done = true; break; }
-            if (!done && c >= depthC) { haveC = true; lenC = best > 3 ? best : 0; offC = boff; }
-        }
-        if (lazy && !done) {
-            const uint32_t e = min(c, depthB);
-            for (; k <= e; k++) if (node()) { done = true; break; }
-            if (!done && c >= depthB) { haveB = true; lenB = best > 3 ? best : 0; offB = boff; }
-        }
-        if (!done)
-            for (; k <= c; k++) if (node()) break;
-        uint32_t lenA = best > 3 ? best : 0;
-        if (!haveB) { lenB = lenA; offB = boff; }
-        if (M2) { if (!haveC) { lenC = lenA; offC = boff; } M2[p] = (lenC ? lenC - 3 : 0) | (offC << 8); }
-        if (!lazy) { lenB = 0; offB = 0; }
-        M[p] = pack_entry(lenA, boff, lenB, offB, d3 != 0, off3);
-        EMU_STAT(p, i, min(k, c), npos);
-    }
-}
-
-// =============================================================================
-// k_emit: parse + Huffman + bit packing + container.  1 CTA (128 threads) per
-// unit, many CTAs per SM.  Thread 0 runs the sequential parser (greedy / lazy,
-// min_len heuristics, block splitting) over match-table tiles streamed into a
-// 2-slot shared-memory ring by TMA bulk copies; at each DEFLATE block boundary
-// the whole CTA builds the Huffman codes (libdeflate's sort / in-place tree /
-// length limiting / canonical codewords restated), picks the cheapest of
-// dynamic / static / stored, and packs the tokens in parallel (prefix scan of
-// code lengths, OR-merge in a shared staging buffer, coalesced 32-bit stores).
+// k_emit: parse + Huffman + bit packing + container.  1 CTA (one warp) per unit, 22 CTAs per SM.  The warp runs the
+// reference's parser as a windowed parse over match-table tiles streamed into a 4-slot shared-memory ring by TMA bulk
+// copies (every lane evaluates the parser's two states at its position, the warp follows the path through the window
+// and stops exactly at state-changing events: min_len re-calculation, block-split checks, sequence-store limit); at
+// each DEFLATE block boundary it builds the Huffman codes (libdeflate's sort / in-place tree / length limiting /
+// canonical codewords restated), picks the cheapest of dynamic / static / stored, and packs the tokens in parallel
+// (prefix scan of code lengths, OR-merge in a shared staging buffer, coalesced 32-bit stores).
 // =============================================================================
 constexpr int kEmitThreads = 32;
 constexpr int kTile = 128;                 // positions per streamed tile
@@ -812,7 +466,7 @@ struct EmitShared {
     uint32_t scan[kEmitThreads / 32];
     uint32_t used[8];
     // control block written by thread 0
-    uint32_t blk_begin, blk_end, ntok, is_final, min_len, tok0;
+    uint32_t blk_begin, blk_end, ntok, is_final, min_len;
     uint32_t nused, nitems, nlit, noff, nexpl, btype;
     uint32_t cost_dyn, cost_static;
     uint32_t G;        // bit position in the payload
@@ -1032,437 +686,14 @@ __device__ __forceinline__ void table_search(uint64_t e, uint32_t b, bool useB, 
     } else if (lx > b) { len = lx; off = ox; }
 }
 
-// =============================================================================
-// k_smatch (GZPB_SPARSE=1): the match table only where the parser looks.
-//
-// libdeflate's parser searches ~42 % of the positions of a text block and walks 4.4x fewer chain nodes than a
-// table of every position costs (tests/search_stats.py).  Which positions it searches depends on its own
-// decisions — but a parse started cold at any position re-joins the true parse within a few positions
-// (tests/spec_parse_sim.py; oracle_deflate_spec is the CPU statement of the algorithm).  So: the unit is cut
-// into chunks of kSparseChunk positions, one thread per chunk.  (A) Every thread runs the reference's parser
-// loop from its chunk's first position, computing — and publishing with atomicOr — the table entry of every
-// position it searches (full-depth entries for fresh searches, depth/2 entries for look-aheads), and marks its
-// iteration starts.  (B) Every thread then re-parses from where the previous chunk's last iteration ended until
-// it stands on one of its own iteration starts; chunks that never re-join (a match spanning the chunk) pass their
-// real end to the next chunk in further rounds.  Every position the true parse searches now has its entry —
-// provided min_len is what this kernel assumed (the value at the start of the unit's first DEFLATE block).
-// k_emit checks the valid bits of every entry it commits; a unit that misses one (min_len changed inside the
-// unit) is flagged and redone by k_match + k_emit in a second, filtered pass.  Bit-identical either way.
-// =============================================================================
-constexpr int kSparseThreads = 512;
-constexpr uint32_t kTokEnd = 1u << 30;          // tokens mode: a parser iteration ends after this token
-constexpr uint32_t kSparseListWords = 2 * 204800; // per unit: speculative lists + gap lists, (chunk + 264) words per chunk
-constexpr uint32_t kSparseChunk = 128;          // default positions per chunk (GZPB_SPARSE_CHUNK overrides: 128..4096)
-
-// the body of k_match's phase 2 for one position: best match over `depth` nodes with the depth/2 snapshot
-// (full), or over depth/2 nodes only (look-ahead entry: B column + hash3 fields)
-__device__ __forceinline__ uint64_t sparse_entry(const uint32_t *s_in, const uint16_t *s_next, const uint16_t *p3, uint32_t n, uint32_t p,
-                                                 uint32_t depth, uint32_t nice, bool lazy, bool full, uint32_t limit)
-{
-    const uint32_t maxlen = min((uint32_t)kMaxMatch, n - p);
-    if (maxlen < 5) return kValidA | kValidB;
-    const uint32_t nicep = min(nice, maxlen);
-    const uint32_t seq4 = ld32u(s_in, p);
-    const uint32_t w1 = ld32u(s_in, p + 4), w2 = ld32u(s_in, p + 8);
-    const uint32_t d3 = p3[p];
-    uint32_t off3 = 0;
-    if (d3 && d3 <= 8192u && ((ld32u(s_in, p - d3) ^ seq4) & 0xFFFFFFu) == 0) off3 = d3;
-    const uint32_t depthB = depth >> 1;              // limit: nodes to walk (depth for a fresh search, depth/2 or depth/4 for the look-aheads)
-    const uint8_t *b8 = (const uint8_t *)s_in;
-    uint32_t best = 3, boff = 0, lenB = 0, offB = 0, pbest = 0;
-    bool haveB = !(lazy && full);
-    uint32_t q = p, visited = 0;
-    if (limit) for (;;) {
-        const uint32_t d = s_next[q];
-        if (d == 0) break;
-        q -= d;
-        if (p - q >= (uint32_t)kWindow) break;
-        visited++;
-        bool cand;
-        if (best == 3) cand = (ld32u(s_in, q) == seq4);
-        else cand = (b8[q + best] == pbest) && (ld32u(s_in, q) == seq4);
-        if (cand) {
-            uint32_t len;
-            uint32_t x = ld32u(s_in, q + 4) ^ w1;
-            if (x) len = 4 + ((__ffs(x) - 1) >> 3);
-            else {
-                x = ld32u(s_in, q + 8) ^ w2;
-                if (x) len = 8 + ((__ffs(x) - 1) >> 3);
-                else len = (maxlen > 12) ? lz_extend(s_in, p, q, 12, maxlen) : 12;
-            }
-            len = min(len, maxlen);
-            if (len > best) {
-                best = len; boff = p - q;
-                if (len >= nicep) break;
-                pbest = b8[p + best];
-            }
-        }
-        if (!haveB && visited == depthB) { haveB = true; lenB = best > 3 ? best : 0; offB = boff; }
-        if (visited == limit) break;
-    }
-#ifdef GZPB_EMU
-    gzpb_emu_sparse_searches++; gzpb_emu_sparse_nodes += visited;
-#endif
-    const uint32_t lenA = best > 3 ? best : 0;
-    if (!full) return pack_entry(0, 0, lenA, boff, d3 != 0, off3) | kValidB;
-    if (!haveB) { lenB = lenA; offB = boff; }
-    if (!lazy) { lenB = 0; offB = 0; }
-    return pack_entry(lenA, boff, lenB, offB, d3 != 0, off3) | kValidA | kValidB;
-}
-
-// kTable (k_smatch<true>, "k_tparse"): the same chunked speculation + stitch + event scan, fed from k_match's FULL match
-// table instead of its own searches — no chain walks at all, every `search` is one table entry (tokens mode only).  It
-// turns k_emit's sequential windowed parse (one warp per unit, ~70 % of k_emit) into 512 chunk parses per unit.
-template <bool kTable>
-__global__ void __launch_bounds__(kSparseThreads, kTable ? 2 : 1)
-k_smatch(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, const uint16_t *__restrict__ prev3g,
-         uint64_t *__restrict__ mtab, const uint32_t *__restrict__ mtab2, int depth, int nice, int mode, uint32_t chunk,
-         uint32_t *__restrict__ tok_base, uint32_t *__restrict__ lists_g, uint16_t *__restrict__ idx_g, uint32_t *__restrict__ unit_ntok)
-{
-    GZPB_DYN_SMEM(smem);
-    uint32_t *s_in = (uint32_t *)smem;
-    uint16_t *s_next = (uint16_t *)(smem + kInStride);
-    __shared__ __align__(8) uint64_t bar;
-    __shared__ uint32_t s_iter[2048];            // iteration starts of the speculative parses, one bit per position
-    __shared__ uint32_t s_end[kSparseThreads];   // where each chunk's last iteration ends
-    __shared__ uint32_t s_used[8], s_flag, s_over, s_wsum[kSparseThreads / 32];
-    __shared__ uint32_t s_fl[256], s_obs[10], s_nobs[10];      // event scan: literal frequencies and split statistics of the current DEFLATE block
-    __shared__ uint32_t s_chg[4];                               // event scan -> all threads: {changed, token index, unit position, new min_len}
-    const uint32_t tid = threadIdx.x;
-    // tokens mode (GZPB_SPARSE=2): the chunk threads also record their tokens; after the stitch the tokens of the true
-    // parse are compacted, in order, into the unit's token array and k_emit<2> only replays the parser's events over them
-    const bool tokens = tok_base != nullptr;
-    // One CTA per unit.  A long unit (tokens mode only) is walked sub-unit by sub-unit — [32 KiB halo | new positions |
-    // look-ahead], the geometry k_split / k_link built their chains for — and the parse is carried across: where the
-    // last iteration of one sub-unit ends is where the first chunk of the next one enters.
-    const uint32_t u = blockIdx.x;
-    uint32_t min_len = 3, tok_run = 0, carry = 0xFFFFFFFFu;       // carry: unit position at which the true parse stands
-    // event scan (warp 0, tokens mode): the parser's state that outlives an iteration — replayed over the stitched tokens to
-    // find the places where min_len changes (re-calculation schedule, start of a new DEFLATE block); unit coordinates
-    const uint32_t unit_n = g.unit_len[u], unit_dict = g.unit_dict[u];
-    uint32_t rt = 0, rp = unit_dict, bb = unit_dict, next_recalc = unit_dict + min(unit_n - unit_dict, 10000u);
-    uint32_t num_obs = 0, num_new_obs = 0, nmatch = 0, in_h = 0;
-    if (tid < 256) s_fl[tid] = 0;
-    if (tid < 10) { s_obs[tid] = 0; s_nobs[tid] = 0; }
-    if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); s_over = 0; }
-    if (tid < 8) s_used[tid] = 0;
-    __syncthreads();
-    for (uint32_t k = 0; k < g.spu; k++) {
-    const Sub sb = sub_geometry(g, u * g.spu + k);
-    if (!sb.valid) break;                                          // uniform: the unit ends before this sub-unit
-    const uint32_t n = sb.len, nb = sb.nb, ne = sb.ne;
-    const uint8_t *in = g.in + (size_t)sb.u * g.in_stride + sb.h;
-    unsigned long long *M = (unsigned long long *)(mtab + (size_t)sb.u * g.m_stride + sb.h);
-    const uint16_t *p3 = prev3g + (size_t)(u * g.spu + k) * kMaxUnitBytes;
-    // positions at or beyond `safe` cannot be searched from this sub-unit's window (their matches would be cut short):
-    // only a parse that drifts more than 4 positions past the sub-unit's new range gets there — flagged, unit redone
-    const bool last_sub = (size_t)sb.h + n >= g.unit_len[sb.u];
-    const uint32_t safe = (last_sub || kTable) ? 0xFFFFFFFFu : ne + 4;    // the full table holds every position's true entry
-    const uint32_t *M2 = (kTable && mode == 2) ? mtab2 + (size_t)sb.u * g.m_stride + sb.h : nullptr;
-
-    __syncthreads();                                               // the previous sub-unit's readers are done with shared memory
-    for (uint32_t i = tid; i < 2048; i += kSparseThreads) s_iter[i] = 0;
-    if (!tokens) for (uint32_t i = (nb & ~127u) + tid; i < n; i += kSparseThreads) M[i] = 0ull;     // no stale entries from the lane's previous batch
-    __syncthreads();
-    if (!kTable && n >= 5) {
-        if (tid == 0) {
-            uint32_t bin = (n + 15u) & ~15u, bnx = (n * 2 + 15u) & ~15u;
-            fence_proxy_async();                                   // shared memory is reused from sub-unit to sub-unit
-            mbar_expect_tx(&bar, bin + bnx);
-            tma_load_1d(s_in, in, bin, &bar);
-            tma_load_1d(s_next, next4g + (size_t)(u * g.spu + k) * kMaxUnitBytes, bnx, &bar);
-        }
-        mbar_wait(&bar, k & 1);
-    }
-    // min_len at the start of the unit's first DEFLATE block (calculate_min_match_len)
-    if (k == 0 && g.unit_len[sb.u] - g.unit_dict[sb.u] >= 512) {
-        const uint32_t span = min(min(g.unit_len[sb.u] - g.unit_dict[sb.u], n - nb), 4096u);
-        const uint8_t *b8 = kTable ? in : (const uint8_t *)s_in;
-        for (uint32_t i = tid; i < span; i += kSparseThreads) { const uint32_t c = b8[nb + i]; atomicOr(&s_used[c >> 5], 1u << (c & 31)); }
-        __syncthreads();
-        uint32_t nu = 0;
-        for (int i = 0; i < 8; i++) nu += __popc(s_used[i]);
-        min_len = choose_min_match_len(nu, depth);
-    }
-    const bool lazy = mode != 0;
-    // The reference's parser loop (compress_hc, modes 0 and 1) as a state machine that performs exactly ONE search per
-    // trip — a fresh full-depth search at an iteration start, or the depth/2 look-ahead behind a pending match — so that
-    // the lanes of a warp, each parsing its own chunk, meet in the same chain-walk loop.  Runs from iteration start q0
-    // until an iteration ends at or beyond `stop`, or (rejoin) on an iteration start this chunk's speculation marked.
-    const uint32_t lcap = (chunk + 264 + 3) & ~3u;                // tokens one chunk's parse can produce (multiple of 4: 16-byte stores)
-    uint32_t *spec_list = tokens ? lists_g + (size_t)u * kSparseListWords + (size_t)tid * lcap : nullptr;
-    uint32_t *gap_list = tokens ? spec_list + kSparseListWords / 2 : nullptr;
-    uint16_t *idx_at = tokens ? idx_g + (size_t)u * kMaxUnitBytes : nullptr;
-    const uint8_t *b8 = kTable ? in : (const uint8_t *)s_in;
-    auto run = [&](uint32_t q0, uint32_t stop, bool rejoin, uint32_t *list, uint32_t &cnt) -> uint32_t {
-        uint32_t q = q0, m = 0, cl = 0, co = 0;
-        uint32_t in_look = 0;                                      // 0 fresh search, 1 look-ahead at m + 1 (depth/2), 2 at m + 2 (depth/4, lazy2)
-        // tokens leave in 16-byte stores: four at a time through a register buffer (lists are 16-byte aligned, lcap % 4 == 0)
-        uint32_t eb0 = 0, eb1 = 0, eb2 = 0;
-        auto emit = [&](uint32_t t) {
-            if (!list) return;
-            const uint32_t k = cnt & 3u;
-            if (k == 0) eb0 = t; else if (k == 1) eb1 = t; else if (k == 2) eb2 = t;
-            else if (cnt < lcap) *(uint4 *)(list + (cnt - 3)) = make_uint4(eb0, eb1, eb2, t);
-            cnt++;
-        };
-        auto flush = [&]() {
-            if (!list) return;
-            const uint32_t k = cnt & 3u, b = cnt - k;
-            if (k >= 1 && b < lcap) list[b] = eb0;
-            if (k >= 2 && b + 1 < lcap) list[b + 1] = eb1;
-            if (k >= 3 && b + 2 < lcap) list[b + 2] = eb2;
-        };
-        for (;;) {
-            if (!in_look) {
-                if (q >= stop || (rejoin && ((s_iter[q >> 5] >> (q & 31)) & 1u))) { flush(); return q; }
-                if (!rejoin) { atomicOr(&s_iter[q >> 5], 1u << (q & 31)); if (list) idx_at[q] = (uint16_t)cnt; }
-            }
-            const uint32_t pos = in_look ? m + in_look : q;
-            if (pos >= safe) s_over = 1;
-            const uint32_t maxlen = pos < n ? min((uint32_t)kMaxMatch, n - pos) : 0u;
-            uint64_t e = 0;
-            if (!in_look || maxlen >= 5) {
-                if (kTable) {
-                    e = maxlen >= 5 ? (uint64_t)M[pos] : 0ull;
-                    if (in_look == 2) {                            // lazy2's second look-ahead: the depth/4 column takes the place of depth/2
-                        const uint64_t c2 = M2[pos];
-                        e = (e & ~(0x7FFFFFull << 23)) | ((c2 & 0xFFull) << 23) | (((c2 >> 8) & 0x7FFFull) << 31);
-                    }
-                } else {
-                    e = sparse_entry(s_in, s_next, p3, n, pos, (uint32_t)depth, (uint32_t)nice, lazy, !in_look, (uint32_t)depth >> in_look);
-                    if (!tokens) atomicOr(&M[pos], (unsigned long long)e);
-                }
-            }
-            if (!in_look) {
-                table_search(e, min_len - 1, false, maxlen, cl, co);
-                if (mode == 0) {
-                    if (cl >= min_len && (cl > 3 || co <= 4096)) { emit(kTokEnd | 0x80000000u | (cl << 16) | co); q += cl; }
-                    else { emit(kTokEnd | b8[q]); q += 1; }
-                    continue;
-                }
-                if (cl < min_len || (cl == 3 && co > 8192)) { emit(kTokEnd | b8[q]); q = q + 1; continue; }
-                m = q;
-                if (cl >= min((uint32_t)nice, maxlen)) { emit(kTokEnd | 0x80000000u | (cl << 16) | co); q = m + cl; continue; }
-                in_look = 1;
-            } else {
-                uint32_t nl, no;
-                table_search(e, cl - 1, true, maxlen, nl, no);
-                if (nl >= cl && 4 * (int)(nl - cl) + ((int)bsr32(co) - (int)bsr32(no)) > (in_look == 1 ? 2 : 6)) {
-                    emit(b8[m]);                                   // literal(s); the look-ahead match becomes the pending one
-                    if (in_look == 2) emit(b8[m + 1]);
-                    m += in_look; cl = nl; co = no;
-                    if (cl >= min((uint32_t)nice, maxlen)) { emit(kTokEnd | 0x80000000u | (cl << 16) | co); q = m + cl; in_look = 0; }
-                    else in_look = 1;
-                } else if (mode == 2 && in_look == 1) in_look = 2;   // lazy2: one more look, two positions ahead
-                else { emit(kTokEnd | 0x80000000u | (cl << 16) | co); q = m + cl; in_look = 0; }
-            }
-        }
-    };
-    // An epoch = one speculation + stitch of [E, ne) with one min_len.  The event scan below ends it early where min_len
-    // changes; the rest of the sub-unit is then speculated again from there (tokens mode; the table form has one epoch).
-    uint32_t E = nb, epoch_entry = (carry != 0xFFFFFFFFu) ? carry - sb.h : nb;
-    for (uint32_t epoch = 0;; epoch++) {
-    if (epoch) {
-        __syncthreads();
-        for (uint32_t i = tid; i < 2048; i += kSparseThreads) s_iter[i] = 0;
-        __syncthreads();
-    }
-    // ---- (A) speculate: chunk `tid` from its first position ----
-    const uint32_t nchunks = (ne - E + chunk - 1) / chunk;        // <= kSparseThreads (the launcher checks)
-    const uint32_t s0 = E + tid * chunk, s1 = min(ne, s0 + chunk);
-    uint32_t spec_end = 0;
-    uint32_t cnt_spec = 0, cnt_gap = 0, gap_q = 0;
-    if (tid < nchunks) {
-        spec_end = run(s0, s1, false, spec_list, cnt_spec);
-        s_end[tid] = spec_end;
-    }
-    __syncthreads();
-    // ---- (B) stitch: re-parse from the previous chunk's end until this chunk's own speculation takes over ----
-    // chunk 0 of a later sub-unit enters where the previous sub-unit's parse ended (unit position -> local position)
-    const bool chained0 = tid == 0 && epoch_entry != E;
-    uint32_t entry = (tid >= 1 && tid < nchunks) ? s_end[tid - 1] : chained0 ? epoch_entry : 0xFFFFFFFFu, done_entry = 0xFFFFFFFFu;
-    for (;;) {
-        if (tid == 0) s_flag = 0;
-        __syncthreads();
-        if ((tid >= 1 || chained0) && tid < nchunks && entry != done_entry) {
-            uint32_t new_end;
-            if (entry >= s1) new_end = entry;                      // the chunk lies inside a match of an earlier one
-            else {
-                cnt_gap = 0;
-                gap_q = run(entry, s1, true, gap_list, cnt_gap);
-                new_end = gap_q < s1 ? spec_end : gap_q;
-            }
-            done_entry = entry;
-            if (new_end != s_end[tid]) { s_end[tid] = new_end; s_flag = 1; }
-        }
-        __syncthreads();
-        const bool again = s_flag != 0;
-        if (tid >= 1 && tid < nchunks) entry = s_end[tid - 1];
-        __syncthreads();
-        if (!again) break;
-    }
-    if (!tokens) return;                                           // table mode: single sub-unit
-    // ---- (C) compact the tokens of the true parse: [gap tokens | this chunk's speculation from the re-join on] ----
-    uint32_t ngap = 0, from = 0, nspec = 0;
-    if (tid < nchunks) {
-        if (tid == 0 && !chained0) nspec = cnt_spec;
-        else if (entry < s1) {
-            ngap = cnt_gap;
-            if (gap_q < s1) { from = idx_at[gap_q]; nspec = cnt_spec - from; }
-        }
-        if (cnt_spec > lcap || ngap > lcap) s_over = 1;
-    }
-    const uint32_t mine = ngap + nspec, lane = tid & 31, warp = tid >> 5;
-    uint32_t incl = mine;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= (uint32_t)d) incl += v; }
-    if (lane == 31) s_wsum[warp] = incl;
-    __syncthreads();
-    uint32_t base = 0, total = 0;
-    for (int w = 0; w < kSparseThreads / 32; w++) { const uint32_t v = s_wsum[w]; if (w < (int)warp) base += v; total += v; }
-    // every warp copies the lists of its 32 chunks one after another, lanes striding over the tokens (coalesced both ways)
-    if (!s_over && tok_run + total <= g.tok_stride) {
-        uint32_t *unit_tok = tok_base + (size_t)sb.u * g.tok_stride + tok_run;
-        const uint32_t my_off = base + incl - mine;
-        for (uint32_t c = 0; c < 32; c++) {
-            const uint32_t c_gap = __shfl_sync(0xFFFFFFFFu, ngap, c), c_spec = __shfl_sync(0xFFFFFFFFu, nspec, c);
-            const uint32_t c_from = __shfl_sync(0xFFFFFFFFu, from, c), c_off = __shfl_sync(0xFFFFFFFFu, my_off, c);
-            const uint32_t *c_gl = lists_g + (size_t)u * kSparseListWords + kSparseListWords / 2 + (size_t)(warp * 32 + c) * lcap;
-            const uint32_t *c_sl = lists_g + (size_t)u * kSparseListWords + (size_t)(warp * 32 + c) * lcap;
-            for (uint32_t j = lane; j < c_gap; j += 32) unit_tok[c_off + j] = c_gl[j];
-            for (uint32_t j = lane; j < c_spec; j += 32) unit_tok[c_off + c_gap + j] = c_sl[c_from + j];
-        }
-    }
-    if (tok_run + total > g.tok_stride) s_over = 1;
-    tok_run += total;
-    const uint32_t sub_end = sb.h + s_end[nchunks - 1];            // unit position where this epoch's parse ends
-    __syncthreads();                                               // the compacted tokens are visible to warp 0
-    // ---- (D) event scan (warp 0): replay what outlives an iteration over the new tokens, stop where min_len changes ----
-    if (warp == 0) {
-        const uint32_t *ut = tok_base + (size_t)sb.u * g.tok_stride;
-        const uint32_t limit_t = s_over ? rt : tok_run;
-        bool changed = false;
-        uint32_t new_min = min_len;
-        while (rt < limit_t && !changed) {
-            const uint32_t max_block_end = (unit_n - bb < (uint32_t)kSoftMaxBlockLength + (uint32_t)kMinBlockLength) ? unit_n : bb + (uint32_t)kSoftMaxBlockLength;
-            const uint32_t ti = rt + lane;
-            const bool valid = ti < limit_t;
-            const uint32_t t = valid ? ut[ti] : 0u;
-            const bool isM = (t >> 31) & 1u, ends_iter = (t >> 30) & 1u;
-            const uint32_t mlen = isM ? (t >> 16) & 0x1FF : 1u, lit = t & 0xFF;
-            const uint32_t len = valid ? mlen : 0u;
-            uint32_t pincl = len;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, pincl, d); if (lane >= (uint32_t)d) pincl += v; }
-            const uint32_t q = rp + pincl - len, e_l = rp + pincl;
-            const uint32_t prev_ends = __shfl_up_sync(0xFFFFFFFFu, (uint32_t)ends_iter, 1);
-            const bool starts_iter = lane == 0 ? (in_h == 0) : (prev_ends != 0);
-            const uint32_t vis = __ballot_sync(0xFFFFFFFFu, valid);
-            const uint32_t lastl = 31 - __clz(vis);
-            uint32_t commit_mask = vis, next_p = __shfl_sync(0xFFFFFFFFu, e_l, lastl), next_h = __shfl_sync(0xFFFFFFFFu, (uint32_t)!ends_iter, lastl);
-            int event = 0;
-            const uint32_t mmask = __ballot_sync(0xFFFFFFFFu, valid && isM);
-            const uint32_t rmask = (mode != 0) ? __ballot_sync(0xFFFFFFFFu, valid && starts_iter && q >= next_recalc) : 0u;
-            const uint32_t cmask = __ballot_sync(0xFFFFFFFFu, valid && ends_iter && (num_new_obs + lane + 1 >= (uint32_t)kObsPerCheck) &&
-                                                             (e_l - bb >= (uint32_t)kMinBlockLength) && (unit_n - e_l >= (uint32_t)kMinBlockLength));
-            const uint32_t mincl = __popc(mmask & (lane == 31 ? 0xFFFFFFFFu : ((2u << lane) - 1)));
-            const uint32_t smask = __ballot_sync(0xFFFFFFFFu, valid && ends_iter && ((nmatch + mincl >= (uint32_t)kSeqStoreLength) || e_l >= max_block_end));
-            const int Lr = rmask ? __ffs(rmask) - 1 : 64, Lc = cmask ? __ffs(cmask) - 1 : 64, Ls = smask ? __ffs(smask) - 1 : 64;
-            if (Lr <= Lc && Lr <= Ls && Lr < 64) { event = 1; commit_mask = vis & ((1u << Lr) - 1); next_p = __shfl_sync(0xFFFFFFFFu, q, Lr); next_h = 0; }
-            else if (Ls <= Lc && Ls < 64) { event = 3; commit_mask = vis & (Ls == 31 ? 0xFFFFFFFFu : ((2u << Ls) - 1)); next_p = __shfl_sync(0xFFFFFFFFu, e_l, Ls); next_h = 0; }
-            else if (Lc < 64) { event = 2; commit_mask = vis & (Lc == 31 ? 0xFFFFFFFFu : ((2u << Lc) - 1)); next_p = __shfl_sync(0xFFFFFFFFu, e_l, Lc); next_h = 0; }
-            if ((commit_mask >> lane) & 1u) {
-                if (!isM) atomicAdd(&s_fl[lit], 1u);
-                atomicAdd(&s_nobs[isM ? 8 + (mlen >= 9) : (((lit >> 5) & 6) | (lit & 1))], 1u);
-            }
-            const uint32_t added = __popc(commit_mask);
-            num_new_obs += added; rt += added; nmatch += __popc(commit_mask & mmask);
-            in_h = next_h; rp = next_p;
-            __syncwarp();
-            bool end_block = false;
-            if (event == 1) {
-                uint32_t tot = 0;
-                for (int i = 0; i < 8; i++) tot += s_fl[lane * 8 + i];
-                for (int o = 16; o; o >>= 1) tot += __shfl_xor_sync(0xFFFFFFFFu, tot, o);
-                uint32_t cutoff = tot >> 10, nu = 0;
-                for (int i = 0; i < 8; i++) nu += (s_fl[lane * 8 + i] > cutoff);
-                for (int o = 16; o; o >>= 1) nu += __shfl_xor_sync(0xFFFFFFFFu, nu, o);
-                new_min = choose_min_match_len(nu, depth);
-                next_recalc += min(unit_n - next_recalc, rp - bb);
-                if (new_min != min_len) changed = true;
-            } else if (event == 2) {
-                const uint32_t block_length = rp - bb;
-                if (num_obs > 0) {
-                    uint32_t d = 0;
-                    if (lane < 10) {
-                        const uint32_t expected = s_obs[lane] * num_new_obs, actual = s_nobs[lane] * num_obs;
-                        d = actual > expected ? actual - expected : expected - actual;
-                    }
-                    for (int o = 16; o; o >>= 1) d += __shfl_xor_sync(0xFFFFFFFFu, d, o);
-                    const uint32_t num_items = num_obs + num_new_obs;
-                    uint32_t cutoff = num_new_obs * 200 / 512 * num_obs;
-                    if (block_length < 10000 && num_items < 8192) cutoff += (uint32_t)((uint64_t)cutoff * (8192 - num_items) / 8192);
-                    if (d + (block_length / 4096) * num_obs >= cutoff) end_block = true;
-                }
-                if (!end_block) {
-                    if (lane < 10) { s_obs[lane] += s_nobs[lane]; s_nobs[lane] = 0; }
-                    num_obs += num_new_obs; num_new_obs = 0;
-                }
-                __syncwarp();
-            } else if (event == 3) end_block = true;
-            if (end_block && rp < unit_n) {
-                // a new DEFLATE block starts at rp: fresh statistics, calculate_min_match_len over its first <= 4096 bytes
-                bb = rp; next_recalc = bb + min(unit_n - bb, 10000u);
-                num_obs = 0; num_new_obs = 0; nmatch = 0;
-                for (int i = 0; i < 8; i++) s_fl[lane * 8 + i] = 0;
-                if (lane < 10) { s_obs[lane] = 0; s_nobs[lane] = 0; }
-                const uint32_t mbe = (unit_n - bb < (uint32_t)kSoftMaxBlockLength + (uint32_t)kMinBlockLength) ? unit_n : bb + (uint32_t)kSoftMaxBlockLength;
-                new_min = 3;
-                if (mbe - bb >= 512) {
-                    const uint8_t *ub = g.in + (size_t)sb.u * g.in_stride;
-                    const uint32_t span = min(mbe - bb, 4096u);
-                    uint32_t used[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                    for (uint32_t i = lane; i < span; i += 32) { const uint32_t c = ub[bb + i]; used[c >> 5] |= 1u << (c & 31); }
-                    uint32_t nu = 0;
-                    for (int w = 0; w < 8; w++) { uint32_t v = used[w]; for (int o = 16; o; o >>= 1) v |= __shfl_xor_sync(0xFFFFFFFFu, v, o); nu += __popc(v); }
-                    new_min = choose_min_match_len(nu, depth);
-                }
-                __syncwarp();
-                if (new_min != min_len) changed = true;
-            }
-        }
-        if (lane == 0) { s_chg[0] = changed ? 1u : 0u; s_chg[1] = rt; s_chg[2] = rp; s_chg[3] = new_min; }
-    }
-    __syncthreads();
-    if (s_chg[0]) {
-        // min_len changes at unit position s_chg[2] (token s_chg[1]): what was parsed behind it is void
-        tok_run = s_chg[1]; min_len = s_chg[3];
-        const uint32_t newE = s_chg[2] - sb.h;
-        if (newE >= ne) { carry = s_chg[2]; break; }               // the change falls on the sub-unit's end: nothing to redo here
-        E = newE; epoch_entry = newE;
-        continue;
-    }
-    carry = sub_end;
-    break;
-    }   // epochs
-    }
-    __syncthreads();
-    if (tokens && tid == 0) unit_ntok[u] = s_over ? 0xFFFFFFFFu : tok_run;
-}
-
-template <int kSparse>
 __global__ void __launch_bounds__(kEmitThreads)
 k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
        const uint64_t *__restrict__ mtab, const uint32_t *__restrict__ mtab2, const uint32_t *__restrict__ crc_in, uint32_t *__restrict__ tok_base,
        uint8_t *__restrict__ out_base, uint32_t *__restrict__ out_len, int32_t *__restrict__ out_status,
-       int mode, int depth, int nice, int level, int format, int pass2, const uint32_t *__restrict__ unit_ntok)
+       int mode, int depth, int nice, int level, int format)
 {
     __shared__ EmitShared S;
     const uint32_t u = blockIdx.x, tid = threadIdx.x;
-    // kSparse: the match table comes from k_smatch — every committed entry's valid bits are checked and a miss flags the
-    // unit (kStatusMiss); pass2: the filtered second pass that redoes exactly those units from k_match's full table
-    if (pass2 && out_status[u] != kStatusMiss) return;
     const uint32_t n = g.unit_len[u];          // dictionary + data
     const uint32_t dict = g.unit_dict[u];      // preset dictionary in front of the data (never emitted)
     const uint32_t dl = n - dict;              // bytes to encode
@@ -1520,7 +751,6 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
     } else if (dl > 0) {
         uint32_t p = dict;           // parser position (warp 0 is authoritative)
         uint32_t next_recalc = 0, min_len = 3;
-        uint32_t tcur = 0;                        // tokens mode (kSparse == 2): next token of k_smatch's list
         while (true) {
             // ---------------- block start (all threads) ----------------
             if (tid == 0) S.blk_begin = p;
@@ -1559,98 +789,6 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
                 next_recalc = bb + min(n - bb, 10000u);
                 uint32_t ntok = 0, nmatch = 0, num_obs = 0, num_new_obs = 0, in_h = 0;
                 bool end_block = false;
-                if (kSparse == 2) {
-                    // ---- replay: the tokens of the true parse are already in tok[] (k_smatch, in order, iteration ends
-                    // flagged); what is left of the parser here is where its DEFLATE blocks end — block-split checks, the
-                    // sequence-store limit, SOFT_MAX_BLOCK_LENGTH — evaluated 32 tokens at a time exactly where the sequential
-                    // parser would.
-                    // (min_len and its re-calculation schedule only steer the parser: k_smatch has replayed them already)
-                    const uint32_t total = unit_ntok[u];
-                    bool miss = (total == 0xFFFFFFFFu);                                  // k_smatch gave up on this unit
-                    if (lane == 0) S.tok0 = tcur;
-                    uint32_t tpre = (!miss && tcur + lane < total) ? tok[tcur + lane] : 0u;      // this window's token, loaded one window ahead
-                    do {
-                        const uint32_t ti = tcur + lane;
-                        const bool valid = !miss && ti < total;
-                        const uint32_t t = valid ? tpre : 0u;
-                        const uint32_t tfut = (!miss && ti + 32 < total) ? tok[ti + 32] : 0u;      // the usual next window (all 32 tokens commit)
-                        const bool isM = (t >> 31) & 1u, ends_iter = (t >> 30) & 1u;
-                        const uint32_t mlen = isM ? (t >> 16) & 0x1FF : 1u, moff = t & 0xFFFF, lit = t & 0xFF;
-                        const uint32_t len = valid ? mlen : 0u;
-                        uint32_t pincl = len;
-#pragma unroll
-                        for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, pincl, d); if (lane >= (uint32_t)d) pincl += v; }
-                        const uint32_t e_l = p + pincl;
-                        const uint32_t vis = __ballot_sync(0xFFFFFFFFu, valid);
-                        if (vis == 0) { miss = true; break; }                 // the list ended before the data did
-                        const uint32_t incl = lane + 1;                       // tokens up to and including mine
-                        uint32_t commit_mask = vis;
-                        uint32_t next_p = __shfl_sync(0xFFFFFFFFu, e_l, 31 - __clz(vis));
-                        uint32_t next_h = __shfl_sync(0xFFFFFFFFu, (uint32_t)!ends_iter, 31 - __clz(vis));
-                        int event = 0;
-                        const uint32_t mmask = __ballot_sync(0xFFFFFFFFu, valid && isM);
-                        const bool may_check = (num_new_obs + 32 >= (uint32_t)kObsPerCheck) && (next_p - bb >= (uint32_t)kMinBlockLength) && (n - p > (uint32_t)kMinBlockLength);
-                        const bool may_seq = nmatch + 32 >= seq_limit;
-                        const bool may_max = next_p >= max_block_end && max_block_end < n;       // SOFT_MAX_BLOCK_LENGTH reached inside this window
-                        if (may_check || may_seq || may_max) {
-                            const uint32_t cmask = __ballot_sync(0xFFFFFFFFu, valid && ends_iter && (num_new_obs + incl >= (uint32_t)kObsPerCheck) &&
-                                                                             (e_l - bb >= (uint32_t)kMinBlockLength) && (n - e_l >= (uint32_t)kMinBlockLength));
-                            const uint32_t mincl = __popc(mmask & (lane == 31 ? 0xFFFFFFFFu : ((2u << lane) - 1)));
-                            // the loop condition `p < max_block_end` and the sequence-store limit both end the block after the iteration
-                            const uint32_t smask = __ballot_sync(0xFFFFFFFFu, valid && ends_iter && ((nmatch + mincl >= seq_limit) || e_l >= max_block_end));
-                            const int Lc = cmask ? __ffs(cmask) - 1 : 64, Ls = smask ? __ffs(smask) - 1 : 64;
-                            if (Ls <= Lc && Ls < 64) { event = 3; commit_mask = vis & (Ls == 31 ? 0xFFFFFFFFu : ((2u << Ls) - 1)); next_p = __shfl_sync(0xFFFFFFFFu, e_l, Ls); next_h = 0; }
-                            else if (Lc < 64) { event = 2; commit_mask = vis & (Lc == 31 ? 0xFFFFFFFFu : ((2u << Lc) - 1)); next_p = __shfl_sync(0xFFFFFFFFu, e_l, Lc); next_h = 0; }
-                        }
-                        if ((commit_mask >> lane) & 1u) {
-                            const uint32_t lsym = isM ? kFirstLenSym + len_slot_only(mlen) : lit;
-                            const uint32_t ocls = isM ? 8 + (mlen >= 9) : (((lit >> 5) & 6) | (lit & 1));
-                            atomicAdd(&S.fl[lsym], 1u);
-                            atomicAdd(&S.new_obs[ocls], 1u);
-                            if (isM) atomicAdd(&S.fo[off_slot_only(moff)], 1u);
-                            tok[ti] = isM ? (0x80000000u | (mlen << 16) | moff) : lit;      // the flag bit goes
-                        }
-                        {
-                            const uint32_t added = __popc(commit_mask);
-                            ntok += added; num_new_obs += added; tcur += added;
-                            nmatch += __popc(commit_mask & mmask);
-                            __syncwarp();
-                            tpre = added == 32 ? tfut : ((tcur + lane < total) ? tok[tcur + lane] : 0u);   // an event cut the window short: reload
-                        }
-                        in_h = next_h;
-                        p = next_p;
-                        __syncwarp();
-                        if (event == 2) {
-                            uint32_t block_length = p - bb;
-                            if (num_obs > 0) {
-                                uint32_t d = 0;
-                                if (lane < 10) {
-                                    uint32_t expected = S.obs[lane] * num_new_obs, actual = S.new_obs[lane] * num_obs;
-                                    d = actual > expected ? actual - expected : expected - actual;
-                                }
-                                for (int o = 16; o; o >>= 1) d += __shfl_xor_sync(0xFFFFFFFFu, d, o);
-                                uint32_t num_items = num_obs + num_new_obs;
-                                uint32_t cutoff = num_new_obs * 200 / 512 * num_obs;
-                                if (block_length < 10000 && num_items < 8192)
-                                    cutoff += (uint32_t)((uint64_t)cutoff * (8192 - num_items) / 8192);
-                                if (d + (block_length / 4096) * num_obs >= cutoff) end_block = true;
-                            }
-                            if (!end_block) {
-                                if (lane < 10) { S.obs[lane] += S.new_obs[lane]; S.new_obs[lane] = 0; }
-                                num_obs += num_new_obs; num_new_obs = 0;
-                            }
-                            __syncwarp();
-                        } else if (event == 3) {
-                            end_block = true;
-                        }
-                    } while (p < max_block_end && !end_block && !miss);
-                    if (miss) {
-                        // flag the unit (redone from the full table by the second pass) and close this block at the end of
-                        // the data so that the rest of the kernel stays well-formed
-                        if (lane == 0) S.status = kStatusMiss;
-                        p = n;
-                    }
-                } else
                 if (mode == 2) {
                     // lazy2 (levels 8-9): the reference's loop restated one iteration at a time; every lane
                     // runs the same (uniform) control flow, lane 0 commits.  These levels are bound by the
@@ -1763,7 +901,6 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
                     //   word = advance (bits 0-8) | next-is-H (bit 9) | token-is-match (bit 10)
                     const uint32_t q = p + lane;
                     uint32_t wF = 1, wH = 1, lenF = 0, offF = 0, lenH = 0, offH = 0;
-                    bool badF = false, badH = false;            // sparse table: this step used an entry that is not there
                     if (q < max_block_end) {
                         const uint64_t e0 = P.M(q);
                         const uint32_t maxlen = min((uint32_t)kMaxMatch, n - q);
@@ -1772,8 +909,6 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
                         const uint32_t nice_q = min((uint32_t)nice, maxlen);
                         uint32_t cl, co;
                         table_search(e0, min_len - 1, false, maxlen, cl, co);
-                        const bool e1_missing = kSparse == 1 && maxlen1 >= 5 && !(e1 & kValidB);
-                        if (kSparse == 1) { badF = !(e0 & kValidA); badH = !(e0 & kValidB); }
                         if (mode == 0) {
                             if (cl >= min_len && (cl > 3 || co <= 4096)) { lenF = cl; offF = co; wF = cl | (1u << 10); }
                         } else {
@@ -1784,7 +919,6 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
                                     uint32_t nl, no;
                                     table_search(e1, cl - 1, true, maxlen1, nl, no);
                                     take = !(nl >= cl && 4 * (int)(nl - cl) + ((int)bsr32(co) - (int)bsr32(no)) > 2);
-                                    badF = badF || e1_missing;
                                 }
                                 if (take) { lenF = cl; offF = co; wF = cl | (1u << 10); }
                                 else wF = 1u | (1u << 9);
@@ -1799,7 +933,6 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
                                     uint32_t nl, no;
                                     table_search(e1, hl - 1, true, maxlen1, nl, no);
                                     take = !(nl >= hl && 4 * (int)(nl - hl) + ((int)bsr32(ho) - (int)bsr32(no)) > 2);
-                                    badH = badH || e1_missing;
                                 }
                                 if (take) { lenH = hl; offH = ho; wH = hl | (1u << 10); }
                                 else wH = 1u | (1u << 9);
@@ -1839,10 +972,6 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
                         if (Lr <= Lc && Lr <= Ls && Lr < 64) { event = 1; commit_mask = vis & ((1u << Lr) - 1); next_p = p + Lr; next_h = 0; }
                         else if (Ls <= Lc && Ls < 64) { event = 3; commit_mask = vis & (Ls == 31 ? 0xFFFFFFFFu : ((2u << Ls) - 1)); next_p = __shfl_sync(0xFFFFFFFFu, e_l, Ls); next_h = 0; }
                         else if (Lc < 64) { event = 2; commit_mask = vis & (Lc == 31 ? 0xFFFFFFFFu : ((2u << Lc) - 1)); next_p = __shfl_sync(0xFFFFFFFFu, e_l, Lc); next_h = 0; }
-                    }
-                    if (kSparse == 1) {
-                        const uint32_t missed = __ballot_sync(0xFFFFFFFFu, ((commit_mask >> lane) & 1u) && (asH ? badH : badF));
-                        if (missed && lane == 0) S.status = kStatusMiss;
                     }
                     // ---- commit ----
                     if ((commit_mask >> lane) & 1u) {
@@ -2062,7 +1191,7 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
                         uint32_t ti = t0 + tid * kTokPerThread + k;
                         uint64_t c = 0; uint32_t l = 0;
                         if (ti < ntok) {
-                            uint32_t t = tok[(kSparse == 2 ? S.tok0 : 0u) + ti];
+                            uint32_t t = tok[ti];
                             if (!(t & 0x80000000u)) {
                                 c = dynamic ? S.lcw[t] : c_static_litlen_cw[t];
                                 l = dynamic ? ll[t] : c_static_litlen_len[t];
@@ -2157,7 +1286,6 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
             uint32_t avail = dl + max(128u, (uint32_t)((double)dl * 0.1));
             if (nbytes > avail) st = -4;
         }
-        if (kSparse != 0) { atomicAdd(&g_sparse_stats[0], 1ull); if (S.status == kStatusMiss) { atomicAdd(&g_sparse_stats[1], 1ull); st = kStatusMiss; } }
         out_len[u * 2] = total;
         out_len[u * 2 + 1] = hdr_off;
         out_status[u] = st;
@@ -2194,24 +1322,27 @@ k_scan(const uint32_t *__restrict__ out_len, uint64_t *__restrict__ offsets, uin
 
 __global__ void __launch_bounds__(256)
 k_gather(const uint8_t *__restrict__ out_base, const uint32_t *__restrict__ out_len, const uint64_t *__restrict__ offsets,
-         uint8_t *__restrict__ dst, const int32_t *__restrict__ overflow, uint32_t out_stride)
+         uint8_t *__restrict__ dst, const int32_t *__restrict__ overflow, uint32_t out_stride, uint32_t nunits)
 {
-    const uint32_t u = blockIdx.x;
     if (*overflow) return;
-    const uint32_t len = out_len[2 * u], hoff = out_len[2 * u + 1];
-    const uint8_t *src = out_base + (size_t)u * out_stride + hoff;
-    uint8_t *d = dst + offsets[u];
-    // head bytes until d is 4-byte aligned
-    uint32_t head = min(len, (uint32_t)((4 - ((uintptr_t)d & 3)) & 3));
-    if (threadIdx.x < head) d[threadIdx.x] = src[threadIdx.x];
-    const uint8_t *s2 = src + head; uint8_t *d2 = d + head;
-    uint32_t rem = len - head, nw = rem >> 2;
-    const uint32_t *sw = (const uint32_t *)((uintptr_t)s2 & ~(uintptr_t)3);
-    uint32_t sh = ((uintptr_t)s2 & 3) * 8;
-    uint32_t *dw = (uint32_t *)d2;
-    for (uint32_t i = threadIdx.x; i < nw; i += blockDim.x) dw[i] = __funnelshift_r(sw[i], sw[i + 1], sh);
-    uint32_t tail = rem & 3;
-    if (threadIdx.x < tail) d2[nw * 4 + threadIdx.x] = s2[nw * 4 + threadIdx.x];
+    // grid-stride over the units: a host-memory target (zero-copy D2H) is launched with a small grid — its stores drain
+    // at PCIe speed, and a full grid of stalled CTAs would hold the thread slots the next batch's kernels need
+    for (uint32_t u = blockIdx.x; u < nunits; u += gridDim.x) {
+        const uint32_t len = out_len[2 * u], hoff = out_len[2 * u + 1];
+        const uint8_t *src = out_base + (size_t)u * out_stride + hoff;
+        uint8_t *d = dst + offsets[u];
+        // head bytes until d is 4-byte aligned
+        uint32_t head = min(len, (uint32_t)((4 - ((uintptr_t)d & 3)) & 3));
+        if (threadIdx.x < head) d[threadIdx.x] = src[threadIdx.x];
+        const uint8_t *s2 = src + head; uint8_t *d2 = d + head;
+        uint32_t rem = len - head, nw = rem >> 2;
+        const uint32_t *sw = (const uint32_t *)((uintptr_t)s2 & ~(uintptr_t)3);
+        uint32_t sh = ((uintptr_t)s2 & 3) * 8;
+        uint32_t *dw = (uint32_t *)d2;
+        for (uint32_t i = threadIdx.x; i < nw; i += blockDim.x) dw[i] = __funnelshift_r(sw[i], sw[i + 1], sh);
+        uint32_t tail = rem & 3;
+        if (threadIdx.x < tail) d2[nw * 4 + threadIdx.x] = s2[nw * 4 + threadIdx.x];
+    }
 }
 
 // =============================================================================
@@ -2332,12 +1463,6 @@ cudaError_t launch_check_combine(const uint32_t *sums, const uint32_t *unit_len,
     return cudaGetLastError();
 }
 
-void read_sparse_stats(unsigned long long *out2, bool reset)
-{
-    cudaMemcpyFromSymbol(out2, g_sparse_stats, 2 * sizeof(unsigned long long));
-    if (reset) { unsigned long long z[2] = {0, 0}; cudaMemcpyToSymbol(g_sparse_stats, z, sizeof z); }
-}
-
 void read_phase_counters(unsigned long long *out, bool reset)
 {
     cudaMemcpyFromSymbol(out, g_phase, sizeof(unsigned long long) * 32);
@@ -2369,16 +1494,12 @@ static Geo make_geo(const DeflateBatch &b)
 cudaError_t launch_deflate_pipeline(const DeflateBatch &b, cudaStream_t st)
 {
     static bool attr_done[64] = {};          // function attributes are per device (several GPUs in one process)
-    const int chain_smem = (65536 + 32768) * 2;
     const int match_smem = kInStride + 65536 * 2;
     int cur_dev = 0;
     cudaGetDevice(&cur_dev);
     if (cur_dev < 0 || cur_dev >= 64) return cudaErrorInvalidValue;
     if (!attr_done[cur_dev]) {
-        cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, chain_smem);
         cudaFuncSetAttribute(k_match, cudaFuncAttributeMaxDynamicSharedMemorySize, match_smem);
-        cudaFuncSetAttribute(k_match2, cudaFuncAttributeMaxDynamicSharedMemorySize, match_smem);
-        cudaFuncSetAttribute(k_smatch<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, match_smem);
         attr_done[cur_dev] = true;
     }
     if (b.nunits == 0) return cudaSuccess;
@@ -2392,77 +1513,18 @@ cudaError_t launch_deflate_pipeline(const DeflateBatch &b, cudaStream_t st)
     }
     if (lp.mode >= 0) {
         if (b.timer) b.timer->start(KT_CHAIN, st);
-        if (b.lists) {
-            GZPB_LAUNCH(k_split, b.nunits * b.spu, kSplitThreads, 0, st, g, b.lists, b.list_start, b.next4, b.prev3, lp.ht);
-            DBG_SYNC("k_split");
-            if (b.gidx) {
-                // match path v2: hash4 lists -> groups (k_group), hash3 lists -> links (k_link)
-                GZPB_LAUNCH(k_group, b.nunits * b.spu * kL4, 32, 0, st, g, b.lists, b.list_start, b.next4, b.gidx, b.gocc);
-                DBG_SYNC("k_group");
-                GZPB_LAUNCH(k_link, b.nunits * b.spu * kL3, 32, 0, st, g, b.lists, b.list_start, b.next4, b.prev3, b.clen, 1);
-            } else {
-                GZPB_LAUNCH(k_link, b.nunits * b.spu * kSplitLists, 32, 0, st, g, b.lists, b.list_start, b.next4, b.prev3, b.clen, 0);
-            }
-            DBG_SYNC("k_link");
-        } else {
-            if (lp.ht) return cudaErrorInvalidValue;   // the legacy k_chain path has no 15-bit mode
-            GZPB_LAUNCH(k_chain, b.nunits * b.spu, kChainThreads, chain_smem, st, g, b.next4, b.prev3);
-            DBG_SYNC("k_chain");
-        }
+        GZPB_LAUNCH(k_split, b.nunits * b.spu, kSplitThreads, 0, st, g, b.lists, b.list_start, b.next4, b.prev3, lp.ht);
+        DBG_SYNC("k_split");
+        GZPB_LAUNCH(k_link, b.nunits * b.spu * kSplitLists, 32, 0, st, g, b.lists, b.list_start, b.next4, b.prev3, b.clen);
+        DBG_SYNC("k_link");
         if (b.timer) { b.timer->stop(st); b.timer->start(KT_MATCH, st); }
-        const bool sparse_tokens = b.sparse == 2 && b.slists && b.sidx && b.sntok;
-        if (b.sparse && b.sparse != 3 && b.lists && (b.spu == 1 || sparse_tokens) && !lp.ht && (lp.mode == 0 || lp.mode == 1 || (lp.mode == 2 && sparse_tokens))) {
-            // sparse path: speculative table, parse with miss detection, then the two filtered fallback launches
-            const uint32_t chunk = (b.sparse_chunk >= kSparseChunk && b.sparse_chunk <= 4096u) ? b.sparse_chunk : kSparseChunk;   // 512 x 128 covers a unit
-            const bool tokens = sparse_tokens;
-            GZPB_LAUNCH(k_smatch<false>, b.nunits, kSparseThreads, match_smem, st, g, b.next4, b.prev3, b.mtab, (const uint32_t *)nullptr, lp.depth, lp.nice, lp.mode, chunk,
-                        tokens ? b.tokens : (uint32_t *)nullptr, b.slists, b.sidx, b.sntok);
-            DBG_SYNC("k_smatch");
-            if (b.timer) { b.timer->stop(st); b.timer->start(KT_EMIT, st); }
-            if (tokens)
-                GZPB_LAUNCH(k_emit<2>, b.nunits, kEmitThreads, 0, st, g, b.unit_flags, b.mtab, b.mtab2, b.crc, b.tokens, b.out, b.out_len,
-                            b.status, lp.mode, lp.depth, lp.nice, b.level, b.format, 0, b.sntok);
-            else
-                GZPB_LAUNCH(k_emit<1>, b.nunits, kEmitThreads, 0, st, g, b.unit_flags, b.mtab, b.mtab2, b.crc, b.tokens, b.out, b.out_len,
-                            b.status, lp.mode, lp.depth, lp.nice, b.level, b.format, 0, (const uint32_t *)nullptr);
-            DBG_SYNC("k_emit(sparse)");
-            if (b.timer) { b.timer->stop(st); b.timer->start(KT_MATCH, st); }
-            GZPB_LAUNCH(k_match, b.nunits * b.spu, kMatchThreads, match_smem, st, g, b.next4, b.prev3, b.mtab, b.mtab2, b.clen, b.order, lp.depth, lp.nice, lp.mode, 1, lp.ht, b.status);
-            DBG_SYNC("k_match(missed)");
-            if (b.timer) { b.timer->stop(st); b.timer->start(KT_EMIT, st); }
-            GZPB_LAUNCH(k_emit<0>, b.nunits, kEmitThreads, 0, st, g, b.unit_flags, b.mtab, b.mtab2, b.crc, b.tokens, b.out, b.out_len,
-                        b.status, lp.mode, lp.depth, lp.nice, b.level, b.format, 1, (const uint32_t *)nullptr);
-            DBG_SYNC("k_emit(missed)");
-            if (b.timer) b.timer->stop(st);
-            return cudaGetLastError();
-        }
-        if (b.gidx && b.lists)
-            GZPB_LAUNCH(k_match2, b.nunits * b.spu, kMatchThreads, match_smem, st, g, b.next4, b.prev3, b.gidx, b.gocc, b.mtab, b.mtab2, b.clen, b.order, lp.depth, lp.nice, lp.mode, lp.ht);
-        else
-            GZPB_LAUNCH(k_match, b.nunits * b.spu, kMatchThreads, match_smem, st, g, b.next4, b.prev3, b.mtab, b.mtab2, b.clen, b.order, lp.depth, lp.nice, lp.mode, b.lists != nullptr, lp.ht, (const int32_t *)nullptr);
+        GZPB_LAUNCH(k_match, b.nunits * b.spu, kMatchThreads, match_smem, st, g, b.next4, b.prev3, b.mtab, b.mtab2, b.clen, b.order, lp.depth, lp.nice, lp.mode, lp.ht);
         DBG_SYNC("k_match");
         if (b.timer) b.timer->stop(st);
-        if (b.sparse == 3 && b.slists && b.sidx && b.sntok && !lp.ht) {
-            // table-fed chunk parse: tokens of the true parse from k_match's full table (k_smatch<true>), k_emit<2> ends the
-            // DEFLATE blocks and packs; a unit whose chunk lists overflowed is redone by the sequential parser (pass 2)
-            const uint32_t chunk = (b.sparse_chunk >= kSparseChunk && b.sparse_chunk <= 4096u) ? b.sparse_chunk : kSparseChunk;
-            if (b.timer) b.timer->start(KT_EMIT, st);
-            GZPB_LAUNCH(k_smatch<true>, b.nunits, kSparseThreads, 0, st, g, b.next4, b.prev3, b.mtab, b.mtab2, lp.depth, lp.nice, lp.mode, chunk,
-                        b.tokens, b.slists, b.sidx, b.sntok);
-            DBG_SYNC("k_tparse");
-            GZPB_LAUNCH(k_emit<2>, b.nunits, kEmitThreads, 0, st, g, b.unit_flags, b.mtab, b.mtab2, b.crc, b.tokens, b.out, b.out_len,
-                        b.status, lp.mode, lp.depth, lp.nice, b.level, b.format, 0, b.sntok);
-            DBG_SYNC("k_emit<2>");
-            GZPB_LAUNCH(k_emit<0>, b.nunits, kEmitThreads, 0, st, g, b.unit_flags, b.mtab, b.mtab2, b.crc, b.tokens, b.out, b.out_len,
-                        b.status, lp.mode, lp.depth, lp.nice, b.level, b.format, 1, (const uint32_t *)nullptr);
-            DBG_SYNC("k_emit(missed)");
-            if (b.timer) b.timer->stop(st);
-            return cudaGetLastError();
-        }
     }
     if (b.timer) b.timer->start(KT_EMIT, st);
-    GZPB_LAUNCH(k_emit<0>, b.nunits, kEmitThreads, 0, st, g, b.unit_flags, b.mtab, b.mtab2, b.crc, b.tokens, b.out, b.out_len,
-                                             b.status, lp.mode, lp.depth, lp.nice, b.level, b.format, 0, (const uint32_t *)nullptr);
+    GZPB_LAUNCH(k_emit, b.nunits, kEmitThreads, 0, st, g, b.unit_flags, b.mtab, b.mtab2, b.crc, b.tokens, b.out, b.out_len,
+                b.status, lp.mode, lp.depth, lp.nice, b.level, b.format);
     DBG_SYNC("k_emit");
     if (b.timer) b.timer->stop(st);
     return cudaGetLastError();
@@ -2475,7 +1537,8 @@ cudaError_t launch_pack(const DeflateBatch &b, cudaStream_t st)
     if (b.nunits == 0) return cudaSuccess;
     if (b.timer) b.timer->start(KT_GATHER, st);
     GZPB_LAUNCH(k_scan, 1, 1024, 0, st, b.out_len, b.offsets, b.nunits, b.base_ptr, b.packed_cap, b.overflow, b.end_mirror);
-    GZPB_LAUNCH(k_gather, b.nunits, 256, 0, st, b.out, b.out_len, b.offsets, b.packed, b.overflow, b.out_stride);
+    const uint32_t ggrid = (b.packed_on_host && b.nunits > (uint32_t)b.packed_on_host) ? (uint32_t)b.packed_on_host : b.nunits;
+    GZPB_LAUNCH(k_gather, ggrid, 256, 0, st, b.out, b.out_len, b.offsets, b.packed, b.overflow, b.out_stride, b.nunits);
     DBG_SYNC("k_scan+k_gather");
     if (b.timer) b.timer->stop(st);
     return cudaGetLastError();

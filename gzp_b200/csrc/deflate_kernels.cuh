@@ -41,13 +41,12 @@ struct DeflateBatch {
     const uint32_t *unit_flags;  // bit0 = is_last (BGZF EOF), bit1 = sync flush (no BFINAL)
     uint16_t *next4;          // nunits * spu * 65536
     uint16_t *prev3;          // nunits * spu * 65536
-    uint32_t *lists;          // nunits * spu * 2 * 65536 (k_split position lists), NULL = use k_chain
+    uint32_t *lists;          // nunits * spu * 2 * 65536 (k_split position lists)
     uint32_t *list_start;     // nunits * spu * 16
     uint64_t *mtab;           // nunits * m_stride
     uint32_t *mtab2;          // nunits * m_stride, lazy2 levels only (depth/4 column), else NULL
     uint8_t *clen;            // nunits * spu * 65536 (chain lengths, k_match scratch)
     uint16_t *order;          // nunits * spu * 65536 (positions sorted by chain length)
-    uint16_t *gidx, *gocc;    // nunits * spu * 65536 each: match path v2 (k_group / k_match2: `next4` then holds the hash groups), else NULL
     uint32_t *crc;            // nunits
     uint32_t *tokens;         // nunits * kTokStride
     uint8_t *out;             // nunits * kOutStride
@@ -56,6 +55,7 @@ struct DeflateBatch {
     uint64_t *offsets;        // nunits + 1 (exclusive scan of sizes; [nunits] = total)
     uint8_t *packed;          // compacted stream (device memory or mapped pinned host memory)
     uint64_t packed_cap;      // bytes available at `packed`
+    int packed_on_host;       // > 0: `packed` is mapped host memory — k_gather runs with at most this many thread blocks (0 = one per unit)
     const uint64_t *base_ptr; // device-visible address holding this batch's first offset (NULL = 0)
     uint64_t *end_mirror;     // optional second copy of offsets[nunits] (mapped pinned host memory: the next batch of a multi-device stream reads its base there)
     int32_t *overflow;        // set to 1 by k_scan when the batch would exceed packed_cap
@@ -63,15 +63,10 @@ struct DeflateBatch {
     uint32_t in_stride, m_stride, tok_stride, out_stride;   // per-unit strides (bytes / entries / tokens / bytes)
     uint32_t spu, seg;        // sub-units per unit and new positions per sub-unit (gzpb_common.cuh: Geo)
     int check_kind;           // -1 none, 0 CRC-32, 1 Adler-32 (written to `crc`)
-    int sparse;               // 1 = sparse match table (k_smatch) where the level and the unit geometry allow it, 2 = k_smatch also hands over the tokens
-    uint32_t *slists; uint16_t *sidx; uint32_t *sntok;   // sparse == 2: per-chunk token lists (kSparseListWords per unit), iteration index per position, tokens per unit
-    uint32_t sparse_chunk;    // positions per speculative chunk (0 = default)
 };
 
-constexpr size_t kSparseListWordsPerUnit = 2 * 204800;
 void upload_deflate_constants();
 void read_phase_counters(unsigned long long *out, bool reset);
-void read_sparse_stats(unsigned long long *out2, bool reset);
 cudaError_t launch_deflate_pipeline(const DeflateBatch &b, cudaStream_t st);
 cudaError_t launch_pack(const DeflateBatch &b, cudaStream_t st);
 cudaError_t launch_check_combine(const uint32_t *sums, const uint32_t *unit_len, const uint32_t *unit_dict, uint32_t nunits, int kind,

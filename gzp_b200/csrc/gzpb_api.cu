@@ -43,8 +43,7 @@ struct Lane {
     // device
     uint8_t *d_in = nullptr;
     uint32_t *d_len = nullptr, *d_dict = nullptr, *d_flags = nullptr, *d_crc = nullptr, *d_tokens = nullptr, *d_out_len = nullptr;
-    uint16_t *d_next4 = nullptr, *d_prev3 = nullptr, *d_order = nullptr, *d_gidx = nullptr, *d_gocc = nullptr, *d_sidx = nullptr;
-    uint32_t *d_slists = nullptr, *d_sntok = nullptr;
+    uint16_t *d_next4 = nullptr, *d_prev3 = nullptr, *d_order = nullptr;
     uint8_t *d_clen = nullptr;
     uint64_t *d_mtab = nullptr, *d_offsets = nullptr;
     uint32_t *d_mtab2 = nullptr, *d_lists = nullptr, *d_list_start = nullptr;
@@ -69,11 +68,9 @@ struct gzpb_ctx {
     uint32_t dict_cap = 0;                         // 32 KiB for the dictionary formats, else 0
     uint32_t in_stride = 0, m_stride = 0, tok_stride = 0, out_stride = 0, spu = 1, seg = 0;
     int check_kind = -1;
-    uint32_t sparse_chunk = 0;                     // GZPB_SPARSE_CHUNK: positions per speculative chunk (tuning aid)
-    int sparse = 0;                                // GZPB_SPARSE=1: k_smatch (speculative sparse match table) + filtered fallback; 2: k_smatch hands over tokens
-    bool match_v2 = false;                         // GZPB_MATCH_V2=1: k_group + k_match2 instead of k_link(hash4) + k_match
     uint32_t cpu = 1;                              // gather entries per unit (Snap: 64 KiB chunks per block)
     Lane lanes[kLanes];
+    int gather_host_ctas = 148;                      // thread blocks of a k_gather that writes host memory (GZPB_GATHER_CTAS; measured 148/296/592/all: e2e 8.79/8.68/8.55/8.45 GiB/s)
     uint64_t *d_base0 = nullptr, *h_base0 = nullptr; // first stream offset of a gzpb_encode_stream call: device copy / mapped pinned copy
     bool scratch_only = false;
     KernelTimer timer;
@@ -232,19 +229,8 @@ static int lane_alloc(gzpb_ctx *c, Lane &L, bool with_io)
     CK(dmalloc(&L.d_next4, U * c->spu * kMaxUnitBytes));
     CK(dmalloc(&L.d_prev3, U * c->spu * kMaxUnitBytes));
     CK(dmalloc(&L.d_order, U * c->spu * kMaxUnitBytes));
-    if (!getenv("GZPB_USE_KCHAIN")) {
-        CK(dmalloc(&L.d_lists, U * c->spu * 2 * kMaxUnitBytes));
-        CK(dmalloc(&L.d_list_start, U * c->spu * 32));
-        if (c->sparse >= 2) {
-            CK(dmalloc(&L.d_slists, U * kSparseListWordsPerUnit));
-            CK(dmalloc(&L.d_sidx, U * (size_t)kMaxUnitBytes));
-            CK(dmalloc(&L.d_sntok, U));
-        }
-        if (c->match_v2) {
-            CK(dmalloc(&L.d_gidx, U * c->spu * kMaxUnitBytes));
-            CK(dmalloc(&L.d_gocc, U * c->spu * kMaxUnitBytes));
-        }
-    }
+    CK(dmalloc(&L.d_lists, U * c->spu * 2 * kMaxUnitBytes));
+    CK(dmalloc(&L.d_list_start, U * c->spu * 32));
     CK(dmalloc(&L.d_clen, U * c->spu * kMaxUnitBytes));
     CK(dmalloc(&L.d_mtab, U * c->m_stride));
     if (c->level >= 8) CK(dmalloc(&L.d_mtab2, U * c->m_stride));
@@ -279,7 +265,7 @@ static int lane_alloc(gzpb_ctx *c, Lane &L, bool with_io)
 static void lane_free(Lane &L)
 {
     cudaFree(L.d_in); cudaFree(L.d_len); cudaFree(L.d_dict); cudaFree(L.d_flags); cudaFree(L.d_crc); cudaFree(L.d_tokens); cudaFree(L.d_out_len);
-    cudaFree(L.d_slists); cudaFree(L.d_sidx); cudaFree(L.d_sntok); cudaFree(L.d_gidx); cudaFree(L.d_gocc); cudaFree(L.d_next4); cudaFree(L.d_prev3); cudaFree(L.d_order); cudaFree(L.d_clen); cudaFree(L.d_mtab2); cudaFree(L.d_lists); cudaFree(L.d_list_start); cudaFree(L.d_mtab); cudaFree(L.d_offsets); cudaFree(L.d_out); cudaFree(L.d_packed);
+    cudaFree(L.d_next4); cudaFree(L.d_prev3); cudaFree(L.d_order); cudaFree(L.d_clen); cudaFree(L.d_mtab2); cudaFree(L.d_lists); cudaFree(L.d_list_start); cudaFree(L.d_mtab); cudaFree(L.d_offsets); cudaFree(L.d_out); cudaFree(L.d_packed);
     cudaFree(L.d_status); cudaFree(L.d_overflow); cudaFree(L.d_comb); cudaFreeHost(L.h_comb);
     cudaFreeHost(L.h_in); cudaFreeHost(L.h_packed); cudaFreeHost(L.h_len); cudaFreeHost(L.h_dict); cudaFreeHost(L.h_flags); cudaFreeHost(L.h_crc);
     cudaFreeHost(L.h_offsets); cudaFreeHost(L.h_status); cudaFreeHost(L.h_overflow); cudaFreeHost(L.h_end);
@@ -313,10 +299,7 @@ extern "C" int gzpb_create(gzpb_ctx **out, int device, int format, int level, si
     gzpb_ctx *c = new gzpb_ctx();
     c->device = device; c->format = format; c->level = level;
     c->max_block_bytes = max_block_bytes; c->max_units = max_blocks_in_flight;
-    { const char *e = getenv("GZPB_SPARSE"); c->sparse = (e && (*e == '1' || *e == '2' || *e == '3') && !getenv("GZPB_USE_KCHAIN")) ? *e - '0' : 0; }
-    { const char *e = getenv("GZPB_SPARSE_CHUNK"); c->sparse_chunk = e ? (uint32_t)atoi(e) : 0; }
-    { const char *e = getenv("GZPB_MATCH_V2"); c->match_v2 = e && *e == '1' && !getenv("GZPB_USE_KCHAIN"); }
-    if (c->sparse) c->match_v2 = false;            // the variants are alternatives: k_smatch walks k_link's chains, not k_group's arrays
+    { const char *e = getenv("GZPB_GATHER_CTAS"); if (e && atoi(e) > 0) c->gather_host_ctas = atoi(e); }
     {
         const size_t U = dict + max_block_bytes;
         c->dict_cap = (uint32_t)dict;
@@ -393,11 +376,7 @@ extern "C" uint64_t gzpb_launch_count(gzpb_ctx *c) { return c ? c->launches : 0;
 extern "C" const char *gzpb_ctx_variant(gzpb_ctx *c)
 {
     if (!c) return "";
-    if (c->format == GZPB_SNAP) return "snap";
-    if (c->sparse == 3) return "split+link+match+tparse";
-    if (c->sparse == 2) return "split+link+smatch+replay";
-    if (c->sparse) return "split+link+smatch";
-    return c->match_v2 ? "split+group+match2" : (c->lanes[0].d_lists ? "split+link+match" : "chain+match");
+    return c->format == GZPB_SNAP ? "snap" : "split+link+match";
 }
 
 /* debugging aid (not part of the reference-facing surface): SM-cycle totals per kernel phase */
@@ -407,20 +386,6 @@ extern "C" int gzpb_debug_phase_cycles(gzpb_ctx *c, uint64_t *out32, int reset)
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     read_phase_counters((unsigned long long *)out32, reset != 0);
-    return GZPB_OK;
-}
-
-/* statistics of the sparse path (GZPB_SPARSE=1): units parsed from the speculative table, units that missed an entry
- * and were redone from the full table; device-wide counters */
-extern "C" int gzpb_debug_sparse_stats(gzpb_ctx *c, uint64_t *units, uint64_t *missed, int reset)
-{
-    if (!c) return GZPB_EINVAL;
-    cudaSetDevice(c->device);
-    cudaDeviceSynchronize();
-    unsigned long long v[2] = {0, 0};
-    read_sparse_stats(v, reset != 0);
-    if (units) *units = v[0];
-    if (missed) *missed = v[1];
     return GZPB_OK;
 }
 
@@ -439,10 +404,10 @@ static void fill_batch(gzpb_ctx *c, Lane &L, DeflateBatch &b, size_t n)
     b.nunits = (uint32_t)n; b.level = c->level; b.format = c->format;
     b.in = L.d_in; b.unit_len = L.d_len; b.unit_dict = L.d_dict; b.unit_flags = L.d_flags;
     b.in_stride = c->in_stride; b.m_stride = c->m_stride; b.tok_stride = c->tok_stride; b.out_stride = c->out_stride;
-    b.spu = c->spu; b.seg = c->seg; b.check_kind = c->check_kind; b.sparse = c->sparse; b.sparse_chunk = c->sparse_chunk; b.slists = L.d_slists; b.sidx = L.d_sidx; b.sntok = L.d_sntok;
-    b.next4 = L.d_next4; b.prev3 = L.d_prev3; b.clen = L.d_clen; b.order = L.d_order; b.mtab = L.d_mtab; b.mtab2 = L.d_mtab2; b.gidx = L.d_gidx; b.gocc = L.d_gocc; b.lists = L.d_lists; b.list_start = L.d_list_start; b.crc = L.d_crc; b.tokens = L.d_tokens;
+    b.spu = c->spu; b.seg = c->seg; b.check_kind = c->check_kind;
+    b.next4 = L.d_next4; b.prev3 = L.d_prev3; b.clen = L.d_clen; b.order = L.d_order; b.mtab = L.d_mtab; b.mtab2 = L.d_mtab2; b.lists = L.d_lists; b.list_start = L.d_list_start; b.crc = L.d_crc; b.tokens = L.d_tokens;
     b.out = L.d_out; b.out_len = L.d_out_len; b.status = L.d_status; b.offsets = L.d_offsets;
-    b.packed = nullptr; b.packed_cap = 0; b.base_ptr = nullptr; b.end_mirror = nullptr; b.overflow = L.d_overflow;
+    b.packed = nullptr; b.packed_cap = 0; b.packed_on_host = 0; b.base_ptr = nullptr; b.end_mirror = nullptr; b.overflow = L.d_overflow;
     b.timer = c->profiling ? &c->timer : nullptr;
 }
 
@@ -599,6 +564,7 @@ static int lane_pack(gzpb_ctx *c, Lane &L, uint8_t *packed, uint64_t cap, const 
     const size_t entries = L.nunits * c->cpu;
     b.nunits = (uint32_t)entries;
     b.packed = packed; b.packed_cap = cap; b.base_ptr = base_ptr; b.end_mirror = end_mirror;
+    b.packed_on_host = c->gather_host_ctas;          // lane_pack always gathers into pinned host memory (zero-copy D2H)
     if (prev) CK(cudaStreamWaitEvent(L.st, prev->ev_scan, 0));
     CK(launch_pack(b, L.st));
     CK(cudaEventRecord(L.ev_scan, L.st));
@@ -1095,6 +1061,8 @@ extern "C" int gzpb_writer_create_multi(gzpb_writer **out, const int *devices, s
         int rc = gzpb_create(&c, devices[i], format, level, buffer_size, blocks_in_flight);
         if (rc != GZPB_OK) { gzpb_writer_destroy(w); return rc; }
         w->ctx.push_back(c);
+        for (int l = 0; l < kLanes; l++)                        // the writer's batches always land in the lanes' pinned output
+            if ((rc = lane_host_packed(c, c->lanes[l])) != GZPB_OK) { gzpb_writer_destroy(w); return rc; }
     }
     w->slab_cap = (blocks_in_flight + 1) * buffer_size;
     const size_t nslabs = ndevices * kLanes + 1;                 // every batch in flight keeps its slab + the one being filled

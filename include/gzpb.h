@@ -211,8 +211,7 @@ void gzpb_host_free(void *p);
 int gzpb_set_profiling(gzpb_ctx *ctx, int on);
 int gzpb_kernel_ms(gzpb_ctx *ctx, const char *name, double *total_ms, uint64_t *launches);
 uint64_t gzpb_launch_count(gzpb_ctx *ctx);
-/* which kernel set this context runs: "split+link+match" (default), "split+group+match2" (GZPB_MATCH_V2=1 in
- * the environment at gzpb_create: hash groups instead of linked chains), "chain+match" (GZPB_USE_KCHAIN), "snap" */
+/* which kernel set this context runs: "split+link+match" (the DEFLATE family) or "snap" */
 const char *gzpb_ctx_variant(gzpb_ctx *ctx);
 
 /* ---- decoder: the ParDecompress path -------------------------------

@@ -95,24 +95,6 @@ def deflate(data, level=6):
     return out.raw[:n]
 
 
-def deflate_spec(data, level=6, chunk=256, dictionary=b"", flush=0):
-    """Raw DEFLATE through the chunk-speculative restatement of the parser (oracle_deflate_spec); returns
-    (bytes, stats dict).  Must equal deflate() / oracle_deflate_ex byte for byte."""
-    L = lib()
-    L.oracle_deflate_spec.restype = ctypes.c_size_t
-    L.oracle_deflate_spec.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_size_t,
-                                      ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_uint64)]
-    buf = bytes(dictionary) + bytes(data)
-    cap = len(data) + max(128, len(data) // 10) + 64
-    out = ctypes.create_string_buffer(cap)
-    st = (ctypes.c_uint64 * 8)()
-    n = L.oracle_deflate_spec(buf, len(dictionary), len(data), level, flush, chunk, out, cap, st)
-    if n == 0:
-        raise ValueError("oracle_deflate_spec: output did not fit / unsupported level")
-    names = ("epochs", "positions_speculated", "chunks_skipped", "positions_restitched", "min_len_changes", "deflate_blocks", "searches", "hops")
-    return out.raw[:n], dict(zip(names, (int(v) for v in st)))
-
-
 def deflate_ex(data, level=6, dictionary=b"", flush=0):
     """oracle_deflate_ex: raw DEFLATE of `data` primed with `dictionary`; flush 0 = finish, 1 = sync flush."""
     L = lib()

@@ -644,245 +644,6 @@ static void compress_hc(comp_t *c, const uint8_t *in, size_t start, size_t n, bi
 }
 
 
-/* ---- chunk-speculative restatement of compress_hc ---------------------------------
- * The SAME parser, organised the way a GPU can run it: the hash chains are built up front for every
- * position (they do not depend on parsing decisions: every position is inserted, by a search or by a
- * skip), the data is cut into chunks that are parsed independently from their first position
- * ("speculation"), the true parse is stitched from chunk to chunk (a chunk's speculative iterations are
- * adopted from the first position where the true parse stands at one of their starts), and the events
- * that carry state across the block — the min_len re-calculation schedule, the block-split statistics,
- * the sequence-store limit — are replayed over the stitched iterations; an event that changes min_len or
- * ends the DEFLATE block closes the epoch and everything behind it is speculated again.
- * Must produce exactly the bytes of compress_hc (tests/test_oracle.py::test_speculative_parse_*). */
-typedef struct { uint32_t start, end, tok0, ntok; } spec_iter_t;
-typedef struct {
-    const uint8_t *in; size_t n;
-    const int32_t *c3of, *next;       /* static chains: hash3 predecessor of p, hash4 chain link of p */
-    unsigned depth, nice; int mode;
-    uint64_t searches, hops;
-} spec_ctx_t;
-
-static unsigned lm_static(spec_ctx_t *x, size_t p, unsigned best_len, unsigned max_len, unsigned nice_len, unsigned depth,
-                          unsigned *off_ret)
-{
-    const uint8_t *in = x->in;
-    size_t best_q = p;
-    const unsigned depth0 = depth;
-    if (max_len < 5) goto out;
-    x->searches++;
-    {
-        int32_t c3 = x->c3of[p], c4 = x->next[p];
-        uint32_t seq4 = ld32(in + p);
-        if (best_len < 4) {
-            if (!INWIN(c3)) goto out;
-            if (best_len < 3) {
-                if ((ld32(in + c3) & 0xFFFFFF) == (seq4 & 0xFFFFFF)) { best_len = 3; best_q = (size_t)c3; }
-            }
-            if (!INWIN(c4)) goto out;
-            for (;;) {
-                if (ld32(in + c4) == seq4) break;
-                c4 = x->next[c4];
-                if (!INWIN(c4) || !--depth) goto out;
-            }
-            best_q = (size_t)c4;
-            best_len = lz_extend(in + p, in + c4, 4, max_len);
-            if (best_len >= nice_len) goto out;
-            c4 = x->next[c4];
-            if (!INWIN(c4) || !--depth) goto out;
-        } else {
-            if (!INWIN(c4) || best_len >= nice_len) goto out;
-        }
-        for (;;) {
-            for (;;) {
-                if (ld32(in + c4 + best_len - 3) == ld32(in + p + best_len - 3) && ld32(in + c4) == seq4) break;
-                c4 = x->next[c4];
-                if (!INWIN(c4) || !--depth) goto out;
-            }
-            unsigned l = lz_extend(in + p, in + c4, 4, max_len);
-            if (l > best_len) {
-                best_len = l; best_q = (size_t)c4;
-                if (best_len >= nice_len) goto out;
-            }
-            c4 = x->next[c4];
-            if (!INWIN(c4) || !--depth) goto out;
-        }
-    }
-out:
-    x->hops += depth0 - depth;
-    *off_ret = (unsigned)(p - best_q);
-    return best_len;
-}
-
-/* One iteration of the parser loop of compress_hc from a fresh state at p; tokens appended to tok[*nt...].
- * Returns the position at which the next iteration starts. */
-static size_t spec_iteration(spec_ctx_t *x, size_t p, unsigned min_len, uint32_t *tok, size_t *nt)
-{
-    const uint8_t *in = x->in; const size_t n = x->n;
-    unsigned max_len, nice_len, cur_len, cur_off, next_len, next_off;
-#define SADJ(rem) do { max_len = (rem) < MAX_MATCH ? (unsigned)(rem) : MAX_MATCH; nice_len = x->nice < max_len ? x->nice : max_len; } while (0)
-#define SLIT(b) (tok[(*nt)++] = (uint32_t)(b))
-#define SMATCH(l, o) (tok[(*nt)++] = 0x80000000u | ((uint32_t)(l) << 16) | (uint32_t)(o))
-    SADJ(n - p);
-    cur_len = lm_static(x, p, min_len - 1, max_len, nice_len, x->depth, &cur_off);
-    if (x->mode == 0) {
-        if (cur_len >= min_len && (cur_len > MIN_MATCH || cur_off <= 4096)) { SMATCH(cur_len, cur_off); return p + cur_len; }
-        SLIT(in[p]);
-        return p + 1;
-    }
-    if (cur_len < min_len || (cur_len == MIN_MATCH && cur_off > 8192)) { SLIT(in[p]); return p + 1; }
-    p++;
-    for (;;) {
-        if (cur_len >= nice_len) { SMATCH(cur_len, cur_off); return p + cur_len - 1; }
-        SADJ(n - p);
-        next_len = lm_static(x, p, cur_len - 1, max_len, nice_len, x->depth >> 1, &next_off);
-        p++;
-        if (next_len >= cur_len && 4 * (int)(next_len - cur_len) + ((int)bsr32(cur_off) - (int)bsr32(next_off)) > 2) {
-            SLIT(in[p - 2]);
-            cur_len = next_len; cur_off = next_off;
-            continue;
-        }
-        if (x->mode == 2) {
-            SADJ(n - p);
-            next_len = lm_static(x, p, cur_len - 1, max_len, nice_len, x->depth >> 2, &next_off);
-            p++;
-            if (next_len >= cur_len && 4 * (int)(next_len - cur_len) + ((int)bsr32(cur_off) - (int)bsr32(next_off)) > 6) {
-                SLIT(in[p - 3]); SLIT(in[p - 2]);
-                cur_len = next_len; cur_off = next_off;
-                continue;
-            }
-            SMATCH(cur_len, cur_off);
-            return cur_len > 3 ? p + cur_len - 3 : p;
-        }
-        SMATCH(cur_len, cur_off);
-        return p + cur_len - 2;
-    }
-#undef SADJ
-#undef SLIT
-#undef SMATCH
-}
-
-typedef struct {
-    uint32_t *stok, *gtok; spec_iter_t *sit, *git; size_t *cfirst;
-    size_t ngi;                                                           /* stitched iterations of the current epoch */
-} spec_epoch_t;
-
-/* (A) speculate every chunk of [E, n) from its first position with `min_len`, (B) stitch the true parse from E. */
-static void spec_build_epoch(spec_ctx_t *x, spec_epoch_t *ep, size_t E, unsigned min_len, size_t chunk, uint64_t stats[8])
-{
-    const size_t n = x->n;
-    size_t nst = 0, nsi = 0, nchunks = 0;
-    stats[0]++;                                                           /* epochs */
-    for (size_t s = E; s < n; s += chunk) {
-        const size_t s_next = s + chunk < n ? s + chunk : n;
-        ep->cfirst[nchunks++] = nsi;
-        for (size_t q = s; q < s_next;) {
-            spec_iter_t *it = &ep->sit[nsi++];
-            size_t before = nst;
-            it->start = (uint32_t)q; it->tok0 = (uint32_t)nst;
-            q = spec_iteration(x, q, min_len, ep->stok, &nst);
-            it->ntok = (uint32_t)(nst - before); it->end = (uint32_t)q;
-            stats[1] += it->end - it->start;                             /* positions parsed speculatively */
-        }
-    }
-    ep->cfirst[nchunks] = nsi;
-    size_t ngt = 0, ngi = 0, e = E;
-    for (size_t k = 0; k < nchunks; k++) {
-        const size_t s = E + k * chunk, s_next = s + chunk < n ? s + chunk : n;
-        if (e >= s_next) { stats[2]++; continue; }                       /* chunk covered by a match of an earlier one */
-        size_t j = ep->cfirst[k];
-        for (;;) {
-            while (j < ep->cfirst[k + 1] && ep->sit[j].start < e) j++;
-            if (j < ep->cfirst[k + 1] && ep->sit[j].start == e) break;   /* the true parse stands at a speculative iteration start */
-            if (e >= s_next) { j = ep->cfirst[k + 1]; break; }           /* never re-joined inside this chunk */
-            spec_iter_t *g = &ep->git[ngi++];
-            size_t before = ngt;
-            g->start = (uint32_t)e; g->tok0 = (uint32_t)ngt;
-            e = spec_iteration(x, e, min_len, ep->gtok, &ngt);
-            g->ntok = (uint32_t)(ngt - before); g->end = (uint32_t)e;
-            stats[3] += g->end - g->start;                               /* positions parsed again while stitching */
-        }
-        for (; j < ep->cfirst[k + 1]; j++) {                             /* adopt the rest of the chunk's speculation */
-            spec_iter_t *g = &ep->git[ngi++];
-            *g = ep->sit[j];
-            g->tok0 = (uint32_t)ngt;
-            memcpy(ep->gtok + ngt, ep->stok + ep->sit[j].tok0, ep->sit[j].ntok * sizeof(uint32_t));
-            ngt += ep->sit[j].ntok;
-            e = ep->sit[j].end;
-        }
-    }
-    ep->ngi = ngi;
-}
-
-static void compress_hc_spec(comp_t *c, const uint8_t *in, size_t start, size_t n, bitw_t *w, int final_block, size_t chunk,
-                             uint64_t stats[8])
-{
-    spec_ctx_t x; memset(&x, 0, sizeof x);
-    spec_epoch_t ep; memset(&ep, 0, sizeof ep);
-    int32_t *c3of = malloc((n + 1) * sizeof(int32_t));
-    ep.stok = malloc((2 * n + 1024) * sizeof(uint32_t));                 /* speculative tokens of the current epoch */
-    ep.sit = malloc((n + 16) * sizeof(spec_iter_t));                     /* speculative iterations, chunk after chunk */
-    ep.gtok = malloc((n + 1024) * sizeof(uint32_t));                     /* stitched tokens */
-    ep.git = malloc((n + 16) * sizeof(spec_iter_t));                     /* stitched iterations (tok0 indexes gtok) */
-    ep.cfirst = malloc((n / chunk + 4) * sizeof(size_t));                /* first iteration of each chunk in sit[] */
-    x.in = in; x.n = n; x.c3of = c3of; x.next = c->next; x.depth = c->max_depth; x.nice = c->nice; x.mode = c->mode;
-
-    /* static chains: what longest_match / skip_bytes leave behind, for every position with 5 bytes ahead */
-    for (size_t i = 0; i < 32768; i++) c->head3[i] = -1;
-    for (size_t i = 0; i < 65536; i++) c->head4[i] = -1;
-    for (size_t q = 0; q + 5 <= n; q++) {
-        uint32_t seq = ld32(in + q);
-        uint32_t h3 = lz_hash(seq & 0xFFFFFF, 15), h4 = lz_hash(seq, 16);
-        if (q == 0 && start == 0) h3 = h4 = 0;                           /* next_hashes start at {0, 0} */
-        c3of[q] = c->head3[h3]; c->next[q] = c->head4[h4];
-        c->head3[h3] = (int32_t)q; c->head4[h4] = (int32_t)q;
-    }
-
-    /* Parse decisions depend on the position and on min_len only, so one speculation + stitch ("epoch") stays valid
-     * across DEFLATE block boundaries and re-calculations until min_len actually changes. */
-    size_t p = start, gi = 0;
-    unsigned min_len = 0;
-    int have_epoch = 0;
-    do {
-        const size_t block_begin = p;
-        const size_t max_block_end = (n - p < SOFT_MAX_BLOCK_LENGTH + MIN_BLOCK_LENGTH) ? n : p + SOFT_MAX_BLOCK_LENGTH;
-        size_t next_recalc = p + (n - p < 10000 ? n - p : 10000);
-        begin_block(c);
-        {
-            unsigned m = calc_min_match_len(in + p, max_block_end - p, c->max_depth);
-            if (!have_epoch || m != min_len) {
-                if (have_epoch) stats[4]++;                              /* min_len changes */
-                min_len = m; have_epoch = 1;
-                spec_build_epoch(&x, &ep, p, min_len, chunk, stats); gi = 0;
-            }
-        }
-        /* ---- (C) replay the events over the stitched iterations ---- */
-        for (;;) {
-            const spec_iter_t *g = &ep.git[gi];
-            if (c->mode != 0 && g->start >= next_recalc) {
-                unsigned m2 = recalc_min_match_len(c->fl, c->max_depth);
-                size_t a = n - next_recalc, b = g->start - block_begin;
-                next_recalc += a < b ? a : b;
-                if (m2 != min_len) {
-                    stats[4]++;
-                    min_len = m2;
-                    spec_build_epoch(&x, &ep, g->start, min_len, chunk, stats); gi = 0;
-                    g = &ep.git[0];
-                }
-            }
-            for (uint32_t t = 0; t < g->ntok; t++) {
-                uint32_t tk = ep.gtok[g->tok0 + t];
-                if (tk & 0x80000000u) choose_match(c, (tk >> 16) & 0x7FFF, tk & 0xFFFF); else choose_literal(c, (uint8_t)tk);
-            }
-            p = g->end; gi++;
-            if (!(p < max_block_end && c->nmatch < SEQ_STORE_LENGTH && !should_end_block(c, block_begin, p, n))) break;
-        }
-        finish_block(c, w, in, block_begin, p - block_begin, final_block && p == n);
-        stats[5]++;                                                       /* DEFLATE blocks */
-    } while (p != n && !w->overflow);
-    stats[6] += x.searches; stats[7] += x.hops;
-    free(c3of); free(ep.stok); free(ep.sit); free(ep.gtok); free(ep.git); free(ep.cfirst);
-}
-
 /* ---- level 1: deflate_compress_fastest() + ht_matchfinder restated ---------------------------
  * Hash table of 2-entry buckets keyed by a 15-bit hash of 4 bytes (HT_MATCHFINDER_HASH_ORDER 15,
  * BUCKET_SIZE 2, MIN_MATCH_LEN 4, REQUIRED_NBYTES 5); every position is inserted (searched ones by
@@ -1068,39 +829,4 @@ size_t oracle_deflate_ex(const uint8_t *in, size_t dict_len, size_t n, int level
 size_t oracle_deflate(const uint8_t *in, size_t n, int level, uint8_t *out, size_t out_cap)
 {
     return oracle_deflate_ex(in, 0, n, level, 0, out, out_cap, NULL);
-}
-
-/* oracle_deflate_ex through the chunk-speculative parser (levels 2-9); stats (may be NULL): epochs, positions
- * speculated, chunks skipped, positions re-parsed by the stitch, min_len changes, DEFLATE blocks, searches, chain hops. */
-size_t oracle_deflate_spec(const uint8_t *in, size_t dict_len, size_t n, int level, int flush, size_t chunk,
-                           uint8_t *out, size_t out_cap, uint64_t stats[8])
-{
-    bitw_t w = {out, out_cap, 0, 0, 0, 0};
-    comp_t c; memset(&c, 0, sizeof c);
-    uint64_t local[8] = {0};
-    if (!stats) stats = local;
-    init_tabs();
-    c.level = level;
-    int final_block = (flush == 0);
-    if (level < 2 || level > 9 || chunk < 16) return 0;
-    if (level_params(level, &c.max_depth, &c.nice, &c.mode) != 0) return 0;
-    size_t passthrough = (size_t)(55 - level * 4);
-    if (n <= passthrough && !(flush == 1 && n == 0)) {
-        compress_none(in + dict_len, n, &w, final_block);
-    } else if (n > 0) {
-        size_t tot = dict_len + n;
-        c.head3 = malloc(32768 * sizeof(int32_t)); c.head4 = malloc(65536 * sizeof(int32_t));
-        c.next = malloc((tot + 1) * sizeof(int32_t)); c.tokens = malloc((tot + 1 + tot / 4) * sizeof(uint32_t));
-        init_static(&c);
-        compress_hc_spec(&c, in, dict_len, tot, &w, final_block, chunk, stats);
-        free(c.head3); free(c.head4); free(c.next); free(c.tokens);
-    }
-    if (flush == 1) {
-        bw_add(&w, 0, 3);
-        bw_align(&w);
-        bw_add(&w, 0, 16); bw_add(&w, 0xFFFF, 16);
-    }
-    bw_flush(&w);
-    if (w.overflow) return 0;
-    return w.pos;
 }

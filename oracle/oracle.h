@@ -38,8 +38,6 @@ int oracle_level_supported(int level);
 void oracle_thread_cleanup(void);
 size_t oracle_deflate(const uint8_t *in, size_t n, int level, uint8_t *out, size_t out_cap);
 void oracle_search_stats(uint64_t *searches, uint64_t *hops, int reset);
-size_t oracle_deflate_spec(const uint8_t *in, size_t dict_len, size_t n, int level, int flush, size_t chunk,
-                           uint8_t *out, size_t out_cap, uint64_t stats[8]);
 size_t oracle_deflate_ex(const uint8_t *in, size_t dict_len, size_t n, int level, int flush,
                          uint8_t *out, size_t out_cap, oracle_trace_t *trace);
 void oracle_make_huffman_code(unsigned num_syms, unsigned max_len, const uint32_t *freqs,

@@ -466,34 +466,6 @@ def test_emu_compress_file_and_zero_copy_reserve(emu_backend, tmp_path):
     assert bytes(chunks) == oracle.compress_stream(oracle.BGZF, 6, 65280, [TEXT])
 
 
-@pytest.fixture()
-def match_v2(monkeypatch):
-    """Select the match path v2 (k_group + k_match2: hash groups instead of linked chains) for contexts created in the test."""
-    monkeypatch.setenv("GZPB_MATCH_V2", "1")
-    yield
-
-
-@pytest.mark.parametrize("level", [1, 4, 6, 9])
-def test_emu_match_v2_bgzf_levels(match_v2, level):
-    ctx = emu.EmuContext(oracle.BGZF, level)
-    assert ctx.L.gzpb_ctx_variant(ctx.h) == b"split+group+match2"
-    ctx.close()
-    got = _run(oracle.BGZF, level, 0, TEXT[:140000])
-    assert gzip.decompress(got) == TEXT[:140000]
-
-
-def test_emu_match_v2_edges_long_units_and_dictionaries(match_v2):
-    rnd = random.Random(5)
-    cases = [b"", b"x", TEXT[:33], bytes(70000), bytes(rnd.getrandbits(8) for _ in range(30000)),
-             b"abcdefghij" * 6500, TEXT[:65280], synth.low_entropy(65280)]
-    for d in cases:
-        assert gzip.decompress(_run(oracle.BGZF, 6, 0, d)) == d
-    assert gzip.decompress(_run(oracle.MGZIP, 6, 131072, TEXT[:200000])) == TEXT[:200000]   # sub-units with a 32 KiB halo
-    d = synth.fastq(60000) + TEXT[:120000]
-    assert gzip.decompress(_run(oracle.GZIP, 8, 131072, d)) == d                            # dictionary carry, lazy2: depth/4 column
-    assert zlib.decompress(_run(oracle.ZLIB, 1, 40000, TEXT[:130000])) == TEXT[:130000]     # ht matchfinder
-
-
 def test_emu_writer_emits_the_gzi_index(emu_backend):
     """The Bgzf writer's own .gzi (collected as batches retire) equals the index scanned from the finished stream,
     including empty flush blocks and the EOF marker, which carry no entry."""
@@ -610,8 +582,7 @@ def test_emu_memcheck_under_address_sanitizer():
     if not asan or not os.path.isabs(asan) or not os.path.exists(asan):
         pytest.skip("no libasan on this machine")
     env = dict(os.environ, GZPB_EMU_ASAN="1", LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0:detect_stack_use_after_return=0")
-    env.pop("GZPB_MATCH_V2", None)
-    sel = "bgzf_edges or emu_snap or block_size_exceeded or sparse_chunk_sizes"
+    sel = "bgzf_edges or emu_snap or block_size_exceeded or encode_stream_multi"
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-k", sel, "-p", "no:cacheprovider"],
                        env=env, capture_output=True, text=True, timeout=1500, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert "AddressSanitizer" not in r.stdout + r.stderr, (r.stdout + r.stderr)[-4000:]
@@ -635,162 +606,11 @@ def test_emu_results_do_not_depend_on_the_fiber_schedule(sched):
     assert " passed" in r.stdout
 
 
-def _sparse_stats(ctx):
-    import ctypes as C
-    u, m = C.c_uint64(0), C.c_uint64(0)
-    ctx.L.gzpb_debug_sparse_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_int]
-    ctx.L.gzpb_debug_sparse_stats(ctx.h, C.byref(u), C.byref(m), 1)
-    return u.value, m.value
-
-
-def _run_sparse(fmt, level, bs, data):
-    ctx = emu.EmuContext(fmt, level, max_block_bytes=bs)
-    try:
-        assert ctx.L.gzpb_ctx_variant(ctx.h) in (b"split+link+smatch", b"split+link+smatch+replay", b"split+link+match+tparse")
-        _sparse_stats(ctx)                                        # device-wide counters: start from zero
-        got = ctx.encode_stream(data, bs)
-        units, missed = _sparse_stats(ctx)
-    finally:
-        ctx.close()
-    assert got == oracle.compress_stream(fmt, level, bs or oracle.DEFAULT_BUFSIZE[fmt], [data]), (fmt, level, len(data))
-    return units, missed
-
-
-@pytest.mark.parametrize("level", [2, 4, 6, 7])
-def test_emu_sparse_match_table_levels(monkeypatch, level):
-    """GZPB_SPARSE=1 (k_smatch: speculative chunk parses fill the match table only where the parser looks): bit-exact,
-    and plain text never needs the fallback pass."""
-    monkeypatch.setenv("GZPB_SPARSE", "1")
-    units, missed = _run_sparse(oracle.BGZF, level, 0, TEXT[:140000])
-    assert units == 3 and missed == 0
-
-
-def test_emu_sparse_match_table_edges_and_fallback(monkeypatch):
-    monkeypatch.setenv("GZPB_SPARSE", "1")
-    rnd = random.Random(77)
-    rand = bytes(rnd.getrandbits(8) for _ in range(30000))
-    few = bytes(rnd.choice(b"ACGT") for _ in range(40000))
-    clean = [b"", b"x", TEXT[:33], TEXT[:700], bytes(70000), rand, b"abcdefghij" * 6000, TEXT[:65280], synth.low_entropy(65280)]
-    for d in clean:
-        units, missed = _run_sparse(oracle.BGZF, 6, 0, d)
-        assert missed == 0, len(d)
-    # symbol statistics that change inside the unit change min_len: the parse misses entries, the unit is flagged and
-    # redone from the full table by the filtered second pass — still the oracle's bytes
-    for d in ((few + TEXT[:60000])[:65280], (TEXT[:20000] + rand[:20000] + few)[:65280]):
-        units, missed = _run_sparse(oracle.BGZF, 6, 0, d)
-        assert (units, missed) == (1, 1)
-    # a stream mixing both kinds of unit
-    units, missed = _run_sparse(oracle.BGZF, 5, 0, TEXT[:65280] + (few + TEXT[:60000])[:65280] + TEXT[:30000])
-    assert units == 3 and missed == 1
-    # dictionary formats whose unit (32 KiB dictionary + block) still fits one sub-unit take the sparse path too
-    units, missed = _run_sparse(oracle.GZIP, 6, 32768, TEXT[:150000])
-    assert units >= 4 and missed == 0
-    units, missed = _run_sparse(oracle.ZLIB, 4, 32768, TEXT[:100000])
-    assert missed == 0
-    # long units (sub-units with a halo), lazy2 levels and level 1 keep the full table
-    for fmt, level, bs in ((oracle.MGZIP, 6, 131072), (oracle.BGZF, 9, 0), (oracle.BGZF, 1, 0)):
-        units, missed = _run_sparse(fmt, level, bs, TEXT[:140000])
-        assert units == 0
-
-
-@pytest.mark.parametrize("chunk", ["256", "1000"])
-def test_emu_sparse_chunk_sizes(monkeypatch, chunk):
-    monkeypatch.setenv("GZPB_SPARSE", "1")
-    monkeypatch.setenv("GZPB_SPARSE_CHUNK", chunk)
-    units, missed = _run_sparse(oracle.BGZF, 6, 0, TEXT[:100000] + bytes(30000))
-    assert units == 2 and missed == 0
-
-
-@pytest.mark.parametrize("sparse", ["2", "3"])
-@pytest.mark.parametrize("level", [2, 5, 6, 7, 9])
-def test_emu_sparse_tokens_and_replay_levels(monkeypatch, level, sparse):
-    """GZPB_SPARSE=2: k_smatch also hands over the stitched, compacted tokens of the true parse and k_emit<2> only
-    replays the parser's events over them (min_len re-calculation, block-split checks, sequence-store limit).
-    GZPB_SPARSE=3: the same chunked parse fed from k_match's full table (k_smatch<true>) — no searches of its own."""
-    monkeypatch.setenv("GZPB_SPARSE", sparse)
-    units, missed = _run_sparse(oracle.BGZF, level, 0, TEXT[:140000])
-    assert units == 3 and missed == 0
-
-
-@pytest.mark.parametrize("sparse", ["2", "3"])
-def test_emu_sparse_tokens_and_replay_edges_and_fallback(monkeypatch, sparse):
-    monkeypatch.setenv("GZPB_SPARSE", sparse)
-    rnd = random.Random(77)
-    rand = bytes(rnd.getrandbits(8) for _ in range(30000))
-    few = bytes(rnd.choice(b"ACGT") for _ in range(40000))
-    clean = [b"", b"x", TEXT[:33], TEXT[:700], bytes(70000), rand, b"abcdefghij" * 6000, TEXT[:65280],
-             synth.low_entropy(65280), (b"\x00" * 300 + b"\xff" * 5 + TEXT[:50]) * 150]
-    for d in clean:
-        units, missed = _run_sparse(oracle.BGZF, 6, 0, d)
-        assert missed == 0, len(d)
-    # symbol statistics that change inside the unit change min_len: k_smatch's event scan ends the epoch there and
-    # speculates the rest again with the new value — no fallback in this form
-    for d in ((few + TEXT[:60000])[:65280], (TEXT[:20000] + rand[:20000] + few)[:65280]):
-        for level in (6, 9):
-            units, missed = _run_sparse(oracle.BGZF, level, 0, d)
-            assert (units, missed) == (1, 0)
-    units, missed = _run_sparse(oracle.BGZF, 4, 0, TEXT[:65280] + (few + TEXT[:60000])[:65280] + TEXT[:30000])
-    assert units == 3 and missed == 0
-    units, missed = _run_sparse(oracle.MGZIP, 6, 131072, (few + TEXT[:60000] + rand + few + TEXT[:90000]))   # epochs inside sub-units of a long unit
-    assert missed == 0
-    units, missed = _run_sparse(oracle.GZIP, 6, 32768, TEXT[:150000])               # dictionary in front of the unit
-    assert units >= 4 and missed == 0
-    monkeypatch.setenv("GZPB_SPARSE_CHUNK", "512")
-    units, missed = _run_sparse(oracle.BGZF, 6, 0, TEXT[:100000] + bytes(30000))
-    assert units == 2 and missed == 0
-
-
-def test_emu_sparse_fuzz(monkeypatch):
-    """Random formats / levels / block sizes / chunk sizes / data kinds through the tokens + replay path (and its fallbacks)."""
-    monkeypatch.setenv("GZPB_SPARSE", "2")
-    rnd = random.Random(2025)
-
-    def gen(n):
-        k = rnd.randrange(5)
-        if k == 0:
-            return bytes(rnd.randrange(255) for _ in range(n))
-        if k == 1:
-            o = rnd.randrange(0, len(TEXT) - min(n, len(TEXT) - 1))
-            return (TEXT[o:] + TEXT)[:n]
-        if k == 2:
-            return ((bytes([rnd.randrange(256)]) * rnd.randrange(1, 700) + bytes(rnd.randrange(4) for _ in range(rnd.randrange(1, 50)))) * (n // 20 + 1))[:n]
-        if k == 3:
-            return synth.low_entropy(n, seed=rnd.randrange(1 << 30))
-        out = bytearray()
-        while len(out) < n:
-            out += gen(rnd.randrange(1, 4000))
-        return bytes(out[:n])
-
-    for _ in range(8):
-        fmt = rnd.choice([oracle.BGZF, oracle.BGZF, oracle.GZIP, oracle.ZLIB, oracle.RAWDEFLATE])
-        level = rnd.choice([2, 4, 5, 6, 7])
-        bs = rnd.randrange(32768, 65280) if fmt == oracle.BGZF else rnd.randrange(32768, 80000)
-        d = gen(rnd.randrange(0, 150000))
-        monkeypatch.setenv("GZPB_SPARSE_CHUNK", str(rnd.choice([128, 200, 256, 512])))
-        ctx = emu.EmuContext(fmt, level, max_block_bytes=bs, max_blocks_in_flight=rnd.choice([1, 2, 5]))
-        try:
-            got = ctx.encode_stream(d, bs)
-        finally:
-            ctx.close()
-        assert got == oracle.compress_stream(fmt, level, bs, [d]), (fmt, level, bs, len(d))
-
-
 def test_emu_units_longer_than_512k_checksum():
     """Regression: k_check's x^(8*512*j) table spans 512 KiB; longer units (up to 4 MiB) need the second table —
     the Mgzip / Gzip CRC-32 of a 590 000-byte block was wrong before."""
     big = (TEXT * 3)[:600000]
     assert gzip.decompress(_run(oracle.MGZIP, 2, 590000, big)) == big
-
-
-def test_emu_sparse_tokens_long_units(monkeypatch):
-    """GZPB_SPARSE=2 on long units: k_smatch walks the unit sub-unit by sub-unit and carries the parse across; the
-    replay also ends a DEFLATE block at SOFT_MAX_BLOCK_LENGTH (units above 300 000 bytes)."""
-    monkeypatch.setenv("GZPB_SPARSE", "2")
-    for fmt, level, bs, d in ((oracle.MGZIP, 6, 131072, TEXT[:200000]), (oracle.MGZIP, 2, 131072, bytes(200000)),
-                              (oracle.MGZIP, 4, 310000, (TEXT * 2)[:330000]),                            # DEFLATE blocks end at SOFT_MAX_BLOCK_LENGTH
-                              (oracle.GZIP, 9, 262144, synth.fastq(60000) + TEXT[:230000])):             # BASELINE configs[4] shape: lazy2 on long units
-        units, missed = _run_sparse(fmt, level, bs, d)
-        assert units >= 2 and missed == 0, (fmt, level, bs)
 
 
 def test_emu_encode_stream_multi_devices(monkeypatch):
