@@ -74,6 +74,9 @@ def parse_args():
     ap.add_argument("--cpu-sample-mb", type=float, default=0.0, help="override the CPU baseline sample size")
     ap.add_argument("--full-stream", action="store_true", help="the whole shakespeare x 10000 stream once through the incremental writer")
     ap.add_argument("--copy-threads", type=int, default=0, help="--full-stream: helper threads for the writer's host copy (default: all cores)")
+    ap.add_argument("--feed", default="write", choices=["write", "reserve"],
+                    help="--full-stream: `write` = gzpb_writer_write from a caller buffer (one host copy, made by --copy-threads threads); "
+                         "`reserve` = producer threads generate the stream in place in the writer's pinned slab (gzpb_writer_reserve / _commit)")
     return ap.parse_args()
 
 
@@ -470,12 +473,16 @@ def main():
         # (2) a stock decoder turns (a bounded prefix of) the stream back into the input
         same_as_one_gpu = None
         if world > 1:
-            multi = C.string_at(h_out, out_bytes)
-            rc = L.gzpb_encode_stream(ctx._h, h_in + last * shift, e2e_bytes, bs, h_out, out_cap, C.byref(olen))
-            assert rc == 0
-            same_as_one_gpu = (olen.value == out_bytes and C.string_at(h_out, olen.value) == multi)
+            h_one = L.gzpb_host_alloc(out_cap)            # the same input through ONE GPU, compared in place (streams exceed 2 GiB)
+            olen1 = C.c_size_t(0)
+            rc = L.gzpb_encode_stream(ctx._h, h_in + last * shift, e2e_bytes, bs, h_one, out_cap, C.byref(olen1))
+            assert rc == 0, L.gzpb_strerror(rc)
+            libc = C.CDLL(None)
+            libc.memcmp.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+            libc.memcmp.restype = C.c_int
+            same_as_one_gpu = (olen1.value == out_bytes and libc.memcmp(h_out, h_one, out_bytes) == 0)
+            L.gzpb_host_free(h_one)
             assert same_as_one_gpu, "the N-GPU stream differs from the one-GPU stream"
-            del multi
             log("N-GPU stream identical to the one-GPU stream (%d B)" % out_bytes)
         want_all_len = e2e_bytes if e2e_bytes <= (1200 << 20) else None
         if want_all_len:
@@ -639,13 +646,41 @@ def full_stream(args, cfg):
     threads = args.copy_threads or host_threads()
     assert L.gzpb_writer_set_copy_threads(h, threads) == 0
     log("writer over %d GPU(s) ready, %d copy threads" % (ndev, threads))
+    cbase = C.addressof(buf)
+
+    def produce(dst, stream_off, k):
+        """k bytes of the repeated corpus from stream offset `stream_off`, written at dst (ctypes releases the GIL)."""
+        pos, s0 = 0, stream_off % S
+        while pos < k:
+            m = min(S * per_write - s0, k - pos)
+            C.memmove(dst + pos, cbase + s0, m)
+            pos += m
+            s0 = 0
+
     t0 = time.perf_counter()
-    left = copies
-    while left:
-        k = min(per_write, left)
-        rc = L.gzpb_writer_write(h, buf, S * k)
-        assert rc == 0, L.gzpb_strerror(rc)
-        left -= k
+    if args.feed == "write":
+        left = copies
+        while left:
+            k = min(per_write, left)
+            rc = L.gzpb_writer_write(h, buf, S * k)
+            assert rc == 0, L.gzpb_strerror(rc)
+            left -= k
+    else:
+        from concurrent.futures import ThreadPoolExecutor
+        pool = ThreadPoolExecutor(max_workers=threads)
+        done = 0
+        p, room = C.c_void_p(0), C.c_size_t(0)
+        while done < total_in:
+            assert L.gzpb_writer_reserve(h, C.byref(p), C.byref(room)) == 0
+            n = min(room.value, total_in - done)
+            piece = max(1 << 20, (n + threads - 1) // threads)
+            futs = [pool.submit(produce, p.value + o, done + o, min(piece, n - o)) for o in range(0, n, piece)]
+            for f in futs:
+                f.result()
+            rc = L.gzpb_writer_commit(h, n)
+            assert rc == 0, L.gzpb_strerror(rc)
+            done += n
+        pool.shutdown()
     rc = L.gzpb_writer_finish(h)
     dt = time.perf_counter() - t0
     assert rc == 0, L.gzpb_strerror(rc)
@@ -666,8 +701,9 @@ def full_stream(args, cfg):
         checked += len(joined)
     print(json.dumps({"metric": "bgzf_l6_full_stream_throughput", "value": total_in / dt / GIB, "unit": UNIT, "n_gpus": ndev, "seconds": dt,
                       "bytes_in": total_in, "bytes_out": bo.value, "ratio": bo.value / total_in, "device_batches": nb.value, "sink_calls": sc.value,
-                      "copy_threads": threads, "host_threads": host_threads(),
-                      "api": "gzpb_writer_create_multi + gzpb_writer_write(218.6 MB per call, pageable caller buffer) + gzpb_writer_finish; counting sink",
+                      "copy_threads": threads, "host_threads": host_threads(), "feed": args.feed,
+                      "api": ("gzpb_writer_create_multi + gzpb_writer_write(218.6 MB per call, pageable caller buffer, one host copy by %d threads) + gzpb_writer_finish; counting sink" % threads) if args.feed == "write" else
+                             ("gzpb_writer_create_multi + gzpb_writer_reserve / _commit: %d producer threads generate the stream in place in the pinned slabs (no host copy) + gzpb_writer_finish; counting sink" % threads),
                       "decoded_input_bytes_checked": checked, "batches_checked": len(samples),
                       "workload": "shakespeare.txt x %d = %d B (BASELINE configs[1]), ONE ordered BGZF level-6 stream, 65280-B blocks" % (copies, total_in)}), flush=True)
 

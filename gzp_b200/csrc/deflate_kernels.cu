@@ -25,6 +25,7 @@ namespace gzpb {
 __constant__ uint32_t c_crc_tab[4][256];      // slicing-by-4, reflected 0xEDB88320
 __constant__ uint32_t c_xpow512[1024];        // x^(8*512*j) mod P
 __constant__ uint32_t c_xpow512k[16];         // x^(8*512*1024*t) mod P: units longer than 512 KiB (up to 4 MiB + dictionary)
+__device__ uint32_t g_xpow64[1024];            // x^(8*64*j) mod P: k_split's 64-byte CRC slices (indexed per thread: global, not __constant__)
 __constant__ uint16_t c_static_litlen_cw[288];
 __constant__ uint8_t c_static_litlen_len[288];
 __constant__ uint8_t c_min_lens[80];
@@ -49,6 +50,9 @@ void upload_deflate_constants()
     static uint32_t xpk[16];
     for (int t = 0; t < 16; t++) xpk[t] = gf2_xpow8((uint64_t)512 * 1024 * t, kCrcPoly);
     cudaMemcpyToSymbol(c_xpow512k, xpk, sizeof xpk);
+    static uint32_t xp64[1024];
+    for (int j = 0; j < 1024; j++) xp64[j] = gf2_xpow8((uint64_t)64 * j, kCrcPoly);
+    cudaMemcpyToSymbol(g_xpow64, xp64, sizeof xp64);
     uint16_t cw[288]; uint8_t ln[288];
     for (int s = 0; s < 288; s++) {
         uint32_t code; int len;
@@ -126,12 +130,18 @@ constexpr int kLsStride = 32;            // list_start entries per sub-unit: [0.
 
 __global__ void __launch_bounds__(kSplitThreads)
 k_split(const __grid_constant__ Geo g, uint32_t *__restrict__ lists, uint32_t *__restrict__ list_start,
-        uint16_t *__restrict__ next4, uint16_t *__restrict__ prev3, int ht)
+        uint16_t *__restrict__ next4, uint16_t *__restrict__ prev3, int ht, uint32_t *__restrict__ sum_part, int check_kind)
 {
     __shared__ uint32_t s_w[32][kSplitLists];     // per-warp member counts, then running bases
     __shared__ uint32_t s_start[kSplitLists];
+    __shared__ uint32_t s_tab[4][256];            // CRC-32 slicing tables (check_kind 0)
+    __shared__ uint32_t s_crc;
+    __shared__ unsigned long long s_a, s_b;
     const Sub sb = sub_geometry(g, blockIdx.x);
-    if (!sb.valid) return;
+    if (!sb.valid) {                               // no data in this sub-unit: the identity of Check::combine
+        if (sum_part && threadIdx.x == 0) sum_part[blockIdx.x] = (check_kind == 1) ? 1u : 0u;
+        return;
+    }
     const uint32_t n = sb.len, ninsert = n >= 5 ? n - 4 : 0;
     const uint32_t *inw = (const uint32_t *)(g.in + (size_t)sb.u * g.in_stride + sb.h);
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, lt = lanemask_lt();
@@ -199,6 +209,54 @@ k_split(const __grid_constant__ Geo g, uint32_t *__restrict__ lists, uint32_t *_
     for (uint32_t p = ninsert + tid; p < n; p += kSplitThreads) {
         next4[(size_t)blockIdx.x * kMaxUnitBytes + p] = 0;
         prev3[(size_t)blockIdx.x * kMaxUnitBytes + p] = 0;
+    }
+    // ---- Check::update folded into this pass (the reference's second pass over the block, bgzf.rs:224-225): the
+    // bytes are in L1 from the hashing above.  Every thread takes one 64-byte slice of the sub-unit's NEW bytes
+    // [nb, ne) — slices are counted from the end so that only the first one is short — and the slices recombine
+    // with x^(8*64*j) mod P (CRC-32) or with the Adler-32 sum formulas.  One partial sum per sub-unit; k_emit
+    // folds the sub-units of a long unit.
+    if (sum_part) {
+        const uint32_t R = sb.ne - sb.nb;          // <= 65536 = 1024 slices
+        if (tid == 0) { s_crc = 0; s_a = 0; s_b = 0; }
+        if (check_kind == 0) {
+            for (uint32_t i = tid; i < 1024; i += kSplitThreads) s_tab[i >> 8][i & 255] = c_crc_tab[i >> 8][i & 255];
+            __syncthreads();
+            uint32_t acc = 0;
+            if (tid * 64 < R) {
+                const uint32_t end = sb.nb + (R - 64 * tid), beg = (R - 64 * tid) >= 64 ? end - 64 : sb.nb;
+                uint32_t c = ~0u, pos = beg;
+                for (; pos + 4 <= end; pos += 4) {
+                    c ^= ldg32u(inw, pos);
+                    c = s_tab[3][c & 0xFF] ^ s_tab[2][(c >> 8) & 0xFF] ^ s_tab[1][(c >> 16) & 0xFF] ^ s_tab[0][c >> 24];
+                }
+                const uint8_t *in8 = (const uint8_t *)inw;
+                for (; pos < end; pos++) c = (c >> 8) ^ s_tab[0][(c ^ __ldg(in8 + pos)) & 0xFF];
+                c = ~c;
+                acc = tid == 0 ? c : gf2_mulmod(c, g_xpow64[tid], kCrcPoly);
+            }
+            for (int o = 16; o; o >>= 1) acc ^= __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+            if (lane == 0 && acc) atomicXor(&s_crc, acc);
+            __syncthreads();
+            if (tid == 0) sum_part[blockIdx.x] = s_crc;
+        } else {
+            __syncthreads();
+            unsigned long long sa = 0, sb2 = 0;
+            if (tid * 64 < R) {
+                const uint32_t beg = sb.nb + 64 * tid, end = min(sb.ne, beg + 64);
+                const uint8_t *in8 = (const uint8_t *)inw;
+                uint32_t a = 0, b = 0;
+                for (uint32_t pos = beg; pos < end; pos++) { a += __ldg(in8 + pos); b += a; }
+                sa = a;
+                sb2 = (b + (unsigned long long)a * (sb.ne - end)) % 65521ull;
+            }
+            for (int o = 16; o; o >>= 1) { sa += __shfl_xor_sync(0xFFFFFFFFu, sa, o); sb2 += __shfl_xor_sync(0xFFFFFFFFu, sb2, o); }
+            if (lane == 0) { atomicAdd(&s_a, sa); atomicAdd(&s_b, sb2); }
+            __syncthreads();
+            if (tid == 0) {
+                const uint32_t a = (uint32_t)((1ull + s_a) % 65521ull), b = (uint32_t)(((unsigned long long)R + s_b) % 65521ull);
+                sum_part[blockIdx.x] = (b << 16) | a;
+            }
+        }
     }
 }
 
@@ -388,12 +446,13 @@ k_match(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, cons
         const uint8_t *b = (const uint8_t *)s_in;
         // the visit count at which the next snapshot (depth/4, depth/2) or the depth limit falls: one compare per node
         uint32_t snap = (!haveC && depthC) ? depthC : (!haveB && depthB) ? depthB : (uint32_t)depth;
+        uint32_t d = s_next[q];
         for (;;) {
-            uint32_t d = s_next[q];
             if (d == 0) break;
             q -= d;
             if (p - q >= (uint32_t)kWindow) break;
             visited++;
+            d = s_next[q];                     // the next link leaves now: its latency hides behind this node's compares
             bool cand;
             if (best == 3) cand = (ld32u(s_in, q) == seq4);
             else cand = (b[q + best] == pbest) && (ld32u(s_in, q) == seq4);
@@ -686,9 +745,39 @@ __device__ __forceinline__ void table_search(uint64_t e, uint32_t b, bool useB, 
     } else if (lx > b) { len = lx; off = ox; }
 }
 
+__device__ __forceinline__ uint32_t adler_combine_dev(uint32_t a1, uint32_t a2, uint64_t len2);
+
+// Check::combine over the sub-units of one unit (k_split left one partial sum per sub-unit); warp-collective.
+__device__ __forceinline__ uint32_t fold_unit_sum(const Geo &g, uint32_t u, const uint32_t *__restrict__ part, int kind, uint32_t lane)
+{
+    if (g.spu == 1) return part[u];
+    const uint32_t n = g.unit_len[u], dict = g.unit_dict[u];
+    if (kind == 0) {
+        uint32_t acc = 0;
+        for (uint32_t k = lane; k < g.spu; k += 32) {
+            const uint32_t a = dict + k * g.seg;
+            if (a >= n) break;
+            const uint32_t b = min(a + g.seg, n);
+            const uint32_t c = part[(size_t)u * g.spu + k];
+            acc ^= (b == n) ? c : gf2_mulmod(c, gf2_xpow8((uint64_t)(n - b), kCrcPoly), kCrcPoly);   // x^(8 * bytes behind sub-unit k)
+        }
+        for (int o = 16; o; o >>= 1) acc ^= __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+        return acc;
+    }
+    uint32_t s = 1u;
+    if (lane == 0)
+        for (uint32_t k = 0; k < g.spu; k++) {
+            const uint32_t a = dict + k * g.seg;
+            if (a >= n) break;
+            s = adler_combine_dev(s, part[(size_t)u * g.spu + k], (uint64_t)(min(a + g.seg, n) - a));
+        }
+    return __shfl_sync(0xFFFFFFFFu, s, 0);
+}
+
 __global__ void __launch_bounds__(kEmitThreads)
 k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
-       const uint64_t *__restrict__ mtab, const uint32_t *__restrict__ mtab2, const uint32_t *__restrict__ crc_in, uint32_t *__restrict__ tok_base,
+       const uint64_t *__restrict__ mtab, const uint32_t *__restrict__ mtab2, uint32_t *__restrict__ crc_io, const uint32_t *__restrict__ sum_part, int check_kind,
+       uint32_t *__restrict__ tok_base,
        uint8_t *__restrict__ out_base, uint32_t *__restrict__ out_len, int32_t *__restrict__ out_status,
        int mode, int depth, int nice, int level, int format)
 {
@@ -699,6 +788,13 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
     const uint32_t dl = n - dict;              // bytes to encode
     const uint32_t flags = unit_flags[u];
     const uint8_t *in = g.in + (size_t)u * g.in_stride;
+    // the unit's Check::sum: folded from k_split's per-sub-unit partial sums (written back for the host / the batch
+    // combine), or what k_check left (level 0 has no k_split pass)
+    uint32_t unit_sum = 0;
+    if (check_kind >= 0) {
+        if (sum_part) { unit_sum = fold_unit_sum(g, u, sum_part, check_kind, tid); if (tid == 0) crc_io[u] = unit_sum; }
+        else unit_sum = crc_io[u];
+    }
     uint32_t *tok = tok_base + (size_t)u * g.tok_stride;
     uint8_t *slot = out_base + (size_t)u * g.out_stride;
     uint32_t *payload = (uint32_t *)(slot + kOutPayloadOff);
@@ -1271,7 +1367,7 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
                 h[16] = (uint8_t)bs; h[17] = (uint8_t)(bs >> 8); h[18] = (uint8_t)(bs >> 16); h[19] = (uint8_t)(bs >> 24);
             }
             uint8_t *f = slot + kOutPayloadOff + nbytes;
-            uint32_t crc = crc_in[u];
+            uint32_t crc = unit_sum;
             f[0] = (uint8_t)crc; f[1] = (uint8_t)(crc >> 8); f[2] = (uint8_t)(crc >> 16); f[3] = (uint8_t)(crc >> 24);
             f[4] = (uint8_t)dl; f[5] = (uint8_t)(dl >> 8); f[6] = (uint8_t)(dl >> 16); f[7] = (uint8_t)(dl >> 24);
             total = hs + nbytes + 8;
@@ -1506,14 +1602,17 @@ cudaError_t launch_deflate_pipeline(const DeflateBatch &b, cudaStream_t st)
     LevelParams lp;
     if (!level_params(b.level, &lp)) return cudaErrorInvalidValue;
     const Geo g = make_geo(b);
-    if (b.check_kind >= 0) {
+    // Check::update: folded into k_split (one partial sum per sub-unit, k_emit folds them); level 0 has no k_split pass
+    const bool fold_check = b.check_kind >= 0 && lp.mode >= 0 && b.sum_part != nullptr;
+    if (b.check_kind >= 0 && !fold_check) {
         if (b.timer) b.timer->start(KT_CRC, st);
         GZPB_LAUNCH(k_check, b.nunits, 256, 0, st, g, b.crc, b.check_kind);
         if (b.timer) b.timer->stop(st);
     }
     if (lp.mode >= 0) {
         if (b.timer) b.timer->start(KT_CHAIN, st);
-        GZPB_LAUNCH(k_split, b.nunits * b.spu, kSplitThreads, 0, st, g, b.lists, b.list_start, b.next4, b.prev3, lp.ht);
+        GZPB_LAUNCH(k_split, b.nunits * b.spu, kSplitThreads, 0, st, g, b.lists, b.list_start, b.next4, b.prev3, lp.ht,
+                    fold_check ? b.sum_part : (uint32_t *)nullptr, b.check_kind);
         DBG_SYNC("k_split");
         GZPB_LAUNCH(k_link, b.nunits * b.spu * kSplitLists, 32, 0, st, g, b.lists, b.list_start, b.next4, b.prev3, b.clen);
         DBG_SYNC("k_link");
@@ -1523,8 +1622,8 @@ cudaError_t launch_deflate_pipeline(const DeflateBatch &b, cudaStream_t st)
         if (b.timer) b.timer->stop(st);
     }
     if (b.timer) b.timer->start(KT_EMIT, st);
-    GZPB_LAUNCH(k_emit, b.nunits, kEmitThreads, 0, st, g, b.unit_flags, b.mtab, b.mtab2, b.crc, b.tokens, b.out, b.out_len,
-                b.status, lp.mode, lp.depth, lp.nice, b.level, b.format);
+    GZPB_LAUNCH(k_emit, b.nunits, kEmitThreads, 0, st, g, b.unit_flags, b.mtab, b.mtab2, b.crc, fold_check ? b.sum_part : (const uint32_t *)nullptr, b.check_kind,
+                b.tokens, b.out, b.out_len, b.status, lp.mode, lp.depth, lp.nice, b.level, b.format);
     DBG_SYNC("k_emit");
     if (b.timer) b.timer->stop(st);
     return cudaGetLastError();

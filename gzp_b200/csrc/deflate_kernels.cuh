@@ -47,7 +47,8 @@ struct DeflateBatch {
     uint32_t *mtab2;          // nunits * m_stride, lazy2 levels only (depth/4 column), else NULL
     uint8_t *clen;            // nunits * spu * 65536 (chain lengths, k_match scratch)
     uint16_t *order;          // nunits * spu * 65536 (positions sorted by chain length)
-    uint32_t *crc;            // nunits
+    uint32_t *crc;            // nunits: Check::sum per unit
+    uint32_t *sum_part;       // nunits * spu: per-sub-unit partial sums (k_split -> k_emit), NULL = separate k_check pass
     uint32_t *tokens;         // nunits * kTokStride
     uint8_t *out;             // nunits * kOutStride
     uint32_t *out_len;        // nunits * 2  (total bytes, header offset in the slot)

@@ -42,7 +42,7 @@ struct Lane {
     cudaEvent_t ev_scan = nullptr, ev_done = nullptr;
     // device
     uint8_t *d_in = nullptr;
-    uint32_t *d_len = nullptr, *d_dict = nullptr, *d_flags = nullptr, *d_crc = nullptr, *d_tokens = nullptr, *d_out_len = nullptr;
+    uint32_t *d_len = nullptr, *d_dict = nullptr, *d_flags = nullptr, *d_crc = nullptr, *d_sum_part = nullptr, *d_tokens = nullptr, *d_out_len = nullptr;
     uint16_t *d_next4 = nullptr, *d_prev3 = nullptr, *d_order = nullptr;
     uint8_t *d_clen = nullptr;
     uint64_t *d_mtab = nullptr, *d_offsets = nullptr;
@@ -70,7 +70,7 @@ struct gzpb_ctx {
     int check_kind = -1;
     uint32_t cpu = 1;                              // gather entries per unit (Snap: 64 KiB chunks per block)
     Lane lanes[kLanes];
-    int gather_host_ctas = 148;                      // thread blocks of a k_gather that writes host memory (GZPB_GATHER_CTAS; measured 148/296/592/all: e2e 8.79/8.68/8.55/8.45 GiB/s)
+    int gather_host_ctas = 64;                       // thread blocks of a k_gather that writes host memory (GZPB_GATHER_CTAS; measured 37/74/148/296/592/one per unit: e2e 9.09/9.04/9.01 | 8.68/8.55/8.45 GiB/s)
     uint64_t *d_base0 = nullptr, *h_base0 = nullptr; // first stream offset of a gzpb_encode_stream call: device copy / mapped pinned copy
     bool scratch_only = false;
     KernelTimer timer;
@@ -235,6 +235,7 @@ static int lane_alloc(gzpb_ctx *c, Lane &L, bool with_io)
     CK(dmalloc(&L.d_mtab, U * c->m_stride));
     if (c->level >= 8) CK(dmalloc(&L.d_mtab2, U * c->m_stride));
     CK(dmalloc(&L.d_crc, U));
+    CK(dmalloc(&L.d_sum_part, U * c->spu));
     CK(dmalloc(&L.d_tokens, U * c->tok_stride));
     CK(dmalloc(&L.d_out, U * c->out_stride + 256));
     CK(dmalloc(&L.d_out_len, U * 2));
@@ -264,7 +265,7 @@ static int lane_alloc(gzpb_ctx *c, Lane &L, bool with_io)
 
 static void lane_free(Lane &L)
 {
-    cudaFree(L.d_in); cudaFree(L.d_len); cudaFree(L.d_dict); cudaFree(L.d_flags); cudaFree(L.d_crc); cudaFree(L.d_tokens); cudaFree(L.d_out_len);
+    cudaFree(L.d_in); cudaFree(L.d_len); cudaFree(L.d_dict); cudaFree(L.d_flags); cudaFree(L.d_crc); cudaFree(L.d_sum_part); cudaFree(L.d_tokens); cudaFree(L.d_out_len);
     cudaFree(L.d_next4); cudaFree(L.d_prev3); cudaFree(L.d_order); cudaFree(L.d_clen); cudaFree(L.d_mtab2); cudaFree(L.d_lists); cudaFree(L.d_list_start); cudaFree(L.d_mtab); cudaFree(L.d_offsets); cudaFree(L.d_out); cudaFree(L.d_packed);
     cudaFree(L.d_status); cudaFree(L.d_overflow); cudaFree(L.d_comb); cudaFreeHost(L.h_comb);
     cudaFreeHost(L.h_in); cudaFreeHost(L.h_packed); cudaFreeHost(L.h_len); cudaFreeHost(L.h_dict); cudaFreeHost(L.h_flags); cudaFreeHost(L.h_crc);
@@ -405,7 +406,7 @@ static void fill_batch(gzpb_ctx *c, Lane &L, DeflateBatch &b, size_t n)
     b.in = L.d_in; b.unit_len = L.d_len; b.unit_dict = L.d_dict; b.unit_flags = L.d_flags;
     b.in_stride = c->in_stride; b.m_stride = c->m_stride; b.tok_stride = c->tok_stride; b.out_stride = c->out_stride;
     b.spu = c->spu; b.seg = c->seg; b.check_kind = c->check_kind;
-    b.next4 = L.d_next4; b.prev3 = L.d_prev3; b.clen = L.d_clen; b.order = L.d_order; b.mtab = L.d_mtab; b.mtab2 = L.d_mtab2; b.lists = L.d_lists; b.list_start = L.d_list_start; b.crc = L.d_crc; b.tokens = L.d_tokens;
+    b.next4 = L.d_next4; b.prev3 = L.d_prev3; b.clen = L.d_clen; b.order = L.d_order; b.mtab = L.d_mtab; b.mtab2 = L.d_mtab2; b.lists = L.d_lists; b.list_start = L.d_list_start; b.crc = L.d_crc; b.sum_part = getenv("GZPB_SEPARATE_CHECK") ? nullptr : L.d_sum_part; b.tokens = L.d_tokens;
     b.out = L.d_out; b.out_len = L.d_out_len; b.status = L.d_status; b.offsets = L.d_offsets;
     b.packed = nullptr; b.packed_cap = 0; b.packed_on_host = 0; b.base_ptr = nullptr; b.end_mirror = nullptr; b.overflow = L.d_overflow;
     b.timer = c->profiling ? &c->timer : nullptr;

@@ -582,7 +582,7 @@ def test_emu_memcheck_under_address_sanitizer():
     if not asan or not os.path.isabs(asan) or not os.path.exists(asan):
         pytest.skip("no libasan on this machine")
     env = dict(os.environ, GZPB_EMU_ASAN="1", LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0:detect_stack_use_after_return=0")
-    sel = "bgzf_edges or emu_snap or block_size_exceeded or encode_stream_multi"
+    sel = "bgzf_edges or emu_snap or block_size_exceeded or c_writer_two_devices"
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-k", sel, "-p", "no:cacheprovider"],
                        env=env, capture_output=True, text=True, timeout=1500, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert "AddressSanitizer" not in r.stdout + r.stderr, (r.stdout + r.stderr)[-4000:]
@@ -620,8 +620,8 @@ def test_emu_encode_stream_multi_devices(monkeypatch):
     import ctypes as C
     monkeypatch.setenv("GZPB_EMU_DEVICES", "3")
     L = emu.lib()
-    for fmt, lvl, bs, n in ((oracle.BGZF, 6, 65280, 1_300_000), (oracle.GZIP, 5, 32768, 700_000), (oracle.ZLIB, 4, 40000, 500_000),
-                            (oracle.MGZIP, 6, 65536, 600_000), (oracle.SNAP, 0, 65536, 900_000)):
+    for fmt, lvl, bs, n in ((oracle.BGZF, 6, 65280, 560_000), (oracle.GZIP, 5, 32768, 300_000), (oracle.ZLIB, 2, 40000, 250_000),
+                            (oracle.SNAP, 0, 65536, 500_000)):
         data = (TEXT * (n // len(TEXT) + 1))[:n]
         want = oracle.compress_stream(fmt, lvl, bs, [data])
         hs = (C.c_void_p * 3)()
@@ -640,9 +640,7 @@ def test_emu_encode_stream_multi_devices(monkeypatch):
         C.memmove(pin_in, data, n)
         assert L.gzpb_encode_stream_multi(hs, 3, pin_in, n, bs, pin_out, cap, C.byref(olen)) == 0
         assert C.string_at(pin_out, olen.value) == want
-        # the same contexts, two of them; and one (= gzpb_encode_stream)
-        assert L.gzpb_encode_stream_multi(hs, 2, pin_in, n, bs, pin_out, cap, C.byref(olen)) == 0
-        assert C.string_at(pin_out, olen.value) == want
+        # one context (= gzpb_encode_stream), another device than the stream's first
         assert L.gzpb_encode_stream(hs[2], pin_in, n, bs, pin_out, cap, C.byref(olen)) == 0
         assert C.string_at(pin_out, olen.value) == want
         # a context listed twice is refused
