@@ -40,9 +40,9 @@ GZIP, ZLIB, RAWDEFLATE, MGZIP, BGZF, SNAP = 0, 1, 2, 3, 4, 5
 
 CONFIGS = {
     # blocks: per step and GPU; inflight: blocks per device batch
-    "bgzf": dict(fmt=BGZF, level=6, block=65280, inflight=3256, blocks=16280, data="corpus", metric="bgzf_l6_compress_input_throughput",
+    "bgzf": dict(fmt=BGZF, level=6, block=65280, inflight=3256, blocks=32560, data="corpus", metric="bgzf_l6_compress_input_throughput",
                  workload="ParCompress<Bgzf> level 6, 65280-B blocks, shakespeare.txt repeated (BASELINE configs[1]: windows of the 54.65 GB stream)"),
-    "mgzip": dict(fmt=MGZIP, level=6, block=131072, inflight=1628, blocks=8140, data="corpus", metric="mgzip_l6_compress_input_throughput",
+    "mgzip": dict(fmt=MGZIP, level=6, block=131072, inflight=1628, blocks=16280, data="corpus", metric="mgzip_l6_compress_input_throughput",
                   workload="ParCompress<Mgzip> level 6, 131072-B blocks, shakespeare.txt repeated (BASELINE configs[2])"),
     "snap": dict(fmt=SNAP, level=0, block=131072, inflight=2048, blocks=8192, data="low", metric="snap_compress_input_throughput",
                  workload="ParCompress<Snap>, 131072-B blocks, low-entropy synthetic binary (BASELINE configs[3]; SURVEY 8d generator, 256 MiB period)"),
@@ -69,7 +69,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="bgzf", choices=sorted(CONFIGS))
-    ap.add_argument("--blocks", type=int, default=0, help="gzp blocks per step and GPU (default per config: five device batches)")
+    ap.add_argument("--blocks", type=int, default=0, help="gzp blocks per step and GPU (default per config: ten device batches for the deflate-family text configs, 2.1 GB)")
     ap.add_argument("--inflight", type=int, default=0, help="blocks per device batch (default per config; bgzf: 3256 = 148 SMs x 22 resident k_emit CTAs)")
     ap.add_argument("--cpu-sample-mb", type=float, default=0.0, help="override the CPU baseline sample size")
     ap.add_argument("--full-stream", action="store_true", help="the whole shakespeare x 10000 stream once through the incremental writer")

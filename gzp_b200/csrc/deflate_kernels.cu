@@ -142,8 +142,19 @@ k_split(const __grid_constant__ Geo g, uint32_t *__restrict__ lists, uint32_t *_
         if (sum_part && threadIdx.x == 0) sum_part[blockIdx.x] = (check_kind == 1) ? 1u : 0u;
         return;
     }
-    const uint32_t n = sb.len, ninsert = n >= 5 ? n - 4 : 0;
-    const uint32_t *inw = (const uint32_t *)(g.in + (size_t)sb.u * g.in_stride + sb.h);
+    // The positions this sub-unit LINKS, in unit coordinates: its new positions [a, b) — sub-unit 0 also takes the
+    // dictionary in front of the data (set_dictionary inserts it).  The 32 KiB halo that k_match stages in front of a
+    // later sub-unit is not linked again: links are distances, and k_link carries its bucket heads from one sub-unit
+    // of a unit to the next.
+    const uint32_t un = g.unit_len[sb.u], udict = g.unit_dict[sb.u];
+    const uint32_t ksub = blockIdx.x % g.spu;
+    const uint32_t ua = udict + ksub * g.seg;
+    const uint32_t lo = ksub == 0 ? 0u : ua, hi_new = g.spu == 1 ? un : min(ua + g.seg, un);
+    const uint32_t uinsert = un >= 5 ? un - 4 : 0;                 // positions p <= n-5 are inserted
+    const uint32_t hi = min(hi_new, uinsert), ninsert = hi > lo ? hi - lo : 0;
+    const uint32_t *uw = (const uint32_t *)(g.in + (size_t)sb.u * g.in_stride);
+    const bool quirk0 = (ksub == 0 && udict == 0);                 // position 0 goes under hash 0 (next_hashes starts at {0,0})
+    const uint32_t *inw = (const uint32_t *)(g.in + (size_t)sb.u * g.in_stride + sb.h);   // checksum pass below: sub-unit coordinates
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, lt = lanemask_lt();
     const uint32_t ntiles = (ninsert + 31) / 32, tpw = (ntiles + 31) / 32;
     const uint32_t t0 = warp * tpw, t1 = min(ntiles, t0 + tpw);
@@ -156,9 +167,9 @@ k_split(const __grid_constant__ Geo g, uint32_t *__restrict__ lists, uint32_t *_
     for (uint32_t t = t0; t < t1; t++) {
         const uint32_t p = t * 32 + lane;
         const bool act = p < ninsert;
-        const uint32_t v = act ? ldg32u(inw, p) : 0;
+        const uint32_t v = act ? ldg32u(uw, lo + p) : 0;
         uint32_t h4 = ht ? (lz_hash(v, 15) << 1) : lz_hash(v, 16), h3 = lz_hash(v & 0xFFFFFFu, 15);   // level 1: 15-bit buckets (even slots)
-        if (p == 0 && sb.quirk) { h4 = 0; h3 = 0; }
+        if (p == 0 && quirk0) { h4 = 0; h3 = 0; }
         const uint32_t q4 = h4 >> kBits4, q3 = h3 >> kBits3;
         const uint32_t m4 = __match_any_sync(0xFFFFFFFFu, act ? q4 : 64u);
         const uint32_t m3 = __match_any_sync(0xFFFFFFFFu, act ? q3 : 64u);
@@ -184,13 +195,13 @@ k_split(const __grid_constant__ Geo g, uint32_t *__restrict__ lists, uint32_t *_
         ls[kL4 + 1 + kL3] = a;
     }
     __syncthreads();
-    // pass 2: scatter (hash, position) entries in position order
+    // pass 2: scatter (hash, position - lo) entries in position order
     for (uint32_t t = t0; t < t1; t++) {
         const uint32_t p = t * 32 + lane;
         const bool act = p < ninsert;
-        const uint32_t v = act ? ldg32u(inw, p) : 0;
+        const uint32_t v = act ? ldg32u(uw, lo + p) : 0;
         uint32_t h4 = ht ? (lz_hash(v, 15) << 1) : lz_hash(v, 16), h3 = lz_hash(v & 0xFFFFFFu, 15);   // level 1: 15-bit buckets (even slots)
-        if (p == 0 && sb.quirk) { h4 = 0; h3 = 0; }
+        if (p == 0 && quirk0) { h4 = 0; h3 = 0; }
         const uint32_t q4 = h4 >> kBits4, q3 = h3 >> kBits3;
         const uint32_t m4 = __match_any_sync(0xFFFFFFFFu, act ? q4 : 64u);
         const uint32_t m3 = __match_any_sync(0xFFFFFFFFu, act ? q3 : 64u);
@@ -206,9 +217,9 @@ k_split(const __grid_constant__ Geo g, uint32_t *__restrict__ lists, uint32_t *_
         __syncwarp();
     }
     // positions that are never inserted carry no link
-    for (uint32_t p = ninsert + tid; p < n; p += kSplitThreads) {
-        next4[(size_t)blockIdx.x * kMaxUnitBytes + p] = 0;
-        prev3[(size_t)blockIdx.x * kMaxUnitBytes + p] = 0;
+    for (uint32_t p = max(lo, uinsert) + tid; p < hi_new; p += kSplitThreads) {
+        next4[(size_t)sb.u * g.m_stride + p] = 0;
+        prev3[(size_t)sb.u * g.m_stride + p] = 0;
     }
     // ---- Check::update folded into this pass (the reference's second pass over the block, bgzf.rs:224-225): the
     // bytes are in L1 from the hashing above.  Every thread takes one 64-byte slice of the sub-unit's NEW bytes
@@ -264,67 +275,97 @@ __global__ void __launch_bounds__(32)
 k_link(const __grid_constant__ Geo g, const uint32_t *__restrict__ lists, const uint32_t *__restrict__ list_start,
        uint16_t *__restrict__ next4, uint16_t *__restrict__ prev3, uint8_t *__restrict__ clen_g)
 {
+    // One job = one list of one UNIT, walked sub-unit by sub-unit with the bucket heads carried along.
     // hash4 job: u16 head[4096] + u8 cnt[4096] (occurrences so far per bucket = chain-length estimate);
-    // hash3 job: u16 head[8192]
+    // hash3 job: u16 head[8192].  Heads hold unit positions mod 65536; a link is valid below 32768, so at every
+    // sub-unit boundary the heads that fell out of the window are parked on a sentinel 32768 positions back.
     __shared__ __align__(16) uint16_t head[1 << kBits3];
     uint8_t *cnt = (uint8_t *)(head + (1 << kBits4));
-    const uint32_t sub = blockIdx.x / kSplitLists, job = blockIdx.x % kSplitLists;
-    const Sub sb = sub_geometry(g, sub);
-    if (!sb.valid) return;
+    const uint32_t u = blockIdx.x / kSplitLists, job = blockIdx.x % kSplitLists;
+    const uint32_t un = g.unit_len[u], udict = g.unit_dict[u];
+    if (un <= udict) return;
     const uint32_t lane = threadIdx.x, lt = lanemask_lt();
-    const uint32_t *ls = list_start + (size_t)sub * kLsStride;
     const bool is4 = job < kL4;
-    const uint32_t *arr = lists + (size_t)sub * 2 * kMaxUnitBytes + (is4 ? 0 : kMaxUnitBytes);
-    const uint32_t beg = is4 ? ls[job] : ls[kL4 + 1 + (job - kL4)];
-    const uint32_t end = is4 ? ls[job + 1] : ls[kL4 + 2 + (job - kL4)];
-    uint16_t *out = (is4 ? next4 : prev3) + (size_t)sub * kMaxUnitBytes;
-    uint8_t *clen = clen_g + (size_t)sub * kMaxUnitBytes;
+    const uint32_t nb16 = is4 ? (2u << kBits4) / 16 : (2u << kBits3) / 16;     // uint4 words of the head table
+    uint16_t *out = (is4 ? next4 : prev3) + (size_t)u * g.m_stride;
+    uint8_t *clen = clen_g + (size_t)u * g.m_stride;
     {
         uint4 ones = make_uint4(~0u, ~0u, ~0u, ~0u), zero = make_uint4(0, 0, 0, 0);
         uint4 *h = (uint4 *)head, *c4 = (uint4 *)cnt;
-        for (uint32_t i = lane; i < (is4 ? (2u << kBits4) : (2u << kBits3)) / 16; i += 32) h[i] = ones;
+        for (uint32_t i = lane; i < nb16; i += 32) h[i] = ones;
         if (is4) for (uint32_t i = lane; i < (1u << kBits4) / 16; i += 32) c4[i] = zero;
     }
     __syncwarp();
-    constexpr int G = 8;
-    uint32_t en[G];
+    for (uint32_t ksub = 0; ksub < g.spu; ksub++) {
+        const uint32_t ua = udict + ksub * g.seg;
+        if (ksub && ua >= un) break;
+        const uint32_t lo = ksub == 0 ? 0u : ua;
+        const uint32_t sub = u * g.spu + ksub;
+        if (ksub) {
+            // heads older than the window (and, once, the never-used ones) -> sentinel; occurrence counts decay
+            const uint32_t sentinel = (lo - (uint32_t)kWindow) & 0xFFFFu;
+            uint32_t *h32 = (uint32_t *)head;
+            for (uint32_t i = lane; i < nb16 * 4; i += 32) {
+                uint32_t w = h32[i], r = 0;
 #pragma unroll
-    for (int k = 0; k < G; k++) { uint32_t i = beg + 32 * k + lane; en[k] = i < end ? __ldg(arr + i) : 0; }
-    for (uint32_t base0 = beg; base0 < end; base0 += 32 * G) {
-        uint32_t e[G];
-#pragma unroll
-        for (int k = 0; k < G; k++) e[k] = en[k];
-#pragma unroll
-        for (int k = 0; k < G; k++) { uint32_t i = base0 + 32 * (G + k) + lane; en[k] = i < end ? __ldg(arr + i) : 0; }
-#pragma unroll
-        for (int k = 0; k < G; k++) {
-            const uint32_t i = base0 + 32 * k + lane;
-            if (base0 + 32 * k >= end) break;
-            const bool act = i < end;
-            const uint32_t b = e[k] & (is4 ? ((1u << kBits4) - 1) : ((1u << kBits3) - 1)), p = e[k] >> 16;
-            // Entries of one tile that share a bucket are ordered by lane (= position order): MATCH.ANY gives every
-            // lane its group; the predecessor is the nearest lower member, or the bucket head for the group's first
-            // member; the group's last member becomes the new head.
-            const uint32_t grp = __match_any_sync(0xFFFFFFFFu, act ? b : (0x10000u + lane));
-            const uint32_t lower = grp & lt;
-            const uint32_t pl = __shfl_sync(0xFFFFFFFFu, p, lower ? 31 - __clz(lower) : lane);
-            uint32_t prev = kNone16, occ = 0;
-            if (act) {
-                prev = lower ? pl : (uint32_t)head[b];
-                if (is4) occ = (uint32_t)cnt[b] + (uint32_t)__popc(lower);
-            }
-            __syncwarp();   // every lane has read its bucket before a group's last member overwrites it
-            if (act) {
-                if ((grp >> lane) == 1u) {
-                    head[b] = (uint16_t)p;
-                    if (is4) cnt[b] = (uint8_t)min(occ + 1u, 255u);   // occurrences so far
+                for (int hf = 0; hf < 2; hf++) {
+                    uint32_t hv = (w >> (16 * hf)) & 0xFFFFu;
+                    const uint32_t age = (lo - hv) & 0xFFFFu;
+                    if ((ksub == 1 && hv == kNone16) || age >= (uint32_t)kWindow || age == 0) hv = sentinel;
+                    r |= hv << (16 * hf);
                 }
-                uint32_t dist = (prev != kNone16) ? p - prev : 0;
-                if (dist >= (uint32_t)kWindow) dist = 0;
-                out[p] = (uint16_t)dist;
-                if (is4) clen[p] = (uint8_t)min(occ, 127u);
+                h32[i] = r;
             }
+            if (is4) { uint32_t *c32 = (uint32_t *)cnt; for (uint32_t i = lane; i < (1u << kBits4) / 4; i += 32) c32[i] = (c32[i] >> 1) & 0x7F7F7F7Fu; }
             __syncwarp();
+        }
+        const uint32_t *ls = list_start + (size_t)sub * kLsStride;
+        const uint32_t *arr = lists + (size_t)sub * 2 * kMaxUnitBytes + (is4 ? 0 : kMaxUnitBytes);
+        const uint32_t beg = is4 ? ls[job] : ls[kL4 + 1 + (job - kL4)];
+        const uint32_t end = is4 ? ls[job + 1] : ls[kL4 + 2 + (job - kL4)];
+        constexpr int G = 8;
+        uint32_t en[G];
+#pragma unroll
+        for (int k = 0; k < G; k++) { uint32_t i = beg + 32 * k + lane; en[k] = i < end ? __ldg(arr + i) : 0; }
+        for (uint32_t base0 = beg; base0 < end; base0 += 32 * G) {
+            uint32_t e[G];
+#pragma unroll
+            for (int k = 0; k < G; k++) e[k] = en[k];
+#pragma unroll
+            for (int k = 0; k < G; k++) { uint32_t i = base0 + 32 * (G + k) + lane; en[k] = i < end ? __ldg(arr + i) : 0; }
+#pragma unroll
+            for (int k = 0; k < G; k++) {
+                const uint32_t i = base0 + 32 * k + lane;
+                if (base0 + 32 * k >= end) break;
+                const bool act = i < end;
+                const uint32_t b = e[k] & (is4 ? ((1u << kBits4) - 1) : ((1u << kBits3) - 1)), p = lo + (e[k] >> 16);   // unit position
+                // Entries of one tile that share a bucket are ordered by lane (= position order): MATCH.ANY gives every
+                // lane its group; the predecessor is the nearest lower member, or the bucket head for the group's first
+                // member; the group's last member becomes the new head.
+                const uint32_t grp = __match_any_sync(0xFFFFFFFFu, act ? b : (0x10000u + lane));
+                const uint32_t lower = grp & lt;
+                const uint32_t pl = __shfl_sync(0xFFFFFFFFu, p, lower ? 31 - __clz(lower) : lane);
+                uint32_t dist = 0, occ = 0;
+                if (act) {
+                    if (lower) dist = p - pl;
+                    else {
+                        const uint32_t hv = head[b];
+                        dist = (ksub == 0 && hv == kNone16) ? 0u : ((p - hv) & 0xFFFFu);
+                    }
+                    if (is4) occ = (uint32_t)cnt[b] + (uint32_t)__popc(lower);
+                }
+                __syncwarp();   // every lane has read its bucket before a group's last member overwrites it
+                if (act) {
+                    if ((grp >> lane) == 1u) {
+                        head[b] = (uint16_t)p;
+                        if (is4) cnt[b] = (uint8_t)min(occ + 1u, 255u);   // occurrences so far
+                    }
+                    if (dist >= (uint32_t)kWindow) dist = 0;
+                    out[p] = (uint16_t)dist;
+                    if (is4) clen[p] = (uint8_t)min(occ, 127u);
+                }
+                __syncwarp();
+            }
         }
     }
 }
@@ -380,11 +421,11 @@ k_match(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, cons
             uint32_t bin = (n + 15u) & ~15u, bnx = (n * 2 + 15u) & ~15u;
             mbar_expect_tx(&bar, bin + bnx);
             tma_load_1d(s_in, in, bin, &bar);
-            tma_load_1d(s_next, next4g + (size_t)blockIdx.x * kMaxUnitBytes, bnx, &bar);
+            tma_load_1d(s_next, next4g + (size_t)sb.u * g.m_stride + sb.h, bnx, &bar);
         }
         mbar_wait(&bar, 0);
     }
-    const uint16_t *p3 = prev3g + (size_t)blockIdx.x * kMaxUnitBytes;
+    const uint16_t *p3 = prev3g + (size_t)sb.u * g.m_stride + sb.h;
     const uint32_t depthB = (uint32_t)depth >> 1, depthC = (uint32_t)depth >> 2;
 
     // ---- phase 1: order the positions by chain length -------------------------
@@ -394,7 +435,7 @@ k_match(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, cons
     // sort (per-warp histograms in shared memory) then lets each warp of phase 2
     // process 32 positions of EQUAL chain length.  Ordering only changes the
     // schedule, never a result.
-    uint8_t *clen = clen_g + (size_t)blockIdx.x * kMaxUnitBytes;
+    uint8_t *clen = clen_g + (size_t)sb.u * g.m_stride + sb.h;
     uint16_t *order = order_g + (size_t)blockIdx.x * kMaxUnitBytes;
     const uint32_t warp = tid >> 5;
     for (uint32_t i = tid; i < 32 * 128; i += kMatchThreads) (&s_whist[0][0])[i] = 0;
@@ -1614,7 +1655,7 @@ cudaError_t launch_deflate_pipeline(const DeflateBatch &b, cudaStream_t st)
         GZPB_LAUNCH(k_split, b.nunits * b.spu, kSplitThreads, 0, st, g, b.lists, b.list_start, b.next4, b.prev3, lp.ht,
                     fold_check ? b.sum_part : (uint32_t *)nullptr, b.check_kind);
         DBG_SYNC("k_split");
-        GZPB_LAUNCH(k_link, b.nunits * b.spu * kSplitLists, 32, 0, st, g, b.lists, b.list_start, b.next4, b.prev3, b.clen);
+        GZPB_LAUNCH(k_link, b.nunits * kSplitLists, 32, 0, st, g, b.lists, b.list_start, b.next4, b.prev3, b.clen);
         DBG_SYNC("k_link");
         if (b.timer) { b.timer->stop(st); b.timer->start(KT_MATCH, st); }
         GZPB_LAUNCH(k_match, b.nunits * b.spu, kMatchThreads, match_smem, st, g, b.next4, b.prev3, b.mtab, b.mtab2, b.clen, b.order, lp.depth, lp.nice, lp.mode, lp.ht);

@@ -39,13 +39,13 @@ struct DeflateBatch {
     const uint32_t *unit_len; // nunits: dictionary + data bytes of the unit
     const uint32_t *unit_dict; // nunits: dictionary bytes in front of the data
     const uint32_t *unit_flags;  // bit0 = is_last (BGZF EOF), bit1 = sync flush (no BFINAL)
-    uint16_t *next4;          // nunits * spu * 65536
-    uint16_t *prev3;          // nunits * spu * 65536
+    uint16_t *next4;          // nunits * m_stride: hash4 chain link of every unit position (distance, 0 = none)
+    uint16_t *prev3;          // nunits * m_stride: hash3 link
     uint32_t *lists;          // nunits * spu * 2 * 65536 (k_split position lists)
     uint32_t *list_start;     // nunits * spu * 16
     uint64_t *mtab;           // nunits * m_stride
     uint32_t *mtab2;          // nunits * m_stride, lazy2 levels only (depth/4 column), else NULL
-    uint8_t *clen;            // nunits * spu * 65536 (chain lengths, k_match scratch)
+    uint8_t *clen;            // nunits * m_stride (chain-length estimates: k_link -> k_match)
     uint16_t *order;          // nunits * spu * 65536 (positions sorted by chain length)
     uint32_t *crc;            // nunits: Check::sum per unit
     uint32_t *sum_part;       // nunits * spu: per-sub-unit partial sums (k_split -> k_emit), NULL = separate k_check pass

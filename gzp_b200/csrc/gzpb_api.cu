@@ -226,12 +226,12 @@ static int lane_alloc(gzpb_ctx *c, Lane &L, bool with_io)
         memset(L.h_crc, 0, U * sizeof(uint32_t));
         return GZPB_OK;
     }
-    CK(dmalloc(&L.d_next4, U * c->spu * kMaxUnitBytes));
-    CK(dmalloc(&L.d_prev3, U * c->spu * kMaxUnitBytes));
+    CK(dmalloc(&L.d_next4, U * (size_t)c->m_stride + 64));      // per unit position (k_link carries its heads across sub-units)
+    CK(dmalloc(&L.d_prev3, U * (size_t)c->m_stride + 64));
     CK(dmalloc(&L.d_order, U * c->spu * kMaxUnitBytes));
     CK(dmalloc(&L.d_lists, U * c->spu * 2 * kMaxUnitBytes));
     CK(dmalloc(&L.d_list_start, U * c->spu * 32));
-    CK(dmalloc(&L.d_clen, U * c->spu * kMaxUnitBytes));
+    CK(dmalloc(&L.d_clen, U * (size_t)c->m_stride + 64));
     CK(dmalloc(&L.d_mtab, U * c->m_stride));
     if (c->level >= 8) CK(dmalloc(&L.d_mtab2, U * c->m_stride));
     CK(dmalloc(&L.d_crc, U));

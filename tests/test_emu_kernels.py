@@ -649,3 +649,17 @@ def test_emu_encode_stream_multi_devices(monkeypatch):
         L.gzpb_host_free(pin_in); L.gzpb_host_free(pin_out)
         for d in range(3):
             L.gzpb_destroy(hs[d])
+
+
+def test_emu_long_units_carried_heads_window_edges():
+    """Long units are linked sub-unit by sub-unit with the bucket heads carried along (positions mod 65536, stale heads
+    parked on a sentinel): data whose repeats sit exactly at, just inside and just outside the 32 KiB window, and
+    low-entropy data whose buckets are hit in every sub-unit, over units several 64 KiB wraps long."""
+    rnd = random.Random(4711)
+    base = bytes(rnd.getrandbits(8) for _ in range(33000))
+    for period in (32767, 32768, 32769, 20000):
+        data = (base[:period] * 12)[:300000]
+        assert gzip.decompress(_run(oracle.MGZIP, 6, 300000, data)) == data
+    mixed = (synth.low_entropy(150000) + TEXT[:70000] + bytes(40000) + synth.fastq(140000))[:400000]
+    assert gzip.decompress(_run(oracle.MGZIP, 5, 400000, mixed)) == mixed
+    assert gzip.decompress(_run(oracle.GZIP, 6, 200000, mixed + mixed[:150000])) == mixed + mixed[:150000]
