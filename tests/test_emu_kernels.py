@@ -70,8 +70,14 @@ def test_emu_level1_fastest_all_formats():
 
 
 def test_emu_snap():
+    """k_snap (chunk staged in shared memory, 32 probes per step, CRC-32C on the helper warps) against the oracle's
+    sequential encoder: text, runs, random data (the accelerating skip crosses many probe batches), mixtures whose
+    hits fall on every lane of a batch, sizes around the 17-byte / 15-byte margins and the 64 KiB chunk boundary."""
     rnd = random.Random(7)
-    for d in (TEXT, bytes(70000), bytes(rnd.getrandbits(8) for _ in range(50000)), b"", b"abc"):
+    rand = bytes(rnd.getrandbits(8) for _ in range(50000))
+    mix = b"".join(rand[i * 40:(i + 1) * 40] + TEXT[i * 7:i * 7 + rnd.randrange(1, 90)] + rand[i * 40:i * 40 + rnd.randrange(4, 40)] for i in range(900))
+    for d in (TEXT, bytes(70000), rand, b"", b"abc", mix, synth.low_entropy(140000), synth.fastq(70000), bytes(rnd.choice(b"ab") for _ in range(3000)) * 25,
+              TEXT[:65536], TEXT[:65537], TEXT[3:3 + 65535], rand[:4000] + bytes(5000) + rand[:4000], b"x" * 16, b"x" * 17, b"xy" * 9, TEXT[:31], TEXT[:32], TEXT[:47]):
         _run(oracle.SNAP, 0, 131072, d)
 
 
