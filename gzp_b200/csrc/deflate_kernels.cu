@@ -271,6 +271,7 @@ k_split(const __grid_constant__ Geo g, uint32_t *__restrict__ lists, uint32_t *_
     }
 }
 
+template <bool kMulti>     // kMulti: units of several sub-units (the loop over them and the head sweep exist only there)
 __global__ void __launch_bounds__(32)
 k_link(const __grid_constant__ Geo g, const uint32_t *__restrict__ lists, const uint32_t *__restrict__ list_start,
        uint16_t *__restrict__ next4, uint16_t *__restrict__ prev3, uint8_t *__restrict__ clen_g)
@@ -296,12 +297,12 @@ k_link(const __grid_constant__ Geo g, const uint32_t *__restrict__ lists, const 
         if (is4) for (uint32_t i = lane; i < (1u << kBits4) / 16; i += 32) c4[i] = zero;
     }
     __syncwarp();
-    for (uint32_t ksub = 0; ksub < g.spu; ksub++) {
+    for (uint32_t ksub = 0; ksub < (kMulti ? g.spu : 1u); ksub++) {
         const uint32_t ua = udict + ksub * g.seg;
         if (ksub && ua >= un) break;
         const uint32_t lo = ksub == 0 ? 0u : ua;
         const uint32_t sub = u * g.spu + ksub;
-        if (ksub) {
+        if (kMulti && ksub) {
             // heads older than the window (and, once, the never-used ones) -> sentinel; occurrence counts decay
             const uint32_t sentinel = (lo - (uint32_t)kWindow) & 0xFFFFu;
             uint32_t *h32 = (uint32_t *)head;
@@ -350,7 +351,7 @@ k_link(const __grid_constant__ Geo g, const uint32_t *__restrict__ lists, const 
                     if (lower) dist = p - pl;
                     else {
                         const uint32_t hv = head[b];
-                        dist = (ksub == 0 && hv == kNone16) ? 0u : ((p - hv) & 0xFFFFu);
+                        dist = (!kMulti || ksub == 0) ? (hv == kNone16 ? 0u : p - hv) : ((p - hv) & 0xFFFFu);
                     }
                     if (is4) occ = (uint32_t)cnt[b] + (uint32_t)__popc(lower);
                 }
@@ -1655,7 +1656,8 @@ cudaError_t launch_deflate_pipeline(const DeflateBatch &b, cudaStream_t st)
         GZPB_LAUNCH(k_split, b.nunits * b.spu, kSplitThreads, 0, st, g, b.lists, b.list_start, b.next4, b.prev3, lp.ht,
                     fold_check ? b.sum_part : (uint32_t *)nullptr, b.check_kind);
         DBG_SYNC("k_split");
-        GZPB_LAUNCH(k_link, b.nunits * kSplitLists, 32, 0, st, g, b.lists, b.list_start, b.next4, b.prev3, b.clen);
+        if (b.spu > 1) GZPB_LAUNCH(k_link<true>, b.nunits * kSplitLists, 32, 0, st, g, b.lists, b.list_start, b.next4, b.prev3, b.clen);
+        else GZPB_LAUNCH(k_link<false>, b.nunits * kSplitLists, 32, 0, st, g, b.lists, b.list_start, b.next4, b.prev3, b.clen);
         DBG_SYNC("k_link");
         if (b.timer) { b.timer->stop(st); b.timer->start(KT_MATCH, st); }
         GZPB_LAUNCH(k_match, b.nunits * b.spu, kMatchThreads, match_smem, st, g, b.next4, b.prev3, b.mtab, b.mtab2, b.clen, b.order, lp.depth, lp.nice, lp.mode, lp.ht);
