@@ -128,6 +128,20 @@ constexpr int kSplitLists = kL4 + kL3;
 constexpr int kBits4 = 12, kBits3 = 13;  // buckets per link job: hash4 8 KiB table + 4 KiB counts, hash3 16 KiB table
 constexpr int kLsStride = 32;            // list_start entries per sub-unit: [0..kL4] hash4 bounds, [kL4+1..kL4+1+kL3] hash3 bounds
 
+// Lanes of the warp whose (active) list id equals this lane's: the id has only BITS bits, so BITS ballots do what a
+// MATCH.ANY does at a fraction of its latency (k_split ranks every position twice per pass).
+template <int BITS>
+__device__ __forceinline__ uint32_t same_list_mask(uint32_t id, bool act)
+{
+    uint32_t m = __ballot_sync(0xFFFFFFFFu, act);
+#pragma unroll
+    for (int b = 0; b < BITS; b++) {
+        const uint32_t v = __ballot_sync(0xFFFFFFFFu, (id >> b) & 1u);
+        m &= ((id >> b) & 1u) ? v : ~v;
+    }
+    return m;
+}
+
 __global__ void __launch_bounds__(kSplitThreads)
 k_split(const __grid_constant__ Geo g, uint32_t *__restrict__ lists, uint32_t *__restrict__ list_start,
         uint16_t *__restrict__ next4, uint16_t *__restrict__ prev3, int ht, uint32_t *__restrict__ sum_part, int check_kind)
@@ -171,8 +185,7 @@ k_split(const __grid_constant__ Geo g, uint32_t *__restrict__ lists, uint32_t *_
         uint32_t h4 = ht ? (lz_hash(v, 15) << 1) : lz_hash(v, 16), h3 = lz_hash(v & 0xFFFFFFu, 15);   // level 1: 15-bit buckets (even slots)
         if (p == 0 && quirk0) { h4 = 0; h3 = 0; }
         const uint32_t q4 = h4 >> kBits4, q3 = h3 >> kBits3;
-        const uint32_t m4 = __match_any_sync(0xFFFFFFFFu, act ? q4 : 64u);
-        const uint32_t m3 = __match_any_sync(0xFFFFFFFFu, act ? q3 : 64u);
+        const uint32_t m4 = same_list_mask<4>(q4, act), m3 = same_list_mask<2>(q3, act);
         if (act && (m4 & lt) == 0) s_w[warp][q4] += __popc(m4);          // group leader
         if (act && (m3 & lt) == 0) s_w[warp][kL4 + q3] += __popc(m3);
         __syncwarp();
@@ -203,8 +216,7 @@ k_split(const __grid_constant__ Geo g, uint32_t *__restrict__ lists, uint32_t *_
         uint32_t h4 = ht ? (lz_hash(v, 15) << 1) : lz_hash(v, 16), h3 = lz_hash(v & 0xFFFFFFu, 15);   // level 1: 15-bit buckets (even slots)
         if (p == 0 && quirk0) { h4 = 0; h3 = 0; }
         const uint32_t q4 = h4 >> kBits4, q3 = h3 >> kBits3;
-        const uint32_t m4 = __match_any_sync(0xFFFFFFFFu, act ? q4 : 64u);
-        const uint32_t m3 = __match_any_sync(0xFFFFFFFFu, act ? q3 : 64u);
+        const uint32_t m4 = same_list_mask<4>(q4, act), m3 = same_list_mask<2>(q3, act);
         uint32_t b4 = 0, b3 = 0;
         if (act) { b4 = s_w[warp][q4]; b3 = s_w[warp][kL4 + q3]; }
         __syncwarp();
@@ -1078,13 +1090,15 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
                         }
                     }
                     // ---- follow the path through the window (one token per hop) ----
-                    uint32_t visF = 0, visH = 0, c = 0, st_h = in_h;
-                    while (c < 32 && p + c < max_block_end) {
-                        if (st_h) visH |= 1u << c; else visF |= 1u << c;
-                        uint32_t w = __shfl_sync(0xFFFFFFFFu, st_h ? wH : wF, c);
+                    // (every lane walks the same path: both transition words of a position travel in one shuffle)
+                    const uint32_t wlimit = min(32u, max_block_end - p), wFH = wF | (wH << 16);
+                    uint32_t vis = 0, visH = 0, c = 0, st_h = in_h;
+                    while (c < wlimit) {
+                        vis |= 1u << c; visH |= st_h << c;
+                        const uint32_t w2 = __shfl_sync(0xFFFFFFFFu, wFH, c);
+                        const uint32_t w = st_h ? (w2 >> 16) : w2;
                         c += w & 0x1FF; st_h = (w >> 9) & 1;
                     }
-                    const uint32_t vis = visF | visH;
                     const bool onpath = (vis >> lane) & 1u;
                     const bool asH = (visH >> lane) & 1u;
                     const uint32_t myw = asH ? wH : wF;

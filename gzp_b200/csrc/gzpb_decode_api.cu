@@ -94,6 +94,9 @@ extern "C" int gzpb_scan_blocks(int format, const void *in_v, size_t in_len, gzp
         const uint8_t *f = in + pos + size - 8;                        // get_footer_values (lib.rs:440-447)
         const uint32_t crc = (uint32_t)f[0] | ((uint32_t)f[1] << 8) | ((uint32_t)f[2] << 16) | ((uint32_t)f[3] << 24);
         const uint32_t isize = (uint32_t)f[4] | ((uint32_t)f[5] << 8) | ((uint32_t)f[6] << 16) | ((uint32_t)f[7] << 24);
+        // ISIZE sizes the output buffers before anything is decoded: DEFLATE expands at most 1032:1, so a footer that
+        // claims more than its payload can hold is corrupt data — not a multi-GiB allocation request
+        if ((uint64_t)isize > 1032ull * (uint64_t)((size_t)size - hs - 8) + 64) { rc = GZPB_EDECOMPRESS; break; }
         if (descs) {
             if (n >= max_descs) break;
             gzpb_block_desc &d = descs[n];
@@ -329,6 +332,7 @@ struct gzpb_reader {
     size_t in_cap = 0, in_len = 0, out_cap = 0, out_len = 0, out_pos = 0, chunk = 0;
     bool eof = false;
     int error = GZPB_OK;
+    int pending_error = GZPB_OK;                 // a bad member behind good ones: the good ones are handed out first
     uint64_t bytes_in = 0, bytes_out = 0;
 };
 
@@ -362,6 +366,7 @@ extern "C" int gzpb_reader_create(gzpb_reader **out, int device, int format, siz
 // one round of the reader loop: pull up to `chunk` bytes, decode the whole members that are there
 static int reader_fill(gzpb_reader *r)
 {
+    if (r->pending_error) return r->pending_error;
     int rc = reader_grow(&r->in, &r->in_cap, r->in_len, r->in_len + r->chunk);
     if (rc != GZPB_OK) return rc;
     while (!r->eof && r->in_len < r->in_cap) {                          // a source may return short reads
@@ -375,8 +380,13 @@ static int reader_fill(gzpb_reader *r)
     uint64_t total = 0;
     rc = gzpb_scan_blocks(r->format, r->in, r->in_len, nullptr, 0, &nb, &consumed, &total);
     if (rc == GZPB_EIO && !r->eof) rc = GZPB_OK;                        // incomplete trailing member: wait for more bytes
-    if (rc != GZPB_OK) return rc;
-    if (r->eof && r->in_len - consumed >= header_size(r->format)) return GZPB_EIO;
+    if (rc == GZPB_OK && r->eof && r->in_len - consumed >= header_size(r->format)) rc = GZPB_EIO;
+    if (rc != GZPB_OK) {
+        // like the reference's reader thread (decompress.rs:190-207), which has already sent the members in front of a
+        // bad one to the workers: they are decoded and delivered, the error surfaces on the read after them
+        if (nb == 0) return rc;
+        r->pending_error = rc;
+    }
     if (nb == 0) {
         if (r->eof) r->in_len = 0;                                      // a short trailing header is EOF
         return GZPB_OK;                                                 // (a member larger than the chunk: the buffer grows next round)

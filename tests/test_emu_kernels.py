@@ -566,6 +566,25 @@ def test_emu_native_pardecompress_reader_object(emu_backend):
     with pytest.raises(gzp_b200.GzpError) as ei:
         gzp_b200.NativeParDecompress(gzp_b200.Bgzf(), io.BytesIO(bytes(hdr))).read()
     assert ei.value.variant == "InvalidHeader"
+    # a bad member BEHIND good ones: the good ones are delivered first (the reference's reader thread has already sent
+    # them to the workers, decompress.rs:190-207), then the error
+    sizes, pos = [], 0
+    while pos < len(comp):
+        sizes.append(struct.unpack_from("<H", comp, pos + 16)[0] + 1); pos += sizes[-1]
+    third = sum(sizes[:3])
+    for mutate, variant in ((lambda b: b.__setitem__(third + 12, ord("X")), "InvalidHeader"),
+                            (lambda b: b.__setitem__(slice(third + sizes[3] - 4, third + sizes[3]), b"\xf0\xff\xff\xff"), "LibDelfaterDecompress")):
+        bad = bytearray(comp); mutate(bad)
+        r = gzp_b200.NativeParDecompress(gzp_b200.Bgzf(), io.BytesIO(bytes(bad)))
+        got = bytearray()
+        with pytest.raises(gzp_b200.GzpError) as ei:
+            while True:
+                b = r.read(65280)
+                assert b
+                got += b
+        assert ei.value.variant == variant, ei.value.variant
+        assert len(got) == 3 * 65280 and bytes(got) == TEXT[:3 * 65280]                      # an implausible ISIZE is corrupt data, not an allocation request
+        r.close()
 
     class Failing:
         def read(self, n):
