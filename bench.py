@@ -46,7 +46,7 @@ CONFIGS = {
                   workload="ParCompress<Mgzip> level 6, 131072-B blocks, shakespeare.txt repeated (BASELINE configs[2])"),
     "snap": dict(fmt=SNAP, level=0, block=131072, inflight=2048, blocks=8192, data="low", metric="snap_compress_input_throughput",
                  workload="ParCompress<Snap>, 131072-B blocks, low-entropy synthetic binary (BASELINE configs[3]; SURVEY 8d generator, 256 MiB period)"),
-    "gzip9": dict(fmt=GZIP, level=9, block=262144, inflight=1776, blocks=5328, data="fastq", metric="gzip_l9_dict_compress_input_throughput",
+    "gzip9": dict(fmt=GZIP, level=9, block=262144, inflight=2368, blocks=7104, data="fastq", metric="gzip_l9_dict_compress_input_throughput",
                   workload="ParCompress<Gzip> level 9 (dictionary carry), 262144-B blocks, FASTQ-shaped synthetic (BASELINE configs[4]; 64 MiB period)"),
 }
 # Algorithmic HBM bytes per input byte of each config's dominant kernel:

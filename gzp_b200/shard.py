@@ -1,6 +1,8 @@
 """Multi-GPU sharding of the block stream: blocks are independent, so
-the host deals contiguous batches of blocks round-robin to the ranks (batch k -> rank
-k mod G) and the single ticket FIFO restores order.  No data-path collective."""
+the host deals contiguous batches of blocks round-robin to the GPUs (batch k -> GPU
+k mod G) and one ordered drain restores the stream.  No data-path collective.
+This is the dealing rule of gzpb_encode_stream_multi / gzpb_writer_create_multi (gzpb_api.cu) stated in
+Python, so that the world_size-2 gloo test (tests/test_shard_gloo.py) can hold it on CPU."""
 
 
 def batch_ranges(nblocks, batch, world):
