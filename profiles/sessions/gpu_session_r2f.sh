@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round-2 session f (not a test), on a multi-GPU box (gpurun --gpus N): one ordered stream over N GPUs.
-#   gpurun --gpus 2 --timeout 900 -- 'bash tests/gpu_session_r2f.sh 2'
+#   gpurun --gpus 2 --timeout 900 -- 'bash profiles/sessions/gpu_session_r2f.sh 2'
 N=${1:-2}
 mkdir -p gpurun_out
 ( nvidia-smi -L; nproc; free -g | head -2; nvidia-smi topo -m; lscpu | grep -i "numa\|socket\|model name" ) > gpurun_out/r2k_host_n$N.txt 2>&1

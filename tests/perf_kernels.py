@@ -1,5 +1,5 @@
 """Per-kernel device times of one kernel-set configuration (not a test; run under gpurun).  The configuration comes
-from the environment (GZPB_MATCH_BATCH, GZPB_SPARSE, ...), one process per configuration, so that A/B loops are
+from the environment (GZPB_LIB = another build of the library, GZPB_GATHER_CTAS, GZPB_SEPARATE_CHECK, ...), one process per configuration, so that A/B loops are
 plain shell loops.  Prints one JSON line: total ms per batch, per-kernel ms, sha1 of the packed stream.
 usage: python tests/perf_kernels.py [blocks] [level] [steps] [label]"""
 import ctypes as C
