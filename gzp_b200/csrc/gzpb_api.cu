@@ -1221,6 +1221,7 @@ extern "C" void gzpb_writer_destroy(gzpb_writer *w)
 #ifndef GZPB_EMU_NO_FILES
 #include <errno.h>
 #include <fcntl.h>
+#include <sys/stat.h>
 #include <unistd.h>
 
 static int file_sink(void *user, const void *data, size_t len)
@@ -1247,6 +1248,15 @@ extern "C" int gzpb_compress_file(const int *devices, size_t ndevices, int forma
 #ifdef POSIX_FADV_SEQUENTIAL
     posix_fadvise(fin, 0, 0, POSIX_FADV_SEQUENTIAL);
 #endif
+    if (blocks_in_flight == 0) {
+        // context and slab allocation scale with the batch size: a file that fills only a few batches gets smaller ones
+        struct stat sb;
+        const size_t bs = buffer_size ? buffer_size : gzpb_default_bufsize(format);
+        if (fstat(fin, &sb) == 0 && sb.st_size > 0 && ndevices) {
+            const size_t nblocks = (size_t)sb.st_size / bs + 1, per = nblocks / (kLanes * ndevices) + 1;
+            blocks_in_flight = std::min((size_t)1184, std::max((size_t)74, per));
+        }
+    }
     gzpb_writer *w = nullptr;
     int rc = gzpb_writer_create_multi(&w, devices, ndevices, format, level, buffer_size, blocks_in_flight, file_sink, &fout);
     while (rc == GZPB_OK) {

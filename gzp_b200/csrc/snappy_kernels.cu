@@ -4,9 +4,11 @@
 // chunk {type, u24 length, masked CRC-32C, raw Snappy block or stored bytes}.
 //
 // One warp per 64 KiB chunk, thousands of chunks in flight.  The greedy parse of
-// the raw encoder is inherently sequential (the u16 hash table is only updated at
-// visited positions), so lane 0 runs the probe loop exactly as the oracle
-// (oracle/snappy_oracle.c) while the whole warp does the byte-heavy parts:
+// the raw encoder is sequential only where the format makes it so (the u16 hash
+// table is updated at visited positions only): the probe loop — the scan for the
+// next 4-byte match with its accelerating skip — is evaluated 32 probes at a time
+// (hashes and candidate compares in parallel, MATCH.ANY orders probes that share a
+// bucket, the first hit wins), and the whole warp does the byte-heavy parts:
 // literal copies, match extension (32 bytes per ballot), CRC-32C, stored copies.
 // Results are bit-identical to the oracle (tests/test_gpu_parity.py).
 //
@@ -135,30 +137,48 @@ k_snap(const uint8_t *__restrict__ in_base, const uint32_t *__restrict__ unit_le
         emit_literal(n);
     } else {
         const uint32_t s_limit = n - kInputMargin;
+        const uint32_t lt = lanemask_lt();
         uint32_t s = 1;
-        uint32_t next_hash = HASH(g32(src + s));
         bool finished = false;
         while (!finished) {
-            // ---- lane 0: probe for the next 4-byte match (accelerating skip) ----
-            uint32_t candidate = 0, found = 0;
-            if (lane == 0) {
-                uint32_t skip = 32, s_next = s;
-                for (;;) {
-                    s = s_next;
-                    uint32_t step = skip >> 5;
-                    s_next = s + step;
-                    skip += step;
-                    if (s_next > s_limit) break;
-                    candidate = table[next_hash];
-                    table[next_hash] = (uint16_t)s;
-                    next_hash = HASH(g32(src + s_next));
-                    if (g32(src + s) == g32(src + candidate)) { found = 1; break; }
+            // ---- the probe loop of the raw encoder, 32 probes per step: probe i looks at P_i (P_0 = s, P_{i+1} = P_i +
+            // (skip_i >> 5), skip_{i+1} = skip_i + (skip_i >> 5), skip_0 = 32) and runs only while P_{i+1} <= s_limit; it
+            // takes the bucket's entry as candidate, stores P_i there and hits when the 4 bytes at both places agree.
+            // In a batch: MATCH.ANY gives the probes of one bucket in order (a later probe's candidate is the nearest
+            // earlier probe), the first hit ends the loop and the probes behind it leave no trace in the table. ----
+            uint32_t candidate = 0, found = 0, skip = 32;
+            for (;;) {
+                uint32_t P = s, sk = skip;
+                if (skip == 32) { P = s + lane; sk = 32 + lane; }                 // first batch: steps of one
+                else for (uint32_t j = 0; j < lane; j++) { const uint32_t st = sk >> 5; P += st; sk += st; }
+                const uint32_t Pn = P + (sk >> 5), skn = sk + (sk >> 5);            // the next probe's position / skip
+                const bool valid = Pn <= s_limit;
+                const uint32_t v = valid ? g32(src + P) : 0;
+                const uint32_t h = HASH(v);
+                const uint32_t grp = __match_any_sync(0xFFFFFFFFu, valid ? h : (0x10000u + lane));
+                const uint32_t lower = grp & lt;
+                const uint32_t pl = __shfl_sync(0xFFFFFFFFu, P, lower ? 31 - __clz(lower) : lane);
+                const uint32_t cand = valid ? (lower ? pl : (uint32_t)table[h]) : 0;
+                const bool hit = valid && g32(src + cand) == v;
+                const uint32_t vmask = __ballot_sync(0xFFFFFFFFu, valid), hmask = __ballot_sync(0xFFFFFFFFu, hit);
+                // probes that really run: up to the first hit, or the valid prefix
+                const uint32_t f = hmask ? (uint32_t)__ffs(hmask) - 1 : 32u;
+                const uint32_t run = hmask ? ((f == 31 ? 0xFFFFFFFFu : ((2u << f) - 1))) : vmask;
+                const uint32_t mine = grp & run;
+                __syncwarp();   // every probe has read its bucket
+                if (valid && ((run >> lane) & 1u) && (mine >> lane) == 1u) table[h] = (uint16_t)P;   // the bucket keeps its last probe
+                __syncwarp();
+                if (hmask) {
+                    found = 1;
+                    s = __shfl_sync(0xFFFFFFFFu, P, f);
+                    candidate = __shfl_sync(0xFFFFFFFFu, cand, f);
+                    break;
                 }
+                if (vmask != 0xFFFFFFFFu) break;                                    // s_next ran past s_limit: no further match
+                s = __shfl_sync(0xFFFFFFFFu, Pn, 31);
+                skip = __shfl_sync(0xFFFFFFFFu, skn, 31);
             }
-            found = __shfl_sync(0xFFFFFFFFu, found, 0);
             if (!found) break;
-            s = __shfl_sync(0xFFFFFFFFu, s, 0);
-            candidate = __shfl_sync(0xFFFFFFFFu, candidate, 0);
             emit_literal(s);
             for (;;) {
                 // ---- warp: extend the match 32 bytes per step ----
@@ -187,7 +207,7 @@ k_snap(const uint8_t *__restrict__ in_base, const uint32_t *__restrict__ unit_le
                         uint32_t cur = (uint32_t)(x >> 8), ch = HASH(cur);
                         candidate = table[ch];
                         table[ch] = (uint16_t)s;
-                        if (cur != g32(src + candidate)) { next_hash = HASH((uint32_t)(x >> 16)); s++; again = 0; }
+                        if (cur != g32(src + candidate)) { s++; again = 0; }
                         else again = 1;
                     }
                 }
