@@ -939,182 +939,104 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
                 next_recalc = bb + min(n - bb, 10000u);
                 uint32_t ntok = 0, nmatch = 0, num_obs = 0, num_new_obs = 0, in_h = 0;
                 bool end_block = false;
-                if (mode == 2) {
-                    // lazy2 (levels 8-9): the reference's loop restated one iteration at a time; every lane
-                    // runs the same (uniform) control flow, lane 0 commits.  These levels are bound by the
-                    // depth-300/600 chain walks of k_match, not by this loop.
-                    const uint32_t *M2 = mtab2 + (size_t)u * g.m_stride;
-                    auto emit_lit = [&](uint32_t pos) {
-                        if (lane == 0) {
-                            uint32_t lit = in[pos];
-                            atomicAdd(&S.fl[lit], 1u);
-                            atomicAdd(&S.new_obs[((lit >> 5) & 6) | (lit & 1)], 1u);
-                            tok[ntok] = lit;
-                        }
-                        ntok++; num_new_obs++;
-                    };
-                    do {
-                        P.advance(p);
-                        P.need(min(n - 1, p + 3));
-                        if (p >= next_recalc) {
-                            __syncwarp();
-                            uint32_t total = 0;
-                            for (int i = 0; i < 8; i++) total += S.fl[lane * 8 + i];
-                            for (int o = 16; o; o >>= 1) total += __shfl_xor_sync(0xFFFFFFFFu, total, o);
-                            uint32_t cutoff = total >> 10, nu = 0;
-                            for (int i = 0; i < 8; i++) nu += (S.fl[lane * 8 + i] > cutoff);
-                            for (int o = 16; o; o >>= 1) nu += __shfl_xor_sync(0xFFFFFFFFu, nu, o);
-                            min_len = choose_min_match_len(nu, depth);
-                            next_recalc += min(n - next_recalc, p - bb);
-                        }
-                        uint32_t cur_len, cur_off;
-                        table_search(P.M(p), min_len - 1, false, min((uint32_t)kMaxMatch, n - p), cur_len, cur_off);
-                        if (cur_len < min_len || (cur_len == 3 && cur_off > 8192)) { emit_lit(p); p++; }
-                        else {
-                            uint32_t m = p;
-                            for (;;) {
-                                const uint32_t nice_m = min((uint32_t)nice, min((uint32_t)kMaxMatch, n - m));
-                                if (cur_len >= nice_m) break;
-                                P.advance(m);
-                                P.need(min(n - 1, m + 3));
-                                uint32_t nl, no;
-                                const uint32_t maxlen1 = (m + 1 < n) ? min((uint32_t)kMaxMatch, n - (m + 1)) : 0u;
-                                table_search(maxlen1 >= 5 ? P.M(m + 1) : 0ull, cur_len - 1, true, maxlen1, nl, no);
-                                if (nl >= cur_len && 4 * (int)(nl - cur_len) + ((int)bsr32(cur_off) - (int)bsr32(no)) > 2) {
-                                    emit_lit(m); m++; cur_len = nl; cur_off = no;
-                                    continue;
-                                }
-                                const uint32_t maxlen2 = (m + 2 < n) ? min((uint32_t)kMaxMatch, n - (m + 2)) : 0u;
-                                nl = cur_len - 1; no = 0;
-                                if (maxlen2 >= 5) {
-                                    // longest_match(m+2, cur_len-1, depth>>2) answered from the depth/4 column
-                                    const uint64_t e2 = P.M(m + 2);
-                                    const uint32_t c2 = M2[m + 2];
-                                    uint32_t lx = c2 & 0xFF, ox = (c2 >> 8) & 0x7FFF, b = cur_len - 1;
-                                    if (lx) lx += 3;
-                                    if (b < 4) {
-                                        if ((e2 >> 46) & 1) {
-                                            uint32_t off3 = (uint32_t)(e2 >> 47) & 0x3FFF;
-                                            if (b < 3 && off3) { nl = 3; no = off3; }
-                                            if (lx) { nl = lx; no = ox; }
-                                        }
-                                    } else if (lx > b) { nl = lx; no = ox; }
-                                }
-                                if (nl >= cur_len && 4 * (int)(nl - cur_len) + ((int)bsr32(cur_off) - (int)bsr32(no)) > 6) {
-                                    emit_lit(m); emit_lit(m + 1); m += 2; cur_len = nl; cur_off = no;
-                                    continue;
-                                }
-                                break;
-                            }
-                            if (lane == 0) {
-                                atomicAdd(&S.fl[kFirstLenSym + len_slot_only(cur_len)], 1u);
-                                atomicAdd(&S.fo[off_slot_only(cur_off)], 1u);
-                                atomicAdd(&S.new_obs[8 + (cur_len >= 9)], 1u);
-                                tok[ntok] = 0x80000000u | (cur_len << 16) | cur_off;
-                            }
-                            ntok++; num_new_obs++; nmatch++;
-                            p = m + cur_len;
-                        }
-                        if (nmatch >= (uint32_t)kSeqStoreLength) end_block = true;
-                        else if (num_new_obs >= (uint32_t)kObsPerCheck && p - bb >= (uint32_t)kMinBlockLength && n - p >= (uint32_t)kMinBlockLength) {
-                            __syncwarp();
-                            uint32_t block_length = p - bb;
-                            if (num_obs > 0) {
-                                uint32_t d = 0;
-                                if (lane < 10) {
-                                    uint32_t expected = S.obs[lane] * num_new_obs, actual = S.new_obs[lane] * num_obs;
-                                    d = actual > expected ? actual - expected : expected - actual;
-                                }
-                                for (int o = 16; o; o >>= 1) d += __shfl_xor_sync(0xFFFFFFFFu, d, o);
-                                uint32_t num_items = num_obs + num_new_obs;
-                                uint32_t cutoff = num_new_obs * 200 / 512 * num_obs;
-                                if (block_length < 10000 && num_items < 8192)
-                                    cutoff += (uint32_t)((uint64_t)cutoff * (8192 - num_items) / 8192);
-                                if (d + (block_length / 4096) * num_obs >= cutoff) end_block = true;
-                            }
-                            if (!end_block) {
-                                if (lane < 10) { S.obs[lane] += S.new_obs[lane]; S.new_obs[lane] = 0; }
-                                num_obs += num_new_obs; num_new_obs = 0;
-                            }
-                            __syncwarp();
-                        }
-                    } while (p < max_block_end && !end_block);
-                } else
+                const uint32_t *M2 = (mode == 2) ? mtab2 + (size_t)u * g.m_stride : nullptr;   // lazy2: depth/4 column
                 do {
                     P.advance(p);
-                    P.need(min(n - 1, p + 33));
+                    P.need(min(n - 1, p + 33 + (mode == 2 ? 1u : 0u)));
                     // ---- per-lane transitions at q = p + lane ----
-                    // F(q): parser in its fresh state at q (top of the reference's main loop).
-                    // H(q): parser at `have_cur_match` at q, the current match being the
-                    //       depth/2 search result at q (the only way that state is reached).
+                    // F(q)  : parser in its fresh state at q (top of the reference's main loop).
+                    // HB(q) : parser at `have_cur_match` at q, the current match being the depth/2 search result at q
+                    //         (reached through the look-ahead at the next position).
+                    // HC(q) : the same with the depth/4 result at q (lazy2: reached through the look-ahead two positions on).
+                    // X(q)  : lazy2, second of the two literals in front of an HC match: literal at q, then HC(q + 1).
                     // A transition emits ONE token and names the next state:
-                    //   word = advance (bits 0-8) | next-is-H (bit 9) | token-is-match (bit 10)
+                    //   word = match length (bits 0-8, bit 9 clear: next state F) | 0x200 + next state (a literal)
                     const uint32_t q = p + lane;
-                    uint32_t wF = 1, wH = 1, lenF = 0, offF = 0, lenH = 0, offH = 0;
+                    uint32_t wF = 0x200, wHB = 0x200, wHC = 0x200, lenF = 0, offF = 0, lenHB = 0, offHB = 0, lenHC = 0, offHC = 0;
                     if (q < max_block_end) {
                         const uint64_t e0 = P.M(q);
                         const uint32_t maxlen = min((uint32_t)kMaxMatch, n - q);
                         const uint32_t maxlen1 = (q + 1 < n) ? min((uint32_t)kMaxMatch, n - (q + 1)) : 0u;
                         const uint64_t e1 = maxlen1 >= 5 ? P.M(q + 1) : 0ull;
                         const uint32_t nice_q = min((uint32_t)nice, maxlen);
+                        const uint32_t maxlen2 = (mode == 2 && q + 2 < n) ? min((uint32_t)kMaxMatch, n - (q + 2)) : 0u;
+                        const uint64_t e2 = maxlen2 >= 5 ? P.M(q + 2) : 0ull;
+                        const uint32_t c2 = maxlen2 >= 5 ? M2[q + 2] : 0u;
+                        // decide(): with the current match (cl, co) at q — emit it, or a literal and move on to the better
+                        // match one (lazy) or two (lazy2) positions ahead
+                        auto decide = [&](uint32_t cl, uint32_t co) -> uint32_t {
+                            if (cl >= nice_q) return cl;
+                            uint32_t nl, no;
+                            table_search(e1, cl - 1, true, maxlen1, nl, no);
+                            if (nl >= cl && 4 * (int)(nl - cl) + ((int)bsr32(co) - (int)bsr32(no)) > 2) return 0x200u | 1u;
+                            if (mode == 2) {
+                                // longest_match(q + 2, cl - 1, depth >> 2) answered from the depth/4 column
+                                nl = cl - 1; no = 0;
+                                if (maxlen2 >= 5) {
+                                    uint32_t lx = c2 & 0xFF, ox = (c2 >> 8) & 0x7FFF;
+                                    const uint32_t bl = cl - 1;
+                                    if (lx) lx += 3;
+                                    if (bl < 4) {
+                                        if ((e2 >> 46) & 1) {
+                                            const uint32_t off3 = (uint32_t)(e2 >> 47) & 0x3FFF;
+                                            if (bl < 3 && off3) { nl = 3; no = off3; }
+                                            if (lx) { nl = lx; no = ox; }
+                                        }
+                                    } else if (lx > bl) { nl = lx; no = ox; }
+                                }
+                                if (nl >= cl && 4 * (int)(nl - cl) + ((int)bsr32(co) - (int)bsr32(no)) > 6) return 0x200u | 3u;
+                            }
+                            return cl;
+                        };
                         uint32_t cl, co;
                         table_search(e0, min_len - 1, false, maxlen, cl, co);
                         if (mode == 0) {
-                            if (cl >= min_len && (cl > 3 || co <= 4096)) { lenF = cl; offF = co; wF = cl | (1u << 10); }
+                            if (cl >= min_len && (cl > 3 || co <= 4096)) { lenF = cl; offF = co; wF = cl; }
                         } else {
-                            // decide(): emit the current match, or a literal and move to H(q+1)
-                            if (!(cl < min_len || (cl == 3 && co > 8192))) {
-                                bool take = cl >= nice_q;
-                                if (!take) {
-                                    uint32_t nl, no;
-                                    table_search(e1, cl - 1, true, maxlen1, nl, no);
-                                    take = !(nl >= cl && 4 * (int)(nl - cl) + ((int)bsr32(co) - (int)bsr32(no)) > 2);
-                                }
-                                if (take) { lenF = cl; offF = co; wF = cl | (1u << 10); }
-                                else wF = 1u | (1u << 9);
-                            }
-                            // H(q): current match = depth/2 result at q (or the 3-byte match)
+                            if (!(cl < min_len || (cl == 3 && co > 8192))) { lenF = cl; offF = co; wF = decide(cl, co); }
+                            const uint32_t off3q = (uint32_t)(e0 >> 47) & 0x3FFF;
+                            // HB(q): current match = depth/2 result at q (or the 3-byte match)
                             uint32_t hl = (uint32_t)(e0 >> 23) & 0xFF, ho = (uint32_t)(e0 >> 31) & 0x7FFF;
                             if (hl) hl += 3;
-                            else { ho = (uint32_t)(e0 >> 47) & 0x3FFF; hl = ho ? 3 : 0; }
-                            if (hl && maxlen >= 5) {
-                                bool take = hl >= nice_q;
-                                if (!take) {
-                                    uint32_t nl, no;
-                                    table_search(e1, hl - 1, true, maxlen1, nl, no);
-                                    take = !(nl >= hl && 4 * (int)(nl - hl) + ((int)bsr32(ho) - (int)bsr32(no)) > 2);
-                                }
-                                if (take) { lenH = hl; offH = ho; wH = hl | (1u << 10); }
-                                else wH = 1u | (1u << 9);
+                            else { ho = off3q; hl = ho ? 3 : 0; }
+                            if (hl && maxlen >= 5) { lenHB = hl; offHB = ho; wHB = decide(hl, ho); }
+                            if (mode == 2) {
+                                // HC(q): current match = depth/4 result at q (or the 3-byte match)
+                                const uint32_t c0 = maxlen >= 5 ? M2[q] : 0u;
+                                hl = c0 & 0xFF; ho = (c0 >> 8) & 0x7FFF;
+                                if (hl) hl += 3;
+                                else { ho = off3q; hl = ho ? 3 : 0; }
+                                if (hl && maxlen >= 5) { lenHC = hl; offHC = ho; wHC = decide(hl, ho); }
                             }
                         }
                     }
                     // ---- follow the path through the window (one token per hop) ----
-                    // (every lane walks the same path: both transition words of a position travel in one shuffle)
-                    const uint32_t wlimit = min(32u, max_block_end - p), wFH = wF | (wH << 16);
-                    uint32_t vis = 0, visH = 0, c = 0, st_h = in_h;
+                    // (every lane walks the same path: the three transition words of a position travel in one shuffle)
+                    const uint32_t wlimit = min(32u, max_block_end - p), w3 = wF | (wHB << 10) | (wHC << 20);
+                    uint32_t vis = 0, sm0 = 0, sm1 = 0, c = 0, st = in_h;          // state: 0 F, 1 HB, 2 HC, 3 X
                     while (c < wlimit) {
-                        vis |= 1u << c; visH |= st_h << c;
-                        const uint32_t w2 = __shfl_sync(0xFFFFFFFFu, wFH, c);
-                        const uint32_t w = st_h ? (w2 >> 16) : w2;
-                        c += w & 0x1FF; st_h = (w >> 9) & 1;
+                        vis |= 1u << c; sm0 |= (st & 1u) << c; sm1 |= (st >> 1) << c;
+                        const uint32_t w3c = __shfl_sync(0xFFFFFFFFu, w3, c);
+                        const uint32_t w = (st == 3u) ? (0x200u | 2u) : ((w3c >> (10u * st)) & 0x3FFu);
+                        if (w & 0x200u) { c += 1; st = w & 3u; } else { c += w; st = 0; }
                     }
                     const bool onpath = (vis >> lane) & 1u;
-                    const bool asH = (visH >> lane) & 1u;
-                    const uint32_t myw = asH ? wH : wF;
+                    const uint32_t myst = ((sm0 >> lane) & 1u) | (((sm1 >> lane) & 1u) << 1);
+                    const uint32_t myw = (myst == 3u) ? (0x200u | 2u) : ((w3 >> (10u * myst)) & 0x3FFu);
+                    const bool myM = !(myw & 0x200u);                                // my token is a match
                     const uint32_t incl = __popc(vis & (lane == 31 ? 0xFFFFFFFFu : ((2u << lane) - 1)));   // tokens up to and including mine
-                    const uint32_t e_l = q + (myw & 0x1FF);
-                    const bool ends_iter = !((myw >> 9) & 1);     // next state is F: a main-loop iteration ends here
+                    const uint32_t e_l = q + (myM ? myw : 1u);
+                    const bool ends_iter = myM || (myw & 3u) == 0;    // next state is F: a main-loop iteration ends here
                     // ---- events ----
                     // (cheap uniform pre-test: most windows cannot contain any event)
-                    uint32_t commit_mask = vis, next_p = p + c, next_h = st_h;
+                    uint32_t commit_mask = vis, next_p = p + c, next_h = st;
                     int event = 0;   // 1 = recalc before lane Lr, 2 = block check after lane Lc, 3 = sequence store full after lane Ls
-                    uint32_t mmask = __ballot_sync(0xFFFFFFFFu, onpath && ((myw >> 10) & 1));
+                    uint32_t mmask = __ballot_sync(0xFFFFFFFFu, onpath && myM);
                     const bool may_check = !fast && (num_new_obs + 32 >= (uint32_t)kObsPerCheck) && (p + 32 + 258 - bb >= (uint32_t)kMinBlockLength) && (n - p > (uint32_t)kMinBlockLength);
                     const bool may_recalc = (mode != 0) && (p + 32 > next_recalc);
                     const bool may_seq = nmatch + 32 >= seq_limit;
                     if (may_check || may_recalc || may_seq) {
-                        uint32_t rmask = may_recalc ? __ballot_sync(0xFFFFFFFFu, onpath && !asH && q >= next_recalc) : 0u;
+                        uint32_t rmask = may_recalc ? __ballot_sync(0xFFFFFFFFu, onpath && myst == 0 && q >= next_recalc) : 0u;
                         uint32_t cmask = __ballot_sync(0xFFFFFFFFu, !fast && onpath && ends_iter && (num_new_obs + incl >= (uint32_t)kObsPerCheck) &&
                                                                          (e_l - bb >= (uint32_t)kMinBlockLength) && (n - e_l >= (uint32_t)kMinBlockLength));
                         // sequence store full (SEQ_STORE_LENGTH matches in this DEFLATE block): the block ends
@@ -1128,8 +1050,8 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
                     // ---- commit ----
                     if ((commit_mask >> lane) & 1u) {
                         const uint32_t ti = ntok + incl - 1;
-                        const bool isM = (myw >> 10) & 1;
-                        const uint32_t mlen = asH ? lenH : lenF, moff = asH ? offH : offF;
+                        const bool isM = myM;
+                        const uint32_t mlen = myst == 0 ? lenF : myst == 1 ? lenHB : lenHC, moff = myst == 0 ? offF : myst == 1 ? offHB : offHC;
                         const uint32_t lit = isM ? 0u : P.B(q);
                         const uint32_t lsym = isM ? kFirstLenSym + len_slot_only(mlen) : lit;
                         const uint32_t ocls = isM ? 8 + (mlen >= 9) : (((lit >> 5) & 6) | (lit & 1));
