@@ -828,6 +828,7 @@ __device__ __forceinline__ uint32_t fold_unit_sum(const Geo &g, uint32_t u, cons
     return __shfl_sync(0xFFFFFFFFu, s, 0);
 }
 
+template <bool kLazy2>     // levels 8-9: the parser looks two positions ahead (states HC / X below); compiled out otherwise
 __global__ void __launch_bounds__(kEmitThreads)
 k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
        const uint64_t *__restrict__ mtab, const uint32_t *__restrict__ mtab2, uint32_t *__restrict__ crc_io, const uint32_t *__restrict__ sum_part, int check_kind,
@@ -939,10 +940,10 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
                 next_recalc = bb + min(n - bb, 10000u);
                 uint32_t ntok = 0, nmatch = 0, num_obs = 0, num_new_obs = 0, in_h = 0;
                 bool end_block = false;
-                const uint32_t *M2 = (mode == 2) ? mtab2 + (size_t)u * g.m_stride : nullptr;   // lazy2: depth/4 column
+                const uint32_t *M2 = kLazy2 ? mtab2 + (size_t)u * g.m_stride : nullptr;   // lazy2: depth/4 column
                 do {
                     P.advance(p);
-                    P.need(min(n - 1, p + 33 + (mode == 2 ? 1u : 0u)));
+                    P.need(min(n - 1, p + 33 + (kLazy2 ? 1u : 0u)));
                     // ---- per-lane transitions at q = p + lane ----
                     // F(q)  : parser in its fresh state at q (top of the reference's main loop).
                     // HB(q) : parser at `have_cur_match` at q, the current match being the depth/2 search result at q
@@ -950,26 +951,27 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
                     // HC(q) : the same with the depth/4 result at q (lazy2: reached through the look-ahead two positions on).
                     // X(q)  : lazy2, second of the two literals in front of an HC match: literal at q, then HC(q + 1).
                     // A transition emits ONE token and names the next state:
-                    //   word = match length (bits 0-8, bit 9 clear: next state F) | 0x200 + next state (a literal)
+                    //   word = advance (bits 0-8) | next state (bits 9-10: 0 F, 1 HB, 2 HC, 3 X) | token-is-match (bit 11)
+                    constexpr uint32_t kToHB = 1u | (1u << 9), kToHC = 1u | (2u << 9), kToX = 1u | (3u << 9), kIsM = 1u << 11;
                     const uint32_t q = p + lane;
-                    uint32_t wF = 0x200, wHB = 0x200, wHC = 0x200, lenF = 0, offF = 0, lenHB = 0, offHB = 0, lenHC = 0, offHC = 0;
+                    uint32_t wF = 1, wHB = 1, wHC = 1, lenF = 0, offF = 0, lenHB = 0, offHB = 0, lenHC = 0, offHC = 0;
                     if (q < max_block_end) {
                         const uint64_t e0 = P.M(q);
                         const uint32_t maxlen = min((uint32_t)kMaxMatch, n - q);
                         const uint32_t maxlen1 = (q + 1 < n) ? min((uint32_t)kMaxMatch, n - (q + 1)) : 0u;
                         const uint64_t e1 = maxlen1 >= 5 ? P.M(q + 1) : 0ull;
                         const uint32_t nice_q = min((uint32_t)nice, maxlen);
-                        const uint32_t maxlen2 = (mode == 2 && q + 2 < n) ? min((uint32_t)kMaxMatch, n - (q + 2)) : 0u;
-                        const uint64_t e2 = maxlen2 >= 5 ? P.M(q + 2) : 0ull;
-                        const uint32_t c2 = maxlen2 >= 5 ? M2[q + 2] : 0u;
+                        const uint32_t maxlen2 = (kLazy2 && q + 2 < n) ? min((uint32_t)kMaxMatch, n - (q + 2)) : 0u;
+                        const uint64_t e2 = (kLazy2 && maxlen2 >= 5) ? P.M(q + 2) : 0ull;
+                        const uint32_t c2 = (kLazy2 && maxlen2 >= 5) ? M2[q + 2] : 0u;
                         // decide(): with the current match (cl, co) at q — emit it, or a literal and move on to the better
                         // match one (lazy) or two (lazy2) positions ahead
                         auto decide = [&](uint32_t cl, uint32_t co) -> uint32_t {
-                            if (cl >= nice_q) return cl;
+                            if (cl >= nice_q) return cl | kIsM;
                             uint32_t nl, no;
                             table_search(e1, cl - 1, true, maxlen1, nl, no);
-                            if (nl >= cl && 4 * (int)(nl - cl) + ((int)bsr32(co) - (int)bsr32(no)) > 2) return 0x200u | 1u;
-                            if (mode == 2) {
+                            if (nl >= cl && 4 * (int)(nl - cl) + ((int)bsr32(co) - (int)bsr32(no)) > 2) return kToHB;
+                            if (kLazy2) {
                                 // longest_match(q + 2, cl - 1, depth >> 2) answered from the depth/4 column
                                 nl = cl - 1; no = 0;
                                 if (maxlen2 >= 5) {
@@ -984,14 +986,14 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
                                         }
                                     } else if (lx > bl) { nl = lx; no = ox; }
                                 }
-                                if (nl >= cl && 4 * (int)(nl - cl) + ((int)bsr32(co) - (int)bsr32(no)) > 6) return 0x200u | 3u;
+                                if (nl >= cl && 4 * (int)(nl - cl) + ((int)bsr32(co) - (int)bsr32(no)) > 6) return kToX;
                             }
-                            return cl;
+                            return cl | kIsM;
                         };
                         uint32_t cl, co;
                         table_search(e0, min_len - 1, false, maxlen, cl, co);
                         if (mode == 0) {
-                            if (cl >= min_len && (cl > 3 || co <= 4096)) { lenF = cl; offF = co; wF = cl; }
+                            if (cl >= min_len && (cl > 3 || co <= 4096)) { lenF = cl; offF = co; wF = cl | kIsM; }
                         } else {
                             if (!(cl < min_len || (cl == 3 && co > 8192))) { lenF = cl; offF = co; wF = decide(cl, co); }
                             const uint32_t off3q = (uint32_t)(e0 >> 47) & 0x3FFF;
@@ -1000,7 +1002,7 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
                             if (hl) hl += 3;
                             else { ho = off3q; hl = ho ? 3 : 0; }
                             if (hl && maxlen >= 5) { lenHB = hl; offHB = ho; wHB = decide(hl, ho); }
-                            if (mode == 2) {
+                            if (kLazy2) {
                                 // HC(q): current match = depth/4 result at q (or the 3-byte match)
                                 const uint32_t c0 = maxlen >= 5 ? M2[q] : 0u;
                                 hl = c0 & 0xFF; ho = (c0 >> 8) & 0x7FFF;
@@ -1011,22 +1013,27 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
                         }
                     }
                     // ---- follow the path through the window (one token per hop) ----
-                    // (every lane walks the same path: the three transition words of a position travel in one shuffle)
-                    const uint32_t wlimit = min(32u, max_block_end - p), w3 = wF | (wHB << 10) | (wHC << 20);
-                    uint32_t vis = 0, sm0 = 0, sm1 = 0, c = 0, st = in_h;          // state: 0 F, 1 HB, 2 HC, 3 X
+                    // (every lane walks the same path: the F and HB words of a position travel in one shuffle)
+                    const uint32_t wlimit = min(32u, max_block_end - p), w2 = wF | (wHB << 12);
+                    uint32_t vis = 0, sm0 = 0, sm1 = 0, c = 0, st = in_h;
                     while (c < wlimit) {
-                        vis |= 1u << c; sm0 |= (st & 1u) << c; sm1 |= (st >> 1) << c;
-                        const uint32_t w3c = __shfl_sync(0xFFFFFFFFu, w3, c);
-                        const uint32_t w = (st == 3u) ? (0x200u | 2u) : ((w3c >> (10u * st)) & 0x3FFu);
-                        if (w & 0x200u) { c += 1; st = w & 3u; } else { c += w; st = 0; }
+                        vis |= 1u << c; sm0 |= (kLazy2 ? (st & 1u) : st) << c;
+                        const uint32_t a = __shfl_sync(0xFFFFFFFFu, w2, c);
+                        uint32_t w = (st & 1u) ? (a >> 12) : a;
+                        if (kLazy2) {
+                            sm1 |= (st >> 1) << c;
+                            const uint32_t b = __shfl_sync(0xFFFFFFFFu, wHC, c);
+                            if (st == 2u) w = b; else if (st == 3u) w = kToHC;
+                        }
+                        c += w & 0x1FF; st = (w >> 9) & 3u;
                     }
                     const bool onpath = (vis >> lane) & 1u;
-                    const uint32_t myst = ((sm0 >> lane) & 1u) | (((sm1 >> lane) & 1u) << 1);
-                    const uint32_t myw = (myst == 3u) ? (0x200u | 2u) : ((w3 >> (10u * myst)) & 0x3FFu);
-                    const bool myM = !(myw & 0x200u);                                // my token is a match
+                    const uint32_t myst = ((sm0 >> lane) & 1u) | (kLazy2 ? (((sm1 >> lane) & 1u) << 1) : 0u);
+                    const uint32_t myw = kLazy2 ? (myst == 0 ? wF : myst == 1 ? wHB : myst == 2 ? wHC : kToHC) : (myst ? wHB : wF);
+                    const bool myM = (myw & kIsM) != 0;                             // my token is a match
                     const uint32_t incl = __popc(vis & (lane == 31 ? 0xFFFFFFFFu : ((2u << lane) - 1)));   // tokens up to and including mine
-                    const uint32_t e_l = q + (myM ? myw : 1u);
-                    const bool ends_iter = myM || (myw & 3u) == 0;    // next state is F: a main-loop iteration ends here
+                    const uint32_t e_l = q + (myw & 0x1FF);
+                    const bool ends_iter = ((myw >> 9) & 3u) == 0;     // next state is F: a main-loop iteration ends here
                     // ---- events ----
                     // (cheap uniform pre-test: most windows cannot contain any event)
                     uint32_t commit_mask = vis, next_p = p + c, next_h = st;
@@ -1051,7 +1058,8 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
                     if ((commit_mask >> lane) & 1u) {
                         const uint32_t ti = ntok + incl - 1;
                         const bool isM = myM;
-                        const uint32_t mlen = myst == 0 ? lenF : myst == 1 ? lenHB : lenHC, moff = myst == 0 ? offF : myst == 1 ? offHB : offHC;
+                        const uint32_t mlen = kLazy2 ? (myst == 0 ? lenF : myst == 1 ? lenHB : lenHC) : (myst ? lenHB : lenF);
+                        const uint32_t moff = kLazy2 ? (myst == 0 ? offF : myst == 1 ? offHB : offHC) : (myst ? offHB : offF);
                         const uint32_t lit = isM ? 0u : P.B(q);
                         const uint32_t lsym = isM ? kFirstLenSym + len_slot_only(mlen) : lit;
                         const uint32_t ocls = isM ? 8 + (mlen >= 9) : (((lit >> 5) & 6) | (lit & 1));
@@ -1601,8 +1609,12 @@ cudaError_t launch_deflate_pipeline(const DeflateBatch &b, cudaStream_t st)
         if (b.timer) b.timer->stop(st);
     }
     if (b.timer) b.timer->start(KT_EMIT, st);
-    GZPB_LAUNCH(k_emit, b.nunits, kEmitThreads, 0, st, g, b.unit_flags, b.mtab, b.mtab2, b.crc, fold_check ? b.sum_part : (const uint32_t *)nullptr, b.check_kind,
-                b.tokens, b.out, b.out_len, b.status, lp.mode, lp.depth, lp.nice, b.level, b.format);
+    if (lp.mode == 2)
+        GZPB_LAUNCH(k_emit<true>, b.nunits, kEmitThreads, 0, st, g, b.unit_flags, b.mtab, b.mtab2, b.crc, fold_check ? b.sum_part : (const uint32_t *)nullptr, b.check_kind,
+                    b.tokens, b.out, b.out_len, b.status, lp.mode, lp.depth, lp.nice, b.level, b.format);
+    else
+        GZPB_LAUNCH(k_emit<false>, b.nunits, kEmitThreads, 0, st, g, b.unit_flags, b.mtab, b.mtab2, b.crc, fold_check ? b.sum_part : (const uint32_t *)nullptr, b.check_kind,
+                    b.tokens, b.out, b.out_len, b.status, lp.mode, lp.depth, lp.nice, b.level, b.format);
     DBG_SYNC("k_emit");
     if (b.timer) b.timer->stop(st);
     return cudaGetLastError();
