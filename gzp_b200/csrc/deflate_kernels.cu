@@ -123,10 +123,18 @@ __device__ __forceinline__ uint32_t ldg32u(const uint32_t *__restrict__ words, u
 // 192 KiB of bucket tables in shared memory, kept two latency-bound warps per SM busy: 6.7 ms vs 4.7 ms per batch.)
 // =============================================================================
 constexpr int kSplitThreads = 1024;
-constexpr int kL4 = 16, kL3 = 4;         // lists: hash4 space in 16ths, hash3 space in quarters
+#ifndef GZPB_LISTS
+#define GZPB_LISTS 0
+#endif
+#if GZPB_LISTS == 0
+constexpr int kBits4 = 12, kBits3 = 13;  // buckets per link job: hash4 8 KiB table + 4 KiB counts, hash3 16 KiB table (14 jobs per SM)
+#else
+constexpr int kBits4 = 11, kBits3 = 12;  // buckets per link job: hash4 4 KiB table + 2 KiB counts, hash3 8 KiB table (28 jobs per SM)
+#endif
+constexpr int kQ4Bits = 16 - kBits4, kQ3Bits = 15 - kBits3;
+constexpr int kL4 = 1 << kQ4Bits, kL3 = 1 << kQ3Bits;   // lists: equal ranges of the hash4 / hash3 bucket space
 constexpr int kSplitLists = kL4 + kL3;
-constexpr int kBits4 = 12, kBits3 = 13;  // buckets per link job: hash4 8 KiB table + 4 KiB counts, hash3 16 KiB table
-constexpr int kLsStride = 32;            // list_start entries per sub-unit: [0..kL4] hash4 bounds, [kL4+1..kL4+1+kL3] hash3 bounds
+constexpr int kLsStride = 64;            // list_start entries per sub-unit: [0..kL4] hash4 bounds, [kL4+1..kL4+1+kL3] hash3 bounds
 
 // Lanes of the warp whose (active) list id equals this lane's: the id has only BITS bits, so BITS ballots do what a
 // MATCH.ANY does at a fraction of its latency (k_split ranks every position twice per pass).
@@ -175,7 +183,7 @@ k_split(const __grid_constant__ Geo g, uint32_t *__restrict__ lists, uint32_t *_
     uint32_t *arr4 = lists + (size_t)blockIdx.x * 2 * kMaxUnitBytes;
     uint32_t *arr3 = arr4 + kMaxUnitBytes;
 
-    if (lane < kSplitLists) s_w[warp][lane] = 0;
+    for (uint32_t i = lane; i < (uint32_t)kSplitLists; i += 32) s_w[warp][i] = 0;
     __syncwarp();
     // pass 1: every warp counts the list members of its contiguous range of tiles
     for (uint32_t t = t0; t < t1; t++) {
@@ -185,7 +193,7 @@ k_split(const __grid_constant__ Geo g, uint32_t *__restrict__ lists, uint32_t *_
         uint32_t h4 = ht ? (lz_hash(v, 15) << 1) : lz_hash(v, 16), h3 = lz_hash(v & 0xFFFFFFu, 15);   // level 1: 15-bit buckets (even slots)
         if (p == 0 && quirk0) { h4 = 0; h3 = 0; }
         const uint32_t q4 = h4 >> kBits4, q3 = h3 >> kBits3;
-        const uint32_t m4 = same_list_mask<4>(q4, act), m3 = same_list_mask<2>(q3, act);
+        const uint32_t m4 = same_list_mask<kQ4Bits>(q4, act), m3 = same_list_mask<kQ3Bits>(q3, act);
         if (act && (m4 & lt) == 0) s_w[warp][q4] += __popc(m4);          // group leader
         if (act && (m3 & lt) == 0) s_w[warp][kL4 + q3] += __popc(m3);
         __syncwarp();
@@ -216,7 +224,7 @@ k_split(const __grid_constant__ Geo g, uint32_t *__restrict__ lists, uint32_t *_
         uint32_t h4 = ht ? (lz_hash(v, 15) << 1) : lz_hash(v, 16), h3 = lz_hash(v & 0xFFFFFFu, 15);   // level 1: 15-bit buckets (even slots)
         if (p == 0 && quirk0) { h4 = 0; h3 = 0; }
         const uint32_t q4 = h4 >> kBits4, q3 = h3 >> kBits3;
-        const uint32_t m4 = same_list_mask<4>(q4, act), m3 = same_list_mask<2>(q3, act);
+        const uint32_t m4 = same_list_mask<kQ4Bits>(q4, act), m3 = same_list_mask<kQ3Bits>(q3, act);
         uint32_t b4 = 0, b3 = 0;
         if (act) { b4 = s_w[warp][q4]; b3 = s_w[warp][kL4 + q3]; }
         __syncwarp();

@@ -230,7 +230,7 @@ static int lane_alloc(gzpb_ctx *c, Lane &L, bool with_io)
     CK(dmalloc(&L.d_prev3, U * (size_t)c->m_stride + 64));
     CK(dmalloc(&L.d_order, U * c->spu * kMaxUnitBytes));
     CK(dmalloc(&L.d_lists, U * c->spu * 2 * kMaxUnitBytes));
-    CK(dmalloc(&L.d_list_start, U * c->spu * 32));
+    CK(dmalloc(&L.d_list_start, U * c->spu * 64));       // kLsStride
     CK(dmalloc(&L.d_clen, U * (size_t)c->m_stride + 64));
     CK(dmalloc(&L.d_mtab, U * c->m_stride));
     if (c->level >= 8) CK(dmalloc(&L.d_mtab2, U * c->m_stride));
