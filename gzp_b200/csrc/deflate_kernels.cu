@@ -401,13 +401,19 @@ k_link(const __grid_constant__ Geo g, const uint32_t *__restrict__ lists, const 
 // depend on parsing decisions, so all positions are searched in parallel.
 // =============================================================================
 constexpr int kMatchThreads = 1024;
+// Extend a match of `len` bytes between positions p and q, 4 bytes per step: both sides step through aligned words
+// with their own fixed shift, so a step costs two shared-memory loads (not four) and no address arithmetic.
 __device__ __forceinline__ uint32_t lz_extend(const uint32_t *s_in, uint32_t p, uint32_t q, uint32_t len, uint32_t maxlen)
 {
     const uint8_t *b = (const uint8_t *)s_in;
+    uint32_t wp = (p + len) >> 2, wq = (q + len) >> 2;
+    const uint32_t shp = ((p + len) & 3) * 8, shq = ((q + len) & 3) * 8;
+    uint32_t lo_p = s_in[wp], lo_q = s_in[wq];
     while (len + 4 <= maxlen) {
-        uint32_t x = ld32u(s_in, p + len) ^ ld32u(s_in, q + len);
+        const uint32_t hi_p = s_in[++wp], hi_q = s_in[++wq];
+        const uint32_t x = __funnelshift_r(lo_p, hi_p, shp) ^ __funnelshift_r(lo_q, hi_q, shq);
         if (x) return len + ((__ffs(x) - 1) >> 3);
-        len += 4;
+        len += 4; lo_p = hi_p; lo_q = hi_q;
     }
     while (len < maxlen && b[p + len] == b[q + len]) len++;
     return len;
@@ -494,8 +500,11 @@ k_match(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, cons
         const uint32_t maxlen = min((uint32_t)kMaxMatch, n - p);
         if (maxlen < 5) { M[p] = 0; if (M2) M2[p] = 0; continue; }
         const uint32_t nicep = min((uint32_t)nice, maxlen);
-        const uint32_t seq4 = ld32u(s_in, p);
-        const uint32_t w1 = ld32u(s_in, p + 4), w2 = ld32u(s_in, p + 8);   // bytes 4..11 of this position, for the inline extension
+        // bytes 0..3 (the quick reject) and 4..11 (the inline extension) of this position: four words, three funnel shifts
+        const uint32_t pw = p >> 2, psh = (p & 3) * 8;
+        const uint32_t pa1 = s_in[pw + 1], pa2 = s_in[pw + 2];
+        const uint32_t seq4 = __funnelshift_r(s_in[pw], pa1, psh);
+        const uint32_t w1 = __funnelshift_r(pa1, pa2, psh), w2 = __funnelshift_r(pa2, s_in[pw + 3], psh);
         // level 1 (ht_matchfinder) has no hash3 table: the parser must see "bucket usable, no 3-byte match"
         uint32_t d3 = ht ? 1u : p3[p];
         uint32_t off3 = 0;
@@ -515,16 +524,19 @@ k_match(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, cons
             if (p - q >= (uint32_t)kWindow) break;
             visited++;
             d = s_next[q];                     // the next link leaves now: its latency hides behind this node's compares
-            bool cand;
-            if (best == 3) cand = (ld32u(s_in, q) == seq4);
-            else cand = (b[q + best] == pbest) && (ld32u(s_in, q) == seq4);
+            // the bytes at q, q + 4, q + 8 share their word offset and their shift: every word is loaded once
+            const uint32_t wq = q >> 2, sh = (q & 3) * 8;
+            uint32_t a1 = 0;
+            bool cand = (best == 3) || (b[q + best] == pbest);
+            if (cand) { a1 = s_in[wq + 1]; cand = __funnelshift_r(s_in[wq], a1, sh) == seq4; }
             if (cand) {
                 // most matches are short: first 8 bytes of the extension inline, the rest in lz_extend
                 uint32_t len;
-                uint32_t x = ld32u(s_in, q + 4) ^ w1;
+                const uint32_t a2 = s_in[wq + 2];
+                uint32_t x = __funnelshift_r(a1, a2, sh) ^ w1;
                 if (x) len = 4 + ((__ffs(x) - 1) >> 3);
                 else {
-                    x = ld32u(s_in, q + 8) ^ w2;
+                    x = __funnelshift_r(a2, s_in[wq + 3], sh) ^ w2;
                     if (x) len = 8 + ((__ffs(x) - 1) >> 3);
                     else len = (maxlen > 12) ? lz_extend(s_in, p, q, 12, maxlen) : 12;
                 }
