@@ -409,11 +409,18 @@ __device__ __forceinline__ uint32_t lz_extend(const uint32_t *s_in, uint32_t p, 
     uint32_t wp = (p + len) >> 2, wq = (q + len) >> 2;
     const uint32_t shp = ((p + len) & 3) * 8, shq = ((q + len) & 3) * 8;
     uint32_t lo_p = s_in[wp], lo_q = s_in[wq];
-    while (len + 4 <= maxlen) {
-        const uint32_t hi_p = s_in[++wp], hi_q = s_in[++wq];
+    while (len + 8 <= maxlen) {                                    // 8 bytes per trip: one exit test for two words
+        const uint32_t m_p = s_in[wp + 1], m_q = s_in[wq + 1], hi_p = s_in[wp + 2], hi_q = s_in[wq + 2];
+        const uint32_t x0 = __funnelshift_r(lo_p, m_p, shp) ^ __funnelshift_r(lo_q, m_q, shq);
+        const uint32_t x1 = __funnelshift_r(m_p, hi_p, shp) ^ __funnelshift_r(m_q, hi_q, shq);
+        if (x0 | x1) return x0 ? len + ((__ffs(x0) - 1) >> 3) : len + 4 + ((__ffs(x1) - 1) >> 3);
+        len += 8; wp += 2; wq += 2; lo_p = hi_p; lo_q = hi_q;
+    }
+    if (len + 4 <= maxlen) {
+        const uint32_t hi_p = s_in[wp + 1], hi_q = s_in[wq + 1];
         const uint32_t x = __funnelshift_r(lo_p, hi_p, shp) ^ __funnelshift_r(lo_q, hi_q, shq);
         if (x) return len + ((__ffs(x) - 1) >> 3);
-        len += 4; lo_p = hi_p; lo_q = hi_q;
+        len += 4;
     }
     while (len < maxlen && b[p + len] == b[q + len]) len++;
     return len;
