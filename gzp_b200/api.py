@@ -233,9 +233,9 @@ class Context:
 
 
 class ParCompressBuilder:
-    """ParCompressBuilder<F> (par/compress.rs:33-138).  `num_threads` is kept for
-    API parity (it sizes nothing on the GPU); `blocks_in_flight` is the device
-    analogue of the 2*num_threads channel bound."""
+    """ParCompressBuilder<F> (par/compress.rs:33-138).  `num_threads` sizes nothing on the GPU; with the native
+    writer (`devices(...)`) it is the number of threads that make the one host copy of `write`
+    (gzpb_writer_set_copy_threads).  `blocks_in_flight` is the device analogue of the 2*num_threads channel bound."""
 
     def __init__(self, fmt=Gzip):
         self.format = fmt() if isinstance(fmt, type) else fmt
@@ -289,7 +289,8 @@ class ParCompressBuilder:
 
     def from_writer(self, writer):
         if self._devices is not None:
-            return NativeParCompress(self.format, writer, self._level, self._buffer_size, self._devices, self._blocks_in_flight)
+            return NativeParCompress(self.format, writer, self._level, self._buffer_size, self._devices, self._blocks_in_flight,
+                                     copy_threads=max(1, self._num_threads))
         return ParCompress(self.format, writer, self._level, self._buffer_size, self._device, self._blocks_in_flight)
 
     from_borrowed_writer = from_writer
@@ -410,7 +411,7 @@ class NativeParCompress:
     the batches in flight on one or several GPUs and the ordered hand-over to `writer.write` all live in
     libgzpb.so; Python only forwards `write` / `flush` / `finish` (par/compress.rs:377-388, 413-468)."""
 
-    def __init__(self, fmt, writer, level, buffer_size, devices=(0,), blocks_in_flight=0):
+    def __init__(self, fmt, writer, level, buffer_size, devices=(0,), blocks_in_flight=0, copy_threads=1):
         self._lib = _lib.load()
         self.format = fmt
         self.writer = writer
@@ -436,6 +437,8 @@ class NativeParCompress:
         if rc != 0:
             raise GzpError(rc)
         self._h = h
+        if copy_threads > 1:
+            self._lib.gzpb_writer_set_copy_threads(h, int(copy_threads))
 
     def _check(self, rc):
         if rc != 0:

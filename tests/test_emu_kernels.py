@@ -688,3 +688,17 @@ def test_emu_long_units_carried_heads_window_edges():
     mixed = (synth.low_entropy(150000) + TEXT[:70000] + bytes(40000) + synth.fastq(140000))[:400000]
     assert gzip.decompress(_run(oracle.MGZIP, 5, 400000, mixed)) == mixed
     assert gzip.decompress(_run(oracle.GZIP, 6, 200000, mixed + mixed[:150000])) == mixed + mixed[:150000]
+
+
+def test_emu_native_writer_copy_threads(emu_backend):
+    """ParCompressBuilder.num_threads(n) with the native writer = n threads making the one host copy of `write`
+    (gzpb_writer_set_copy_threads): writes of 8 MiB and more are cut into 2 MiB pieces copied side by side; same stream.
+    (Level 0 keeps the emulated kernels cheap; the slab of 160 blocks holds 10 MB, so the first write is copied by the pool.)"""
+    import gzp_b200
+    data = (TEXT * 40)[:10_300_000]
+    sink = io.BytesIO()
+    w = gzp_b200.ParCompressBuilder(gzp_b200.Bgzf).compression_level(0).num_threads(4).blocks_in_flight(160).devices([0]).from_writer(sink)
+    w.write(data[:9_500_000])
+    w.write(data[9_500_000:])
+    w.finish()
+    assert sink.getvalue() == oracle.compress_stream(oracle.BGZF, 0, 65280, [data[:9_500_000], data[9_500_000:]])
