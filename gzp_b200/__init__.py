@@ -9,4 +9,4 @@ src/par/compress.rs:33-233) so that tests read like the reference's own.
 from ._lib import BGZF, GZIP, MGZIP, RAWDEFLATE, SNAP, ZLIB, load  # noqa: F401
 from .api import (BGZF_EOF, BgzfSyncWriter, MgzipSyncWriter, SyncZ, SyncZBuilder, BUFSIZE, DICT_SIZE, Bgzf, Compression, Context, Decoder, Gzip, GzpError, Mgzip,  # noqa: F401
                   NativeParCompress, NativeParDecompress, ParCompress, ParCompressBuilder, ParDecompress, ParDecompressBuilder, bgzf_index, bgzf_virtual_offset, compress_file, RawDeflate, Snap, ZBuilder, Zlib, adler32_combine, crc32_combine,
-                  encode_capacity, footer, header)
+                  encode_capacity, encode_stream_multi, footer, header)

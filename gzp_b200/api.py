@@ -232,6 +232,26 @@ class Context:
         return self._lib.gzpb_launch_count(self._h)
 
 
+def encode_stream_multi(contexts, data, buffer_size=0):
+    """ParCompress over an in-memory input as ONE ordered stream dealt over several GPUs (gzpb_encode_stream_multi):
+    `contexts` = one Context per GPU, created with the same format, level and sizes.  Byte-identical to
+    `contexts[0].encode_stream(data)`."""
+    lib = _lib.load()
+    data = bytes(data)
+    n, c0 = len(data), contexts[0]
+    bs = buffer_size or lib.gzpb_default_bufsize(c0.fmt)
+    nblocks = max(1, (n + bs - 1) // bs)
+    cap = 64 + nblocks * lib.gzpb_encode_capacity(c0.fmt, bs)
+    out = C.create_string_buffer(cap)
+    olen = C.c_size_t(0)
+    src = C.create_string_buffer(data, n) if n else C.create_string_buffer(1)
+    hs = (C.c_void_p * len(contexts))(*[c._h for c in contexts])
+    rc = lib.gzpb_encode_stream_multi(hs, len(contexts), src, n, buffer_size, out, cap, C.byref(olen))
+    if rc != 0:
+        raise GzpError(rc)
+    return out.raw[:olen.value]
+
+
 class ParCompressBuilder:
     """ParCompressBuilder<F> (par/compress.rs:33-138).  `num_threads` sizes nothing on the GPU; with the native
     writer (`devices(...)`) it is the number of threads that make the one host copy of `write`

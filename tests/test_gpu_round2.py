@@ -280,3 +280,14 @@ def test_probe_this_box_for_the_real_libraries():
     print(r.stdout)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "identical" in r.stdout or "parity unpinned" in r.stdout
+
+
+def test_python_encode_stream_multi_wrapper():
+    """gzp_b200.encode_stream_multi (the Python face of gzpb_encode_stream_multi) over every GPU of the box."""
+    n = min(_ndev(), 8)
+    data = synth.corpus_stream(3_000_000, 555)
+    ctxs = [gzp_b200.Context(BGZF, 6, device=d, max_block_bytes=65280, max_blocks_in_flight=8) for d in range(n)]
+    got = gzp_b200.encode_stream_multi(ctxs, data)
+    assert got == ctxs[0].encode_stream(data) == oracle.compress_stream(BGZF, 6, 65280, [data])
+    for c in ctxs:
+        c.close()
