@@ -13,9 +13,12 @@
  *
  * PARITY UNPINNED against real libdeflate bytes: the reference's own tests only
  * pin round trips, so this oracle is anchored on (i) stock
- * decoders (zlib / gzip) and (ii) the container golden vectors in the
- * reference (BGZF_EOF, header recipes).  The CUDA path is held bit-exact to
- * THIS file.
+ * decoders (zlib / gzip), (ii) the container golden vectors in the
+ * reference (BGZF_EOF, header recipes) and (iii) the libdeflate outputs that
+ * follow exactly from its documented rules (empty input, pass-through of
+ * inputs <= 55 - 4*level bytes, level 0: tests/golden/libdeflate_exact_vectors.json).
+ * DESIGN.md §2 lists what is pinned and what is not.  The CUDA path is held
+ * bit-exact to THIS file.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
  * --impl reference legs may load this code.
