@@ -607,7 +607,7 @@ def test_emu_memcheck_under_address_sanitizer():
     if not asan or not os.path.isabs(asan) or not os.path.exists(asan):
         pytest.skip("no libasan on this machine")
     env = dict(os.environ, GZPB_EMU_ASAN="1", LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0:detect_stack_use_after_return=0")
-    sel = "bgzf_edges or emu_snap or block_size_exceeded or c_writer_two_devices"
+    sel = "bgzf_edges or emu_snap or block_size_exceeded or c_writer_two_devices or copy_threads or reader_object or mgzip_long"
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-k", sel, "-p", "no:cacheprovider"],
                        env=env, capture_output=True, text=True, timeout=1500, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert "AddressSanitizer" not in r.stdout + r.stderr, (r.stdout + r.stderr)[-4000:]
@@ -624,7 +624,7 @@ def test_emu_results_do_not_depend_on_the_fiber_schedule(sched):
     import subprocess
     import sys
     env = dict(os.environ, GZPB_EMU_SCHED=sched)
-    sel = "bgzf_levels and (6 or 1) or emu_snap or inflate_roundtrip"
+    sel = "bgzf_levels and (6 or 1 or 9) or emu_snap or inflate_roundtrip or mgzip_long"
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-k", sel, "-p", "no:cacheprovider"],
                        env=env, capture_output=True, text=True, timeout=1500, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert r.returncode == 0, (r.stdout + r.stderr)[-4000:]
