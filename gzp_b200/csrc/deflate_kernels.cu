@@ -131,6 +131,15 @@ constexpr int kBits4 = 12, kBits3 = 13;  // buckets per link job: hash4 8 KiB ta
 #else
 constexpr int kBits4 = 11, kBits3 = 12;  // buckets per link job: hash4 4 KiB table + 2 KiB counts, hash3 8 KiB table (28 jobs per SM)
 #endif
+#ifndef GZPB_LINK_MATCHANY
+#define GZPB_LINK_MATCHANY 0
+#endif
+#ifndef GZPB_MATCH_PIPE
+#define GZPB_MATCH_PIPE 1
+#endif
+#ifndef GZPB_PLAIN_BALLOT
+#define GZPB_PLAIN_BALLOT 0
+#endif
 constexpr int kQ4Bits = 16 - kBits4, kQ3Bits = 15 - kBits3;
 constexpr int kL4 = 1 << kQ4Bits, kL3 = 1 << kQ3Bits;   // lists: equal ranges of the hash4 / hash3 bucket space
 constexpr int kSplitLists = kL4 + kL3;
@@ -142,11 +151,24 @@ template <int BITS>
 __device__ __forceinline__ uint32_t same_list_mask(uint32_t id, bool act)
 {
     uint32_t m = __ballot_sync(0xFFFFFFFFu, act);
+#if !defined(GZPB_EMU) && !GZPB_PLAIN_BALLOT
+    // four instructions per bit (bit test with predicate, VOTE, two predicated LOP3); the C++ form below compiles to seven
+#pragma unroll
+    for (int b = 0; b < BITS; b++)
+        asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 t, v;\n\t"
+                     "and.b32 t, %1, %2;\n\t"
+                     "setp.ne.u32 p, t, 0;\n\t"
+                     "vote.sync.ballot.b32 v, p, 0xffffffff;\n\t"
+                     "@p lop3.b32 %0, %0, v, 0, 0xC0;\n\t"      // m & v
+                     "@!p lop3.b32 %0, %0, v, 0, 0x30;\n\t"     // m & ~v
+                     "}" : "+r"(m) : "r"(id), "r"(1u << b));
+#else
 #pragma unroll
     for (int b = 0; b < BITS; b++) {
         const uint32_t v = __ballot_sync(0xFFFFFFFFu, (id >> b) & 1u);
         m &= ((id >> b) & 1u) ? v : ~v;
     }
+#endif
     return m;
 }
 
@@ -291,7 +313,15 @@ k_split(const __grid_constant__ Geo g, uint32_t *__restrict__ lists, uint32_t *_
     }
 }
 
-template <bool kMulti>     // kMulti: units of several sub-units (the loop over them and the head sweep exist only there)
+#ifndef GZPB_LINK_SPLIT
+#define GZPB_LINK_SPLIT 0
+#endif
+#ifndef GZPB_LINK_PIPE
+#define GZPB_LINK_PIPE 0
+#endif
+// kMulti: units of several sub-units (the loop over them and the head sweep exist only there)
+// kWhich: 0 = one launch for all lists; 1 = the hash4 lists only (12 KiB table: 17 jobs per SM instead of 13), 2 = the hash3 lists only
+template <bool kMulti, int kWhich>
 __global__ void __launch_bounds__(32)
 k_link(const __grid_constant__ Geo g, const uint32_t *__restrict__ lists, const uint32_t *__restrict__ list_start,
        uint16_t *__restrict__ next4, uint16_t *__restrict__ prev3, uint8_t *__restrict__ clen_g)
@@ -300,13 +330,22 @@ k_link(const __grid_constant__ Geo g, const uint32_t *__restrict__ lists, const 
     // hash4 job: u16 head[4096] + u8 cnt[4096] (occurrences so far per bucket = chain-length estimate);
     // hash3 job: u16 head[8192].  Heads hold unit positions mod 65536; a link is valid below 32768, so at every
     // sub-unit boundary the heads that fell out of the window are parked on a sentinel 32768 positions back.
-    __shared__ __align__(16) uint16_t head[1 << kBits3];
+    constexpr int kStateSlots = kWhich == 1 ? (1 << kBits4) + (1 << kBits4) / 2 : (1 << kBits3);   // u16 slots of bucket state
+    static_assert(kBits3 > kBits4, "the hash3 table is the larger one");
+#if GZPB_LINK_PIPE
+    // + one byte per bucket for the group tags of the NEXT tile (see the tile loop)
+    __shared__ __align__(16) uint16_t head[kStateSlots + (kWhich == 1 ? (1 << kBits4) : (1 << kBits3)) / 2];
+    uint8_t *tag = (uint8_t *)(head + kStateSlots);
+#else
+    __shared__ __align__(16) uint16_t head[kStateSlots];
+#endif
     uint8_t *cnt = (uint8_t *)(head + (1 << kBits4));
-    const uint32_t u = blockIdx.x / kSplitLists, job = blockIdx.x % kSplitLists;
+    constexpr uint32_t kJobs = kWhich == 0 ? kSplitLists : kWhich == 1 ? kL4 : kL3;
+    const uint32_t u = blockIdx.x / kJobs, job = blockIdx.x % kJobs + (kWhich == 2 ? kL4 : 0);
     const uint32_t un = g.unit_len[u], udict = g.unit_dict[u];
     if (un <= udict) return;
     const uint32_t lane = threadIdx.x, lt = lanemask_lt();
-    const bool is4 = job < kL4;
+    const bool is4 = kWhich == 0 ? job < kL4 : kWhich == 1;
     const uint32_t nb16 = is4 ? (2u << kBits4) / 16 : (2u << kBits3) / 16;     // uint4 words of the head table
     uint16_t *out = (is4 ? next4 : prev3) + (size_t)u * g.m_stride;
     uint8_t *clen = clen_g + (size_t)u * g.m_stride;
@@ -348,6 +387,11 @@ k_link(const __grid_constant__ Geo g, const uint32_t *__restrict__ lists, const 
         uint32_t en[G];
 #pragma unroll
         for (int k = 0; k < G; k++) { uint32_t i = beg + 32 * k + lane; en[k] = i < end ? __ldg(arr + i) : 0; }
+#if GZPB_LINK_PIPE
+        const uint32_t bmask = is4 ? ((1u << kBits4) - 1) : ((1u << kBits3) - 1);
+        if (beg + lane < end) tag[en[0] & bmask] = (uint8_t)lane;     // group tags of the first tile
+        __syncwarp();
+#endif
         for (uint32_t base0 = beg; base0 < end; base0 += 32 * G) {
             uint32_t e[G];
 #pragma unroll
@@ -360,22 +404,51 @@ k_link(const __grid_constant__ Geo g, const uint32_t *__restrict__ lists, const 
                 if (base0 + 32 * k >= end) break;
                 const bool act = i < end;
                 const uint32_t b = e[k] & (is4 ? ((1u << kBits4) - 1) : ((1u << kBits3) - 1)), p = lo + (e[k] >> 16);   // unit position
-                // Entries of one tile that share a bucket are ordered by lane (= position order): MATCH.ANY gives every
-                // lane its group; the predecessor is the nearest lower member, or the bucket head for the group's first
-                // member; the group's last member becomes the new head.
+                // Entries of one tile that share a bucket are ordered by lane (= position order).  Every lane needs its
+                // group (the lanes with the same bucket): the predecessor is the nearest lower member, or the bucket head
+                // for the group's first member; the group's last member becomes the new head.
+#if GZPB_LINK_MATCHANY
+                // One MATCH.ANY per tile.  ncu (profiles/r2w): the ADU pipe that executes it is 88 % busy — about 60
+                // cycles per MATCH.ANY per SM — and bounds this kernel whatever the occupancy.
+                uint32_t hv = 0, c0 = 0;
                 const uint32_t grp = __match_any_sync(0xFFFFFFFFu, act ? b : (0x10000u + lane));
+                if (act) { hv = head[b]; if (is4) c0 = cnt[b]; }
+#elif GZPB_LINK_PIPE
+                // A tag byte per bucket names the groups: every member of a tile stored its LANE id in its bucket's tag
+                // one tile ago; whichever store survived, all members read the same 5-bit id back, and five ballots turn
+                // equal ids into the group mask (ALU work instead of the ADU pipe).  The ballots are also the point where
+                // every lane has read this tile's tags, so the next tile's tags are stored right behind them and travel
+                // with this tile's head update: one shared-memory round trip and one __syncwarp per tile.
+                uint32_t hv = 0, c0 = 0, rep = 0;
+                if (act) { rep = tag[b]; hv = head[b]; if (is4) c0 = cnt[b]; }
+                const uint32_t grp = same_list_mask<5>(rep, act);
+                __syncwarp();       // (memory order: every lane's loads above before the stores below)
+                {
+                    const uint32_t nxt = (k + 1 < G) ? e[(k + 1) % G] : en[0];
+                    if (i + 32 < end) tag[nxt & bmask] = (uint8_t)lane;
+                }
+#else
+                // The bucket table itself names the groups: every lane reads its bucket's state, then writes its LANE id
+                // there; whichever member's store survives, all members read the same 5-bit id back, and five ballots
+                // turn equal ids into the group mask (ALU work instead of the ADU pipe).
+                uint32_t hv = 0, c0 = 0;
+                if (act) { hv = head[b]; if (is4) c0 = cnt[b]; }
+                __syncwarp();
+                if (act) head[b] = (uint16_t)lane;
+                __syncwarp();
+                const uint32_t grp = same_list_mask<5>(act ? (uint32_t)head[b] : 0u, act);   // (the ballots order these reads before the stores below)
+#endif
                 const uint32_t lower = grp & lt;
                 const uint32_t pl = __shfl_sync(0xFFFFFFFFu, p, lower ? 31 - __clz(lower) : lane);
                 uint32_t dist = 0, occ = 0;
                 if (act) {
                     if (lower) dist = p - pl;
-                    else {
-                        const uint32_t hv = head[b];
-                        dist = (!kMulti || ksub == 0) ? (hv == kNone16 ? 0u : p - hv) : ((p - hv) & 0xFFFFu);
-                    }
-                    if (is4) occ = (uint32_t)cnt[b] + (uint32_t)__popc(lower);
+                    else dist = (!kMulti || ksub == 0) ? (hv == kNone16 ? 0u : p - hv) : ((p - hv) & 0xFFFFu);
+                    if (is4) occ = c0 + (uint32_t)__popc(lower);
                 }
+#if GZPB_LINK_MATCHANY
                 __syncwarp();   // every lane has read its bucket before a group's last member overwrites it
+#endif
                 if (act) {
                     if ((grp >> lane) == 1u) {
                         head[b] = (uint16_t)p;
@@ -502,20 +575,38 @@ k_match(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, cons
 
     // ---- phase 2: the searches, 32 positions of equal chain length per warp ----
     const uint32_t npos = sb.ne - sb.nb;
+#if GZPB_MATCH_PIPE
+    // The two global loads of a position — its slot in the sorted order and its hash3 link, a scattered 2-byte load that
+    // misses L1 — are issued one position ahead (ncu, profiles/r2w: 22 % of k_match's warp time was long-scoreboard stall):
+    // the next position's order entry at the top of this position's walk, its prev3 link right after the walk.
+    uint32_t p_cur = tid < npos ? order[tid] : 0u;
+    uint32_t d3_cur = (tid < npos && !ht) ? p3[p_cur] : 1u;
+#endif
     for (uint32_t i = tid; i < npos; i += kMatchThreads) {
+#if GZPB_MATCH_PIPE
+        const uint32_t p = p_cur;
+        const uint32_t d3 = d3_cur;            // level 1 (ht_matchfinder) has no hash3 table: the parser must see "bucket usable, no 3-byte match"
+        const bool have_next = i + kMatchThreads < npos;
+        const uint32_t p_next = have_next ? order[i + kMatchThreads] : 0u;
+#define GZPB_MATCH_NEXT() do { p_cur = p_next; d3_cur = (have_next && !ht) ? p3[p_next] : 1u; } while (0)
+#else
         const uint32_t p = order[i];
+#define GZPB_MATCH_NEXT() do { } while (0)
+#endif
         const uint32_t maxlen = min((uint32_t)kMaxMatch, n - p);
-        if (maxlen < 5) { M[p] = 0; if (M2) M2[p] = 0; continue; }
+        if (maxlen < 5) { M[p] = 0; if (M2) M2[p] = 0; GZPB_MATCH_NEXT(); continue; }
         const uint32_t nicep = min((uint32_t)nice, maxlen);
         // bytes 0..3 (the quick reject) and 4..11 (the inline extension) of this position: four words, three funnel shifts
         const uint32_t pw = p >> 2, psh = (p & 3) * 8;
         const uint32_t pa1 = s_in[pw + 1], pa2 = s_in[pw + 2];
         const uint32_t seq4 = __funnelshift_r(s_in[pw], pa1, psh);
         const uint32_t w1 = __funnelshift_r(pa1, pa2, psh), w2 = __funnelshift_r(pa2, s_in[pw + 3], psh);
+#if !GZPB_MATCH_PIPE
         // level 1 (ht_matchfinder) has no hash3 table: the parser must see "bucket usable, no 3-byte match"
         uint32_t d3 = ht ? 1u : p3[p];
         uint32_t off3 = 0;
         if (!ht && d3 && d3 <= 8192u && ((ld32u(s_in, p - d3) ^ seq4) & 0xFFFFFFu) == 0) off3 = d3;
+#endif
 
         uint32_t best = 3, boff = 0, lenB = 0, offB = 0, lenC = 0, offC = 0;
         bool haveB = !lazy, haveC = (lazy != 2);
@@ -561,6 +652,11 @@ k_match(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, cons
                 snap = (!haveC && depthC > visited) ? depthC : (!haveB && depthB > visited) ? depthB : (uint32_t)depth;
             }
         }
+        GZPB_MATCH_NEXT();
+#if GZPB_MATCH_PIPE
+        uint32_t off3 = 0;
+        if (!ht && d3 && d3 <= 8192u && ((ld32u(s_in, p - d3) ^ seq4) & 0xFFFFFFu) == 0) off3 = d3;
+#endif
         uint32_t lenA = best > 3 ? best : 0;
         if (!haveB) { lenB = lenA; offB = boff; }
         if (M2) { if (!haveC) { lenC = lenA; offC = boff; } M2[p] = (lenC ? lenC - 3 : 0) | (offC << 8); }
@@ -580,7 +676,18 @@ k_match(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, cons
 // =============================================================================
 constexpr int kEmitThreads = 32;
 constexpr int kTile = 128;                 // positions per streamed tile
-constexpr int kRing = 4;                   // tiles resident in the shared-memory ring
+#ifndef GZPB_EMIT_RING
+#define GZPB_EMIT_RING 4
+#endif
+#ifndef GZPB_EMIT_DIET
+#define GZPB_EMIT_DIET 0
+#endif
+#ifdef GZPB_EMIT_MINCTAS
+#define GZPB_EMIT_BOUNDS __launch_bounds__(kEmitThreads, GZPB_EMIT_MINCTAS)
+#else
+#define GZPB_EMIT_BOUNDS __launch_bounds__(kEmitThreads)
+#endif
+constexpr int kRing = GZPB_EMIT_RING;      // tiles resident in the shared-memory ring
 constexpr int kTokPerThread = 8;
 constexpr int kChunkTok = kEmitThreads * kTokPerThread;
 constexpr int kStageWords = (kChunkTok * 48) / 32 + 8;
@@ -598,11 +705,26 @@ struct EmitShared {
     uint8_t plen[kNumPrecode];
     uint16_t pcw[kNumPrecode];
     uint32_t pfreq[kNumPrecode];
+#if GZPB_EMIT_DIET
+    // Scratch that is only live while a DEFLATE block is being finished borrows memory that is idle then (32 instead of
+    // 22 resident units per SM): the Huffman sort array and the bit-packing staging words live in the tile ring (the
+    // parser drains it at the block end and issues its tiles again afterwards: a few tiles per ~50 KB block), the
+    // precode items in the literal/length frequencies (dead once the symbol costs are summed).
+    static_assert(sizeof(uint64_t) * kRing * kTile >= sizeof(uint32_t) * kStageWords && kStageWords >= kNumLitlen, "scratch must fit the tile ring");
+    static_assert(sizeof(uint32_t) * kNumLitlen >= sizeof(uint16_t) * (kNumLitlen + kNumOffset), "items must fit the frequencies");
+    __device__ __forceinline__ uint32_t *Ap() { return (uint32_t *)&mt[0][0]; }
+    __device__ __forceinline__ uint32_t *stagep() { return (uint32_t *)&mt[0][0]; }
+    __device__ __forceinline__ uint16_t *itemsp() { return (uint16_t *)fl; }
+#else
     uint16_t items[kNumLitlen + kNumOffset];
     union {                                  // never live at the same time
         uint32_t A[kNumLitlen];              // Huffman sort / tree array
         uint32_t stage[kStageWords];         // bit-packing staging words
     };
+    __device__ __forceinline__ uint32_t *Ap() { return A; }
+    __device__ __forceinline__ uint32_t *stagep() { return stage; }
+    __device__ __forceinline__ uint16_t *itemsp() { return items; }
+#endif
     uint32_t scan[kEmitThreads / 32];
     uint32_t used[8];
     // control block written by thread 0
@@ -682,13 +804,13 @@ __device__ void make_huffman_code(EmitShared &S, const uint32_t *freqs, uint32_t
                 uint32_t ft = freqs[t];
                 rank += (ft && (t | (ft << 10)) < key);
             }
-            S.A[rank] = key;
+            S.Ap()[rank] = key;
             atomicAdd(&S.nused, 1u);
         }
     }
     __syncthreads();
     if (tid == 0) {
-        uint32_t *A = S.A;
+        uint32_t *A = S.Ap();
         const uint32_t n = S.nused;
         if (n < 2) {
             uint32_t sym = n ? (A[0] & 1023u) : 0;
@@ -753,17 +875,17 @@ __device__ __forceinline__ void stage_commit(EmitShared &S, uint32_t *__restrict
 {
     __syncthreads();
     const uint32_t g = S.G, bw = g >> 5, nfull = ((g & 31) + nbits) >> 5;
-    for (uint32_t i = threadIdx.x; i < nfull; i += kEmitThreads) payload[bw + i] = S.stage[i];
+    for (uint32_t i = threadIdx.x; i < nfull; i += kEmitThreads) payload[bw + i] = S.stagep()[i];
     __syncthreads();
-    if (threadIdx.x == 0) { S.carry = S.stage[nfull]; S.G = g + nbits; }
+    if (threadIdx.x == 0) { S.carry = S.stagep()[nfull]; S.G = g + nbits; }
     __syncthreads();
 }
 // zero the staging area and seed word 0 with the carry; all threads call it.
 __device__ __forceinline__ void stage_begin(EmitShared &S, uint32_t words)
 {
-    for (uint32_t i = threadIdx.x; i < words; i += kEmitThreads) S.stage[i] = 0;
+    for (uint32_t i = threadIdx.x; i < words; i += kEmitThreads) S.stagep()[i] = 0;
     __syncthreads();
-    if (threadIdx.x == 0) S.stage[0] = S.carry;
+    if (threadIdx.x == 0) S.stagep()[0] = S.carry;
     __syncthreads();
 }
 
@@ -775,6 +897,7 @@ struct Parser {
     const uint8_t *in_g;
     EmitShared *S;
     uint32_t n, ntiles, issued, ready;
+    uint32_t phase;    // bit s: the parity slot s's barrier completes next (every issued tile is waited for exactly once)
     __device__ __forceinline__ void issue(uint32_t t)
     {
         uint32_t slot = t % kRing, pos = t * kTile;
@@ -784,6 +907,13 @@ struct Parser {
         tma_load_1d(S->mt[slot], mt_g + pos, bm, &S->bar[slot]);
         tma_load_1d(S->inb[slot], in_g + pos, bi, &S->bar[slot]);
     }
+    __device__ __forceinline__ void wait_next()
+    {
+        const uint32_t slot = ready % kRing;
+        mbar_wait(&S->bar[slot], (phase >> slot) & 1u);
+        phase ^= 1u << slot;
+        ready++;
+    }
     // tiles below p's tile are dead: refill their slots
     __device__ __forceinline__ void advance(uint32_t p)
     {
@@ -792,7 +922,8 @@ struct Parser {
             // tiles a long match jumped over were issued but never consumed: observe their
             // completion before their slots (and mbarrier phases) are reused
             const uint32_t first = p / kTile;
-            while (ready < issued && ready < first) { mbar_wait(&S->bar[ready % kRing], (ready / kRing) & 1); ready++; }
+            while (ready < issued && ready < first) wait_next();
+            if (issued < first) issued = ready = first;     // tiles a long match jumped over entirely are never loaded
             __syncwarp();
             if ((threadIdx.x & 31) == 0) {
                 fence_proxy_async();
@@ -804,8 +935,16 @@ struct Parser {
     __device__ __forceinline__ void need(uint32_t p)
     {
         uint32_t t = p / kTile;
-        while (ready <= t) { mbar_wait(&S->bar[ready % kRing], (ready / kRing) & 1); ready++; }
+        while (ready <= t) wait_next();
     }
+    // the ring memory is about to be used as scratch: nothing may be in flight
+    __device__ __forceinline__ void drain()
+    {
+        while (ready < issued) wait_next();
+        __syncwarp();
+    }
+    // the scratch use is over: the tiles from p's on are issued again by the next advance()
+    __device__ __forceinline__ void restart(uint32_t p) { issued = ready = p / kTile; }
     __device__ __forceinline__ uint64_t M(uint32_t p) { return S->mt[(p / kTile) % kRing][p % kTile]; }
     __device__ __forceinline__ uint32_t B(uint32_t p) { return S->inb[(p / kTile) % kRing][p % kTile]; }
 };
@@ -856,7 +995,7 @@ __device__ __forceinline__ uint32_t fold_unit_sum(const Geo &g, uint32_t u, cons
 }
 
 template <bool kLazy2>     // levels 8-9: the parser looks two positions ahead (states HC / X below); compiled out otherwise
-__global__ void __launch_bounds__(kEmitThreads)
+__global__ void GZPB_EMIT_BOUNDS
 k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
        const uint64_t *__restrict__ mtab, const uint32_t *__restrict__ mtab2, uint32_t *__restrict__ crc_io, const uint32_t *__restrict__ sum_part, int check_kind,
        uint32_t *__restrict__ tok_base,
@@ -890,7 +1029,7 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
 
     Parser P;
     P.mt_g = mtab + (size_t)u * g.m_stride; P.in_g = in; P.S = &S; P.n = n;
-    P.ntiles = (n + kTile - 1) / kTile; P.issued = dict / kTile; P.ready = dict / kTile;
+    P.ntiles = (n + kTile - 1) / kTile; P.issued = dict / kTile; P.ready = dict / kTile; P.phase = 0;
 
     if (tid == 0) {
         for (int i = 0; i < kRing; i++) mbar_init(&S.bar[i], 1);
@@ -919,7 +1058,7 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
                     else if (bit < 24) v = (len >> (bit - 8)) & 0xFF;
                     else if (bit < 40) v = ((~len & 0xFFFF) >> (bit - 24)) & 0xFF;
                     else v = in[pos + (bit - 40) / 8];
-                    stage_put(S.stage, g0 + (bit - cb), v, 8);
+                    stage_put(S.stagep(), g0 + (bit - cb), v, 8);
                 }
                 stage_commit(S, payload, chunk);
                 cb += chunk;
@@ -1138,6 +1277,9 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
                         end_block = true;
                     }
                 } while (p < max_block_end && !end_block);
+                // nothing stays in flight across the block end: the CTA must not exit under a pending copy (tiles a final
+                // long match jumped over), and with GZPB_EMIT_DIET the ring doubles as the block-finishing scratch
+                P.drain();
                 if (lane == 0) {
                     S.blk_end = p; S.ntok = ntok; S.is_final = (final_block && p == n) ? 1u : 0u;
                     S.fl[kEndOfBlock] += 1;
@@ -1153,6 +1295,27 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
             PHASE(3);
             make_huffman_code<uint16_t>(S, S.fo, kNumOffset, kMaxOffsetCw, ol, S.ocw);
             PHASE(4);
+            {   // symbol costs (parallel) — before the precode items are written: those reuse the frequency array (GZPB_EMIT_DIET)
+                uint32_t dyn = 0, stat = 0;
+                for (uint32_t s = tid; s < kNumLitlen; s += kEmitThreads) {
+                    uint32_t f = S.fl[s];
+                    if (s < 256) { dyn += f * ll[s]; stat += f * (s < 144 ? 8 : 9); }
+                    else if (s == 256) { dyn += ll[s]; stat += 7; }   // one end-of-block symbol
+                    else if (s < 286) {
+                        uint32_t k = s - 257;
+                        uint32_t extra = (k < 8 || k == 28) ? 0 : (k - 4) / 4;
+                        dyn += f * (extra + ll[s]); stat += f * (extra + c_static_litlen_len[s]);
+                    }
+                }
+                if (tid < 30) {
+                    uint32_t extra = tid < 4 ? 0 : (tid - 2) / 2;
+                    dyn += S.fo[tid] * (extra + ol[tid]); stat += S.fo[tid] * (extra + 5);
+                }
+                static_assert(kEmitThreads == 32, "one warp sums the symbol costs");
+                for (int o = 16; o; o >>= 1) { dyn += __shfl_xor_sync(0xFFFFFFFFu, dyn, o); stat += __shfl_xor_sync(0xFFFFFFFFu, stat, o); }
+                if (tid == 0) { S.cost_dyn = dyn; S.cost_static = stat; }
+            }
+            __syncthreads();
             if (tid == 0) {
                 // deflate_precompute_huffman_header(): RLE of the code lengths
                 uint32_t nlit = kNumLitlen, noff = kNumOffset;
@@ -1170,20 +1333,20 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
                     if (len == 0) {
                         while (run_end - run_start >= 11) {
                             uint32_t eb = min(run_end - run_start - 11, 0x7Fu);
-                            S.pfreq[18]++; S.items[ni++] = (uint16_t)(18 | (eb << 5)); run_start += 11 + eb;
+                            S.pfreq[18]++; S.itemsp()[ni++] = (uint16_t)(18 | (eb << 5)); run_start += 11 + eb;
                         }
                         if (run_end - run_start >= 3) {
                             uint32_t eb = min(run_end - run_start - 3, 7u);
-                            S.pfreq[17]++; S.items[ni++] = (uint16_t)(17 | (eb << 5)); run_start += 3 + eb;
+                            S.pfreq[17]++; S.itemsp()[ni++] = (uint16_t)(17 | (eb << 5)); run_start += 3 + eb;
                         }
                     } else if (run_end - run_start >= 4) {
-                        S.pfreq[len]++; S.items[ni++] = (uint16_t)len; run_start++;
+                        S.pfreq[len]++; S.itemsp()[ni++] = (uint16_t)len; run_start++;
                         do {
                             uint32_t eb = min(run_end - run_start - 3, 3u);
-                            S.pfreq[16]++; S.items[ni++] = (uint16_t)(16 | (eb << 5)); run_start += 3 + eb;
+                            S.pfreq[16]++; S.itemsp()[ni++] = (uint16_t)(16 | (eb << 5)); run_start += 3 + eb;
                         } while (run_end - run_start >= 3);
                     }
-                    while (run_start != run_end) { S.pfreq[len]++; S.items[ni++] = (uint16_t)len; run_start++; }
+                    while (run_start != run_end) { S.pfreq[len]++; S.itemsp()[ni++] = (uint16_t)len; run_start++; }
                 } while (run_start != num_lens);
 #undef LENS_AT
                 S.nitems = ni;
@@ -1202,27 +1365,7 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
                     uint32_t extra = s == 16 ? 2 : s == 17 ? 3 : s == 18 ? 7 : 0;
                     dyn += S.pfreq[s] * (extra + S.plen[s]);
                 }
-                S.cost_dyn = dyn; S.cost_static = stat;
-            }
-            __syncthreads();
-            {   // symbol costs (parallel)
-                uint32_t dyn = 0, stat = 0;
-                for (uint32_t s = tid; s < kNumLitlen; s += kEmitThreads) {
-                    uint32_t f = S.fl[s];
-                    if (s < 256) { dyn += f * ll[s]; stat += f * (s < 144 ? 8 : 9); }
-                    else if (s == 256) { dyn += ll[s]; stat += 7; }   // one end-of-block symbol
-                    else if (s < 286) {
-                        uint32_t k = s - 257;
-                        uint32_t extra = (k < 8 || k == 28) ? 0 : (k - 4) / 4;
-                        dyn += f * (extra + ll[s]); stat += f * (extra + c_static_litlen_len[s]);
-                    }
-                }
-                if (tid < 30) {
-                    uint32_t extra = tid < 4 ? 0 : (tid - 2) / 2;
-                    dyn += S.fo[tid] * (extra + ol[tid]); stat += S.fo[tid] * (extra + 5);
-                }
-                for (int o = 16; o; o >>= 1) { dyn += __shfl_xor_sync(0xFFFFFFFFu, dyn, o); stat += __shfl_xor_sync(0xFFFFFFFFu, stat, o); }
-                if ((tid & 31) == 0) { atomicAdd(&S.cost_dyn, dyn); atomicAdd(&S.cost_static, stat); }
+                S.cost_dyn += dyn; S.cost_static += stat;
             }
             __syncthreads();
             if (tid == 0) {
@@ -1243,7 +1386,7 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
                     stage_begin(S, 4);
                     uint32_t g0 = S.G & 31;
                     uint32_t hb = 3 + ((0u - ((S.G & 7) + 3)) & 7);
-                    if (tid == 0) stage_put(S.stage, g0, bfinal, 3);
+                    if (tid == 0) stage_put(S.stagep(), g0, bfinal, 3);
                     stage_commit(S, payload, hb);
                     uint32_t tot_bits = 32 + 8 * len;
                     for (uint32_t cb = 0; cb < tot_bits;) {
@@ -1255,7 +1398,7 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
                             if (bit < 16) v = (len >> bit) & 0xFF;
                             else if (bit < 32) v = ((~len & 0xFFFF) >> (bit - 16)) & 0xFF;
                             else v = in[pos + (bit - 32) / 8];
-                            stage_put(S.stage, g0 + (bit - cb), v, 8);
+                            stage_put(S.stagep(), g0 + (bit - cb), v, 8);
                         }
                         stage_commit(S, payload, chunk);
                         cb += chunk;
@@ -1268,19 +1411,19 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
                 uint32_t hbits = 0;
                 if (tid == 0) {
                     uint32_t g0 = S.G & 31, bp = g0;
-                    stage_put(S.stage, bp, is_final | (btype << 1), 3); bp += 3;
+                    stage_put(S.stagep(), bp, is_final | (btype << 1), 3); bp += 3;
                     if (btype == 2) {
                         const uint8_t perm[19] = {16,17,18,0,8,7,9,6,10,5,11,4,12,3,13,2,14,1,15};
-                        stage_put(S.stage, bp, S.nlit - 257, 5); bp += 5;
-                        stage_put(S.stage, bp, S.noff - 1, 5); bp += 5;
-                        stage_put(S.stage, bp, S.nexpl - 4, 4); bp += 4;
-                        for (uint32_t i = 0; i < S.nexpl; i++) { stage_put(S.stage, bp, S.plen[perm[i]], 3); bp += 3; }
+                        stage_put(S.stagep(), bp, S.nlit - 257, 5); bp += 5;
+                        stage_put(S.stagep(), bp, S.noff - 1, 5); bp += 5;
+                        stage_put(S.stagep(), bp, S.nexpl - 4, 4); bp += 4;
+                        for (uint32_t i = 0; i < S.nexpl; i++) { stage_put(S.stagep(), bp, S.plen[perm[i]], 3); bp += 3; }
                         for (uint32_t i = 0; i < S.nitems; i++) {
-                            uint32_t it = S.items[i], sym = it & 0x1F;
+                            uint32_t it = S.itemsp()[i], sym = it & 0x1F;
                             uint32_t pl = S.plen[sym];
-                            stage_put(S.stage, bp, S.pcw[sym], pl); bp += pl;
+                            stage_put(S.stagep(), bp, S.pcw[sym], pl); bp += pl;
                             uint32_t extra = sym == 16 ? 2 : sym == 17 ? 3 : sym == 18 ? 7 : 0;
-                            stage_put(S.stage, bp, it >> 5, extra); bp += extra;
+                            stage_put(S.stagep(), bp, it >> 5, extra); bp += extra;
                         }
                     }
                     S.scan[0] = bp - g0;
@@ -1333,12 +1476,15 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
                     for (int w = 0; w < kEmitThreads / 32; w++) { uint32_t v = S.scan[w]; if (w < (int)(tid >> 5)) woff += v; total += v; }
                     uint32_t bp = (S.G & 31) + woff + incl - sum;
 #pragma unroll
-                    for (int k = 0; k < kTokPerThread; k++) { stage_put(S.stage, bp, code[k], cl[k]); bp += cl[k]; }
+                    for (int k = 0; k < kTokPerThread; k++) { stage_put(S.stagep(), bp, code[k], cl[k]); bp += cl[k]; }
                     stage_commit(S, payload, total);
                 }
             }
             PHASE(9);
-            p = be;   // (only thread 0's copy matters)
+            p = be;
+#if GZPB_EMIT_DIET
+            P.restart(be);
+#endif
             if (be >= n) break;
         }
     }
@@ -1350,7 +1496,7 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
         uint32_t hb = 3 + ((0u - ((S.G & 7) + 3)) & 7);
         stage_commit(S, payload, hb);            // 3 zero bits + padding
         stage_begin(S, 8);
-        if (tid == 0) stage_put(S.stage, S.G & 31, 0xFFFF0000ull, 32);
+        if (tid == 0) stage_put(S.stagep(), S.G & 31, 0xFFFF0000ull, 32);
         stage_commit(S, payload, 32);
     }
     __syncthreads();
@@ -1627,8 +1773,18 @@ cudaError_t launch_deflate_pipeline(const DeflateBatch &b, cudaStream_t st)
         GZPB_LAUNCH(k_split, b.nunits * b.spu, kSplitThreads, 0, st, g, b.lists, b.list_start, b.next4, b.prev3, lp.ht,
                     fold_check ? b.sum_part : (uint32_t *)nullptr, b.check_kind);
         DBG_SYNC("k_split");
-        if (b.spu > 1) GZPB_LAUNCH(k_link<true>, b.nunits * kSplitLists, 32, 0, st, g, b.lists, b.list_start, b.next4, b.prev3, b.clen);
-        else GZPB_LAUNCH(k_link<false>, b.nunits * kSplitLists, 32, 0, st, g, b.lists, b.list_start, b.next4, b.prev3, b.clen);
+#if GZPB_LINK_SPLIT
+        if (b.spu > 1) {
+            GZPB_LAUNCH((k_link<true, 2>), b.nunits * kL3, 32, 0, st, g, b.lists, b.list_start, b.next4, b.prev3, b.clen);
+            GZPB_LAUNCH((k_link<true, 1>), b.nunits * kL4, 32, 0, st, g, b.lists, b.list_start, b.next4, b.prev3, b.clen);
+        } else {
+            GZPB_LAUNCH((k_link<false, 2>), b.nunits * kL3, 32, 0, st, g, b.lists, b.list_start, b.next4, b.prev3, b.clen);
+            GZPB_LAUNCH((k_link<false, 1>), b.nunits * kL4, 32, 0, st, g, b.lists, b.list_start, b.next4, b.prev3, b.clen);
+        }
+#else
+        if (b.spu > 1) GZPB_LAUNCH((k_link<true, 0>), b.nunits * kSplitLists, 32, 0, st, g, b.lists, b.list_start, b.next4, b.prev3, b.clen);
+        else GZPB_LAUNCH((k_link<false, 0>), b.nunits * kSplitLists, 32, 0, st, g, b.lists, b.list_start, b.next4, b.prev3, b.clen);
+#endif
         DBG_SYNC("k_link");
         if (b.timer) { b.timer->stop(st); b.timer->start(KT_MATCH, st); }
         GZPB_LAUNCH(k_match, b.nunits * b.spu, kMatchThreads, match_smem, st, g, b.next4, b.prev3, b.mtab, b.mtab2, b.clen, b.order, lp.depth, lp.nice, lp.mode, lp.ht);

@@ -200,11 +200,17 @@ inline void emu_mbar_check(EmuMbar *b)
 }
 inline void mbar_init(uint64_t *bar, uint32_t count) { EmuMbar *b = (EmuMbar *)bar; b->tx = 0; b->pending = (uint16_t)count; b->count_phase = (uint16_t)count; }
 inline void mbar_expect_tx(uint64_t *bar, uint32_t bytes) { EmuMbar *b = (EmuMbar *)bar; b->tx += (int32_t)bytes; b->pending--; emu_mbar_check(b); }
-inline bool mbar_try_wait(uint64_t *bar, uint32_t phase) { EmuMbar *b = (EmuMbar *)bar; return (uint32_t)(b->count_phase >> 15) != (phase & 1u); }
+inline bool mbar_try_wait(uint64_t *bar, uint32_t phase)
+{
+    EmuMbar *b = (EmuMbar *)bar;
+    if (gzpb_emu::tma_late()) { const uint32_t moved = gzpb_emu::tma_deliver(bar); if (moved) { b->tx -= (int32_t)moved; emu_mbar_check(b); } }
+    return (uint32_t)(b->count_phase >> 15) != (phase & 1u);
+}
 inline void mbar_wait(uint64_t *bar, uint32_t phase) { while (!mbar_try_wait(bar, phase)) gzpb_emu::wait_yield(); }
 inline void tma_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar)
 {
     if (((uintptr_t)smem_dst & 15) || ((uintptr_t)gsrc & 15) || (bytes & 15)) gzpb_emu::trap("cp.async.bulk: dst/src/size must be 16-byte aligned");
+    if (gzpb_emu::tma_late()) { gzpb_emu::tma_defer(bar, smem_dst, gsrc, bytes); return; }     // lands when somebody waits for it
     memcpy(smem_dst, gsrc, bytes);
     EmuMbar *b = (EmuMbar *)bar; b->tx -= (int32_t)bytes; emu_mbar_check(b);
 }

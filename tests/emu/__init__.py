@@ -18,13 +18,16 @@ _CSRC = os.path.join(_ROOT, "gzp_b200", "csrc")
 # and ASAN_OPTIONS=detect_leaks=0): "device" memory is host heap here, so an out-of-bounds access of a kernel or of the
 # host runtime is reported with the kernel's source line — compute-sanitizer's memcheck without a GPU.
 _ASAN = os.environ.get("GZPB_EMU_ASAN") == "1"
-_BUILD = os.path.join(_HERE, "_build_asan" if _ASAN else "_build")
+# GZPB_EMU_DEFS="-DGZPB_X=1 ...": compile-time kernel variants (the A/B candidates of a GPU session) in their own directory
+_DEFS = os.environ.get("GZPB_EMU_DEFS", "").split()
+_BUILD = os.path.join(_HERE, ("_build_asan" if _ASAN else "_build") +
+                      ("_" + "".join(c if c.isalnum() else "_" for c in "".join(_DEFS)) if _DEFS else ""))
 SO = os.path.join(_BUILD, "libgzpb_emu.so")
 CXX = os.environ.get("CXX", "g++")
 if os.environ.get("GZPB_EMU_ASAN") == "1" and os.path.exists("/usr/bin/g++"):
     CXX = "/usr/bin/g++"           # the distribution compiler knows where its libasan lives
 FLAGS = ["-std=c++17", "-O2", "-g", "-fPIC", "-fno-strict-aliasing", "-Wno-unused", "-I", os.path.join(_HERE, "shim"),
-         "-I", _CSRC, "-DGZPB_EMU=1"] + (["-fsanitize=address", "-fno-omit-frame-pointer"] if _ASAN else [])
+         "-I", _CSRC, "-DGZPB_EMU=1"] + _DEFS + (["-fsanitize=address", "-fno-omit-frame-pointer"] if _ASAN else [])
 
 
 def build(force=False):

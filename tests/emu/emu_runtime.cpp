@@ -63,6 +63,8 @@ std::vector<WarpState> g_warps;
 void *g_sched_sp = nullptr;
 const std::function<void()> *g_body = nullptr;
 unsigned g_nthreads = 0, g_live = 0, g_bar_count = 0, g_bar_gen = 0;
+struct TmaPending { void *bar; void *dst; const void *src; uint32_t bytes; };
+std::vector<TmaPending> g_tma_pending;    // bulk copies issued, not yet waited for (tma_late)
 bool g_progress = false;
 uint8_t *g_dyn = nullptr;
 size_t g_dyn_cap = 0;
@@ -235,8 +237,27 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> &bod
                     }
                 }
                 g_self = nullptr;
+                if (!g_tma_pending.empty()) {
+                    fprintf(stderr, "[gzpb_emu] block (%u,%u,%u) ended with %zu bulk copies in flight\n", bx, by, bz, g_tma_pending.size());
+                    abort();
+                }
             }
     g_body = nullptr;
+}
+
+bool tma_late() { static const bool late = [] { const char *e = getenv("GZPB_EMU_TMA"); return !(e && !strcmp(e, "eager")); }(); return late; }
+void tma_defer(void *bar, void *dst, const void *src, uint32_t bytes) { g_tma_pending.push_back(TmaPending{bar, dst, src, bytes}); }
+uint32_t tma_deliver(void *bar)
+{
+    uint32_t moved = 0;
+    for (size_t i = 0; i < g_tma_pending.size();) {
+        if (g_tma_pending[i].bar == bar) {
+            memcpy(g_tma_pending[i].dst, g_tma_pending[i].src, g_tma_pending[i].bytes);
+            moved += g_tma_pending[i].bytes;
+            g_tma_pending.erase(g_tma_pending.begin() + (long)i);
+        } else i++;
+    }
+    return moved;
 }
 
 }  // namespace gzpb_emu

@@ -97,6 +97,13 @@ long long clock();
 void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> &body);
 void launch_async(void *stream, dim3 grid, dim3 block, size_t smem, std::function<void()> body);   // queued on the (lazy) stream
 [[noreturn]] void trap(const char *why);
+// Bulk copies (cp.async.bulk) land LATE by default: the bytes are moved only when a thread waits on the copy's
+// mbarrier, i.e. at the last moment the hardware could deliver them.  A kernel that reads a tile before waiting for
+// it, reuses the destination as scratch while the copy is in flight, or exits with a copy pending is wrong here every
+// time, as it is sometimes on a GPU.  GZPB_EMU_TMA=eager copies at issue time.
+bool tma_late();
+void tma_defer(void *bar, void *dst, const void *src, uint32_t bytes);
+uint32_t tma_deliver(void *bar);        // performs every copy pending on `bar`, returns the bytes moved
 }  // namespace gzpb_emu
 
 #define threadIdx (gzpb_emu::g_self->tid)

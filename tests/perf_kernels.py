@@ -34,7 +34,7 @@ def main():
     d_status = torch.zeros((nblk,), dtype=torch.int32, device=dev)
     st = torch.cuda.current_stream()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    ctx = gzp_b200.Context(gzp_b200.BGZF, level, device=0, max_block_bytes=BLOCK, max_blocks_in_flight=min(nblk, 3256))
+    ctx = gzp_b200.Context(gzp_b200.BGZF, level, device=0, max_block_bytes=BLOCK, max_blocks_in_flight=min(nblk, int(os.environ.get("GZPB_PERF_INFLIGHT", "3256"))))
     d_packed = torch.zeros((nblk * 73728,), dtype=torch.uint8, device=dev)
 
     def step():
