@@ -19,6 +19,7 @@
 
 #include "gzpb_common.cuh"
 #include "deflate_kernels.cuh"
+#include <type_traits>
 
 namespace gzpb {
 
@@ -127,7 +128,9 @@ constexpr int kSplitThreads = 1024;
 #define GZPB_LISTS 0
 #endif
 #if GZPB_LISTS == 0
-constexpr int kBits4 = 12, kBits3 = 13;  // buckets per link job: hash4 8 KiB table + 4 KiB counts, hash3 16 KiB table (14 jobs per SM)
+constexpr int kBits4 = 12, kBits3 = 13;  // buckets per link job: hash4 8 KiB table + 4 KiB counts, hash3 16 KiB table
+#elif GZPB_LISTS == 2
+constexpr int kBits4 = 12, kBits3 = 12;  // 16 + 8 lists: hash4 8 KiB table + 4 KiB counts, hash3 8 KiB table — every job fits 12 KiB (one launch, 17 jobs per SM)
 #else
 constexpr int kBits4 = 11, kBits3 = 12;  // buckets per link job: hash4 4 KiB table + 2 KiB counts, hash3 8 KiB table (28 jobs per SM)
 #endif
@@ -136,6 +139,9 @@ constexpr int kBits4 = 11, kBits3 = 12;  // buckets per link job: hash4 4 KiB ta
 #endif
 #ifndef GZPB_MATCH_PIPE
 #define GZPB_MATCH_PIPE 1
+#endif
+#ifndef GZPB_FULL_TILES
+#define GZPB_FULL_TILES 0
 #endif
 #ifndef GZPB_PLAIN_BALLOT
 #define GZPB_PLAIN_BALLOT 0
@@ -147,10 +153,10 @@ constexpr int kLsStride = 64;            // list_start entries per sub-unit: [0.
 
 // Lanes of the warp whose (active) list id equals this lane's: the id has only BITS bits, so BITS ballots do what a
 // MATCH.ANY does at a fraction of its latency (k_split ranks every position twice per pass).
-template <int BITS>
+template <int BITS, bool kAllActive = false>
 __device__ __forceinline__ uint32_t same_list_mask(uint32_t id, bool act)
 {
-    uint32_t m = __ballot_sync(0xFFFFFFFFu, act);
+    uint32_t m = kAllActive ? 0xFFFFFFFFu : __ballot_sync(0xFFFFFFFFu, act);
 #if !defined(GZPB_EMU) && !GZPB_PLAIN_BALLOT
     // four instructions per bit (bit test with predicate, VOTE, two predicated LOP3); the C++ form below compiles to seven
 #pragma unroll
@@ -172,7 +178,7 @@ __device__ __forceinline__ uint32_t same_list_mask(uint32_t id, bool act)
     return m;
 }
 
-__global__ void __launch_bounds__(kSplitThreads)
+__global__ void __launch_bounds__(kSplitThreads, 2)
 k_split(const __grid_constant__ Geo g, uint32_t *__restrict__ lists, uint32_t *__restrict__ list_start,
         uint16_t *__restrict__ next4, uint16_t *__restrict__ prev3, int ht, uint32_t *__restrict__ sum_part, int check_kind)
 {
@@ -208,18 +214,23 @@ k_split(const __grid_constant__ Geo g, uint32_t *__restrict__ lists, uint32_t *_
     for (uint32_t i = lane; i < (uint32_t)kSplitLists; i += 32) s_w[warp][i] = 0;
     __syncwarp();
     // pass 1: every warp counts the list members of its contiguous range of tiles
-    for (uint32_t t = t0; t < t1; t++) {
+    // (tiles in front of the last one are full: their code carries no activity predicate — GZPB_FULL_TILES)
+    const uint32_t tfull = GZPB_FULL_TILES ? min(t1, ninsert / 32) : t0;
+    auto count_tile = [&](uint32_t t, auto full) {
+        constexpr bool kFull = decltype(full)::value;
         const uint32_t p = t * 32 + lane;
-        const bool act = p < ninsert;
+        const bool act = kFull || p < ninsert;
         const uint32_t v = act ? ldg32u(uw, lo + p) : 0;
         uint32_t h4 = ht ? (lz_hash(v, 15) << 1) : lz_hash(v, 16), h3 = lz_hash(v & 0xFFFFFFu, 15);   // level 1: 15-bit buckets (even slots)
         if (p == 0 && quirk0) { h4 = 0; h3 = 0; }
         const uint32_t q4 = h4 >> kBits4, q3 = h3 >> kBits3;
-        const uint32_t m4 = same_list_mask<kQ4Bits>(q4, act), m3 = same_list_mask<kQ3Bits>(q3, act);
+        const uint32_t m4 = same_list_mask<kQ4Bits, kFull>(q4, act), m3 = same_list_mask<kQ3Bits, kFull>(q3, act);
         if (act && (m4 & lt) == 0) s_w[warp][q4] += __popc(m4);          // group leader
         if (act && (m3 & lt) == 0) s_w[warp][kL4 + q3] += __popc(m3);
         __syncwarp();
-    }
+    };
+    for (uint32_t t = t0; t < max(t0, tfull); t++) count_tile(t, std::true_type{});
+    for (uint32_t t = max(t0, tfull); t < t1; t++) count_tile(t, std::false_type{});
     __syncthreads();
     if (tid < kSplitLists) {
         // exclusive prefix over the warps (position order) for list `tid`
@@ -239,14 +250,15 @@ k_split(const __grid_constant__ Geo g, uint32_t *__restrict__ lists, uint32_t *_
     }
     __syncthreads();
     // pass 2: scatter (hash, position - lo) entries in position order
-    for (uint32_t t = t0; t < t1; t++) {
+    auto scatter_tile = [&](uint32_t t, auto full) {
+        constexpr bool kFull = decltype(full)::value;
         const uint32_t p = t * 32 + lane;
-        const bool act = p < ninsert;
+        const bool act = kFull || p < ninsert;
         const uint32_t v = act ? ldg32u(uw, lo + p) : 0;
         uint32_t h4 = ht ? (lz_hash(v, 15) << 1) : lz_hash(v, 16), h3 = lz_hash(v & 0xFFFFFFu, 15);   // level 1: 15-bit buckets (even slots)
         if (p == 0 && quirk0) { h4 = 0; h3 = 0; }
         const uint32_t q4 = h4 >> kBits4, q3 = h3 >> kBits3;
-        const uint32_t m4 = same_list_mask<kQ4Bits>(q4, act), m3 = same_list_mask<kQ3Bits>(q3, act);
+        const uint32_t m4 = same_list_mask<kQ4Bits, kFull>(q4, act), m3 = same_list_mask<kQ3Bits, kFull>(q3, act);
         uint32_t b4 = 0, b3 = 0;
         if (act) { b4 = s_w[warp][q4]; b3 = s_w[warp][kL4 + q3]; }
         __syncwarp();
@@ -257,7 +269,9 @@ k_split(const __grid_constant__ Geo g, uint32_t *__restrict__ lists, uint32_t *_
             if ((m3 & lt) == 0) s_w[warp][kL4 + q3] = b3 + __popc(m3);
         }
         __syncwarp();
-    }
+    };
+    for (uint32_t t = t0; t < max(t0, tfull); t++) scatter_tile(t, std::true_type{});
+    for (uint32_t t = max(t0, tfull); t < t1; t++) scatter_tile(t, std::false_type{});
     // positions that are never inserted carry no link
     for (uint32_t p = max(lo, uinsert) + tid; p < hi_new; p += kSplitThreads) {
         next4[(size_t)sb.u * g.m_stride + p] = 0;
@@ -314,7 +328,7 @@ k_split(const __grid_constant__ Geo g, uint32_t *__restrict__ lists, uint32_t *_
 }
 
 #ifndef GZPB_LINK_SPLIT
-#define GZPB_LINK_SPLIT 0
+#define GZPB_LINK_SPLIT 1
 #endif
 #ifndef GZPB_LINK_PIPE
 #define GZPB_LINK_PIPE 0
@@ -330,8 +344,8 @@ k_link(const __grid_constant__ Geo g, const uint32_t *__restrict__ lists, const 
     // hash4 job: u16 head[4096] + u8 cnt[4096] (occurrences so far per bucket = chain-length estimate);
     // hash3 job: u16 head[8192].  Heads hold unit positions mod 65536; a link is valid below 32768, so at every
     // sub-unit boundary the heads that fell out of the window are parked on a sentinel 32768 positions back.
-    constexpr int kStateSlots = kWhich == 1 ? (1 << kBits4) + (1 << kBits4) / 2 : (1 << kBits3);   // u16 slots of bucket state
-    static_assert(kBits3 > kBits4, "the hash3 table is the larger one");
+    constexpr int kSlots4 = (1 << kBits4) + (1 << kBits4) / 2, kSlots3 = 1 << kBits3;             // u16 slots of bucket state per job type
+    constexpr int kStateSlots = kWhich == 1 ? kSlots4 : kWhich == 2 ? kSlots3 : (kSlots4 > kSlots3 ? kSlots4 : kSlots3);
 #if GZPB_LINK_PIPE
     // + one byte per bucket for the group tags of the NEXT tile (see the tile loop)
     __shared__ __align__(16) uint16_t head[kStateSlots + (kWhich == 1 ? (1 << kBits4) : (1 << kBits3)) / 2];
@@ -398,12 +412,12 @@ k_link(const __grid_constant__ Geo g, const uint32_t *__restrict__ lists, const 
             for (int k = 0; k < G; k++) e[k] = en[k];
 #pragma unroll
             for (int k = 0; k < G; k++) { uint32_t i = base0 + 32 * (G + k) + lane; en[k] = i < end ? __ldg(arr + i) : 0; }
-#pragma unroll
-            for (int k = 0; k < G; k++) {
-                const uint32_t i = base0 + 32 * k + lane;
-                if (base0 + 32 * k >= end) break;
-                const bool act = i < end;
-                const uint32_t b = e[k] & (is4 ? ((1u << kBits4) - 1) : ((1u << kBits3) - 1)), p = lo + (e[k] >> 16);   // unit position
+            // one tile of 32 entries; kFull: every lane has an entry (all tiles but a list's last), no activity predicates
+            auto tile = [&](const uint32_t ek, const uint32_t ek_next, const uint32_t i, auto full) {
+                constexpr bool kFull = decltype(full)::value;
+                const bool act = kFull || i < end;
+                (void)ek_next;
+                const uint32_t b = ek & (is4 ? ((1u << kBits4) - 1) : ((1u << kBits3) - 1)), p = lo + (ek >> 16);   // unit position
                 // Entries of one tile that share a bucket are ordered by lane (= position order).  Every lane needs its
                 // group (the lanes with the same bucket): the predecessor is the nearest lower member, or the bucket head
                 // for the group's first member; the group's last member becomes the new head.
@@ -421,10 +435,10 @@ k_link(const __grid_constant__ Geo g, const uint32_t *__restrict__ lists, const 
                 // with this tile's head update: one shared-memory round trip and one __syncwarp per tile.
                 uint32_t hv = 0, c0 = 0, rep = 0;
                 if (act) { rep = tag[b]; hv = head[b]; if (is4) c0 = cnt[b]; }
-                const uint32_t grp = same_list_mask<5>(rep, act);
+                const uint32_t grp = same_list_mask<5, kFull>(rep, act);
                 __syncwarp();       // (memory order: every lane's loads above before the stores below)
                 {
-                    const uint32_t nxt = (k + 1 < G) ? e[(k + 1) % G] : en[0];
+                    const uint32_t nxt = ek_next;
                     if (i + 32 < end) tag[nxt & bmask] = (uint8_t)lane;
                 }
 #else
@@ -436,7 +450,7 @@ k_link(const __grid_constant__ Geo g, const uint32_t *__restrict__ lists, const 
                 __syncwarp();
                 if (act) head[b] = (uint16_t)lane;
                 __syncwarp();
-                const uint32_t grp = same_list_mask<5>(act ? (uint32_t)head[b] : 0u, act);   // (the ballots order these reads before the stores below)
+                const uint32_t grp = same_list_mask<5, kFull>(act ? (uint32_t)head[b] : 0u, act);   // (the ballots order these reads before the stores below)
 #endif
                 const uint32_t lower = grp & lt;
                 const uint32_t pl = __shfl_sync(0xFFFFFFFFu, p, lower ? 31 - __clz(lower) : lane);
@@ -459,6 +473,16 @@ k_link(const __grid_constant__ Geo g, const uint32_t *__restrict__ lists, const 
                     if (is4) clen[p] = (uint8_t)min(occ, 127u);
                 }
                 __syncwarp();
+            };
+            if (GZPB_FULL_TILES && base0 + 32 * G <= end) {
+#pragma unroll
+                for (int k = 0; k < G; k++) tile(e[k], (k + 1 < G) ? e[(k + 1) % G] : en[0], base0 + 32 * k + lane, std::true_type{});
+            } else {
+#pragma unroll
+                for (int k = 0; k < G; k++) {
+                    if (base0 + 32 * k >= end) break;
+                    tile(e[k], (k + 1 < G) ? e[(k + 1) % G] : en[0], base0 + 32 * k + lane, std::false_type{});
+                }
             }
         }
     }
@@ -677,10 +701,16 @@ k_match(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, cons
 constexpr int kEmitThreads = 32;
 constexpr int kTile = 128;                 // positions per streamed tile
 #ifndef GZPB_EMIT_RING
-#define GZPB_EMIT_RING 4
+#define GZPB_EMIT_RING 3
 #endif
 #ifndef GZPB_EMIT_DIET
-#define GZPB_EMIT_DIET 0
+#define GZPB_EMIT_DIET 1
+#endif
+#ifndef GZPB_EMIT_WALK2
+#define GZPB_EMIT_WALK2 0
+#endif
+#ifndef GZPB_EMIT_MINCTAS
+#define GZPB_EMIT_MINCTAS 32
 #endif
 #ifdef GZPB_EMIT_MINCTAS
 #define GZPB_EMIT_BOUNDS __launch_bounds__(kEmitThreads, GZPB_EMIT_MINCTAS)
@@ -1180,21 +1210,41 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
                     }
                     // ---- follow the path through the window (one token per hop) ----
                     // (every lane walks the same path: the F and HB words of a position travel in one shuffle)
-                    const uint32_t wlimit = min(32u, max_block_end - p), w2 = wF | (wHB << 12);
-                    uint32_t vis = 0, sm0 = 0, sm1 = 0, c = 0, st = in_h;
-                    while (c < wlimit) {
-                        vis |= 1u << c; sm0 |= (kLazy2 ? (st & 1u) : st) << c;
-                        const uint32_t a = __shfl_sync(0xFFFFFFFFu, w2, c);
-                        uint32_t w = (st & 1u) ? (a >> 12) : a;
-                        if (kLazy2) {
-                            sm1 |= (st >> 1) << c;
-                            const uint32_t b = __shfl_sync(0xFFFFFFFFu, wHC, c);
-                            if (st == 2u) w = b; else if (st == 3u) w = kToHC;
+                    const uint32_t wlimit = min(32u, max_block_end - p);
+                    uint32_t vis = 0, c = 0, st = in_h, myst;
+#if GZPB_EMIT_WALK2
+                    if (!kLazy2) {
+                        // ten instructions per hop: the state travels as the shift (0 / 16) that selects its transition word,
+                        // the lane a hop lands on notes the state itself, one ballot afterwards gives the path
+                        const uint32_t w2 = wF | (wHB << 16);
+                        uint32_t sh = in_h << 4, mine = 0xFFu;
+                        while (c < wlimit) {
+                            const uint32_t a = __shfl_sync(0xFFFFFFFFu, w2, c);
+                            mine = (lane == c) ? sh : mine;
+                            const uint32_t w = a >> sh;
+                            c += w & 0x1FF; sh = (w >> 5) & 16u;
                         }
-                        c += w & 0x1FF; st = (w >> 9) & 3u;
+                        vis = __ballot_sync(0xFFFFFFFFu, mine != 0xFFu);
+                        myst = (mine >> 4) & 1u; st = sh >> 4;
+                    } else
+#endif
+                    {
+                        const uint32_t w2 = wF | (wHB << 12);
+                        uint32_t sm0 = 0, sm1 = 0;
+                        while (c < wlimit) {
+                            vis |= 1u << c; sm0 |= (kLazy2 ? (st & 1u) : st) << c;
+                            const uint32_t a = __shfl_sync(0xFFFFFFFFu, w2, c);
+                            uint32_t w = (st & 1u) ? (a >> 12) : a;
+                            if (kLazy2) {
+                                sm1 |= (st >> 1) << c;
+                                const uint32_t b = __shfl_sync(0xFFFFFFFFu, wHC, c);
+                                if (st == 2u) w = b; else if (st == 3u) w = kToHC;
+                            }
+                            c += w & 0x1FF; st = (w >> 9) & 3u;
+                        }
+                        myst = ((sm0 >> lane) & 1u) | (kLazy2 ? (((sm1 >> lane) & 1u) << 1) : 0u);
                     }
                     const bool onpath = (vis >> lane) & 1u;
-                    const uint32_t myst = ((sm0 >> lane) & 1u) | (kLazy2 ? (((sm1 >> lane) & 1u) << 1) : 0u);
                     const uint32_t myw = kLazy2 ? (myst == 0 ? wF : myst == 1 ? wHB : myst == 2 ? wHC : kToHC) : (myst ? wHB : wF);
                     const bool myM = (myw & kIsM) != 0;                             // my token is a match
                     const uint32_t incl = __popc(vis & (lane == 31 ? 0xFFFFFFFFu : ((2u << lane) - 1)));   // tokens up to and including mine
@@ -1746,6 +1796,7 @@ static Geo make_geo(const DeflateBatch &b)
     return g;
 }
 
+#define GZPB_COUNTED_LAUNCH(...) do { GZPB_LAUNCH(__VA_ARGS__); if (b.launch_counter) ++*b.launch_counter; } while (0)
 cudaError_t launch_deflate_pipeline(const DeflateBatch &b, cudaStream_t st)
 {
     static bool attr_done[64] = {};          // function attributes are per device (several GPUs in one process)
@@ -1765,38 +1816,38 @@ cudaError_t launch_deflate_pipeline(const DeflateBatch &b, cudaStream_t st)
     const bool fold_check = b.check_kind >= 0 && lp.mode >= 0 && b.sum_part != nullptr;
     if (b.check_kind >= 0 && !fold_check) {
         if (b.timer) b.timer->start(KT_CRC, st);
-        GZPB_LAUNCH(k_check, b.nunits, 256, 0, st, g, b.crc, b.check_kind);
+        GZPB_COUNTED_LAUNCH(k_check, b.nunits, 256, 0, st, g, b.crc, b.check_kind);
         if (b.timer) b.timer->stop(st);
     }
     if (lp.mode >= 0) {
         if (b.timer) b.timer->start(KT_CHAIN, st);
-        GZPB_LAUNCH(k_split, b.nunits * b.spu, kSplitThreads, 0, st, g, b.lists, b.list_start, b.next4, b.prev3, lp.ht,
+        GZPB_COUNTED_LAUNCH(k_split, b.nunits * b.spu, kSplitThreads, 0, st, g, b.lists, b.list_start, b.next4, b.prev3, lp.ht,
                     fold_check ? b.sum_part : (uint32_t *)nullptr, b.check_kind);
         DBG_SYNC("k_split");
 #if GZPB_LINK_SPLIT
         if (b.spu > 1) {
-            GZPB_LAUNCH((k_link<true, 2>), b.nunits * kL3, 32, 0, st, g, b.lists, b.list_start, b.next4, b.prev3, b.clen);
-            GZPB_LAUNCH((k_link<true, 1>), b.nunits * kL4, 32, 0, st, g, b.lists, b.list_start, b.next4, b.prev3, b.clen);
+            GZPB_COUNTED_LAUNCH((k_link<true, 2>), b.nunits * kL3, 32, 0, st, g, b.lists, b.list_start, b.next4, b.prev3, b.clen);
+            GZPB_COUNTED_LAUNCH((k_link<true, 1>), b.nunits * kL4, 32, 0, st, g, b.lists, b.list_start, b.next4, b.prev3, b.clen);
         } else {
-            GZPB_LAUNCH((k_link<false, 2>), b.nunits * kL3, 32, 0, st, g, b.lists, b.list_start, b.next4, b.prev3, b.clen);
-            GZPB_LAUNCH((k_link<false, 1>), b.nunits * kL4, 32, 0, st, g, b.lists, b.list_start, b.next4, b.prev3, b.clen);
+            GZPB_COUNTED_LAUNCH((k_link<false, 2>), b.nunits * kL3, 32, 0, st, g, b.lists, b.list_start, b.next4, b.prev3, b.clen);
+            GZPB_COUNTED_LAUNCH((k_link<false, 1>), b.nunits * kL4, 32, 0, st, g, b.lists, b.list_start, b.next4, b.prev3, b.clen);
         }
 #else
-        if (b.spu > 1) GZPB_LAUNCH((k_link<true, 0>), b.nunits * kSplitLists, 32, 0, st, g, b.lists, b.list_start, b.next4, b.prev3, b.clen);
-        else GZPB_LAUNCH((k_link<false, 0>), b.nunits * kSplitLists, 32, 0, st, g, b.lists, b.list_start, b.next4, b.prev3, b.clen);
+        if (b.spu > 1) GZPB_COUNTED_LAUNCH((k_link<true, 0>), b.nunits * kSplitLists, 32, 0, st, g, b.lists, b.list_start, b.next4, b.prev3, b.clen);
+        else GZPB_COUNTED_LAUNCH((k_link<false, 0>), b.nunits * kSplitLists, 32, 0, st, g, b.lists, b.list_start, b.next4, b.prev3, b.clen);
 #endif
         DBG_SYNC("k_link");
         if (b.timer) { b.timer->stop(st); b.timer->start(KT_MATCH, st); }
-        GZPB_LAUNCH(k_match, b.nunits * b.spu, kMatchThreads, match_smem, st, g, b.next4, b.prev3, b.mtab, b.mtab2, b.clen, b.order, lp.depth, lp.nice, lp.mode, lp.ht);
+        GZPB_COUNTED_LAUNCH(k_match, b.nunits * b.spu, kMatchThreads, match_smem, st, g, b.next4, b.prev3, b.mtab, b.mtab2, b.clen, b.order, lp.depth, lp.nice, lp.mode, lp.ht);
         DBG_SYNC("k_match");
         if (b.timer) b.timer->stop(st);
     }
     if (b.timer) b.timer->start(KT_EMIT, st);
     if (lp.mode == 2)
-        GZPB_LAUNCH(k_emit<true>, b.nunits, kEmitThreads, 0, st, g, b.unit_flags, b.mtab, b.mtab2, b.crc, fold_check ? b.sum_part : (const uint32_t *)nullptr, b.check_kind,
+        GZPB_COUNTED_LAUNCH(k_emit<true>, b.nunits, kEmitThreads, 0, st, g, b.unit_flags, b.mtab, b.mtab2, b.crc, fold_check ? b.sum_part : (const uint32_t *)nullptr, b.check_kind,
                     b.tokens, b.out, b.out_len, b.status, lp.mode, lp.depth, lp.nice, b.level, b.format);
     else
-        GZPB_LAUNCH(k_emit<false>, b.nunits, kEmitThreads, 0, st, g, b.unit_flags, b.mtab, b.mtab2, b.crc, fold_check ? b.sum_part : (const uint32_t *)nullptr, b.check_kind,
+        GZPB_COUNTED_LAUNCH(k_emit<false>, b.nunits, kEmitThreads, 0, st, g, b.unit_flags, b.mtab, b.mtab2, b.crc, fold_check ? b.sum_part : (const uint32_t *)nullptr, b.check_kind,
                     b.tokens, b.out, b.out_len, b.status, lp.mode, lp.depth, lp.nice, b.level, b.format);
     DBG_SYNC("k_emit");
     if (b.timer) b.timer->stop(st);
@@ -1805,6 +1856,7 @@ cudaError_t launch_deflate_pipeline(const DeflateBatch &b, cudaStream_t st)
 
 // scan + gather are launched separately so that the caller can order them
 // after the previous batch's scan (stream offsets chain from batch to batch).
+#undef GZPB_COUNTED_LAUNCH
 cudaError_t launch_pack(const DeflateBatch &b, cudaStream_t st)
 {
     if (b.nunits == 0) return cudaSuccess;

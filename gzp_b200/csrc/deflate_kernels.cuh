@@ -61,6 +61,7 @@ struct DeflateBatch {
     uint64_t *end_mirror;     // optional second copy of offsets[nunits] (mapped pinned host memory: the next batch of a multi-device stream reads its base there)
     int32_t *overflow;        // set to 1 by k_scan when the batch would exceed packed_cap
     KernelTimer *timer;       // optional
+    uint64_t *launch_counter; // optional: += the kernels launch_deflate_pipeline launches (gzpb_launch_count)
     uint32_t in_stride, m_stride, tok_stride, out_stride;   // per-unit strides (bytes / entries / tokens / bytes)
     uint32_t spu, seg;        // sub-units per unit and new positions per sub-unit (gzpb_common.cuh: Geo)
     int check_kind;           // -1 none, 0 CRC-32, 1 Adler-32 (written to `crc`)

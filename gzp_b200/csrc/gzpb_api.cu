@@ -410,6 +410,7 @@ static void fill_batch(gzpb_ctx *c, Lane &L, DeflateBatch &b, size_t n)
     b.out = L.d_out; b.out_len = L.d_out_len; b.status = L.d_status; b.offsets = L.d_offsets;
     b.packed = nullptr; b.packed_cap = 0; b.packed_on_host = 0; b.base_ptr = nullptr; b.end_mirror = nullptr; b.overflow = L.d_overflow;
     b.timer = c->profiling ? &c->timer : nullptr;
+    b.launch_counter = &c->launches;
 }
 
 static bool is_pinned(const void *p)
@@ -453,7 +454,7 @@ extern "C" int gzpb_encode_device_ex(gzpb_ctx *c, const void *d_in, const uint32
             if (d_dict) b.unit_dict = d_dict + done;
             b.status = d_status + done; b.offsets = d_offsets + done; b.base_ptr = d_offsets + done;
             CK(launch_deflate_pipeline(b, st));
-            c->launches += 6 + (c->check_kind >= 0 ? 1 : 0);   // [k_check,] k_split, k_link, k_match, k_emit, k_scan, k_gather
+            c->launches += 2;   // k_scan, k_gather (the pipeline's kernels count themselves: DeflateBatch::launch_counter)
         }
         b.packed = (uint8_t *)d_packed; b.packed_cap = ~0ull;
         CK(launch_pack(b, st));
@@ -542,7 +543,6 @@ static int lane_launch(gzpb_ctx *c, Lane &L, const UnitRef *units, size_t n, boo
     DeflateBatch b;
     fill_batch(c, L, b, n);
     CK(launch_deflate_pipeline(b, L.st));
-    c->launches += 5;   // k_check, k_split, k_link, k_match, k_emit
     L.nunits = n; L.busy = true;
     return GZPB_OK;
 }
