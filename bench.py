@@ -42,7 +42,7 @@ CONFIGS = {
     # blocks: per step and GPU; inflight: blocks per device batch
     "bgzf": dict(fmt=BGZF, level=6, block=65280, inflight=4736, blocks=47360, data="corpus", metric="bgzf_l6_compress_input_throughput",
                  workload="ParCompress<Bgzf> level 6, 65280-B blocks, shakespeare.txt repeated (BASELINE configs[1]: windows of the 54.65 GB stream)"),
-    "mgzip": dict(fmt=MGZIP, level=6, block=131072, inflight=1628, blocks=16280, data="corpus", metric="mgzip_l6_compress_input_throughput",
+    "mgzip": dict(fmt=MGZIP, level=6, block=131072, inflight=3256, blocks=16280, data="corpus", metric="mgzip_l6_compress_input_throughput",
                   workload="ParCompress<Mgzip> level 6, 131072-B blocks, shakespeare.txt repeated (BASELINE configs[2])"),
     "snap": dict(fmt=SNAP, level=0, block=131072, inflight=2048, blocks=8192, data="low", metric="snap_compress_input_throughput",
                  workload="ParCompress<Snap>, 131072-B blocks, low-entropy synthetic binary (BASELINE configs[3]; SURVEY 8d generator, 256 MiB period)"),

@@ -120,32 +120,12 @@ __device__ __forceinline__ uint32_t ldg32u(const uint32_t *__restrict__ words, u
 // 32 KiB window), prev3[p] likewise for the 15-bit hash of 3 bytes.
 // A fully parallel pass (k_split) partitions the positions of a sub-unit stably by bucket range into position-ordered
 // lists (16 ranges of the hash4 space, 4 of the hash3 space); each list is linked by its own single-warp job (k_link)
-// that needs only an 8-16 KiB bucket table, so 14 jobs share an SM.  (The first design, one CTA per unit with the whole
-// 192 KiB of bucket tables in shared memory, kept two latency-bound warps per SM busy: 6.7 ms vs 4.7 ms per batch.)
+// that needs only a 12-16 KiB bucket table, so 13 (hash3) / 17 (hash4) jobs share an SM.  (The first design, one CTA per
+// unit with the whole 192 KiB of bucket tables in shared memory, kept two latency-bound warps per SM busy: 6.7 ms per
+// batch of 3256 units; lists + MATCH.ANY grouping 4.7 ms; grouping through the bucket table + ballots, below, 3.9 ms.)
 // =============================================================================
 constexpr int kSplitThreads = 1024;
-#ifndef GZPB_LISTS
-#define GZPB_LISTS 0
-#endif
-#if GZPB_LISTS == 0
 constexpr int kBits4 = 12, kBits3 = 13;  // buckets per link job: hash4 8 KiB table + 4 KiB counts, hash3 16 KiB table
-#elif GZPB_LISTS == 2
-constexpr int kBits4 = 12, kBits3 = 12;  // 16 + 8 lists: hash4 8 KiB table + 4 KiB counts, hash3 8 KiB table — every job fits 12 KiB (one launch, 17 jobs per SM)
-#else
-constexpr int kBits4 = 11, kBits3 = 12;  // buckets per link job: hash4 4 KiB table + 2 KiB counts, hash3 8 KiB table (28 jobs per SM)
-#endif
-#ifndef GZPB_LINK_MATCHANY
-#define GZPB_LINK_MATCHANY 0
-#endif
-#ifndef GZPB_MATCH_PIPE
-#define GZPB_MATCH_PIPE 1
-#endif
-#ifndef GZPB_FULL_TILES
-#define GZPB_FULL_TILES 0
-#endif
-#ifndef GZPB_PLAIN_BALLOT
-#define GZPB_PLAIN_BALLOT 0
-#endif
 constexpr int kQ4Bits = 16 - kBits4, kQ3Bits = 15 - kBits3;
 constexpr int kL4 = 1 << kQ4Bits, kL3 = 1 << kQ3Bits;   // lists: equal ranges of the hash4 / hash3 bucket space
 constexpr int kSplitLists = kL4 + kL3;
@@ -157,7 +137,7 @@ template <int BITS, bool kAllActive = false>
 __device__ __forceinline__ uint32_t same_list_mask(uint32_t id, bool act)
 {
     uint32_t m = kAllActive ? 0xFFFFFFFFu : __ballot_sync(0xFFFFFFFFu, act);
-#if !defined(GZPB_EMU) && !GZPB_PLAIN_BALLOT
+#ifndef GZPB_EMU
     // four instructions per bit (bit test with predicate, VOTE, two predicated LOP3); the C++ form below compiles to seven
 #pragma unroll
     for (int b = 0; b < BITS; b++)
@@ -214,8 +194,8 @@ k_split(const __grid_constant__ Geo g, uint32_t *__restrict__ lists, uint32_t *_
     for (uint32_t i = lane; i < (uint32_t)kSplitLists; i += 32) s_w[warp][i] = 0;
     __syncwarp();
     // pass 1: every warp counts the list members of its contiguous range of tiles
-    // (tiles in front of the last one are full: their code carries no activity predicate — GZPB_FULL_TILES)
-    const uint32_t tfull = GZPB_FULL_TILES ? min(t1, ninsert / 32) : t0;
+    // (tiles in front of the last one are full: their code carries no activity predicate)
+    const uint32_t tfull = min(t1, ninsert / 32);
     auto count_tile = [&](uint32_t t, auto full) {
         constexpr bool kFull = decltype(full)::value;
         const uint32_t p = t * 32 + lane;
@@ -327,15 +307,9 @@ k_split(const __grid_constant__ Geo g, uint32_t *__restrict__ lists, uint32_t *_
     }
 }
 
-#ifndef GZPB_LINK_SPLIT
-#define GZPB_LINK_SPLIT 1
-#endif
-#ifndef GZPB_LINK_PIPE
-#define GZPB_LINK_PIPE 0
-#endif
 // kMulti: units of several sub-units (the loop over them and the head sweep exist only there)
-// kWhich: 0 = one launch for all lists; 1 = the hash4 lists only (12 KiB table: 17 jobs per SM instead of 13), 2 = the hash3 lists only
-template <bool kMulti, int kWhich>
+// kHash4: the hash4 lists (12 KiB of bucket state: 17 jobs per SM) or the hash3 lists (16 KiB: 13 per SM) — two launches
+template <bool kMulti, bool kHash4>
 __global__ void __launch_bounds__(32)
 k_link(const __grid_constant__ Geo g, const uint32_t *__restrict__ lists, const uint32_t *__restrict__ list_start,
        uint16_t *__restrict__ next4, uint16_t *__restrict__ prev3, uint8_t *__restrict__ clen_g)
@@ -344,22 +318,15 @@ k_link(const __grid_constant__ Geo g, const uint32_t *__restrict__ lists, const 
     // hash4 job: u16 head[4096] + u8 cnt[4096] (occurrences so far per bucket = chain-length estimate);
     // hash3 job: u16 head[8192].  Heads hold unit positions mod 65536; a link is valid below 32768, so at every
     // sub-unit boundary the heads that fell out of the window are parked on a sentinel 32768 positions back.
-    constexpr int kSlots4 = (1 << kBits4) + (1 << kBits4) / 2, kSlots3 = 1 << kBits3;             // u16 slots of bucket state per job type
-    constexpr int kStateSlots = kWhich == 1 ? kSlots4 : kWhich == 2 ? kSlots3 : (kSlots4 > kSlots3 ? kSlots4 : kSlots3);
-#if GZPB_LINK_PIPE
-    // + one byte per bucket for the group tags of the NEXT tile (see the tile loop)
-    __shared__ __align__(16) uint16_t head[kStateSlots + (kWhich == 1 ? (1 << kBits4) : (1 << kBits3)) / 2];
-    uint8_t *tag = (uint8_t *)(head + kStateSlots);
-#else
+    constexpr int kStateSlots = kHash4 ? (1 << kBits4) + (1 << kBits4) / 2 : (1 << kBits3);      // u16 slots of bucket state
     __shared__ __align__(16) uint16_t head[kStateSlots];
-#endif
     uint8_t *cnt = (uint8_t *)(head + (1 << kBits4));
-    constexpr uint32_t kJobs = kWhich == 0 ? kSplitLists : kWhich == 1 ? kL4 : kL3;
-    const uint32_t u = blockIdx.x / kJobs, job = blockIdx.x % kJobs + (kWhich == 2 ? kL4 : 0);
+    constexpr uint32_t kJobs = kHash4 ? kL4 : kL3;
+    const uint32_t u = blockIdx.x / kJobs, job = blockIdx.x % kJobs + (kHash4 ? 0 : kL4);
     const uint32_t un = g.unit_len[u], udict = g.unit_dict[u];
     if (un <= udict) return;
     const uint32_t lane = threadIdx.x, lt = lanemask_lt();
-    const bool is4 = kWhich == 0 ? job < kL4 : kWhich == 1;
+    constexpr bool is4 = kHash4;
     const uint32_t nb16 = is4 ? (2u << kBits4) / 16 : (2u << kBits3) / 16;     // uint4 words of the head table
     uint16_t *out = (is4 ? next4 : prev3) + (size_t)u * g.m_stride;
     uint8_t *clen = clen_g + (size_t)u * g.m_stride;
@@ -401,11 +368,6 @@ k_link(const __grid_constant__ Geo g, const uint32_t *__restrict__ lists, const 
         uint32_t en[G];
 #pragma unroll
         for (int k = 0; k < G; k++) { uint32_t i = beg + 32 * k + lane; en[k] = i < end ? __ldg(arr + i) : 0; }
-#if GZPB_LINK_PIPE
-        const uint32_t bmask = is4 ? ((1u << kBits4) - 1) : ((1u << kBits3) - 1);
-        if (beg + lane < end) tag[en[0] & bmask] = (uint8_t)lane;     // group tags of the first tile
-        __syncwarp();
-#endif
         for (uint32_t base0 = beg; base0 < end; base0 += 32 * G) {
             uint32_t e[G];
 #pragma unroll
@@ -413,35 +375,13 @@ k_link(const __grid_constant__ Geo g, const uint32_t *__restrict__ lists, const 
 #pragma unroll
             for (int k = 0; k < G; k++) { uint32_t i = base0 + 32 * (G + k) + lane; en[k] = i < end ? __ldg(arr + i) : 0; }
             // one tile of 32 entries; kFull: every lane has an entry (all tiles but a list's last), no activity predicates
-            auto tile = [&](const uint32_t ek, const uint32_t ek_next, const uint32_t i, auto full) {
+            auto tile = [&](const uint32_t ek, const uint32_t i, auto full) {
                 constexpr bool kFull = decltype(full)::value;
                 const bool act = kFull || i < end;
-                (void)ek_next;
                 const uint32_t b = ek & (is4 ? ((1u << kBits4) - 1) : ((1u << kBits3) - 1)), p = lo + (ek >> 16);   // unit position
                 // Entries of one tile that share a bucket are ordered by lane (= position order).  Every lane needs its
                 // group (the lanes with the same bucket): the predecessor is the nearest lower member, or the bucket head
                 // for the group's first member; the group's last member becomes the new head.
-#if GZPB_LINK_MATCHANY
-                // One MATCH.ANY per tile.  ncu (profiles/r2w): the ADU pipe that executes it is 88 % busy — about 60
-                // cycles per MATCH.ANY per SM — and bounds this kernel whatever the occupancy.
-                uint32_t hv = 0, c0 = 0;
-                const uint32_t grp = __match_any_sync(0xFFFFFFFFu, act ? b : (0x10000u + lane));
-                if (act) { hv = head[b]; if (is4) c0 = cnt[b]; }
-#elif GZPB_LINK_PIPE
-                // A tag byte per bucket names the groups: every member of a tile stored its LANE id in its bucket's tag
-                // one tile ago; whichever store survived, all members read the same 5-bit id back, and five ballots turn
-                // equal ids into the group mask (ALU work instead of the ADU pipe).  The ballots are also the point where
-                // every lane has read this tile's tags, so the next tile's tags are stored right behind them and travel
-                // with this tile's head update: one shared-memory round trip and one __syncwarp per tile.
-                uint32_t hv = 0, c0 = 0, rep = 0;
-                if (act) { rep = tag[b]; hv = head[b]; if (is4) c0 = cnt[b]; }
-                const uint32_t grp = same_list_mask<5, kFull>(rep, act);
-                __syncwarp();       // (memory order: every lane's loads above before the stores below)
-                {
-                    const uint32_t nxt = ek_next;
-                    if (i + 32 < end) tag[nxt & bmask] = (uint8_t)lane;
-                }
-#else
                 // The bucket table itself names the groups: every lane reads its bucket's state, then writes its LANE id
                 // there; whichever member's store survives, all members read the same 5-bit id back, and five ballots
                 // turn equal ids into the group mask (ALU work instead of the ADU pipe).
@@ -451,7 +391,6 @@ k_link(const __grid_constant__ Geo g, const uint32_t *__restrict__ lists, const 
                 if (act) head[b] = (uint16_t)lane;
                 __syncwarp();
                 const uint32_t grp = same_list_mask<5, kFull>(act ? (uint32_t)head[b] : 0u, act);   // (the ballots order these reads before the stores below)
-#endif
                 const uint32_t lower = grp & lt;
                 const uint32_t pl = __shfl_sync(0xFFFFFFFFu, p, lower ? 31 - __clz(lower) : lane);
                 uint32_t dist = 0, occ = 0;
@@ -460,9 +399,6 @@ k_link(const __grid_constant__ Geo g, const uint32_t *__restrict__ lists, const 
                     else dist = (!kMulti || ksub == 0) ? (hv == kNone16 ? 0u : p - hv) : ((p - hv) & 0xFFFFu);
                     if (is4) occ = c0 + (uint32_t)__popc(lower);
                 }
-#if GZPB_LINK_MATCHANY
-                __syncwarp();   // every lane has read its bucket before a group's last member overwrites it
-#endif
                 if (act) {
                     if ((grp >> lane) == 1u) {
                         head[b] = (uint16_t)p;
@@ -474,14 +410,14 @@ k_link(const __grid_constant__ Geo g, const uint32_t *__restrict__ lists, const 
                 }
                 __syncwarp();
             };
-            if (GZPB_FULL_TILES && base0 + 32 * G <= end) {
+            if (base0 + 32 * G <= end) {
 #pragma unroll
-                for (int k = 0; k < G; k++) tile(e[k], (k + 1 < G) ? e[(k + 1) % G] : en[0], base0 + 32 * k + lane, std::true_type{});
+                for (int k = 0; k < G; k++) tile(e[k], base0 + 32 * k + lane, std::true_type{});
             } else {
 #pragma unroll
                 for (int k = 0; k < G; k++) {
                     if (base0 + 32 * k >= end) break;
-                    tile(e[k], (k + 1 < G) ? e[(k + 1) % G] : en[0], base0 + 32 * k + lane, std::false_type{});
+                    tile(e[k], base0 + 32 * k + lane, std::false_type{});
                 }
             }
         }
@@ -599,38 +535,24 @@ k_match(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, cons
 
     // ---- phase 2: the searches, 32 positions of equal chain length per warp ----
     const uint32_t npos = sb.ne - sb.nb;
-#if GZPB_MATCH_PIPE
     // The two global loads of a position — its slot in the sorted order and its hash3 link, a scattered 2-byte load that
     // misses L1 — are issued one position ahead (ncu, profiles/r2w: 22 % of k_match's warp time was long-scoreboard stall):
     // the next position's order entry at the top of this position's walk, its prev3 link right after the walk.
     uint32_t p_cur = tid < npos ? order[tid] : 0u;
     uint32_t d3_cur = (tid < npos && !ht) ? p3[p_cur] : 1u;
-#endif
     for (uint32_t i = tid; i < npos; i += kMatchThreads) {
-#if GZPB_MATCH_PIPE
         const uint32_t p = p_cur;
         const uint32_t d3 = d3_cur;            // level 1 (ht_matchfinder) has no hash3 table: the parser must see "bucket usable, no 3-byte match"
         const bool have_next = i + kMatchThreads < npos;
         const uint32_t p_next = have_next ? order[i + kMatchThreads] : 0u;
-#define GZPB_MATCH_NEXT() do { p_cur = p_next; d3_cur = (have_next && !ht) ? p3[p_next] : 1u; } while (0)
-#else
-        const uint32_t p = order[i];
-#define GZPB_MATCH_NEXT() do { } while (0)
-#endif
         const uint32_t maxlen = min((uint32_t)kMaxMatch, n - p);
-        if (maxlen < 5) { M[p] = 0; if (M2) M2[p] = 0; GZPB_MATCH_NEXT(); continue; }
+        if (maxlen < 5) { M[p] = 0; if (M2) M2[p] = 0; p_cur = p_next; d3_cur = (have_next && !ht) ? p3[p_next] : 1u; continue; }
         const uint32_t nicep = min((uint32_t)nice, maxlen);
         // bytes 0..3 (the quick reject) and 4..11 (the inline extension) of this position: four words, three funnel shifts
         const uint32_t pw = p >> 2, psh = (p & 3) * 8;
         const uint32_t pa1 = s_in[pw + 1], pa2 = s_in[pw + 2];
         const uint32_t seq4 = __funnelshift_r(s_in[pw], pa1, psh);
         const uint32_t w1 = __funnelshift_r(pa1, pa2, psh), w2 = __funnelshift_r(pa2, s_in[pw + 3], psh);
-#if !GZPB_MATCH_PIPE
-        // level 1 (ht_matchfinder) has no hash3 table: the parser must see "bucket usable, no 3-byte match"
-        uint32_t d3 = ht ? 1u : p3[p];
-        uint32_t off3 = 0;
-        if (!ht && d3 && d3 <= 8192u && ((ld32u(s_in, p - d3) ^ seq4) & 0xFFFFFFu) == 0) off3 = d3;
-#endif
 
         uint32_t best = 3, boff = 0, lenB = 0, offB = 0, lenC = 0, offC = 0;
         bool haveB = !lazy, haveC = (lazy != 2);
@@ -676,11 +598,9 @@ k_match(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, cons
                 snap = (!haveC && depthC > visited) ? depthC : (!haveB && depthB > visited) ? depthB : (uint32_t)depth;
             }
         }
-        GZPB_MATCH_NEXT();
-#if GZPB_MATCH_PIPE
+        p_cur = p_next; d3_cur = (have_next && !ht) ? p3[p_next] : 1u;      // (the next position's hash3 link leaves now)
         uint32_t off3 = 0;
         if (!ht && d3 && d3 <= 8192u && ((ld32u(s_in, p - d3) ^ seq4) & 0xFFFFFFu) == 0) off3 = d3;
-#endif
         uint32_t lenA = best > 3 ? best : 0;
         if (!haveB) { lenB = lenA; offB = boff; }
         if (M2) { if (!haveC) { lenC = lenA; offC = boff; } M2[p] = (lenC ? lenC - 3 : 0) | (offC << 8); }
@@ -690,8 +610,8 @@ k_match(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, cons
 }
 
 // =============================================================================
-// k_emit: parse + Huffman + bit packing + container.  1 CTA (one warp) per unit, 22 CTAs per SM.  The warp runs the
-// reference's parser as a windowed parse over match-table tiles streamed into a 4-slot shared-memory ring by TMA bulk
+// k_emit: parse + Huffman + bit packing + container.  1 CTA (one warp) per unit, 32 CTAs per SM.  The warp runs the
+// reference's parser as a windowed parse over match-table tiles streamed into a 3-slot shared-memory ring by TMA bulk
 // copies (every lane evaluates the parser's two states at its position, the warp follows the path through the window
 // and stops exactly at state-changing events: min_len re-calculation, block-split checks, sequence-store limit); at
 // each DEFLATE block boundary it builds the Huffman codes (libdeflate's sort / in-place tree / length limiting /
@@ -700,24 +620,8 @@ k_match(const __grid_constant__ Geo g, const uint16_t *__restrict__ next4g, cons
 // =============================================================================
 constexpr int kEmitThreads = 32;
 constexpr int kTile = 128;                 // positions per streamed tile
-#ifndef GZPB_EMIT_RING
-#define GZPB_EMIT_RING 3
-#endif
-#ifndef GZPB_EMIT_DIET
-#define GZPB_EMIT_DIET 1
-#endif
-#ifndef GZPB_EMIT_WALK2
-#define GZPB_EMIT_WALK2 0
-#endif
-#ifndef GZPB_EMIT_MINCTAS
-#define GZPB_EMIT_MINCTAS 32
-#endif
-#ifdef GZPB_EMIT_MINCTAS
-#define GZPB_EMIT_BOUNDS __launch_bounds__(kEmitThreads, GZPB_EMIT_MINCTAS)
-#else
-#define GZPB_EMIT_BOUNDS __launch_bounds__(kEmitThreads)
-#endif
-constexpr int kRing = GZPB_EMIT_RING;      // tiles resident in the shared-memory ring
+constexpr int kRing = 3;                   // tiles resident in the shared-memory ring
+constexpr int kEmitUnitsPerSM = 32;        // 7 KiB of shared memory and 64 registers per unit: the CTA limit of an SM
 constexpr int kTokPerThread = 8;
 constexpr int kChunkTok = kEmitThreads * kTokPerThread;
 constexpr int kStageWords = (kChunkTok * 48) / 32 + 8;
@@ -735,7 +639,6 @@ struct EmitShared {
     uint8_t plen[kNumPrecode];
     uint16_t pcw[kNumPrecode];
     uint32_t pfreq[kNumPrecode];
-#if GZPB_EMIT_DIET
     // Scratch that is only live while a DEFLATE block is being finished borrows memory that is idle then (32 instead of
     // 22 resident units per SM): the Huffman sort array and the bit-packing staging words live in the tile ring (the
     // parser drains it at the block end and issues its tiles again afterwards: a few tiles per ~50 KB block), the
@@ -745,16 +648,6 @@ struct EmitShared {
     __device__ __forceinline__ uint32_t *Ap() { return (uint32_t *)&mt[0][0]; }
     __device__ __forceinline__ uint32_t *stagep() { return (uint32_t *)&mt[0][0]; }
     __device__ __forceinline__ uint16_t *itemsp() { return (uint16_t *)fl; }
-#else
-    uint16_t items[kNumLitlen + kNumOffset];
-    union {                                  // never live at the same time
-        uint32_t A[kNumLitlen];              // Huffman sort / tree array
-        uint32_t stage[kStageWords];         // bit-packing staging words
-    };
-    __device__ __forceinline__ uint32_t *Ap() { return A; }
-    __device__ __forceinline__ uint32_t *stagep() { return stage; }
-    __device__ __forceinline__ uint16_t *itemsp() { return items; }
-#endif
     uint32_t scan[kEmitThreads / 32];
     uint32_t used[8];
     // control block written by thread 0
@@ -1025,7 +918,7 @@ __device__ __forceinline__ uint32_t fold_unit_sum(const Geo &g, uint32_t u, cons
 }
 
 template <bool kLazy2>     // levels 8-9: the parser looks two positions ahead (states HC / X below); compiled out otherwise
-__global__ void GZPB_EMIT_BOUNDS
+__global__ void __launch_bounds__(kEmitThreads, kEmitUnitsPerSM)
 k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
        const uint64_t *__restrict__ mtab, const uint32_t *__restrict__ mtab2, uint32_t *__restrict__ crc_io, const uint32_t *__restrict__ sum_part, int check_kind,
        uint32_t *__restrict__ tok_base,
@@ -1212,7 +1105,6 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
                     // (every lane walks the same path: the F and HB words of a position travel in one shuffle)
                     const uint32_t wlimit = min(32u, max_block_end - p);
                     uint32_t vis = 0, c = 0, st = in_h, myst;
-#if GZPB_EMIT_WALK2
                     if (!kLazy2) {
                         // ten instructions per hop: the state travels as the shift (0 / 16) that selects its transition word,
                         // the lane a hop lands on notes the state itself, one ballot afterwards gives the path
@@ -1227,7 +1119,6 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
                         vis = __ballot_sync(0xFFFFFFFFu, mine != 0xFFu);
                         myst = (mine >> 4) & 1u; st = sh >> 4;
                     } else
-#endif
                     {
                         const uint32_t w2 = wF | (wHB << 12);
                         uint32_t sm0 = 0, sm1 = 0;
@@ -1328,7 +1219,7 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
                     }
                 } while (p < max_block_end && !end_block);
                 // nothing stays in flight across the block end: the CTA must not exit under a pending copy (tiles a final
-                // long match jumped over), and with GZPB_EMIT_DIET the ring doubles as the block-finishing scratch
+                // long match jumped over), and the ring doubles as the block-finishing scratch
                 P.drain();
                 if (lane == 0) {
                     S.blk_end = p; S.ntok = ntok; S.is_final = (final_block && p == n) ? 1u : 0u;
@@ -1345,7 +1236,7 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
             PHASE(3);
             make_huffman_code<uint16_t>(S, S.fo, kNumOffset, kMaxOffsetCw, ol, S.ocw);
             PHASE(4);
-            {   // symbol costs (parallel) — before the precode items are written: those reuse the frequency array (GZPB_EMIT_DIET)
+            {   // symbol costs (parallel) — before the precode items are written: those reuse the frequency array
                 uint32_t dyn = 0, stat = 0;
                 for (uint32_t s = tid; s < kNumLitlen; s += kEmitThreads) {
                     uint32_t f = S.fl[s];
@@ -1532,9 +1423,7 @@ k_emit(const __grid_constant__ Geo g, const uint32_t *__restrict__ unit_flags,
             }
             PHASE(9);
             p = be;
-#if GZPB_EMIT_DIET
             P.restart(be);
-#endif
             if (be >= n) break;
         }
     }
@@ -1824,18 +1713,13 @@ cudaError_t launch_deflate_pipeline(const DeflateBatch &b, cudaStream_t st)
         GZPB_COUNTED_LAUNCH(k_split, b.nunits * b.spu, kSplitThreads, 0, st, g, b.lists, b.list_start, b.next4, b.prev3, lp.ht,
                     fold_check ? b.sum_part : (uint32_t *)nullptr, b.check_kind);
         DBG_SYNC("k_split");
-#if GZPB_LINK_SPLIT
         if (b.spu > 1) {
-            GZPB_COUNTED_LAUNCH((k_link<true, 2>), b.nunits * kL3, 32, 0, st, g, b.lists, b.list_start, b.next4, b.prev3, b.clen);
-            GZPB_COUNTED_LAUNCH((k_link<true, 1>), b.nunits * kL4, 32, 0, st, g, b.lists, b.list_start, b.next4, b.prev3, b.clen);
+            GZPB_COUNTED_LAUNCH((k_link<true, false>), b.nunits * kL3, 32, 0, st, g, b.lists, b.list_start, b.next4, b.prev3, b.clen);
+            GZPB_COUNTED_LAUNCH((k_link<true, true>), b.nunits * kL4, 32, 0, st, g, b.lists, b.list_start, b.next4, b.prev3, b.clen);
         } else {
-            GZPB_COUNTED_LAUNCH((k_link<false, 2>), b.nunits * kL3, 32, 0, st, g, b.lists, b.list_start, b.next4, b.prev3, b.clen);
-            GZPB_COUNTED_LAUNCH((k_link<false, 1>), b.nunits * kL4, 32, 0, st, g, b.lists, b.list_start, b.next4, b.prev3, b.clen);
+            GZPB_COUNTED_LAUNCH((k_link<false, false>), b.nunits * kL3, 32, 0, st, g, b.lists, b.list_start, b.next4, b.prev3, b.clen);
+            GZPB_COUNTED_LAUNCH((k_link<false, true>), b.nunits * kL4, 32, 0, st, g, b.lists, b.list_start, b.next4, b.prev3, b.clen);
         }
-#else
-        if (b.spu > 1) GZPB_COUNTED_LAUNCH((k_link<true, 0>), b.nunits * kSplitLists, 32, 0, st, g, b.lists, b.list_start, b.next4, b.prev3, b.clen);
-        else GZPB_COUNTED_LAUNCH((k_link<false, 0>), b.nunits * kSplitLists, 32, 0, st, g, b.lists, b.list_start, b.next4, b.prev3, b.clen);
-#endif
         DBG_SYNC("k_link");
         if (b.timer) { b.timer->stop(st); b.timer->start(KT_MATCH, st); }
         GZPB_COUNTED_LAUNCH(k_match, b.nunits * b.spu, kMatchThreads, match_smem, st, g, b.next4, b.prev3, b.mtab, b.mtab2, b.clen, b.order, lp.depth, lp.nice, lp.mode, lp.ht);
