@@ -134,7 +134,10 @@ int gzpb_encode_stream_multi(gzpb_ctx *const *ctxs, size_t nctx, const void *in,
  * The caller's bytes are copied once into pinned slabs; up to 3 device batches of `blocks_in_flight`
  * blocks per GPU stay in flight while the caller keeps writing (back-pressure = the bounded channels
  * of :111-112); `sink` is called once per finished batch, in order, from the calling thread.
- * buffer_size 0 = the format's default; blocks_in_flight 0 = 1184 (8 thread blocks per SM on 148 SMs). */
+ * buffer_size 0 = the format's default; blocks_in_flight 0 = 1184 (8 units per SM on 148 SMs: a small memory
+ * footprint).  Throughput peaks when a batch fills the GPU with one wave of k_emit units — 148 SMs x 32 = 4736
+ * blocks (bench.py's BGZF batch; Mgzip 131072-byte blocks: 3256) — at about 2.1 MB of device scratch per 64 KiB
+ * block and batch in flight. */
 typedef int (*gzpb_sink_fn)(void *user, const void *data, size_t len);
 typedef struct gzpb_writer gzpb_writer;
 int gzpb_writer_create(gzpb_writer **w, int device, int format, int level, size_t buffer_size,

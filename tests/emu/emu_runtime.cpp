@@ -64,7 +64,8 @@ void *g_sched_sp = nullptr;
 const std::function<void()> *g_body = nullptr;
 unsigned g_nthreads = 0, g_live = 0, g_bar_count = 0, g_bar_gen = 0;
 struct TmaPending { void *bar; void *dst; const void *src; uint32_t bytes; };
-std::vector<TmaPending> g_tma_pending;    // bulk copies issued, not yet waited for (tma_late)
+std::vector<TmaPending> g_tma_pending;       // bulk copies issued, not yet waited for (tma_late)
+unsigned long long g_launches_queued = 0;    // kernels launched in this process (gzpb_emu_kernel_launches)
 bool g_progress = false;
 uint8_t *g_dyn = nullptr;
 size_t g_dyn_cap = 0;
@@ -347,9 +348,13 @@ void launch_async(void *stream, dim3 grid, dim3 block, size_t smem, std::functio
 {
     emu_stream *s = S((cudaStream_t)stream);
     if (s->device != g_cur_device && s != legacy_stream()) trap("kernel launch on a stream of another device (missing cudaSetDevice)");
+    g_launches_queued++;
     enqueue((cudaStream_t)stream, [=]() { launch(grid, block, smem, body); });
 }
 }  // namespace gzpb_emu
+
+// kernels launched so far in this process (tests compare it with the library's own gzpb_launch_count)
+extern "C" unsigned long long gzpb_emu_kernel_launches() { return gzpb_emu::g_launches_queued; }
 
 cudaError_t cudaMalloc(void **p, size_t n)
 {

@@ -7,6 +7,7 @@ arithmetic and control flow bit-for-bit in the container that has no GPU; the
 `-m gpu` tests remain the parity tests proper (real hardware, real memory model).
 Test infrastructure only: nothing in gzp_b200/ can load the emulated library.
 """
+import ctypes as C
 import gzip
 import random
 import zlib
@@ -702,3 +703,28 @@ def test_emu_native_writer_copy_threads(emu_backend):
     w.write(data[9_500_000:])
     w.finish()
     assert sink.getvalue() == oracle.compress_stream(oracle.BGZF, 0, 65280, [data[:9_500_000], data[9_500_000:]])
+
+
+def test_emu_launch_count_is_exact():
+    """gzpb_launch_count (bench.py's `gpu_launches`) equals the kernels the emulator actually saw launched: per batch
+    k_split, k_link (hash3 lists), k_link (hash4 lists), k_match, k_emit, k_scan, k_gather — and k_check instead of the
+    first four at level 0, k_snap for Snap, k_check_combine per batch for the one-stream checksums."""
+    L = emu.lib()
+    L.gzpb_emu_kernel_launches.restype = C.c_ulonglong
+    L.gzpb_launch_count.restype = C.c_uint64
+    L.gzpb_launch_count.argtypes = [C.c_void_p]
+    for fmt, level, bs, nbytes, per_batch in ((oracle.BGZF, 6, 0, 65280 * 5 + 7, 7), (oracle.BGZF, 0, 0, 65280 * 2, 4),
+                                              (oracle.GZIP, 6, 65536, 65536 * 3, None), (oracle.SNAP, 0, 0, 131072 * 2, 3)):
+        ctx = emu.EmuContext(fmt, level, max_block_bytes=bs, max_blocks_in_flight=4)
+        try:
+            before = L.gzpb_emu_kernel_launches()
+            ctx.encode_stream(TEXT[:nbytes], bs)
+            seen = L.gzpb_emu_kernel_launches() - before
+            claimed = L.gzpb_launch_count(ctx.h)
+        finally:
+            ctx.close()
+        assert claimed == seen and seen > 0, (fmt, level, claimed, seen)
+        if per_batch:
+            blk = bs or oracle.DEFAULT_BUFSIZE[fmt]
+            nbatches = -(-max(1, -(-nbytes // blk)) // 4)
+            assert seen == per_batch * nbatches, (fmt, level, seen, per_batch, nbatches)
