@@ -728,3 +728,27 @@ def test_emu_launch_count_is_exact():
             blk = bs or oracle.DEFAULT_BUFSIZE[fmt]
             nbatches = -(-max(1, -(-nbytes // blk)) // 4)
             assert seen == per_batch * nbatches, (fmt, level, seen, per_batch, nbatches)
+
+
+def test_emu_arbitrary_dictionary_lengths():
+    """gzpb_encode_batch with preset dictionaries of any length (the reference only ever passes 32 KiB, the ABI does not
+    say so): the unit starts anywhere inside a match-table tile, so k_emit's tile ring starts at any slot and phase."""
+    from gzp_b200 import _lib
+    L = emu.lib()
+    h = C.c_void_p()
+    assert L.gzpb_create(C.byref(h), 0, oracle.RAWDEFLATE, 6, 50000, 4) == 0
+    try:
+        cap = L.gzpb_encode_capacity(oracle.RAWDEFLATE, 50000) + 64
+        for dl in (1, 100, 127, 128, 129, 383, 384, 385, 5000, 32767, 32768):
+            d, data = TEXT[70000 - dl:70000], TEXT[70000:70000 + 45000]
+            ins, outs = (_lib.BlockIn * 1)(), (_lib.BlockOut * 1)()
+            src, dic, dst = C.create_string_buffer(data, len(data)), C.create_string_buffer(d, dl), C.create_string_buffer(cap)
+            ins[0].ptr = C.cast(src, C.c_void_p); ins[0].len = len(data)
+            ins[0].dict = C.cast(dic, C.c_void_p); ins[0].dict_len = dl; ins[0].is_last = 1
+            outs[0].dst = C.cast(dst, C.c_void_p); outs[0].cap = cap
+            assert L.gzpb_encode_batch(h, 1, ins, outs) == 0 and outs[0].status == 0
+            got = C.string_at(outs[0].dst, outs[0].out_len)
+            assert got == oracle.encode_block(oracle.RAWDEFLATE, 6, data, d, True), dl
+            assert zlib.decompressobj(-15, zdict=d).decompress(got) == data
+    finally:
+        L.gzpb_destroy(h)
