@@ -133,6 +133,28 @@ constexpr int kLsStride = 64;            // list_start entries per sub-unit: [0.
 
 // Lanes of the warp whose (active) list id equals this lane's: the id has only BITS bits, so BITS ballots do what a
 // MATCH.ANY does at a fraction of its latency (k_split ranks every position twice per pass).
+// Strong (relaxed, CTA scope) 16-bit shared-memory accesses: several lanes of a warp storing different values to one
+// address is k_link's grouping mechanism — conflicting STRONG writes are ordered by coherence and are no data race in the
+// PTX memory model (conflicting weak ones would be); same STS.U16 / LDS.U16 instructions either way.
+__device__ __forceinline__ void st_relaxed_shared_u16(uint16_t *p, uint32_t v)
+{
+#ifndef GZPB_EMU
+    asm volatile("st.relaxed.cta.shared.u16 [%0], %1;" ::"r"(smem_u32(p)), "h"((uint16_t)v) : "memory");
+#else
+    *p = (uint16_t)v;
+#endif
+}
+__device__ __forceinline__ uint32_t ld_relaxed_shared_u16(const uint16_t *p)
+{
+#ifndef GZPB_EMU
+    uint16_t v;
+    asm volatile("ld.relaxed.cta.shared.u16 %0, [%1];" : "=h"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+#else
+    return *p;
+#endif
+}
+
 template <int BITS, bool kAllActive = false>
 __device__ __forceinline__ uint32_t same_list_mask(uint32_t id, bool act)
 {
@@ -388,9 +410,9 @@ k_link(const __grid_constant__ Geo g, const uint32_t *__restrict__ lists, const 
                 uint32_t hv = 0, c0 = 0;
                 if (act) { hv = head[b]; if (is4) c0 = cnt[b]; }
                 __syncwarp();
-                if (act) head[b] = (uint16_t)lane;
+                if (act) st_relaxed_shared_u16(&head[b], lane);
                 __syncwarp();
-                const uint32_t grp = same_list_mask<5, kFull>(act ? (uint32_t)head[b] : 0u, act);   // (the ballots order these reads before the stores below)
+                const uint32_t grp = same_list_mask<5, kFull>(act ? ld_relaxed_shared_u16(&head[b]) : 0u, act);   // (the ballots order these reads before the stores below)
                 const uint32_t lower = grp & lt;
                 const uint32_t pl = __shfl_sync(0xFFFFFFFFu, p, lower ? 31 - __clz(lower) : lane);
                 uint32_t dist = 0, occ = 0;
