@@ -31,7 +31,8 @@ def build(force=False, verbose=False):
         cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-x", "cu", "-c", s, "-o", o]
         subprocess.check_call(cmd)
         objs.append(o)
-    subprocess.check_call([NVCC, "-shared", "-o", SO] + objs + ["-lpthread"])
+    # (the arch again at link time: nvcc otherwise adds an empty device-link stub for its default, pre-sm_75 architecture)
+    subprocess.check_call([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", SO] + objs + ["-lpthread"])
     return SO
 
 

@@ -151,3 +151,37 @@ def test_bgzf_gzi_index_and_virtual_offsets():
         assert member == data[u:u + len(member)] and len(member) > 0
     assert gzp_b200.bgzf_virtual_offset(0x1234, 77) == (0x1234 << 16) | 77
     assert gzp_b200.bgzf_index(oracle.compress_stream(oracle.BGZF, 6, 65280, [b""])) == struct.pack("<Q", 0)
+
+
+def test_shipped_sass_properties():
+    """What the shipped library's machine code must keep (cross-compiled here; `cuobjdump -sass`): sm_100a only; TMA bulk
+    copies + mbarrier waits in k_match / k_emit; k_link without MATCH.ANY (its ADU pipe bounded the kernel, profiles/README.md)
+    and with its ballots; k_emit at 64 registers and under 7.3 KiB of shared memory (32 resident units per SM); k_split at 32
+    registers (two CTAs of 1024 threads per SM)."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    so = _lib.SO_PATH
+    sass = subprocess.run([cuobjdump, "-sass", so], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass and not re.search(r"arch = sm_(?!100a)", sass)
+    funcs = {}
+    for part in sass.split("Function : ")[1:]:
+        name, body = part.split("\n", 1)
+        funcs[name.strip()] = body
+    def body_of(key):
+        hits = [b for n, b in funcs.items() if key in n]
+        assert hits, key
+        return "\n".join(hits)
+    assert "UBLKCP" in body_of("k_match") and "UBLKCP" in body_of("k_emit") and "SYNCS" in body_of("k_emit")
+    link = body_of("k_link")
+    assert "MATCH" not in link and link.count("VOTE") >= 5
+    res = subprocess.run([cuobjdump, "--dump-resource-usage", so], capture_output=True, text=True).stdout
+    usage = {}
+    for m in re.finditer(r"Function (\S+):\s*\n\s*REG:(\d+) STACK:\d+ SHARED:(\d+)", res):
+        usage[m.group(1)] = (int(m.group(2)), int(m.group(3)))
+    emit = [v for k, v in usage.items() if "k_emit" in k]
+    assert emit and all(r <= 64 and s <= 7296 for r, s in emit), emit
+    split = [v for k, v in usage.items() if "k_split" in k]
+    assert split and all(r <= 32 for r, _ in split), split
