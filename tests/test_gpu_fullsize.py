@@ -77,7 +77,7 @@ def test_c2_full_size_every_block_round_trips_on_device():
     total = P * 10000                                             # 54 653 940 000 B = "55 GiB" of BASELINE.json
     nblocks = (total + BLOCK - 1) // BLOCK
     assert nblocks == 837224
-    B = 3256                                                      # one full wave of k_emit CTAs
+    B = 3256                                                      # 22 k_emit units per SM (the shipped batch size is 4736 = 32 per SM)
     S = torch.frombuffer(bytearray(synth.text_stream(P)), dtype=torch.uint8).to(dev)
     S_rep = S.repeat((B * BLOCK + P) // P + 2)
     ctx = gzp_b200.Context(gzp_b200.BGZF, 6, device=0, max_block_bytes=BLOCK, max_blocks_in_flight=B)
